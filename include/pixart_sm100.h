@@ -1,0 +1,133 @@
+/* pixart_sm100.h -- C ABI of libpixart_sm100.so: hand-written sm_100a (B200) kernels for the
+ * PixArt-Sigma DiT denoiser hot path  PixArtMS.forward -> 28 x PixArtMSBlock.forward.
+ *
+ * The reference (PixArt-alpha/PixArt-sigma) is pure Python and has NO FFI / plugin interface; its GPU math is
+ * reached through library calls (torch nn.Linear / LayerNorm / GELU, xformers memory_efficient_attention).
+ * Each entry point below replaces one such call site (file:line relative to the reference root) and is what a
+ * ctypes binding inside diffusion/model/nets/PixArt_blocks.py would bind.
+ *
+ * Contract (all entry points):
+ *   - plain pointers and sizes only; every buffer (inputs, outputs, workspace) is owned by the caller and is
+ *     DEVICE memory; the library never allocates, frees or synchronises and launches only on `stream`
+ *     (a cudaStream_t passed as void*), so calls are CUDA-graph capturable;
+ *   - returns 0 on success, a negative PXA_ERR_* otherwise; pxa_last_error() gives the message (thread local);
+ *   - bf16 operands, fp32 accumulation / statistics / softmax; pointers must be 16-byte aligned;
+ *   - requires an sm_100 device (PXA_ERR_ARCH otherwise). There is no CPU or non-Blackwell path.
+ */
+#ifndef PIXART_SM100_H_
+#define PIXART_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PXA_OK 0
+#define PXA_ERR_ARG (-1)     /* bad shape / null pointer / unsupported option */
+#define PXA_ERR_ALIGN (-2)   /* pointer or stride not 16-byte aligned */
+#define PXA_ERR_ARCH (-3)    /* device is not sm_100 */
+#define PXA_ERR_CUDA (-4)    /* CUDA runtime / driver error (launch, tensor-map encode) */
+
+#define PXA_DTYPE_BF16 0
+#define PXA_DTYPE_F32 1
+
+int pxa_version(void);
+const char* pxa_last_error(void);
+/* Number of kernel launches issued by this library since load (all streams) -- bench.py's `gpu_launches`. */
+uint64_t pxa_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------- GEMM
+ * out = epilogue( A[M,K] . W[N,K]^T + bias[N] ),  A/W bf16 K-contiguous (W is the nn.Linear weight as stored).
+ * tcgen05 (UMMA 128xBNx16, fp32 accumulators in TMEM), TMA-fed smem ring, persistent, warp-specialised.
+ *
+ * Replaces: attn.qkv PixArt_blocks.py:130 | attn.proj + gate + residual PixArt_blocks.py:155, PixArtMS.py:75 |
+ *   cross_attn.q_linear / kv_linear / proj (+residual) PixArt_blocks.py:47,48,55, PixArtMS.py:76 |
+ *   mlp.fc1 + GELU(tanh) / fc2 + gate + residual (timm Mlp; PixArtMS.py:67,77) | y_embedder.y_proj PixArt_blocks.py:406.
+ */
+#define PXA_EPI_BIAS 0          /* out = acc + bias                                   */
+#define PXA_EPI_BIAS_GELU 1     /* out = gelu_tanh(acc + bias)                        */
+#define PXA_EPI_BIAS_RESIDUAL 2 /* out = residual + gate[row/rows_per_batch, n] * (acc + bias); gate NULL -> 1 */
+
+typedef struct PxaGemmArgs {
+  const void* a;        /* bf16 [M, K], row stride lda (elements)                                   */
+  const void* w;        /* bf16 [N, K], row stride ldw (elements)                                   */
+  const void* bias;     /* bf16 [N] or NULL                                                         */
+  void* out;            /* [M, N], row stride ldo (elements), dtype out_dtype                       */
+  void* out_aux_bf16;   /* optional second bf16 copy of out (row stride ldo) or NULL                */
+  const void* residual; /* EPI_BIAS_RESIDUAL: [M, N] row stride ldo, dtype out_dtype (may alias out)*/
+  const float* gate;    /* EPI_BIAS_RESIDUAL: fp32, element (b, n) at gate[b*gate_batch_stride + n], or NULL */
+  int64_t gate_batch_stride;
+  int32_t rows_per_batch; /* rows of A per sample (tokens N); row r belongs to sample r / rows_per_batch */
+  int32_t M, N, K;
+  int32_t lda, ldw, ldo;
+  int32_t epilogue;     /* PXA_EPI_*            */
+  int32_t out_dtype;    /* PXA_DTYPE_*          */
+  int32_t block_n;      /* 0 = auto (192 when it divides N, else 128); or 128 / 192 / 256           */
+  int32_t max_ctas;     /* 0 = one CTA per SM; >0 caps the persistent grid (tests)                  */
+} PxaGemmArgs;
+int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------ LayerNorm + modulate
+ * out[r,:] = LN(x[r,:]; eps, no affine) * (1 + scale[b,:]) + shift[b,:]  with b = r / rows_per_batch, bf16 out.
+ * Replaces norm1/norm2 + t2i_modulate (PixArtMS.py:58,64,75,77; PixArt_blocks.py:24-25) and the final-layer
+ * modulate (PixArt_blocks.py:218-219).  HBM-bound: reads x once, writes out once.
+ */
+typedef struct PxaLnModArgs {
+  const void* x;        /* [M, C] row stride ldx, dtype x_dtype */
+  void* out;            /* bf16 [M, C] contiguous                */
+  const float* shift;   /* fp32, (b, c) at shift[b*mod_batch_stride + c] */
+  const float* scale;   /* fp32, same addressing                  */
+  int64_t mod_batch_stride;
+  int32_t rows_per_batch;
+  int32_t M, C, ldx;
+  int32_t x_dtype;      /* PXA_DTYPE_* */
+  float eps;
+} PxaLnModArgs;
+int pxa_ln_modulate(const PxaLnModArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------- attention
+ * out[b, i, h, :] = softmax_j( q[b,i,h,:] . k[b,j,h,:] * scale ) v[b,j,h,:],  j < kv_len[b],  head_dim 72.
+ * Flash-style: TMA-staged K/V ring, S = QK^T and O += PV on tcgen05 with S/P/O in TMEM, fp32 online softmax.
+ * One kernel serves self-attention (PixArt_blocks.py:153, optionally KV-compressed: Nk < Nq) and the packed
+ * var-len T5 cross-attention (PixArt_blocks.py:50-53, BlockDiagonalMask semantics via kv_off/kv_len).
+ * Rows with kv_len == 0 produce zeros (xformers behaviour).
+ */
+typedef struct PxaAttnArgs {
+  const void* q;  /* bf16, element (b, i, h, d) at q[b*q_sb + i*q_sn + h*q_sh + d] */
+  const void* k;  /* bf16, element (row, h, d) at k[row*k_sn + h*k_sh + d], row = kv_off[b] + j (see below) */
+  const void* v;  /* bf16, same addressing as k with v_sn / v_sh */
+  void* out;      /* bf16, element (b, i, h, d) at out[(b*Nq + i)*ldo + h*72 + d] */
+  const int32_t* kv_len; /* device [B] or NULL (-> Nk for every sample)                                */
+  const int32_t* kv_off; /* device [B] first key row of sample b, or NULL (-> b*Nk: padded/unpacked)   */
+  int64_t q_sb, q_sn, q_sh;
+  int64_t k_sn, k_sh, v_sn, v_sh;
+  int64_t kv_rows;  /* total rows addressable through k / v (B*Nk unpacked, sum(kv_len) packed)          */
+  int32_t B, H, Nq, Nk; /* Nk = max keys per sample (loop bound) */
+  int32_t ldo;
+  float scale;      /* softmax scale, 72^-0.5 */
+} PxaAttnArgs;
+int pxa_flash_attn_d72_bf16(const PxaAttnArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------- KV token compression
+ * out[b, p, c] = LN_c( bias[c] + sum_{dy,dx<2} w[c,dy,dx] * in[b, (2py+dy)*W + 2px+dx, c] ) * gamma[c] + beta[c]
+ * Depthwise conv k=s=2 + LayerNorm(affine, eps 1e-5) on K and V (PixArt_blocks.py:84-89, 115-117), both tensors in
+ * one launch.  in: bf16 rows of `ld_in` elements (k and v are column slices of the qkv GEMM output).
+ */
+typedef struct PxaKvCompressArgs {
+  const void* k_in; const void* v_in; /* bf16, token row stride ld_in, batch stride H*W*ld_in */
+  void* k_out; void* v_out;           /* bf16 [B, (H/2)*(W/2), C] contiguous                   */
+  const void* conv_w;   /* bf16 [C, 1, 2, 2] */
+  const void* conv_b;   /* bf16 [C]          */
+  const void* ln_w;     /* bf16 [C]          */
+  const void* ln_b;     /* bf16 [C]          */
+  int32_t B, H, W, C, ld_in;
+  float eps;
+} PxaKvCompressArgs;
+int pxa_kv_compress_conv2_ln(const PxaKvCompressArgs* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIXART_SM100_H_ */

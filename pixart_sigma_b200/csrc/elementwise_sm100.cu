@@ -1,0 +1,194 @@
+// HBM-bound helper kernels of the block: LayerNorm + adaLN-single modulate, KV token compression.
+// One warp per token row, 128-bit loads/stores, fp32 statistics (two-pass over registers: mean, then variance).
+#include "host_common.cuh"
+#include "ptx.cuh"
+
+namespace pxa {
+
+PXA_DEVICE float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------- LN + modulate
+// C = 32 lanes * kVec * 4 elements (1152 -> kVec = 9). Each lane owns kVec float4 groups, group g at column
+// (g*32 + lane)*4, so every warp-level access is a contiguous 512 B (fp32) / 256 B (bf16) segment.
+template <int kVec, typename XT>
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const XT* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                          const float* __restrict__ shift,
+                                                          const float* __restrict__ scale, long long mod_bs,
+                                                          int rows_per_batch, int M, int ldx, float eps) {
+  constexpr int C = kVec * 128;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float4 v[kVec];
+  const XT* xr = x + (size_t)row * ldx;
+#pragma unroll
+  for (int g = 0; g < kVec; ++g) {
+    const int col = (g * 32 + lane) * 4;
+    if constexpr (sizeof(XT) == 4) {
+      v[g] = *reinterpret_cast<const float4*>(xr + col);
+    } else {
+      uint2 u = *reinterpret_cast<const uint2*>(xr + col);
+      v[g] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int g = 0; g < kVec; ++g) s += (v[g].x + v[g].y) + (v[g].z + v[g].w);
+  const float mean = warp_sum(s) * (1.0f / C);
+  float ss = 0.f;
+#pragma unroll
+  for (int g = 0; g < kVec; ++g) {
+    const float a = v[g].x - mean, b = v[g].y - mean, c = v[g].z - mean, d = v[g].w - mean;
+    ss += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / C) + eps);
+  const int bidx = row / rows_per_batch;
+  const float* sh = shift + (size_t)bidx * mod_bs;
+  const float* sc = scale + (size_t)bidx * mod_bs;
+  __nv_bfloat16* orow = out + (size_t)row * C;
+#pragma unroll
+  for (int g = 0; g < kVec; ++g) {
+    const int col = (g * 32 + lane) * 4;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(sc + col));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(sh + col));
+    const float y0 = fmaf((v[g].x - mean) * rstd, 1.0f + a.x, b.x);
+    const float y1 = fmaf((v[g].y - mean) * rstd, 1.0f + a.y, b.y);
+    const float y2 = fmaf((v[g].z - mean) * rstd, 1.0f + a.z, b.z);
+    const float y3 = fmaf((v[g].w - mean) * rstd, 1.0f + a.w, b.w);
+    *reinterpret_cast<uint2*>(orow + col) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- KV compress
+// Depthwise 2x2 stride-2 conv + bias, then LayerNorm(affine) over channels; one warp per OUTPUT token, blockIdx.y
+// selects K (0) or V (1). Reads 4 input rows (bf16), writes one row.
+template <int kVec>
+__global__ void __launch_bounds__(256) kv_compress_kernel(const __nv_bfloat16* __restrict__ k_in,
+                                                          const __nv_bfloat16* __restrict__ v_in,
+                                                          __nv_bfloat16* __restrict__ k_out,
+                                                          __nv_bfloat16* __restrict__ v_out,
+                                                          const __nv_bfloat16* __restrict__ conv_w,
+                                                          const __nv_bfloat16* __restrict__ conv_b,
+                                                          const __nv_bfloat16* __restrict__ ln_w,
+                                                          const __nv_bfloat16* __restrict__ ln_b, int B, int H, int W,
+                                                          int ld_in, float eps) {
+  constexpr int C = kVec * 128;
+  const int Ho = H >> 1, Wo = W >> 1;
+  const int orow = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (orow >= B * Ho * Wo) return;
+  const __nv_bfloat16* in = blockIdx.y == 0 ? k_in : v_in;
+  __nv_bfloat16* out = blockIdx.y == 0 ? k_out : v_out;
+  const int b = orow / (Ho * Wo);
+  const int p = orow % (Ho * Wo);
+  const int py = p / Wo, px = p % Wo;
+  const __nv_bfloat16* base = in + ((size_t)b * H * W + (size_t)(2 * py) * W + 2 * px) * ld_in;
+  float4 acc[kVec];
+#pragma unroll
+  for (int g = 0; g < kVec; ++g) {
+    const int col = (g * 32 + lane) * 4;
+    // conv weight [C,1,2,2]: channel c taps at conv_w[c*4 + dy*2 + dx]; 4 channels = 16 bf16 = 2 x 16 B
+    const uint4 w01 = __ldg(reinterpret_cast<const uint4*>(conv_w + col * 4));
+    const uint4 w23 = __ldg(reinterpret_cast<const uint4*>(conv_w + col * 4 + 8));
+    const uint2 bb = __ldg(reinterpret_cast<const uint2*>(conv_b + col));
+    float4 a = make_float4(bf16_lo(bb.x), bf16_hi(bb.x), bf16_lo(bb.y), bf16_hi(bb.y));
+    const float wt[4][4] = {{bf16_lo(w01.x), bf16_hi(w01.x), bf16_lo(w01.y), bf16_hi(w01.y)},
+                            {bf16_lo(w01.z), bf16_hi(w01.z), bf16_lo(w01.w), bf16_hi(w01.w)},
+                            {bf16_lo(w23.x), bf16_hi(w23.x), bf16_lo(w23.y), bf16_hi(w23.y)},
+                            {bf16_lo(w23.z), bf16_hi(w23.z), bf16_lo(w23.w), bf16_hi(w23.w)}};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {  // tap t = dy*2 + dx
+      const uint2 u = *reinterpret_cast<const uint2*>(base + ((size_t)(t >> 1) * W + (t & 1)) * ld_in + col);
+      a.x = fmaf(wt[0][t], bf16_lo(u.x), a.x);
+      a.y = fmaf(wt[1][t], bf16_hi(u.x), a.y);
+      a.z = fmaf(wt[2][t], bf16_lo(u.y), a.z);
+      a.w = fmaf(wt[3][t], bf16_hi(u.y), a.w);
+    }
+    acc[g] = a;   // kept in fp32 through the LayerNorm (more precise than the reference's bf16 conv output)
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int g = 0; g < kVec; ++g) s += (acc[g].x + acc[g].y) + (acc[g].z + acc[g].w);
+  const float mean = warp_sum(s) * (1.0f / C);
+  float ss = 0.f;
+#pragma unroll
+  for (int g = 0; g < kVec; ++g) {
+    const float a = acc[g].x - mean, b2 = acc[g].y - mean, c = acc[g].z - mean, d = acc[g].w - mean;
+    ss += (a * a + b2 * b2) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / C) + eps);
+  __nv_bfloat16* orowp = out + (size_t)orow * C;
+#pragma unroll
+  for (int g = 0; g < kVec; ++g) {
+    const int col = (g * 32 + lane) * 4;
+    const uint2 gw = __ldg(reinterpret_cast<const uint2*>(ln_w + col));
+    const uint2 gb = __ldg(reinterpret_cast<const uint2*>(ln_b + col));
+    const float y0 = fmaf((acc[g].x - mean) * rstd, bf16_lo(gw.x), bf16_lo(gb.x));
+    const float y1 = fmaf((acc[g].y - mean) * rstd, bf16_hi(gw.x), bf16_hi(gb.x));
+    const float y2 = fmaf((acc[g].z - mean) * rstd, bf16_lo(gw.y), bf16_lo(gb.y));
+    const float y3 = fmaf((acc[g].w - mean) * rstd, bf16_hi(gw.y), bf16_hi(gb.y));
+    *reinterpret_cast<uint2*>(orowp + col) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+  }
+}
+
+}  // namespace pxa
+
+extern "C" int pxa_ln_modulate(const PxaLnModArgs* args, void* stream) {
+  using namespace pxa;
+  if (!args) return fail(PXA_ERR_ARG, "null args");
+  const PxaLnModArgs& a = *args;
+  if (!a.x || !a.out || !a.shift || !a.scale) return fail(PXA_ERR_ARG, "null pointer");
+  if (a.C != 1152) return fail(PXA_ERR_ARG, "pxa_ln_modulate is specialised for C=1152 (got %d)", a.C);
+  if (a.M <= 0 || a.rows_per_batch <= 0) return fail(PXA_ERR_ARG, "bad M / rows_per_batch");
+  if ((a.ldx & 3) || (a.mod_batch_stride & 3)) return fail(PXA_ERR_ALIGN, "ldx / mod_batch_stride must be multiples of 4");
+  if ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(a.shift) |
+       reinterpret_cast<uintptr_t>(a.scale)) & 15)
+    return fail(PXA_ERR_ALIGN, "pointers must be 16-byte aligned");
+  PXA_REQUIRE_SM100();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = (a.M + 7) / 8;
+  if (a.x_dtype == PXA_DTYPE_F32)
+    ln_modulate_kernel<9, float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(a.x),
+                                                      reinterpret_cast<__nv_bfloat16*>(a.out), a.shift, a.scale,
+                                                      a.mod_batch_stride, a.rows_per_batch, a.M, a.ldx, a.eps);
+  else
+    ln_modulate_kernel<9, __nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(a.x),
+                                                              reinterpret_cast<__nv_bfloat16*>(a.out), a.shift,
+                                                              a.scale, a.mod_batch_stride, a.rows_per_batch, a.M,
+                                                              a.ldx, a.eps);
+  launch_counter()++;
+  PXA_CHECK_CUDA(cudaGetLastError());
+  return PXA_OK;
+}
+
+extern "C" int pxa_kv_compress_conv2_ln(const PxaKvCompressArgs* args, void* stream) {
+  using namespace pxa;
+  if (!args) return fail(PXA_ERR_ARG, "null args");
+  const PxaKvCompressArgs& a = *args;
+  if (!a.k_in || !a.v_in || !a.k_out || !a.v_out || !a.conv_w || !a.conv_b || !a.ln_w || !a.ln_b)
+    return fail(PXA_ERR_ARG, "null pointer");
+  if (a.C != 1152) return fail(PXA_ERR_ARG, "specialised for C=1152 (got %d)", a.C);
+  if (a.B <= 0 || a.H < 2 || a.W < 2) return fail(PXA_ERR_ARG, "bad B/H/W");
+  if (a.ld_in & 7) return fail(PXA_ERR_ALIGN, "ld_in must be a multiple of 8");
+  if ((reinterpret_cast<uintptr_t>(a.k_in) | reinterpret_cast<uintptr_t>(a.v_in) | reinterpret_cast<uintptr_t>(a.k_out) |
+       reinterpret_cast<uintptr_t>(a.v_out) | reinterpret_cast<uintptr_t>(a.conv_w) |
+       reinterpret_cast<uintptr_t>(a.conv_b) | reinterpret_cast<uintptr_t>(a.ln_w) | reinterpret_cast<uintptr_t>(a.ln_b)) & 15)
+    return fail(PXA_ERR_ALIGN, "pointers must be 16-byte aligned");
+  PXA_REQUIRE_SM100();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int rows = a.B * (a.H / 2) * (a.W / 2);
+  dim3 grid((rows + 7) / 8, 2);
+  kv_compress_kernel<9><<<grid, 256, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(a.k_in), reinterpret_cast<const __nv_bfloat16*>(a.v_in),
+      reinterpret_cast<__nv_bfloat16*>(a.k_out), reinterpret_cast<__nv_bfloat16*>(a.v_out),
+      reinterpret_cast<const __nv_bfloat16*>(a.conv_w), reinterpret_cast<const __nv_bfloat16*>(a.conv_b),
+      reinterpret_cast<const __nv_bfloat16*>(a.ln_w), reinterpret_cast<const __nv_bfloat16*>(a.ln_b), a.B, a.H, a.W,
+      a.ld_in, a.eps);
+  launch_counter()++;
+  PXA_CHECK_CUDA(cudaGetLastError());
+  return PXA_OK;
+}

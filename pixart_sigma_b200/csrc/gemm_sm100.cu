@@ -1,0 +1,387 @@
+// pxa_gemm_bf16: out = epilogue(A[M,K] . W[N,K]^T + bias) on tcgen05 tensor cores (sm_100a).
+//
+// Structure (one persistent CTA per SM, 256 threads):
+//   warp 0      TMA producer: A tile 128x64 and W tile BNx64 (bf16, 128B-swizzled) into a kStages-deep smem ring
+//   warp 1      MMA issuer: one thread issues tcgen05.mma 128xBNx16 (SS), fp32 accumulators in TMEM,
+//               double-buffered accumulator (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue: tcgen05.ld (row-per-thread) -> bias / GELU / gate*x + residual -> smem transpose (XOR
+//               swizzled, conflict-free) -> 128-bit coalesced global stores
+// Tiles are visited n-fastest so the CTAs running concurrently share the same few A row-blocks through L2 and the
+// whole weight matrix stays L2-resident.
+//
+// Algorithmic work: 2*M*N*K FLOP; bytes: M*K*2 (A) + N*K*2 (W) + M*N*out bytes (+ residual read).
+#include "host_common.cuh"
+#include "ptx.cuh"
+
+namespace pxa {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;            // 64 bf16 = 128 B = one swizzle atom row
+constexpr int kGemmThreads = 256;
+constexpr int kEpiWarp0 = 4;       // first epilogue warp
+constexpr int kNumEpiThreads = 128;
+
+struct GemmParams {
+  const __nv_bfloat16* bias;
+  void* out;
+  __nv_bfloat16* out_aux;
+  const void* residual;
+  const float* gate;
+  long long gate_batch_stride;
+  int rows_per_batch;
+  int M, N, K, ldo;
+  int num_m_tiles, num_n_tiles;
+};
+
+template <int BN> struct GemmCfg {
+  static constexpr int kStageA = kBM * kBK * 2;                 // 16 KB
+  static constexpr int kStageB = BN * kBK * 2;
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
+  static constexpr int kEpiSmem = 4 * 32 * 32 * 4;              // 4 epilogue warps x (32 rows x 128 B)
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmem = kStages * kStage + kEpiSmem + kBarBytes + 1024;  // +1024 alignment slack
+  static constexpr uint32_t kTmemCols = (2 * BN <= 256) ? 256 : 512;
+};
+
+// ------------------------------------------------------------------------------------------------- epilogues
+// Row-per-thread registers `v` hold acc for columns [col0, col0+32) of this thread's row.
+
+// bf16 output (EPI 0/1): math in row-per-thread layout, pack to bf16, transpose through smem (64 B per row).
+template <int EPI>
+PXA_DEVICE void epilogue_chunk_bf16(uint32_t (&v)[32], const GemmParams& p, uint8_t* stile, int lane, int row0, int col0) {
+  // bias: every lane needs the same 32 values -> 4 broadcast 16-byte loads
+  float b[32];
+  if (p.bias != nullptr) {
+    const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 u = make_uint4(0u, 0u, 0u, 0u);
+      if (col0 + 8 * i < p.N) u = __ldg(bp + i);
+      b[8 * i + 0] = bf16_lo(u.x); b[8 * i + 1] = bf16_hi(u.x);
+      b[8 * i + 2] = bf16_lo(u.y); b[8 * i + 3] = bf16_hi(u.y);
+      b[8 * i + 4] = bf16_lo(u.z); b[8 * i + 5] = bf16_hi(u.z);
+      b[8 * i + 6] = bf16_lo(u.w); b[8 * i + 7] = bf16_hi(u.w);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) b[i] = 0.f;
+  }
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float x0 = __uint_as_float(v[2 * i]) + b[2 * i];
+    float x1 = __uint_as_float(v[2 * i + 1]) + b[2 * i + 1];
+    if (EPI == PXA_EPI_BIAS_GELU) {
+      x0 = gelu_tanh(x0);
+      x1 = gelu_tanh(x1);
+    }
+    pk[i] = pack_bf16x2(x0, x1);
+  }
+  // smem tile: 32 rows x 64 B; 16-byte chunk c of row r lives at r*64 + ((c ^ ((r >> 1) & 3)) * 16)
+  {
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint4 u = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      *reinterpret_cast<uint4*>(stile + lane * 64 + ((c ^ sw) << 4)) = u;
+    }
+  }
+  __syncwarp();
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  const int c = lane & 3;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + (lane >> 2);
+    uint4 u = *reinterpret_cast<const uint4*>(stile + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+    const int grow = row0 + r;
+    const int gcol = col0 + c * 8;
+    if (grow < p.M && gcol < p.N) {
+      *reinterpret_cast<uint4*>(out + (size_t)grow * p.ldo + gcol) = u;
+    }
+  }
+  __syncwarp();
+}
+
+// Residual epilogue (EPI 2): fp32 acc transposed through smem (128 B per row), then in the coalesced layout
+// out = residual + gate * (acc + bias); optional bf16 aux copy.
+template <typename OutT>
+PXA_DEVICE void epilogue_chunk_residual(uint32_t (&v)[32], const GemmParams& p, uint8_t* stile, int lane, int row0,
+                                        int col0) {
+  // smem tile: 32 rows x 128 B; 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) * 16)
+  {
+    const int sw = lane & 7;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint4 u = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      *reinterpret_cast<uint4*>(stile + lane * 128 + ((c ^ sw) << 4)) = u;
+    }
+  }
+  __syncwarp();
+  const int c = lane & 7;
+  const int gcol = col0 + c * 4;
+  const bool col_ok = gcol < p.N;
+  float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+  if (p.bias != nullptr && col_ok) {
+    uint2 u = __ldg(reinterpret_cast<const uint2*>(p.bias + gcol));
+    b0 = bf16_lo(u.x); b1 = bf16_hi(u.x); b2 = bf16_lo(u.y); b3 = bf16_hi(u.y);
+  }
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + (lane >> 3);
+    const int grow = row0 + r;
+    float4 a = *reinterpret_cast<const float4*>(stile + r * 128 + ((c ^ (r & 7)) << 4));
+    if (grow < p.M && col_ok) {
+      float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (p.gate != nullptr) {
+        const int bidx = grow / p.rows_per_batch;
+        g = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)bidx * p.gate_batch_stride + gcol));
+      }
+      const size_t off = (size_t)grow * p.ldo + gcol;
+      float4 res;
+      if constexpr (sizeof(OutT) == 4) {
+        res = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + off);
+      } else {
+        uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + off);
+        res = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+      }
+      float4 o;
+      o.x = fmaf(g.x, a.x + b0, res.x);
+      o.y = fmaf(g.y, a.y + b1, res.y);
+      o.z = fmaf(g.z, a.z + b2, res.z);
+      o.w = fmaf(g.w, a.w + b3, res.w);
+      if constexpr (sizeof(OutT) == 4) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = o;
+      } else {
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) =
+            make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      }
+      if (p.out_aux != nullptr) {
+        *reinterpret_cast<uint2*>(p.out_aux + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------- kernel
+template <int BN, int EPI, typename OutT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi_smem = smem + kStages * Cfg::kStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Cfg::kEpiSmem);
+  uint64_t* full_bar = bars;                    // [kStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + kStages;         // [kStages]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * kStages;     // [2]        MMA -> epilogue
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]      epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = warp_idx_sync();
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_w);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], kNumEpiThreads);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_kb = (p.K + kBK - 1) / kBK;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.num_n_tiles) * kBM;
+        const int n0 = (tile % p.num_n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStage;
+          uint8_t* sb = sa + Cfg::kStageA;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStage);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBK, m0, kEvictNormal);
+          tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * kBK, n0, kEvictLast);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStage);
+          const uint64_t adesc = make_smem_desc(sa, 16, 1024, kLayoutSW128);
+          const uint64_t bdesc = make_smem_desc(sa + Cfg::kStageA, 16, 1024, kLayoutSW128);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
+            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ================================================================ epilogue
+    const int q = warp & 3;                         // TMEM sub-partition of this warp
+    uint8_t* stile = epi_smem + (warp - kEpiWarp0) * 4096;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.num_n_tiles) * kBM;
+      const int n0 = (tile % p.num_n_tiles) * BN;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_acc + cc * 32, v);   // includes tcgen05.wait::ld
+        if (cc == BN / 32 - 1) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[as]);
+        }
+        if (n0 + cc * 32 < p.N) {
+          if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL)
+            epilogue_chunk_residual<OutT>(v, p, stile, lane, m0 + q * 32, n0 + cc * 32);
+          else
+            epilogue_chunk_bf16<EPI>(v, p, stile, lane, m0 + q * 32, n0 + cc * 32);
+        }
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- host
+template <int BN, int EPI, typename OutT>
+static int launch_gemm(const PxaGemmArgs& a, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap ta, tw;
+  {
+    uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
+    uint64_t str[1] = {(uint64_t)a.lda * 2};
+    uint32_t box[2] = {kBK, kBM};
+    int rc = make_tmap_bf16(&ta, a.a, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.N};
+    uint64_t str[1] = {(uint64_t)a.ldw * 2};
+    uint32_t box[2] = {kBK, (uint32_t)BN};
+    int rc = make_tmap_bf16(&tw, a.w, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  GemmParams p;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(a.bias);
+  p.out = a.out;
+  p.out_aux = reinterpret_cast<__nv_bfloat16*>(a.out_aux_bf16);
+  p.residual = a.residual;
+  p.gate = a.gate;
+  p.gate_batch_stride = a.gate_batch_stride;
+  p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : a.M;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.ldo = a.ldo;
+  p.num_m_tiles = (a.M + kBM - 1) / kBM;
+  p.num_n_tiles = (a.N + BN - 1) / BN;
+  auto kern = gemm_bf16_kernel<BN, EPI, OutT>;
+  PXA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+  int grid = device_info().sms;
+  if (a.max_ctas > 0 && a.max_ctas < grid) grid = a.max_ctas;
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  if (tiles < grid) grid = tiles;
+  kern<<<grid, kGemmThreads, Cfg::kSmem, stream>>>(ta, tw, p);
+  launch_counter()++;
+  PXA_CHECK_CUDA(cudaGetLastError());
+  return PXA_OK;
+}
+
+template <int BN>
+static int dispatch_epi(const PxaGemmArgs& a, cudaStream_t s) {
+  switch (a.epilogue) {
+    case PXA_EPI_BIAS:
+      if (a.out_dtype != PXA_DTYPE_BF16) return fail(PXA_ERR_ARG, "EPI_BIAS writes bf16 only");
+      return launch_gemm<BN, PXA_EPI_BIAS, __nv_bfloat16>(a, s);
+    case PXA_EPI_BIAS_GELU:
+      if (a.out_dtype != PXA_DTYPE_BF16) return fail(PXA_ERR_ARG, "EPI_BIAS_GELU writes bf16 only");
+      return launch_gemm<BN, PXA_EPI_BIAS_GELU, __nv_bfloat16>(a, s);
+    case PXA_EPI_BIAS_RESIDUAL:
+      if (a.residual == nullptr) return fail(PXA_ERR_ARG, "EPI_BIAS_RESIDUAL needs residual");
+      if (a.out_dtype == PXA_DTYPE_F32) return launch_gemm<BN, PXA_EPI_BIAS_RESIDUAL, float>(a, s);
+      return launch_gemm<BN, PXA_EPI_BIAS_RESIDUAL, __nv_bfloat16>(a, s);
+    default:
+      return fail(PXA_ERR_ARG, "unknown epilogue %d", a.epilogue);
+  }
+}
+
+}  // namespace pxa
+
+extern "C" int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream) {
+  using namespace pxa;
+  if (!args) return fail(PXA_ERR_ARG, "null args");
+  const PxaGemmArgs& a = *args;
+  if (!a.a || !a.w || !a.out) return fail(PXA_ERR_ARG, "null a / w / out");
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0) return fail(PXA_ERR_ARG, "bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
+  if ((a.N & 7) || (a.K & 7) || (a.lda & 7) || (a.ldw & 7) || (a.ldo & 7))
+    return fail(PXA_ERR_ALIGN, "N, K, lda, ldw, ldo must be multiples of 8 (N=%d K=%d lda=%d ldw=%d ldo=%d)", a.N, a.K,
+                a.lda, a.ldw, a.ldo);
+  if ((reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(a.bias) |
+       reinterpret_cast<uintptr_t>(a.residual) | reinterpret_cast<uintptr_t>(a.gate) |
+       reinterpret_cast<uintptr_t>(a.out_aux_bf16)) & 15)
+    return fail(PXA_ERR_ALIGN, "out / bias / residual / gate / aux must be 16-byte aligned");
+  if (a.gate && (a.gate_batch_stride & 3)) return fail(PXA_ERR_ALIGN, "gate_batch_stride must be a multiple of 4");
+  PXA_REQUIRE_SM100();
+  int bn = a.block_n;
+  if (bn == 0) bn = (a.N % 192 == 0) ? 192 : ((a.N % 256 == 0) ? 256 : (a.N >= 192 ? 192 : 128));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 128: return dispatch_epi<128>(a, s);
+    case 192: return dispatch_epi<192>(a, s);
+    case 256: return dispatch_epi<256>(a, s);
+    default: return fail(PXA_ERR_ARG, "block_n must be 0, 128, 192 or 256 (got %d)", bn);
+  }
+}
