@@ -95,13 +95,13 @@ int pxa_ln_modulate(const PxaLnModArgs* args, void* stream);
  * Rows with kv_len == 0 produce zeros (xformers behaviour).
  */
 typedef struct PxaAttnArgs {
-  const void* q;  /* bf16, element (b, i, h, d) at q[b*q_sb + i*q_sn + h*q_sh + d] */
+  const void* q;  /* bf16, element (b, i, h, d) at q[(b*Nq + i)*q_sn + h*q_sh + d] */
   const void* k;  /* bf16, element (row, h, d) at k[row*k_sn + h*k_sh + d], row = kv_off[b] + j (see below) */
   const void* v;  /* bf16, same addressing as k with v_sn / v_sh */
   void* out;      /* bf16, element (b, i, h, d) at out[(b*Nq + i)*ldo + h*72 + d] */
   const int32_t* kv_len; /* device [B] or NULL (-> Nk for every sample)                                */
   const int32_t* kv_off; /* device [B] first key row of sample b, or NULL (-> b*Nk: padded/unpacked)   */
-  int64_t q_sb, q_sn, q_sh;
+  int64_t q_sn, q_sh;
   int64_t k_sn, k_sh, v_sn, v_sh;
   int64_t kv_rows;  /* total rows addressable through k / v (B*Nk unpacked, sum(kv_len) packed)          */
   int32_t B, H, Nq, Nk; /* Nk = max keys per sample (loop bound) */

@@ -1,0 +1,167 @@
+"""ctypes binding of libpixart_sm100.so (the C-ABI declared in include/pixart_sm100.h).
+
+PyTorch is used only for device memory and streams: every call passes raw `data_ptr()`s and the current
+CUDA stream.  There is no fallback: if the shared library is missing or the device is not sm_100 the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpixart_sm100.so")
+
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
+DTYPE_BF16, DTYPE_F32 = 0, 1
+
+
+class PxaError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p),
+                ("out_aux_bf16", C.c_void_p), ("residual", C.c_void_p), ("gate", C.c_void_p),
+                ("gate_batch_stride", C.c_int64), ("rows_per_batch", C.c_int32),
+                ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+                ("lda", C.c_int32), ("ldw", C.c_int32), ("ldo", C.c_int32),
+                ("epilogue", C.c_int32), ("out_dtype", C.c_int32), ("block_n", C.c_int32), ("max_ctas", C.c_int32)]
+
+
+class LnModArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("out", C.c_void_p), ("shift", C.c_void_p), ("scale", C.c_void_p),
+                ("mod_batch_stride", C.c_int64), ("rows_per_batch", C.c_int32),
+                ("M", C.c_int32), ("C", C.c_int32), ("ldx", C.c_int32), ("x_dtype", C.c_int32), ("eps", C.c_float)]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p),
+                ("kv_len", C.c_void_p), ("kv_off", C.c_void_p),
+                ("q_sn", C.c_int64), ("q_sh", C.c_int64),
+                ("k_sn", C.c_int64), ("k_sh", C.c_int64), ("v_sn", C.c_int64), ("v_sh", C.c_int64),
+                ("kv_rows", C.c_int64),
+                ("B", C.c_int32), ("H", C.c_int32), ("Nq", C.c_int32), ("Nk", C.c_int32),
+                ("ldo", C.c_int32), ("scale", C.c_float)]
+
+
+class KvCompressArgs(C.Structure):
+    _fields_ = [("k_in", C.c_void_p), ("v_in", C.c_void_p), ("k_out", C.c_void_p), ("v_out", C.c_void_p),
+                ("conv_w", C.c_void_p), ("conv_b", C.c_void_p), ("ln_w", C.c_void_p), ("ln_b", C.c_void_p),
+                ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("ld_in", C.c_int32),
+                ("eps", C.c_float)]
+
+
+EXPORTS = ("pxa_version", "pxa_last_error", "pxa_launch_count", "pxa_gemm_bf16", "pxa_ln_modulate",
+           "pxa_flash_attn_d72_bf16", "pxa_kv_compress_conv2_ln")
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the C-ABI library (built in-tree by `pixart_sigma_b200.build`). Raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PxaError(f"{LIB_PATH} not found: run `python -m pixart_sigma_b200.build` (there is no fallback path)")
+        lib = C.CDLL(LIB_PATH)
+        lib.pxa_version.restype = C.c_int
+        lib.pxa_last_error.restype = C.c_char_p
+        lib.pxa_launch_count.restype = C.c_uint64
+        for name, struct in (("pxa_gemm_bf16", GemmArgs), ("pxa_ln_modulate", LnModArgs),
+                             ("pxa_flash_attn_d72_bf16", AttnArgs), ("pxa_kv_compress_conv2_ln", KvCompressArgs)):
+            fn = getattr(lib, name)
+            fn.restype = C.c_int
+            fn.argtypes = [C.POINTER(struct), C.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def launch_count() -> int:
+    return int(load().pxa_launch_count())
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise PxaError(f"{what} failed ({rc}): {load().pxa_last_error().decode()}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _dt(dtype: torch.dtype) -> int:
+    if dtype == torch.bfloat16:
+        return DTYPE_BF16
+    if dtype == torch.float32:
+        return DTYPE_F32
+    raise PxaError(f"unsupported dtype {dtype}")
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, *,
+         epilogue: int = EPI_BIAS, residual: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
+         gate_batch_stride: int = 0, rows_per_batch: int = 0, out_aux: Optional[torch.Tensor] = None,
+         block_n: int = 0, max_ctas: int = 0) -> torch.Tensor:
+    """out = epilogue(a @ w.T + bias). a (M,K) bf16, w (N,K) bf16 (nn.Linear layout), both K-contiguous."""
+    assert a.is_cuda and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1 and out.dim() == 2 and out.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and out.shape == (M, N)
+    if bias is not None:
+        assert bias.dtype == torch.bfloat16 and bias.is_contiguous() and bias.numel() == N
+    if residual is not None:
+        assert residual.dtype == out.dtype and residual.shape == out.shape and residual.stride() == out.stride()
+    if gate is not None:
+        assert gate.dtype == torch.float32
+    if out_aux is not None:
+        assert out_aux.dtype == torch.bfloat16 and out_aux.shape == out.shape and out_aux.stride() == out.stride()
+    args = GemmArgs(a=_ptr(a), w=_ptr(w), bias=_ptr(bias), out=_ptr(out), out_aux_bf16=_ptr(out_aux),
+                    residual=_ptr(residual), gate=_ptr(gate), gate_batch_stride=gate_batch_stride,
+                    rows_per_batch=rows_per_batch or M, M=M, N=N, K=K, lda=a.stride(0), ldw=w.stride(0),
+                    ldo=out.stride(0), epilogue=epilogue, out_dtype=_dt(out.dtype), block_n=block_n, max_ctas=max_ctas)
+    _check(load().pxa_gemm_bf16(C.byref(args), _stream()), "pxa_gemm_bf16")
+    return out
+
+
+def ln_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, out: torch.Tensor, *,
+                mod_batch_stride: int, rows_per_batch: int, eps: float = 1e-6) -> torch.Tensor:
+    """out = LN(x) * (1 + scale[b]) + shift[b]; x (M,C) fp32/bf16, shift/scale fp32 views (row b at b*stride)."""
+    assert x.dim() == 2 and x.stride(1) == 1 and out.is_contiguous() and out.dtype == torch.bfloat16
+    assert shift.dtype == torch.float32 and scale.dtype == torch.float32
+    M, Cc = x.shape
+    args = LnModArgs(x=_ptr(x), out=_ptr(out), shift=_ptr(shift), scale=_ptr(scale), mod_batch_stride=mod_batch_stride,
+                     rows_per_batch=rows_per_batch, M=M, C=Cc, ldx=x.stride(0), x_dtype=_dt(x.dtype), eps=eps)
+    _check(load().pxa_ln_modulate(C.byref(args), _stream()), "pxa_ln_modulate")
+    return out
+
+
+def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, B: int, H: int, Nq: int,
+               Nk: int, kv_rows: int, kv_len: Optional[torch.Tensor] = None, kv_off: Optional[torch.Tensor] = None,
+               q_strides=None, k_strides=None, v_strides=None, scale: Optional[float] = None) -> torch.Tensor:
+    """Head-dim-72 attention. q/k/v are bf16 *views*; strides are (row, head) in elements, e.g. slices of the
+    (rows, 3, H, 72) qkv GEMM output. out is (B*Nq, H*72) bf16."""
+    assert q.dtype == k.dtype == v.dtype == out.dtype == torch.bfloat16
+    for tns in (kv_len, kv_off):
+        if tns is not None:
+            assert tns.dtype == torch.int32 and tns.is_cuda and tns.numel() == B
+    args = AttnArgs(q=_ptr(q), k=_ptr(k), v=_ptr(v), out=_ptr(out), kv_len=_ptr(kv_len), kv_off=_ptr(kv_off),
+                    q_sn=q_strides[0], q_sh=q_strides[1], k_sn=k_strides[0], k_sh=k_strides[1],
+                    v_sn=v_strides[0], v_sh=v_strides[1], kv_rows=kv_rows, B=B, H=H, Nq=Nq, Nk=Nk,
+                    ldo=out.stride(0), scale=scale if scale is not None else 72 ** -0.5)
+    _check(load().pxa_flash_attn_d72_bf16(C.byref(args), _stream()), "pxa_flash_attn_d72_bf16")
+    return out
+
+
+def kv_compress(k_in: torch.Tensor, v_in: torch.Tensor, k_out: torch.Tensor, v_out: torch.Tensor, conv_w, conv_b,
+                ln_w, ln_b, *, B: int, H: int, W: int, ld_in: int, eps: float = 1e-5) -> None:
+    args = KvCompressArgs(k_in=_ptr(k_in), v_in=_ptr(v_in), k_out=_ptr(k_out), v_out=_ptr(v_out), conv_w=_ptr(conv_w),
+                          conv_b=_ptr(conv_b), ln_w=_ptr(ln_w), ln_b=_ptr(ln_b), B=B, H=H, W=W, C=k_out.shape[-1],
+                          ld_in=ld_in, eps=eps)
+    _check(load().pxa_kv_compress_conv2_ln(C.byref(args), _stream()), "pxa_kv_compress_conv2_ln")

@@ -1,0 +1,203 @@
+"""GPU parity tests (-m gpu) of the individual sm_100a kernels, called through the C-ABI (ctypes), against the
+oracle's fp32 restatement of the same op evaluated on the same bf16-rounded inputs.
+
+Tolerances (normwise ||a-b||/||b||, stated per test): a bf16 result carries 2^-9 relative rounding per element
+(~1.7e-3 normwise), so bf16-output kernels are held to 4e-3 and the fp32-residual path to 2e-4.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import pixart_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from pixart_sigma_b200 import lib
+DEV = "cuda"
+
+
+def _randn(*shape, seed=0, scale=1.0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+# ------------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 192, 64, 0), (256, 384, 1152, 0), (1000, 1152, 1152, 0), (4096, 3456, 1152, 0), (300, 2304, 1152, 0),
+    (512, 1152, 4608, 0), (384, 256, 128, 256), (384, 256, 128, 128), (200, 200, 200, 192), (200, 200, 200, 128),
+    (130, 32, 1152, 128),
+])
+def test_gemm_bias_bf16(M, N, K, bn):
+    a, w, bias = _randn(M, K, seed=1), _randn(N, K, seed=2, scale=K ** -0.5), _randn(N, seed=3, scale=0.1)
+    out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV)
+    lib.gemm(a, w, bias, out, epilogue=lib.EPI_BIAS, block_n=bn)
+    want = F.linear(a.float(), w.float(), bias.float())
+    assert po.rel_err(out.float(), want) < 4e-3
+
+
+def test_gemm_many_tiles_per_cta_and_no_bias():
+    """3 CTAs walk 8x6 tiles: exercises smem-ring / TMEM double-buffer phase wrap-around."""
+    M, N, K = 1024, 1152, 1152
+    a, w = _randn(M, K, seed=4), _randn(N, K, seed=5, scale=K ** -0.5)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    lib.gemm(a, w, None, out, max_ctas=3)
+    assert po.rel_err(out.float(), a.float() @ w.float().T) < 4e-3
+
+
+def test_gemm_gelu_tanh():
+    M, N, K = 2048, 4608, 1152
+    a, w, bias = _randn(M, K, seed=6), _randn(N, K, seed=7, scale=K ** -0.5), _randn(N, seed=8, scale=0.1)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    lib.gemm(a, w, bias, out, epilogue=lib.EPI_BIAS_GELU)
+    want = F.gelu(F.linear(a.float(), w.float(), bias.float()), approximate="tanh")
+    assert po.rel_err(out.float(), want) < 4e-3
+
+
+@pytest.mark.parametrize("out_dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 4e-3)])
+@pytest.mark.parametrize("gated", [True, False])
+def test_gemm_gate_residual(out_dtype, tol, gated):
+    B, Ntok, N, K = 3, 400, 1152, 4608            # M = 1200: M tail + rows_per_batch not a tile multiple
+    M = B * Ntok
+    a, w, bias = _randn(M, K, seed=9), _randn(N, K, seed=10, scale=K ** -0.5), _randn(N, seed=11, scale=0.1)
+    res = _randn(M, N, seed=12, dtype=out_dtype)
+    mod = _randn(B, 6, N, seed=13, dtype=torch.float32)
+    gate = mod[:, 2] if gated else None
+    out = torch.empty(M, N, dtype=out_dtype, device=DEV)
+    aux = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    lib.gemm(a, w, bias, out, epilogue=lib.EPI_BIAS_RESIDUAL, residual=res, gate=gate, gate_batch_stride=6 * N,
+             rows_per_batch=Ntok, out_aux=aux)
+    y = F.linear(a.float(), w.float(), bias.float())
+    if gated:
+        y = y * mod[:, 2].repeat_interleave(Ntok, 0)
+    want = res.float() + y
+    assert po.rel_err(out.float(), want) < tol
+    assert po.rel_err(aux.float(), want) < 4e-3
+
+
+def test_gemm_residual_in_place():
+    M, N, K = 512, 1152, 1152
+    a, w = _randn(M, K, seed=14), _randn(N, K, seed=15, scale=K ** -0.5)
+    x = _randn(M, N, seed=16, dtype=torch.float32)
+    want = x + a.float() @ w.float().T
+    lib.gemm(a, w, None, x, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x)
+    assert po.rel_err(x, want) < 2e-4
+
+
+def test_gemm_rejects_bad_arguments():
+    a, w = _randn(128, 64), _randn(192, 64)
+    out = torch.empty(128, 192, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(lib.PxaError):
+        lib.gemm(a, w, None, out, block_n=100)
+    with pytest.raises(lib.PxaError):
+        lib.gemm(a, w, None, out, epilogue=lib.EPI_BIAS_RESIDUAL)     # residual missing
+
+
+# ------------------------------------------------------------------------------------------------- LN + modulate
+@pytest.mark.parametrize("xdtype", [torch.float32, torch.bfloat16])
+def test_ln_modulate(xdtype):
+    B, Ntok, Cc = 3, 333, 1152
+    x = (_randn(B * Ntok, Cc, seed=20, dtype=torch.float32) * 3 + 0.5).to(xdtype)
+    mod = _randn(B, 6, Cc, seed=21, dtype=torch.float32)
+    out = torch.empty(B * Ntok, Cc, dtype=torch.bfloat16, device=DEV)
+    lib.ln_modulate(x, mod[:, 3], mod[:, 4], out, mod_batch_stride=6 * Cc, rows_per_batch=Ntok)
+    want = po.ln_modulate(x.float().view(B, Ntok, Cc), mod[:, 3:4], mod[:, 4:5]).view(-1, Cc)
+    assert po.rel_err(out.float(), want) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------- attention
+def _attn_ref(q, k, v, lens):
+    """oracle sdpa per sample on fp32 copies; q (B,Nq,H,72), k/v (B,Nk,H,72); lens = valid keys per sample."""
+    outs = []
+    for b, L in enumerate(lens):
+        if L == 0:
+            outs.append(torch.zeros_like(q[b:b + 1]).float())
+        else:
+            outs.append(po.sdpa_heads(q[b:b + 1].float(), k[b:b + 1, :L].float(), v[b:b + 1, :L].float()))
+    return torch.cat(outs, 0)
+
+
+@pytest.mark.parametrize("B,H,Nq,Nk", [(1, 1, 128, 128), (1, 2, 256, 256), (2, 16, 1024, 1024), (1, 16, 1000, 1000),
+                                       (2, 4, 1024, 256), (1, 3, 300, 77)])
+def test_flash_attn_self_from_qkv_layout(B, H, Nq, Nk):
+    """q/k/v are strided views of a (B*N, 3, H, 72)-style buffer exactly as the QKV GEMM leaves them."""
+    q = _randn(B, Nq, H, 72, seed=30)
+    k = _randn(B, Nk, H, 72, seed=31)
+    v = _randn(B, Nk, H, 72, seed=32)
+    out = torch.full((B * Nq, H * 72), float("nan"), dtype=torch.bfloat16, device=DEV)
+    lib.flash_attn(q, k, v, out, B=B, H=H, Nq=Nq, Nk=Nk, kv_rows=B * Nk,
+                   q_strides=(H * 72, 72), k_strides=(H * 72, 72), v_strides=(H * 72, 72))
+    want = _attn_ref(q, k, v, [Nk] * B).reshape(B * Nq, H * 72)
+    assert torch.isfinite(out.float()).all()
+    assert po.rel_err(out.float(), want) < 6e-3
+
+
+def test_flash_attn_interleaved_qkv_buffer():
+    B, H, N = 2, 16, 512
+    qkv = _randn(B * N, 3, H, 72, seed=33)
+    out = torch.empty(B * N, H * 72, dtype=torch.bfloat16, device=DEV)
+    lib.flash_attn(qkv[:, 0], qkv[:, 1], qkv[:, 2], out, B=B, H=H, Nq=N, Nk=N, kv_rows=B * N,
+                   q_strides=(3 * H * 72, 72), k_strides=(3 * H * 72, 72), v_strides=(3 * H * 72, 72))
+    r = qkv.view(B, N, 3, H, 72)
+    want = _attn_ref(r[:, :, 0], r[:, :, 1], r[:, :, 2], [N] * B).reshape(B * N, H * 72)
+    assert po.rel_err(out.float(), want) < 6e-3
+
+
+def test_flash_attn_large_logits_trigger_rescale():
+    """Keys ordered so the running max keeps growing by > 2^8 between blocks: exercises the lazy O rescale."""
+    B, H, N = 1, 2, 512
+    q = _randn(B, N, H, 72, seed=34)
+    k = _randn(B, N, H, 72, seed=35)
+    ramp = torch.linspace(0.2, 6.0, N, device=DEV).view(1, N, 1, 1)
+    k = (k.float() * ramp).to(torch.bfloat16)
+    v = _randn(B, N, H, 72, seed=36)
+    out = torch.empty(B * N, H * 72, dtype=torch.bfloat16, device=DEV)
+    lib.flash_attn(q, k, v, out, B=B, H=H, Nq=N, Nk=N, kv_rows=B * N, q_strides=(H * 72, 72), k_strides=(H * 72, 72),
+                   v_strides=(H * 72, 72))
+    want = _attn_ref(q, k, v, [N]).reshape(B * N, H * 72)
+    assert po.rel_err(out.float(), want) < 8e-3
+
+
+def test_flash_attn_cross_packed_varlen():
+    """T5 cross-attention: packed keys (1, sum L, 2, H, 72) with BlockDiagonalMask semantics, incl. an empty sample."""
+    H, Nq = 16, 384
+    lens = [300, 8, 0, 129, 128, 77]
+    B = len(lens)
+    tot = sum(lens)
+    q = _randn(B, Nq, H, 72, seed=37)
+    kv = _randn(tot, 2, H, 72, seed=38)
+    off = torch.tensor([sum(lens[:i]) for i in range(B)], dtype=torch.int32, device=DEV)
+    ln = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    out = torch.full((B * Nq, H * 72), float("nan"), dtype=torch.bfloat16, device=DEV)
+    lib.flash_attn(q, kv[:, 0], kv[:, 1], out, B=B, H=H, Nq=Nq, Nk=300, kv_rows=tot, kv_len=ln, kv_off=off,
+                   q_strides=(H * 72, 72), k_strides=(2 * H * 72, 72), v_strides=(2 * H * 72, 72))
+    wants, o = [], 0
+    for b, L in enumerate(lens):
+        if L == 0:
+            wants.append(torch.zeros(1, Nq, H, 72, device=DEV))
+        else:
+            wants.append(po.sdpa_heads(q[b:b + 1].float(), kv[None, o:o + L, 0].float(), kv[None, o:o + L, 1].float()))
+        o += L
+    want = torch.cat(wants, 0).reshape(B * Nq, H * 72)
+    assert torch.isfinite(out.float()).all()
+    assert po.rel_err(out.float(), want) < 6e-3
+
+
+# ------------------------------------------------------------------------------------------------- KV compression
+def test_kv_compress_conv2_ln():
+    B, Hh, Ww, Cc = 2, 16, 24, 1152
+    qkv = _randn(B * Hh * Ww, 3 * Cc, seed=40)
+    sd = {"a.sr.weight": _randn(Cc, 1, 2, 2, seed=41, scale=0.3), "a.sr.bias": _randn(Cc, seed=42, scale=0.1),
+          "a.norm.weight": (1 + _randn(Cc, seed=43, scale=0.1).float()).to(torch.bfloat16),
+          "a.norm.bias": _randn(Cc, seed=44, scale=0.1)}
+    ko = torch.empty(B, Hh * Ww // 4, Cc, dtype=torch.bfloat16, device=DEV)
+    vo = torch.empty_like(ko)
+    lib.kv_compress(qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:], ko, vo, sd["a.sr.weight"], sd["a.sr.bias"], sd["a.norm.weight"],
+                    sd["a.norm.bias"], B=B, H=Hh, W=Ww, ld_in=3 * Cc)
+    sdf = {k_: v_.float() for k_, v_ in sd.items()}
+    for got, col in ((ko, 1), (vo, 2)):
+        src = qkv[:, col * Cc:(col + 1) * Cc].float().view(B, Hh * Ww, Cc)
+        want = po.kv_downsample(sdf, "a", src, Hh, Ww, 2, "conv")
+        assert po.rel_err(got.float(), want) < 4e-3

@@ -99,8 +99,13 @@ def test_oracle_matches_live_reference_ragged_mask():
         want = ref(x, t, y, mask=mask, data_info=None)
     got = po.forward(sd, cfg, x, t, y, mask=mask)
     assert po.rel_err(got, want) < TOL
-    # (1,1,L) masks and batch-broadcast masks (CFG: n masks for 2n samples, PixArtMS.py:197-198)
+    # batch-broadcast 2-D mask (CFG: n masks for 2n samples, PixArtMS.py:197-198) ...
     with torch.no_grad():
-        want2 = ref(x, t, y, mask=mask[:1].reshape(1, 1, 1, 300), data_info=None)
-    got2 = po.forward(sd, cfg, x, t, y, mask=mask[:1].reshape(1, 1, 1, 300))
+        want2 = ref(x, t, y, mask=mask[:1], data_info=None)
+    got2 = po.forward(sd, cfg, x, t, y, mask=mask[:1])
     assert po.rel_err(got2, want2) < TOL
+    # ... and the trainer's (B,1,1,L) layout (train.py:158-168; squeezed at PixArtMS.py:199)
+    with torch.no_grad():
+        want3 = ref(x, t, y, mask=mask.reshape(2, 1, 1, 300), data_info=None)
+    got3 = po.forward(sd, cfg, x, t, y, mask=mask.reshape(2, 1, 1, 300))
+    assert po.rel_err(got3, want3) < TOL
