@@ -1,0 +1,540 @@
+"""Host-side mirror of the reference denoiser API on top of the sm_100a kernels.
+
+`PixArtMS`, `PixArtMSBlock`, `PixArtMS_XL_2` keep the reference's constructor arguments, method signatures,
+attribute names and `state_dict()` key layout (diffusion/model/nets/PixArtMS.py:49-293, PixArt_blocks.py:28-158,
+205-221, 267-407; checkpoint keys tools/convert_pixart_to_diffusers.py:30-155), so `scripts/inference.py`,
+the DPM-Solver / IDDPM wrappers and `load_state_dict` of a reference `.pth` work unchanged.  What differs is
+*where the math runs*: every per-block op is a call into libpixart_sm100.so (see `lib.py`), the residual stream
+is carried in fp32 between blocks, and nothing in `forward` synchronises with the host (cached positional table,
+device-side key lengths instead of `.tolist()`).
+
+There is deliberately no CPU / eager fallback: `forward` requires CUDA bf16 parameters and raises otherwise.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import lib
+
+__all__ = ["PixArtMS", "PixArtMSBlock", "PixArtMS_XL_2", "MODELS", "build_model", "install_into_reference"]
+
+
+# ------------------------------------------------------------------------------------------------- registry
+class _Registry:
+    """Name -> constructor table with the two mmcv.Registry methods the reference uses (builder.py:5,11)."""
+
+    def __init__(self, name: str):
+        self.name, self.module_dict = name, {}
+
+    def register_module(self, name: Optional[str] = None, force: bool = False, module=None):
+        def _add(obj):
+            self.module_dict[name or obj.__name__] = obj
+            return obj
+        return _add(module) if module is not None else _add
+
+    def build(self, cfg, default_args: Optional[dict] = None):
+        kw = dict(cfg)
+        for k, v in (default_args or {}).items():
+            kw.setdefault(k, v)
+        ctor = kw.pop("type")
+        return (self.module_dict[ctor] if isinstance(ctor, str) else ctor)(**kw)
+
+
+MODELS = _Registry("models")
+
+
+def build_model(cfg, use_grad_checkpoint=False, use_fp32_attention=False, gc_step=1, **kwargs):
+    """Same call surface as diffusion/model/builder.py:8-14."""
+    if isinstance(cfg, str):
+        cfg = dict(type=cfg)
+    model = MODELS.build(cfg, default_args=kwargs)
+    if use_grad_checkpoint:
+        def mark(m):  # diffusion/model/utils.py:28-35
+            m.grad_checkpointing, m.fp32_attention, m.grad_checkpointing_step = True, use_fp32_attention, gc_step
+        model.apply(mark)
+    return model
+
+
+# ------------------------------------------------------------------------------------------------- leaf modules
+class _Mlp(nn.Module):
+    """fc1 -> GELU(tanh) -> fc2; parameter names of timm 0.6.12 `Mlp` (PixArtMS.py:67)."""
+
+    def __init__(self, in_features: int, hidden_features: int, out_features: Optional[int] = None):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = nn.GELU(approximate="tanh")
+        self.fc2 = nn.Linear(hidden_features, out_features or in_features)
+
+
+class PatchEmbed(nn.Module):
+    """Conv2d(k = s = patch) tokeniser (PixArtMS.py:22-46)."""
+
+    def __init__(self, patch_size=2, in_chans=4, embed_dim=1152, bias=True):
+        super().__init__()
+        self.patch_size = (patch_size, patch_size) if isinstance(patch_size, int) else tuple(patch_size)
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=self.patch_size, stride=self.patch_size, bias=bias)
+
+
+class TimestepEmbedder(nn.Module):
+    """Sinusoid(256) -> Linear -> SiLU -> Linear (PixArt_blocks.py:267-309). Tiny; evaluated in fp32 by torch."""
+
+    def __init__(self, hidden_size: int, frequency_embedding_size: int = 256):
+        super().__init__()
+        self.mlp = nn.Sequential(nn.Linear(frequency_embedding_size, hidden_size), nn.SiLU(),
+                                 nn.Linear(hidden_size, hidden_size))
+        self.frequency_embedding_size = frequency_embedding_size
+
+    @staticmethod
+    def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
+        half = dim // 2
+        freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
+        ang = t[:, None].float() * freqs[None]
+        return torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1)
+
+    def embed_fp32(self, t: torch.Tensor) -> torch.Tensor:
+        f = self.timestep_embedding(t, self.frequency_embedding_size)
+        h = F.silu(F.linear(f, self.mlp[0].weight.float(), self.mlp[0].bias.float()))
+        return F.linear(h, self.mlp[2].weight.float(), self.mlp[2].bias.float())
+
+    def forward(self, t):
+        return self.embed_fp32(t).to(self.mlp[0].weight.dtype)
+
+
+class SizeEmbedder(TimestepEmbedder):
+    """One embedding per scalar of `s`, concatenated (PixArt_blocks.py:312-344)."""
+
+    def __init__(self, hidden_size: int, frequency_embedding_size: int = 256):
+        super().__init__(hidden_size, frequency_embedding_size)
+        self.outdim = hidden_size
+
+    def embed_fp32(self, s: torch.Tensor, bs: int) -> torch.Tensor:  # type: ignore[override]
+        if s.ndim == 1:
+            s = s[:, None]
+        if s.shape[0] != bs:
+            s = s.repeat(bs // s.shape[0], 1)
+        b, d = s.shape
+        e = TimestepEmbedder.embed_fp32(self, s.reshape(-1))
+        return e.reshape(b, d * self.outdim)
+
+    def forward(self, s, bs):
+        return self.embed_fp32(s, bs).to(self.mlp[0].weight.dtype)
+
+
+class CaptionEmbedder(nn.Module):
+    """T5 feature projector 4096 -> C -> C with train-time caption dropout (PixArt_blocks.py:378-407)."""
+
+    def __init__(self, in_channels, hidden_size, uncond_prob, token_num=120):
+        super().__init__()
+        self.y_proj = _Mlp(in_channels, hidden_size, hidden_size)
+        self.register_buffer("y_embedding", torch.randn(token_num, in_channels) / in_channels ** 0.5)
+        self.uncond_prob = uncond_prob
+
+    def token_drop(self, caption, force_drop_ids=None):
+        if force_drop_ids is None:
+            drop = torch.rand(caption.shape[0], device=caption.device) < self.uncond_prob
+        else:
+            drop = force_drop_ids == 1
+        return torch.where(drop[:, None, None, None], self.y_embedding.to(caption.dtype), caption)
+
+
+class T2IFinalLayer(nn.Module):
+    """LN -> modulate(table + t) -> Linear C -> p*p*out (PixArt_blocks.py:205-221)."""
+
+    def __init__(self, hidden_size, patch_size, out_channels):
+        super().__init__()
+        self.norm_final = nn.LayerNorm(hidden_size, elementwise_affine=False, eps=1e-6)
+        self.linear = nn.Linear(hidden_size, patch_size * patch_size * out_channels)
+        self.scale_shift_table = nn.Parameter(torch.randn(2, hidden_size) / hidden_size ** 0.5)
+        self.out_channels = out_channels
+
+
+class MultiHeadCrossAttention(nn.Module):
+    """Parameter holder for q_linear / kv_linear / proj (PixArt_blocks.py:28-58)."""
+
+    def __init__(self, d_model, num_heads, attn_drop=0.0, proj_drop=0.0, **_):
+        super().__init__()
+        assert d_model % num_heads == 0, "d_model must be divisible by num_heads"
+        self.d_model, self.num_heads, self.head_dim = d_model, num_heads, d_model // num_heads
+        self.q_linear = nn.Linear(d_model, d_model)
+        self.kv_linear = nn.Linear(d_model, d_model * 2)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(d_model, d_model)
+        self.proj_drop = nn.Dropout(proj_drop)
+
+
+class AttentionKVCompress(nn.Module):
+    """Parameter holder for qkv / proj (+ sr conv, norm for KV compression; q_norm / k_norm) (PixArt_blocks.py:61-95)."""
+
+    def __init__(self, dim, num_heads=8, qkv_bias=True, sampling="conv", sr_ratio=1, qk_norm=False, **_):
+        super().__init__()
+        assert dim % num_heads == 0
+        self.num_heads, self.scale = num_heads, (dim // num_heads) ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(0.0)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(0.0)
+        self.sampling, self.sr_ratio = sampling, sr_ratio
+        if sr_ratio > 1 and sampling == "conv":
+            self.sr = nn.Conv2d(dim, dim, groups=dim, kernel_size=sr_ratio, stride=sr_ratio)
+            self.sr.weight.data.fill_(1 / sr_ratio ** 2)
+            self.sr.bias.data.zero_()
+            self.norm = nn.LayerNorm(dim)
+        if qk_norm:
+            self.q_norm, self.k_norm = nn.LayerNorm(dim), nn.LayerNorm(dim)
+        else:
+            self.q_norm, self.k_norm = nn.Identity(), nn.Identity()
+
+
+# ------------------------------------------------------------------------------------------------- workspace
+class _Workspace:
+    """Activation buffers reused by all 28 blocks of one forward (owned by the model, sized on first use)."""
+
+    def __init__(self):
+        self.key, self.buf = None, {}
+
+    def get(self, name: str, shape: Tuple[int, ...], dtype: torch.dtype, device) -> torch.Tensor:
+        t = self.buf.get(name)
+        if t is None or t.shape != tuple(shape) or t.dtype != dtype or t.device != device:
+            t = torch.empty(shape, dtype=dtype, device=device)
+            self.buf[name] = t
+        return t
+
+
+def _require_kernel_ready(p: torch.Tensor, what: str) -> None:
+    if not p.is_cuda:
+        raise RuntimeError(f"{what}: parameters are on {p.device}; pixart_sigma_b200 has no CPU path "
+                           "(move the model to a B200 with .cuda())")
+    if p.dtype != torch.bfloat16:
+        raise RuntimeError(f"{what}: parameters are {p.dtype}; the sm_100a kernels take bf16 weights "
+                           "(use model.to(torch.bfloat16))")
+
+
+# ------------------------------------------------------------------------------------------------- block
+class PixArtMSBlock(nn.Module):
+    """adaLN-single DiT block: modulated self-attention, T5 cross-attention, modulated MLP (PixArtMS.py:49-79)."""
+
+    def __init__(self, hidden_size, num_heads, mlp_ratio=4.0, drop_path=0.0, input_size=None, sampling=None,
+                 sr_ratio=1, qk_norm=False, **block_kwargs):
+        super().__init__()
+        self.hidden_size = hidden_size
+        self.norm1 = nn.LayerNorm(hidden_size, elementwise_affine=False, eps=1e-6)
+        self.attn = AttentionKVCompress(hidden_size, num_heads=num_heads, qkv_bias=True, sampling=sampling,
+                                        sr_ratio=sr_ratio, qk_norm=qk_norm, **block_kwargs)
+        self.cross_attn = MultiHeadCrossAttention(hidden_size, num_heads, **block_kwargs)
+        self.norm2 = nn.LayerNorm(hidden_size, elementwise_affine=False, eps=1e-6)
+        self.mlp = _Mlp(hidden_size, int(hidden_size * mlp_ratio))
+        self.drop_path_rate = float(drop_path)
+        self.drop_path = nn.Identity()
+        self.scale_shift_table = nn.Parameter(torch.randn(6, hidden_size) / hidden_size ** 0.5)
+        self._ws = _Workspace()
+
+    # -- the fused path ---------------------------------------------------------------------------------------
+    def run_kernels(self, x32: torch.Tensor, cond: torch.Tensor, kv_len: Optional[torch.Tensor],
+                    kv_off: Optional[torch.Tensor], max_keys: int, mod: torch.Tensor, B: int, N: int,
+                    HW: Tuple[int, int], ws: _Workspace) -> torch.Tensor:
+        """One block on the kernels, in place on the fp32 residual stream.
+
+        x32  (B*N, C) fp32 residual stream (updated in place and returned)
+        cond (rows, C) bf16 embedded caption tokens; sample b's keys are rows kv_off[b] .. +kv_len[b]
+             (kv_off None -> b*max_keys, kv_len None -> max_keys)
+        mod  (B, 6, C) fp32 = scale_shift_table + t0  (shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp)
+        """
+        C, H = self.hidden_size, self.attn.num_heads
+        M, dev = B * N, x32.device
+        a, ca, mlp = self.attn, self.cross_attn, self.mlp
+        _require_kernel_ready(a.qkv.weight, "PixArtMSBlock")
+        if self.training and self.drop_path_rate > 0:
+            raise NotImplementedError("stochastic depth (drop_path > 0) is not supported by the fused block")
+        if not isinstance(a.q_norm, nn.Identity):
+            raise NotImplementedError("qk_norm=True is not supported by the fused block yet")
+        bf = torch.bfloat16
+        xn = ws.get("xn", (M, C), bf, dev)
+        qkv = ws.get("qkv", (M, 3 * C), bf, dev)
+        ao = ws.get("attn_o", (M, C), bf, dev)
+        xb = ws.get("x_bf16", (M, C), bf, dev)
+        ms = mod.stride(0)
+
+        # (1) x += gate_msa * proj(attn(LN(x) * (1 + scale_msa) + shift_msa))                     PixArtMS.py:75
+        lib.ln_modulate(x32, mod[:, 0], mod[:, 1], xn, mod_batch_stride=ms, rows_per_batch=N)
+        lib.gemm(xn, a.qkv.weight, a.qkv.bias, qkv)
+        q3 = qkv.view(M, 3, H, C // H)
+        k_src, v_src, k_str, n_keys = q3[:, 1], q3[:, 2], (3 * C, C // H), N
+        if a.sr_ratio > 1:                                                                   # PixArt_blocks.py:137-139
+            k_src, v_src, n_keys = self._compress_kv(qkv, B, N, HW, ws)
+            k_str = (C, C // H)
+        lib.flash_attn(q3[:, 0], k_src, v_src, ao, B=B, H=H, Nq=N, Nk=n_keys, kv_rows=B * n_keys,
+                       q_strides=(3 * C, C // H), k_strides=k_str, v_strides=k_str, scale=a.scale)
+        lib.gemm(ao, a.proj.weight, a.proj.bias, x32, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x32, gate=mod[:, 2],
+                 gate_batch_stride=ms, rows_per_batch=N, out_aux=xb)
+
+        # (2) x += proj(cross_attn(x, cond))            (no norm, no gate)                       PixArtMS.py:76
+        qx = ws.get("q_cross", (M, C), bf, dev)
+        kv = ws.get("kv_cross", (cond.shape[0], 2 * C), bf, dev)
+        lib.gemm(xb, ca.q_linear.weight, ca.q_linear.bias, qx)
+        lib.gemm(cond, ca.kv_linear.weight, ca.kv_linear.bias, kv)
+        kv4 = kv.view(-1, 2, H, C // H)
+        lib.flash_attn(qx, kv4[:, 0], kv4[:, 1], ao, B=B, H=H, Nq=N, Nk=max_keys, kv_rows=cond.shape[0],
+                       kv_len=kv_len, kv_off=kv_off, q_strides=(C, C // H), k_strides=(2 * C, C // H),
+                       v_strides=(2 * C, C // H), scale=(C // H) ** -0.5)
+        lib.gemm(ao, ca.proj.weight, ca.proj.bias, x32, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x32)
+
+        # (3) x += gate_mlp * fc2(gelu_tanh(fc1(LN(x) * (1 + scale_mlp) + shift_mlp)))           PixArtMS.py:77
+        hid = ws.get("mlp_hidden", (M, mlp.fc1.out_features), bf, dev)
+        lib.ln_modulate(x32, mod[:, 3], mod[:, 4], xn, mod_batch_stride=ms, rows_per_batch=N)
+        lib.gemm(xn, mlp.fc1.weight, mlp.fc1.bias, hid, epilogue=lib.EPI_BIAS_GELU)
+        lib.gemm(hid, mlp.fc2.weight, mlp.fc2.bias, x32, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x32, gate=mod[:, 5],
+                 gate_batch_stride=ms, rows_per_batch=N)
+        return x32
+
+    def _compress_kv(self, qkv, B, N, HW, ws):
+        """K / V token compression (PixArt_blocks.py:97-121). 'conv' sr=2 runs the fused conv+LN kernel; the
+        parameter-free samplings are strided views materialised by torch (pure data movement)."""
+        a, C = self.attn, self.hidden_size
+        Hh, Ww = HW
+        sr, dev = a.sr_ratio, qkv.device
+        k_in, v_in = qkv[:, C:2 * C], qkv[:, 2 * C:]
+        if a.sampling == "conv":
+            if sr != 2:
+                raise NotImplementedError("conv KV compression kernel is specialised for scale_factor 2")
+            n_out = (Hh // 2) * (Ww // 2)
+            kc = ws.get("k_comp", (B, n_out, C), torch.bfloat16, dev)
+            vc = ws.get("v_comp", (B, n_out, C), torch.bfloat16, dev)
+            lib.kv_compress(k_in, v_in, kc, vc, a.sr.weight, a.sr.bias, a.norm.weight, a.norm.bias, B=B, H=Hh, W=Ww,
+                            ld_in=qkv.stride(0), eps=a.norm.eps)
+            return kc.view(-1, C), vc.view(-1, C), n_out
+        if a.sampling == "uniform_every":
+            pick = lambda t: t.reshape(B, N, C)[:, ::sr].contiguous()
+        elif a.sampling in ("uniform", "ave"):     # the reference's 'ave' is nearest-neighbour = the same strided pick
+            pick = lambda t: t.reshape(B, Hh, Ww, C)[:, ::sr, ::sr].contiguous()
+        else:
+            raise ValueError(a.sampling)
+        kc, vc = pick(k_in), pick(v_in)
+        n_out = kc.numel() // (B * C)
+        return kc.view(-1, C), vc.view(-1, C), n_out
+
+    # -- reference call signature -------------------------------------------------------------------------------
+    def forward(self, x, y, t, mask=None, HW=None, **kwargs):
+        """x (B,N,C), y (1, sum(y_lens), C) packed caption tokens, t (B, 6C), mask = list y_lens (PixArtMS.py:71,206)."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("PixArtMSBlock: the backward kernels are not implemented yet; run under "
+                                      "torch.no_grad() (inference)")
+        B, N, C = x.shape
+        if HW is None:
+            HW = (int(N ** 0.5),) * 2
+        cond = y.reshape(-1, C).to(torch.bfloat16).contiguous()
+        if mask is None:
+            lens = [cond.shape[0] // B] * B
+        else:
+            lens = [int(v) for v in mask]
+        kv_len = torch.tensor(lens, dtype=torch.int32, device=x.device)
+        kv_off = torch.tensor([sum(lens[:i]) for i in range(B)], dtype=torch.int32, device=x.device)
+        mod = (self.scale_shift_table.float()[None] + t.reshape(B, 6, C).float()).contiguous()
+        x32 = x.reshape(B * N, C).float().contiguous()
+        out = self.run_kernels(x32, cond, kv_len, kv_off, max(max(lens), 1), mod, B, N, tuple(HW), self._ws)
+        return out.view(B, N, C).to(x.dtype)
+
+
+# ------------------------------------------------------------------------------------------------- model
+_POS_CACHE: Dict[tuple, torch.Tensor] = {}
+
+
+def _pos_embed_fp32(C: int, h: int, w: int, pe_interpolation: float, base_size: int, device) -> torch.Tensor:
+    """(h*w, C) fp32 2-D sin/cos table, float64 math as the reference (PixArt.py:258-307), cached per geometry so the
+    per-forward host computation + H2D copy of PixArtMS.py:177-182 happens once."""
+    key = (C, h, w, float(pe_interpolation), int(base_size), str(device))
+    tab = _POS_CACHE.get(key)
+    if tab is None:
+        pos_h = np.arange(h, dtype=np.float32) / (h / base_size) / pe_interpolation
+        pos_w = np.arange(w, dtype=np.float32) / (w / base_size) / pe_interpolation
+        omega = 1.0 / 10000 ** (np.arange(C // 4, dtype=np.float64) / (C // 4))
+        aw = np.tile(pos_w[None, :], (h, 1)).reshape(-1)[:, None] * omega[None]     # w varies fastest
+        ah = np.repeat(pos_h, w)[:, None] * omega[None]
+        full = np.concatenate([np.sin(aw), np.cos(aw), np.sin(ah), np.cos(ah)], axis=1)
+        tab = torch.from_numpy(full).to(torch.float32).to(device)
+        _POS_CACHE[key] = tab
+    return tab
+
+
+@MODELS.register_module()
+class PixArtMS(nn.Module):
+    """Multi-scale PixArt-Sigma DiT (PixArtMS.py:85-285) running on the sm_100a kernels."""
+
+    def __init__(self, input_size=32, patch_size=2, in_channels=4, hidden_size=1152, depth=28, num_heads=16,
+                 mlp_ratio=4.0, class_dropout_prob=0.1, learn_sigma=True, pred_sigma=True, drop_path: float = 0.0,
+                 caption_channels=4096, pe_interpolation=1.0, config=None, model_max_length=120,
+                 micro_condition=False, qk_norm=False, kv_compress_config=None, **kwargs):
+        super().__init__()
+        self.pred_sigma = pred_sigma
+        self.in_channels = in_channels
+        self.out_channels = in_channels * 2 if pred_sigma else in_channels
+        self.patch_size, self.num_heads, self.depth = patch_size, num_heads, depth
+        self.pe_interpolation = pe_interpolation
+        self.base_size = input_size // patch_size
+        self.h = self.w = 0
+        self.hidden_size = hidden_size
+        # zero buffer kept only for checkpoint-key compatibility; the table is recomputed per geometry
+        self.register_buffer("pos_embed", torch.zeros(1, self.base_size ** 2, hidden_size))
+        self.x_embedder = PatchEmbed(patch_size, in_channels, hidden_size, bias=True)
+        self.t_embedder = TimestepEmbedder(hidden_size)
+        self.t_block = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size, 6 * hidden_size, bias=True))
+        self.y_embedder = CaptionEmbedder(caption_channels, hidden_size, class_dropout_prob, token_num=model_max_length)
+        self.micro_conditioning = micro_condition
+        if micro_condition:
+            self.csize_embedder = SizeEmbedder(hidden_size // 3)
+            self.ar_embedder = SizeEmbedder(hidden_size // 3)
+        self.kv_compress_config = kv_compress_config or {"sampling": None, "scale_factor": 1, "kv_compress_layer": []}
+        kvc = self.kv_compress_config
+        rates = [float(v) for v in torch.linspace(0, drop_path, depth)]
+        grid = (input_size // patch_size,) * 2
+        self.blocks = nn.ModuleList([
+            PixArtMSBlock(hidden_size, num_heads, mlp_ratio=mlp_ratio, drop_path=rates[i], input_size=grid,
+                          sampling=kvc["sampling"],
+                          sr_ratio=int(kvc["scale_factor"]) if i in kvc["kv_compress_layer"] else 1, qk_norm=qk_norm)
+            for i in range(depth)])
+        self.final_layer = T2IFinalLayer(hidden_size, patch_size, self.out_channels)
+        self.output_dtype: Optional[torch.dtype] = None    # None -> model dtype (reference behaviour)
+        self._ws = _Workspace()
+        self.initialize()
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return next(self.parameters()).dtype
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _condition(self, y: torch.Tensor, mask: Optional[torch.Tensor], B: int):
+        """Caption embedding + key bookkeeping, all on device (replaces PixArtMS.py:194-204).
+
+        Returns (cond (B*L, C) bf16, kv_len int32 (B,) or None, max_keys).  With a mask, each sample's selected
+        tokens are moved to the front of its L-row slot (stable order), which is what masked_select packing feeds the
+        block-diagonal attention -- softmax over a key *set* -- without the dynamic shape or the .tolist() sync."""
+        ye, C = self.y_embedder, self.hidden_size
+        L = y.shape[2]
+        if self.training and ye.uncond_prob > 0:
+            y = ye.token_drop(y)
+        rows = y.reshape(B * L, -1).to(torch.bfloat16).contiguous()
+        hid = self._ws.get("y_hidden", (B * L, C), torch.bfloat16, y.device)
+        cond = self._ws.get("y_cond", (B * L, C), torch.bfloat16, y.device)
+        lib.gemm(rows, ye.y_proj.fc1.weight, ye.y_proj.fc1.bias, hid, epilogue=lib.EPI_BIAS_GELU)
+        lib.gemm(hid, ye.y_proj.fc2.weight, ye.y_proj.fc2.bias, cond)
+        if mask is None:
+            return cond, None, L
+        if mask.shape[0] != B:
+            mask = mask.repeat(B // mask.shape[0], *([1] * (mask.dim() - 1)))
+        valid = mask.reshape(B, L) != 0
+        order = torch.argsort((~valid).to(torch.uint8), dim=1, stable=True)              # selected tokens first
+        cond = torch.gather(cond.view(B, L, C), 1, order[..., None].expand(B, L, C)).reshape(B * L, C)
+        return cond, valid.sum(dim=1).to(torch.int32), L
+
+    def forward(self, x, timestep, y, mask=None, data_info=None, **kwargs):
+        """x (B, 4, H, W) latents, timestep (B,), y (B, 1, L, 4096) T5 features, mask (n, L) | (B,1,1,L) | None
+        -> (B, 8, H, W)   (PixArtMS.py:165-211)."""
+        w0 = self.blocks[0].attn.qkv.weight
+        _require_kernel_ready(w0, "PixArtMS.forward")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("PixArtMS: backward kernels are not implemented yet; call under torch.no_grad()")
+        dt, dev, C, p = self.dtype, w0.device, self.hidden_size, self.patch_size
+        B = x.shape[0]
+        x = x.to(device=dev, dtype=dt)
+        timestep = timestep.to(device=dev, dtype=dt)        # the reference rounds t to the model dtype here (:174)
+        y = y.to(device=dev)
+        self.h, self.w = x.shape[-2] // p, x.shape[-1] // p
+        N = self.h * self.w
+
+        pe = self.x_embedder.proj
+        tok = F.conv2d(x.float(), pe.weight.float(), pe.bias.float(), stride=p).flatten(2).transpose(1, 2)
+        x32 = (tok + _pos_embed_fp32(C, self.h, self.w, self.pe_interpolation, self.base_size, dev)[None])
+        x32 = x32.reshape(B * N, C).contiguous()                                               # fp32 residual stream
+
+        t = self.t_embedder.embed_fp32(timestep)                                               # (B, C) fp32
+        if self.micro_conditioning:
+            csize = self.csize_embedder.embed_fp32(data_info["img_hw"].to(dev, dt), B)
+            ar = self.ar_embedder.embed_fp32(data_info["aspect_ratio"].to(dev, dt), B)
+            t = t + torch.cat([csize, ar], dim=1)
+        t0 = F.linear(F.silu(t), self.t_block[1].weight.float(), self.t_block[1].bias.float())  # (B, 6C) fp32
+        tables = torch.stack([blk.scale_shift_table for blk in self.blocks]).float()           # (depth, 6, C)
+        mod_all = (tables[:, None] + t0.view(1, B, 6, C)).contiguous()                          # (depth, B, 6, C)
+
+        cond, kv_len, max_keys = self._condition(y, mask, B)
+        for i, blk in enumerate(self.blocks):
+            blk.run_kernels(x32, cond, kv_len, None, max_keys, mod_all[i], B, N, (self.h, self.w), self._ws)
+
+        fl = self.final_layer                                                                  # uses t, not t0 (:208)
+        fmod = (fl.scale_shift_table.float()[None] + t[:, None]).contiguous()                  # (B, 2, C): shift, scale
+        xn = self._ws.get("xn", (B * N, C), torch.bfloat16, dev)
+        lib.ln_modulate(x32, fmod[:, 0], fmod[:, 1], xn, mod_batch_stride=fmod.stride(0), rows_per_batch=N)
+        out = F.linear(xn.float(), fl.linear.weight.float(), fl.linear.bias.float()).view(B, N, -1)
+        return self.unpatchify(out).to(self.output_dtype or dt)
+
+    def forward_with_dpmsolver(self, x, timestep, y, data_info, **kwargs):
+        """DPM-Solver wants eps only: first half of the channels (PixArtMS.py:213-219)."""
+        return self.forward(x, timestep, y, data_info=data_info, **kwargs).chunk(2, dim=1)[0]
+
+    def forward_with_cfg(self, x, timestep, y, cfg_scale, data_info, mask=None, **kwargs):
+        """Classifier-free guidance over a [cond | uncond] batch; like the reference, only the first THREE channels
+        are mixed (PixArtMS.py:221-234)."""
+        half = x[: len(x) // 2]
+        out = self.forward(torch.cat([half, half], dim=0), timestep, y, mask, data_info=data_info, **kwargs)
+        eps, rest = out[:, :3], out[:, 3:]
+        cond_eps, uncond_eps = torch.split(eps, len(eps) // 2, dim=0)
+        mixed = uncond_eps + cfg_scale * (cond_eps - uncond_eps)
+        return torch.cat([torch.cat([mixed, mixed], dim=0), rest], dim=1)
+
+    def unpatchify(self, x):
+        """(B, h*w, p*p*c) -> (B, c, h*p, w*p) (PixArtMS.py:236-248)."""
+        c, p = self.out_channels, self.x_embedder.patch_size[0]
+        assert self.h * self.w == x.shape[1]
+        x = x.reshape(x.shape[0], self.h, self.w, p, p, c)
+        return x.permute(0, 5, 1, 3, 2, 4).reshape(x.shape[0], c, self.h * p, self.w * p)
+
+    def initialize(self):
+        """Same initial distribution as PixArtMS.initialize (PixArtMS.py:250-285)."""
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+        w = self.x_embedder.proj.weight.data
+        nn.init.xavier_uniform_(w.view(w.shape[0], -1))
+        small = [self.t_embedder.mlp[0], self.t_embedder.mlp[2], self.t_block[1], self.y_embedder.y_proj.fc1,
+                 self.y_embedder.y_proj.fc2]
+        if self.micro_conditioning:
+            small += [self.csize_embedder.mlp[0], self.csize_embedder.mlp[2], self.ar_embedder.mlp[0],
+                      self.ar_embedder.mlp[2]]
+        for m in small:
+            nn.init.normal_(m.weight, std=0.02)
+        for blk in self.blocks:
+            nn.init.zeros_(blk.cross_attn.proj.weight)
+            nn.init.zeros_(blk.cross_attn.proj.bias)
+        nn.init.zeros_(self.final_layer.linear.weight)
+        nn.init.zeros_(self.final_layer.linear.bias)
+
+
+@MODELS.register_module()
+def PixArtMS_XL_2(**kwargs):
+    """PixArt-Sigma-XL/2: depth 28, width 1152, 16 heads, patch 2 (PixArtMS.py:291-293)."""
+    return PixArtMS(depth=28, hidden_size=1152, patch_size=2, num_heads=16, **kwargs)
+
+
+def install_into_reference() -> bool:
+    """Re-point the reference's registry and module names at these classes, so an unmodified
+    `scripts/inference.py` / `train_scripts/train.py` builds the B200 model. Returns False when the
+    reference package is not importable."""
+    try:
+        import diffusion.model.builder as builder          # noqa: reference package, if on sys.path
+        import diffusion.model.nets as nets
+    except Exception:
+        return False
+    for name, obj in (("PixArtMS", PixArtMS), ("PixArtMS_XL_2", PixArtMS_XL_2)):
+        reg = builder.MODELS
+        table = getattr(reg, "_module_dict", None) or getattr(reg, "module_dict", None) or getattr(reg, "_m", None)
+        if table is not None:
+            table[name] = obj
+        setattr(nets, name, obj)
+    nets.PixArtMSBlock = PixArtMSBlock
+    return True

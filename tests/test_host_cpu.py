@@ -1,0 +1,120 @@
+"""CPU tests (-m "not gpu"): host-side mirror of the reference interface, C-ABI library surface, build recipe."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import pixart_oracle as po
+from oracle import refshim
+from pixart_sigma_b200 import MODELS, PixArtMS, PixArtMS_XL_2, PixArtMSBlock, build_model, lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _tiny(**kw):
+    return PixArtMS(depth=2, hidden_size=1152, num_heads=16, input_size=32, pe_interpolation=0.5,
+                    model_max_length=300, **kw)
+
+
+def test_state_dict_layout_matches_reference_checkpoint_keys():
+    """Key names AND shapes equal the reference layout restated in the oracle."""
+    m = _tiny()
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items() if k != "pos_embed"}
+    want = po.state_dict_shapes(po.OracleConfig(depth=2))
+    assert got == want
+    assert tuple(m.state_dict()["pos_embed"].shape) == (1, 256, 1152)
+
+
+@pytest.mark.parametrize("kw,cfg", [
+    (dict(kv_compress_config=dict(sampling="conv", scale_factor=2, kv_compress_layer=[1])),
+     dict(kv_sampling="conv", kv_scale_factor=2, kv_compress_layer=[1])),
+    (dict(qk_norm=True), dict(qk_norm=True)),
+    (dict(micro_condition=True), dict(micro_condition=True)),
+])
+def test_state_dict_layout_optional_modules(kw, cfg):
+    got = {k: tuple(v.shape) for k, v in _tiny(**kw).state_dict().items() if k != "pos_embed"}
+    assert got == po.state_dict_shapes(po.OracleConfig(depth=2, **cfg))
+
+
+@pytest.mark.skipif(not refshim.reference_available(), reason="/root/reference not present")
+def test_state_dict_keys_equal_live_reference():
+    from oracle.gen_golden import build_reference
+    refshim.install_reference_shims()
+    cfg = po.OracleConfig(depth=1, kv_sampling="conv", kv_scale_factor=2, kv_compress_layer=[0])
+    ref = build_reference(cfg, po.synthetic_state_dict(cfg))
+    ours = PixArtMS(depth=1, input_size=32, model_max_length=300,
+                    kv_compress_config=dict(sampling="conv", scale_factor=2, kv_compress_layer=[0]))
+    rs, os_ = ref.state_dict(), ours.state_dict()
+    assert set(rs) == set(os_)
+    assert all(rs[k].shape == os_[k].shape for k in rs)
+    # a reference checkpoint loads with the same strict=False call the reference scripts use
+    sd = {k: v for k, v in rs.items() if k != "pos_embed"}            # scripts/inference.py:181-184
+    missing, unexpected = ours.load_state_dict(sd, strict=False)
+    assert missing == ["pos_embed"] and not unexpected
+
+
+def test_registry_and_builder_surface():
+    assert set(MODELS.module_dict) >= {"PixArtMS", "PixArtMS_XL_2"}
+    m = build_model(dict(type="PixArtMS", depth=1), use_grad_checkpoint=True, use_fp32_attention=True,
+                    input_size=32, model_max_length=300)
+    assert isinstance(m, PixArtMS) and m.blocks[0].grad_checkpointing and m.blocks[0].attn.fp32_attention
+    assert m.depth == 1 and m.out_channels == 8 and m.patch_size == 2 and m.base_size == 16
+    assert isinstance(m.blocks[0], PixArtMSBlock)
+    assert callable(PixArtMS_XL_2)
+
+
+def test_initialisation_zeroes_the_layers_the_reference_zeroes():
+    m = _tiny()
+    assert float(m.final_layer.linear.weight.abs().sum()) == 0.0
+    assert all(float(b.cross_attn.proj.weight.abs().sum()) == 0.0 for b in m.blocks)
+    assert float(m.blocks[0].attn.qkv.bias.abs().sum()) == 0.0
+    assert 0.015 < float(m.t_block[1].weight.std()) < 0.025
+
+
+def test_no_cpu_path():
+    """The product must fail loudly without the GPU kernels: no eager / CPU fallback exists."""
+    m = _tiny().eval()
+    x, t, y, _ = po.synthetic_inputs(po.OracleConfig(depth=2), 1, (32, 32))
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU path"):
+        m(x, t, y)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU path"):
+        m.blocks[0](torch.zeros(1, 256, 1152), torch.zeros(1, 300, 1152), torch.zeros(1, 6 * 1152), [300], (16, 16))
+
+
+def test_unpatchify_matches_oracle():
+    m = _tiny()
+    m.h, m.w = 3, 5
+    x = torch.randn(2, 15, 32)
+    assert torch.equal(m.unpatchify(x), po.unpatchify(x, 3, 5, 2, 8))
+
+
+def test_library_exports_every_symbol_the_header_declares():
+    hdr = open(os.path.join(ROOT, "include", "pixart_sm100.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|uint64_t|const char\*)\s+(pxa_\w+)\s*\(", hdr, flags=re.M))
+    assert declared == set(lib.EXPORTS)
+    dll = lib.load()
+    for name in declared:
+        assert hasattr(dll, name), name
+    assert dll.pxa_version() == 100
+
+
+def test_ctypes_structs_match_header_sizes():
+    """Field-by-field size check of the POD argument structs against a compile of the header with gcc."""
+    import subprocess, tempfile
+    src = '#include <stdio.h>\n#include "pixart_sm100.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(PxaGemmArgs),' \
+          ' sizeof(PxaLnModArgs), sizeof(PxaAttnArgs), sizeof(PxaKvCompressArgs));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
+        sizes = [int(v) for v in subprocess.check_output([os.path.join(d, "s")]).split()]
+    assert sizes == [ctypes.sizeof(lib.GemmArgs), ctypes.sizeof(lib.LnModArgs), ctypes.sizeof(lib.AttnArgs),
+                     ctypes.sizeof(lib.KvCompressArgs)]
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "pixart_sigma_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            assert "oracle" not in open(os.path.join(pkg, fn)).read().replace("the oracle", ""), fn
