@@ -126,9 +126,9 @@ def ln_modulate(x: Tensor, shift: Tensor, scale: Tensor, eps: float = 1e-6) -> T
 
 def sdpa_heads(q: Tensor, k: Tensor, v: Tensor) -> Tensor:
     """softmax(q k^T / sqrt(d)) v for (B, n, H, d) operands -- xformers default scale (PixArt_blocks.py:153)."""
-    d = q.shape[-1]
-    s = torch.einsum("bqhd,bkhd->bhqk", q, k) * (d ** -0.5)
-    return torch.einsum("bhqk,bkhd->bqhd", torch.softmax(s.float(), dim=-1).to(q.dtype), v)
+    o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
+                                       scale=q.shape[-1] ** -0.5)
+    return o.transpose(1, 2)
 
 
 def kv_downsample(sd, prefix: str, t: Tensor, H: int, W: int, sr: int, sampling: Optional[str]) -> Tensor:
