@@ -2,13 +2,15 @@
 //
 // One CTA = one (sample, head) x 256 query rows, processed as two 128-row tiles A / B that ping-pong between the
 // tensor pipe and the softmax warps (while the softmax warps of A run exp2 on S_A, the tensor pipe does P_B V and
-// the next Q_B K^T).  384 threads:
+// the next Q_B K^T).  640 threads:
 //   warp 0      TMA producer: Q once, then K / V blocks of 128 keys into two 3-deep smem rings
 //   warp 1      MMA issuer (one thread): S = Q K^T (SS), O += P V (TS: P read from TMEM)
 //   warp 2      TMEM allocator (512 columns: S_A | S_B | O_A | O_B)
-//   warps 4-7   softmax warpgroup of tile A, warps 8-11 of tile B: one thread per query row; online softmax in
-//               fp32 with lazy rescaling of O (only when the running max grows by > 2^8), P written back to TMEM as
-//               bf16 over the S columns, final O / rowsum -> bf16 -> global
+//   warps 4-19  softmax: per tile two warpgroups, "lo" owns keys 0..63 and "hi" keys 64..127 of every block, so a
+//               query row is shared by a thread pair (64 S values each; row max exchanged through smem once per
+//               block).  4 softmax warps per SM sub-partition keep the MUFU fed while others wait on TMEM / barriers.
+//               Online softmax in fp32 with lazy rescaling of O (only when the running max grows by > 2^8), P written
+//               back to TMEM as bf16 over each half's own S columns, final O / rowsum -> bf16 -> global
 //
 // head_dim 72 is not a multiple of the 64-element swizzle atom, nor of UMMA K=16 / N%16: each Q/K/V tile is staged
 // as a "main" part (d 0..63, 128B swizzle) plus a "tail" part (d 64..79, 32B swizzle) whose d 72..79 are zero-filled
@@ -22,7 +24,7 @@
 
 namespace pxa {
 
-constexpr int kAttnThreads = 384;
+constexpr int kAttnThreads = 640;
 constexpr int kD = 72;
 constexpr int kTileQ = 128;
 constexpr int kTileKV = 128;
@@ -39,10 +41,11 @@ constexpr int kOffQTail = kOffVMain + kKVStages * kMainBytes;
 constexpr int kOffKTail = kOffQTail + 2 * kTailBytes;
 constexpr int kOffVTail = kOffKTail + kKVStages * kTailBytes;
 constexpr int kOffBars = kOffVTail + kKVStages * kTailBytes;
-constexpr int kAttnSmem = kOffBars + 256 + 1024;
+constexpr int kOffXchg = kOffBars + 256;                            // float [2 parity][2 tile][2 half][128 row]
+constexpr int kAttnSmem = kOffXchg + 2 * 2 * 2 * 128 * 4 + 1024;
 
 // TMEM columns
-constexpr uint32_t kColS = 0;       // S_A at 0, S_B at 128 (P aliases the first 64 columns of each)
+constexpr uint32_t kColS = 0;       // S_A at 0, S_B at 128; P (bf16) aliases S: keys 0..63 -> cols [0,32), keys 64..127 -> [64,96)
 constexpr uint32_t kColO = 256;     // O_A at 256 (main 64 + tail 16), O_B at 384
 
 struct AttnParams {
@@ -92,7 +95,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 128);
+      mbar_init(&p_full[t], 256);
     }
     mbar_init(o_full, 1);
     fence_mbar_init();
@@ -157,8 +160,9 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
 #pragma unroll
         for (int k = 0; k < kTileKV / 16; ++k) {
           const uint32_t acc = (first && k == 0) ? 0u : 1u;
-          umma_ts(om, pt + 8 * k, vd + (uint64_t)(k * (2048 >> 4)), idesc_pv_main, acc);
-          umma_ts(om + 64, pt + 8 * k, vt + (uint64_t)(k * (512 >> 4)), idesc_pv_tail, acc);
+          const uint32_t pa = pt + (k < 4 ? 8 * k : 64 + 8 * (k - 4));   // lo half at cols 0..31, hi half at 64..95
+          umma_ts(om, pa, vd + (uint64_t)(k * (2048 >> 4)), idesc_pv_main, acc);
+          umma_ts(om + 64, pa, vt + (uint64_t)(k * (512 >> 4)), idesc_pv_tail, acc);
         }
       };
 
@@ -205,75 +209,76 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       umma_commit(o_full);
     }
   } else if (warp >= 4) {
-    // ================================================================ softmax + epilogue (one thread per query row)
-    const int t = (warp - 4) >> 2;                 // tile 0 (A) / 1 (B)
-    const int qd = warp & 3;                       // TMEM sub-partition
+    // ================================================================ softmax + epilogue (two threads per query row)
+    const int w = warp - 4;
+    const int t = w >> 3;                          // tile 0 (A) / 1 (B)
+    const int hf = (w >> 2) & 1;                   // 0: keys 0..63 of each block, 1: keys 64..127
+    const int qd = w & 3;                          // TMEM sub-partition (= warp % 4)
     const int row_in_tile = qd * 32 + lane;
     const int qrow = q0 + t * kTileQ + row_in_tile;             // query index within the sample
     const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
-    const uint32_t t_s = tmem_base + kColS + t * 128 + lane_sel;
-    const uint32_t t_o = tmem_base + kColO + t * 128 + lane_sel;
+    const uint32_t t_s = tmem_base + kColS + t * 128 + hf * 64 + lane_sel;   // this half's 64 S columns (P over the first 32)
+    const uint32_t t_o = tmem_base + kColO + t * 128 + hf * 32 + lane_sel;   // lo: O cols 0..31, hi: O cols 32..71
     const float sl2 = p.scale_log2;
+    float* xchg = reinterpret_cast<float*>(smem + kOffXchg);
+    const uint32_t bar_id = 1 + t;                 // named barrier of this tile's 256 softmax threads
 
-    float m_ref = -INFINITY;     // reference max used in the exponent (raw S units)
-    float row_sum = 0.f;
+    float m_ref = -INFINITY;     // reference max used in the exponent (raw S units); identical in both halves
+    float row_sum = 0.f;         // partial: this half's keys only
 
     for (int j = 0; j < n_blocks; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
-      uint32_t v0[32], v1[32], v2[32], v3[32];
-      tmem_ld_32x32b_x32(t_s + 0, v0);
-      tmem_ld_32x32b_x32(t_s + 32, v1);
-      tmem_ld_32x32b_x32(t_s + 64, v2);
-      tmem_ld_32x32b_x32(t_s + 96, v3);
-      const int rem = kv_len - j * kTileKV;       // valid keys in this block
-      if (rem < kTileKV) {
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32b_x32_pair(t_s, v0, t_s + 32, v1);
+      const int rem = kv_len - j * kTileKV - hf * 64;           // valid keys among this half's 64
+      if (rem < 64) {
         const uint32_t ninf = 0xff800000u;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           if (i >= rem) v0[i] = ninf;
           if (32 + i >= rem) v1[i] = ninf;
-          if (64 + i >= rem) v2[i] = ninf;
-          if (96 + i >= rem) v3[i] = ninf;
         }
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        mx0 = fmaxf(mx0, __uint_as_float(v0[i]));
-        mx1 = fmaxf(mx1, __uint_as_float(v1[i]));
-        mx2 = fmaxf(mx2, __uint_as_float(v2[i]));
-        mx3 = fmaxf(mx3, __uint_as_float(v3[i]));
+      for (int i = 0; i < 16; ++i) {
+        mx0 = fmaxf(mx0, __uint_as_float(v0[2 * i]));
+        mx1 = fmaxf(mx1, __uint_as_float(v0[2 * i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(v1[2 * i]));
+        mx3 = fmaxf(mx3, __uint_as_float(v1[2 * i + 1]));
       }
-      const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_ref);
+      const float m_half = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      float* xb = xchg + ((j & 1) * 4 + t * 2) * 128;
+      xb[hf * 128 + row_in_tile] = m_half;
+      named_bar_sync(bar_id, 256);
+      const float m_new = fmaxf(fmaxf(m_half, xb[(hf ^ 1) * 128 + row_in_tile]), m_ref);
       // Lazy rescale: keep the old reference max unless it is stale by more than 2^8 (P stays <= 256, exact in the
-      // fp32 accumulators); the decision is warp-uniform because the TMEM round trip below is warp-collective.
+      // fp32 accumulators).  The decision is warp-uniform (the TMEM round trip below is warp-collective) and identical
+      // in the partner warp of the other half, which sees the same m_new / m_ref for the same 32 rows.
       const bool stale = (m_new - m_ref) * sl2 > 8.0f;          // true on the first block (m_ref = -inf)
       if (__any_sync(0xffffffffu, stale)) {
         const float factor = (m_ref == -INFINITY) ? 0.f : fast_exp2((m_ref - m_new) * sl2);
         if (j > 0) {
           // PV of block j-1 has completed (it was issued before the QK^T that produced this S)
-          uint32_t o0[32], o1[32], o2[16];
-          tmem_ld_32x32b_x32(t_o + 0, o0);
-          tmem_ld_32x32b_x32(t_o + 32, o1);
-          tmem_ld_32x32b_x16(t_o + 64, o2);
+          uint32_t o0[32], o1[8];
+          tmem_ld_32x32b_x32(t_o, o0);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            o0[i] = __float_as_uint(__uint_as_float(o0[i]) * factor);
-            o1[i] = __float_as_uint(__uint_as_float(o1[i]) * factor);
+          for (int i = 0; i < 32; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * factor);
+          tmem_st_32x32b_x32(t_o, o0);
+          if (hf == 1) {                         // warp-uniform: d 64..71 (the 8 zero pad columns 72..79 need no scaling)
+            tmem_ld_32x32b_x8(t_o + 32, o1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o1[i] = __float_as_uint(__uint_as_float(o1[i]) * factor);
+            tmem_st_32x32b_x8(t_o + 32, o1);
           }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) o2[i] = __float_as_uint(__uint_as_float(o2[i]) * factor);
-          tmem_st_32x32b_x32(t_o + 0, o0);
-          tmem_st_32x32b_x32(t_o + 32, o1);
-          tmem_st_32x32b_x16(t_o + 64, o2);
         }
         row_sum *= factor;
         m_ref = m_new;
       }
       const float neg_m = -m_ref * sl2;
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-      uint32_t pk0[32], pk1[32];
+      uint32_t pk[32];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float a0 = fast_exp2(fmaf(__uint_as_float(v0[2 * i]), sl2, neg_m));
@@ -281,45 +286,38 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         const float b0 = fast_exp2(fmaf(__uint_as_float(v1[2 * i]), sl2, neg_m));
         const float b1 = fast_exp2(fmaf(__uint_as_float(v1[2 * i + 1]), sl2, neg_m));
         sum0 += a0; sum1 += a1; sum2 += b0; sum3 += b1;
-        pk0[i] = pack_bf16x2(a0, a1);
-        pk0[16 + i] = pack_bf16x2(b0, b1);
+        pk[i] = pack_bf16x2(a0, a1);
+        pk[16 + i] = pack_bf16x2(b0, b1);
       }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float a0 = fast_exp2(fmaf(__uint_as_float(v2[2 * i]), sl2, neg_m));
-        const float a1 = fast_exp2(fmaf(__uint_as_float(v2[2 * i + 1]), sl2, neg_m));
-        const float b0 = fast_exp2(fmaf(__uint_as_float(v3[2 * i]), sl2, neg_m));
-        const float b1 = fast_exp2(fmaf(__uint_as_float(v3[2 * i + 1]), sl2, neg_m));
-        sum0 += a0; sum1 += a1; sum2 += b0; sum3 += b1;
-        pk1[i] = pack_bf16x2(a0, a1);
-        pk1[16 + i] = pack_bf16x2(b0, b1);
-      }
-      // P (bf16, 128 keys = 64 packed columns) over the first 64 columns of S
-      tmem_st_32x32b_x32(t_s + 0, pk0);
-      tmem_st_32x32b_x32(t_s + 32, pk1);
+      // P (bf16, this half's 64 keys = 32 packed columns) over the first 32 of this half's own S columns
+      tmem_st_32x32b_x32(t_s, pk);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
       row_sum += (sum0 + sum1) + (sum2 + sum3);
     }
 
-    // ---- epilogue: O / row_sum -> bf16 -> out[(b*Nq + qrow), h*72 .. h*72+71]
-    uint32_t o0[32], o1[32], o2[8];
+    // ---- epilogue: O / row_sum -> bf16 -> out[(b*Nq + qrow), h*72 + hf*32 .. ]   (lo: d 0..31, hi: d 32..71)
+    float* xs = xchg + (t * 2) * 128;               // parity-0 slots are free again after the last block's barrier
+    named_bar_sync(bar_id, 256);                    // everybody is done reading the max exchange buffers
+    xs[hf * 128 + row_in_tile] = row_sum;
+    named_bar_sync(bar_id, 256);
+    const float total = row_sum + xs[(hf ^ 1) * 128 + row_in_tile];
+    uint32_t o0[32], o1[8];
     if (n_blocks > 0) {
       mbar_wait(o_full, 0);
       tc_fence_after();
-      tmem_ld_32x32b_x32(t_o + 0, o0);
-      tmem_ld_32x32b_x32(t_o + 32, o1);
-      tmem_ld_32x32b_x8(t_o + 64, o2);
+      tmem_ld_32x32b_x32(t_o, o0);
+      if (hf == 1) tmem_ld_32x32b_x8(t_o + 32, o1);
     } else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { o0[i] = 0u; o1[i] = 0u; }
+      for (int i = 0; i < 32; ++i) o0[i] = 0u;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o2[i] = 0u;
+      for (int i = 0; i < 8; ++i) o1[i] = 0u;
     }
     if (qrow < p.Nq) {
-      const float inv = row_sum > 0.f ? 1.0f / row_sum : 0.f;
-      __nv_bfloat16* dst = p.out + (size_t)(b * p.Nq + qrow) * p.ldo + h * kD;
+      const float inv = total > 0.f ? 1.0f / total : 0.f;
+      __nv_bfloat16* dst = p.out + (size_t)(b * p.Nq + qrow) * p.ldo + h * kD + hf * 32;
       uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -327,15 +325,13 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
                            pack_bf16x2(__uint_as_float(o0[8 * c + 2]) * inv, __uint_as_float(o0[8 * c + 3]) * inv),
                            pack_bf16x2(__uint_as_float(o0[8 * c + 4]) * inv, __uint_as_float(o0[8 * c + 5]) * inv),
                            pack_bf16x2(__uint_as_float(o0[8 * c + 6]) * inv, __uint_as_float(o0[8 * c + 7]) * inv));
-        d4[4 + c] = make_uint4(pack_bf16x2(__uint_as_float(o1[8 * c]) * inv, __uint_as_float(o1[8 * c + 1]) * inv),
-                               pack_bf16x2(__uint_as_float(o1[8 * c + 2]) * inv, __uint_as_float(o1[8 * c + 3]) * inv),
-                               pack_bf16x2(__uint_as_float(o1[8 * c + 4]) * inv, __uint_as_float(o1[8 * c + 5]) * inv),
-                               pack_bf16x2(__uint_as_float(o1[8 * c + 6]) * inv, __uint_as_float(o1[8 * c + 7]) * inv));
       }
-      d4[8] = make_uint4(pack_bf16x2(__uint_as_float(o2[0]) * inv, __uint_as_float(o2[1]) * inv),
-                         pack_bf16x2(__uint_as_float(o2[2]) * inv, __uint_as_float(o2[3]) * inv),
-                         pack_bf16x2(__uint_as_float(o2[4]) * inv, __uint_as_float(o2[5]) * inv),
-                         pack_bf16x2(__uint_as_float(o2[6]) * inv, __uint_as_float(o2[7]) * inv));
+      if (hf == 1) {
+        d4[4] = make_uint4(pack_bf16x2(__uint_as_float(o1[0]) * inv, __uint_as_float(o1[1]) * inv),
+                           pack_bf16x2(__uint_as_float(o1[2]) * inv, __uint_as_float(o1[3]) * inv),
+                           pack_bf16x2(__uint_as_float(o1[4]) * inv, __uint_as_float(o1[5]) * inv),
+                           pack_bf16x2(__uint_as_float(o1[6]) * inv, __uint_as_float(o1[7]) * inv));
+      }
     }
   }
 

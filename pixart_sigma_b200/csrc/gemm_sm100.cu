@@ -106,9 +106,37 @@ PXA_DEVICE void epilogue_chunk_bf16(uint32_t (&v)[32], const GemmParams& p, uint
 
 // Residual epilogue (EPI 2): fp32 acc transposed through smem (128 B per row), then in the coalesced layout
 // out = residual + gate * (acc + bias); optional bf16 aux copy.
+// In the coalesced layout lane l owns columns [4*(l&7), +4) of rows 4*it + (l>>3), it = 0..7.
+// The residual fragment of chunk c+1 is loaded BEFORE chunk c is processed (software prefetch): the epilogue would
+// otherwise serialise one DRAM round trip per 4 rows (loads may not be hoisted over the stores by the compiler because
+// `residual` may alias `out`), which made the K=1152 residual GEMMs epilogue-bound (profiles/r1: 11% tensor pipe).
+struct ResFrag {
+  float4 r[8];
+};
+
 template <typename OutT>
-PXA_DEVICE void epilogue_chunk_residual(uint32_t (&v)[32], const GemmParams& p, uint8_t* stile, int lane, int row0,
-                                        int col0) {
+PXA_DEVICE void load_residual_frag(ResFrag& f, const GemmParams& p, int lane, int row0, int col0) {
+  const int gcol = col0 + (lane & 7) * 4;
+  const bool col_ok = gcol < p.N;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int grow = row0 + it * 4 + (lane >> 3);
+    f.r[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (grow < p.M && col_ok) {
+      const size_t off = (size_t)grow * p.ldo + gcol;
+      if constexpr (sizeof(OutT) == 4) {
+        f.r[it] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + off);
+      } else {
+        uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + off);
+        f.r[it] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+      }
+    }
+  }
+}
+
+template <typename OutT>
+PXA_DEVICE void epilogue_chunk_residual(uint32_t (&v)[32], const ResFrag& res, const GemmParams& p, uint8_t* stile,
+                                        int lane, int row0, int col0) {
   // smem tile: 32 rows x 128 B; 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) * 16)
   {
     const int sw = lane & 7;
@@ -127,30 +155,29 @@ PXA_DEVICE void epilogue_chunk_residual(uint32_t (&v)[32], const GemmParams& p, 
     uint2 u = __ldg(reinterpret_cast<const uint2*>(p.bias + gcol));
     b0 = bf16_lo(u.x); b1 = bf16_hi(u.x); b2 = bf16_lo(u.y); b3 = bf16_hi(u.y);
   }
+  // gate: all loads first (tiny table, L1/L2 resident), then compute + store
+  float4 g[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int grow = row0 + it * 4 + (lane >> 3);
+    g[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (p.gate != nullptr && grow < p.M && col_ok) {
+      const int bidx = grow / p.rows_per_batch;
+      g[it] = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)bidx * p.gate_batch_stride + gcol));
+    }
+  }
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int r = it * 4 + (lane >> 3);
     const int grow = row0 + r;
-    float4 a = *reinterpret_cast<const float4*>(stile + r * 128 + ((c ^ (r & 7)) << 4));
+    const float4 a = *reinterpret_cast<const float4*>(stile + r * 128 + ((c ^ (r & 7)) << 4));
     if (grow < p.M && col_ok) {
-      float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (p.gate != nullptr) {
-        const int bidx = grow / p.rows_per_batch;
-        g = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)bidx * p.gate_batch_stride + gcol));
-      }
       const size_t off = (size_t)grow * p.ldo + gcol;
-      float4 res;
-      if constexpr (sizeof(OutT) == 4) {
-        res = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + off);
-      } else {
-        uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + off);
-        res = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
-      }
       float4 o;
-      o.x = fmaf(g.x, a.x + b0, res.x);
-      o.y = fmaf(g.y, a.y + b1, res.y);
-      o.z = fmaf(g.z, a.z + b2, res.z);
-      o.w = fmaf(g.w, a.w + b3, res.w);
+      o.x = fmaf(g[it].x, a.x + b0, res.r[it].x);
+      o.y = fmaf(g[it].y, a.y + b1, res.r[it].y);
+      o.z = fmaf(g[it].z, a.z + b2, res.r[it].z);
+      o.w = fmaf(g[it].w, a.w + b3, res.r[it].w);
       if constexpr (sizeof(OutT) == 4) {
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = o;
       } else {
@@ -266,11 +293,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.num_n_tiles) * kBM;
       const int n0 = (tile % p.num_n_tiles) * BN;
+      ResFrag res_next;
+      if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
+        // first residual fragment: issued before the accumulator is ready, so its latency hides under the MMAs
+        load_residual_frag<OutT>(res_next, p, lane, m0 + q * 32, n0);
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
+        ResFrag res_cur;
+        if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
+          res_cur = res_next;
+          if (cc + 1 < BN / 32 && n0 + (cc + 1) * 32 < p.N)
+            load_residual_frag<OutT>(res_next, p, lane, m0 + q * 32, n0 + (cc + 1) * 32);
+        }
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_acc + cc * 32, v);   // includes tcgen05.wait::ld
         if (cc == BN / 32 - 1) {
@@ -280,7 +318,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         if (n0 + cc * 32 < p.N) {
           if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL)
-            epilogue_chunk_residual<OutT>(v, p, stile, lane, m0 + q * 32, n0 + cc * 32);
+            epilogue_chunk_residual<OutT>(v, res_cur, p, stile, lane, m0 + q * 32, n0 + cc * 32);
           else
             epilogue_chunk_bf16<EPI>(v, p, stile, lane, m0 + q * 32, n0 + cc * 32);
         }

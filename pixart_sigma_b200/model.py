@@ -399,6 +399,10 @@ class PixArtMS(nn.Module):
             for i in range(depth)])
         self.final_layer = T2IFinalLayer(hidden_size, patch_size, self.out_channels)
         self.output_dtype: Optional[torch.dtype] = None    # None -> model dtype (reference behaviour)
+        # The reference casts `timestep` to the model dtype before the sinusoid (PixArtMS.py:174), which at bf16 turns
+        # the DPM-Solver time 749.25 into 748 and moves the output by up to 5e-2.  Default: keep the
+        # timestep in fp32 like the fp32 reference does; set True to reproduce the bf16 cast bit for bit.
+        self.round_timestep_to_dtype = False
         self._ws = _Workspace()
         self.initialize()
 
@@ -441,8 +445,10 @@ class PixArtMS(nn.Module):
         dt, dev, C, p = self.dtype, w0.device, self.hidden_size, self.patch_size
         B = x.shape[0]
         x = x.to(device=dev, dtype=dt)
-        timestep = timestep.to(device=dev, dtype=dt)        # the reference rounds t to the model dtype here (:174)
+        timestep = timestep.to(device=dev, dtype=dt if self.round_timestep_to_dtype else torch.float32)
         y = y.to(device=dev)
+        if mask is not None:
+            mask = mask.to(device=dev)
         self.h, self.w = x.shape[-2] // p, x.shape[-1] // p
         N = self.h * self.w
 
