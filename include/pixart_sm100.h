@@ -107,6 +107,7 @@ typedef struct PxaAttnArgs {
   int32_t B, H, Nq, Nk; /* Nk = max keys per sample (loop bound) */
   int32_t ldo;
   float scale;      /* softmax scale, 72^-0.5 */
+  int64_t* debug_trace; /* NULL in production. Else device int64[16 warps + 2][kTraceMax] cycle stamps of CTA (0,0,0) */
 } PxaAttnArgs;
 int pxa_flash_attn_d72_bf16(const PxaAttnArgs* args, void* stream);
 

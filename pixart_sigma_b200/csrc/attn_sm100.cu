@@ -54,7 +54,15 @@ struct AttnParams {
   const int* kv_off;
   int B, H, Nq, Nk, ldo;
   float scale_log2;
+  long long* trace;     // debug only (NULL in production): cycle stamps of CTA (0,0,0), see PXA_TRACE
 };
+
+constexpr int kTraceMax = 512;
+// Slot `who` (0..15 softmax warps, 16 = MMA thread, 17 = TMA thread) appends clock64() stamps.
+#define PXA_TRACE(who, cnt)                                                                        \
+  do {                                                                                             \
+    if (tracing && (cnt) < kTraceMax) p.trace[(who) * kTraceMax + (cnt)++] = clock64();            \
+  } while (0)
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
 flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_constant__ CUtensorMap tm_q_tail,
@@ -83,6 +91,8 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
   kv_len = min(max(kv_len, 0), p.Nk);
   const int kv_row0 = p.kv_off ? p.kv_off[b] : b * p.Nk;
   const int n_blocks = (kv_len + kTileKV - 1) / kTileKV;
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+  int tcnt = 0;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tm_q_main); prefetch_tmap(&tm_q_tail);
@@ -122,6 +132,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       for (int j = 0; j < n_blocks; ++j) {
         const int krow = kv_row0 + j * kTileKV;
         mbar_wait(&k_empty[stage], phase ^ 1);
+        PXA_TRACE(17, tcnt);
         mbar_arrive_expect_tx(&k_full[stage], kTileBytes);
         tma_load_3d(smem + kOffKMain + stage * kMainBytes, &tm_k_main, &k_full[stage], 0, h, krow, kEvictLast);
         tma_load_3d(smem + kOffKTail + stage * kTailBytes, &tm_k_tail, &k_full[stage], 64, h, krow, kEvictLast);
@@ -184,7 +195,9 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         const bool more = (j + 1 < n_blocks);
         mbar_wait(&v_full[stage], phase);
         // ---- tile A
+        PXA_TRACE(16, tcnt);                       // [4j+0] start waiting for P_A
         mbar_wait(&p_full[0], j & 1);
+        PXA_TRACE(16, tcnt);                       // [4j+1] P_A ready
         tc_fence_after();
         issue_pv(0, stage, j == 0);
         if (more) {
@@ -194,7 +207,9 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
           umma_commit(&s_full[0]);
         }
         // ---- tile B
+        PXA_TRACE(16, tcnt);                       // [4j+2] A's MMAs issued, start waiting for P_B
         mbar_wait(&p_full[1], j & 1);
+        PXA_TRACE(16, tcnt);                       // [4j+3] P_B ready
         tc_fence_after();
         issue_pv(1, stage, j == 0);
         umma_commit(&v_empty[stage]);
@@ -227,10 +242,13 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
     float row_sum = 0.f;         // partial: this half's keys only
 
     for (int j = 0; j < n_blocks; ++j) {
+      PXA_TRACE(w, tcnt);                          // [5j+0] start waiting for S
       mbar_wait(&s_full[t], j & 1);
+      PXA_TRACE(w, tcnt);                          // [5j+1] S ready
       tc_fence_after();
       uint32_t v0[32], v1[32];
       tmem_ld_32x32b_x32_pair(t_s, v0, t_s + 32, v1);
+      PXA_TRACE(w, tcnt);                          // [5j+2] S in registers
       const int rem = kv_len - j * kTileKV - hf * 64;           // valid keys among this half's 64
       if (rem < 64) {
         const uint32_t ninf = 0xff800000u;
@@ -252,6 +270,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       float* xb = xchg + ((j & 1) * 4 + t * 2) * 128;
       xb[hf * 128 + row_in_tile] = m_half;
       named_bar_sync(bar_id, 256);
+      PXA_TRACE(w, tcnt);                          // [5j+3] row max exchanged
       const float m_new = fmaxf(fmaxf(m_half, xb[(hf ^ 1) * 128 + row_in_tile]), m_ref);
       // Lazy rescale: keep the old reference max unless it is stale by more than 2^8 (P stays <= 256, exact in the
       // fp32 accumulators).  The decision is warp-uniform (the TMEM round trip below is warp-collective) and identical
@@ -294,6 +313,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
+      PXA_TRACE(w, tcnt);                          // [5j+4] P published
       row_sum += (sum0 + sum1) + (sum2 + sum3);
     }
 
@@ -379,6 +399,7 @@ extern "C" int pxa_flash_attn_d72_bf16(const PxaAttnArgs* args, void* stream) {
   p.kv_off = a.kv_off;
   p.B = a.B; p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk; p.ldo = a.ldo;
   p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.trace = reinterpret_cast<long long*>(a.debug_trace);
   PXA_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_d72_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
   dim3 grid((a.Nq + 2 * kTileQ - 1) / (2 * kTileQ), a.H, a.B);
   flash_attn_d72_kernel<<<grid, kAttnThreads, kAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(qm, qt, km, kt, vm,

@@ -196,7 +196,7 @@ PXA_DEVICE void epilogue_chunk_residual(uint32_t (&v)[32], const ResFrag& res, c
 template <int BN, int EPI, typename OutT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmap_res, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -242,6 +242,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / p.num_n_tiles) * kBM;
         const int n0 = (tile % p.num_n_tiles) * BN;
+        if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
+          // pull this tile's residual block into L2 now: the epilogue reads it one mainloop (~7k cycles) later
+          tma_prefetch_l2_2d(&tmap_res, n0, m0);
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStage;
@@ -355,6 +359,15 @@ static int launch_gemm(const PxaGemmArgs& a, cudaStream_t stream) {
     int rc = make_tmap_bf16(&tw, a.w, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
+  CUtensorMap tr = ta;   // unused unless EPI_BIAS_RESIDUAL
+  if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
+    uint64_t dims[2] = {(uint64_t)a.N, (uint64_t)a.M};
+    uint64_t str[1] = {(uint64_t)a.ldo * sizeof(OutT)};
+    uint32_t box[2] = {(uint32_t)BN, kBM};
+    int rc = make_tmap(&tr, sizeof(OutT) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                       a.residual, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+  }
   GemmParams p;
   p.bias = reinterpret_cast<const __nv_bfloat16*>(a.bias);
   p.out = a.out;
@@ -372,7 +385,7 @@ static int launch_gemm(const PxaGemmArgs& a, cudaStream_t stream) {
   if (a.max_ctas > 0 && a.max_ctas < grid) grid = a.max_ctas;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   if (tiles < grid) grid = tiles;
-  kern<<<grid, kGemmThreads, Cfg::kSmem, stream>>>(ta, tw, p);
+  kern<<<grid, kGemmThreads, Cfg::kSmem, stream>>>(ta, tw, tr, p);
   launch_counter()++;
   PXA_CHECK_CUDA(cudaGetLastError());
   return PXA_OK;

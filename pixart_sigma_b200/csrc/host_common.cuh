@@ -87,8 +87,8 @@ inline EncodeTiledFn encode_tiled_fn() {
 
 // bf16 tensor map of rank `rank` (<= 4). dims[0] is the contiguous dimension; strides_bytes[i] is the byte stride of
 // dims[i+1]. OOB elements read as zero.
-inline int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                          const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+inline int make_tmap(CUtensorMap* map, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return fail(PXA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   if (reinterpret_cast<uintptr_t>(base) & 15) return fail(PXA_ERR_ALIGN, "tensor base %p not 16-byte aligned", base);
@@ -104,11 +104,16 @@ inline int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const ui
       if (s[i] & 15) return fail(PXA_ERR_ALIGN, "tensor stride %llu bytes not a multiple of 16", (unsigned long long)s[i]);
     }
   }
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), d, s, b, e,
+  CUresult r = fn(map, dtype, rank, const_cast<void*>(base), d, s, b, e,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(PXA_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return PXA_OK;
+}
+
+inline int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+  return make_tmap(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swz);
 }
 
 }  // namespace pxa

@@ -44,7 +44,7 @@ class AttnArgs(C.Structure):
                 ("k_sn", C.c_int64), ("k_sh", C.c_int64), ("v_sn", C.c_int64), ("v_sh", C.c_int64),
                 ("kv_rows", C.c_int64),
                 ("B", C.c_int32), ("H", C.c_int32), ("Nq", C.c_int32), ("Nk", C.c_int32),
-                ("ldo", C.c_int32), ("scale", C.c_float)]
+                ("ldo", C.c_int32), ("scale", C.c_float), ("debug_trace", C.c_void_p)]
 
 
 class KvCompressArgs(C.Structure):
@@ -144,7 +144,8 @@ def ln_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, out: 
 
 def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, B: int, H: int, Nq: int,
                Nk: int, kv_rows: int, kv_len: Optional[torch.Tensor] = None, kv_off: Optional[torch.Tensor] = None,
-               q_strides=None, k_strides=None, v_strides=None, scale: Optional[float] = None) -> torch.Tensor:
+               q_strides=None, k_strides=None, v_strides=None, scale: Optional[float] = None,
+               debug_trace: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Head-dim-72 attention. q/k/v are bf16 *views*; strides are (row, head) in elements, e.g. slices of the
     (rows, 3, H, 72) qkv GEMM output. out is (B*Nq, H*72) bf16."""
     assert q.dtype == k.dtype == v.dtype == out.dtype == torch.bfloat16
@@ -154,7 +155,8 @@ def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Ten
     args = AttnArgs(q=_ptr(q), k=_ptr(k), v=_ptr(v), out=_ptr(out), kv_len=_ptr(kv_len), kv_off=_ptr(kv_off),
                     q_sn=q_strides[0], q_sh=q_strides[1], k_sn=k_strides[0], k_sh=k_strides[1],
                     v_sn=v_strides[0], v_sh=v_strides[1], kv_rows=kv_rows, B=B, H=H, Nq=Nq, Nk=Nk,
-                    ldo=out.stride(0), scale=scale if scale is not None else 72 ** -0.5)
+                    ldo=out.stride(0), scale=scale if scale is not None else 72 ** -0.5,
+                    debug_trace=_ptr(debug_trace))
     _check(load().pxa_flash_attn_d72_bf16(C.byref(args), _stream()), "pxa_flash_attn_d72_bf16")
     return out
 

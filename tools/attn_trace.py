@@ -1,0 +1,36 @@
+"""Cycle trace of one CTA of the attention kernel under a full-grid launch (debug aid, see PXA_TRACE in attn_sm100.cu)."""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pixart_sigma_b200 import lib
+
+B, H, N = 8, 16, 4096
+g = torch.Generator().manual_seed(0)
+qkv = (torch.randn(B * N, 3, H, 72, generator=g)).to(torch.bfloat16).cuda()
+out = torch.empty(B * N, H * 72, dtype=torch.bfloat16, device="cuda")
+trace = torch.zeros(18, 512, dtype=torch.int64, device="cuda")
+kw = dict(B=B, H=H, Nq=N, Nk=N, kv_rows=B * N, q_strides=(3 * H * 72, 72), k_strides=(3 * H * 72, 72), v_strides=(3 * H * 72, 72))
+for _ in range(2):
+    lib.flash_attn(qkv[:, 0], qkv[:, 1], qkv[:, 2], out, **kw)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+lib.flash_attn(qkv[:, 0], qkv[:, 1], qkv[:, 2], out, debug_trace=trace, **kw)
+e1.record()
+torch.cuda.synchronize()
+print(f"kernel {e0.elapsed_time(e1):.3f} ms, {4*B*H*N*N*72/e0.elapsed_time(e1)/1e9:.1f} TFLOP/s")
+tr = trace.cpu()
+t0 = int(tr[tr > 0].min())
+names = {0: "A-lo q0", 4: "A-hi q0", 8: "B-lo q0", 12: "B-hi q0"}
+print("softmax stamps per block j: [wait S | S ready | S in regs | max exchanged | P published] (cycles since CTA start)")
+for w, nm in names.items():
+    for j in range(0, 8):
+        row = [int(v) - t0 for v in tr[w, 5 * j:5 * j + 5]]
+        d = [row[i + 1] - row[i] for i in range(4)]
+        print(f"  {nm} j={j}: {row}  d(waitS,ld,xchg,exp+st)={d}")
+print("MMA thread per block j: [wait P_A | P_A ready | wait P_B | P_B ready]")
+for j in range(0, 10):
+    row = [int(v) - t0 for v in tr[16, 4 * j:4 * j + 4]]
+    print(f"  j={j}: {row}  wait_A={row[1]-row[0]} issueA={row[2]-row[1]} wait_B={row[3]-row[2]}")
+per = [int(tr[16, 4 * (j + 1)]) - int(tr[16, 4 * j]) for j in range(4, 28)]
+print("cycles per block (MMA loop period), j=4..27:", per, "mean", sum(per) / len(per))
