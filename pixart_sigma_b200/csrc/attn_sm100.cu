@@ -118,7 +118,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
 
   if (warp == 0) {
     // ================================================================ TMA producer
-    if (lane == 0 && n_blocks > 0) {
+    if (n_blocks > 0 && elect_one()) {
       const int qrow = b * p.Nq + q0;
       mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
       for (int t = 0; t < 2; ++t) {
@@ -145,7 +145,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    if (lane == 0 && n_blocks > 0) {
+    if (n_blocks > 0 && elect_one()) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv_main = make_idesc_bf16(128, 64, 0, 1);   // V is MN-major
       constexpr uint32_t idesc_pv_tail = make_idesc_bf16(128, 16, 0, 1);
