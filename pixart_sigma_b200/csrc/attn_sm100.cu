@@ -80,7 +80,8 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
   uint64_t* s_full = v_empty + kKVStages;     // [2]  MMA -> softmax (S ready; also implies previous PV done)
   uint64_t* p_full = s_full + 2;              // [2]  softmax -> MMA (P written, S consumed)
   uint64_t* o_full = p_full + 2;              // [1]  MMA -> softmax (all PV done)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* exp_turn = o_full + 1;            // [2]  softmax A <-> softmax B: serialises the two tiles' exp2 sections
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(exp_turn + 2);
 
   const int warp = warp_idx_sync();
   const int lane = threadIdx.x & 31;
@@ -108,6 +109,8 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       mbar_init(&p_full[t], 256);
     }
     mbar_init(o_full, 1);
+    mbar_init(&exp_turn[0], 256);
+    mbar_init(&exp_turn[1], 256);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -298,6 +301,14 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       const float neg_m = -m_ref * sl2;
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
       uint32_t pk[32];
+      // The MUFU pipe is the bottleneck resource: run the exp2 sections of tile A and tile B strictly one after the
+      // other (A_j, B_j, A_j+1, ...) so each gets the full MUFU rate and the other tile's MMA / TMEM / barrier
+      // latencies hide underneath, instead of both tiles crawling through exp2 in lockstep at half rate.
+      if (t == 0) {
+        if (j > 0) mbar_wait(&exp_turn[0], (j - 1) & 1);      // B finished the exp2 section of block j-1
+      } else {
+        mbar_wait(&exp_turn[1], j & 1);                        // A finished the exp2 section of block j
+      }
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float a0 = fast_exp2(fmaf(__uint_as_float(v0[2 * i]), sl2, neg_m));
@@ -308,6 +319,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         pk[i] = pack_bf16x2(a0, a1);
         pk[16 + i] = pack_bf16x2(b0, b1);
       }
+      mbar_arrive(&exp_turn[t ^ 1]);                           // hand the MUFU to the other tile
       // P (bf16, this half's 64 keys = 32 packed columns) over the first 32 of this half's own S columns
       tmem_st_32x32b_x32(t_s, pk);
       tmem_st_wait();
