@@ -301,14 +301,12 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       const float neg_m = -m_ref * sl2;
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
       uint32_t pk[32];
-      // The MUFU pipe is the bottleneck resource: run the exp2 sections of tile A and tile B strictly one after the
-      // other (A_j, B_j, A_j+1, ...) so each gets the full MUFU rate and the other tile's MMA / TMEM / barrier
-      // latencies hide underneath, instead of both tiles crawling through exp2 in lockstep at half rate.
-      if (t == 0) {
-        if (j > 0) mbar_wait(&exp_turn[0], (j - 1) & 1);      // B finished the exp2 section of block j-1
-      } else {
-        mbar_wait(&exp_turn[1], j & 1);                        // A finished the exp2 section of block j
-      }
+      // The MUFU pipe is the bottleneck resource.  If both tiles run their exp2 sections in lockstep each gets half
+      // the MUFU rate and the block period is 2E + W (E = exp2 section alone, W = MMA + TMEM + barrier latency of a
+      // tile); offset by E the period drops to E + W.  The offset between the tiles is preserved from block to block
+      // (both slow down equally while they overlap), so it only has to be set up once: tile B starts its first exp2
+      // section when tile A has finished its first one.
+      if (j == 0 && t == 1) mbar_wait(&exp_turn[1], 0);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float a0 = fast_exp2(fmaf(__uint_as_float(v0[2 * i]), sl2, neg_m));
@@ -319,7 +317,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         pk[i] = pack_bf16x2(a0, a1);
         pk[16 + i] = pack_bf16x2(b0, b1);
       }
-      mbar_arrive(&exp_turn[t ^ 1]);                           // hand the MUFU to the other tile
+      if (j == 0 && t == 0) mbar_arrive(&exp_turn[1]);         // releases tile B's first exp2 section
       // P (bf16, this half's 64 keys = 32 packed columns) over the first 32 of this half's own S columns
       tmem_st_32x32b_x32(t_s, pk);
       tmem_st_wait();
