@@ -306,18 +306,26 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       // tile); offset by E the period drops to E + W.  The offset between the tiles is preserved from block to block
       // (both slow down equally while they overlap), so it only has to be set up once: tile B starts its first exp2
       // section when tile A has finished its first one.
-      if (j == 0 && t == 1) mbar_wait(&exp_turn[1], 0);
+      float neg_m_dep = neg_m;
+      if (j == 0 && t == 1) {
+        mbar_wait(&exp_turn[1], 0);
+        // the exp2 below are plain register math: tie them to the wait so the compiler cannot hoist them above it
+        asm volatile("" : "+f"(neg_m_dep)::"memory");
+      }
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float a0 = fast_exp2(fmaf(__uint_as_float(v0[2 * i]), sl2, neg_m));
-        const float a1 = fast_exp2(fmaf(__uint_as_float(v0[2 * i + 1]), sl2, neg_m));
-        const float b0 = fast_exp2(fmaf(__uint_as_float(v1[2 * i]), sl2, neg_m));
-        const float b1 = fast_exp2(fmaf(__uint_as_float(v1[2 * i + 1]), sl2, neg_m));
+        const float a0 = fast_exp2(fmaf(__uint_as_float(v0[2 * i]), sl2, neg_m_dep));
+        const float a1 = fast_exp2(fmaf(__uint_as_float(v0[2 * i + 1]), sl2, neg_m_dep));
+        const float b0 = fast_exp2(fmaf(__uint_as_float(v1[2 * i]), sl2, neg_m_dep));
+        const float b1 = fast_exp2(fmaf(__uint_as_float(v1[2 * i + 1]), sl2, neg_m_dep));
         sum0 += a0; sum1 += a1; sum2 += b0; sum3 += b1;
         pk[i] = pack_bf16x2(a0, a1);
         pk[16 + i] = pack_bf16x2(b0, b1);
       }
-      if (j == 0 && t == 0) mbar_arrive(&exp_turn[1]);         // releases tile B's first exp2 section
+      if (j == 0 && t == 0) {
+        asm volatile("" ::"r"(pk[0]), "r"(pk[15]), "r"(pk[16]), "r"(pk[31]) : "memory");   // exp2 results exist
+        mbar_arrive(&exp_turn[1]);                             // releases tile B's first exp2 section
+      }
       // P (bf16, this half's 64 keys = 32 packed columns) over the first 32 of this half's own S columns
       tmem_st_32x32b_x32(t_s, pk);
       tmem_st_wait();

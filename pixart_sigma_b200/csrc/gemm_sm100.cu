@@ -11,186 +11,9 @@
 // whole weight matrix stays L2-resident.
 //
 // Algorithmic work: 2*M*N*K FLOP; bytes: M*K*2 (A) + N*K*2 (W) + M*N*out bytes (+ residual read).
-#include "host_common.cuh"
-#include "ptx.cuh"
+#include "gemm_common.cuh"
 
 namespace pxa {
-
-constexpr int kBM = 128;
-constexpr int kBK = 64;            // 64 bf16 = 128 B = one swizzle atom row
-constexpr int kGemmThreads = 256;
-constexpr int kEpiWarp0 = 4;       // first epilogue warp
-constexpr int kNumEpiThreads = 128;
-
-struct GemmParams {
-  const __nv_bfloat16* bias;
-  void* out;
-  __nv_bfloat16* out_aux;
-  const void* residual;
-  const float* gate;
-  long long gate_batch_stride;
-  int rows_per_batch;
-  int M, N, K, ldo;
-  int num_m_tiles, num_n_tiles;
-};
-
-template <int BN> struct GemmCfg {
-  static constexpr int kStageA = kBM * kBK * 2;                 // 16 KB
-  static constexpr int kStageB = BN * kBK * 2;
-  static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
-  static constexpr int kEpiSmem = 4 * 32 * 32 * 4;              // 4 epilogue warps x (32 rows x 128 B)
-  static constexpr int kBarBytes = 256;
-  static constexpr int kSmem = kStages * kStage + kEpiSmem + kBarBytes + 1024;  // +1024 alignment slack
-  static constexpr uint32_t kTmemCols = (2 * BN <= 256) ? 256 : 512;
-};
-
-// ------------------------------------------------------------------------------------------------- epilogues
-// Row-per-thread registers `v` hold acc for columns [col0, col0+32) of this thread's row.
-
-// bf16 output (EPI 0/1): math in row-per-thread layout, pack to bf16, transpose through smem (64 B per row).
-template <int EPI>
-PXA_DEVICE void epilogue_chunk_bf16(uint32_t (&v)[32], const GemmParams& p, uint8_t* stile, int lane, int row0, int col0) {
-  // bias: every lane needs the same 32 values -> 4 broadcast 16-byte loads
-  float b[32];
-  if (p.bias != nullptr) {
-    const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 u = make_uint4(0u, 0u, 0u, 0u);
-      if (col0 + 8 * i < p.N) u = __ldg(bp + i);
-      b[8 * i + 0] = bf16_lo(u.x); b[8 * i + 1] = bf16_hi(u.x);
-      b[8 * i + 2] = bf16_lo(u.y); b[8 * i + 3] = bf16_hi(u.y);
-      b[8 * i + 4] = bf16_lo(u.z); b[8 * i + 5] = bf16_hi(u.z);
-      b[8 * i + 6] = bf16_lo(u.w); b[8 * i + 7] = bf16_hi(u.w);
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) b[i] = 0.f;
-  }
-  uint32_t pk[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    float x0 = __uint_as_float(v[2 * i]) + b[2 * i];
-    float x1 = __uint_as_float(v[2 * i + 1]) + b[2 * i + 1];
-    if (EPI == PXA_EPI_BIAS_GELU) {
-      x0 = gelu_tanh(x0);
-      x1 = gelu_tanh(x1);
-    }
-    pk[i] = pack_bf16x2(x0, x1);
-  }
-  // smem tile: 32 rows x 64 B; 16-byte chunk c of row r lives at r*64 + ((c ^ ((r >> 1) & 3)) * 16)
-  {
-    const int sw = (lane >> 1) & 3;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint4 u = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-      *reinterpret_cast<uint4*>(stile + lane * 64 + ((c ^ sw) << 4)) = u;
-    }
-  }
-  __syncwarp();
-  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-  const int c = lane & 3;
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int r = it * 8 + (lane >> 2);
-    uint4 u = *reinterpret_cast<const uint4*>(stile + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
-    const int grow = row0 + r;
-    const int gcol = col0 + c * 8;
-    if (grow < p.M && gcol < p.N) {
-      *reinterpret_cast<uint4*>(out + (size_t)grow * p.ldo + gcol) = u;
-    }
-  }
-  __syncwarp();
-}
-
-// Residual epilogue (EPI 2): fp32 acc transposed through smem (128 B per row), then in the coalesced layout
-// out = residual + gate * (acc + bias); optional bf16 aux copy.
-// In the coalesced layout lane l owns columns [4*(l&7), +4) of rows 4*it + (l>>3), it = 0..7.
-// The residual fragment of chunk c+1 is loaded BEFORE chunk c is processed (software prefetch): the epilogue would
-// otherwise serialise one DRAM round trip per 4 rows (loads may not be hoisted over the stores by the compiler because
-// `residual` may alias `out`), which made the K=1152 residual GEMMs epilogue-bound (profiles/r1: 11% tensor pipe).
-struct ResFrag {
-  float4 r[8];
-};
-
-template <typename OutT>
-PXA_DEVICE void load_residual_frag(ResFrag& f, const GemmParams& p, int lane, int row0, int col0) {
-  const int gcol = col0 + (lane & 7) * 4;
-  const bool col_ok = gcol < p.N;
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int grow = row0 + it * 4 + (lane >> 3);
-    f.r[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (grow < p.M && col_ok) {
-      const size_t off = (size_t)grow * p.ldo + gcol;
-      if constexpr (sizeof(OutT) == 4) {
-        f.r[it] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + off);
-      } else {
-        uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + off);
-        f.r[it] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
-      }
-    }
-  }
-}
-
-template <typename OutT>
-PXA_DEVICE void epilogue_chunk_residual(uint32_t (&v)[32], const ResFrag& res, const GemmParams& p, uint8_t* stile,
-                                        int lane, int row0, int col0) {
-  // smem tile: 32 rows x 128 B; 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) * 16)
-  {
-    const int sw = lane & 7;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      uint4 u = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-      *reinterpret_cast<uint4*>(stile + lane * 128 + ((c ^ sw) << 4)) = u;
-    }
-  }
-  __syncwarp();
-  const int c = lane & 7;
-  const int gcol = col0 + c * 4;
-  const bool col_ok = gcol < p.N;
-  float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-  if (p.bias != nullptr && col_ok) {
-    uint2 u = __ldg(reinterpret_cast<const uint2*>(p.bias + gcol));
-    b0 = bf16_lo(u.x); b1 = bf16_hi(u.x); b2 = bf16_lo(u.y); b3 = bf16_hi(u.y);
-  }
-  // gate: all loads first (tiny table, L1/L2 resident), then compute + store
-  float4 g[8];
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int grow = row0 + it * 4 + (lane >> 3);
-    g[it] = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (p.gate != nullptr && grow < p.M && col_ok) {
-      const int bidx = grow / p.rows_per_batch;
-      g[it] = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)bidx * p.gate_batch_stride + gcol));
-    }
-  }
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int r = it * 4 + (lane >> 3);
-    const int grow = row0 + r;
-    const float4 a = *reinterpret_cast<const float4*>(stile + r * 128 + ((c ^ (r & 7)) << 4));
-    if (grow < p.M && col_ok) {
-      const size_t off = (size_t)grow * p.ldo + gcol;
-      float4 o;
-      o.x = fmaf(g[it].x, a.x + b0, res.r[it].x);
-      o.y = fmaf(g[it].y, a.y + b1, res.r[it].y);
-      o.z = fmaf(g[it].z, a.z + b2, res.r[it].z);
-      o.w = fmaf(g[it].w, a.w + b3, res.r[it].w);
-      if constexpr (sizeof(OutT) == 4) {
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = o;
-      } else {
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) =
-            make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
-      }
-      if (p.out_aux != nullptr) {
-        *reinterpret_cast<uint2*>(p.out_aux + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
-      }
-    }
-  }
-  __syncwarp();
-}
 
 // ------------------------------------------------------------------------------------------------- kernel
 template <int BN, int EPI, typename OutT>
