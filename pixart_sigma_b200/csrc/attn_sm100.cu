@@ -323,7 +323,13 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         pk[16 + i] = pack_bf16x2(b0, b1);
       }
       if (j == 0 && t == 0) {
-        asm volatile("" ::"r"(pk[0]), "r"(pk[15]), "r"(pk[16]), "r"(pk[31]) : "memory");   // exp2 results exist
+        // every exp2 result of this thread exists before the hand-off (keeps the compiler from sinking exp2 below it)
+        asm volatile("" ::"r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]),
+                     "r"(pk[8]), "r"(pk[9]), "r"(pk[10]), "r"(pk[11]), "r"(pk[12]), "r"(pk[13]), "r"(pk[14]), "r"(pk[15]),
+                     "r"(pk[16]), "r"(pk[17]), "r"(pk[18]), "r"(pk[19]), "r"(pk[20]), "r"(pk[21]), "r"(pk[22]),
+                     "r"(pk[23]), "r"(pk[24]), "r"(pk[25]), "r"(pk[26]), "r"(pk[27]), "r"(pk[28]), "r"(pk[29]),
+                     "r"(pk[30]), "r"(pk[31])
+                     : "memory");
         mbar_arrive(&exp_turn[1]);                             // releases tile B's first exp2 section
       }
       // P (bf16, this half's 64 keys = 32 packed columns) over the first 32 of this half's own S columns

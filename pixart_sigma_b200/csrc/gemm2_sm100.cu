@@ -1,0 +1,302 @@
+// 2-CTA (cta_group::2) variant of pxa_gemm_bf16: a CTA pair on one TPC computes a 256 x BN tile.
+//
+// Each CTA stages its own 128 rows of A and its own BN/2 rows of W per K-block, so per-SM operand traffic from L2 and
+// through shared memory drops from (128 + BN) to (128 + BN/2) rows per 128xBNx64 of MMA work (-30 % at BN = 192); the
+// leader CTA's single elected thread issues tcgen05.mma.cta_group::2 (UMMA 256 x BN x 16) which reads both CTAs'
+// shared memory and writes each CTA's half of the accumulator into that CTA's own TMEM.
+//
+//   rank 0 (leader)                                   rank 1
+//   warp 0  TMA: A[m0..+128], W[n0..+BN/2]            TMA: A[m0+128..+128], W[n0+BN/2..+BN/2]
+//           both signal complete_tx on the LEADER's full barrier (peer bit of the mbarrier address cleared)
+//   warp 1  MMA issue + tcgen05.commit multicast      (idle)
+//           -> empty[stage] and tmem_full[] of BOTH CTAs
+//   warp 2  tcgen05.alloc.cta_group::2 (both CTAs, same warp id)
+//   warps 4-7 epilogue of the CTA's own 128 rows; tmem_empty is the leader's barrier (256 arrivals, peer arrives
+//           through mapa / shared::cluster)
+#include "gemm_common.cuh"
+
+namespace pxa {
+
+template <int BN> struct Gemm2Cfg {
+  static constexpr int kStageA = kBM * kBK * 2;                 // 16 KB: this CTA's 128 rows of A
+  static constexpr int kStageB = (BN / 2) * kBK * 2;            // this CTA's BN/2 rows of W
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kEpiSmem = 4 * 32 * 32 * 4;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kStages = (227 * 1024 - kEpiSmem - kBarBytes - 1024) / kStage > 8
+                                     ? 8 : (227 * 1024 - kEpiSmem - kBarBytes - 1024) / kStage;
+  static constexpr int kSmem = kStages * kStage + kEpiSmem + kBarBytes + 1024;
+  static constexpr uint32_t kTmemCols = (2 * BN <= 256) ? 256 : 512;
+};
+
+PXA_DEVICE uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+PXA_DEVICE void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> rank 0
+
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (executed by both CTAs of the pair).
+PXA_DEVICE void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar_local, int c0, int c1, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar_local) & kPeerBitMask), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+PXA_DEVICE void umma2_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on the barrier at this smem offset in every CTA of `mask` once all prior tcgen05 ops of this thread are done.
+PXA_DEVICE void umma2_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+// Arrive on the barrier at the same smem offset in CTA `rank` of the cluster.
+PXA_DEVICE void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+template <uint32_t kCols> PXA_DEVICE void tmem_alloc_pair(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(dst_smem)), "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+}
+template <uint32_t kCols> PXA_DEVICE void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "n"(kCols) : "memory");
+}
+
+template <int BN, int EPI, typename OutT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                  const __grid_constant__ CUtensorMap tmap_res, const GemmParams p) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi_smem = smem + kStages * Cfg::kStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Cfg::kEpiSmem);
+  uint64_t* full_bar = bars;                      // [kStages] leader's is the live one: both CTAs' TMA bytes land here
+  uint64_t* empty_bar = bars + kStages;           // [kStages] per CTA: leader's MMA commit (multicast) frees the slot
+  uint64_t* tfull_bar = bars + 2 * kStages;       // [2] per CTA: accumulator ready (multicast commit)
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2] leader's: 256 arrivals (both CTAs' epilogue threads)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = warp_idx_sync();
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_w);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 2 * kNumEpiThreads);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();               // barriers of BOTH CTAs are initialised before anybody signals remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;      // tiles of 256 x BN, one per cluster at a time
+  const int num_kb = (p.K + kBK - 1) / kBK;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer (both CTAs)
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile / p.num_n_tiles) * (2 * kBM) + rank * kBM;
+        const int n0 = (tile % p.num_n_tiles) * BN;
+        if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) tma_prefetch_l2_2d(&tmap_res, n0, m0);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStage;
+          uint8_t* sb = sa + Cfg::kStageA;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStage);   // bytes of both CTAs
+          tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * kBK, m0, kEvictNormal);
+          tma_load_2d_pair(sb, &tmap_w, &full_bar[stage], kb * kBK, n0 + rank * (BN / 2), kEvictLast);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (leader CTA only)
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * kBM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStage);
+          const uint64_t adesc = make_smem_desc(sa, 16, 1024, kLayoutSW128);
+          const uint64_t bdesc = make_smem_desc(sa + Cfg::kStageA, 16, 1024, kLayoutSW128);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            umma2_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma2_commit_mc(&empty_bar[stage], 0x3);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma2_commit_mc(&tfull_bar[as], 0x3);
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ================================================================ epilogue (both CTAs, own 128 rows)
+    const int q = warp & 3;
+    uint8_t* stile = epi_smem + (warp - kEpiWarp0) * 4096;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m0 = (tile / p.num_n_tiles) * (2 * kBM) + rank * kBM;
+      const int n0 = (tile % p.num_n_tiles) * BN;
+      ResFrag res_next;
+      if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) load_residual_frag<OutT>(res_next, p, lane, m0 + q * 32, n0);
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        ResFrag res_cur;
+        if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
+          res_cur = res_next;
+          if (cc + 1 < BN / 32 && n0 + (cc + 1) * 32 < p.N)
+            load_residual_frag<OutT>(res_next, p, lane, m0 + q * 32, n0 + (cc + 1) * 32);
+        }
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_acc + cc * 32, v);
+        if (cc == BN / 32 - 1) {
+          tc_fence_before();
+          mbar_arrive_cluster(&tempty_bar[as], 0);       // the leader's MMA thread owns the accumulator hand-off
+        }
+        if (n0 + cc * 32 < p.N) {
+          if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL)
+            epilogue_chunk_residual<OutT>(v, res_cur, p, stile, lane, m0 + q * 32, n0 + cc * 32);
+          else
+            epilogue_chunk_bf16<EPI>(v, p, stile, lane, m0 + q * 32, n0 + cc * 32);
+        }
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();               // nobody may exit (or free TMEM) while the peer can still touch this CTA's smem
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN, int EPI, typename OutT>
+static int launch_gemm2(const PxaGemmArgs& a, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  CUtensorMap ta, tw;
+  {
+    uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
+    uint64_t str[1] = {(uint64_t)a.lda * 2};
+    uint32_t box[2] = {kBK, kBM};
+    int rc = make_tmap_bf16(&ta, a.a, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.N};
+    uint64_t str[1] = {(uint64_t)a.ldw * 2};
+    uint32_t box[2] = {kBK, (uint32_t)(BN / 2)};
+    int rc = make_tmap_bf16(&tw, a.w, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  CUtensorMap tr = ta;
+  if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
+    uint64_t dims[2] = {(uint64_t)a.N, (uint64_t)a.M};
+    uint64_t str[1] = {(uint64_t)a.ldo * sizeof(OutT)};
+    uint32_t box[2] = {(uint32_t)BN, kBM};
+    int rc = make_tmap(&tr, sizeof(OutT) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                       a.residual, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+  }
+  GemmParams p;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(a.bias);
+  p.out = a.out;
+  p.out_aux = reinterpret_cast<__nv_bfloat16*>(a.out_aux_bf16);
+  p.residual = a.residual;
+  p.gate = a.gate;
+  p.gate_batch_stride = a.gate_batch_stride;
+  p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : a.M;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.ldo = a.ldo;
+  p.num_m_tiles = (a.M + 2 * kBM - 1) / (2 * kBM);
+  p.num_n_tiles = (a.N + BN - 1) / BN;
+  auto kern = gemm2_bf16_kernel<BN, EPI, OutT>;
+  PXA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+  int clusters = device_info().sms / 2;
+  if (a.max_ctas > 0 && a.max_ctas / 2 < clusters) clusters = a.max_ctas / 2 > 0 ? a.max_ctas / 2 : 1;
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  if (tiles < clusters) clusters = tiles;
+  kern<<<2 * clusters, kGemmThreads, Cfg::kSmem, stream>>>(ta, tw, tr, p);
+  launch_counter()++;
+  PXA_CHECK_CUDA(cudaGetLastError());
+  return PXA_OK;
+}
+
+template <int BN>
+static int dispatch_epi2(const PxaGemmArgs& a, cudaStream_t s) {
+  switch (a.epilogue) {
+    case PXA_EPI_BIAS:
+      return launch_gemm2<BN, PXA_EPI_BIAS, __nv_bfloat16>(a, s);
+    case PXA_EPI_BIAS_GELU:
+      return launch_gemm2<BN, PXA_EPI_BIAS_GELU, __nv_bfloat16>(a, s);
+    case PXA_EPI_BIAS_RESIDUAL:
+      if (a.out_dtype == PXA_DTYPE_F32) return launch_gemm2<BN, PXA_EPI_BIAS_RESIDUAL, float>(a, s);
+      return launch_gemm2<BN, PXA_EPI_BIAS_RESIDUAL, __nv_bfloat16>(a, s);
+    default:
+      return fail(PXA_ERR_ARG, "unknown epilogue %d", a.epilogue);
+  }
+}
+
+// Called by pxa_gemm_bf16 after argument validation when the CTA-pair path is selected.
+int gemm_pair_dispatch(const PxaGemmArgs& a, int bn, cudaStream_t s) {
+  switch (bn) {
+    case 128: return dispatch_epi2<128>(a, s);
+    case 192: return dispatch_epi2<192>(a, s);
+    case 256: return dispatch_epi2<256>(a, s);
+    default: return fail(PXA_ERR_ARG, "block_n must be 128, 192 or 256 (got %d)", bn);
+  }
+}
+
+}  // namespace pxa

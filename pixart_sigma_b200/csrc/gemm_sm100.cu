@@ -232,6 +232,8 @@ static int dispatch_epi(const PxaGemmArgs& a, cudaStream_t s) {
   }
 }
 
+int gemm_pair_dispatch(const PxaGemmArgs& a, int bn, cudaStream_t s);   // gemm2_sm100.cu
+
 }  // namespace pxa
 
 extern "C" int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream) {
@@ -252,6 +254,12 @@ extern "C" int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream) {
   int bn = a.block_n;
   if (bn == 0) bn = (a.N % 192 == 0) ? 192 : ((a.N % 256 == 0) ? 256 : (a.N >= 192 ? 192 : 128));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (a.epilogue == PXA_EPI_BIAS_RESIDUAL && a.residual == nullptr) return fail(PXA_ERR_ARG, "EPI_BIAS_RESIDUAL needs residual");
+  if (a.epilogue != PXA_EPI_BIAS_RESIDUAL && a.out_dtype != PXA_DTYPE_BF16)
+    return fail(PXA_ERR_ARG, "EPI_BIAS / EPI_BIAS_GELU write bf16 only");
+  if (a.cta_pair < 0 || a.cta_pair > 2) return fail(PXA_ERR_ARG, "cta_pair must be 0, 1 or 2");
+  const bool pair = a.cta_pair == 2;       // auto (0) currently selects the single-CTA kernel
+  if (pair) return gemm_pair_dispatch(a, bn, s);
   switch (bn) {
     case 128: return dispatch_epi<128>(a, s);
     case 192: return dispatch_epi<192>(a, s);

@@ -38,6 +38,33 @@ def test_gemm_bias_bf16(M, N, K, bn):
     assert po.rel_err(out.float(), want) < 4e-3
 
 
+@pytest.mark.parametrize("M,N,K,bn", [(256, 192, 64, 192), (512, 384, 1152, 192), (1000, 1152, 1152, 192),
+                                      (4096, 3456, 1152, 192), (300, 2304, 1152, 0), (640, 4608, 1152, 256),
+                                      (384, 256, 128, 128), (200, 200, 200, 192)])
+def test_gemm_cta_pair_bias_bf16(M, N, K, bn):
+    """CTA-pair (tcgen05.mma.cta_group::2, 256 x BN tiles) variant of the same GEMM."""
+    a, w, bias = _randn(M, K, seed=1), _randn(N, K, seed=2, scale=K ** -0.5), _randn(N, seed=3, scale=0.1)
+    out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV)
+    lib.gemm(a, w, bias, out, epilogue=lib.EPI_BIAS, block_n=bn, cta_pair=2)
+    want = F.linear(a.float(), w.float(), bias.float())
+    assert po.rel_err(out.float(), want) < 4e-3
+
+
+def test_gemm_cta_pair_many_tiles_gelu_and_residual():
+    M, N, K = 2048, 1152, 1152
+    a, w, bias = _randn(M, K, seed=4), _randn(N, K, seed=5, scale=K ** -0.5), _randn(N, seed=6, scale=0.1)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    lib.gemm(a, w, bias, out, epilogue=lib.EPI_BIAS_GELU, max_ctas=6, cta_pair=2)     # 3 clusters walk 8 x 6 tiles
+    want = F.gelu(F.linear(a.float(), w.float(), bias.float()), approximate="tanh")
+    assert po.rel_err(out.float(), want) < 4e-3
+    x = _randn(M, N, seed=7, dtype=torch.float32)
+    gate = _randn(2, 6, N, seed=8, dtype=torch.float32)
+    want = x + gate[:, 2].repeat_interleave(M // 2, 0) * F.linear(a.float(), w.float(), bias.float())
+    lib.gemm(a, w, bias, x, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x, gate=gate[:, 2], gate_batch_stride=6 * N,
+             rows_per_batch=M // 2, cta_pair=2)
+    assert po.rel_err(x, want) < 2e-4
+
+
 def test_gemm_many_tiles_per_cta_and_no_bias():
     """3 CTAs walk 8x6 tiles: exercises smem-ring / TMEM double-buffer phase wrap-around."""
     M, N, K = 1024, 1152, 1152

@@ -6,7 +6,7 @@ from pixart_sigma_b200 import lib
 
 M = 32768
 dev = "cuda"
-def run(N, K, epi, bn, iters=20):
+def run(N, K, epi, bn, pair=1, iters=20):
     a = torch.randn(M, K, device=dev).to(torch.bfloat16)
     w = (torch.randn(N, K, device=dev) * K ** -0.5).to(torch.bfloat16)
     b = torch.randn(N, device=dev).to(torch.bfloat16)
@@ -17,11 +17,11 @@ def run(N, K, epi, bn, iters=20):
     else:
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     for _ in range(3):
-        lib.gemm(a, w, b, out, epilogue=epi, block_n=bn, **kw)
+        lib.gemm(a, w, b, out, epilogue=epi, block_n=bn, cta_pair=pair, **kw)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        lib.gemm(a, w, b, out, epilogue=epi, block_n=bn, **kw)
+        lib.gemm(a, w, b, out, epilogue=epi, block_n=bn, cta_pair=pair, **kw)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     return ms, 2 * M * N * K / ms / 1e9
@@ -31,5 +31,6 @@ for (N, K, epi) in [(3456, 1152, 0), (1152, 1152, 0), (1152, 1152, 2), (4608, 11
     for bn in (128, 192, 256):
         if N % bn and bn != 192:
             pass
-        ms, tf = run(N, K, epi, bn)
-        print(f"N={N:5d} K={K:5d} {names[epi]:5s} BN={bn:3d}: {ms*1e3:8.1f} us  {tf:7.1f} TFLOP/s", flush=True)
+        for pair in (1, 2):
+            ms, tf = run(N, K, epi, bn, pair)
+            print(f"N={N:5d} K={K:5d} {names[epi]:5s} BN={bn:3d} {'pair' if pair == 2 else '1cta'}: {ms*1e3:8.1f} us  {tf:7.1f} TFLOP/s", flush=True)
