@@ -311,6 +311,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         mbar_wait(&exp_turn[1], 0);
         // the exp2 below are plain register math: tie them to the wait so the compiler cannot hoist them above it
         asm volatile("" : "+f"(neg_m_dep)::"memory");
+        if (tracing) p.trace[w * kTraceMax + 500] = clock64();     // tile B released
       }
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -331,6 +332,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
                      "r"(pk[30]), "r"(pk[31])
                      : "memory");
         mbar_arrive(&exp_turn[1]);                             // releases tile B's first exp2 section
+        if (tracing) p.trace[w * kTraceMax + 501] = clock64();     // tile A handed over
       }
       // P (bf16, this half's 64 keys = 32 packed columns) over the first 32 of this half's own S columns
       tmem_st_32x32b_x32(t_s, pk);

@@ -23,13 +23,21 @@ struct GemmParams {
   int num_m_tiles, num_n_tiles;
 };
 
-template <int BN> struct GemmCfg {
+constexpr int kResBufs = 3;
+constexpr int kResChunkBytes = 128 * 32 * 4;     // 16 KB: 128 rows x 32 fp32 columns
+constexpr int kAuxChunkBytes = 128 * 32 * 2;     // 8 KB
+constexpr int kResEpiSmem = kResBufs * kResChunkBytes + 2 * kAuxChunkBytes;   // 64 KB
+constexpr int kSmemBudget = 227 * 1024;
+
+// kTmaRes: fp32 residual epilogue streamed through smem by TMA (see the end of this file)
+template <int BN, bool kTmaRes = false> struct GemmCfg {
   static constexpr int kStageA = kBM * kBK * 2;                 // 16 KB
   static constexpr int kStageB = BN * kBK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
-  static constexpr int kEpiSmem = 4 * 32 * 32 * 4;              // 4 epilogue warps x (32 rows x 128 B)
+  static constexpr int kEpiSmem = kTmaRes ? kResEpiSmem : 4 * 32 * 32 * 4;   // else 4 epilogue warps x (32 rows x 128 B)
   static constexpr int kBarBytes = 256;
+  static constexpr int kMaxStages = (kSmemBudget - kEpiSmem - kBarBytes - 1024) / kStage;
+  static constexpr int kStages = kMaxStages > 6 ? 6 : kMaxStages;
   static constexpr int kSmem = kStages * kStage + kEpiSmem + kBarBytes + 1024;  // +1024 alignment slack
   static constexpr uint32_t kTmemCols = (2 * BN <= 256) ? 256 : 512;
 };
@@ -179,6 +187,76 @@ PXA_DEVICE void epilogue_chunk_residual(uint32_t (&v)[32], const ResFrag& res, c
     }
   }
   __syncwarp();
+}
+
+
+// ------------------------------------------------------------------------------------------------- TMA residual epilogue
+// fp32 residual stream: out = residual + gate * (acc + bias), the residual tile streamed global -> smem and the result
+// smem -> global by TMA in 128-row x 32-column chunks (kResBufs chunk buffers, loads issued kResBufs-1 chunks ahead,
+// across tile boundaries).  This keeps ~32-48 KB of residual reads in flight per SM without holding registers, which
+// the register-prefetch version could not (Little's law: 16 KB in flight per SM capped it at ~2.4 TB/s chip-wide).
+// Row-per-thread all the way: no transpose, TMA clips the M / N tails.  Chunk buffers use the 128B TMA swizzle so the
+// row-per-thread 16-byte accesses are bank-conflict free; the optional bf16 aux copy uses a 64B-swizzled buffer.
+struct ResTileCursor {      // walks the (tile, chunk) sequence of this CTA
+  int tile, cc;
+};
+
+template <int BN>
+PXA_DEVICE int chunks_of_tile(const GemmParams& p, int n0) {
+  const int rem = (p.N - n0 + 31) / 32;
+  return rem < BN / 32 ? rem : BN / 32;
+}
+
+// One chunk for the calling thread (row `r` of the 128-row tile): v = acc of 32 columns.
+PXA_DEVICE void residual_chunk_row(uint32_t (&v)[32], const GemmParams& p, uint8_t* rbuf, uint8_t* abuf, int r, int grow,
+                                   int col0) {
+  // bias / gate: 32 consecutive columns, same for the whole warp except across a sample boundary (L1 broadcast hits)
+  float b[32];
+  if (p.bias != nullptr) {
+    const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 u = make_uint4(0u, 0u, 0u, 0u);
+      if (col0 + 8 * i < p.N) u = __ldg(bp + i);
+      b[8 * i + 0] = bf16_lo(u.x); b[8 * i + 1] = bf16_hi(u.x);
+      b[8 * i + 2] = bf16_lo(u.y); b[8 * i + 3] = bf16_hi(u.y);
+      b[8 * i + 4] = bf16_lo(u.z); b[8 * i + 5] = bf16_hi(u.z);
+      b[8 * i + 6] = bf16_lo(u.w); b[8 * i + 7] = bf16_hi(u.w);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) b[i] = 0.f;
+  }
+  const float* gp = nullptr;
+  if (p.gate != nullptr) {
+    const int row_c = grow < p.M ? grow : p.M - 1;
+    gp = p.gate + (size_t)(row_c / p.rows_per_batch) * p.gate_batch_stride + col0;
+  }
+  const int sw = r & 7;
+  uint8_t* rrow = rbuf + r * 128;
+  uint32_t aux[16];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (gp != nullptr && col0 + 4 * c < p.N) g = __ldg(reinterpret_cast<const float4*>(gp + 4 * c));
+    float4* slot = reinterpret_cast<float4*>(rrow + ((c ^ sw) << 4));
+    const float4 res = *slot;
+    float4 o;
+    o.x = fmaf(g.x, __uint_as_float(v[4 * c + 0]) + b[4 * c + 0], res.x);
+    o.y = fmaf(g.y, __uint_as_float(v[4 * c + 1]) + b[4 * c + 1], res.y);
+    o.z = fmaf(g.z, __uint_as_float(v[4 * c + 2]) + b[4 * c + 2], res.z);
+    o.w = fmaf(g.w, __uint_as_float(v[4 * c + 3]) + b[4 * c + 3], res.w);
+    *slot = o;
+    aux[2 * c] = pack_bf16x2(o.x, o.y);
+    aux[2 * c + 1] = pack_bf16x2(o.z, o.w);
+  }
+  if (abuf != nullptr) {
+    const int sw2 = (r >> 1) & 3;
+    uint8_t* arow = abuf + r * 64;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<uint4*>(arow + ((c ^ sw2) << 4)) = make_uint4(aux[4 * c], aux[4 * c + 1], aux[4 * c + 2], aux[4 * c + 3]);
+  }
 }
 
 }  // namespace pxa

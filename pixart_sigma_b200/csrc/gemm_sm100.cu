@@ -19,8 +19,10 @@ namespace pxa {
 template <int BN, int EPI, typename OutT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                 const __grid_constant__ CUtensorMap tmap_res, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+                 const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out,
+                 const __grid_constant__ CUtensorMap tmap_aux, const GemmParams p) {
+  constexpr bool kTmaRes = (EPI == PXA_EPI_BIAS_RESIDUAL) && sizeof(OutT) == 4;
+  using Cfg = GemmCfg<BN, kTmaRes>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -30,7 +32,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* empty_bar = bars + kStages;         // [kStages]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * kStages;     // [2]        MMA -> epilogue
   uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]      epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* res_full = bars + 2 * kStages + 4;    // [kResBufs] TMA residual chunk landed (kTmaRes only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4 + kResBufs);
 
   const int warp = warp_idx_sync();
   const int lane = threadIdx.x & 31;
@@ -46,6 +49,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], kNumEpiThreads);
     }
+    for (int s = 0; s < kResBufs; ++s) mbar_init(&res_full[s], 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -67,7 +71,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int n0 = (tile % p.num_n_tiles) * BN;
         if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
           // pull this tile's residual block into L2 now: the epilogue reads it one mainloop (~7k cycles) later
-          tma_prefetch_l2_2d(&tmap_res, n0, m0);
+          if constexpr (kTmaRes) {
+            for (int c = 0; c < BN / 32; ++c) tma_prefetch_l2_2d(&tmap_res, n0 + c * 32, m0);
+          } else {
+            tma_prefetch_l2_2d(&tmap_res, n0, m0);
+          }
         }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -114,9 +122,65 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp >= kEpiWarp0) {
     // ================================================================ epilogue
     const int q = warp & 3;                         // TMEM sub-partition of this warp
-    uint8_t* stile = epi_smem + (warp - kEpiWarp0) * 4096;
     int as = 0;
     uint32_t aphase = 0;
+    if constexpr (kTmaRes) {
+      // ---- fp32 residual stream: residual in / result out through smem chunk buffers by TMA (gemm_common.cuh)
+      const int r = q * 32 + lane;                                  // row of the 128-row tile owned by this thread
+      uint8_t* rbufs = epi_smem;
+      uint8_t* abufs = epi_smem + kResBufs * kResChunkBytes;
+      const bool issuer = (warp == kEpiWarp0) && (lane == 0);       // owns every TMA op of the epilogue
+      int l_tile = blockIdx.x, l_cc = 0, l_g = 0;                   // issuer: next residual chunk to request
+      auto request_next = [&]() {
+        if (l_tile >= num_tiles) return;
+        const int lm0 = (l_tile / p.num_n_tiles) * kBM;
+        const int ln0 = (l_tile % p.num_n_tiles) * BN;
+        const int buf = l_g % kResBufs;
+        mbar_arrive_expect_tx(&res_full[buf], kResChunkBytes);
+        tma_load_2d(rbufs + buf * kResChunkBytes, &tmap_res, &res_full[buf], ln0 + l_cc * 32, lm0, kEvictFirst);
+        ++l_g;
+        if (++l_cc == chunks_of_tile<BN>(p, ln0)) { l_cc = 0; l_tile += gridDim.x; }
+      };
+      if (issuer) {
+        for (int i = 0; i < kResBufs - 1; ++i) request_next();
+      }
+      int g = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.num_n_tiles) * kBM;
+        const int n0 = (tile % p.num_n_tiles) * BN;
+        const int nch = chunks_of_tile<BN>(p, n0);
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        const uint32_t t_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+        for (int cc = 0; cc < nch; ++cc, ++g) {
+          const int buf = g % kResBufs;
+          uint8_t* rb = rbufs + buf * kResChunkBytes;
+          uint8_t* ab = p.out_aux != nullptr ? abufs + (g & 1) * kAuxChunkBytes : nullptr;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_acc + cc * 32, v);
+          if (cc == nch - 1) {
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[as]);
+          }
+          mbar_wait(&res_full[buf], (g / kResBufs) & 1);           // residual chunk has landed in smem
+          residual_chunk_row(v, p, rb, ab, r, m0 + r, n0 + cc * 32);
+          fence_proxy_async_smem();                                 // generic-proxy writes -> visible to the TMA store
+          if (issuer) tma_store_wait_read<0>();                     // earlier stores have drained their buffers
+          named_bar_sync(1, kNumEpiThreads);
+          if (issuer) {
+            tma_store_2d(&tmap_out, rb, n0 + cc * 32, m0);
+            if (ab != nullptr) tma_store_2d(&tmap_aux, ab, n0 + cc * 32, m0);
+            tma_store_commit();
+            request_next();                                         // refills the buffer chunk g-1 has just left
+          }
+        }
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+      if (issuer) tma_store_wait_all<0>();
+    } else {
+    uint8_t* stile = epi_smem + (warp - kEpiWarp0) * 4096;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.num_n_tiles) * kBM;
       const int n0 = (tile % p.num_n_tiles) * BN;
@@ -153,6 +217,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
+    }
   }
 
   tc_fence_before();
@@ -166,7 +231,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // ------------------------------------------------------------------------------------------------- host
 template <int BN, int EPI, typename OutT>
 static int launch_gemm(const PxaGemmArgs& a, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
   CUtensorMap ta, tw;
   {
     uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
@@ -182,14 +246,28 @@ static int launch_gemm(const PxaGemmArgs& a, cudaStream_t stream) {
     int rc = make_tmap_bf16(&tw, a.w, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  CUtensorMap tr = ta;   // unused unless EPI_BIAS_RESIDUAL
+  constexpr bool kTmaRes = (EPI == PXA_EPI_BIAS_RESIDUAL) && sizeof(OutT) == 4;
+  using Cfg = GemmCfg<BN, kTmaRes>;
+  CUtensorMap tr = ta, to = ta, tx = ta;   // residual / out / aux maps: only meaningful for EPI_BIAS_RESIDUAL
   if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
     uint64_t dims[2] = {(uint64_t)a.N, (uint64_t)a.M};
     uint64_t str[1] = {(uint64_t)a.ldo * sizeof(OutT)};
-    uint32_t box[2] = {(uint32_t)BN, kBM};
-    int rc = make_tmap(&tr, sizeof(OutT) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                       a.residual, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
-    if (rc) return rc;
+    if constexpr (kTmaRes) {
+      uint32_t box[2] = {32, kBM};         // 32 fp32 = 128 B rows: one TMA 128B-swizzle atom per row
+      int rc = make_tmap(&tr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a.residual, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+      rc = make_tmap(&to, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a.out, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+      if (a.out_aux_bf16 != nullptr) {
+        uint64_t astr[1] = {(uint64_t)a.ldo * 2};
+        rc = make_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.out_aux_bf16, 2, dims, astr, box, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+      }
+    } else {
+      uint32_t box[2] = {(uint32_t)BN, kBM};   // L2 prefetch only
+      int rc = make_tmap(&tr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.residual, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+      if (rc) return rc;
+    }
   }
   GemmParams p;
   p.bias = reinterpret_cast<const __nv_bfloat16*>(a.bias);
@@ -208,7 +286,7 @@ static int launch_gemm(const PxaGemmArgs& a, cudaStream_t stream) {
   if (a.max_ctas > 0 && a.max_ctas < grid) grid = a.max_ctas;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   if (tiles < grid) grid = tiles;
-  kern<<<grid, kGemmThreads, Cfg::kSmem, stream>>>(ta, tw, tr, p);
+  kern<<<grid, kGemmThreads, Cfg::kSmem, stream>>>(ta, tw, tr, to, tx, p);
   launch_counter()++;
   PXA_CHECK_CUDA(cudaGetLastError());
   return PXA_OK;
@@ -258,7 +336,13 @@ extern "C" int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream) {
   if (a.epilogue != PXA_EPI_BIAS_RESIDUAL && a.out_dtype != PXA_DTYPE_BF16)
     return fail(PXA_ERR_ARG, "EPI_BIAS / EPI_BIAS_GELU write bf16 only");
   if (a.cta_pair < 0 || a.cta_pair > 2) return fail(PXA_ERR_ARG, "cta_pair must be 0, 1 or 2");
-  const bool pair = a.cta_pair == 2;       // auto (0) currently selects the single-CTA kernel
+  // auto: the CTA pair pays off for wide outputs (measured +3..9 % at N >= 2304, M = 32768); narrow-N GEMMs and the
+  // residual epilogues stay on the single-CTA kernel
+  bool pair = a.cta_pair == 2;
+  if (a.cta_pair == 0 && a.block_n == 0 && a.epilogue != PXA_EPI_BIAS_RESIDUAL && a.N >= 2304 && a.M >= 2048) {
+    pair = true;
+    bn = 256;
+  }
   if (pair) return gemm_pair_dispatch(a, bn, s);
   switch (bn) {
     case 128: return dispatch_epi<128>(a, s);

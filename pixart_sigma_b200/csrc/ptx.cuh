@@ -79,6 +79,17 @@ PXA_DEVICE void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* ba
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
+// smem -> global tile store (bulk-group completion) and its group bookkeeping
+PXA_DEVICE void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+PXA_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int kN> PXA_DEVICE void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(kN) : "memory"); }
+template <int kN> PXA_DEVICE void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;\n" ::"n"(kN) : "memory"); }
+
 // Pull a 2-D tile into L2 only (no smem destination, no barrier).
 PXA_DEVICE void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(reinterpret_cast<uint64_t>(map)),

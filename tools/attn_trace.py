@@ -28,6 +28,7 @@ for w, nm in names.items():
         row = [int(v) - t0 for v in tr[w, 5 * j:5 * j + 5]]
         d = [row[i + 1] - row[i] for i in range(4)]
         print(f"  {nm} j={j}: {row}  d(waitS,ld,xchg,exp+st)={d}")
+print("stagger stamps: A arrive", [int(tr[w,501])-t0 for w in (0,4)], " B released", [int(tr[w,500])-t0 for w in (8,12)])
 print("MMA thread per block j: [wait P_A | P_A ready | wait P_B | P_B ready]")
 for j in range(0, 10):
     row = [int(v) - t0 for v in tr[16, 4 * j:4 * j + 4]]
