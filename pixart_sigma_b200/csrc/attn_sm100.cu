@@ -5,12 +5,17 @@
 // the next Q_B K^T).  640 threads:
 //   warp 0      TMA producer: Q once, then K / V blocks of 128 keys into two 3-deep smem rings
 //   warp 1      MMA issuer (one thread): S = Q K^T (SS), O += P V (TS: P read from TMEM)
-//   warp 2      TMEM allocator (512 columns: S_A | S_B | O_A | O_B)
+//   warp 2      TMEM allocator (512 columns: S_A | S_B | O_A | O_B | one P buffer shared by both tiles)
 //   warps 4-19  softmax: per tile two warpgroups, "lo" owns keys 0..63 and "hi" keys 64..127 of every block, so a
 //               query row is shared by a thread pair (64 S values each; row max exchanged through smem once per
 //               block).  4 softmax warps per SM sub-partition keep the MUFU fed while others wait on TMEM / barriers.
-//               Online softmax in fp32 with lazy rescaling of O (only when the running max grows by > 2^8), P written
-//               back to TMEM as bf16 over each half's own S columns, final O / rowsum -> bf16 -> global
+//               Online softmax in fp32 with lazy rescaling of O (only when the running max grows by > 2^8), final
+//               O / rowsum -> bf16 -> global.
+// Pipeline: P (bf16) does NOT alias S.  As soon as the softmax threads hold S_t(j) in registers they release S_t
+// (s_free) and the MMA thread issues Q_t K(j+1)^T while the exp2 of block j is still running, so the next S is ready
+// before it is needed and the MUFU (exp2) pipe -- the bottleneck resource at head_dim 72 -- never waits for the
+// tensor pipe.  TMEM has room for only ONE 64-column P buffer next to 2 x S and 2 x O; the two tiles take turns
+// (p_free), which also staggers them by half a block so that their exp2 sections alternate.
 //
 // head_dim 72 is not a multiple of the 64-element swizzle atom, nor of UMMA K=16 / N%16: each Q/K/V tile is staged
 // as a "main" part (d 0..63, 128B swizzle) plus a "tail" part (d 64..79, 32B swizzle) whose d 72..79 are zero-filled
@@ -45,8 +50,10 @@ constexpr int kOffXchg = kOffBars + 256;                            // float [2 
 constexpr int kAttnSmem = kOffXchg + 2 * 2 * 2 * 128 * 4 + 1024;
 
 // TMEM columns
-constexpr uint32_t kColS = 0;       // S_A at 0, S_B at 128; P (bf16) aliases S: keys 0..63 -> cols [0,32), keys 64..127 -> [64,96)
-constexpr uint32_t kColO = 256;     // O_A at 256 (main 64 + tail 16), O_B at 384
+constexpr uint32_t kColS = 0;       // S_A at 0, S_B at 128 (fp32, 128 keys each)
+constexpr uint32_t kColO = 256;     // O main (d 0..63, fp32): tile A at 256, tile B at 320
+constexpr uint32_t kColOT = 384;    // O tail (d 64..79): tile A at 384, tile B at 400
+constexpr uint32_t kColP = 416;     // shared P buffer: 128 keys bf16 = 64 columns (lo half 416..447, hi half 448..479)
 
 struct AttnParams {
   __nv_bfloat16* out;
@@ -80,8 +87,10 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
   uint64_t* s_full = v_empty + kKVStages;     // [2]  MMA -> softmax (S ready; also implies previous PV done)
   uint64_t* p_full = s_full + 2;              // [2]  softmax -> MMA (P written, S consumed)
   uint64_t* o_full = p_full + 2;              // [1]  MMA -> softmax (all PV done)
-  uint64_t* exp_turn = o_full + 1;            // [2]  softmax A <-> softmax B: serialises the two tiles' exp2 sections
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(exp_turn + 2);
+  uint64_t* s_free = o_full + 1;              // [2]  softmax -> MMA (S_t is in registers, may be overwritten)
+  uint64_t* pv_done = s_free + 2;             // [2]  MMA -> softmax (P_t V of a block has completed: O_t may be rescaled)
+  uint64_t* p_free = pv_done + 2;             // [1]  MMA -> softmax (shared P buffer consumed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 1);
 
   const int warp = warp_idx_sync();
   const int lane = threadIdx.x & 31;
@@ -109,8 +118,11 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       mbar_init(&p_full[t], 256);
     }
     mbar_init(o_full, 1);
-    mbar_init(&exp_turn[0], 256);
-    mbar_init(&exp_turn[1], 256);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_free[t], 256);
+      mbar_init(&pv_done[t], 1);
+    }
+    mbar_init(p_free, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -165,18 +177,18 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         const uint64_t kt = make_smem_desc(sbase + kOffKTail + stage * kTailBytes, 16, 256, kLayoutSW32);
         umma_ss(d, qt, kt, idesc_qk, 1u);
       };
-      // O_t += P_t V : per 16 keys one N=64 MMA (d 0..63) and one N=16 MMA (d 64..79); P from TMEM
+      // O_t += P V : per 16 keys one N=64 MMA (d 0..63) and one N=16 MMA (d 64..79); P from the shared TMEM buffer
       auto issue_pv = [&](int t, int stage, bool first) {
         const uint64_t vd = make_smem_desc(sbase + kOffVMain + stage * kMainBytes, 1024, 1024, kLayoutSW128);
         const uint64_t vt = make_smem_desc(sbase + kOffVTail + stage * kTailBytes, 256, 256, kLayoutSW32);
-        const uint32_t pt = tmem_base + kColS + t * 128;
-        const uint32_t om = tmem_base + kColO + t * 128;
+        const uint32_t pt = tmem_base + kColP;
+        const uint32_t om = tmem_base + kColO + t * 64;
+        const uint32_t ot = tmem_base + kColOT + t * 16;
 #pragma unroll
         for (int k = 0; k < kTileKV / 16; ++k) {
           const uint32_t acc = (first && k == 0) ? 0u : 1u;
-          const uint32_t pa = pt + (k < 4 ? 8 * k : 64 + 8 * (k - 4));   // lo half at cols 0..31, hi half at 64..95
-          umma_ts(om, pa, vd + (uint64_t)(k * (2048 >> 4)), idesc_pv_main, acc);
-          umma_ts(om + 64, pa, vt + (uint64_t)(k * (512 >> 4)), idesc_pv_tail, acc);
+          umma_ts(om, pt + 8 * k, vd + (uint64_t)(k * (2048 >> 4)), idesc_pv_main, acc);
+          umma_ts(ot, pt + 8 * k, vt + (uint64_t)(k * (512 >> 4)), idesc_pv_tail, acc);
         }
       };
 
@@ -196,31 +208,38 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         uint32_t nphase = phase;
         if (nstage == kKVStages) { nstage = 0; nphase ^= 1; }
         const bool more = (j + 1 < n_blocks);
-        mbar_wait(&v_full[stage], phase);
-        // ---- tile A
-        PXA_TRACE(16, tcnt);                       // [4j+0] start waiting for P_A
-        mbar_wait(&p_full[0], j & 1);
-        PXA_TRACE(16, tcnt);                       // [4j+1] P_A ready
-        tc_fence_after();
-        issue_pv(0, stage, j == 0);
+        // ---- tile A: next S as soon as the softmax threads hold S_A(j) in registers, then P_A(j) V(j)
         if (more) {
+          PXA_TRACE(16, tcnt);
+          mbar_wait(&s_free[0], j & 1);
           mbar_wait(&k_full[nstage], nphase);
           tc_fence_after();
           issue_qk(0, nstage);
           umma_commit(&s_full[0]);
         }
-        // ---- tile B
-        PXA_TRACE(16, tcnt);                       // [4j+2] A's MMAs issued, start waiting for P_B
-        mbar_wait(&p_full[1], j & 1);
-        PXA_TRACE(16, tcnt);                       // [4j+3] P_B ready
+        mbar_wait(&v_full[stage], phase);
+        PXA_TRACE(16, tcnt);
+        mbar_wait(&p_full[0], j & 1);
+        PXA_TRACE(16, tcnt);
         tc_fence_after();
-        issue_pv(1, stage, j == 0);
-        umma_commit(&v_empty[stage]);
+        issue_pv(0, stage, j == 0);
+        umma_commit(&pv_done[0]);
+        umma_commit(p_free);
+        // ---- tile B
         if (more) {
+          mbar_wait(&s_free[1], j & 1);
+          tc_fence_after();
           issue_qk(1, nstage);
           umma_commit(&s_full[1]);
           umma_commit(&k_empty[nstage]);
         }
+        PXA_TRACE(16, tcnt);
+        mbar_wait(&p_full[1], j & 1);
+        tc_fence_after();
+        issue_pv(1, stage, j == 0);
+        umma_commit(&pv_done[1]);
+        umma_commit(p_free);
+        umma_commit(&v_empty[stage]);
         stage = nstage;
         phase = nphase;
       }
@@ -235,8 +254,10 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
     const int row_in_tile = qd * 32 + lane;
     const int qrow = q0 + t * kTileQ + row_in_tile;             // query index within the sample
     const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
-    const uint32_t t_s = tmem_base + kColS + t * 128 + hf * 64 + lane_sel;   // this half's 64 S columns (P over the first 32)
-    const uint32_t t_o = tmem_base + kColO + t * 128 + hf * 32 + lane_sel;   // lo: O cols 0..31, hi: O cols 32..71
+    const uint32_t t_s = tmem_base + kColS + t * 128 + hf * 64 + lane_sel;   // this half's 64 S columns
+    const uint32_t t_p = tmem_base + kColP + hf * 32 + lane_sel;             // this half's 32 packed P columns
+    const uint32_t t_o = tmem_base + kColO + t * 64 + hf * 32 + lane_sel;    // lo: d 0..31, hi: d 32..63
+    const uint32_t t_ot = tmem_base + kColOT + t * 16 + lane_sel;            // d 64..71 (+ 8 zero pad columns), hi half only
     const float sl2 = p.scale_log2;
     float* xchg = reinterpret_cast<float*>(smem + kOffXchg);
     const uint32_t bar_id = 1 + t;                 // named barrier of this tile's 256 softmax threads
@@ -245,13 +266,15 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
     float row_sum = 0.f;         // partial: this half's keys only
 
     for (int j = 0; j < n_blocks; ++j) {
-      PXA_TRACE(w, tcnt);                          // [5j+0] start waiting for S
+      PXA_TRACE(w, tcnt);                          // [7j+0] start waiting for S
       mbar_wait(&s_full[t], j & 1);
-      PXA_TRACE(w, tcnt);                          // [5j+1] S ready
+      PXA_TRACE(w, tcnt);                          // [7j+1] S ready
       tc_fence_after();
       uint32_t v0[32], v1[32];
       tmem_ld_32x32b_x32_pair(t_s, v0, t_s + 32, v1);
-      PXA_TRACE(w, tcnt);                          // [5j+2] S in registers
+      tc_fence_before();
+      mbar_arrive(&s_free[t]);                     // S_t may now be overwritten by Q_t K(j+1)^T
+      PXA_TRACE(w, tcnt);                          // [7j+2] S in registers
       const int rem = kv_len - j * kTileKV - hf * 64;           // valid keys among this half's 64
       if (rem < 64) {
         const uint32_t ninf = 0xff800000u;
@@ -273,7 +296,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       float* xb = xchg + ((j & 1) * 4 + t * 2) * 128;
       xb[hf * 128 + row_in_tile] = m_half;
       named_bar_sync(bar_id, 256);
-      PXA_TRACE(w, tcnt);                          // [5j+3] row max exchanged
+      PXA_TRACE(w, tcnt);                          // [7j+3] row max exchanged
       const float m_new = fmaxf(fmaxf(m_half, xb[(hf ^ 1) * 128 + row_in_tile]), m_ref);
       // Lazy rescale: keep the old reference max unless it is stale by more than 2^8 (P stays <= 256, exact in the
       // fp32 accumulators).  The decision is warp-uniform (the TMEM round trip below is warp-collective) and identical
@@ -282,17 +305,18 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       if (__any_sync(0xffffffffu, stale)) {
         const float factor = (m_ref == -INFINITY) ? 0.f : fast_exp2((m_ref - m_new) * sl2);
         if (j > 0) {
-          // PV of block j-1 has completed (it was issued before the QK^T that produced this S)
+          mbar_wait(&pv_done[t], (j - 1) & 1);     // P_t V of block j-1 has completed: O_t is quiescent
+          tc_fence_after();
           uint32_t o0[32], o1[8];
           tmem_ld_32x32b_x32(t_o, o0);
 #pragma unroll
           for (int i = 0; i < 32; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * factor);
           tmem_st_32x32b_x32(t_o, o0);
           if (hf == 1) {                         // warp-uniform: d 64..71 (the 8 zero pad columns 72..79 need no scaling)
-            tmem_ld_32x32b_x8(t_o + 32, o1);
+            tmem_ld_32x32b_x8(t_ot, o1);
 #pragma unroll
             for (int i = 0; i < 8; ++i) o1[i] = __float_as_uint(__uint_as_float(o1[i]) * factor);
-            tmem_st_32x32b_x8(t_o + 32, o1);
+            tmem_st_32x32b_x8(t_ot, o1);
           }
         }
         row_sum *= factor;
@@ -301,45 +325,33 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       const float neg_m = -m_ref * sl2;
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
       uint32_t pk[32];
-      // The MUFU pipe is the bottleneck resource.  If both tiles run their exp2 sections in lockstep each gets half
-      // the MUFU rate and the block period is 2E + W (E = exp2 section alone, W = MMA + TMEM + barrier latency of a
-      // tile); offset by E the period drops to E + W.  The offset between the tiles is preserved from block to block
-      // (both slow down equally while they overlap), so it only has to be set up once: tile B starts its first exp2
-      // section when tile A has finished its first one.
-      float neg_m_dep = neg_m;
-      if (j == 0 && t == 1) {
-        mbar_wait(&exp_turn[1], 0);
-        // the exp2 below are plain register math: tie them to the wait so the compiler cannot hoist them above it
-        asm volatile("" : "+f"(neg_m_dep)::"memory");
-        if (tracing) p.trace[w * kTraceMax + 500] = clock64();     // tile B released
-      }
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float a0 = fast_exp2(fmaf(__uint_as_float(v0[2 * i]), sl2, neg_m_dep));
-        const float a1 = fast_exp2(fmaf(__uint_as_float(v0[2 * i + 1]), sl2, neg_m_dep));
-        const float b0 = fast_exp2(fmaf(__uint_as_float(v1[2 * i]), sl2, neg_m_dep));
-        const float b1 = fast_exp2(fmaf(__uint_as_float(v1[2 * i + 1]), sl2, neg_m_dep));
+        const float a0 = fast_exp2(fmaf(__uint_as_float(v0[2 * i]), sl2, neg_m));
+        const float a1 = fast_exp2(fmaf(__uint_as_float(v0[2 * i + 1]), sl2, neg_m));
+        const float b0 = fast_exp2(fmaf(__uint_as_float(v1[2 * i]), sl2, neg_m));
+        const float b1 = fast_exp2(fmaf(__uint_as_float(v1[2 * i + 1]), sl2, neg_m));
         sum0 += a0; sum1 += a1; sum2 += b0; sum3 += b1;
         pk[i] = pack_bf16x2(a0, a1);
         pk[16 + i] = pack_bf16x2(b0, b1);
       }
-      if (j == 0 && t == 0) {
-        // every exp2 result of this thread exists before the hand-off (keeps the compiler from sinking exp2 below it)
-        asm volatile("" ::"r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]),
-                     "r"(pk[8]), "r"(pk[9]), "r"(pk[10]), "r"(pk[11]), "r"(pk[12]), "r"(pk[13]), "r"(pk[14]), "r"(pk[15]),
-                     "r"(pk[16]), "r"(pk[17]), "r"(pk[18]), "r"(pk[19]), "r"(pk[20]), "r"(pk[21]), "r"(pk[22]),
-                     "r"(pk[23]), "r"(pk[24]), "r"(pk[25]), "r"(pk[26]), "r"(pk[27]), "r"(pk[28]), "r"(pk[29]),
-                     "r"(pk[30]), "r"(pk[31])
-                     : "memory");
-        mbar_arrive(&exp_turn[1]);                             // releases tile B's first exp2 section
-        if (tracing) p.trace[w * kTraceMax + 501] = clock64();     // tile A handed over
+      // P (bf16, this half's 64 keys = 32 packed columns) into the shared P buffer once the previous user's P V has
+      // consumed it.  Writers alternate A(0), B(0), A(1), ...: writer n = 2j + t waits for the n-1'th P V.
+      if (tracing) asm volatile("" ::"r"(pk[0]), "r"(pk[7]), "r"(pk[15]), "r"(pk[16]), "r"(pk[23]), "r"(pk[31]) : "memory");
+      PXA_TRACE(w, tcnt);                          // [7j+4] exp2 section done
+      {
+        const int n = 2 * j + t;
+        if (n > 0) {
+          mbar_wait(p_free, (n - 1) & 1);
+          tc_fence_after();
+        }
       }
-      // P (bf16, this half's 64 keys = 32 packed columns) over the first 32 of this half's own S columns
-      tmem_st_32x32b_x32(t_s, pk);
+      PXA_TRACE(w, tcnt);                          // [7j+5] P buffer is ours
+      tmem_st_32x32b_x32(t_p, pk);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
-      PXA_TRACE(w, tcnt);                          // [5j+4] P published
+      PXA_TRACE(w, tcnt);                          // [7j+6] P published
       row_sum += (sum0 + sum1) + (sum2 + sum3);
     }
 
@@ -354,7 +366,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       mbar_wait(o_full, 0);
       tc_fence_after();
       tmem_ld_32x32b_x32(t_o, o0);
-      if (hf == 1) tmem_ld_32x32b_x8(t_o + 32, o1);
+      if (hf == 1) tmem_ld_32x32b_x8(t_ot, o1);
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i) o0[i] = 0u;

@@ -22,16 +22,15 @@ print(f"kernel {e0.elapsed_time(e1):.3f} ms, {4*B*H*N*N*72/e0.elapsed_time(e1)/1
 tr = trace.cpu()
 t0 = int(tr[tr > 0].min())
 names = {0: "A-lo q0", 4: "A-hi q0", 8: "B-lo q0", 12: "B-hi q0"}
-print("softmax stamps per block j: [wait S | S ready | S in regs | max exchanged | P published] (cycles since CTA start)")
+print("softmax stamps per block j: [wait S | S ready | S in regs | max exchanged | exp done | P buffer free | P published]")
 for w, nm in names.items():
     for j in range(0, 8):
-        row = [int(v) - t0 for v in tr[w, 5 * j:5 * j + 5]]
-        d = [row[i + 1] - row[i] for i in range(4)]
-        print(f"  {nm} j={j}: {row}  d(waitS,ld,xchg,exp+st)={d}")
-print("stagger stamps: A arrive", [int(tr[w,501])-t0 for w in (0,4)], " B released", [int(tr[w,500])-t0 for w in (8,12)])
-print("MMA thread per block j: [wait P_A | P_A ready | wait P_B | P_B ready]")
+        row = [int(v) - t0 for v in tr[w, 7 * j:7 * j + 7]]
+        d = [row[i + 1] - row[i] for i in range(6)]
+        print(f"  {nm} j={j}: {row}  d(waitS,ld,xchg,exp,pfree,st)={d}")
+print("MMA thread per block j: [wait S_A free | wait P_A | P_A ready | wait P_B]")
 for j in range(0, 10):
     row = [int(v) - t0 for v in tr[16, 4 * j:4 * j + 4]]
-    print(f"  j={j}: {row}  wait_A={row[1]-row[0]} issueA={row[2]-row[1]} wait_B={row[3]-row[2]}")
+    print(f"  j={j}: {row}  d={[row[i+1]-row[i] for i in range(3)]}")
 per = [int(tr[16, 4 * (j + 1)]) - int(tr[16, 4 * j]) for j in range(4, 28)]
 print("cycles per block (MMA loop period), j=4..27:", per, "mean", sum(per) / len(per))
