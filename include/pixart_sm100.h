@@ -67,6 +67,7 @@ typedef struct PxaGemmArgs {
   int32_t block_n;      /* 0 = auto (192 when it divides N, else 128); or 128 / 192 / 256           */
   int32_t max_ctas;     /* 0 = one CTA per SM; >0 caps the persistent grid (tests)                  */
   int32_t cta_pair;     /* 0 = auto, 1 = single-CTA UMMA (128 x BN tiles), 2 = CTA-pair UMMA (256 x BN tiles) */
+  int64_t* debug_trace; /* NULL in production. Else device int64[4096]: cycle stamps of CTA 0's epilogue issuer thread */
 } PxaGemmArgs;
 int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream);
 

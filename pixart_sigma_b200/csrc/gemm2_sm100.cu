@@ -262,6 +262,7 @@ static int launch_gemm2(const PxaGemmArgs& a, cudaStream_t stream) {
   p.M = a.M; p.N = a.N; p.K = a.K; p.ldo = a.ldo;
   p.num_m_tiles = (a.M + 2 * kBM - 1) / (2 * kBM);
   p.num_n_tiles = (a.N + BN - 1) / BN;
+  p.trace = reinterpret_cast<long long*>(a.debug_trace);
   auto kern = gemm2_bf16_kernel<BN, EPI, OutT>;
   PXA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
   int clusters = device_info().sms / 2;

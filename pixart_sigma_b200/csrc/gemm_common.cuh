@@ -21,6 +21,7 @@ struct GemmParams {
   int rows_per_batch;
   int M, N, K, ldo;
   int num_m_tiles, num_n_tiles;
+  long long* trace;     // debug only (NULL in production)
 };
 
 constexpr int kResBufs = 3;

@@ -145,11 +145,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int i = 0; i < kResBufs - 1; ++i) request_next();
       }
       int g = 0;
+      const bool tracing = issuer && p.trace != nullptr && blockIdx.x == 0;
+      int tcnt = 0;
+#define PXA_GTRACE()                                                    \
+  do {                                                                  \
+    if (tracing && tcnt < 4096) p.trace[tcnt++] = clock64();            \
+  } while (0)
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / p.num_n_tiles) * kBM;
         const int n0 = (tile % p.num_n_tiles) * BN;
         const int nch = chunks_of_tile<BN>(p, n0);
+        PXA_GTRACE();                                                 // tile: start waiting for the accumulator
         mbar_wait(&tfull_bar[as], aphase);
+        PXA_GTRACE();                                                 // tile: accumulator ready
         tc_fence_after();
         const uint32_t t_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
@@ -163,11 +171,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             tc_fence_before();
             mbar_arrive(&tempty_bar[as]);
           }
+          PXA_GTRACE();                                             // chunk: acc in registers
           mbar_wait(&res_full[buf], (g / kResBufs) & 1);           // residual chunk has landed in smem
+          PXA_GTRACE();                                             // chunk: residual landed
           residual_chunk_row(v, p, rb, ab, r, m0 + r, n0 + cc * 32);
           fence_proxy_async_smem();                                 // generic-proxy writes -> visible to the TMA store
+          PXA_GTRACE();                                             // chunk: computed
           if (issuer) tma_store_wait_read<0>();                     // earlier stores have drained their buffers
+          PXA_GTRACE();                                             // chunk: previous store drained
           named_bar_sync(1, kNumEpiThreads);
+          PXA_GTRACE();                                             // chunk: barrier passed
           if (issuer) {
             tma_store_2d(&tmap_out, rb, n0 + cc * 32, m0);
             if (ab != nullptr) tma_store_2d(&tmap_aux, ab, n0 + cc * 32, m0);
@@ -280,6 +293,7 @@ static int launch_gemm(const PxaGemmArgs& a, cudaStream_t stream) {
   p.M = a.M; p.N = a.N; p.K = a.K; p.ldo = a.ldo;
   p.num_m_tiles = (a.M + kBM - 1) / kBM;
   p.num_n_tiles = (a.N + BN - 1) / BN;
+  p.trace = reinterpret_cast<long long*>(a.debug_trace);
   auto kern = gemm_bf16_kernel<BN, EPI, OutT>;
   PXA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
   int grid = device_info().sms;

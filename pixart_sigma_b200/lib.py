@@ -29,7 +29,7 @@ class GemmArgs(C.Structure):
                 ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
                 ("lda", C.c_int32), ("ldw", C.c_int32), ("ldo", C.c_int32),
                 ("epilogue", C.c_int32), ("out_dtype", C.c_int32), ("block_n", C.c_int32), ("max_ctas", C.c_int32),
-                ("cta_pair", C.c_int32)]
+                ("cta_pair", C.c_int32), ("debug_trace", C.c_void_p)]
 
 
 class LnModArgs(C.Structure):
@@ -108,7 +108,7 @@ def _dt(dtype: torch.dtype) -> int:
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, *,
          epilogue: int = EPI_BIAS, residual: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
          gate_batch_stride: int = 0, rows_per_batch: int = 0, out_aux: Optional[torch.Tensor] = None,
-         block_n: int = 0, max_ctas: int = 0, cta_pair: int = 0) -> torch.Tensor:
+         block_n: int = 0, max_ctas: int = 0, cta_pair: int = 0, debug_trace: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = epilogue(a @ w.T + bias). a (M,K) bf16, w (N,K) bf16 (nn.Linear layout), both K-contiguous."""
     assert a.is_cuda and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1 and out.dim() == 2 and out.stride(1) == 1
@@ -127,7 +127,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
                     residual=_ptr(residual), gate=_ptr(gate), gate_batch_stride=gate_batch_stride,
                     rows_per_batch=rows_per_batch or M, M=M, N=N, K=K, lda=a.stride(0), ldw=w.stride(0),
                     ldo=out.stride(0), epilogue=epilogue, out_dtype=_dt(out.dtype), block_n=block_n, max_ctas=max_ctas,
-                    cta_pair=cta_pair)
+                    cta_pair=cta_pair, debug_trace=_ptr(debug_trace))
     _check(load().pxa_gemm_bf16(C.byref(args), _stream()), "pxa_gemm_bf16")
     return out
 
