@@ -21,7 +21,8 @@ template <int BN> struct Gemm2Cfg {
   static constexpr int kStageA = kBM * kBK * 2;                 // 16 KB: this CTA's 128 rows of A
   static constexpr int kStageB = (BN / 2) * kBK * 2;            // this CTA's BN/2 rows of W
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kEpiSmem = 4 * 32 * 32 * 4;
+  static constexpr int kEpiBufs = 4 * 32 * 32 * 4;
+  static constexpr int kEpiSmem = kEpiBufs + ((kEpiConstBytes + 127) / 128) * 128;
   static constexpr int kBarBytes = 256;
   static constexpr int kStages = (227 * 1024 - kEpiSmem - kBarBytes - 1024) / kStage > 8
                                      ? 8 : (227 * 1024 - kEpiSmem - kBarBytes - 1024) / kStage;
@@ -179,36 +180,46 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   } else if (warp >= kEpiWarp0) {
     // ================================================================ epilogue (both CTAs, own 128 rows)
     const int q = warp & 3;
+    const int tid = threadIdx.x - kEpiWarp0 * 32;
     uint8_t* stile = epi_smem + (warp - kEpiWarp0) * 4096;
+    EpiConst* consts = reinterpret_cast<EpiConst*>(epi_smem + Cfg::kEpiBufs);
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    int titer = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++titer) {
       const int m0 = (tile / p.num_n_tiles) * (2 * kBM) + rank * kBM;
       const int n0 = (tile % p.num_n_tiles) * BN;
-      ResFrag res_next;
-      if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) load_residual_frag<OutT>(res_next, p, lane, m0 + q * 32, n0);
+      const int nch = chunks_of_tile<BN>(p, n0);
+      EpiConst* cb = consts + (titer & 1);
+      stage_epi_consts<BN>(cb, p, tid, m0, n0);
+      named_bar_sync(2, kNumEpiThreads);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-      for (int cc = 0; cc < BN / 32; ++cc) {
-        ResFrag res_cur;
+      auto process = [&](uint32_t (&v)[32], int cc) {
         if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
-          res_cur = res_next;
-          if (cc + 1 < BN / 32 && n0 + (cc + 1) * 32 < p.N)
-            load_residual_frag<OutT>(res_next, p, lane, m0 + q * 32, n0 + (cc + 1) * 32);
+          ResFrag res;
+          load_residual_frag<OutT>(res, p, lane, m0 + q * 32, n0 + cc * 32);
+          epilogue_chunk_residual<OutT>(v, res, p, stile, lane, m0 + q * 32, n0 + cc * 32);
+        } else {
+          epilogue_chunk_bf16_c<EPI>(v, p, cb, stile, lane, m0 + q * 32, n0 + cc * 32, cc * 32);
         }
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_acc + cc * 32, v);
-        if (cc == BN / 32 - 1) {
-          tc_fence_before();
-          mbar_arrive_cluster(&tempty_bar[as], 0);       // the leader's MMA thread owns the accumulator hand-off
-        }
-        if (n0 + cc * 32 < p.N) {
-          if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL)
-            epilogue_chunk_residual<OutT>(v, res_cur, p, stile, lane, m0 + q * 32, n0 + cc * 32);
-          else
-            epilogue_chunk_bf16<EPI>(v, p, stile, lane, m0 + q * 32, n0 + cc * 32);
+      };
+      auto release_acc = [&]() {
+        tc_fence_before();
+        mbar_arrive_cluster(&tempty_bar[as], 0);       // the leader's MMA thread owns the accumulator hand-off
+      };
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32b_x32_nowait(t_acc, va);
+#pragma unroll 1
+      for (int cc = 0; cc < nch; cc += 2) {
+        tmem_ld_wait_x32(va);
+        if (cc + 1 < nch) tmem_ld_32x32b_x32_nowait(t_acc + (cc + 1) * 32, vb); else release_acc();
+        process(va, cc);
+        if (cc + 1 < nch) {
+          tmem_ld_wait_x32(vb);
+          if (cc + 2 < nch) tmem_ld_32x32b_x32_nowait(t_acc + (cc + 2) * 32, va); else release_acc();
+          process(vb, cc + 1);
         }
       }
       as ^= 1;

@@ -30,12 +30,25 @@ constexpr int kAuxChunkBytes = 128 * 32 * 2;     // 8 KB
 constexpr int kResEpiSmem = kResBufs * kResChunkBytes + 2 * kAuxChunkBytes;   // 64 KB
 constexpr int kSmemBudget = 227 * 1024;
 
+// Per-tile epilogue constants staged in smem while the tile's MMAs run: bias (fp32) and the gate rows of the (at most
+// two) samples a 128-row tile can span.  Reading them per chunk is then an LDS broadcast instead of a chain of L2-latency
+// global loads in the epilogue's critical path.  Double-buffered by tile parity.
+struct EpiConst {
+  float bias[256];
+  float gate0[256];    // gate of the sample of the tile's first row (1.0 when there is no gate)
+  float gate1[256];    // gate of the sample of the tile's last row
+  int row_split;       // tile rows >= row_split belong to the second sample
+  int pad[3];
+};
+constexpr int kEpiConstBytes = 2 * sizeof(EpiConst);    // 6176 B
+
 // kTmaRes: fp32 residual epilogue streamed through smem by TMA (see the end of this file)
 template <int BN, bool kTmaRes = false> struct GemmCfg {
   static constexpr int kStageA = kBM * kBK * 2;                 // 16 KB
   static constexpr int kStageB = BN * kBK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kEpiSmem = kTmaRes ? kResEpiSmem : 4 * 32 * 32 * 4;   // else 4 epilogue warps x (32 rows x 128 B)
+  static constexpr int kEpiBufs = kTmaRes ? kResEpiSmem : 4 * 32 * 32 * 4;   // else 4 epilogue warps x (32 rows x 128 B)
+  static constexpr int kEpiSmem = kEpiBufs + ((kEpiConstBytes + 127) / 128) * 128;
   static constexpr int kBarBytes = 256;
   static constexpr int kMaxStages = (kSmemBudget - kEpiSmem - kBarBytes - 1024) / kStage;
   static constexpr int kStages = kMaxStages > 6 ? 6 : kMaxStages;
@@ -190,6 +203,97 @@ PXA_DEVICE void epilogue_chunk_residual(uint32_t (&v)[32], const ResFrag& res, c
   __syncwarp();
 }
 
+
+// Called by the 128 epilogue threads (tid 0..127) at the start of a tile; followed by a named barrier.
+template <int BN>
+PXA_DEVICE void stage_epi_consts(EpiConst* cb, const GemmParams& p, int tid, int m0, int n0) {
+  const int b0 = m0 / p.rows_per_batch;
+  const int last = (m0 + kBM - 1 < p.M ? m0 + kBM - 1 : p.M - 1);
+  const int b1 = last / p.rows_per_batch;
+#pragma unroll
+  for (int c = tid; c < BN; c += kNumEpiThreads) {
+    const int col = n0 + c;
+    const bool ok = col < p.N;
+    cb->bias[c] = (ok && p.bias != nullptr) ? __bfloat162float(p.bias[col]) : 0.f;
+    cb->gate0[c] = (ok && p.gate != nullptr) ? __ldg(p.gate + (size_t)b0 * p.gate_batch_stride + col) : 1.f;
+    cb->gate1[c] = (ok && p.gate != nullptr) ? __ldg(p.gate + (size_t)b1 * p.gate_batch_stride + col) : 1.f;
+  }
+  if (tid == 0) cb->row_split = (b0 + 1) * p.rows_per_batch - m0;
+}
+
+// bf16 output (EPI 0/1) with staged constants: bias from smem (LDS broadcast).
+template <int EPI>
+PXA_DEVICE void epilogue_chunk_bf16_c(uint32_t (&v)[32], const GemmParams& p, const EpiConst* cb, uint8_t* stile, int lane,
+                                      int row0, int col0, int ccol) {
+  uint32_t pk[16];
+  const float4* bp = reinterpret_cast<const float4*>(cb->bias + ccol);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 b = bp[i];
+    float x0 = __uint_as_float(v[4 * i]) + b.x, x1 = __uint_as_float(v[4 * i + 1]) + b.y;
+    float x2 = __uint_as_float(v[4 * i + 2]) + b.z, x3 = __uint_as_float(v[4 * i + 3]) + b.w;
+    if (EPI == PXA_EPI_BIAS_GELU) {
+      x0 = gelu_tanh(x0); x1 = gelu_tanh(x1); x2 = gelu_tanh(x2); x3 = gelu_tanh(x3);
+    }
+    pk[2 * i] = pack_bf16x2(x0, x1);
+    pk[2 * i + 1] = pack_bf16x2(x2, x3);
+  }
+  {
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<uint4*>(stile + lane * 64 + ((c ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+  }
+  __syncwarp();
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  const int c = lane & 3;
+  uint4 u[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + (lane >> 2);
+    u[it] = *reinterpret_cast<const uint4*>(stile + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+  }
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int grow = row0 + it * 8 + (lane >> 2);
+    const int gcol = col0 + c * 8;
+    if (grow < p.M && gcol < p.N) *reinterpret_cast<uint4*>(out + (size_t)grow * p.ldo + gcol) = u[it];
+  }
+  __syncwarp();
+}
+
+// One residual chunk for the calling thread (row r of the 128-row tile) with staged constants.
+PXA_DEVICE void residual_chunk_row_c(uint32_t (&v)[32], const EpiConst* cb, uint8_t* rbuf, uint8_t* abuf, int r, int ccol) {
+  const int sw = r & 7;
+  uint8_t* rrow = rbuf + r * 128;
+  float4 res[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) res[c] = *reinterpret_cast<const float4*>(rrow + ((c ^ sw) << 4));   // all loads first
+  const float4* bp = reinterpret_cast<const float4*>(cb->bias + ccol);
+  const float4* gp = reinterpret_cast<const float4*>((r >= cb->row_split ? cb->gate1 : cb->gate0) + ccol);
+  uint32_t aux[16];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 b = bp[c], g = gp[c];
+    float4 o;
+    o.x = fmaf(g.x, __uint_as_float(v[4 * c + 0]) + b.x, res[c].x);
+    o.y = fmaf(g.y, __uint_as_float(v[4 * c + 1]) + b.y, res[c].y);
+    o.z = fmaf(g.z, __uint_as_float(v[4 * c + 2]) + b.z, res[c].z);
+    o.w = fmaf(g.w, __uint_as_float(v[4 * c + 3]) + b.w, res[c].w);
+    res[c] = o;
+    aux[2 * c] = pack_bf16x2(o.x, o.y);
+    aux[2 * c + 1] = pack_bf16x2(o.z, o.w);
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) *reinterpret_cast<float4*>(rrow + ((c ^ sw) << 4)) = res[c];           // then all stores
+  if (abuf != nullptr) {
+    const int sw2 = (r >> 1) & 3;
+    uint8_t* arow = abuf + r * 64;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<uint4*>(arow + ((c ^ sw2) << 4)) = make_uint4(aux[4 * c], aux[4 * c + 1], aux[4 * c + 2], aux[4 * c + 3]);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------- TMA residual epilogue
 // fp32 residual stream: out = residual + gate * (acc + bias), the residual tile streamed global -> smem and the result

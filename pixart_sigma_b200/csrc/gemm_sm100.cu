@@ -122,115 +122,93 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp >= kEpiWarp0) {
     // ================================================================ epilogue
     const int q = warp & 3;                         // TMEM sub-partition of this warp
+    const int tid = threadIdx.x - kEpiWarp0 * 32;   // 0..127
+    EpiConst* consts = reinterpret_cast<EpiConst*>(epi_smem + Cfg::kEpiBufs);
     int as = 0;
     uint32_t aphase = 0;
-    if constexpr (kTmaRes) {
-      // ---- fp32 residual stream: residual in / result out through smem chunk buffers by TMA (gemm_common.cuh)
-      const int r = q * 32 + lane;                                  // row of the 128-row tile owned by this thread
-      uint8_t* rbufs = epi_smem;
-      uint8_t* abufs = epi_smem + kResBufs * kResChunkBytes;
-      const bool issuer = (warp == kEpiWarp0) && (lane == 0);       // owns every TMA op of the epilogue
-      int l_tile = blockIdx.x, l_cc = 0, l_g = 0;                   // issuer: next residual chunk to request
-      auto request_next = [&]() {
-        if (l_tile >= num_tiles) return;
-        const int lm0 = (l_tile / p.num_n_tiles) * kBM;
-        const int ln0 = (l_tile % p.num_n_tiles) * BN;
-        const int buf = l_g % kResBufs;
-        mbar_arrive_expect_tx(&res_full[buf], kResChunkBytes);
-        tma_load_2d(rbufs + buf * kResChunkBytes, &tmap_res, &res_full[buf], ln0 + l_cc * 32, lm0, kEvictFirst);
-        ++l_g;
-        if (++l_cc == chunks_of_tile<BN>(p, ln0)) { l_cc = 0; l_tile += gridDim.x; }
-      };
-      if (issuer) {
-        for (int i = 0; i < kResBufs - 1; ++i) request_next();
-      }
-      int g = 0;
-      const bool tracing = issuer && p.trace != nullptr && blockIdx.x == 0;
-      int tcnt = 0;
-#define PXA_GTRACE()                                                    \
-  do {                                                                  \
-    if (tracing && tcnt < 4096) p.trace[tcnt++] = clock64();            \
-  } while (0)
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.num_n_tiles) * kBM;
-        const int n0 = (tile % p.num_n_tiles) * BN;
-        const int nch = chunks_of_tile<BN>(p, n0);
-        PXA_GTRACE();                                                 // tile: start waiting for the accumulator
-        mbar_wait(&tfull_bar[as], aphase);
-        PXA_GTRACE();                                                 // tile: accumulator ready
-        tc_fence_after();
-        const uint32_t t_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-        for (int cc = 0; cc < nch; ++cc, ++g) {
+    int titer = 0;
+    // TMA-streamed fp32 residual path state (unused otherwise)
+    const int r = q * 32 + lane;                                  // row of the 128-row tile owned by this thread
+    uint8_t* rbufs = epi_smem;
+    uint8_t* abufs = epi_smem + kResBufs * kResChunkBytes;
+    const bool issuer = kTmaRes && (warp == kEpiWarp0) && (lane == 0);   // owns every TMA op of the epilogue
+    int l_tile = blockIdx.x, l_cc = 0, l_g = 0;                   // issuer: next residual chunk to request
+    auto request_next = [&]() {
+      if (l_tile >= num_tiles) return;
+      const int lm0 = (l_tile / p.num_n_tiles) * kBM;
+      const int ln0 = (l_tile % p.num_n_tiles) * BN;
+      const int buf = l_g % kResBufs;
+      mbar_arrive_expect_tx(&res_full[buf], kResChunkBytes);
+      tma_load_2d(rbufs + buf * kResChunkBytes, &tmap_res, &res_full[buf], ln0 + l_cc * 32, lm0, kEvictFirst);
+      ++l_g;
+      if (++l_cc == chunks_of_tile<BN>(p, ln0)) { l_cc = 0; l_tile += gridDim.x; }
+    };
+    if (issuer) {
+      for (int i = 0; i < kResBufs - 1; ++i) request_next();
+    }
+    int g = 0;
+    uint8_t* stile = epi_smem + (warp - kEpiWarp0) * 4096;       // bf16 paths: per-warp transpose tile
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
+      const int m0 = (tile / p.num_n_tiles) * kBM;
+      const int n0 = (tile % p.num_n_tiles) * BN;
+      const int nch = chunks_of_tile<BN>(p, n0);
+      EpiConst* cb = consts + (titer & 1);
+      stage_epi_consts<BN>(cb, p, tid, m0, n0);                  // global loads hide under this tile's MMAs
+      named_bar_sync(2, kNumEpiThreads);
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
+
+      // one chunk: v = this thread's 32 accumulator columns [cc*32, +32)
+      auto process = [&](uint32_t (&v)[32], int cc) {
+        if constexpr (kTmaRes) {
           const int buf = g % kResBufs;
           uint8_t* rb = rbufs + buf * kResChunkBytes;
           uint8_t* ab = p.out_aux != nullptr ? abufs + (g & 1) * kAuxChunkBytes : nullptr;
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_acc + cc * 32, v);
-          if (cc == nch - 1) {
-            tc_fence_before();
-            mbar_arrive(&tempty_bar[as]);
-          }
-          PXA_GTRACE();                                             // chunk: acc in registers
           mbar_wait(&res_full[buf], (g / kResBufs) & 1);           // residual chunk has landed in smem
-          PXA_GTRACE();                                             // chunk: residual landed
-          residual_chunk_row(v, p, rb, ab, r, m0 + r, n0 + cc * 32);
+          residual_chunk_row_c(v, cb, rb, ab, r, cc * 32);
           fence_proxy_async_smem();                                 // generic-proxy writes -> visible to the TMA store
-          PXA_GTRACE();                                             // chunk: computed
           if (issuer) tma_store_wait_read<0>();                     // earlier stores have drained their buffers
-          PXA_GTRACE();                                             // chunk: previous store drained
           named_bar_sync(1, kNumEpiThreads);
-          PXA_GTRACE();                                             // chunk: barrier passed
           if (issuer) {
             tma_store_2d(&tmap_out, rb, n0 + cc * 32, m0);
             if (ab != nullptr) tma_store_2d(&tmap_aux, ab, n0 + cc * 32, m0);
             tma_store_commit();
             request_next();                                         // refills the buffer chunk g-1 has just left
           }
+          ++g;
+        } else if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
+          ResFrag res;                                              // bf16 residual stream (rarely used): simple path
+          load_residual_frag<OutT>(res, p, lane, m0 + q * 32, n0 + cc * 32);
+          epilogue_chunk_residual<OutT>(v, res, p, stile, lane, m0 + q * 32, n0 + cc * 32);
+        } else {
+          epilogue_chunk_bf16_c<EPI>(v, p, cb, stile, lane, m0 + q * 32, n0 + cc * 32, cc * 32);
         }
-        as ^= 1;
-        if (as == 0) aphase ^= 1;
-      }
-      if (issuer) tma_store_wait_all<0>();
-    } else {
-    uint8_t* stile = epi_smem + (warp - kEpiWarp0) * 4096;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.num_n_tiles) * kBM;
-      const int n0 = (tile % p.num_n_tiles) * BN;
-      ResFrag res_next;
-      if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
-        // first residual fragment: issued before the accumulator is ready, so its latency hides under the MMAs
-        load_residual_frag<OutT>(res_next, p, lane, m0 + q * 32, n0);
-      }
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
-      const uint32_t t_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
+      };
+      auto release_acc = [&]() {                                    // all TMEM reads of this accumulator are done
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[as]);
+      };
+
+      // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32b_x32_nowait(t_acc, va);
 #pragma unroll 1
-      for (int cc = 0; cc < BN / 32; ++cc) {
-        ResFrag res_cur;
-        if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
-          res_cur = res_next;
-          if (cc + 1 < BN / 32 && n0 + (cc + 1) * 32 < p.N)
-            load_residual_frag<OutT>(res_next, p, lane, m0 + q * 32, n0 + (cc + 1) * 32);
-        }
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_acc + cc * 32, v);   // includes tcgen05.wait::ld
-        if (cc == BN / 32 - 1) {
-          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(&tempty_bar[as]);
-        }
-        if (n0 + cc * 32 < p.N) {
-          if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL)
-            epilogue_chunk_residual<OutT>(v, res_cur, p, stile, lane, m0 + q * 32, n0 + cc * 32);
-          else
-            epilogue_chunk_bf16<EPI>(v, p, stile, lane, m0 + q * 32, n0 + cc * 32);
+      for (int cc = 0; cc < nch; cc += 2) {
+        tmem_ld_wait_x32(va);
+        if (cc + 1 < nch) tmem_ld_32x32b_x32_nowait(t_acc + (cc + 1) * 32, vb); else release_acc();
+        process(va, cc);
+        if (cc + 1 < nch) {
+          tmem_ld_wait_x32(vb);
+          if (cc + 2 < nch) tmem_ld_32x32b_x32_nowait(t_acc + (cc + 2) * 32, va); else release_acc();
+          process(vb, cc + 1);
         }
       }
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
-    }
+    if (issuer) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -342,6 +320,8 @@ extern "C" int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream) {
        reinterpret_cast<uintptr_t>(a.out_aux_bf16)) & 15)
     return fail(PXA_ERR_ALIGN, "out / bias / residual / gate / aux must be 16-byte aligned");
   if (a.gate && (a.gate_batch_stride & 3)) return fail(PXA_ERR_ALIGN, "gate_batch_stride must be a multiple of 4");
+  if (a.gate && a.rows_per_batch > 0 && a.rows_per_batch < 128)
+    return fail(PXA_ERR_ARG, "rows_per_batch must be >= 128 when a gate is given (a 128-row tile may span two samples at most)");
   PXA_REQUIRE_SM100();
   int bn = a.block_n;
   if (bn == 0) bn = (a.N % 192 == 0) ? 192 : ((a.N % 256 == 0) ? 256 : (a.N >= 192 ? 192 : 128));
