@@ -4,8 +4,8 @@
 // tensor pipe and the softmax warps (while the softmax warps of A run exp2 on S_A, the tensor pipe does P_B V and
 // the next Q_B K^T).  640 threads:
 //   warp 0      TMA producer: Q once, then K / V blocks of 128 keys into two 3-deep smem rings
-//   warp 1      MMA issuer (one thread): S = Q K^T (SS), O += P V (TS: P read from TMEM)
-//   warp 2      TMEM allocator (512 columns: S_A | S_B | O_A | O_B | one P buffer shared by both tiles)
+//   warp 1      MMA issuer (one thread): S = Q K^T (SS), O += P V (SS: P staged in smem as a K-major 128B-swizzled tile)
+//   warp 2      TMEM allocator (512 columns: S_A | S_B | O_A | O_B)
 //   warps 4-19  softmax: per tile two warpgroups, "lo" owns keys 0..63 and "hi" keys 64..127 of every block, so a
 //               query row is shared by a thread pair (64 S values each; row max exchanged through smem once per
 //               block).  4 softmax warps per SM sub-partition keep the MUFU fed while others wait on TMEM / barriers.
@@ -14,8 +14,8 @@
 // Pipeline: P (bf16) does NOT alias S.  As soon as the softmax threads hold S_t(j) in registers they release S_t
 // (s_free) and the MMA thread issues Q_t K(j+1)^T while the exp2 of block j is still running, so the next S is ready
 // before it is needed and the MUFU (exp2) pipe -- the bottleneck resource at head_dim 72 -- never waits for the
-// tensor pipe.  TMEM has room for only ONE 64-column P buffer next to 2 x S and 2 x O; the two tiles take turns
-// (p_free), which also staggers them by half a block so that their exp2 sections alternate.
+// tensor pipe.  TMEM has no room for two extra P buffers next to 2 x S and 2 x O, so each tile's P goes to its own
+// 32 KB smem buffer (written row-per-thread into the UMMA K-major swizzled layout) and P V runs in SS mode.
 //
 // head_dim 72 is not a multiple of the 64-element swizzle atom, nor of UMMA K=16 / N%16: each Q/K/V tile is staged
 // as a "main" part (d 0..63, 128B swizzle) plus a "tail" part (d 64..79, 32B swizzle) whose d 72..79 are zero-filled
@@ -33,7 +33,7 @@ constexpr int kAttnThreads = 640;
 constexpr int kD = 72;
 constexpr int kTileQ = 128;
 constexpr int kTileKV = 128;
-constexpr int kKVStages = 3;
+constexpr int kKVStages = 2;
 constexpr int kMainBytes = 128 * 128;   // 128 rows x 64 bf16
 constexpr int kTailBytes = 128 * 32;    // 128 rows x 16 bf16
 constexpr int kTileBytes = kMainBytes + kTailBytes;
@@ -45,7 +45,9 @@ constexpr int kOffVMain = kOffKMain + kKVStages * kMainBytes;
 constexpr int kOffQTail = kOffVMain + kKVStages * kMainBytes;
 constexpr int kOffKTail = kOffQTail + 2 * kTailBytes;
 constexpr int kOffVTail = kOffKTail + kKVStages * kTailBytes;
-constexpr int kOffBars = kOffVTail + kKVStages * kTailBytes;
+constexpr int kOffP = kOffVTail + kKVStages * kTailBytes;           // P (bf16): [2 tiles][2 key halves][128 rows x 128 B]
+constexpr int kPHalfBytes = 128 * 128;
+constexpr int kOffBars = kOffP + 4 * kPHalfBytes;
 constexpr int kOffXchg = kOffBars + 256;                            // float [2 parity][2 tile][2 half][128 row]
 constexpr int kAttnSmem = kOffXchg + 2 * 2 * 2 * 128 * 4 + 1024;
 
@@ -53,7 +55,7 @@ constexpr int kAttnSmem = kOffXchg + 2 * 2 * 2 * 128 * 4 + 1024;
 constexpr uint32_t kColS = 0;       // S_A at 0, S_B at 128 (fp32, 128 keys each)
 constexpr uint32_t kColO = 256;     // O main (d 0..63, fp32): tile A at 256, tile B at 320
 constexpr uint32_t kColOT = 384;    // O tail (d 64..79): tile A at 384, tile B at 400
-constexpr uint32_t kColP = 416;     // shared P buffer: 128 keys bf16 = 64 columns (lo half 416..447, hi half 448..479)
+// P lives in shared memory (one private buffer per tile), consumed by the P V MMAs in SS mode.
 
 struct AttnParams {
   __nv_bfloat16* out;
@@ -88,9 +90,8 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
   uint64_t* p_full = s_full + 2;              // [2]  softmax -> MMA (P written, S consumed)
   uint64_t* o_full = p_full + 2;              // [1]  MMA -> softmax (all PV done)
   uint64_t* s_free = o_full + 1;              // [2]  softmax -> MMA (S_t is in registers, may be overwritten)
-  uint64_t* pv_done = s_free + 2;             // [2]  MMA -> softmax (P_t V of a block has completed: O_t may be rescaled)
-  uint64_t* p_free = pv_done + 2;             // [1]  MMA -> softmax (shared P buffer consumed)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 1);
+  uint64_t* p_empty = s_free + 2;             // [2]  MMA -> softmax (P_t V of a block completed: P_t smem reusable, O_t quiescent)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 2);
 
   const int warp = warp_idx_sync();
   const int lane = threadIdx.x & 31;
@@ -120,9 +121,8 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
     mbar_init(o_full, 1);
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_free[t], 256);
-      mbar_init(&pv_done[t], 1);
+      mbar_init(&p_empty[t], 1);
     }
-    mbar_init(p_free, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -177,18 +177,19 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         const uint64_t kt = make_smem_desc(sbase + kOffKTail + stage * kTailBytes, 16, 256, kLayoutSW32);
         umma_ss(d, qt, kt, idesc_qk, 1u);
       };
-      // O_t += P V : per 16 keys one N=64 MMA (d 0..63) and one N=16 MMA (d 64..79); P from the shared TMEM buffer
+      // O_t += P_t V : per 16 keys one N=64 MMA (d 0..63) and one N=16 MMA (d 64..79); P_t from its smem buffer
       auto issue_pv = [&](int t, int stage, bool first) {
         const uint64_t vd = make_smem_desc(sbase + kOffVMain + stage * kMainBytes, 1024, 1024, kLayoutSW128);
         const uint64_t vt = make_smem_desc(sbase + kOffVTail + stage * kTailBytes, 256, 256, kLayoutSW32);
-        const uint32_t pt = tmem_base + kColP;
         const uint32_t om = tmem_base + kColO + t * 64;
         const uint32_t ot = tmem_base + kColOT + t * 16;
 #pragma unroll
         for (int k = 0; k < kTileKV / 16; ++k) {
           const uint32_t acc = (first && k == 0) ? 0u : 1u;
-          umma_ts(om, pt + 8 * k, vd + (uint64_t)(k * (2048 >> 4)), idesc_pv_main, acc);
-          umma_ts(ot, pt + 8 * k, vt + (uint64_t)(k * (512 >> 4)), idesc_pv_tail, acc);
+          // keys 16k..16k+15: half (k >> 2) of the tile's P buffer, 32 B per K-step inside the 128 B swizzle atom
+          const uint64_t pd = make_smem_desc(sbase + kOffP + (t * 2 + (k >> 2)) * kPHalfBytes, 16, 1024, kLayoutSW128) + 2 * (k & 3);
+          umma_ss(om, pd, vd + (uint64_t)(k * (2048 >> 4)), idesc_pv_main, acc);
+          umma_ss(ot, pd, vt + (uint64_t)(k * (512 >> 4)), idesc_pv_tail, acc);
         }
       };
 
@@ -223,8 +224,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         PXA_TRACE(16, tcnt);
         tc_fence_after();
         issue_pv(0, stage, j == 0);
-        umma_commit(&pv_done[0]);
-        umma_commit(p_free);
+        umma_commit(&p_empty[0]);
         // ---- tile B
         if (more) {
           mbar_wait(&s_free[1], j & 1);
@@ -237,8 +237,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         mbar_wait(&p_full[1], j & 1);
         tc_fence_after();
         issue_pv(1, stage, j == 0);
-        umma_commit(&pv_done[1]);
-        umma_commit(p_free);
+        umma_commit(&p_empty[1]);
         umma_commit(&v_empty[stage]);
         stage = nstage;
         phase = nphase;
@@ -255,7 +254,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
     const int qrow = q0 + t * kTileQ + row_in_tile;             // query index within the sample
     const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
     const uint32_t t_s = tmem_base + kColS + t * 128 + hf * 64 + lane_sel;   // this half's 64 S columns
-    const uint32_t t_p = tmem_base + kColP + hf * 32 + lane_sel;             // this half's 32 packed P columns
+    uint8_t* p_row = smem + kOffP + (t * 2 + hf) * kPHalfBytes + row_in_tile * 128;   // this thread's 64 keys of P (128 B)
     const uint32_t t_o = tmem_base + kColO + t * 64 + hf * 32 + lane_sel;    // lo: d 0..31, hi: d 32..63
     const uint32_t t_ot = tmem_base + kColOT + t * 16 + lane_sel;            // d 64..71 (+ 8 zero pad columns), hi half only
     const float sl2 = p.scale_log2;
@@ -305,7 +304,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       if (__any_sync(0xffffffffu, stale)) {
         const float factor = (m_ref == -INFINITY) ? 0.f : fast_exp2((m_ref - m_new) * sl2);
         if (j > 0) {
-          mbar_wait(&pv_done[t], (j - 1) & 1);     // P_t V of block j-1 has completed: O_t is quiescent
+          mbar_wait(&p_empty[t], (j - 1) & 1);     // P_t V of block j-1 has completed: O_t is quiescent
           tc_fence_after();
           uint32_t o0[32], o1[8];
           tmem_ld_32x32b_x32(t_o, o0);
@@ -335,21 +334,17 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         pk[i] = pack_bf16x2(a0, a1);
         pk[16 + i] = pack_bf16x2(b0, b1);
       }
-      // P (bf16, this half's 64 keys = 32 packed columns) into the shared P buffer once the previous user's P V has
-      // consumed it.  Writers alternate A(0), B(0), A(1), ...: writer n = 2j + t waits for the n-1'th P V.
-      if (tracing) asm volatile("" ::"r"(pk[0]), "r"(pk[7]), "r"(pk[15]), "r"(pk[16]), "r"(pk[23]), "r"(pk[31]) : "memory");
-      PXA_TRACE(w, tcnt);                          // [7j+4] exp2 section done
-      {
-        const int n = 2 * j + t;
-        if (n > 0) {
-          mbar_wait(p_free, (n - 1) & 1);
-          tc_fence_after();
-        }
-      }
+      // P (bf16, this half's 64 keys = 128 B per row) into the tile's smem buffer once P_t V of the previous block has
+      // consumed it; 16-byte chunk c of row r sits at r*128 + ((c ^ (r & 7)) << 4)  (UMMA K-major SWIZZLE_128B)
+      if (j > 0) mbar_wait(&p_empty[t], (j - 1) & 1);
       PXA_TRACE(w, tcnt);                          // [7j+5] P buffer is ours
-      tmem_st_32x32b_x32(t_p, pk);
-      tmem_st_wait();
-      tc_fence_before();
+      {
+        const int sw = row_in_tile & 7;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(p_row + ((c ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      }
+      fence_proxy_async_smem();                    // generic-proxy smem writes -> visible to the tensor core (async proxy)
       mbar_arrive(&p_full[t]);
       PXA_TRACE(w, tcnt);                          // [7j+6] P published
       row_sum += (sum0 + sum1) + (sum2 + sum3);

@@ -330,12 +330,18 @@ extern "C" int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream) {
   if (a.epilogue != PXA_EPI_BIAS_RESIDUAL && a.out_dtype != PXA_DTYPE_BF16)
     return fail(PXA_ERR_ARG, "EPI_BIAS / EPI_BIAS_GELU write bf16 only");
   if (a.cta_pair < 0 || a.cta_pair > 2) return fail(PXA_ERR_ARG, "cta_pair must be 0, 1 or 2");
-  // auto: the CTA pair pays off for wide outputs (measured +3..9 % at N >= 2304, M = 32768); narrow-N GEMMs and the
-  // residual epilogues stay on the single-CTA kernel
+  // auto (measured at M = 32768, tools/gemm_bench.py): the CTA pair with 256 x 256 tiles wins for every bias / GELU
+  // GEMM; the fp32 residual epilogue is HBM-bound at K = 1152 and streams through TMA chunk buffers on the single-CTA
+  // kernel, while at K >= 2304 it is MMA-bound and the pair kernel's deeper smem ring (7 stages) wins.
   bool pair = a.cta_pair == 2;
-  if (a.cta_pair == 0 && a.block_n == 0 && a.epilogue != PXA_EPI_BIAS_RESIDUAL && a.N >= 2304 && a.M >= 2048) {
-    pair = true;
-    bn = 256;
+  if (a.cta_pair == 0 && a.block_n == 0 && a.M >= 1024) {
+    if (a.epilogue != PXA_EPI_BIAS_RESIDUAL) {
+      pair = true;
+      bn = 256;
+    } else if (a.K >= 2304) {
+      pair = true;
+      bn = 192;
+    }
   }
   if (pair) return gemm_pair_dispatch(a, bn, s);
   switch (bn) {
