@@ -4,18 +4,13 @@
 // tensor pipe and the softmax warps (while the softmax warps of A run exp2 on S_A, the tensor pipe does P_B V and
 // the next Q_B K^T).  640 threads:
 //   warp 0      TMA producer: Q once, then K / V blocks of 128 keys into two 3-deep smem rings
-//   warp 1      MMA issuer (one thread): S = Q K^T (SS), O += P V (SS: P staged in smem as a K-major 128B-swizzled tile)
+//   warp 1      MMA issuer (one thread): S = Q K^T (SS), O += P V (TS: P read from TMEM)
 //   warp 2      TMEM allocator (512 columns: S_A | S_B | O_A | O_B)
 //   warps 4-19  softmax: per tile two warpgroups, "lo" owns keys 0..63 and "hi" keys 64..127 of every block, so a
 //               query row is shared by a thread pair (64 S values each; row max exchanged through smem once per
 //               block).  4 softmax warps per SM sub-partition keep the MUFU fed while others wait on TMEM / barriers.
-//               Online softmax in fp32 with lazy rescaling of O (only when the running max grows by > 2^8), final
-//               O / rowsum -> bf16 -> global.
-// Pipeline: P (bf16) does NOT alias S.  As soon as the softmax threads hold S_t(j) in registers they release S_t
-// (s_free) and the MMA thread issues Q_t K(j+1)^T while the exp2 of block j is still running, so the next S is ready
-// before it is needed and the MUFU (exp2) pipe -- the bottleneck resource at head_dim 72 -- never waits for the
-// tensor pipe.  TMEM has no room for two extra P buffers next to 2 x S and 2 x O, so each tile's P goes to its own
-// 32 KB smem buffer (written row-per-thread into the UMMA K-major swizzled layout) and P V runs in SS mode.
+//               Online softmax in fp32 with lazy rescaling of O (only when the running max grows by > 2^8), P written
+//               back to TMEM as bf16 over each half's own S columns, final O / rowsum -> bf16 -> global
 //
 // head_dim 72 is not a multiple of the 64-element swizzle atom, nor of UMMA K=16 / N%16: each Q/K/V tile is staged
 // as a "main" part (d 0..63, 128B swizzle) plus a "tail" part (d 64..79, 32B swizzle) whose d 72..79 are zero-filled
@@ -33,7 +28,7 @@ constexpr int kAttnThreads = 640;
 constexpr int kD = 72;
 constexpr int kTileQ = 128;
 constexpr int kTileKV = 128;
-constexpr int kKVStages = 2;
+constexpr int kKVStages = 3;
 constexpr int kMainBytes = 128 * 128;   // 128 rows x 64 bf16
 constexpr int kTailBytes = 128 * 32;    // 128 rows x 16 bf16
 constexpr int kTileBytes = kMainBytes + kTailBytes;
@@ -45,17 +40,13 @@ constexpr int kOffVMain = kOffKMain + kKVStages * kMainBytes;
 constexpr int kOffQTail = kOffVMain + kKVStages * kMainBytes;
 constexpr int kOffKTail = kOffQTail + 2 * kTailBytes;
 constexpr int kOffVTail = kOffKTail + kKVStages * kTailBytes;
-constexpr int kOffP = kOffVTail + kKVStages * kTailBytes;           // P (bf16): [2 tiles][2 key halves][128 rows x 128 B]
-constexpr int kPHalfBytes = 128 * 128;
-constexpr int kOffBars = kOffP + 4 * kPHalfBytes;
+constexpr int kOffBars = kOffVTail + kKVStages * kTailBytes;
 constexpr int kOffXchg = kOffBars + 256;                            // float [2 parity][2 tile][2 half][128 row]
 constexpr int kAttnSmem = kOffXchg + 2 * 2 * 2 * 128 * 4 + 1024;
 
 // TMEM columns
-constexpr uint32_t kColS = 0;       // S_A at 0, S_B at 128 (fp32, 128 keys each)
-constexpr uint32_t kColO = 256;     // O main (d 0..63, fp32): tile A at 256, tile B at 320
-constexpr uint32_t kColOT = 384;    // O tail (d 64..79): tile A at 384, tile B at 400
-// P lives in shared memory (one private buffer per tile), consumed by the P V MMAs in SS mode.
+constexpr uint32_t kColS = 0;       // S_A at 0, S_B at 128; P (bf16) aliases S: keys 0..63 -> cols [0,32), keys 64..127 -> [64,96)
+constexpr uint32_t kColO = 256;     // O_A at 256 (main 64 + tail 16), O_B at 384
 
 struct AttnParams {
   __nv_bfloat16* out;
@@ -89,9 +80,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
   uint64_t* s_full = v_empty + kKVStages;     // [2]  MMA -> softmax (S ready; also implies previous PV done)
   uint64_t* p_full = s_full + 2;              // [2]  softmax -> MMA (P written, S consumed)
   uint64_t* o_full = p_full + 2;              // [1]  MMA -> softmax (all PV done)
-  uint64_t* s_free = o_full + 1;              // [2]  softmax -> MMA (S_t is in registers, may be overwritten)
-  uint64_t* p_empty = s_free + 2;             // [2]  MMA -> softmax (P_t V of a block completed: P_t smem reusable, O_t quiescent)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = warp_idx_sync();
   const int lane = threadIdx.x & 31;
@@ -119,10 +108,6 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       mbar_init(&p_full[t], 256);
     }
     mbar_init(o_full, 1);
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_free[t], 256);
-      mbar_init(&p_empty[t], 1);
-    }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -177,19 +162,18 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         const uint64_t kt = make_smem_desc(sbase + kOffKTail + stage * kTailBytes, 16, 256, kLayoutSW32);
         umma_ss(d, qt, kt, idesc_qk, 1u);
       };
-      // O_t += P_t V : per 16 keys one N=64 MMA (d 0..63) and one N=16 MMA (d 64..79); P_t from its smem buffer
+      // O_t += P_t V : per 16 keys one N=64 MMA (d 0..63) and one N=16 MMA (d 64..79); P from TMEM
       auto issue_pv = [&](int t, int stage, bool first) {
         const uint64_t vd = make_smem_desc(sbase + kOffVMain + stage * kMainBytes, 1024, 1024, kLayoutSW128);
         const uint64_t vt = make_smem_desc(sbase + kOffVTail + stage * kTailBytes, 256, 256, kLayoutSW32);
-        const uint32_t om = tmem_base + kColO + t * 64;
-        const uint32_t ot = tmem_base + kColOT + t * 16;
+        const uint32_t pt = tmem_base + kColS + t * 128;
+        const uint32_t om = tmem_base + kColO + t * 128;
 #pragma unroll
         for (int k = 0; k < kTileKV / 16; ++k) {
           const uint32_t acc = (first && k == 0) ? 0u : 1u;
-          // keys 16k..16k+15: half (k >> 2) of the tile's P buffer, 32 B per K-step inside the 128 B swizzle atom
-          const uint64_t pd = make_smem_desc(sbase + kOffP + (t * 2 + (k >> 2)) * kPHalfBytes, 16, 1024, kLayoutSW128) + 2 * (k & 3);
-          umma_ss(om, pd, vd + (uint64_t)(k * (2048 >> 4)), idesc_pv_main, acc);
-          umma_ss(ot, pd, vt + (uint64_t)(k * (512 >> 4)), idesc_pv_tail, acc);
+          const uint32_t pa = pt + (k < 4 ? 8 * k : 64 + 8 * (k - 4));   // lo half at cols 0..31, hi half at 64..95
+          umma_ts(om, pa, vd + (uint64_t)(k * (2048 >> 4)), idesc_pv_main, acc);
+          umma_ts(om + 64, pa, vt + (uint64_t)(k * (512 >> 4)), idesc_pv_tail, acc);
         }
       };
 
@@ -209,36 +193,31 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         uint32_t nphase = phase;
         if (nstage == kKVStages) { nstage = 0; nphase ^= 1; }
         const bool more = (j + 1 < n_blocks);
-        // ---- tile A: next S as soon as the softmax threads hold S_A(j) in registers, then P_A(j) V(j)
+        mbar_wait(&v_full[stage], phase);
+        // ---- tile A
+        PXA_TRACE(16, tcnt);                       // [4j+0] start waiting for P_A
+        mbar_wait(&p_full[0], j & 1);
+        PXA_TRACE(16, tcnt);                       // [4j+1] P_A ready
+        tc_fence_after();
+        issue_pv(0, stage, j == 0);
         if (more) {
-          PXA_TRACE(16, tcnt);
-          mbar_wait(&s_free[0], j & 1);
           mbar_wait(&k_full[nstage], nphase);
           tc_fence_after();
           issue_qk(0, nstage);
           umma_commit(&s_full[0]);
         }
-        mbar_wait(&v_full[stage], phase);
-        PXA_TRACE(16, tcnt);
-        mbar_wait(&p_full[0], j & 1);
-        PXA_TRACE(16, tcnt);
-        tc_fence_after();
-        issue_pv(0, stage, j == 0);
-        umma_commit(&p_empty[0]);
         // ---- tile B
+        PXA_TRACE(16, tcnt);                       // [4j+2] A's MMAs issued, start waiting for P_B
+        mbar_wait(&p_full[1], j & 1);
+        PXA_TRACE(16, tcnt);                       // [4j+3] P_B ready
+        tc_fence_after();
+        issue_pv(1, stage, j == 0);
+        umma_commit(&v_empty[stage]);
         if (more) {
-          mbar_wait(&s_free[1], j & 1);
-          tc_fence_after();
           issue_qk(1, nstage);
           umma_commit(&s_full[1]);
           umma_commit(&k_empty[nstage]);
         }
-        PXA_TRACE(16, tcnt);
-        mbar_wait(&p_full[1], j & 1);
-        tc_fence_after();
-        issue_pv(1, stage, j == 0);
-        umma_commit(&p_empty[1]);
-        umma_commit(&v_empty[stage]);
         stage = nstage;
         phase = nphase;
       }
@@ -253,10 +232,8 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
     const int row_in_tile = qd * 32 + lane;
     const int qrow = q0 + t * kTileQ + row_in_tile;             // query index within the sample
     const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
-    const uint32_t t_s = tmem_base + kColS + t * 128 + hf * 64 + lane_sel;   // this half's 64 S columns
-    uint8_t* p_row = smem + kOffP + (t * 2 + hf) * kPHalfBytes + row_in_tile * 128;   // this thread's 64 keys of P (128 B)
-    const uint32_t t_o = tmem_base + kColO + t * 64 + hf * 32 + lane_sel;    // lo: d 0..31, hi: d 32..63
-    const uint32_t t_ot = tmem_base + kColOT + t * 16 + lane_sel;            // d 64..71 (+ 8 zero pad columns), hi half only
+    const uint32_t t_s = tmem_base + kColS + t * 128 + hf * 64 + lane_sel;   // this half's 64 S columns (P over the first 32)
+    const uint32_t t_o = tmem_base + kColO + t * 128 + hf * 32 + lane_sel;   // lo: O cols 0..31, hi: O cols 32..71
     const float sl2 = p.scale_log2;
     float* xchg = reinterpret_cast<float*>(smem + kOffXchg);
     const uint32_t bar_id = 1 + t;                 // named barrier of this tile's 256 softmax threads
@@ -265,15 +242,13 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
     float row_sum = 0.f;         // partial: this half's keys only
 
     for (int j = 0; j < n_blocks; ++j) {
-      PXA_TRACE(w, tcnt);                          // [7j+0] start waiting for S
+      PXA_TRACE(w, tcnt);                          // [5j+0] start waiting for S
       mbar_wait(&s_full[t], j & 1);
-      PXA_TRACE(w, tcnt);                          // [7j+1] S ready
+      PXA_TRACE(w, tcnt);                          // [5j+1] S ready
       tc_fence_after();
       uint32_t v0[32], v1[32];
       tmem_ld_32x32b_x32_pair(t_s, v0, t_s + 32, v1);
-      tc_fence_before();
-      mbar_arrive(&s_free[t]);                     // S_t may now be overwritten by Q_t K(j+1)^T
-      PXA_TRACE(w, tcnt);                          // [7j+2] S in registers
+      PXA_TRACE(w, tcnt);                          // [5j+2] S in registers
       const int rem = kv_len - j * kTileKV - hf * 64;           // valid keys among this half's 64
       if (rem < 64) {
         const uint32_t ninf = 0xff800000u;
@@ -295,7 +270,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       float* xb = xchg + ((j & 1) * 4 + t * 2) * 128;
       xb[hf * 128 + row_in_tile] = m_half;
       named_bar_sync(bar_id, 256);
-      PXA_TRACE(w, tcnt);                          // [7j+3] row max exchanged
+      PXA_TRACE(w, tcnt);                          // [5j+3] row max exchanged
       const float m_new = fmaxf(fmaxf(m_half, xb[(hf ^ 1) * 128 + row_in_tile]), m_ref);
       // Lazy rescale: keep the old reference max unless it is stale by more than 2^8 (P stays <= 256, exact in the
       // fp32 accumulators).  The decision is warp-uniform (the TMEM round trip below is warp-collective) and identical
@@ -304,18 +279,17 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       if (__any_sync(0xffffffffu, stale)) {
         const float factor = (m_ref == -INFINITY) ? 0.f : fast_exp2((m_ref - m_new) * sl2);
         if (j > 0) {
-          mbar_wait(&p_empty[t], (j - 1) & 1);     // P_t V of block j-1 has completed: O_t is quiescent
-          tc_fence_after();
+          // PV of block j-1 has completed (it was issued before the QK^T that produced this S)
           uint32_t o0[32], o1[8];
           tmem_ld_32x32b_x32(t_o, o0);
 #pragma unroll
           for (int i = 0; i < 32; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * factor);
           tmem_st_32x32b_x32(t_o, o0);
           if (hf == 1) {                         // warp-uniform: d 64..71 (the 8 zero pad columns 72..79 need no scaling)
-            tmem_ld_32x32b_x8(t_ot, o1);
+            tmem_ld_32x32b_x8(t_o + 32, o1);
 #pragma unroll
             for (int i = 0; i < 8; ++i) o1[i] = __float_as_uint(__uint_as_float(o1[i]) * factor);
-            tmem_st_32x32b_x8(t_ot, o1);
+            tmem_st_32x32b_x8(t_o + 32, o1);
           }
         }
         row_sum *= factor;
@@ -334,19 +308,12 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         pk[i] = pack_bf16x2(a0, a1);
         pk[16 + i] = pack_bf16x2(b0, b1);
       }
-      // P (bf16, this half's 64 keys = 128 B per row) into the tile's smem buffer once P_t V of the previous block has
-      // consumed it; 16-byte chunk c of row r sits at r*128 + ((c ^ (r & 7)) << 4)  (UMMA K-major SWIZZLE_128B)
-      if (j > 0) mbar_wait(&p_empty[t], (j - 1) & 1);
-      PXA_TRACE(w, tcnt);                          // [7j+5] P buffer is ours
-      {
-        const int sw = row_in_tile & 7;
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<uint4*>(p_row + ((c ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-      }
-      fence_proxy_async_smem();                    // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      // P (bf16, this half's 64 keys = 32 packed columns) over the first 32 of this half's own S columns
+      tmem_st_32x32b_x32(t_s, pk);
+      tmem_st_wait();
+      tc_fence_before();
       mbar_arrive(&p_full[t]);
-      PXA_TRACE(w, tcnt);                          // [7j+6] P published
+      PXA_TRACE(w, tcnt);                          // [5j+4] P published
       row_sum += (sum0 + sum1) + (sum2 + sum3);
     }
 
@@ -361,7 +328,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       mbar_wait(o_full, 0);
       tc_fence_after();
       tmem_ld_32x32b_x32(t_o, o0);
-      if (hf == 1) tmem_ld_32x32b_x8(t_ot, o1);
+      if (hf == 1) tmem_ld_32x32b_x8(t_o + 32, o1);
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i) o0[i] = 0u;

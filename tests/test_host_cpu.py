@@ -118,3 +118,23 @@ def test_product_never_imports_the_oracle():
     for fn in os.listdir(pkg):
         if fn.endswith(".py"):
             assert "oracle" not in open(os.path.join(pkg, fn)).read().replace("the oracle", ""), fn
+
+
+@pytest.mark.skipif(not refshim.reference_available(), reason="/root/reference not present")
+def test_install_into_reference_repoints_registry_and_nets():
+    """INTEGRATION.md level A: after install_into_reference() the reference's own builder / module names construct
+    the B200 model, so scripts/inference.py and train_scripts/train.py pick it up unchanged."""
+    refshim.install_reference_shims()
+    import pixart_sigma_b200
+    assert pixart_sigma_b200.install_into_reference()
+    import diffusion.model.nets as nets
+    from diffusion.model.builder import build_model as ref_build_model
+    assert nets.PixArtMS is PixArtMS and nets.PixArtMSBlock is PixArtMSBlock
+    m = ref_build_model("PixArtMS", False, False, depth=1, input_size=32, model_max_length=300)
+    assert type(m) is PixArtMS
+    # the reference sampler wrapper accepts the model's bound method (diffusion/dpm_solver.py:6-36)
+    from diffusion import DPMS
+    cond = torch.zeros(1, 1, 300, 4096)
+    solver = DPMS(m.forward_with_dpmsolver, condition=cond, uncondition=cond, cfg_scale=4.5,
+                  model_kwargs=dict(data_info=None, mask=None))
+    assert solver is not None
