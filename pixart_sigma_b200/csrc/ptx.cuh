@@ -287,6 +287,17 @@ PXA_DEVICE float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
   return y;
 }
+// exp2 on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 minimax 2^f
+// (max rel err 7.5e-5, far below the bf16 rounding of P), exponent re-inserted with an integer add.
+// Used for a fraction of the softmax exponentials: the MUFU pipe (16 results/clk/SM) is the attention bottleneck.
+PXA_DEVICE float poly_exp2(float x) {
+  x = fmaxf(x, -126.0f);                                   // also maps -inf (masked keys) to ~1e-38
+  const float t = x + 12582912.0f;                         // 1.5 * 2^23: round(x) lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);
+  const float p = fmaf(fmaf(fmaf(0.05517186224460602f, f, 0.2426111400127411f), f, 0.6932609677314758f), f,
+                       0.9999280571937561f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 PXA_DEVICE float fast_tanh(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;\n" : "=f"(y) : "f"(x));
