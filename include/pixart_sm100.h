@@ -130,6 +130,24 @@ typedef struct PxaKvCompressArgs {
 } PxaKvCompressArgs;
 int pxa_kv_compress_conv2_ln(const PxaKvCompressArgs* args, void* stream);
 
+/* ------------------------------------------------------------------------------------ 3x3 convolution (SDXL-VAE decoder)
+ * out[b,y,x,:] = (residual[b,y,x,:] +) bias + sum_{dy,dx,c} w[:, dy, dx, c] * x[b, y+dy-1, x+dx-1, c]   (zero padding 1)
+ * Implicit GEMM on the tcgen05 GEMM kernel: M = B*H*W pixels, N = Cout, K = 9*Cin; the A tiles are 128-pixel blocks of
+ * the NHWC image fetched by a 4-D TMA tensor map whose out-of-bounds fill implements the padding (no im2col buffer).
+ * Replaces the conv1 / conv2 of the decoder ResBlocks of diffusers' AutoencoderKL (reference call site
+ * scripts/inference.py:136 `vae.decode`; GroupNorm + SiLU stay PyTorch).
+ * Requirements: Cin % 64 == 0, Cout % 8 == 0, W a multiple of min(W,128), H a multiple of 128/min(W,128).
+ */
+typedef struct PxaConv3x3Args {
+  const void* x;        /* bf16 NHWC [B, H, W, Cin] contiguous (torch channels_last)                         */
+  const void* w;        /* bf16 [Cout, 3, 3, Cin] contiguous = checkpoint weight [Cout, Cin, 3, 3] permuted    */
+  const void* bias;     /* bf16 [Cout] or NULL                                                               */
+  void* out;            /* bf16 NHWC [B, H, W, Cout]                                                         */
+  const void* residual; /* bf16 NHWC [B, H, W, Cout] or NULL                                                 */
+  int32_t B, H, W, Cin, Cout;
+} PxaConv3x3Args;
+int pxa_conv3x3_nhwc_bf16(const PxaConv3x3Args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

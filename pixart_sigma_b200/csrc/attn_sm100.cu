@@ -303,8 +303,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         const float a0 = fast_exp2(fmaf(__uint_as_float(v0[2 * i]), sl2, neg_m));
         const float a1 = fast_exp2(fmaf(__uint_as_float(v0[2 * i + 1]), sl2, neg_m));
         const float b0 = fast_exp2(fmaf(__uint_as_float(v1[2 * i]), sl2, neg_m));
-        // one exponential in four runs on the FMA pipe instead of the MUFU (see poly_exp2)
-        const float b1 = poly_exp2(fmaf(__uint_as_float(v1[2 * i + 1]), sl2, neg_m));
+        const float b1 = fast_exp2(fmaf(__uint_as_float(v1[2 * i + 1]), sl2, neg_m));
         sum0 += a0; sum1 += a1; sum2 += b0; sum3 += b1;
         pk[i] = pack_bf16x2(a0, a1);
         pk[16 + i] = pack_bf16x2(b0, b1);

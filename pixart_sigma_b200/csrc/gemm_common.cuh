@@ -22,6 +22,8 @@ struct GemmParams {
   int M, N, K, ldo;
   int num_m_tiles, num_n_tiles;
   long long* trace;     // debug only (NULL in production)
+  // implicit-GEMM 3x3 convolution mode (kConv): A is an NHWC image read through a 4-D tensor map
+  int conv_H, conv_W, conv_tile_w, conv_tile_h, conv_cin_blocks;
 };
 
 constexpr int kResBufs = 3;

@@ -16,7 +16,7 @@
 namespace pxa {
 
 // ------------------------------------------------------------------------------------------------- kernel
-template <int BN, int EPI, typename OutT>
+template <int BN, int EPI, typename OutT, bool kConv = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out,
@@ -82,7 +82,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint8_t* sa = smem + stage * Cfg::kStage;
           uint8_t* sb = sa + Cfg::kStageA;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStage);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBK, m0, kEvictNormal);
+          if constexpr (kConv) {
+            // implicit GEMM: K-block kb = (tap, 64-channel slice); the A tile is the tile's pixel block shifted by the
+            // tap offset -- zero padding comes for free from TMA out-of-bounds fill on the W / H dimensions
+            const int tap = kb / p.conv_cin_blocks;
+            const int c0 = (kb - tap * p.conv_cin_blocks) * kBK;
+            const int pix = m0;                                     // first pixel of the tile in (b, y, x) order
+            const int x0 = pix % p.conv_W;
+            const int y0 = (pix / p.conv_W) % p.conv_H;
+            const int b0 = pix / (p.conv_W * p.conv_H);
+            tma_load_4d(sa, &tmap_a, &full_bar[stage], c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, b0, kEvictNormal);
+          } else {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBK, m0, kEvictNormal);
+          }
           tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * kBK, n0, kEvictLast);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -220,10 +232,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------- host
-template <int BN, int EPI, typename OutT>
-static int launch_gemm(const PxaGemmArgs& a, cudaStream_t stream) {
+struct ConvGeom {
+  int B, H, W, Cin, tile_w, tile_h;
+};
+
+template <int BN, int EPI, typename OutT, bool kConv = false>
+static int launch_gemm(const PxaGemmArgs& a, cudaStream_t stream, const ConvGeom* cg = nullptr) {
   CUtensorMap ta, tw;
-  {
+  if constexpr (kConv) {
+    // NHWC image as a 4-D tensor (c, x, y, b); one A tile = tile_h rows x tile_w pixels x 64 channels
+    uint64_t dims[4] = {(uint64_t)cg->Cin, (uint64_t)cg->W, (uint64_t)cg->H, (uint64_t)cg->B};
+    uint64_t str[3] = {(uint64_t)cg->Cin * 2, (uint64_t)cg->W * cg->Cin * 2, (uint64_t)cg->H * cg->W * cg->Cin * 2};
+    uint32_t box[4] = {kBK, (uint32_t)cg->tile_w, (uint32_t)cg->tile_h, 1};
+    int rc = make_tmap_bf16(&ta, a.a, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  } else {
     uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
     uint64_t str[1] = {(uint64_t)a.lda * 2};
     uint32_t box[2] = {kBK, kBM};
@@ -272,7 +295,12 @@ static int launch_gemm(const PxaGemmArgs& a, cudaStream_t stream) {
   p.num_m_tiles = (a.M + kBM - 1) / kBM;
   p.num_n_tiles = (a.N + BN - 1) / BN;
   p.trace = reinterpret_cast<long long*>(a.debug_trace);
-  auto kern = gemm_bf16_kernel<BN, EPI, OutT>;
+  p.conv_H = p.conv_W = p.conv_tile_w = p.conv_tile_h = p.conv_cin_blocks = 0;
+  if constexpr (kConv) {
+    p.conv_H = cg->H; p.conv_W = cg->W; p.conv_tile_w = cg->tile_w; p.conv_tile_h = cg->tile_h;
+    p.conv_cin_blocks = cg->Cin / kBK;
+  }
+  auto kern = gemm_bf16_kernel<BN, EPI, OutT, kConv>;
   PXA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
   int grid = device_info().sms;
   if (a.max_ctas > 0 && a.max_ctas < grid) grid = a.max_ctas;
@@ -304,7 +332,44 @@ static int dispatch_epi(const PxaGemmArgs& a, cudaStream_t s) {
 
 int gemm_pair_dispatch(const PxaGemmArgs& a, int bn, cudaStream_t s);   // gemm2_sm100.cu
 
+template <int BN>
+static int dispatch_conv(const PxaGemmArgs& a, cudaStream_t s, const ConvGeom& cg) {
+  if (a.epilogue == PXA_EPI_BIAS_RESIDUAL) return launch_gemm<BN, PXA_EPI_BIAS_RESIDUAL, __nv_bfloat16, true>(a, s, &cg);
+  return launch_gemm<BN, PXA_EPI_BIAS, __nv_bfloat16, true>(a, s, &cg);
+}
+
 }  // namespace pxa
+
+extern "C" int pxa_conv3x3_nhwc_bf16(const PxaConv3x3Args* args, void* stream) {
+  using namespace pxa;
+  if (!args) return fail(PXA_ERR_ARG, "null args");
+  const PxaConv3x3Args& c = *args;
+  if (!c.x || !c.w || !c.out) return fail(PXA_ERR_ARG, "null x / w / out");
+  if (c.B <= 0 || c.H <= 0 || c.W <= 0 || c.Cin <= 0 || c.Cout <= 0) return fail(PXA_ERR_ARG, "bad shape");
+  if (c.Cin % 64) return fail(PXA_ERR_ARG, "Cin must be a multiple of 64 (got %d)", c.Cin);
+  if (c.Cout % 8) return fail(PXA_ERR_ARG, "Cout must be a multiple of 8 (got %d)", c.Cout);
+  ConvGeom cg;
+  cg.B = c.B; cg.H = c.H; cg.W = c.W; cg.Cin = c.Cin;
+  cg.tile_w = c.W < 128 ? c.W : 128;
+  if (128 % cg.tile_w) return fail(PXA_ERR_ARG, "W must be a power of two <= 128 or a multiple of 128 (got %d)", c.W);
+  cg.tile_h = 128 / cg.tile_w;
+  if (c.W % cg.tile_w || c.H % cg.tile_h) return fail(PXA_ERR_ARG, "H x W = %d x %d is not tileable by %d x %d", c.H, c.W, cg.tile_h, cg.tile_w);
+  if ((reinterpret_cast<uintptr_t>(c.x) | reinterpret_cast<uintptr_t>(c.w) | reinterpret_cast<uintptr_t>(c.out) |
+       reinterpret_cast<uintptr_t>(c.bias) | reinterpret_cast<uintptr_t>(c.residual)) & 15)
+    return fail(PXA_ERR_ALIGN, "pointers must be 16-byte aligned");
+  PXA_REQUIRE_SM100();
+  PxaGemmArgs a = {};
+  a.a = c.x; a.w = c.w; a.bias = c.bias; a.out = c.out; a.residual = c.residual;
+  a.M = c.B * c.H * c.W; a.N = c.Cout; a.K = 9 * c.Cin;
+  a.lda = c.Cin; a.ldw = 9 * c.Cin; a.ldo = c.Cout;
+  a.rows_per_batch = a.M;
+  a.epilogue = c.residual ? PXA_EPI_BIAS_RESIDUAL : PXA_EPI_BIAS;
+  a.out_dtype = PXA_DTYPE_BF16;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (c.Cout % 256 == 0) return dispatch_conv<256>(a, s, cg);
+  if (c.Cout % 192 == 0) return dispatch_conv<192>(a, s, cg);
+  return dispatch_conv<128>(a, s, cg);
+}
 
 extern "C" int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream) {
   using namespace pxa;

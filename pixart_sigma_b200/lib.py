@@ -55,8 +55,13 @@ class KvCompressArgs(C.Structure):
                 ("eps", C.c_float)]
 
 
+class Conv3x3Args(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p), ("residual", C.c_void_p),
+                ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32)]
+
+
 EXPORTS = ("pxa_version", "pxa_last_error", "pxa_launch_count", "pxa_gemm_bf16", "pxa_ln_modulate",
-           "pxa_flash_attn_d72_bf16", "pxa_kv_compress_conv2_ln")
+           "pxa_flash_attn_d72_bf16", "pxa_kv_compress_conv2_ln", "pxa_conv3x3_nhwc_bf16")
 
 _lib = None
 
@@ -72,7 +77,8 @@ def load() -> C.CDLL:
         lib.pxa_last_error.restype = C.c_char_p
         lib.pxa_launch_count.restype = C.c_uint64
         for name, struct in (("pxa_gemm_bf16", GemmArgs), ("pxa_ln_modulate", LnModArgs),
-                             ("pxa_flash_attn_d72_bf16", AttnArgs), ("pxa_kv_compress_conv2_ln", KvCompressArgs)):
+                             ("pxa_flash_attn_d72_bf16", AttnArgs), ("pxa_kv_compress_conv2_ln", KvCompressArgs),
+                             ("pxa_conv3x3_nhwc_bf16", Conv3x3Args)):
             fn = getattr(lib, name)
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(struct), C.c_void_p]
@@ -169,3 +175,17 @@ def kv_compress(k_in: torch.Tensor, v_in: torch.Tensor, k_out: torch.Tensor, v_o
                           conv_b=_ptr(conv_b), ln_w=_ptr(ln_w), ln_b=_ptr(ln_b), B=B, H=H, W=W, C=k_out.shape[-1],
                           ld_in=ld_in, eps=eps)
     _check(load().pxa_kv_compress_conv2_ln(C.byref(args), _stream()), "pxa_kv_compress_conv2_ln")
+
+
+def conv3x3_nhwc(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor,
+                 residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3x3 / stride 1 / pad 1 convolution on NHWC bf16 tensors. x (B,H,W,Cin), w_packed (Cout,3,3,Cin), out (B,H,W,Cout)."""
+    assert x.dtype == w_packed.dtype == out.dtype == torch.bfloat16 and x.is_contiguous() and w_packed.is_contiguous()
+    assert out.is_contiguous() and (residual is None or (residual.is_contiguous() and residual.shape == out.shape))
+    B, H, W, Cin = x.shape
+    Cout = w_packed.shape[0]
+    assert w_packed.shape == (Cout, 3, 3, Cin) and out.shape == (B, H, W, Cout)
+    args = Conv3x3Args(x=_ptr(x), w=_ptr(w_packed), bias=_ptr(bias), out=_ptr(out), residual=_ptr(residual), B=B, H=H, W=W,
+                       Cin=Cin, Cout=Cout)
+    _check(load().pxa_conv3x3_nhwc_bf16(C.byref(args), _stream()), "pxa_conv3x3_nhwc_bf16")
+    return out

@@ -4,7 +4,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 TAG=${1:-r1}
 echo "=== model tests" > gpurun_out/round_summary.txt
-timeout 900 python -m pytest tests/test_model_gpu.py -q -m gpu -p no:cacheprovider > gpurun_out/test_model.log 2>&1
+timeout 900 python -m pytest tests/test_model_gpu.py tests/test_vae_gpu.py -q -m gpu -p no:cacheprovider > gpurun_out/test_model.log 2>&1
 echo "rc=$? $(tail -1 gpurun_out/test_model.log)" >> gpurun_out/round_summary.txt
 echo "=== smoke" >> gpurun_out/round_summary.txt
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1
