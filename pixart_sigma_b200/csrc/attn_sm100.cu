@@ -15,7 +15,7 @@
 // head_dim 72 is not a multiple of the 64-element swizzle atom, nor of UMMA K=16 / N%16: each Q/K/V tile is staged
 // as a "main" part (d 0..63, 128B swizzle) plus a "tail" part (d 64..79, 32B swizzle) whose d 72..79 are zero-filled
 // by TMA out-of-bounds handling (the tensor map's innermost extent is 72).  QK^T = 4 main K-steps + 1 tail K-step;
-// P V = (N=64 main) + (N=16 tail) MMAs per 16 keys, V consumed MN-major straight from its natural [key, d] layout.
+// P V = one N=80 MMA per 16 keys, V consumed MN-major straight from its natural [key, d] layout (two swizzle atoms).
 //
 // Algorithmic work: 4 * Nq * Nk * 72 FLOP per (sample, head); the MUFU (exp2) pipe, not the tensor pipe, is the
 // tighter bound at head_dim 72: 128x128 exp2 per tile-block = 1024 cycles/SM vs 640 cycles of MMA.
@@ -39,8 +39,10 @@ constexpr int kOffKMain = kOffQMain + 2 * kMainBytes;              // kKVStages
 constexpr int kOffVMain = kOffKMain + kKVStages * kMainBytes;
 constexpr int kOffQTail = kOffVMain + kKVStages * kMainBytes;
 constexpr int kOffKTail = kOffQTail + 2 * kTailBytes;
-constexpr int kOffVTail = kOffKTail + kKVStages * kTailBytes;
-constexpr int kOffBars = kOffVTail + kKVStages * kTailBytes;
+constexpr int kOffVTail = kOffKTail + kKVStages * kTailBytes;      // V tails are full 128 B-row tiles (see below)
+constexpr int kVTailBytes = kMainBytes;                            // 128 keys x 128 B: d 64..71 valid, rest zero
+constexpr int kVTileBytes = kMainBytes + kVTailBytes;
+constexpr int kOffBars = kOffVTail + kKVStages * kVTailBytes;
 constexpr int kOffXchg = kOffBars + 256;                            // float [2 parity][2 tile][2 half][128 row]
 constexpr int kAttnSmem = kOffXchg + 2 * 2 * 2 * 128 * 4 + 1024;
 
@@ -137,9 +139,9 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         tma_load_3d(smem + kOffKMain + stage * kMainBytes, &tm_k_main, &k_full[stage], 0, h, krow, kEvictLast);
         tma_load_3d(smem + kOffKTail + stage * kTailBytes, &tm_k_tail, &k_full[stage], 64, h, krow, kEvictLast);
         mbar_wait(&v_empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&v_full[stage], kTileBytes);
+        mbar_arrive_expect_tx(&v_full[stage], kVTileBytes);
         tma_load_3d(smem + kOffVMain + stage * kMainBytes, &tm_v_main, &v_full[stage], 0, h, krow, kEvictLast);
-        tma_load_3d(smem + kOffVTail + stage * kTailBytes, &tm_v_tail, &v_full[stage], 64, h, krow, kEvictLast);
+        tma_load_3d(smem + kOffVTail + stage * kVTailBytes, &tm_v_tail, &v_full[stage], 64, h, krow, kEvictLast);
         if (++stage == kKVStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -147,8 +149,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
     // ================================================================ MMA issuer
     if (n_blocks > 0 && elect_one()) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_pv_main = make_idesc_bf16(128, 64, 0, 1);   // V is MN-major
-      constexpr uint32_t idesc_pv_tail = make_idesc_bf16(128, 16, 0, 1);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 80, 0, 1);        // V is MN-major; N = 80 = d 0..79
       const uint32_t sbase = smem_u32(smem);
 
       // S_t = Q_t K^T : 4 K-steps from the 128B-swizzled main buffers + 1 from the 32B-swizzled tails
@@ -162,18 +163,18 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         const uint64_t kt = make_smem_desc(sbase + kOffKTail + stage * kTailBytes, 16, 256, kLayoutSW32);
         umma_ss(d, qt, kt, idesc_qk, 1u);
       };
-      // O_t += P_t V : per 16 keys one N=64 MMA (d 0..63) and one N=16 MMA (d 64..79); P from TMEM
+      // O_t += P_t V : ONE N=80 MMA per 16 keys.  V is MN-major; its d extent spans two 64-element swizzle atoms: the main
+      // tile (d 0..63) and the tail tile (d 64..127, of which 64..71 are data and the rest TMA zero fill), LBO apart.
+      // (Two MMAs, N=64 + N=16, cost about twice the issue + pipeline overhead of one N=80 MMA.)  P from TMEM.
       auto issue_pv = [&](int t, int stage, bool first) {
-        const uint64_t vd = make_smem_desc(sbase + kOffVMain + stage * kMainBytes, 1024, 1024, kLayoutSW128);
-        const uint64_t vt = make_smem_desc(sbase + kOffVTail + stage * kTailBytes, 256, 256, kLayoutSW32);
+        const uint64_t vd = make_smem_desc(sbase + kOffVMain + stage * kMainBytes, kOffVTail - kOffVMain, 1024, kLayoutSW128);
         const uint32_t pt = tmem_base + kColS + t * 128;
         const uint32_t om = tmem_base + kColO + t * 128;
 #pragma unroll
         for (int k = 0; k < kTileKV / 16; ++k) {
           const uint32_t acc = (first && k == 0) ? 0u : 1u;
           const uint32_t pa = pt + (k < 4 ? 8 * k : 64 + 8 * (k - 4));   // lo half at cols 0..31, hi half at 64..95
-          umma_ts(om, pa, vd + (uint64_t)(k * (2048 >> 4)), idesc_pv_main, acc);
-          umma_ts(om + 64, pa, vt + (uint64_t)(k * (512 >> 4)), idesc_pv_tail, acc);
+          umma_ts(om, pa, vd + (uint64_t)(k * (2048 >> 4)), idesc_pv, acc);
         }
       };
 
@@ -364,13 +365,19 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
 }
 
 static int make_qkv_maps(CUtensorMap* main_map, CUtensorMap* tail_map, const void* base, int H, long long rows,
-                         long long s_row, long long s_head) {
+                         long long s_row, long long s_head, bool wide_tail = false) {
   uint64_t dims[3] = {(uint64_t)kD, (uint64_t)H, (uint64_t)rows};
   uint64_t str[2] = {(uint64_t)s_head * 2, (uint64_t)s_row * 2};
   uint32_t box_main[3] = {64, 1, 128};
   uint32_t box_tail[3] = {16, 1, 128};
   int rc = make_tmap_bf16(main_map, base, 3, dims, str, box_main, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
+  if (wide_tail) {
+    // V: the tail is a full 64-wide 128B-swizzled tile (d 64..127, zero-filled past 71) so that main + tail form one
+    // two-atom MN-major operand for a single N=80 MMA
+    uint32_t box_wide[3] = {64, 1, 128};
+    return make_tmap_bf16(tail_map, base, 3, dims, str, box_wide, CU_TENSOR_MAP_SWIZZLE_128B);
+  }
   return make_tmap_bf16(tail_map, base, 3, dims, str, box_tail, CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
@@ -392,7 +399,7 @@ extern "C" int pxa_flash_attn_d72_bf16(const PxaAttnArgs* args, void* stream) {
   int rc;
   if ((rc = make_qkv_maps(&qm, &qt, a.q, a.H, (long long)a.B * a.Nq, a.q_sn, a.q_sh))) return rc;
   if ((rc = make_qkv_maps(&km, &kt, a.k, a.H, a.kv_rows, a.k_sn, a.k_sh))) return rc;
-  if ((rc = make_qkv_maps(&vm, &vt, a.v, a.H, a.kv_rows, a.v_sn, a.v_sh))) return rc;
+  if ((rc = make_qkv_maps(&vm, &vt, a.v, a.H, a.kv_rows, a.v_sn, a.v_sh, true))) return rc;
   AttnParams p;
   p.out = reinterpret_cast<__nv_bfloat16*>(a.out);
   p.kv_len = a.kv_len;

@@ -265,7 +265,8 @@ PXA_DEVICE void epilogue_chunk_bf16_c(uint32_t (&v)[32], const GemmParams& p, co
 }
 
 // One residual chunk for the calling thread (row r of the 128-row tile) with staged constants.
-PXA_DEVICE void residual_chunk_row_c(uint32_t (&v)[32], const EpiConst* cb, uint8_t* rbuf, uint8_t* abuf, int r, int ccol) {
+PXA_DEVICE void residual_chunk_row_c(uint32_t (&v)[32], const GemmParams& p, const EpiConst* cb, uint8_t* rbuf, uint8_t* abuf,
+                                     int r, int ccol, int grow, int gcol0) {
   const int sw = r & 7;
   uint8_t* rrow = rbuf + r * 128;
   float4 res[8];
@@ -273,10 +274,17 @@ PXA_DEVICE void residual_chunk_row_c(uint32_t (&v)[32], const EpiConst* cb, uint
   for (int c = 0; c < 8; ++c) res[c] = *reinterpret_cast<const float4*>(rrow + ((c ^ sw) << 4));   // all loads first
   const float4* bp = reinterpret_cast<const float4*>(cb->bias + ccol);
   const float4* gp = reinterpret_cast<const float4*>((r >= cb->row_split ? cb->gate1 : cb->gate0) + ccol);
+  // samples shorter than a tile (rows_per_batch < 128, tiny images): a tile may span more than two samples, so the
+  // gate row is looked up per thread in global memory instead of the two staged rows
+  const bool per_row_gate = p.gate != nullptr && p.rows_per_batch < kBM;
+  const float* gg = nullptr;
+  if (per_row_gate) gg = p.gate + (size_t)((grow < p.M ? grow : p.M - 1) / p.rows_per_batch) * p.gate_batch_stride + gcol0;
   uint32_t aux[16];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    const float4 b = bp[c], g = gp[c];
+    const float4 b = bp[c];
+    float4 g = gp[c];
+    if (per_row_gate) g = (gcol0 + 4 * c < p.N) ? __ldg(reinterpret_cast<const float4*>(gg + 4 * c)) : make_float4(1.f, 1.f, 1.f, 1.f);
     float4 o;
     o.x = fmaf(g.x, __uint_as_float(v[4 * c + 0]) + b.x, res[c].x);
     o.y = fmaf(g.y, __uint_as_float(v[4 * c + 1]) + b.y, res[c].y);

@@ -179,7 +179,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint8_t* rb = rbufs + buf * kResChunkBytes;
           uint8_t* ab = p.out_aux != nullptr ? abufs + (g & 1) * kAuxChunkBytes : nullptr;
           mbar_wait(&res_full[buf], (g / kResBufs) & 1);           // residual chunk has landed in smem
-          residual_chunk_row_c(v, cb, rb, ab, r, cc * 32);
+          residual_chunk_row_c(v, p, cb, rb, ab, r, cc * 32, m0 + r, n0 + cc * 32);
           fence_proxy_async_smem();                                 // generic-proxy writes -> visible to the TMA store
           if (issuer) tma_store_wait_read<0>();                     // earlier stores have drained their buffers
           named_bar_sync(1, kNumEpiThreads);
@@ -385,8 +385,6 @@ extern "C" int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream) {
        reinterpret_cast<uintptr_t>(a.out_aux_bf16)) & 15)
     return fail(PXA_ERR_ALIGN, "out / bias / residual / gate / aux must be 16-byte aligned");
   if (a.gate && (a.gate_batch_stride & 3)) return fail(PXA_ERR_ALIGN, "gate_batch_stride must be a multiple of 4");
-  if (a.gate && a.rows_per_batch > 0 && a.rows_per_batch < 128)
-    return fail(PXA_ERR_ARG, "rows_per_batch must be >= 128 when a gate is given (a 128-row tile may span two samples at most)");
   PXA_REQUIRE_SM100();
   int bn = a.block_n;
   if (bn == 0) bn = (a.N % 192 == 0) ? 192 : ((a.N % 256 == 0) ? 256 : (a.N >= 192 ? 192 : 128));

@@ -104,6 +104,19 @@ def test_gemm_gate_residual(out_dtype, tol, gated):
     assert po.rel_err(aux.float(), want) < 4e-3
 
 
+def test_gemm_gate_residual_samples_shorter_than_a_tile():
+    """96 tokens per sample (< the 128-row tile): a tile spans up to three samples, per-row gate lookup."""
+    B, Ntok, N, K = 5, 96, 1152, 1152
+    M = B * Ntok
+    a, w, bias = _randn(M, K, seed=9), _randn(N, K, seed=10, scale=K ** -0.5), _randn(N, seed=11, scale=0.1)
+    x = _randn(M, N, seed=12, dtype=torch.float32)
+    mod = _randn(B, 6, N, seed=13, dtype=torch.float32)
+    want = x + mod[:, 5].repeat_interleave(Ntok, 0) * F.linear(a.float(), w.float(), bias.float())
+    lib.gemm(a, w, bias, x, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x, gate=mod[:, 5], gate_batch_stride=6 * N,
+             rows_per_batch=Ntok)
+    assert po.rel_err(x, want) < 2e-4
+
+
 def test_gemm_residual_in_place():
     M, N, K = 512, 1152, 1152
     a, w = _randn(M, K, seed=14), _randn(N, K, seed=15, scale=K ** -0.5)

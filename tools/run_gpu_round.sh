@@ -19,7 +19,7 @@ if [ "$2" != "noncu" ]; then
       --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
   echo "rc=$?" >> gpurun_out/round_summary.txt
   echo "=== ncu full gemm + attn" >> gpurun_out/round_summary.txt
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_bf16|flash_attn" -s 340 -c 12 \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm|flash_attn" -s 340 -c 14 \
       -o gpurun_out/prof_${TAG} -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
   echo "rc=$?" >> gpurun_out/round_summary.txt
 fi
