@@ -19,6 +19,8 @@
 //
 // Algorithmic work: 4 * Nq * Nk * 72 FLOP per (sample, head); the MUFU (exp2) pipe, not the tensor pipe, is the
 // tighter bound at head_dim 72: 128x128 exp2 per tile-block = 1024 cycles/SM vs 640 cycles of MMA.
+#include <type_traits>
+
 #include "host_common.cuh"
 #include "ptx.cuh"
 
@@ -242,7 +244,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
     float m_ref = -INFINITY;     // reference max used in the exponent (raw S units); identical in both halves
     float row_sum = 0.f;         // partial: this half's keys only
 
-    for (int j = 0; j < n_blocks; ++j) {
+    auto softmax_block = [&](const int j, auto masked_tag) {
       PXA_TRACE(w, tcnt);                          // [5j+0] start waiting for S
       mbar_wait(&s_full[t], j & 1);
       PXA_TRACE(w, tcnt);                          // [5j+1] S ready
@@ -251,7 +253,10 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       tmem_ld_32x32b_x32_pair(t_s, v0, t_s + 32, v1);
       PXA_TRACE(w, tcnt);                          // [5j+2] S in registers
       const int rem = kv_len - j * kTileKV - hf * 64;           // valid keys among this half's 64
-      if (rem < 64) {
+      // Only the last block of a sample can be partial.  The masking selects are compiled into a separate copy of the
+      // block body: if-converted into the common path they cost ~250 extra issue slots per thread per block (the
+      // softmax warps are issue-bound: 4 warps per sub-partition share one issue port).
+      if constexpr (decltype(masked_tag)::value) {
         const uint32_t ninf = 0xff800000u;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -316,6 +321,11 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       mbar_arrive(&p_full[t]);
       PXA_TRACE(w, tcnt);                          // [5j+4] P published
       row_sum += (sum0 + sum1) + (sum2 + sum3);
+    };
+    for (int j = 0; j + 1 < n_blocks; ++j) softmax_block(j, std::false_type{});
+    if (n_blocks > 0) {
+      if (kv_len % kTileKV != 0) softmax_block(n_blocks - 1, std::true_type{});
+      else softmax_block(n_blocks - 1, std::false_type{});
     }
 
     // ---- epilogue: O / row_sum -> bf16 -> out[(b*Nq + qrow), h*72 + hf*32 .. ]   (lo: d 0..31, hi: d 32..71)
