@@ -245,13 +245,13 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
     float row_sum = 0.f;         // partial: this half's keys only
 
     auto softmax_block = [&](const int j, auto masked_tag) {
-      PXA_TRACE(w, tcnt);                          // [5j+0] start waiting for S
+      PXA_TRACE(w, tcnt);                          // [7j+0] start waiting for S
       mbar_wait(&s_full[t], j & 1);
-      PXA_TRACE(w, tcnt);                          // [5j+1] S ready
+      PXA_TRACE(w, tcnt);                          // [7j+1] S ready
       tc_fence_after();
       uint32_t v0[32], v1[32];
       tmem_ld_32x32b_x32_pair(t_s, v0, t_s + 32, v1);
-      PXA_TRACE(w, tcnt);                          // [5j+2] S in registers
+      PXA_TRACE(w, tcnt);                          // [7j+2] S in registers
       const int rem = kv_len - j * kTileKV - hf * 64;           // valid keys among this half's 64
       // Only the last block of a sample can be partial.  The masking selects are compiled into a separate copy of the
       // block body: if-converted into the common path they cost ~250 extra issue slots per thread per block (the
@@ -276,7 +276,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       float* xb = xchg + ((j & 1) * 4 + t * 2) * 128;
       xb[hf * 128 + row_in_tile] = m_half;
       named_bar_sync(bar_id, 256);
-      PXA_TRACE(w, tcnt);                          // [5j+3] row max exchanged
+      PXA_TRACE(w, tcnt);                          // [7j+3] row max exchanged
       const float m_new = fmaxf(fmaxf(m_half, xb[(hf ^ 1) * 128 + row_in_tile]), m_ref);
       // Lazy rescale: keep the old reference max unless it is stale by more than 2^8 (P stays <= 256, exact in the
       // fp32 accumulators).  The decision is warp-uniform (the TMEM round trip below is warp-collective) and identical
@@ -314,12 +314,18 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         pk[i] = pack_bf16x2(a0, a1);
         pk[16 + i] = pack_bf16x2(b0, b1);
       }
+      if (tracing) {   // debug only: pin the end of the exp2 section for the cycle trace
+        asm volatile("" ::"r"(pk[0]), "r"(pk[3]), "r"(pk[7]), "r"(pk[11]), "r"(pk[15]), "r"(pk[16]), "r"(pk[19]), "r"(pk[23]),
+                     "r"(pk[27]), "r"(pk[31]), "f"(sum0), "f"(sum1), "f"(sum2), "f"(sum3) : "memory");
+      }
+      PXA_TRACE(w, tcnt);                          // [7j+4] exp2 section done
       // P (bf16, this half's 64 keys = 32 packed columns) over the first 32 of this half's own S columns
       tmem_st_32x32b_x32(t_s, pk);
       tmem_st_wait();
+      PXA_TRACE(w, tcnt);                          // [7j+5] P in TMEM
       tc_fence_before();
       mbar_arrive(&p_full[t]);
-      PXA_TRACE(w, tcnt);                          // [5j+4] P published
+      PXA_TRACE(w, tcnt);                          // [7j+6] P published
       row_sum += (sum0 + sum1) + (sum2 + sum3);
     };
     for (int j = 0; j + 1 < n_blocks; ++j) softmax_block(j, std::false_type{});

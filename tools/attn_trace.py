@@ -22,12 +22,12 @@ print(f"kernel {e0.elapsed_time(e1):.3f} ms, {4*B*H*N*N*72/e0.elapsed_time(e1)/1
 tr = trace.cpu()
 t0 = int(tr[tr > 0].min())
 names = {0: "A-lo q0", 4: "A-hi q0", 8: "B-lo q0", 12: "B-hi q0"}
-print("softmax stamps per block j: [wait S | S ready | S in regs | max exchanged | P published]")
+print("softmax stamps per block j: [wait S | S ready | S in regs | max exchanged | exp done | P in TMEM | P published]")
 for w, nm in names.items():
-    for j in range(0, 8):
-        row = [int(v) - t0 for v in tr[w, 5 * j:5 * j + 5]]
-        d = [row[i + 1] - row[i] for i in range(4)]
-        print(f"  {nm} j={j}: {row}  d(waitS,ld,xchg,exp+st)={d}")
+    for j in range(0, 6):
+        row = [int(v) - t0 for v in tr[w, 7 * j:7 * j + 7]]
+        d = [row[i + 1] - row[i] for i in range(6)]
+        print(f"  {nm} j={j}: {row}  d(waitS,ld,xchg,exp,st,arrive)={d}")
 print("MMA thread per block j: [wait S_A free | wait P_A | P_A ready | wait P_B]")
 for j in range(0, 10):
     row = [int(v) - t0 for v in tr[16, 4 * j:4 * j + 4]]
