@@ -132,12 +132,30 @@ def cpu_reference_sample(side: int, pe: float, kv: bool, threads: int):
     return 1.0 / (fixed + DEPTH * per_block), t2 + t6
 
 
+def pick_cpu_threads() -> int:
+    """torch CPU GEMMs of this size stop scaling (and regress) long before 128 threads: calibrate on a 1024x1152x4608
+    fp32 matmul and keep the fastest of {all cores, 64, 32, 16}."""
+    cores = os.cpu_count() or 1
+    a, b = torch.randn(1024, 1152), torch.randn(1152, 4608)
+    best, best_t = cores, None
+    for n in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16)}, reverse=True):
+        torch.set_num_threads(n)
+        a @ b
+        t0 = time.perf_counter()
+        for _ in range(5):
+            a @ b
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = n, dt
+    return best
+
+
 def run_reference_arm(args, wl):
     desc, side, imgs, pe, kv = wl
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = pick_cpu_threads()
     for _ in range(max(args.warmup, 0) and 1):
         cpu_reference_sample(side, pe, kv, threads)
     vals, t_all = [], 0.0
@@ -301,7 +319,7 @@ def run_ours(args, wl, wl_name):
                 "whole_step": {"achieved": tot / (ms_step / 1000.0) / 1e12, "frac": tot / (ms_step / 1000.0) / 1e12 / sus}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = pick_cpu_threads()
             v, dt = cpu_reference_sample(side, pe, kv, threads)
             cpu = {"value": v, "unit": "image-steps/s", "cores": threads, "kind": "port",
                    "sample": f"oracle port of the reference forward, fp32 torch CPU, {side * 8}px, forward batch 2: 2- and "

@@ -56,5 +56,18 @@ def build(force: bool = False, verbose: bool = True) -> str:
     return LIB
 
 
+def build_variant(tag: str, defines) -> str:
+    """Experiment build: same sources with extra -D flags into build/variants/libpixart_sm100_<tag>.so (not used by the
+    product; selected through PXA_LIB_PATH by tools/attn_variants.sh)."""
+    vdir = os.path.join(HERE, "build", "variants")
+    os.makedirs(vdir, exist_ok=True)
+    out = os.path.join(vdir, f"libpixart_sm100_{tag}.so")
+    srcs = [os.path.join(CSRC, f) for f in SOURCES if os.path.exists(os.path.join(CSRC, f))]
+    flags = [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")]
+    subprocess.check_call([_nvcc()] + flags + [f"-D{d}" for d in defines] + ["-shared", "-o", out] + srcs + ["-lcudart"],
+                          stderr=subprocess.DEVNULL)
+    return out
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv)

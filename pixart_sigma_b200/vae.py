@@ -65,6 +65,31 @@ class DecoderResBlock(nn.Module):
         return out.permute(0, 3, 1, 2)
 
 
+class UpsampleConv(nn.Module):
+    """Nearest-neighbour x2 upsample followed by a 3x3 convolution (diffusers `Upsample2D` of the SDXL-VAE decoder up
+    blocks; 2.8 TFLOP of the 10.5 TFLOP decode at 1024px).  The interpolation is data movement (PyTorch); the
+    convolution runs on `pxa_conv3x3_nhwc_bf16`."""
+
+    def __init__(self, channels: int):
+        super().__init__()
+        self.conv = nn.Conv2d(channels, channels, 3, padding=1)
+        self._packed = None
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, *args, **kwargs) -> torch.Tensor:
+        if not x.is_cuda or self.conv.weight.dtype != torch.bfloat16:
+            raise RuntimeError("UpsampleConv runs on the sm_100a kernels only: CUDA tensors and bf16 weights required")
+        key = (self.conv.weight._version, self.conv.weight.data_ptr())
+        if self._packed is None or self._packed[0] != key:
+            self._packed = (key, self.conv.weight.detach().permute(0, 2, 3, 1).contiguous())
+        B, Cc, H, W = x.shape
+        up = F.interpolate(x.to(torch.bfloat16), scale_factor=2.0, mode="nearest")
+        up = up.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)           # (B, 2H, 2W, C)
+        out = torch.empty(B, 2 * H, 2 * W, Cc, dtype=torch.bfloat16, device=x.device)
+        lib.conv3x3_nhwc(up, self._packed[1], self.conv.bias, out)
+        return out.permute(0, 3, 1, 2)
+
+
 def patch_diffusers_decoder(vae) -> int:
     """Route every ResnetBlock2D of a diffusers AutoencoderKL *decoder* through `DecoderResBlock` (shares the
     parameters).  Returns the number of blocks patched.  (diffusers is not installed in the build container; this is
@@ -77,5 +102,10 @@ def patch_diffusers_decoder(vae) -> int:
             blk.conv_shortcut = getattr(mod, "conv_shortcut", None)
             scale = getattr(mod, "output_scale_factor", 1.0)
             mod.forward = (lambda b, s: (lambda x, temb=None, *a, **k: b(x) / s))(blk, scale)
+            n += 1
+        elif type(mod).__name__ == "Upsample2D" and getattr(mod, "conv", None) is not None and mod.conv.kernel_size == (3, 3):
+            up = UpsampleConv(mod.conv.in_channels)
+            up.conv = mod.conv
+            mod.forward = (lambda u: (lambda x, *a, **k: u(x)))(up)
             n += 1
     return n

@@ -174,3 +174,20 @@ def test_forward_is_deterministic_and_sync_free_inputs_on_host_ok():
         a = m(x, t, y, mask=mask)          # host tensors are moved by forward, like the reference's .to(self.dtype)
         b = m(x.cuda(), t.cuda(), y.cuda(), mask=mask.cuda())
     assert torch.equal(a, b)
+
+
+def test_cuda_graph_replay_equals_eager():
+    """One whole forward captured as a CUDA graph (no host sync / allocation inside the library) replays bit-exactly."""
+    from pixart_sigma_b200.graph import GraphedForward
+    cfg = po.OracleConfig(depth=2, input_size=32, pe_interpolation=0.5)
+    m = _build(cfg, po.synthetic_state_dict(cfg, seed=1))
+    gf = GraphedForward(m)
+    outs = []
+    for seed in (0, 1):
+        x, t, y, mask = po.synthetic_inputs(cfg, 2, (32, 32), seed=seed, lens=[300, 20 + seed])
+        with torch.no_grad():
+            eager = m.forward_with_dpmsolver(x.cuda(), t.cuda(), y.cuda(), None, mask=mask.cuda()).clone()
+        got = gf(x, t, y.to(torch.bfloat16), mask).clone()
+        assert torch.equal(got, eager)
+        outs.append(got)
+    assert not torch.equal(outs[0], outs[1])

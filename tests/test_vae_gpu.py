@@ -11,7 +11,7 @@ from oracle import pixart_oracle as po
 pytestmark = pytest.mark.gpu
 if torch.cuda.is_available():
     from pixart_sigma_b200 import lib
-    from pixart_sigma_b200.vae import DecoderResBlock
+    from pixart_sigma_b200.vae import DecoderResBlock, UpsampleConv
 
 
 def _rand(*shape, seed, scale=1.0):
@@ -54,3 +54,14 @@ def test_decoder_resblock_matches_oracle(Cin, Cout, H, W):
     want = po.vae_resblock(sd, "b", x.float())
     assert got.shape == want.shape
     assert po.rel_err(got, want) < 6e-3
+
+
+def test_upsample_conv_matches_torch():
+    torch.manual_seed(1)
+    up = UpsampleConv(128).to(torch.bfloat16).cuda()
+    x = _rand(1, 128, 32, 32, seed=6).cuda()
+    got = up(x).float()
+    want = F.conv2d(F.interpolate(x.float(), scale_factor=2.0, mode="nearest"), up.conv.weight.float(), up.conv.bias.float(),
+                    padding=1)
+    assert got.shape == (1, 128, 64, 64)
+    assert po.rel_err(got, want) < 4e-3

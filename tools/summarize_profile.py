@@ -47,6 +47,18 @@ if os.path.exists(rp):
         w.writerow(keep)
         for r in rows[2:]:
             w.writerow([r[idx[k]] if k in idx else "" for k in keep])
+    # average DRAM bytes per GEMM launch (the bench's roofline.traffic for the GEMM family)
+    def to_bytes(v, u):
+        v = float(v.replace(",", ""))
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+    gem = [r for r in rows[2:] if "gemm" in r[idx["Kernel Name"]]]
+    if gem:
+        import json
+        tot = [to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) +
+               to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]]) for r in gem]
+        json.dump({"tag": tag, "gemm_launches_captured": len(gem), "gemm_dram_bytes_per_launch": sum(tot) / len(tot),
+                   "note": "mean of dram__bytes_read.sum + dram__bytes_write.sum over the GEMM launches of one ncu --set full capture"},
+                  open(os.path.join(out_dir, "latest_traffic.json"), "w"), indent=1)
 bp = os.path.join(ROOT, "gpurun_out", f"bench_{tag}.json")
 if os.path.exists(bp):
     lines += ["", "## bench line of the same build", "", "```json", open(bp).read().strip(), "```"]
