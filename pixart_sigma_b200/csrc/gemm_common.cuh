@@ -265,13 +265,16 @@ PXA_DEVICE void epilogue_chunk_bf16_c(uint32_t (&v)[32], const GemmParams& p, co
 }
 
 // One residual chunk for the calling thread (row r of the 128-row tile) with staged constants.
+// `reduce`: the chunk buffer receives only the update gate*(acc+bias); the TMA engine adds it into the residual stream
+// in global memory (no residual read at all).
 PXA_DEVICE void residual_chunk_row_c(uint32_t (&v)[32], const GemmParams& p, const EpiConst* cb, uint8_t* rbuf, uint8_t* abuf,
-                                     int r, int ccol, int grow, int gcol0) {
+                                     int r, int ccol, int grow, int gcol0, bool reduce = false) {
   const int sw = r & 7;
   uint8_t* rrow = rbuf + r * 128;
   float4 res[8];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) res[c] = *reinterpret_cast<const float4*>(rrow + ((c ^ sw) << 4));   // all loads first
+  for (int c = 0; c < 8; ++c)                                                                        // all loads first
+    res[c] = reduce ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(rrow + ((c ^ sw) << 4));
   const float4* bp = reinterpret_cast<const float4*>(cb->bias + ccol);
   const float4* gp = reinterpret_cast<const float4*>((r >= cb->row_split ? cb->gate1 : cb->gate0) + ccol);
   // samples shorter than a tile (rows_per_batch < 128, tiny images): a tile may span more than two samples, so the

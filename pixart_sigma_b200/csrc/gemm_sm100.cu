@@ -72,7 +72,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
           // pull this tile's residual block into L2 now: the epilogue reads it one mainloop (~7k cycles) later
           if constexpr (kTmaRes) {
-            for (int c = 0; c < BN / 32; ++c) tma_prefetch_l2_2d(&tmap_res, n0 + c * 32, m0);
+            if (!(p.out_aux == nullptr && p.residual == p.out))
+              for (int c = 0; c < BN / 32; ++c) tma_prefetch_l2_2d(&tmap_res, n0 + c * 32, m0);
           } else {
             tma_prefetch_l2_2d(&tmap_res, n0, m0);
           }
@@ -144,6 +145,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t* rbufs = epi_smem;
     uint8_t* abufs = epi_smem + kResBufs * kResChunkBytes;
     const bool issuer = kTmaRes && (warp == kEpiWarp0) && (lane == 0);   // owns every TMA op of the epilogue
+    // In-place update without a bf16 copy: skip the residual read altogether and let TMA reduce-add the update into x.
+    const bool reduce = kTmaRes && p.out_aux == nullptr && p.residual == p.out;
     int l_tile = blockIdx.x, l_cc = 0, l_g = 0;                   // issuer: next residual chunk to request
     auto request_next = [&]() {
       if (l_tile >= num_tiles) return;
@@ -155,7 +158,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ++l_g;
       if (++l_cc == chunks_of_tile<BN>(p, ln0)) { l_cc = 0; l_tile += gridDim.x; }
     };
-    if (issuer) {
+    if (issuer && !reduce) {
       for (int i = 0; i < kResBufs - 1; ++i) request_next();
     }
     int g = 0;
@@ -186,9 +189,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint8_t* rb = rbufs + buf * kResChunkBytes;
           uint8_t* ab = p.out_aux != nullptr ? abufs + (g & 1) * kAuxChunkBytes : nullptr;
           stamp();                                                  // chunk: acc in registers
-          mbar_wait(&res_full[buf], (g / kResBufs) & 1);           // residual chunk has landed in smem
+          if (!reduce) mbar_wait(&res_full[buf], (g / kResBufs) & 1);   // residual chunk has landed in smem
           stamp();                                                  // chunk: residual landed
-          residual_chunk_row_c(v, p, cb, rb, ab, r, cc * 32, m0 + r, n0 + cc * 32);
+          residual_chunk_row_c(v, p, cb, rb, ab, r, cc * 32, m0 + r, n0 + cc * 32, reduce);
           fence_proxy_async_smem();                                 // generic-proxy writes -> visible to the TMA store
           stamp();                                                  // chunk: computed
           if (issuer) tma_store_wait_read<0>();                     // earlier stores have drained their buffers
@@ -196,10 +199,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           named_bar_sync(1, kNumEpiThreads);
           stamp();                                                  // chunk: barrier passed
           if (issuer) {
-            tma_store_2d(&tmap_out, rb, n0 + cc * 32, m0);
-            if (ab != nullptr) tma_store_2d(&tmap_aux, ab, n0 + cc * 32, m0);
-            tma_store_commit();
-            request_next();                                         // refills the buffer chunk g-1 has just left
+            if (reduce) {
+              tma_reduce_add_2d(&tmap_out, rb, n0 + cc * 32, m0);
+              tma_store_commit();
+            } else {
+              tma_store_2d(&tmap_out, rb, n0 + cc * 32, m0);
+              if (ab != nullptr) tma_store_2d(&tmap_aux, ab, n0 + cc * 32, m0);
+              tma_store_commit();
+              request_next();                                       // refills the buffer chunk g-1 has just left
+            }
           }
           ++g;
         } else if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
