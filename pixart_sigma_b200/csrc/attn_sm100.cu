@@ -1,16 +1,24 @@
 // pxa_flash_attn_d72_bf16: softmax(Q K^T * scale) V for head_dim 72 on tcgen05 tensor cores (sm_100a).
 //
-// One CTA = one (sample, head) x 256 query rows, processed as two 128-row tiles A / B that ping-pong between the
-// tensor pipe and the softmax warps (while the softmax warps of A run exp2 on S_A, the tensor pipe does P_B V and
-// the next Q_B K^T).  640 threads:
-//   warp 0      TMA producer: Q once, then K / V blocks of 128 keys into two 3-deep smem rings
-//   warp 1      MMA issuer (one thread): S = Q K^T (SS), O += P V (TS: P read from TMEM)
+// One CTA = one (sample, head) x 256 query rows, processed as two 128-row tiles A / B.  384 threads:
+//   warp 0      TMA producer: Q once, then K / V stages of 128 keys into two 3-deep smem rings
+//   warp 1      MMA issuer (one elected thread): S = Q K^T (SS), O += P V (TS: P read from TMEM)
 //   warp 2      TMEM allocator (512 columns: S_A | S_B | O_A | O_B)
-//   warps 4-19  softmax: per tile two warpgroups, "lo" owns keys 0..63 and "hi" keys 64..127 of every block, so a
-//               query row is shared by a thread pair (64 S values each; row max exchanged through smem once per
-//               block).  4 softmax warps per SM sub-partition keep the MUFU fed while others wait on TMEM / barriers.
-//               Online softmax in fp32 with lazy rescaling of O (only when the running max grows by > 2^8), P written
-//               back to TMEM as bf16 over each half's own S columns, final O / rowsum -> bf16 -> global
+//   warps 4-11  softmax, one thread per query row (tile A: warps 4-7, tile B: warps 8-11; 3 warps per SM sub-partition
+//               leave 168 registers per thread).  Online softmax in fp32 with lazy rescaling of O (only when the
+//               running max grows by > 2^8), P written back to TMEM as bf16 over the S columns it came from, final
+//               O / rowsum -> bf16 -> global.
+//
+// The unit of work is a 64-key SUB-BLOCK (half a TMA stage).  The 128 S columns of a tile are two 64-column halves used
+// as a double buffer: while the softmax threads work on S[half h] of sub-block n, Q K^T of sub-block n+1 is already in
+// (or on its way into) the other half, and as soon as P(n) is published the tensor pipe runs P(n) V and then Q K^T of
+// sub-block n+2 into half h.  The MMA round trip (P published -> P V -> next Q K^T -> S ready, ~900 cycles) therefore
+// overlaps the exp2 work of the other half instead of sitting between two exp2 sections of the same tile, which is what
+// bounded the earlier one-S-buffer-per-tile version of this kernel (profiles/r1_attn_variants.txt: 3900 cycles per 128
+// keys, 40 % of them with the MUFU pipe idle).
+//
+// exp2 runs on packed fp32 pairs (FFMA2 / FADD2 / FMNMX3 halve the issue slots of the scale, row-sum and row-max steps)
+// and a fraction of the pairs takes a polynomial exp2 on the FMA pipe instead of MUFU (see PXA_POLY_OF8).
 //
 // head_dim 72 is not a multiple of the 64-element swizzle atom, nor of UMMA K=16 / N%16: each Q/K/V tile is staged
 // as a "main" part (d 0..63, 128B swizzle) plus a "tail" part (d 64..79, 32B swizzle) whose d 72..79 are zero-filled
@@ -24,23 +32,18 @@
 #include "host_common.cuh"
 #include "ptx.cuh"
 
-// Experiment switches (tools/attn_variants.sh builds and times the combinations; defaults = the fastest measured).
-#ifndef PXA_EXP_CHUNKED
-#define PXA_EXP_CHUNKED 1     // cut the exp2 section into four dependency-chained 16-element chunks
-#endif
-#ifndef PXA_EXP_POLY
-#define PXA_EXP_POLY 1        // 1 in 4 exponentials on the FMA pipe (poly_exp2)
-#endif
-#ifndef PXA_STAGGER
-#define PXA_STAGGER 0         // delay tile B's first exp2 section until tile A's first one is done
+// Experiment switch (tools/attn_variants.sh builds and times the alternatives; default = the fastest measured).
+#ifndef PXA_POLY_OF8
+#define PXA_POLY_OF8 3        // how many of every 8 score pairs take the polynomial exp2 (FMA pipe) instead of MUFU
 #endif
 
 namespace pxa {
 
-constexpr int kAttnThreads = 640;
+constexpr int kAttnThreads = 384;   // warps 0..3: TMA, MMA, TMEM alloc, idle; warps 4..11: softmax (3 warps / sub-partition -> 168 regs)
 constexpr int kD = 72;
 constexpr int kTileQ = 128;
-constexpr int kTileKV = 128;
+constexpr int kTileKV = 128;            // keys per TMA stage
+constexpr int kSub = 64;                // keys per MMA / softmax sub-block (half a stage)
 constexpr int kKVStages = 3;
 constexpr int kMainBytes = 128 * 128;   // 128 rows x 64 bf16
 constexpr int kTailBytes = 128 * 32;    // 128 rows x 16 bf16
@@ -56,11 +59,10 @@ constexpr int kOffVTail = kOffKTail + kKVStages * kTailBytes;      // V tails ar
 constexpr int kVTailBytes = kMainBytes;                            // 128 keys x 128 B: d 64..71 valid, rest zero
 constexpr int kVTileBytes = kMainBytes + kVTailBytes;
 constexpr int kOffBars = kOffVTail + kKVStages * kVTailBytes;
-constexpr int kOffXchg = kOffBars + 256;                            // float [2 parity][2 tile][2 half][128 row]
-constexpr int kAttnSmem = kOffXchg + 2 * 2 * 2 * 128 * 4 + 1024;
+constexpr int kAttnSmem = kOffBars + 256 + 1024;                    // + alignment slack
 
 // TMEM columns
-constexpr uint32_t kColS = 0;       // S_A at 0, S_B at 128; P (bf16) aliases S: keys 0..63 -> cols [0,32), keys 64..127 -> [64,96)
+constexpr uint32_t kColS = 0;       // S_A at 0, S_B at 128, each two 64-column halves; P (bf16) over the first 32 columns of its half
 constexpr uint32_t kColO = 256;     // O_A at 256 (main 64 + tail 16), O_B at 384
 
 struct AttnParams {
@@ -92,11 +94,11 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
   uint64_t* k_empty = k_full + kKVStages;     // [kKVStages]
   uint64_t* v_full = k_empty + kKVStages;     // [kKVStages]
   uint64_t* v_empty = v_full + kKVStages;     // [kKVStages]
-  uint64_t* s_full = v_empty + kKVStages;     // [2]  MMA -> softmax (S ready; also implies previous PV done)
-  uint64_t* p_full = s_full + 2;              // [2]  softmax -> MMA (P written, S consumed)
-  uint64_t* o_full = p_full + 2;              // [1]  MMA -> softmax (all PV done)
-  uint64_t* stagger_bar = o_full + 1;         // [1]  PXA_STAGGER experiment only
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stagger_bar + 1);
+  uint64_t* s_full = v_empty + kKVStages;     // [2 tiles][2 halves]  MMA -> softmax: S of a 64-key sub-block ready
+  uint64_t* p_full = s_full + 4;              // [2][2]  softmax -> MMA: P written over that S half
+  uint64_t* pv_done = p_full + 4;             // [2]     MMA -> softmax: P V of a sub-block done (lazy-rescale path only)
+  uint64_t* o_full = pv_done + 2;             // [1]     MMA -> softmax: all P V done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = warp_idx_sync();
   const int lane = threadIdx.x & 31;
@@ -106,7 +108,8 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
   int kv_len = p.kv_len ? p.kv_len[b] : p.Nk;
   kv_len = min(max(kv_len, 0), p.Nk);
   const int kv_row0 = p.kv_off ? p.kv_off[b] : b * p.Nk;
-  const int n_blocks = (kv_len + kTileKV - 1) / kTileKV;
+  const int n_blocks = (kv_len + kTileKV - 1) / kTileKV;     // 128-key TMA stages
+  const int n_sub = (kv_len + kSub - 1) / kSub;              // 64-key sub-blocks (the MMA / softmax unit)
   const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
   int tcnt = 0;
 
@@ -119,12 +122,13 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
       mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
     }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 256);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
     }
+    mbar_init(&pv_done[0], 1);
+    mbar_init(&pv_done[1], 1);
     mbar_init(o_full, 1);
-    mbar_init(stagger_bar, 256);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -162,254 +166,245 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    if (n_blocks > 0 && elect_one()) {
-      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+    if (n_sub > 0 && elect_one()) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(128, kSub, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 80, 0, 1);        // V is MN-major; N = 80 = d 0..79
       const uint32_t sbase = smem_u32(smem);
 
-      // S_t = Q_t K^T : 4 K-steps from the 128B-swizzled main buffers + 1 from the 32B-swizzled tails
-      auto issue_qk = [&](int t, int stage) {
+      // S[t][hh] = Q_t K_hh^T for the 64 keys of half hh of a stage: 4 K-steps from the 128B-swizzled main buffers + 1
+      // from the 32B-swizzled tails.  K rows 64 hh .. 64 hh + 63 start 64 rows into the (K-major) tiles.
+      auto issue_qk = [&](int t, int stage, int hh) {
         const uint64_t qd = make_smem_desc(sbase + kOffQMain + t * kMainBytes, 16, 1024, kLayoutSW128);
-        const uint64_t kd = make_smem_desc(sbase + kOffKMain + stage * kMainBytes, 16, 1024, kLayoutSW128);
-        const uint32_t d = tmem_base + kColS + t * 128;
+        const uint64_t kd = make_smem_desc(sbase + kOffKMain + stage * kMainBytes + hh * (kSub * 128), 16, 1024, kLayoutSW128);
+        const uint32_t d = tmem_base + kColS + t * 128 + hh * kSub;
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_ss(d, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
         const uint64_t qt = make_smem_desc(sbase + kOffQTail + t * kTailBytes, 16, 256, kLayoutSW32);
-        const uint64_t kt = make_smem_desc(sbase + kOffKTail + stage * kTailBytes, 16, 256, kLayoutSW32);
+        const uint64_t kt = make_smem_desc(sbase + kOffKTail + stage * kTailBytes + hh * (kSub * 32), 16, 256, kLayoutSW32);
         umma_ss(d, qt, kt, idesc_qk, 1u);
       };
-      // O_t += P_t V : ONE N=80 MMA per 16 keys.  V is MN-major; its d extent spans two 64-element swizzle atoms: the main
-      // tile (d 0..63) and the tail tile (d 64..127, of which 64..71 are data and the rest TMA zero fill), LBO apart.
-      // (Two MMAs, N=64 + N=16, cost about twice the issue + pipeline overhead of one N=80 MMA.)  P from TMEM.
-      auto issue_pv = [&](int t, int stage, bool first) {
+      // O_t += P[t][hh] V_hh : ONE N=80 MMA per 16 keys.  V is MN-major; its d extent spans two 64-element swizzle atoms:
+      // the main tile (d 0..63) and the tail tile (d 64..127, of which 64..71 are data and the rest TMA zero fill), LBO
+      // apart.  (Two MMAs, N=64 + N=16, cost about twice the issue + pipeline overhead of one N=80 MMA.)  P from TMEM.
+      auto issue_pv = [&](int t, int stage, int hh, bool first) {
         const uint64_t vd = make_smem_desc(sbase + kOffVMain + stage * kMainBytes, kOffVTail - kOffVMain, 1024, kLayoutSW128);
-        const uint32_t pt = tmem_base + kColS + t * 128;
+        const uint32_t pt = tmem_base + kColS + t * 128 + hh * kSub;
         const uint32_t om = tmem_base + kColO + t * 128;
 #pragma unroll
-        for (int k = 0; k < kTileKV / 16; ++k) {
+        for (int k = 0; k < kSub / 16; ++k) {
           const uint32_t acc = (first && k == 0) ? 0u : 1u;
-          const uint32_t pa = pt + (k < 4 ? 8 * k : 64 + 8 * (k - 4));   // lo half at cols 0..31, hi half at 64..95
-          umma_ts(om, pa, vd + (uint64_t)(k * (2048 >> 4)), idesc_pv, acc);
+          umma_ts(om, pt + 8 * k, vd + (uint64_t)((4 * hh + k) * (2048 >> 4)), idesc_pv, acc);
         }
       };
 
+      // prologue: the first two sub-blocks' S for both tiles (the two S halves of a tile are a double buffer)
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      issue_qk(0, 0);
-      umma_commit(&s_full[0]);
-      issue_qk(1, 0);
-      umma_commit(&s_full[1]);
+      for (int hh = 0; hh < 2 && hh < n_sub; ++hh) {
+        for (int t = 0; t < 2; ++t) {
+          issue_qk(t, 0, hh);
+          umma_commit(&s_full[2 * t + hh]);
+        }
+      }
       umma_commit(&k_empty[0]);
 
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < n_blocks; ++j) {
-        int nstage = stage + 1;
-        uint32_t nphase = phase;
-        if (nstage == kKVStages) { nstage = 0; nphase ^= 1; }
-        const bool more = (j + 1 < n_blocks);
-        mbar_wait(&v_full[stage], phase);
-        // ---- tile A
-        PXA_TRACE(16, tcnt);                       // [4j+0] start waiting for P_A
-        mbar_wait(&p_full[0], j & 1);
-        PXA_TRACE(16, tcnt);                       // [4j+1] P_A ready
-        tc_fence_after();
-        issue_pv(0, stage, j == 0);
-        if (more) {
-          mbar_wait(&k_full[nstage], nphase);
+      for (int n = 0; n < n_sub; ++n) {
+        const int j = n >> 1, hh = n & 1;
+        const int stage = j % kKVStages;
+        if (hh == 0) mbar_wait(&v_full[stage], (j / kKVStages) & 1);
+        const int nn = n + 2;                      // the sub-block that reuses this S half
+        const bool has_next = nn < n_sub;
+        const int nstage = (j + 1) % kKVStages;
+        if (has_next && hh == 0) mbar_wait(&k_full[nstage], ((j + 1) / kKVStages) & 1);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          PXA_TRACE(16, tcnt);                     // [4n+2t]   start waiting for P[t]
+          mbar_wait(&p_full[2 * t + hh], j & 1);
+          PXA_TRACE(16, tcnt);                     // [4n+2t+1] P[t] ready
           tc_fence_after();
-          issue_qk(0, nstage);
-          umma_commit(&s_full[0]);
+          issue_pv(t, stage, hh, n == 0);
+          umma_commit(&pv_done[t]);
+          if (has_next) {
+            issue_qk(t, nstage, hh);
+            umma_commit(&s_full[2 * t + hh]);
+          }
         }
-        // ---- tile B
-        PXA_TRACE(16, tcnt);                       // [4j+2] A's MMAs issued, start waiting for P_B
-        mbar_wait(&p_full[1], j & 1);
-        PXA_TRACE(16, tcnt);                       // [4j+3] P_B ready
-        tc_fence_after();
-        issue_pv(1, stage, j == 0);
-        umma_commit(&v_empty[stage]);
-        if (more) {
-          issue_qk(1, nstage);
-          umma_commit(&s_full[1]);
-          umma_commit(&k_empty[nstage]);
-        }
-        stage = nstage;
-        phase = nphase;
+        if (hh == 1 || n + 1 == n_sub) umma_commit(&v_empty[stage]);            // last P V reading this V stage
+        if (has_next && (hh == 1 || nn + 1 == n_sub)) umma_commit(&k_empty[nstage]);   // last Q K^T reading that K stage
       }
       umma_commit(o_full);
     }
   } else if (warp >= 4) {
-    // ================================================================ softmax + epilogue (two threads per query row)
-    const int w = warp - 4;
-    const int t = w >> 3;                          // tile 0 (A) / 1 (B)
-    const int hf = (w >> 2) & 1;                   // 0: keys 0..63 of each block, 1: keys 64..127
-    const int qd = w & 3;                          // TMEM sub-partition (= warp % 4)
+    // ================================================================ softmax + epilogue (one thread per query row)
+    const int w = warp - 4;                        // 0..7
+    const int t = w >> 2;                          // tile 0 (A) / 1 (B)
+    const int qd = warp & 3;                       // TMEM sub-partition a warp may access (= warp % 4)
     const int row_in_tile = qd * 32 + lane;
     const int qrow = q0 + t * kTileQ + row_in_tile;             // query index within the sample
     const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
-    const uint32_t t_s = tmem_base + kColS + t * 128 + hf * 64 + lane_sel;   // this half's 64 S columns (P over the first 32)
-    const uint32_t t_o = tmem_base + kColO + t * 128 + hf * 32 + lane_sel;   // lo: O cols 0..31, hi: O cols 32..71
+    const uint32_t t_s = tmem_base + kColS + t * 128 + lane_sel;   // two 64-column S halves; P (bf16) over the first 32 of each
+    const uint32_t t_o = tmem_base + kColO + t * 128 + lane_sel;   // O columns 0..79 (d 0..71 + 8 zero pad)
     const float sl2 = p.scale_log2;
-    float* xchg = reinterpret_cast<float*>(smem + kOffXchg);
-    const uint32_t bar_id = 1 + t;                 // named barrier of this tile's 256 softmax threads
+    const uint64_t sl2x2 = f32x2(sl2, sl2);
 
-    float m_ref = -INFINITY;     // reference max used in the exponent (raw S units); identical in both halves
-    float row_sum = 0.f;         // partial: this half's keys only
+    float m_ref = -INFINITY;     // reference max used in the exponent (raw S units)
+    uint64_t sa = f32x2(0.f, 0.f), sb = f32x2(0.f, 0.f);        // running row sum, four partial lanes
 
-    auto softmax_block = [&](const int j, auto masked_tag) {
-      PXA_TRACE(w, tcnt);                          // [7j+0] start waiting for S
-      mbar_wait(&s_full[t], j & 1);
-      PXA_TRACE(w, tcnt);                          // [7j+1] S ready
+    auto softmax_sub = [&](const int n, auto masked_tag) {
+      const int j = n >> 1, hh = n & 1;
+      const uint32_t ts = t_s + hh * kSub;
+      PXA_TRACE(w, tcnt);                          // [7n+0] start waiting for S
+      mbar_wait(&s_full[2 * t + hh], j & 1);
+      PXA_TRACE(w, tcnt);                          // [7n+1] S ready
       tc_fence_after();
-      uint32_t v0[32], v1[32];
-      tmem_ld_32x32b_x32_pair(t_s, v0, t_s + 32, v1);
-      PXA_TRACE(w, tcnt);                          // [7j+2] S in registers
-      const int rem = kv_len - j * kTileKV - hf * 64;           // valid keys among this half's 64
-      // Only the last block of a sample can be partial.  The masking selects are compiled into a separate copy of the
-      // block body: if-converted into the common path they cost ~250 extra issue slots per thread per block (the
-      // softmax warps are issue-bound: 4 warps per sub-partition share one issue port).
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32b_x32_nowait(ts, va);
+      tmem_ld_32x32b_x32_nowait(ts + 32, vb);
+      tmem_ld_wait_x32(va);
+      tmem_ld_wait_x32(vb);
+      PXA_TRACE(w, tcnt);                          // [7n+2] S in registers
+      // Only the last sub-block of a sample can be partial.  The masking selects are compiled into a separate copy of
+      // the body: if-converted into the common path they would cost 64 extra issue slots per thread per sub-block.
       if constexpr (decltype(masked_tag)::value) {
-        const uint32_t ninf = 0xff800000u;
+        const int rem = kv_len - n * kSub;         // valid keys in this sub-block
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          if (i >= rem) v0[i] = ninf;
-          if (32 + i >= rem) v1[i] = ninf;
+          if (i >= rem) va[i] = 0xff800000u;       // -inf
+          if (32 + i >= rem) vb[i] = 0xff800000u;
         }
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        mx0 = fmaxf(mx0, __uint_as_float(v0[2 * i]));
-        mx1 = fmaxf(mx1, __uint_as_float(v0[2 * i + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(v1[2 * i]));
-        mx3 = fmaxf(mx3, __uint_as_float(v1[2 * i + 1]));
+      for (int i = 0; i < 8; ++i) {
+        mx0 = fmax3(mx0, __uint_as_float(va[4 * i]), __uint_as_float(va[4 * i + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(va[4 * i + 2]), __uint_as_float(va[4 * i + 3]));
+        mx2 = fmax3(mx2, __uint_as_float(vb[4 * i]), __uint_as_float(vb[4 * i + 1]));
+        mx3 = fmax3(mx3, __uint_as_float(vb[4 * i + 2]), __uint_as_float(vb[4 * i + 3]));
       }
-      const float m_half = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      float* xb = xchg + ((j & 1) * 4 + t * 2) * 128;
-      xb[hf * 128 + row_in_tile] = m_half;
-      named_bar_sync(bar_id, 256);
-      PXA_TRACE(w, tcnt);                          // [7j+3] row max exchanged
-      const float m_new = fmaxf(fmaxf(m_half, xb[(hf ^ 1) * 128 + row_in_tile]), m_ref);
+      const float m_new = fmaxf(fmax3(mx0, mx1, mx2), fmaxf(mx3, m_ref));
+      PXA_TRACE(w, tcnt);                          // [7n+3] row max known
       // Lazy rescale: keep the old reference max unless it is stale by more than 2^8 (P stays <= 256, exact in the
-      // fp32 accumulators).  The decision is warp-uniform (the TMEM round trip below is warp-collective) and identical
-      // in the partner warp of the other half, which sees the same m_new / m_ref for the same 32 rows.
-      const bool stale = (m_new - m_ref) * sl2 > 8.0f;          // true on the first block (m_ref = -inf)
+      // fp32 accumulators).  The decision is warp-uniform because the TMEM round trip below is warp-collective.
+      const bool stale = (m_new - m_ref) * sl2 > 8.0f;          // true on the first sub-block (m_ref = -inf)
       if (__any_sync(0xffffffffu, stale)) {
         const float factor = (m_ref == -INFINITY) ? 0.f : fast_exp2((m_ref - m_new) * sl2);
-        if (j > 0) {
-          // PV of block j-1 has completed (it was issued before the QK^T that produced this S)
-          uint32_t o0[32], o1[8];
-          tmem_ld_32x32b_x32(t_o, o0);
+        if (n > 0) {
+          // O may only be touched between P V (n-1) and P V (n): the latter waits for this thread's P, the former is
+          // awaited here (the S double buffer lets Q K^T run ahead, so "S ready" no longer implies "P V done").
+          mbar_wait(&pv_done[t], (n - 1) & 1);
+          tc_fence_after();
+          // d 0..71 in 9 pieces of 8 columns (rare path: a short register footprint matters more than TMEM round
+          // trips); the pad columns 72..79 hold zeros and need no scaling.
+          for (int piece = 0; piece < 9; ++piece) {
+            uint32_t o[8];
+            tmem_ld_32x32b_x8(t_o + 8 * piece, o);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * factor);
-          tmem_st_32x32b_x32(t_o, o0);
-          if (hf == 1) {                         // warp-uniform: d 64..71 (the 8 zero pad columns 72..79 need no scaling)
-            tmem_ld_32x32b_x8(t_o + 32, o1);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o1[i] = __float_as_uint(__uint_as_float(o1[i]) * factor);
-            tmem_st_32x32b_x8(t_o + 32, o1);
+            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+            tmem_st_32x32b_x8(t_o + 8 * piece, o);
           }
         }
-        row_sum *= factor;
+        const uint64_t f2 = f32x2(factor, factor);
+        sa = mul2(sa, f2);
+        sb = mul2(sb, f2);
         m_ref = m_new;
       }
-      const float neg_m = -m_ref * sl2;
-      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+      const float nm = -m_ref * sl2;
+      const uint64_t nm2 = f32x2(nm, nm);
+      // exp2 on packed fp32 pairs (FFMA2 / FADD2: one issue slot for two lane-ops).  PXA_POLY_OF8 of every 8 pairs take
+      // the polynomial exp2 (FMA pipe) instead of MUFU (16 results/clk/SM), so that both pipes and the issue port end up
+      // about equally loaded.
       uint32_t pk[32];
-      // exp2 section.  Per 4 elements: 3 on the MUFU pipe, 1 on the FMA/ALU pipes (poly_exp2).  The work is cut into four
-      // 16-element chunks chained through a register dependency, so the compiler cannot cluster all MUFU instructions
-      // into one burst: warps issue in order, and when the 4 warps of a sub-partition all sit in a MUFU burst at the same
-      // time the FMA pipe idles (and vice versa).  Fine-grained chunks let one warp's MUFU work overlap another's FMA work.
-      float nm = neg_m;
-#if PXA_STAGGER
-      if (j == 0 && t == 1) {
-        mbar_wait(stagger_bar, 0);
-        asm volatile("" : "+f"(nm)::"memory");       // the exp2 below may not be hoisted above the wait
-      }
-#endif
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-#pragma unroll
-        for (int i = 4 * c; i < 4 * c + 4; ++i) {
-          const float a0 = fast_exp2(fmaf(__uint_as_float(v0[2 * i]), sl2, nm));
-          const float a1 = fast_exp2(fmaf(__uint_as_float(v0[2 * i + 1]), sl2, nm));
-          const float b0 = fast_exp2(fmaf(__uint_as_float(v1[2 * i]), sl2, nm));
-#if PXA_EXP_POLY
-          const float b1 = poly_exp2(fmaf(__uint_as_float(v1[2 * i + 1]), sl2, nm));
-#else
-          const float b1 = fast_exp2(fmaf(__uint_as_float(v1[2 * i + 1]), sl2, nm));
-#endif
-          sum0 += a0; sum1 += a1; sum2 += b0; sum3 += b1;
-          pk[i] = pack_bf16x2(a0, a1);
-          pk[16 + i] = pack_bf16x2(b0, b1);
+      // one pair of scores -> exp2 -> running packed sum + bf16x2 P word; `pair` (0..31) selects MUFU or polynomial
+      auto exp_pair = [&](float s0, float s1, int pair, uint64_t& acc, uint32_t& packed) {
+        const uint64_t x = fma2(f32x2(s0, s1), sl2x2, nm2);
+        uint64_t e;
+        float e0, e1;
+        if (((pair * PXA_POLY_OF8) & 7) < PXA_POLY_OF8) {
+          e = poly_exp2_x2(x);
+          f32x2_split(e, e0, e1);
+        } else {
+          float x0, x1;
+          f32x2_split(x, x0, x1);
+          e0 = fast_exp2(x0);
+          e1 = fast_exp2(x1);
+          e = f32x2(e0, e1);
         }
-#if PXA_EXP_CHUNKED
-        if (c < 3) asm volatile("" : "+f"(nm) : "f"(sum0), "f"(sum1), "f"(sum2), "f"(sum3));
-#endif
+        acc = add2(acc, e);
+        packed = pack_bf16x2(e0, e1);
+      };
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        exp_pair(__uint_as_float(va[2 * i]), __uint_as_float(va[2 * i + 1]), i, sa, pk[i]);
+        exp_pair(__uint_as_float(va[2 * i + 2]), __uint_as_float(va[2 * i + 3]), i + 1, sb, pk[i + 1]);
       }
-#if PXA_STAGGER
-      if (j == 0 && t == 0) {
-        asm volatile("" ::"r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]),
-                     "r"(pk[8]), "r"(pk[9]), "r"(pk[10]), "r"(pk[11]), "r"(pk[12]), "r"(pk[13]), "r"(pk[14]), "r"(pk[15]),
-                     "r"(pk[16]), "r"(pk[17]), "r"(pk[18]), "r"(pk[19]), "r"(pk[20]), "r"(pk[21]), "r"(pk[22]),
-                     "r"(pk[23]), "r"(pk[24]), "r"(pk[25]), "r"(pk[26]), "r"(pk[27]), "r"(pk[28]), "r"(pk[29]),
-                     "r"(pk[30]), "r"(pk[31])
-                     : "memory");
-        mbar_arrive(stagger_bar);
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        exp_pair(__uint_as_float(vb[2 * i]), __uint_as_float(vb[2 * i + 1]), 16 + i, sa, pk[16 + i]);
+        exp_pair(__uint_as_float(vb[2 * i + 2]), __uint_as_float(vb[2 * i + 3]), 16 + i + 1, sb, pk[16 + i + 1]);
       }
-#endif
       if (tracing) {   // debug only: pin the end of the exp2 section for the cycle trace
-        asm volatile("" ::"r"(pk[0]), "r"(pk[3]), "r"(pk[7]), "r"(pk[11]), "r"(pk[15]), "r"(pk[16]), "r"(pk[19]), "r"(pk[23]),
-                     "r"(pk[27]), "r"(pk[31]), "f"(sum0), "f"(sum1), "f"(sum2), "f"(sum3) : "memory");
+        asm volatile("" ::"r"(pk[0]), "r"(pk[7]), "r"(pk[15]), "r"(pk[23]), "r"(pk[31]), "l"(sa), "l"(sb) : "memory");
       }
-      PXA_TRACE(w, tcnt);                          // [7j+4] exp2 section done
-      // P (bf16, this half's 64 keys = 32 packed columns) over the first 32 of this half's own S columns
-      tmem_st_32x32b_x32(t_s, pk);
+      PXA_TRACE(w, tcnt);                          // [7n+4] exp2 section done
+      // P (bf16, 64 keys = 32 packed columns) over the first 32 columns of this S half
+      tmem_st_32x32b_x32(ts, pk);
       tmem_st_wait();
-      PXA_TRACE(w, tcnt);                          // [7j+5] P in TMEM
+      PXA_TRACE(w, tcnt);                          // [7n+5] P in TMEM
       tc_fence_before();
-      mbar_arrive(&p_full[t]);
-      PXA_TRACE(w, tcnt);                          // [7j+6] P published
-      row_sum += (sum0 + sum1) + (sum2 + sum3);
+      mbar_arrive(&p_full[2 * t + hh]);
+      PXA_TRACE(w, tcnt);                          // [7n+6] P published
     };
-    for (int j = 0; j + 1 < n_blocks; ++j) softmax_block(j, std::false_type{});
-    if (n_blocks > 0) {
-      if (kv_len % kTileKV != 0) softmax_block(n_blocks - 1, std::true_type{});
-      else softmax_block(n_blocks - 1, std::false_type{});
+    for (int n = 0; n + 1 < n_sub; ++n) softmax_sub(n, std::false_type{});
+    if (n_sub > 0) {
+      if (kv_len % kSub != 0) softmax_sub(n_sub - 1, std::true_type{});
+      else softmax_sub(n_sub - 1, std::false_type{});
+    }
+    float row_sum;
+    {
+      float s0, s1, s2, s3;
+      f32x2_split(sa, s0, s1);
+      f32x2_split(sb, s2, s3);
+      row_sum = (s0 + s1) + (s2 + s3);
     }
 
-    // ---- epilogue: O / row_sum -> bf16 -> out[(b*Nq + qrow), h*72 + hf*32 .. ]   (lo: d 0..31, hi: d 32..71)
-    float* xs = xchg + (t * 2) * 128;               // parity-0 slots are free again after the last block's barrier
-    named_bar_sync(bar_id, 256);                    // everybody is done reading the max exchange buffers
-    xs[hf * 128 + row_in_tile] = row_sum;
-    named_bar_sync(bar_id, 256);
-    const float total = row_sum + xs[(hf ^ 1) * 128 + row_in_tile];
-    uint32_t o0[32], o1[8];
+    // ---- epilogue: O / row_sum -> bf16 -> out[(b*Nq + qrow), h*72 .. h*72+71]
     if (n_blocks > 0) {
       mbar_wait(o_full, 0);
       tc_fence_after();
-      tmem_ld_32x32b_x32(t_o, o0);
-      if (hf == 1) tmem_ld_32x32b_x8(t_o + 32, o1);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o0[i] = 0u;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o1[i] = 0u;
     }
-    if (qrow < p.Nq) {
-      const float inv = total > 0.f ? 1.0f / total : 0.f;
-      __nv_bfloat16* dst = p.out + (size_t)(b * p.Nq + qrow) * p.ldo + h * kD + hf * 32;
-      uint4* d4 = reinterpret_cast<uint4*>(dst);
+    const float inv = row_sum > 0.f ? 1.0f / row_sum : 0.f;      // n_blocks == 0 (no keys): zeros
+    uint4* d4 = reinterpret_cast<uint4*>(p.out + (size_t)(b * p.Nq + qrow) * p.ldo + h * kD);
+    const bool row_ok = qrow < p.Nq;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        d4[c] = make_uint4(pack_bf16x2(__uint_as_float(o0[8 * c]) * inv, __uint_as_float(o0[8 * c + 1]) * inv),
-                           pack_bf16x2(__uint_as_float(o0[8 * c + 2]) * inv, __uint_as_float(o0[8 * c + 3]) * inv),
-                           pack_bf16x2(__uint_as_float(o0[8 * c + 4]) * inv, __uint_as_float(o0[8 * c + 5]) * inv),
-                           pack_bf16x2(__uint_as_float(o0[8 * c + 6]) * inv, __uint_as_float(o0[8 * c + 7]) * inv));
+    for (int piece = 0; piece < 2; ++piece) {
+      uint32_t o[32];
+      if (n_blocks > 0) {
+        tmem_ld_32x32b_x32(t_o + 32 * piece, o);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0u;
       }
-      if (hf == 1) {
-        d4[4] = make_uint4(pack_bf16x2(__uint_as_float(o1[0]) * inv, __uint_as_float(o1[1]) * inv),
+      if (row_ok) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          d4[4 * piece + c] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv),
+                                         pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv),
+                                         pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv),
+                                         pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv));
+        }
+      }
+    }
+    {
+      uint32_t o1[8];
+      if (n_blocks > 0) {
+        tmem_ld_32x32b_x8(t_o + 64, o1);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o1[i] = 0u;
+      }
+      if (row_ok) {
+        d4[8] = make_uint4(pack_bf16x2(__uint_as_float(o1[0]) * inv, __uint_as_float(o1[1]) * inv),
                            pack_bf16x2(__uint_as_float(o1[2]) * inv, __uint_as_float(o1[3]) * inv),
                            pack_bf16x2(__uint_as_float(o1[4]) * inv, __uint_as_float(o1[5]) * inv),
                            pack_bf16x2(__uint_as_float(o1[6]) * inv, __uint_as_float(o1[7]) * inv));

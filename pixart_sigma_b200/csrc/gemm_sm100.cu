@@ -144,7 +144,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int r = q * 32 + lane;                                  // row of the 128-row tile owned by this thread
     uint8_t* rbufs = epi_smem;
     uint8_t* abufs = epi_smem + kResBufs * kResChunkBytes;
-    const bool issuer = kTmaRes && (warp == kEpiWarp0) && (lane == 0);   // owns every TMA op of the epilogue
+    // One thread of the first epilogue warp owns every TMA op of the epilogue.  It is picked with elect.sync inside a
+    // warp-uniform branch (always the same lane for a full warp), so the TMA / mbarrier operands stay in uniform
+    // registers; `issuer_warp` guards the converged regions, `issuer` the elected lane (bulk groups are per thread).
+    const bool issuer_warp = kTmaRes && (warp == kEpiWarp0);
+    bool issuer = false;
+    if (issuer_warp) issuer = elect_one() != 0;
     // In-place update without a bf16 copy: skip the residual read altogether and let TMA reduce-add the update into x.
     const bool reduce = kTmaRes && p.out_aux == nullptr && p.residual == p.out;
     int l_tile = blockIdx.x, l_cc = 0, l_g = 0;                   // issuer: next residual chunk to request
@@ -158,8 +163,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ++l_g;
       if (++l_cc == chunks_of_tile<BN>(p, ln0)) { l_cc = 0; l_tile += gridDim.x; }
     };
-    if (issuer && !reduce) {
-      for (int i = 0; i < kResBufs - 1; ++i) request_next();
+    if (issuer_warp && !reduce) {
+      if (elect_one()) {
+        for (int i = 0; i < kResBufs - 1; ++i) request_next();
+      }
     }
     int g = 0;
     uint8_t* stile = epi_smem + (warp - kEpiWarp0) * 4096;       // bf16 paths: per-warp transpose tile
@@ -194,19 +201,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           residual_chunk_row_c(v, p, cb, rb, ab, r, cc * 32, m0 + r, n0 + cc * 32, reduce);
           fence_proxy_async_smem();                                 // generic-proxy writes -> visible to the TMA store
           stamp();                                                  // chunk: computed
-          if (issuer) tma_store_wait_read<0>();                     // earlier stores have drained their buffers
+          if (issuer_warp) {
+            if (elect_one()) tma_store_wait_read<0>();              // earlier stores have drained their buffers
+          }
           stamp();                                                  // chunk: previous store drained
           named_bar_sync(1, kNumEpiThreads);
           stamp();                                                  // chunk: barrier passed
-          if (issuer) {
-            if (reduce) {
-              tma_reduce_add_2d(&tmap_out, rb, n0 + cc * 32, m0);
-              tma_store_commit();
-            } else {
-              tma_store_2d(&tmap_out, rb, n0 + cc * 32, m0);
-              if (ab != nullptr) tma_store_2d(&tmap_aux, ab, n0 + cc * 32, m0);
-              tma_store_commit();
-              request_next();                                       // refills the buffer chunk g-1 has just left
+          if (issuer_warp) {
+            if (elect_one()) {
+              if (reduce) {
+                tma_reduce_add_2d(&tmap_out, rb, n0 + cc * 32, m0);
+                tma_store_commit();
+              } else {
+                tma_store_2d(&tmap_out, rb, n0 + cc * 32, m0);
+                if (ab != nullptr) tma_store_2d(&tmap_aux, ab, n0 + cc * 32, m0);
+                tma_store_commit();
+                request_next();                                     // refills the buffer chunk g-1 has just left
+              }
             }
           }
           ++g;
@@ -240,7 +251,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
-    if (issuer) tma_store_wait_all<0>();
+    if (issuer_warp) {
+      if (elect_one()) tma_store_wait_all<0>();
+    }
   }
 
   tc_fence_before();
@@ -424,6 +437,8 @@ extern "C" int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream) {
     } else if (a.K >= 2304) {
       pair = true;
       bn = 192;
+    } else {
+      bn = 256;      // fewer, wider tiles: 100 us vs 107 us (BN = 192) at N = K = 1152, even with a half-empty last column tile
     }
   }
   if (pair) return gemm_pair_dispatch(a, bn, s);

@@ -33,6 +33,10 @@ PXA_DEVICE void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+PXA_DEVICE void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ----------------------------------------------------------------------------- mbarrier
 PXA_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
@@ -304,6 +308,57 @@ PXA_DEVICE float poly_exp2(float x) {
   const float p = fmaf(fmaf(fmaf(0.05517186224460602f, f, 0.2426111400127411f), f, 0.6932609677314758f), f,
                        0.9999280571937561f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+// ---- packed fp32 pairs (FFMA2 / FADD2 / FMUL2: one issue slot for two fp32 lanes-ops) and 3-input max (FMNMX3)
+PXA_DEVICE uint64_t f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};\n" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+PXA_DEVICE void f32x2_split(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;\n" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+PXA_DEVICE uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;\n" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+PXA_DEVICE uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;\n" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+PXA_DEVICE uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;\n" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+PXA_DEVICE uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;\n" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+PXA_DEVICE float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;\n" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// poly_exp2 on a pair: the three Horner steps and the range split run as packed ops (6 issue slots per pair instead of 12)
+PXA_DEVICE uint64_t poly_exp2_x2(uint64_t x) {
+  float x0, x1;
+  f32x2_split(x, x0, x1);
+  x = f32x2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+  const uint64_t magic = f32x2(12582912.0f, 12582912.0f);
+  const uint64_t t = add2(x, magic);
+  const uint64_t f = sub2(x, sub2(t, magic));
+  uint64_t p = fma2(f32x2(0.05517186224460602f, 0.05517186224460602f), f, f32x2(0.2426111400127411f, 0.2426111400127411f));
+  p = fma2(p, f, f32x2(0.6932609677314758f, 0.6932609677314758f));
+  p = fma2(p, f, f32x2(0.9999280571937561f, 0.9999280571937561f));
+  float p0, p1, t0, t1;
+  f32x2_split(p, p0, p1);
+  f32x2_split(t, t0, t1);
+  return f32x2(__int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23)),
+               __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23)));
 }
 PXA_DEVICE float fast_tanh(float x) {
   float y;

@@ -21,16 +21,17 @@ torch.cuda.synchronize()
 print(f"kernel {e0.elapsed_time(e1):.3f} ms, {4*B*H*N*N*72/e0.elapsed_time(e1)/1e9:.1f} TFLOP/s")
 tr = trace.cpu()
 t0 = int(tr[tr > 0].min())
-names = {0: "A-lo q0", 4: "A-hi q0", 8: "B-lo q0", 12: "B-hi q0"}
-print("softmax stamps per block j: [wait S | S ready | S in regs | max exchanged | exp done | P in TMEM | P published]")
+names = {0: "A w0", 4: "B w0"}
+print("softmax stamps per 64-key sub-block n: [wait S | S ready | S in regs | row max | exp done | P in TMEM | P published]")
 for w, nm in names.items():
-    for j in range(0, 6):
-        row = [int(v) - t0 for v in tr[w, 7 * j:7 * j + 7]]
+    for n in range(0, 8):
+        row = [int(v) - t0 for v in tr[w, 7 * n:7 * n + 7]]
         d = [row[i + 1] - row[i] for i in range(6)]
-        print(f"  {nm} j={j}: {row}  d(waitS,ld,xchg,exp,st,arrive)={d}")
-print("MMA thread per block j: [wait S_A free | wait P_A | P_A ready | wait P_B]")
-for j in range(0, 10):
-    row = [int(v) - t0 for v in tr[16, 4 * j:4 * j + 4]]
-    print(f"  j={j}: {row}  d={[row[i+1]-row[i] for i in range(3)]}")
-per = [int(tr[16, 4 * (j + 1)]) - int(tr[16, 4 * j]) for j in range(4, 28)]
-print("cycles per block (MMA loop period), j=4..27:", per, "mean", sum(per) / len(per))
+        print(f"  {nm} n={n}: {row}  d(waitS,ld,max,exp,st,arrive)={d}")
+print("MMA thread per sub-block n: [wait P_A | P_A ready | wait P_B | P_B ready]")
+for n in range(0, 12):
+    row = [int(v) - t0 for v in tr[16, 4 * n:4 * n + 4]]
+    print(f"  n={n}: {row}  d={[row[i+1]-row[i] for i in range(3)]}")
+per = [int(tr[16, 4 * (n + 1)]) - int(tr[16, 4 * n]) for n in range(8, 56)]
+print("cycles per sub-block (MMA loop period), n=8..55:", per)
+print("mean cycles per 128 keys:", 2 * sum(per) / len(per))
