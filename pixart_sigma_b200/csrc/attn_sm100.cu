@@ -33,8 +33,14 @@
 #include "ptx.cuh"
 
 // Experiment switch (tools/attn_variants.sh builds and times the alternatives; default = the fastest measured).
+#ifndef PXA_SUM_MMA
+#define PXA_SUM_MMA 1         // row sums of P on the tensor pipe (P x ones, N=16) instead of 32 FADD2 per thread per sub-block
+#endif
+#ifndef PXA_PREFETCH_S
+#define PXA_PREFETCH_S 1      // read S of sub-block n+1 from TMEM behind the exp2 work of sub-block n
+#endif
 #ifndef PXA_POLY_OF8
-#define PXA_POLY_OF8 3        // how many of every 8 score pairs take the polynomial exp2 (FMA pipe) instead of MUFU
+#define PXA_POLY_OF8 0        // how many of every 8 score pairs take the polynomial exp2 (FMA pipe) instead of MUFU
 #endif
 
 namespace pxa {
@@ -58,12 +64,14 @@ constexpr int kOffKTail = kOffQTail + 2 * kTailBytes;
 constexpr int kOffVTail = kOffKTail + kKVStages * kTailBytes;      // V tails are full 128 B-row tiles (see below)
 constexpr int kVTailBytes = kMainBytes;                            // 128 keys x 128 B: d 64..71 valid, rest zero
 constexpr int kVTileBytes = kMainBytes + kVTailBytes;
-constexpr int kOffBars = kOffVTail + kKVStages * kVTailBytes;
+constexpr int kOffOnes = kOffVTail + kKVStages * kVTailBytes;      // 2 KB of bf16 1.0: B operand of the row-sum MMA
+constexpr int kOffBars = kOffOnes + 2048;
 constexpr int kAttnSmem = kOffBars + 256 + 1024;                    // + alignment slack
 
 // TMEM columns
 constexpr uint32_t kColS = 0;       // S_A at 0, S_B at 128, each two 64-column halves; P (bf16) over the first 32 columns of its half
 constexpr uint32_t kColO = 256;     // O_A at 256 (main 64 + tail 16), O_B at 384
+constexpr uint32_t kColL = 336;     // L_A at 336, L_B at 464: row sums of P (16 identical fp32 columns, PXA_SUM_MMA)
 
 struct AttnParams {
   __nv_bfloat16* out;
@@ -132,6 +140,13 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
+#if PXA_SUM_MMA
+  if (warp == 3) {
+    uint4* ones = reinterpret_cast<uint4*>(smem + kOffOnes);
+    for (int i = lane; i < 2048 / 16; i += 32) ones[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+    fence_proxy_async_smem();                    // generic-proxy stores -> visible to the tensor core's smem reads
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -195,6 +210,15 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
           const uint32_t acc = (first && k == 0) ? 0u : 1u;
           umma_ts(om, pt + 8 * k, vd + (uint64_t)((4 * hh + k) * (2048 >> 4)), idesc_pv, acc);
         }
+#if PXA_SUM_MMA
+        // L_t += P[t][hh] 1 : the row sums of the (bf16-rounded) P that P V multiplies, for free on the tensor pipe.  The
+        // B operand is all ones, so any valid descriptor over the 2 KB ones region will do.
+        constexpr uint32_t idesc_l = make_idesc_bf16(128, 16, 0, 0);
+        const uint64_t od = make_smem_desc(sbase + kOffOnes, 16, 1024, kLayoutSW128);
+        const uint32_t lm = tmem_base + kColL + t * 128;
+#pragma unroll
+        for (int k = 0; k < kSub / 16; ++k) umma_ts(lm, pt + 8 * k, od, idesc_l, (first && k == 0) ? 0u : 1u);
+#endif
       };
 
       // prologue: the first two sub-blocks' S for both tiles (the two S halves of a tile are a double buffer)
@@ -249,20 +273,36 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
     const uint64_t sl2x2 = f32x2(sl2, sl2);
 
     float m_ref = -INFINITY;     // reference max used in the exponent (raw S units)
-    uint64_t sa = f32x2(0.f, 0.f), sb = f32x2(0.f, 0.f);        // running row sum, four partial lanes
+    uint64_t sa = f32x2(0.f, 0.f), sb = f32x2(0.f, 0.f);        // running row sum, four partial lanes (!PXA_SUM_MMA)
+    const uint32_t t_l = tmem_base + kColL + t * 128 + lane_sel;
 
+    uint32_t va[32], vb[32];       // the 64 scores of this row in the current sub-block
+#if PXA_PREFETCH_S
+    if (n_sub > 0) {
+      mbar_wait(&s_full[2 * t], 0);
+      tc_fence_after();
+      tmem_ld_32x32b_x32_nowait(t_s, va);
+      tmem_ld_32x32b_x32_nowait(t_s + 32, vb);
+      tmem_ld_wait_x32(va);
+      tmem_ld_wait_x32(vb);
+    }
+#endif
     auto softmax_sub = [&](const int n, auto masked_tag) {
-      const int j = n >> 1, hh = n & 1;
+      [[maybe_unused]] const int j = n >> 1;
+      const int hh = n & 1;
       const uint32_t ts = t_s + hh * kSub;
       PXA_TRACE(w, tcnt);                          // [7n+0] start waiting for S
+#if !PXA_PREFETCH_S
       mbar_wait(&s_full[2 * t + hh], j & 1);
       PXA_TRACE(w, tcnt);                          // [7n+1] S ready
       tc_fence_after();
-      uint32_t va[32], vb[32];
       tmem_ld_32x32b_x32_nowait(ts, va);
       tmem_ld_32x32b_x32_nowait(ts + 32, vb);
       tmem_ld_wait_x32(va);
       tmem_ld_wait_x32(vb);
+#else
+      PXA_TRACE(w, tcnt);                          // [7n+1] (S was fetched during the previous sub-block)
+#endif
       PXA_TRACE(w, tcnt);                          // [7n+2] S in registers
       // Only the last sub-block of a sample can be partial.  The masking selects are compiled into a separate copy of
       // the body: if-converted into the common path they would cost 64 extra issue slots per thread per sub-block.
@@ -296,12 +336,13 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
           tc_fence_after();
           // d 0..71 in 9 pieces of 8 columns (rare path: a short register footprint matters more than TMEM round
           // trips); the pad columns 72..79 hold zeros and need no scaling.
-          for (int piece = 0; piece < 9; ++piece) {
+          for (int piece = 0; piece < 9 + PXA_SUM_MMA; ++piece) {
+            const uint32_t ta = piece < 9 ? t_o + 8 * piece : t_l;       // the row-sum columns scale like O
             uint32_t o[8];
-            tmem_ld_32x32b_x8(t_o + 8 * piece, o);
+            tmem_ld_32x32b_x8(ta, o);
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-            tmem_st_32x32b_x8(t_o + 8 * piece, o);
+            tmem_st_32x32b_x8(ta, o);
           }
         }
         const uint64_t f2 = f32x2(factor, factor);
@@ -316,7 +357,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       // about equally loaded.
       uint32_t pk[32];
       // one pair of scores -> exp2 -> running packed sum + bf16x2 P word; `pair` (0..31) selects MUFU or polynomial
-      auto exp_pair = [&](float s0, float s1, int pair, uint64_t& acc, uint32_t& packed) {
+      auto exp_pair = [&](float s0, float s1, int pair, [[maybe_unused]] uint64_t& acc, uint32_t& packed) {
         const uint64_t x = fma2(f32x2(s0, s1), sl2x2, nm2);
         uint64_t e;
         float e0, e1;
@@ -330,7 +371,9 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
           e1 = fast_exp2(x1);
           e = f32x2(e0, e1);
         }
+#if !PXA_SUM_MMA
         acc = add2(acc, e);
+#endif
         packed = pack_bf16x2(e0, e1);
       };
 #pragma unroll
@@ -338,11 +381,25 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         exp_pair(__uint_as_float(va[2 * i]), __uint_as_float(va[2 * i + 1]), i, sa, pk[i]);
         exp_pair(__uint_as_float(va[2 * i + 2]), __uint_as_float(va[2 * i + 3]), i + 1, sb, pk[i + 1]);
       }
+#if PXA_PREFETCH_S
+      // S of the next sub-block sits in the other S half (normally complete long ago): fetch it into the registers the
+      // first 32 scores have just left, behind the second half of this sub-block's exp2 work.
+      const bool has_next = n + 1 < n_sub;
+      const uint32_t tn = t_s + (hh ^ 1) * kSub;
+      if (has_next) {
+        mbar_wait(&s_full[2 * t + (hh ^ 1)], ((n + 1) >> 1) & 1);
+        tc_fence_after();
+        tmem_ld_32x32b_x32_nowait(tn, va);
+      }
+#endif
 #pragma unroll
       for (int i = 0; i < 16; i += 2) {
         exp_pair(__uint_as_float(vb[2 * i]), __uint_as_float(vb[2 * i + 1]), 16 + i, sa, pk[16 + i]);
         exp_pair(__uint_as_float(vb[2 * i + 2]), __uint_as_float(vb[2 * i + 3]), 16 + i + 1, sb, pk[16 + i + 1]);
       }
+#if PXA_PREFETCH_S
+      if (has_next) tmem_ld_32x32b_x32_nowait(tn + 32, vb);
+#endif
       if (tracing) {   // debug only: pin the end of the exp2 section for the cycle trace
         asm volatile("" ::"r"(pk[0]), "r"(pk[7]), "r"(pk[15]), "r"(pk[23]), "r"(pk[31]), "l"(sa), "l"(sb) : "memory");
       }
@@ -353,7 +410,13 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       PXA_TRACE(w, tcnt);                          // [7n+5] P in TMEM
       tc_fence_before();
       mbar_arrive(&p_full[2 * t + hh]);
-      PXA_TRACE(w, tcnt);                          // [7n+6] P published
+#if PXA_PREFETCH_S
+      if (has_next) {
+        tmem_ld_wait_x32(va);
+        tmem_ld_wait_x32(vb);
+      }
+#endif
+      PXA_TRACE(w, tcnt);                          // [7n+6] P published (and the next S in registers)
     };
     for (int n = 0; n + 1 < n_sub; ++n) softmax_sub(n, std::false_type{});
     if (n_sub > 0) {
@@ -372,6 +435,11 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
     if (n_blocks > 0) {
       mbar_wait(o_full, 0);
       tc_fence_after();
+#if PXA_SUM_MMA
+      uint32_t l[8];
+      tmem_ld_32x32b_x8(t_l, l);
+      row_sum = __uint_as_float(l[0]);
+#endif
     }
     const float inv = row_sum > 0.f ? 1.0f / row_sum : 0.f;      // n_blocks == 0 (no keys): zeros
     uint4* d4 = reinterpret_cast<uint4*>(p.out + (size_t)(b * p.Nq + qrow) * p.ldo + h * kD);
