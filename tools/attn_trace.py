@@ -24,7 +24,7 @@ t0 = int(tr[tr > 0].min())
 names = {0: "A w0", 4: "B w0"}
 print("softmax stamps per 64-key sub-block n: [wait S | S ready | S in regs | row max | exp done | P in TMEM | P published]")
 for w, nm in names.items():
-    for n in range(0, 8):
+    for n in list(range(0, 8)) + [20, 21, 40, 41]:
         row = [int(v) - t0 for v in tr[w, 7 * n:7 * n + 7]]
         d = [row[i + 1] - row[i] for i in range(6)]
         print(f"  {nm} n={n}: {row}  d(waitS,ld,max,exp,st,arrive)={d}")
