@@ -126,6 +126,28 @@ def test_gemm_residual_in_place():
     assert po.rel_err(x, want) < 2e-4
 
 
+@pytest.mark.parametrize("bn", [128, 192, 256])
+@pytest.mark.parametrize("mode", ["aux", "in_place"])
+def test_gemm_residual_chunk_ring_parity(bn, mode):
+    """fp32 residual epilogue: 3 CTAs walk 8 x ceil(1184/bn) tiles whose last column tile has an odd number of 32-column
+    chunks, so the two epilogue warpgroups swap chunk parity from tile to tile and the 4-deep chunk ring wraps many
+    times; both the load/store path (bf16 aux copy) and the TMA reduce-add path (in place, no aux)."""
+    M, N, K = 1000, 1184, 1152
+    a, w, bias = _randn(M, K, seed=21), _randn(N, K, seed=22, scale=K ** -0.5), _randn(N, seed=23, scale=0.1)
+    x = _randn(M, N, seed=24, dtype=torch.float32)
+    gate = _randn(2, 6, N, seed=25, dtype=torch.float32)
+    want = x + gate[:, 4].repeat_interleave(M // 2, 0) * F.linear(a.float(), w.float(), bias.float())
+    kw = dict(epilogue=lib.EPI_BIAS_RESIDUAL, residual=x, gate=gate[:, 4], gate_batch_stride=6 * N, rows_per_batch=M // 2,
+              block_n=bn, max_ctas=3, cta_pair=1)
+    if mode == "aux":
+        aux = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        lib.gemm(a, w, bias, x, out_aux=aux, **kw)
+        assert po.rel_err(aux.float(), want) < 4e-3
+    else:
+        lib.gemm(a, w, bias, x, **kw)
+    assert po.rel_err(x, want) < 2e-4
+
+
 def test_gemm_rejects_bad_arguments():
     a, w = _randn(128, 64), _randn(192, 64)
     out = torch.empty(128, 192, dtype=torch.bfloat16, device=DEV)
