@@ -26,11 +26,10 @@ struct GemmParams {
   int conv_H, conv_W, conv_tile_w, conv_tile_h, conv_cin_blocks;
 };
 
-constexpr int kResBufs = 4;                      // chunk ring of the TMA-streamed fp32 residual epilogue
+constexpr int kResBufs = 3;
 constexpr int kResChunkBytes = 128 * 32 * 4;     // 16 KB: 128 rows x 32 fp32 columns
 constexpr int kAuxChunkBytes = 128 * 32 * 2;     // 8 KB
-constexpr int kResEpiSmem = kResBufs * (kResChunkBytes + kAuxChunkBytes);     // 96 KB
-constexpr int kGemmThreadsRes = 384;             // TMA-residual kernel: two epilogue warpgroups (warps 4-7, 8-11)
+constexpr int kResEpiSmem = kResBufs * kResChunkBytes + 2 * kAuxChunkBytes;   // 64 KB
 constexpr int kSmemBudget = 227 * 1024;
 
 // Per-tile epilogue constants staged in smem while the tile's MMAs run: bias (fp32) and the gate rows of the (at most

@@ -17,7 +17,7 @@ namespace pxa {
 
 // ------------------------------------------------------------------------------------------------- kernel
 template <int BN, int EPI, typename OutT, bool kConv = false>
-__global__ void __launch_bounds__((EPI == PXA_EPI_BIAS_RESIDUAL && sizeof(OutT) == 4) ? kGemmThreadsRes : kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out,
                  const __grid_constant__ CUtensorMap tmap_aux, const GemmParams p) {
@@ -47,7 +47,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], kTmaRes ? 2 * kNumEpiThreads : kNumEpiThreads);
+      mbar_init(&tempty_bar[s], kNumEpiThreads);
     }
     for (int s = 0; s < kResBufs; ++s) mbar_init(&res_full[s], 1);
     fence_mbar_init();
@@ -132,121 +132,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (as == 0) aphase ^= 1;
       }
     }
-  } else if (kTmaRes && warp == 3) {
-    // ================================================================ epilogue TMA warp (fp32 residual stream only)
-    // Owns every TMA op of the epilogue: residual chunk loads (kResBufs - 1 chunks ahead of the chunk being stored, across
-    // tiles), result / aux stores (or the reduce-add).  Chunk g of this CTA's (tile, 32-column chunk) sequence lives in ring
-    // buffer g % kResBufs and is computed by epilogue warpgroup g & 1, which announces it on a named barrier (two ids per
-    // warpgroup, alternating, so a warpgroup can never arrive twice on an id before this warp has consumed the first).
-    if constexpr (kTmaRes) {
-      uint8_t* rbufs = epi_smem;
-      uint8_t* abufs = epi_smem + kResBufs * kResChunkBytes;
-      // In-place update without a bf16 copy: skip the residual read altogether and let TMA reduce-add the update into x.
-      const bool reduce = p.out_aux == nullptr && p.residual == p.out;
-      int l_tile = blockIdx.x, l_cc = 0, l_g = 0;                 // next residual chunk to request (elected lane only)
-      auto request_next = [&]() {
-        if (l_tile >= num_tiles) return;
-        const int lm0 = (l_tile / p.num_n_tiles) * kBM;
-        const int ln0 = (l_tile % p.num_n_tiles) * BN;
-        const int buf = l_g % kResBufs;
-        if (reduce) {
-          mbar_arrive(&res_full[buf]);                            // nothing to load: the buffer is simply free again
-        } else {
-          mbar_arrive_expect_tx(&res_full[buf], kResChunkBytes);
-          tma_load_2d(rbufs + buf * kResChunkBytes, &tmap_res, &res_full[buf], ln0 + l_cc * 32, lm0, kEvictFirst);
-        }
-        ++l_g;
-        if (++l_cc == chunks_of_tile<BN>(p, ln0)) { l_cc = 0; l_tile += gridDim.x; }
-      };
-      if (elect_one()) {
-        for (int i = 0; i < kResBufs - 1; ++i) request_next();
-      }
-      int g = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.num_n_tiles) * kBM;
-        const int n0 = (tile % p.num_n_tiles) * BN;
-        const int nch = chunks_of_tile<BN>(p, n0);
-        for (int cc = 0; cc < nch; ++cc, ++g) {
-          named_bar_sync(4 + 2 * (g & 1) + ((g >> 1) & 1), kNumEpiThreads + 32);   // chunk g computed and fenced
-          if (elect_one()) {
-            uint8_t* rb = rbufs + (g % kResBufs) * kResChunkBytes;
-            if (reduce) {
-              tma_reduce_add_2d(&tmap_out, rb, n0 + cc * 32, m0);
-            } else {
-              tma_store_2d(&tmap_out, rb, n0 + cc * 32, m0);
-              if (p.out_aux != nullptr) tma_store_2d(&tmap_aux, abufs + (g % kResBufs) * kAuxChunkBytes, n0 + cc * 32, m0);
-            }
-            tma_store_commit();
-            tma_store_wait_read<1>();                             // chunk g-1's store has drained buffer (g-1) % kResBufs
-            request_next();                                       // ... which chunk g + kResBufs - 1 takes over
-          }
-        }
-      }
-      if (elect_one()) tma_store_wait_all<0>();
-    }
   } else if (warp >= kEpiWarp0) {
     // ================================================================ epilogue
-    if constexpr (kTmaRes) {
-      // fp32 residual stream: two warpgroups (warps 4-7 / 8-11) take alternate 32-column chunks, so that one computes
-      // while the other waits on TMEM / the residual chunk / smem latencies (a single warp per sub-partition issues the
-      // ~260 instructions of a chunk at well under 0.5 IPC); TMA traffic is owned by warp 3.
-      const int grp = (warp - kEpiWarp0) >> 2;
-      const int q = warp & 3;                                     // TMEM sub-partition of this warp
-      const int r = q * 32 + lane;                                // row of the 128-row tile owned by this thread
-      const int gtid = threadIdx.x - kEpiWarp0 * 32;              // 0..255
-      EpiConst* consts = reinterpret_cast<EpiConst*>(epi_smem + Cfg::kEpiBufs);
-      uint8_t* rbufs = epi_smem;
-      uint8_t* abufs = epi_smem + kResBufs * kResChunkBytes;
-      const bool reduce = p.out_aux == nullptr && p.residual == p.out;
-      int as = 0;
-      uint32_t aphase = 0;
-      int titer = 0;
-      int g0 = 0;                                                 // index of the tile's first chunk in the CTA's chunk sequence
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
-        const int m0 = (tile / p.num_n_tiles) * kBM;
-        const int n0 = (tile % p.num_n_tiles) * BN;
-        const int nch = chunks_of_tile<BN>(p, n0);
-        EpiConst* cb = consts + (titer & 1);
-        if (gtid < kNumEpiThreads) stage_epi_consts<BN>(cb, p, gtid, m0, n0);   // global loads hide under this tile's MMAs
-        named_bar_sync(2, 2 * kNumEpiThreads);
-        mbar_wait(&tfull_bar[as], aphase);
-        tc_fence_after();
-        const uint32_t t_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
-        auto process = [&](uint32_t (&v)[32], int cc) {
-          const int g = g0 + cc;
-          const int buf = g % kResBufs;
-          uint8_t* rb = rbufs + buf * kResChunkBytes;
-          uint8_t* ab = p.out_aux != nullptr ? abufs + buf * kAuxChunkBytes : nullptr;
-          mbar_wait(&res_full[buf], (g / kResBufs) & 1);          // residual chunk landed (reduce: buffer free again)
-          residual_chunk_row_c(v, p, cb, rb, ab, r, cc * 32, m0 + r, n0 + cc * 32, reduce);
-          fence_proxy_async_smem();                               // generic-proxy writes -> visible to the TMA store
-          named_bar_arrive(4 + 2 * grp + ((g >> 1) & 1), kNumEpiThreads + 32);
-        };
-        auto release_acc = [&]() {                                // this warpgroup's TMEM reads of the accumulator are done
-          tc_fence_before();
-          mbar_arrive(&tempty_bar[as]);
-        };
-        // this warpgroup's chunks of the tile: cc with (g0 + cc) & 1 == grp; the TMEM load of the next one is in flight
-        // while the current one is processed
-        int cc = ((g0 & 1) == grp) ? 0 : 1;
-        uint32_t va[32], vb[32];
-        if (cc < nch) tmem_ld_32x32b_x32_nowait(t_acc + cc * 32, va); else release_acc();
-#pragma unroll 1
-        for (; cc < nch; cc += 4) {
-          tmem_ld_wait_x32(va);
-          if (cc + 2 < nch) tmem_ld_32x32b_x32_nowait(t_acc + (cc + 2) * 32, vb); else release_acc();
-          process(va, cc);
-          if (cc + 2 < nch) {
-            tmem_ld_wait_x32(vb);
-            if (cc + 4 < nch) tmem_ld_32x32b_x32_nowait(t_acc + (cc + 4) * 32, va); else release_acc();
-            process(vb, cc + 2);
-          }
-        }
-        g0 += nch;
-        as ^= 1;
-        if (as == 0) aphase ^= 1;
-      }
-    } else {
     const int q = warp & 3;                         // TMEM sub-partition of this warp
     const int tid = threadIdx.x - kEpiWarp0 * 32;   // 0..127
     EpiConst* consts = reinterpret_cast<EpiConst*>(epi_smem + Cfg::kEpiBufs);
@@ -367,7 +254,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (issuer_warp) {
       if (elect_one()) tma_store_wait_all<0>();
     }
-    }  // !kTmaRes
   }
 
   tc_fence_before();
@@ -453,7 +339,7 @@ static int launch_gemm(const PxaGemmArgs& a, cudaStream_t stream, const ConvGeom
   if (a.max_ctas > 0 && a.max_ctas < grid) grid = a.max_ctas;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   if (tiles < grid) grid = tiles;
-  kern<<<grid, kTmaRes ? kGemmThreadsRes : kGemmThreads, Cfg::kSmem, stream>>>(ta, tw, tr, to, tx, p);
+  kern<<<grid, kGemmThreads, Cfg::kSmem, stream>>>(ta, tw, tr, to, tx, p);
   launch_counter()++;
   PXA_CHECK_CUDA(cudaGetLastError());
   return PXA_OK;
@@ -552,7 +438,7 @@ extern "C" int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream) {
       pair = true;
       bn = 192;
     } else {
-      bn = 192;      // single-CTA kernel: 96 KB of epilogue chunk buffers leave 3 smem stages at BN = 192 (2 at BN = 256)
+      bn = 256;      // fewer, wider tiles: 100 us vs 107 us (BN = 192) at N = K = 1152, even with a half-empty last column tile
     }
   }
   if (pair) return gemm_pair_dispatch(a, bn, s);
