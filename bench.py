@@ -174,7 +174,7 @@ def run_reference_arm(args, wl):
             "cpu_baseline": {"value": value, "unit": "image-steps/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "image-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # --------------------------------------------------------------------------------------------- our arm
@@ -348,9 +348,17 @@ def run_ours(args, wl, wl_name):
                 "e2e": {"value": e2e_v, "unit": "image-steps/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h_out.numel() * 2},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_JSON_FD = None
+
+
+def _emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
 
 
 def main():
@@ -366,6 +374,12 @@ def main():
                          "per-kernel event timing (roofline) is unavailable in this mode")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
+    # The contract is ONE JSON line on stdout.  Libraries write banners there too (NCCL prints its version line at the
+    # first communicator init), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved fd.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args, wl)
     else:

@@ -62,6 +62,18 @@ PXA_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Blocking wait on phase `parity`.  try_wait suspends in hardware up to a time limit, so this is not a hot spin.
+// non-blocking probe (mbarrier.test_wait: no hardware time-out wait like try_wait)
+PXA_DEVICE bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 PXA_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }

@@ -28,10 +28,8 @@ for w, nm in names.items():
         row = [int(v) - t0 for v in tr[w, 7 * n:7 * n + 7]]
         d = [row[i + 1] - row[i] for i in range(6)]
         print(f"  {nm} n={n}: {row}  d(waitS,ld,max,exp,st,arrive)={d}")
-print("MMA thread per sub-block n: [wait P_A | P_A ready | wait P_B | P_B ready]")
-for n in range(0, 12):
-    row = [int(v) - t0 for v in tr[16, 4 * n:4 * n + 4]]
-    print(f"  n={n}: {row}  d={[row[i+1]-row[i] for i in range(3)]}")
-per = [int(tr[16, 4 * (n + 1)]) - int(tr[16, 4 * n]) for n in range(8, 56)]
-print("cycles per sub-block (MMA loop period), n=8..55:", per)
+per = [int(tr[0, 7 * (n + 1)]) - int(tr[0, 7 * n]) for n in range(8, 56)]
+print("cycles per sub-block (softmax warp A w0 loop period), n=8..55:", per)
 print("mean cycles per 128 keys:", 2 * sum(per) / len(per))
+lag = [int(tr[4, 7 * n + 3]) - int(tr[0, 7 * n + 3]) for n in (4, 12, 20, 28, 36, 44, 52)]
+print("tile B behind tile A at 'row max known' (cycles), n=4,12,..,52:", lag)
