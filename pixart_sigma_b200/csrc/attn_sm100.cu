@@ -39,12 +39,6 @@
 #ifndef PXA_PREFETCH_S
 #define PXA_PREFETCH_S 1      // read S of sub-block n+1 from TMEM behind the exp2 work of sub-block n
 #endif
-#ifndef PXA_DECOUPLED
-#define PXA_DECOUPLED 1       // the MMA thread serves whichever tile has its P ready instead of A-then-B per sub-block
-#endif
-#ifndef PXA_STAGGER_CYC
-#define PXA_STAGGER_CYC 0     // experiment: tile B's softmax warps idle this many cycles before their first exp2 section
-#endif
 #ifndef PXA_POLY_OF8
 #define PXA_POLY_OF8 0        // how many of every 8 score pairs take the polynomial exp2 (FMA pipe) instead of MUFU
 #endif
@@ -133,8 +127,8 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
     prefetch_tmap(&tm_v_main); prefetch_tmap(&tm_v_tail);
     mbar_init(q_full, 1);
     for (int s = 0; s < kKVStages; ++s) {
-      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], PXA_DECOUPLED ? 2 : 1);     // decoupled: one release per tile
-      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], PXA_DECOUPLED ? 2 : 1);
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
@@ -237,39 +231,6 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
           umma_commit(&s_full[2 * t + hh]);
         }
       }
-#if PXA_DECOUPLED
-      umma_commit(&k_empty[0]);                     // one release per tile
-      umma_commit(&k_empty[0]);
-      // The two tiles are served independently, whichever publishes its P first: a fixed A-then-B order per sub-block
-      // ties tile B's phase to tile A's (B ends up ~480 cycles behind A for the whole kernel), and with it the times at
-      // which the two softmax warps of a sub-partition want the MUFU.
-      int nt[2] = {0, 0};
-      while (nt[0] < n_sub || nt[1] < n_sub) {
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int n = nt[t];
-          if (n >= n_sub) continue;
-          const int j = n >> 1, hh = n & 1;
-          if (!mbar_test(&p_full[2 * t + hh], j & 1)) continue;
-          PXA_TRACE(16, tcnt);                     // served tile t sub-block n
-          const int stage = j % kKVStages;
-          mbar_wait(&v_full[stage], (j / kKVStages) & 1);
-          const bool has_next = n + 2 < n_sub;     // the sub-block that reuses this S half
-          const int nstage = (j + 1) % kKVStages;
-          if (has_next) mbar_wait(&k_full[nstage], ((j + 1) / kKVStages) & 1);
-          tc_fence_after();
-          issue_pv(t, stage, hh, n == 0);
-          umma_commit(&pv_done[t]);
-          if (has_next) {
-            issue_qk(t, nstage, hh);
-            umma_commit(&s_full[2 * t + hh]);
-          }
-          if (hh == 1 || n + 1 == n_sub) umma_commit(&v_empty[stage]);                 // this tile's last P V on the V stage
-          if (has_next && (hh == 1 || n + 3 == n_sub)) umma_commit(&k_empty[nstage]);   // this tile's last Q K^T on that K stage
-          nt[t] = n + 1;
-        }
-      }
-#else
       umma_commit(&k_empty[0]);
 
       for (int n = 0; n < n_sub; ++n) {
@@ -296,7 +257,6 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         if (hh == 1 || n + 1 == n_sub) umma_commit(&v_empty[stage]);            // last P V reading this V stage
         if (has_next && (hh == 1 || nn + 1 == n_sub)) umma_commit(&k_empty[nstage]);   // last Q K^T reading that K stage
       }
-#endif
       umma_commit(o_full);
     }
   } else if (warp >= 4) {
@@ -390,14 +350,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         sb = mul2(sb, f2);
         m_ref = m_new;
       }
-      float nm = -m_ref * sl2;
-#if PXA_STAGGER_CYC
-      if (n == 0 && t == 1) {
-        const long long c0 = clock64();
-        while (clock64() - c0 < PXA_STAGGER_CYC) {}
-        asm volatile("" : "+f"(nm)::"memory");
-      }
-#endif
+      const float nm = -m_ref * sl2;
       const uint64_t nm2 = f32x2(nm, nm);
       // exp2 on packed fp32 pairs (FFMA2 / FADD2: one issue slot for two lane-ops).  PXA_POLY_OF8 of every 8 pairs take
       // the polynomial exp2 (FMA pipe) instead of MUFU (16 results/clk/SM), so that both pipes and the issue port end up
