@@ -303,6 +303,19 @@ def run_ours(args, wl, wl_name):
             launches = launches_per_forward * args.steps       # graph replays bypass the library's host-side counter
         ms_e2e = timed(step_e2e, args.steps)
         clocks = sampler.stop() if sampler else None
+        loop = None
+        if args.sampling_loop:
+            # the caller of the path: a full 20-step DPM-Solver++ CFG sampling run of `imgs` images
+            # through pixart_sigma_b200.sampler (fused step kernel; whole loop as one CUDA graph with --cuda-graph)
+            from pixart_sigma_b200.sampler import DPMS
+            cond, null = d_y[imgs:], d_y[:imgs]
+            solver = DPMS(model.forward_with_dpmsolver, condition=cond, uncondition=null, cfg_scale=4.5,
+                          model_kwargs=dict(data_info=None, mask=d_mask))
+            z = d_x[:imgs].float()
+            solver.sample(z, steps=20, cuda_graph=args.cuda_graph)                 # warm-up (and graph capture)
+            ms_loop = timed(lambda i: solver.sample(z, steps=20, cuda_graph=args.cuda_graph), 1)
+            loop = {"steps": 20, "images": imgs * world, "ms": ms_loop, "images_per_s": imgs * world / (ms_loop / 1000.0),
+                    "denoise_steps_per_s": imgs * world * 20 / (ms_loop / 1000.0), "cuda_graph": bool(args.cuda_graph)}
 
     if rank == 0:
         tot, f_gemm, f_attn = flops_per_forward(n_tok, B, kv)
@@ -348,6 +361,8 @@ def run_ours(args, wl, wl_name):
                 "e2e": {"value": e2e_v, "unit": "image-steps/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h_out.numel() * 2},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+        if loop is not None:
+            line["sampling_loop"] = loop
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -369,6 +384,9 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sampling-loop", action="store_true",
+                    help="also time one full 20-step DPM-Solver++ sampling run through pixart_sigma_b200.sampler "
+                         "(extra key `sampling_loop`; not part of the timed region of `value` / `e2e`)")
     ap.add_argument("--cuda-graph", action="store_true",
                     help="replay the resident-input forward as one CUDA graph (pixart_sigma_b200.graph.GraphedForward); "
                          "per-kernel event timing (roofline) is unavailable in this mode")

@@ -148,6 +148,31 @@ typedef struct PxaConv3x3Args {
 } PxaConv3x3Args;
 int pxa_conv3x3_nhwc_bf16(const PxaConv3x3Args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------ DPM-Solver++ sampler step
+ * One fused elementwise pass per sampling step of the multistep DPM-Solver++ (2M) loop the reference runs in PyTorch
+ * (diffusion/model/dpm_solver.py: CFG combine :326-332, data prediction :435-444, first-order update :565-577,
+ * second-order multistep update :822-840; loop :1196-1241; call site scripts/inference.py:102-118):
+ *     eps   = eps_uncond + cfg_scale * (eps_cond - eps_uncond)
+ *     x0    = (x - sigma_s * eps) * inv_alpha_s                      (data prediction at the current time s)
+ *     x    <- a * x - b * x0 - c * (x0 - x0_prev)                    (c = 0: first-order update)
+ *     x0_prev <- x0
+ * with host-computed scalars a = sigma_t / sigma_s, b = alpha_t * expm1(-h), c = 0.5 * b / r0.
+ * `model_out` is the denoiser output of the CFG batch [uncond (n) ; cond (n)]: element (i, ch, p) at
+ * model_out[i * out_batch_stride + ch * hw + p], ch < 4 (so the 8-channel learn-sigma output can be passed as is).
+ * fp32 arithmetic; x, x0_prev: fp32 [n, 4, hw] contiguous, updated in place.  HBM-bound: 24 (fp32 out) / 16 (bf16 out)
+ * algorithmic bytes per latent element.
+ */
+typedef struct PxaDpmStepArgs {
+  const void* model_out;    /* [2n, >=4, hw], dtype out_dtype                         */
+  float* x;                 /* fp32 [n, 4, hw] in/out                                 */
+  float* x0_prev;           /* fp32 [n, 4, hw] in/out (ignored on input when c == 0)  */
+  int64_t out_batch_stride; /* elements                                               */
+  int32_t n, hw;
+  int32_t out_dtype;        /* PXA_DTYPE_*                                            */
+  float cfg_scale, sigma_s, inv_alpha_s, a, b, c;
+} PxaDpmStepArgs;
+int pxa_dpm_solver_pp_step(const PxaDpmStepArgs* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

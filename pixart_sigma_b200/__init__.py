@@ -4,8 +4,10 @@ Only what the path `PixArtMS.forward -> 28 x PixArtMSBlock.forward` needs:
   csrc/      hand-written CUDA (tcgen05 / TMA / TMEM) behind the C-ABI of include/pixart_sm100.h
   lib.py     ctypes binding of libpixart_sm100.so
   model.py   host-side mirror of the reference model API (same names, ctor, state_dict layout)
+  sampler.py DPM-Solver++ loop around the path (mirror of the reference's `diffusion.DPMS`), fused step kernel + CUDA graph
   build.py   in-tree nvcc build
 """
 from .model import (MODELS, PixArtMS, PixArtMS_XL_2, PixArtMSBlock, build_model, install_into_reference)  # noqa: F401
+from .sampler import DPMS, DPMSolverPP  # noqa: F401
 
 __version__ = "0.1.0"

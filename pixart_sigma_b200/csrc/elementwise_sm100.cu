@@ -192,3 +192,79 @@ extern "C" int pxa_kv_compress_conv2_ln(const PxaKvCompressArgs* args, void* str
   PXA_CHECK_CUDA(cudaGetLastError());
   return PXA_OK;
 }
+
+namespace pxa {
+
+// ------------------------------------------------------------------------------------------------- DPM-Solver++ step
+// One thread per 4 consecutive latent elements (hw % 4 == 0): CFG combine + data prediction + multistep update.
+template <typename OT>
+__global__ void __launch_bounds__(256) dpm_step_kernel(const OT* __restrict__ mo, float* __restrict__ x,
+                                                       float* __restrict__ x0_prev, long long obs, int n, int hw,
+                                                       float cfg, float sigma_s, float inv_alpha_s, float a, float b,
+                                                       float c) {
+  const int per_img = hw;                                    // 4 channels * hw elements / 4 per thread
+  const long long total = (long long)n * per_img;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int img = (int)(i / per_img);
+    const int e = (int)(i - (long long)img * per_img) * 4;   // element offset inside the image's [4, hw] block
+    const OT* pu = mo + (size_t)img * obs + e;               // channel ch at ch*hw + p == contiguous [4, hw] prefix
+    const OT* pc = mo + (size_t)(img + n) * obs + e;
+    float eu[4], ec[4];
+    if constexpr (sizeof(OT) == 4) {
+      const float4 u = *reinterpret_cast<const float4*>(pu), v = *reinterpret_cast<const float4*>(pc);
+      eu[0] = u.x; eu[1] = u.y; eu[2] = u.z; eu[3] = u.w;
+      ec[0] = v.x; ec[1] = v.y; ec[2] = v.z; ec[3] = v.w;
+    } else {
+      const uint2 u = *reinterpret_cast<const uint2*>(pu), v = *reinterpret_cast<const uint2*>(pc);
+      eu[0] = bf16_lo(u.x); eu[1] = bf16_hi(u.x); eu[2] = bf16_lo(u.y); eu[3] = bf16_hi(u.y);
+      ec[0] = bf16_lo(v.x); ec[1] = bf16_hi(v.x); ec[2] = bf16_lo(v.y); ec[3] = bf16_hi(v.y);
+    }
+    const size_t off = (size_t)img * 4 * hw + e;
+    const float4 xv = *reinterpret_cast<const float4*>(x + off);
+    float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c != 0.f) pv = *reinterpret_cast<const float4*>(x0_prev + off);
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    const float ps[4] = {pv.x, pv.y, pv.z, pv.w};
+    float xn[4], x0[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float eps = eu[k] + cfg * (ec[k] - eu[k]);
+      x0[k] = (xs[k] - sigma_s * eps) * inv_alpha_s;
+      xn[k] = a * xs[k] - b * x0[k] - c * (x0[k] - ps[k]);
+    }
+    *reinterpret_cast<float4*>(x + off) = make_float4(xn[0], xn[1], xn[2], xn[3]);
+    *reinterpret_cast<float4*>(x0_prev + off) = make_float4(x0[0], x0[1], x0[2], x0[3]);
+  }
+}
+
+}  // namespace pxa
+
+extern "C" int pxa_dpm_solver_pp_step(const PxaDpmStepArgs* args, void* stream) {
+  using namespace pxa;
+  if (!args) return fail(PXA_ERR_ARG, "null args");
+  const PxaDpmStepArgs& a = *args;
+  if (!a.model_out || !a.x || !a.x0_prev) return fail(PXA_ERR_ARG, "null pointer");
+  if (a.n <= 0 || a.hw <= 0 || (a.hw & 3)) return fail(PXA_ERR_ARG, "n > 0 and hw a positive multiple of 4 required (n=%d hw=%d)", a.n, a.hw);
+  if (a.out_batch_stride < 4LL * a.hw) return fail(PXA_ERR_ARG, "out_batch_stride smaller than 4*hw");
+  const int esz = a.out_dtype == PXA_DTYPE_F32 ? 4 : 2;
+  if (a.out_dtype != PXA_DTYPE_F32 && a.out_dtype != PXA_DTYPE_BF16) return fail(PXA_ERR_ARG, "out_dtype must be PXA_DTYPE_F32 or PXA_DTYPE_BF16");
+  if ((reinterpret_cast<uintptr_t>(a.model_out) & (4 * esz - 1)) || ((a.out_batch_stride * esz) & (4 * esz - 1)) ||
+      ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.x0_prev)) & 15))
+    return fail(PXA_ERR_ALIGN, "model_out / x / x0_prev must be aligned to 4 elements");
+  PXA_REQUIRE_SM100();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = (long long)a.n * a.hw;
+  int grid = (int)((total + 255) / 256);
+  const int cap = device_info().sms * 8;
+  if (grid > cap) grid = cap;
+  if (a.out_dtype == PXA_DTYPE_F32)
+    dpm_step_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(a.model_out), a.x, a.x0_prev, a.out_batch_stride,
+                                                a.n, a.hw, a.cfg_scale, a.sigma_s, a.inv_alpha_s, a.a, a.b, a.c);
+  else
+    dpm_step_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(a.model_out), a.x, a.x0_prev,
+                                                        a.out_batch_stride, a.n, a.hw, a.cfg_scale, a.sigma_s, a.inv_alpha_s,
+                                                        a.a, a.b, a.c);
+  launch_counter()++;
+  PXA_CHECK_CUDA(cudaGetLastError());
+  return PXA_OK;
+}

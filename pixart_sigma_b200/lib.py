@@ -60,8 +60,15 @@ class Conv3x3Args(C.Structure):
                 ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32)]
 
 
+class DpmStepArgs(C.Structure):
+    _fields_ = [("model_out", C.c_void_p), ("x", C.c_void_p), ("x0_prev", C.c_void_p), ("out_batch_stride", C.c_int64),
+                ("n", C.c_int32), ("hw", C.c_int32), ("out_dtype", C.c_int32),
+                ("cfg_scale", C.c_float), ("sigma_s", C.c_float), ("inv_alpha_s", C.c_float),
+                ("a", C.c_float), ("b", C.c_float), ("c", C.c_float)]
+
+
 EXPORTS = ("pxa_version", "pxa_last_error", "pxa_launch_count", "pxa_gemm_bf16", "pxa_ln_modulate",
-           "pxa_flash_attn_d72_bf16", "pxa_kv_compress_conv2_ln", "pxa_conv3x3_nhwc_bf16")
+           "pxa_flash_attn_d72_bf16", "pxa_kv_compress_conv2_ln", "pxa_conv3x3_nhwc_bf16", "pxa_dpm_solver_pp_step")
 
 _lib = None
 
@@ -78,7 +85,7 @@ def load() -> C.CDLL:
         lib.pxa_launch_count.restype = C.c_uint64
         for name, struct in (("pxa_gemm_bf16", GemmArgs), ("pxa_ln_modulate", LnModArgs),
                              ("pxa_flash_attn_d72_bf16", AttnArgs), ("pxa_kv_compress_conv2_ln", KvCompressArgs),
-                             ("pxa_conv3x3_nhwc_bf16", Conv3x3Args)):
+                             ("pxa_conv3x3_nhwc_bf16", Conv3x3Args), ("pxa_dpm_solver_pp_step", DpmStepArgs)):
             fn = getattr(lib, name)
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(struct), C.c_void_p]
@@ -189,3 +196,20 @@ def conv3x3_nhwc(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.T
                        Cin=Cin, Cout=Cout)
     _check(load().pxa_conv3x3_nhwc_bf16(C.byref(args), _stream()), "pxa_conv3x3_nhwc_bf16")
     return out
+
+
+def dpm_solver_pp_step(model_out: torch.Tensor, x: torch.Tensor, x0_prev: torch.Tensor, *, cfg_scale: float, sigma_s: float,
+                       alpha_s: float, a: float, b: float, c: float) -> torch.Tensor:
+    """One DPM-Solver++ (2M) update, in place on x and x0_prev (include/pixart_sm100.h: pxa_dpm_solver_pp_step).
+    model_out: denoiser output of the CFG batch [uncond; cond], (2n, C>=4, h, w) fp32 or bf16 -- a channel-sliced view of
+    the 8-channel learn-sigma output is fine; x, x0_prev: fp32 (n, 4, h, w) contiguous."""
+    assert model_out.is_cuda and x.is_cuda and x0_prev.is_cuda and x.dtype == x0_prev.dtype == torch.float32
+    assert x.is_contiguous() and x0_prev.is_contiguous() and x.shape == x0_prev.shape and x.dim() == 4 and x.shape[1] == 4
+    n, _, h, w = x.shape
+    assert model_out.shape[0] == 2 * n and model_out.shape[1] >= 4 and model_out.shape[2:] == (h, w)
+    assert model_out.stride(3) == 1 and model_out.stride(2) == w and model_out.stride(1) == h * w, "model_out: (.., h, w) planes must be dense"
+    args = DpmStepArgs(model_out=_ptr(model_out), x=_ptr(x), x0_prev=_ptr(x0_prev), out_batch_stride=model_out.stride(0),
+                       n=n, hw=h * w, out_dtype=_dt(model_out.dtype), cfg_scale=cfg_scale, sigma_s=sigma_s,
+                       inv_alpha_s=1.0 / alpha_s, a=a, b=b, c=c)
+    _check(load().pxa_dpm_solver_pp_step(C.byref(args), _stream()), "pxa_dpm_solver_pp_step")
+    return x

@@ -543,4 +543,10 @@ def install_into_reference() -> bool:
             table[name] = obj
         setattr(nets, name, obj)
     nets.PixArtMSBlock = PixArtMSBlock
+    try:                                                   # the sampler the inference script imports from `diffusion`
+        import diffusion
+        from .sampler import DPMS
+        diffusion.DPMS = DPMS
+    except Exception:
+        pass
     return True
