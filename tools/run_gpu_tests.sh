@@ -14,7 +14,7 @@ run() {  # name, timeout, pytest args...
 : > gpurun_out/tests_summary.txt
 run gemm_small 240 tests/test_kernels_gpu.py -k "gemm_bias_bf16 and (128-192-64 or 384-256-128)"
 run gemm_all 300 tests/test_kernels_gpu.py -k "gemm"
-run ln 120 tests/test_kernels_gpu.py -k "ln_modulate or kv_compress"
+run ln 300 tests/test_kernels_gpu.py -k "ln_modulate or kv_compress"
 run attn_small 240 tests/test_kernels_gpu.py -k "flash_attn_self and (1-1-128-128 or 1-2-256-256)"
 run attn_all 400 tests/test_kernels_gpu.py -k "flash_attn"
 for extra in "$@"; do run "$(basename "$extra" .py)" 600 "$extra"; done
