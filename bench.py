@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- denoise-steps/sec of the PixArt-Sigma-XL/2 denoiser hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4|c5] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -13,6 +13,10 @@ reference diffusion/model/dpm_solver.py:328-331), inputs resident in HBM, CUDA-e
 inside every timed step.  Weak scaling: per-GPU work is fixed, ranks are independent replicas (no collective in the
 data path).  The working set per step (1.2 GB of weights + >1 GB of activations) is far larger than
 the 126 MB L2, so no explicit L2 flush is needed between iterations.
+
+`--workload c5` (BASELINE configs[4]) times the TRAINING step instead: IDDPM loss forward + backward through the
+forward/backward kernels with per-block activation checkpointing + the bucketed gradient all-reduce (NCCL) overlapped
+with the backward, 1024px, 4 images per GPU, fp32 master weights; `value` = trained images per second over all ranks.
 
 One JSON line is printed by rank 0.
 """
@@ -40,6 +44,11 @@ WORKLOADS = {
     "c4": ("PixArt-Sigma-XL/2 2K-MS kv-compress sr=2 layers 14-27, 1 image/GPU (forward batch 2), 16384 tokens",
            256, 1, 4.0, True),
 }
+
+
+TRAIN_WORKLOAD = ("PixArt-Sigma-XL/2 1024-MS training step: IDDPM loss fwd + bwd (per-block activation checkpointing) + "
+                  "bucketed gradient all-reduce, 4 images/GPU, 4096 tokens, fp32 master weights / bf16 kernels "
+                  "[BASELINE configs[4]]", 128, 4, 2.0, False)
 
 
 def flops_per_forward(n_tok: int, batch: int, kv_compress: bool):
@@ -368,6 +377,133 @@ def run_ours(args, wl, wl_name):
         dist.destroy_process_group()
 
 
+def run_train(args, wl):
+    """BASELINE configs[4]: one training step = zero_grad + IDDPM loss forward + backward + gradient all-reduce."""
+    import torch.distributed as dist
+    from pixart_sigma_b200 import build_model, lib
+    from pixart_sigma_b200.parallel import GradBucketReducer
+    from pixart_sigma_b200.training import IDDPMLoss, train_step
+
+    desc, side, imgs, pe, _ = wl
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib.load()
+    torch.manual_seed(1234)                                   # same initial weights on every rank (DDP replicas)
+    with torch.device(dev):
+        model = build_model(dict(type="PixArtMS_XL_2", input_size=side, pe_interpolation=pe, model_max_length=L),
+                            use_grad_checkpoint=not args.no_checkpoint)
+        for blk in model.blocks:
+            torch.nn.init.normal_(blk.cross_attn.proj.weight, std=0.02)
+        torch.nn.init.normal_(model.final_layer.linear.weight, std=0.02)
+    model = model.float().train()
+    reducer = GradBucketReducer(model)
+    loss_fn = IDDPMLoss()
+    n_tok = (side // 2) ** 2
+    g = torch.Generator().manual_seed(7 + rank)
+    h_x = (torch.randn(imgs, 4, side, side, generator=g) * 0.5).pin_memory()
+    h_y = torch.randn(imgs, 1, L, 4096, generator=g).to(torch.bfloat16).pin_memory()
+    lens = torch.randint(8, L + 1, (imgs,), generator=g)
+    h_mask = (torch.arange(L)[None] < lens[:, None]).to(torch.int16).view(imgs, 1, 1, L).pin_memory()   # train.py:192 layout
+    h_t = torch.randint(0, 1000, (imgs,), generator=g).pin_memory()
+    h_noise = torch.randn(imgs, 4, side, side, generator=g).pin_memory()
+    d_x, d_y, d_mask, d_t, d_noise = (v.to(dev) for v in (h_x, h_y, h_mask, h_t, h_noise))
+
+    def step_resident(i):
+        reducer.zero_grad()
+        return train_step(model, loss_fn, d_x, d_t, d_y, d_mask, noise=d_noise, reducer=reducer)
+
+    def step_e2e(i):
+        x, y, mk, t, nz = (v.to(dev, non_blocking=True) for v in (h_x, h_y, h_mask, h_t, h_noise))
+        reducer.zero_grad()
+        return float(train_step(model, loss_fn, x, t, y, mk, noise=nz, reducer=reducer))     # loss read back: D2H + sync
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms
+
+    timer = KernelTimer(lib)
+    timer.recs["attn_bwd"] = []
+    timer.install()
+    _ab = lib.flash_attn_bwd
+    lib.flash_attn_bwd = lambda *a, **k: timer._wrap("attn_bwd", _ab, a, k)
+    for i in range(max(args.warmup, 3)):
+        loss0 = step_resident(i)
+    step_e2e(0)
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0 = lib.launch_count()
+    timer.on = True
+    ms = timed(step_resident, args.steps)
+    timer.on = False
+    launches = lib.launch_count() - n0
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if sampler else None
+    peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+    if rank == 0:
+        fwd, f_gemm, f_attn = flops_per_forward(n_tok, imgs, False)
+        sus, burst, hbm, src = measured_peaks()
+        ms_step = ms / args.steps
+        tt = timer.totals_ms()
+        recompute = 0 if args.no_checkpoint else 1
+        gemm_flops = (3 + recompute) * f_gemm * args.steps            # fwd (+ recompute) + dgrad + wgrad
+        gemm_ms, gemm_n = tt["gemm"]
+        gemm_tf = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else None
+        afw_ms, afw_n = tt["attn"]
+        abw_ms, abw_n = tt["attn_bwd"]
+        afw_tf = (1 + recompute) * f_attn * args.steps / (afw_ms / 1000.0) / 1e12 if afw_ms > 0 else None
+        abw_tf = 3.5 * f_attn * args.steps / (abw_ms / 1000.0) / 1e12 if abw_ms > 0 else None     # 14 N Nk d executed (10 model)
+        model_tf = 3 * fwd / (ms_step / 1000.0) / 1e12
+        roof = {"bound": "tensor", "kernel": "pxa::gemm_bf16_kernel (forward, recompute, dgrad and wgrad GEMMs)",
+                "achieved": gemm_tf, "peak": sus, "unit": "TFLOP/s", "frac": (gemm_tf / sus) if gemm_tf else None,
+                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src})", "traffic": None,
+                "launches_timed": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
+                "flops_per_launch_avg": gemm_flops / max(gemm_n, 1), "step_share": gemm_ms / ms,
+                "attention_fwd": {"kernel": "pxa::flash_attn_d72_kernel", "achieved": afw_tf, "frac": afw_tf / sus if afw_tf else None,
+                                  "launches_timed": afw_n, "step_share": afw_ms / ms},
+                "attention_bwd": {"kernel": "pxa::flash_attn_d72_bwd_kernel (dKV + dQ passes + delta)", "achieved": abw_tf,
+                                  "frac": abw_tf / sus if abw_tf else None, "launches_timed": abw_n, "step_share": abw_ms / ms,
+                                  "note": "executed FLOPs (14 N Nk d incl. the dQ-pass recomputation); model FLOPs are 10 N Nk d"},
+                "whole_step": {"model_tflops": model_tf, "frac": model_tf / sus,
+                               "note": "model FLOPs = 3 x forward (no recomputation counted)"}}
+        h2d = h_x.numel() * 4 + h_y.numel() * 2 + h_mask.numel() * 2 + h_t.numel() * 8 + h_noise.numel() * 4
+        line = {"metric": "train-images/sec", "value": imgs * world * args.steps / (ms / 1000.0), "unit": "images/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"c5: {desc}", "images_per_gpu": imgs, "tokens_per_sample": n_tok, "text_tokens": L,
+                           "parallelism": f"ddp{world} (bucketed NCCL all-reduce of {reducer.grad_bytes() / 1e9:.2f} GB fp32 grads, "
+                                          f"{len(reducer.buckets)} buckets, overlapped with backward)",
+                           "grad_checkpointing": not args.no_checkpoint, "optimizer_step": "not included (fwd + bwd + all-reduce, as configs[4] states)",
+                           "l2": "working set (2.4 GB fp32 weights + activations) larger than L2; no flush needed",
+                           "tflop_model_per_step_per_gpu": 3 * fwd / 1e12, "peak_mem_gib": peak_mem, "loss": float(loss0)},
+                "e2e": {"value": imgs * world * args.steps / (ms_e2e / 1000.0), "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": None}
+        _emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 _JSON_FD = None
 
 
@@ -381,7 +517,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c5"])
+    ap.add_argument("--no-checkpoint", action="store_true", help="c5: train without per-block activation checkpointing")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sampling-loop", action="store_true",
@@ -391,14 +528,16 @@ def main():
                     help="replay the resident-input forward as one CUDA graph (pixart_sigma_b200.graph.GraphedForward); "
                          "per-kernel event timing (roofline) is unavailable in this mode")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = TRAIN_WORKLOAD if args.workload == "c5" else WORKLOADS[args.workload]
     # The contract is ONE JSON line on stdout.  Libraries write banners there too (NCCL prints its version line at the
     # first communicator init), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved fd.
     global _JSON_FD
     sys.stdout.flush()
     _JSON_FD = os.dup(1)
     os.dup2(2, 1)
-    if args.impl == "reference":
+    if args.workload == "c5" and args.impl != "reference":
+        run_train(args, wl)
+    elif args.impl == "reference":
         run_reference_arm(args, wl)
     else:
         run_ours(args, wl, args.workload)

@@ -110,6 +110,8 @@ typedef struct PxaAttnArgs {
   int32_t ldo;
   float scale;      /* softmax scale, 72^-0.5 */
   int64_t* debug_trace; /* NULL in production. Else device int64[16 warps + 2][kTraceMax] cycle stamps of CTA (0,0,0) */
+  float* lse;       /* optional fp32 [B, H, Nq]: log2-domain log-sum-exp of the scaled scores, the softmax statistic the
+                       backward pass recomputes P from (training); NULL for inference                              */
 } PxaAttnArgs;
 int pxa_flash_attn_d72_bf16(const PxaAttnArgs* args, void* stream);
 
@@ -172,6 +174,81 @@ typedef struct PxaDpmStepArgs {
   float cfg_scale, sigma_s, inv_alpha_s, a, b, c;
 } PxaDpmStepArgs;
 int pxa_dpm_solver_pp_step(const PxaDpmStepArgs* args, void* stream);
+
+/* =============================================================================================== training backward
+ * The reference trains through torch autograd (train_scripts/train.py:197 `accelerator.backward(loss)`, per-block
+ * activation checkpointing diffusion/model/utils.py:28-45).  The entry points below are the backward twins of the forward
+ * ops above; `pixart_sigma_b200/autograd.py` binds them as torch.autograd.Function s.  The dgrad / wgrad matrix products
+ * run on pxa_gemm_bf16 itself (dX = dY . W  ==  gemm(A = dY, W' = W^T);  dW += dY^T . X  ==  gemm(A = dY^T, W' = X^T) with the
+ * fp32 residual epilogue adding into the gradient buffer), fed by pxa_transpose_bf16.
+ */
+
+/* out[C, R] = in[R, C]^T (bf16; 32-bit accesses when R, C, ldi, ldo are even, element-wise otherwise). */
+int pxa_transpose_bf16(const void* in, void* out, int32_t R, int32_t C, int64_t ldi, int64_t ldo, void* stream);
+
+/* GELU(approximate='tanh') on n bf16 elements (n % 8 == 0): dh == NULL: out = gelu(pre);  else out = dh * gelu'(pre).
+ * Replaces timm Mlp.act (PixArtMS.py:67) forward (training path, which keeps `pre` for the backward) and backward. */
+int pxa_gelu_tanh_bf16(const void* pre, const void* dh, void* out, int64_t n, void* stream);
+
+/* Gated residual add of the block (PixArtMS.py:75-77) on the fp32 residual stream, and its backward.
+ *   fwd: out[r,:] = x[r,:] + gate[b,:] * y[r,:]                      (x, out fp32; y bf16; gate NULL -> 1)
+ *   bwd: x = dout (fp32), out = dy (bf16) = dout * gate[b,:];  dgate[b,:] += sum_{r in b} dout[r,:] * y[r,:]  (if dgate)  */
+typedef struct PxaGateResidualArgs {
+  const void* x;        /* fp32 [M, C] contiguous (fwd: residual stream; bwd: incoming gradient)               */
+  const void* y;        /* bf16 [M, C] contiguous branch output (bwd: only needed with dgate)                   */
+  const float* gate;    /* fp32 (b, c) at gate[b*gate_batch_stride + c], or NULL                                */
+  void* out;            /* fwd: fp32 [M, C];  bwd: bf16 [M, C]                                                  */
+  float* dgate;         /* bwd only: fp32 [B, C] contiguous, accumulated into (atomics); or NULL                */
+  int64_t gate_batch_stride;
+  int32_t rows_per_batch;
+  int32_t M, C;
+} PxaGateResidualArgs;
+int pxa_gate_residual_fwd(const PxaGateResidualArgs* args, void* stream);
+int pxa_gate_residual_bwd(const PxaGateResidualArgs* args, void* stream);
+
+/* Backward of pxa_ln_modulate w.r.t. x, shift and scale (C = 1152):
+ *   dx = LN-backward((1 + scale[b]) * dxn);  dshift[b,:] += sum_r dxn[r,:];  dscale[b,:] += sum_r dxn[r,:] * xhat[r,:]  */
+typedef struct PxaLnModBwdArgs {
+  const void* x;        /* fp32 [M, C] contiguous: the forward input                                            */
+  const void* dxn;      /* bf16 [M, C] contiguous: gradient of the forward output                               */
+  const float* scale;   /* fp32 (b, c) at scale[b*mod_batch_stride + c]                                         */
+  void* dx;             /* fp32 [M, C] contiguous (written)                                                     */
+  float* dshift;        /* fp32 [B, C] contiguous (accumulated, atomics)                                        */
+  float* dscale;        /* fp32 [B, C] contiguous (accumulated, atomics)                                        */
+  int64_t mod_batch_stride;
+  int32_t rows_per_batch;
+  int32_t M, C;
+  float eps;
+} PxaLnModBwdArgs;
+int pxa_ln_modulate_bwd(const PxaLnModBwdArgs* args, void* stream);
+
+/* out[c] += sum_r a[r, c]  (bias gradients; a bf16 [M, N] row stride lda, N % 8 == 0; out fp32 [N], atomics). */
+int pxa_colsum_bf16(const void* a, float* out, int32_t M, int32_t N, int64_t lda, void* stream);
+
+/* delta[(b*H + h)*Nq + i] = sum_d dO[b,i,h,d] * O[b,i,h,d]  (o / dO bf16 [B*Nq, H*72] with row strides ldo / lddo). */
+int pxa_attn_delta_d72(const void* o, const void* d_o, float* delta, int32_t B, int32_t H, int32_t Nq, int64_t ldo,
+                       int64_t lddo, void* stream);
+
+/* Backward of pxa_flash_attn_d72_bf16: dq, dk, dv from (q, k, v, o, dO, lse).  Flash-attention-2 recomputation on
+ * tcgen05 (two passes: dK/dV per key tile, dQ per query tile); nothing N x N reaches HBM.  Same addressing as the
+ * forward (strided bf16 views, packed var-len keys through kv_off / kv_len).  Requires Nq % 128 == 0.
+ * dk / dv rows of keys >= kv_len[b] are not written.  `delta` is caller-owned workspace.                         */
+typedef struct PxaAttnBwdArgs {
+  const void* q; const void* k; const void* v;   /* as PxaAttnArgs                                              */
+  const void* o;        /* bf16 forward output, (b, i, h, d) at o[(b*Nq + i)*ldo + h*72 + d]                      */
+  const void* d_o;      /* bf16 gradient of o, row stride lddo                                                   */
+  const float* lse;     /* fp32 [B, H, Nq] written by the forward (PxaAttnArgs.lse)                              */
+  float* delta;         /* fp32 [B, H, Nq] workspace                                                             */
+  void* dq; void* dk; void* dv;                  /* bf16, addressed like q / k / v with the strides below        */
+  const int32_t* kv_len; const int32_t* kv_off;
+  int64_t q_sn, q_sh, k_sn, k_sh, v_sn, v_sh;
+  int64_t dq_sn, dq_sh, dk_sn, dk_sh, dv_sn, dv_sh;
+  int64_t ldo, lddo;
+  int64_t kv_rows;
+  int32_t B, H, Nq, Nk;
+  float scale;
+} PxaAttnBwdArgs;
+int pxa_flash_attn_d72_bwd_bf16(const PxaAttnBwdArgs* args, void* stream);
 
 #ifdef __cplusplus
 }

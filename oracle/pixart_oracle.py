@@ -261,6 +261,13 @@ def forward(sd: Dict[str, Tensor], cfg: OracleConfig, x: Tensor, timestep: Tenso
     return (out, inter) if return_intermediates else out
 
 
+def forward_grad(sd, cfg, x, timestep, y, mask=None, data_info=None, dtype=torch.float32):
+    """`forward` with autograd recording (the plain `forward` runs under no_grad): the fp32 reference for the
+    training-backward parity tests -- gradients of this graph w.r.t. `sd` entries that require grad are what
+    `loss.backward()` produces in the reference (train_scripts/train.py:197); pinned by tests/golden/train_*.pt."""
+    return forward.__wrapped__(sd, cfg, x, timestep, y, mask=mask, data_info=data_info, dtype=dtype)
+
+
 def forward_with_dpmsolver(sd, cfg, x, timestep, y, data_info=None, **kw) -> Tensor:
     """PixArtMS.forward_with_dpmsolver (PixArtMS.py:213-219): keep the eps half of the channels."""
     return forward(sd, cfg, x, timestep, y, data_info=data_info, **kw).chunk(2, dim=1)[0]

@@ -5,6 +5,8 @@ Only what the path `PixArtMS.forward -> 28 x PixArtMSBlock.forward` needs:
   lib.py     ctypes binding of libpixart_sm100.so
   model.py   host-side mirror of the reference model API (same names, ctor, state_dict layout)
   sampler.py DPM-Solver++ loop around the path (mirror of the reference's `diffusion.DPMS`), fused step kernel + CUDA graph
+  autograd.py / training.py  training path: the block's ops as autograd Functions over forward + backward kernels, IDDPM loss
+  parallel.py  batch-sharded inference replicas; bucketed gradient all-reduce for data-parallel training
   build.py   in-tree nvcc build
 """
 from .model import (MODELS, PixArtMS, PixArtMS_XL_2, PixArtMSBlock, build_model, install_into_reference)  # noqa: F401

@@ -1,0 +1,269 @@
+"""Training path: the block's ops as `torch.autograd.Function`s whose forward AND backward are sm_100a kernels.
+
+The reference trains through torch autograd (`train_scripts/train.py:197 accelerator.backward(loss)`) with per-block
+activation checkpointing (`diffusion/model/utils.py:28-45`, call site `PixArtMS.py:206`).  Here autograd is only the
+tape: every node below calls into libpixart_sm100.so in both directions --
+
+  LinearFn        y = x W^T + b           bwd: dX = dY W and dW += dY^T X on the tcgen05 GEMM (pxa_gemm_bf16 over
+                                          pxa_transpose_bf16'd operands; dW accumulates in fp32 through the TMA
+                                          reduce-add epilogue), db by pxa_colsum_bf16
+  LnModulateFn    LN(x)(1+scale)+shift    bwd: pxa_ln_modulate_bwd (dx, d shift, d scale)            PixArtMS.py:75,77
+  GateResidualFn  x + gate * y            bwd: pxa_gate_residual_bwd (dy, d gate)                    PixArtMS.py:75-77
+  GeluFn          gelu_tanh(pre)          bwd: pxa_gelu_tanh_bf16 with dh                            timm Mlp.act
+  SelfAttnFn / CrossAttnFn                bwd: pxa_flash_attn_d72_bwd_bf16 (flash-attention-2 recomputation from lse)
+                                                                                                PixArt_blocks.py:52-53,153
+
+Parameters may be fp32 (mixed-precision training, `train.py:369` accelerator mixed_precision) or bf16; the kernels
+always consume bf16 shadows, cached per parameter version, and gradients are produced in fp32 and cast to the
+parameter dtype.  There is no eager fallback: a missing library or a non-sm_100 device raises from `lib`.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import lib
+
+_SHADOW: Dict[Tuple[int, str], Tuple[int, torch.Tensor]] = {}
+
+
+def _shadow(p: torch.Tensor, kind: str) -> torch.Tensor:
+    """bf16 copy ('w') or bf16 transposed copy ('t') of a parameter, rebuilt only when the parameter was updated."""
+    key = (id(p), kind)
+    hit = _SHADOW.get(key)
+    if hit is not None and hit[0] == p._version and hit[1].device == p.device:
+        return hit[1]
+    src = p.detach()
+    w16 = src if src.dtype == torch.bfloat16 else src.to(torch.bfloat16)
+    val = w16.contiguous() if kind == "w" else lib.transpose(w16.contiguous())
+    _SHADOW[key] = (p._version, val)
+    return val
+
+
+def clear_shadow_cache() -> None:
+    _SHADOW.clear()
+
+
+def _t_pad8(a: torch.Tensor) -> torch.Tensor:
+    """a (R, C) bf16 -> a^T as a (C, roundup(R, 8)) K-contiguous GEMM operand (zero columns past R)."""
+    R, Cc = a.shape
+    Rp = (R + 7) // 8 * 8
+    if Rp == R:
+        return lib.transpose(a)
+    buf = torch.zeros((Cc, Rp), dtype=torch.bfloat16, device=a.device)
+    lib.transpose(a, buf[:, :R])
+    return buf
+
+
+class LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        assert x.dtype == torch.bfloat16 and x.dim() == 2
+        x = x.contiguous()
+        out = torch.empty((x.shape[0], weight.shape[0]), dtype=torch.bfloat16, device=x.device)
+        lib.gemm(x, _shadow(weight, "w"), None if bias is None else _shadow(bias, "w"), out)
+        ctx.save_for_backward(x, weight, bias)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias = ctx.saved_tensors
+        dy = dy.contiguous()
+        M, K = x.shape
+        N = weight.shape[0]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((M, K), dtype=torch.bfloat16, device=x.device)
+            lib.gemm(dy, _shadow(weight, "t"), None, dx)                       # dX = dY . W   (W^T is K-contiguous in N)
+        if ctx.needs_input_grad[1]:
+            dw32 = torch.zeros((N, K), dtype=torch.float32, device=x.device)
+            lib.gemm(_t_pad8(dy), _t_pad8(x), None, dw32, epilogue=lib.EPI_BIAS_RESIDUAL, residual=dw32)   # dW += dY^T . X
+            dw = dw32 if weight.dtype == torch.float32 else dw32.to(weight.dtype)
+        if bias is not None and ctx.needs_input_grad[2]:
+            db32 = torch.zeros((N,), dtype=torch.float32, device=x.device)
+            lib.colsum(dy, db32)
+            db = db32 if bias.dtype == torch.float32 else db32.to(bias.dtype)
+        return dx, dw, db
+
+
+class LnModulateFn(torch.autograd.Function):
+    """xn = LN(x) * (1 + mod[:, i_scale]) + mod[:, i_shift]; x (B*N, C) fp32, mod (B, G, C) fp32 contiguous."""
+
+    @staticmethod
+    def forward(ctx, x32, mod, i_shift, i_scale, rows_per_batch):
+        assert x32.dtype == torch.float32 and mod.dtype == torch.float32 and mod.is_contiguous()
+        x32 = x32.contiguous()
+        xn = torch.empty(x32.shape, dtype=torch.bfloat16, device=x32.device)
+        lib.ln_modulate(x32, mod[:, i_shift], mod[:, i_scale], xn, mod_batch_stride=mod.stride(0), rows_per_batch=rows_per_batch)
+        ctx.save_for_backward(x32, mod)
+        ctx.idx = (i_shift, i_scale, rows_per_batch)
+        return xn
+
+    @staticmethod
+    def backward(ctx, dxn):
+        x32, mod = ctx.saved_tensors
+        i_shift, i_scale, rpb = ctx.idx
+        B, G, C = mod.shape
+        dx = torch.empty_like(x32)
+        dsh = torch.zeros((B, C), dtype=torch.float32, device=x32.device)
+        dsc = torch.zeros((B, C), dtype=torch.float32, device=x32.device)
+        lib.ln_modulate_bwd(x32, dxn.contiguous(), mod[:, i_scale], dx, dsh, dsc, mod_batch_stride=mod.stride(0),
+                            rows_per_batch=rpb)
+        dmod = None
+        if ctx.needs_input_grad[1]:
+            dmod = torch.zeros_like(mod)
+            dmod[:, i_shift] = dsh
+            dmod[:, i_scale] = dsc
+        return dx, dmod, None, None, None
+
+
+class GateResidualFn(torch.autograd.Function):
+    """out = x + mod[:, i_gate] * y (i_gate < 0: no gate); x, out fp32 (B*N, C), y bf16."""
+
+    @staticmethod
+    def forward(ctx, x32, y, mod, i_gate, rows_per_batch):
+        x32, y = x32.contiguous(), y.contiguous()
+        out = torch.empty_like(x32)
+        gate = mod[:, i_gate] if i_gate >= 0 else None
+        lib.gate_residual_fwd(x32, y, gate, out, gate_batch_stride=mod.stride(0) if gate is not None else 0,
+                              rows_per_batch=rows_per_batch)
+        ctx.save_for_backward(y, mod if gate is not None else None)
+        ctx.idx = (i_gate, rows_per_batch)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, mod = ctx.saved_tensors
+        i_gate, rpb = ctx.idx
+        dout = dout.contiguous()
+        dy = torch.empty(dout.shape, dtype=torch.bfloat16, device=dout.device)
+        dmod = None
+        if mod is not None:
+            B, G, C = mod.shape
+            want_dgate = ctx.needs_input_grad[2]
+            dg = torch.zeros((B, C), dtype=torch.float32, device=dout.device) if want_dgate else None
+            lib.gate_residual_bwd(dout, y if want_dgate else None, mod[:, i_gate], dy, dg, gate_batch_stride=mod.stride(0),
+                                  rows_per_batch=rpb)
+            if want_dgate:
+                dmod = torch.zeros_like(mod)
+                dmod[:, i_gate] = dg
+        else:
+            lib.gate_residual_bwd(dout, None, None, dy, None, rows_per_batch=rpb)
+        return dout, dy, dmod, None, None
+
+
+class GeluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pre):
+        pre = pre.contiguous()
+        ctx.save_for_backward(pre)
+        return lib.gelu_tanh(pre)
+
+    @staticmethod
+    def backward(ctx, dh):
+        (pre,) = ctx.saved_tensors
+        return lib.gelu_tanh(pre, dh=dh.contiguous())
+
+
+class SelfAttnFn(torch.autograd.Function):
+    """o (B*N, C) = attention over the q/k/v slices of the qkv GEMM output (B*N, 3C) (PixArt_blocks.py:130-153)."""
+
+    @staticmethod
+    def forward(ctx, qkv, B, H, N, scale):
+        qkv = qkv.contiguous()
+        M, C3 = qkv.shape
+        C = C3 // 3
+        D = C // H
+        q3 = qkv.view(M, 3, H, D)
+        o = torch.empty((M, C), dtype=torch.bfloat16, device=qkv.device)
+        lse = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device)
+        st = (3 * C, D)
+        lib.flash_attn(q3[:, 0], q3[:, 1], q3[:, 2], o, B=B, H=H, Nq=N, Nk=N, kv_rows=M, q_strides=st, k_strides=st,
+                       v_strides=st, scale=scale, lse=lse)
+        ctx.save_for_backward(qkv, o, lse)
+        ctx.geom = (B, H, N, scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        qkv, o, lse = ctx.saved_tensors
+        B, H, N, scale = ctx.geom
+        M, C3 = qkv.shape
+        C = C3 // 3
+        D = C // H
+        q3 = qkv.view(M, 3, H, D)
+        dqkv = torch.empty_like(qkv)
+        d3 = dqkv.view(M, 3, H, D)
+        st = (3 * C, D)
+        lib.flash_attn_bwd(q3[:, 0], q3[:, 1], q3[:, 2], o, d_o.contiguous(), lse, d3[:, 0], d3[:, 1], d3[:, 2], B=B, H=H,
+                           Nq=N, Nk=N, kv_rows=M, q_strides=st, k_strides=st, v_strides=st, dq_strides=st, dk_strides=st,
+                           dv_strides=st, scale=scale)
+        return dqkv, None, None, None, None
+
+
+class CrossAttnFn(torch.autograd.Function):
+    """o (B*N, C) = var-len attention of q (B*N, C) over the caption keys kv (rows, 2C) (PixArt_blocks.py:43-58)."""
+
+    @staticmethod
+    def forward(ctx, q, kv, kv_len, kv_off, B, H, N, max_keys, scale):
+        q, kv = q.contiguous(), kv.contiguous()
+        M, C = q.shape
+        D = C // H
+        kv4 = kv.view(-1, 2, H, D)
+        o = torch.empty((M, C), dtype=torch.bfloat16, device=q.device)
+        lse = torch.empty((B, H, N), dtype=torch.float32, device=q.device)
+        lib.flash_attn(q, kv4[:, 0], kv4[:, 1], o, B=B, H=H, Nq=N, Nk=max_keys, kv_rows=kv.shape[0], kv_len=kv_len,
+                       kv_off=kv_off, q_strides=(C, D), k_strides=(2 * C, D), v_strides=(2 * C, D), scale=scale, lse=lse)
+        ctx.save_for_backward(q, kv, o, lse, kv_len, kv_off)
+        ctx.geom = (B, H, N, max_keys, scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        q, kv, o, lse, kv_len, kv_off = ctx.saved_tensors
+        B, H, N, max_keys, scale = ctx.geom
+        M, C = q.shape
+        D = C // H
+        kv4 = kv.view(-1, 2, H, D)
+        dq = torch.empty_like(q)
+        dkv = torch.zeros_like(kv)                    # rows of keys >= kv_len[b] (padding) get no gradient
+        d4 = dkv.view(-1, 2, H, D)
+        lib.flash_attn_bwd(q, kv4[:, 0], kv4[:, 1], o, d_o.contiguous(), lse, dq, d4[:, 0], d4[:, 1], B=B, H=H, Nq=N,
+                           Nk=max_keys, kv_rows=kv.shape[0], kv_len=kv_len, kv_off=kv_off, q_strides=(C, D),
+                           k_strides=(2 * C, D), v_strides=(2 * C, D), dq_strides=(C, D), dk_strides=(2 * C, D),
+                           dv_strides=(2 * C, D), scale=scale)
+        return dq, dkv, None, None, None, None, None, None, None
+
+
+def linear(x: torch.Tensor, mod: torch.nn.Linear) -> torch.Tensor:
+    return LinearFn.apply(x, mod.weight, mod.bias)
+
+
+def block_forward_train(blk, x32: torch.Tensor, cond: torch.Tensor, kv_len: Optional[torch.Tensor],
+                        kv_off: Optional[torch.Tensor], max_keys: int, mod: torch.Tensor, B: int, N: int) -> torch.Tensor:
+    """One PixArtMSBlock (PixArtMS.py:71-79) on the differentiable kernel ops; same arguments as `run_kernels`, but
+    out of place (returns the new fp32 residual stream) so autograd / activation checkpointing can replay it."""
+    a, ca, mlp = blk.attn, blk.cross_attn, blk.mlp
+    H = a.num_heads
+    if a.sr_ratio > 1:
+        raise NotImplementedError("training with KV compression (sr_ratio > 1) has no backward kernel yet")
+    if blk.training and blk.drop_path_rate > 0:
+        raise NotImplementedError("stochastic depth (drop_path > 0) is not supported by the kernel block")
+    if not isinstance(a.q_norm, torch.nn.Identity):
+        raise NotImplementedError("qk_norm=True is not supported by the kernel block yet")
+    mod = mod.contiguous()
+    # (1) x += gate_msa * proj(attn(LN(x) * (1 + scale_msa) + shift_msa))                         PixArtMS.py:75
+    xn = LnModulateFn.apply(x32, mod, 0, 1, N)
+    ao = SelfAttnFn.apply(linear(xn, a.qkv), B, H, N, a.scale)
+    x32 = GateResidualFn.apply(x32, linear(ao, a.proj), mod, 2, N)
+    # (2) x += proj(cross_attn(x, cond))                                                          PixArtMS.py:76
+    qx = linear(x32.to(torch.bfloat16), ca.q_linear)
+    kv = linear(cond, ca.kv_linear)
+    ao = CrossAttnFn.apply(qx, kv, kv_len, kv_off, B, H, N, max_keys, ca.head_dim ** -0.5)
+    x32 = GateResidualFn.apply(x32, linear(ao, ca.proj), mod, -1, N)
+    # (3) x += gate_mlp * fc2(gelu_tanh(fc1(LN(x) * (1 + scale_mlp) + shift_mlp)))               PixArtMS.py:77
+    xn = LnModulateFn.apply(x32, mod, 3, 4, N)
+    h = GeluFn.apply(linear(xn, mlp.fc1))
+    x32 = GateResidualFn.apply(x32, linear(h, mlp.fc2), mod, 5, N)
+    return x32

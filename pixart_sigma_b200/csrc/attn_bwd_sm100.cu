@@ -1,0 +1,369 @@
+// pxa_flash_attn_d72_bwd_bf16: backward of softmax(Q K^T * scale) V for head_dim 72 on tcgen05 tensor cores (sm_100a).
+// Replaces the autograd backward of xformers.ops.memory_efficient_attention at PixArt_blocks.py:52-53,153 when
+// train_scripts/train.py:197 runs the loss backward through the blocks.
+//
+// Flash-attention-2 style recomputation from (Q, K, V, dO, lse, delta); nothing N x N ever reaches HBM.  One kernel
+// template, two launches -- each is "a 128-row STATIONARY tile against a stream of 128-row tiles":
+//   dKV pass (kDKV = true):  stationary K_j, V_j;   stream Q_i, dO_i over all query tiles of the sample
+//       S'  = K_j Q_i^T            (keys on TMEM lanes, queries on columns)      P'  = exp2(S' * c - lse[q])
+//       dP' = V_j dO_i^T                                                         dS' = P' * (dP' - delta[q])
+//       dV_j += P' dO_i,   dK_j += dS' Q_i                                       (dK scaled by `scale` at the end)
+//   dQ pass  (kDKV = false): stationary Q_i, dO_i;  stream K_j, V_j over the sample's key tiles
+//       S' = Q_i K_j^T,  dP' = dO_i V_j^T,  dS' as above (statistics per lane),  dQ_i += dS' K_j
+// The dQ pass recomputes S' and dP' instead of exchanging dS through smem / atomics: 7 instead of 5 tile products per
+// (i, j) pair, in exchange for a deterministic kernel built only from the operand forms the forward kernel already
+// uses: score MMAs are SS with both operands K-major (d contiguous; 4 K-steps from the 64-wide main tile + 1 from the
+// tail tile), gradient MMAs are TS (A = P' / dS' read from TMEM as bf16, written by the softmax threads over the fp32
+// columns they came from) with the streamed tile consumed MN-major in its natural [row, d] layout (N = 80: main + tail).
+//
+// 384 threads: warp 0 TMA producer, warp 1 MMA issuer (one elected thread), warp 2 TMEM allocator, warps 4-11 the
+// elementwise stage: thread = (TMEM lane, column half) -> 64 columns of S' and dP' per tile.
+// head_dim 72: every tile is staged as a main part (d 0..63) and a 64-wide tail part (d 64..127, zero-filled past 71 by
+// TMA out-of-bounds handling), both 128B-swizzled, so one staging serves the K-major and the MN-major use.
+//
+// Algorithmic work: dKV pass 8 * Nq * Nk * 72 FLOP, dQ pass 6 * Nq * Nk * 72 FLOP per (sample, head) (model FLOPs of the
+// attention backward: 10 * Nq * Nk * 72 -- the difference is the recomputation).  Requires Nq % 128 == 0.
+#include "host_common.cuh"
+#include "ptx.cuh"
+
+namespace pxa {
+
+constexpr int kBwdThreads = 384;
+constexpr int kBT = 128;                       // rows per tile (both stationary and streamed)
+constexpr int kBMain = 128 * 128;              // 128 rows x 64 bf16
+constexpr int kBTile = 2 * kBMain;             // main + 64-wide tail
+constexpr int kBStages = 2;
+constexpr int kBOffX1 = 0;
+constexpr int kBOffX2 = kBTile;
+constexpr int kBOffY = 2 * kBTile;             // stage s: Y1 at kBOffY + s * 2 * kBTile, Y2 right behind it
+constexpr int kBOffStat = kBOffY + kBStages * 2 * kBTile;   // 2 buffers x (lse[128] | delta[128]) fp32
+constexpr int kBOffBars = kBOffStat + 2048;
+constexpr int kBwdSmem = kBOffBars + 256 + 1024;            // + alignment slack
+
+constexpr uint32_t kBColS = 0;       // S'  (128 fp32 columns; bf16 P' over the first 32 columns of each 64-column half)
+constexpr uint32_t kBColDP = 128;    // dP' (same, dS')
+constexpr uint32_t kBColAcc2 = 256;  // dK (dKV pass) / dQ (dQ pass): 80 columns
+constexpr uint32_t kBColAcc1 = 384;  // dV (dKV pass): 80 columns
+
+struct AttnBwdParams {
+  const float* lse;        // [B, H, Nq] log2-domain log-sum-exp written by the forward kernel
+  const float* delta;      // [B, H, Nq] rowsum(dO * O)
+  __nv_bfloat16* d2;       // dK (dKV pass) / dQ (dQ pass)
+  __nv_bfloat16* d1;       // dV (dKV pass)
+  long long d2_sn, d2_sh, d1_sn, d1_sh;
+  const int* kv_len;
+  const int* kv_off;
+  int B, H, Nq, Nk;
+  float scale, scale_log2;
+};
+
+template <bool kDKV>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __grid_constant__ CUtensorMap tm_x1t,
+                          const __grid_constant__ CUtensorMap tm_x2m, const __grid_constant__ CUtensorMap tm_x2t,
+                          const __grid_constant__ CUtensorMap tm_y1m, const __grid_constant__ CUtensorMap tm_y1t,
+                          const __grid_constant__ CUtensorMap tm_y2m, const __grid_constant__ CUtensorMap tm_y2t,
+                          const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBOffBars);
+  uint64_t* x_full = bars;                     // [1]
+  uint64_t* y_full = bars + 1;                 // [kBStages]  TMA -> MMA
+  uint64_t* y_empty = y_full + kBStages;       // [kBStages]  MMA -> TMA
+  uint64_t* s_full = y_empty + kBStages;       // [1]  MMA -> elementwise: S' and dP' of this iteration are in TMEM
+  uint64_t* p_full = s_full + 1;               // [1]  elementwise -> MMA: P' / dS' written (256 arrivals)
+  uint64_t* acc_full = p_full + 1;             // [1]  MMA -> epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  float* stat = reinterpret_cast<float*>(smem + kBOffStat);     // [2][256]: lse[128] | delta[128] of a streamed q tile
+
+  const int warp = warp_idx_sync();
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int t0 = blockIdx.x * kBT;
+
+  int kv_len = p.kv_len ? p.kv_len[b] : p.Nk;
+  kv_len = min(max(kv_len, 0), p.Nk);
+  const int kv_row0 = p.kv_off ? p.kv_off[b] : b * p.Nk;
+  if (kDKV && t0 >= kv_len) return;            // block-uniform: this key tile holds no keys of the sample
+  const int x_row0 = kDKV ? kv_row0 + t0 : b * p.Nq + t0;
+  const int y_row0 = kDKV ? b * p.Nq : kv_row0;
+  const int n_iter = kDKV ? p.Nq / kBT : (kv_len + kBT - 1) / kBT;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tm_x1m); prefetch_tmap(&tm_x1t); prefetch_tmap(&tm_x2m); prefetch_tmap(&tm_x2t);
+    prefetch_tmap(&tm_y1m); prefetch_tmap(&tm_y1t); prefetch_tmap(&tm_y2m); prefetch_tmap(&tm_y2t);
+    mbar_init(x_full, 1);
+    for (int s = 0; s < kBStages; ++s) {
+      mbar_init(&y_full[s], 1);
+      mbar_init(&y_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 256);
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (n_iter > 0 && elect_one()) {
+      mbar_arrive_expect_tx(x_full, 2 * kBTile);
+      tma_load_3d(smem + kBOffX1, &tm_x1m, x_full, 0, h, x_row0, kEvictNormal);
+      tma_load_3d(smem + kBOffX1 + kBMain, &tm_x1t, x_full, 64, h, x_row0, kEvictNormal);
+      tma_load_3d(smem + kBOffX2, &tm_x2m, x_full, 0, h, x_row0, kEvictNormal);
+      tma_load_3d(smem + kBOffX2 + kBMain, &tm_x2t, x_full, 64, h, x_row0, kEvictNormal);
+      for (int it = 0; it < n_iter; ++it) {
+        const int stage = it % kBStages;
+        const uint32_t ph = (it / kBStages) & 1;
+        mbar_wait(&y_empty[stage], ph ^ 1);
+        uint8_t* y1 = smem + kBOffY + stage * 2 * kBTile;
+        uint8_t* y2 = y1 + kBTile;
+        const int yrow = y_row0 + it * kBT;
+        mbar_arrive_expect_tx(&y_full[stage], 2 * kBTile);
+        tma_load_3d(y1, &tm_y1m, &y_full[stage], 0, h, yrow, kEvictLast);
+        tma_load_3d(y1 + kBMain, &tm_y1t, &y_full[stage], 64, h, yrow, kEvictLast);
+        tma_load_3d(y2, &tm_y2m, &y_full[stage], 0, h, yrow, kEvictLast);
+        tma_load_3d(y2 + kBMain, &tm_y2t, &y_full[stage], 64, h, yrow, kEvictLast);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (n_iter > 0 && elect_one()) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_g = make_idesc_bf16(128, 80, 0, 1);     // streamed tile MN-major, N = d 0..79
+      const uint32_t sbase = smem_u32(smem);
+      const uint32_t t_s = tmem_base + kBColS, t_dp = tmem_base + kBColDP;
+      // score product D = X Y^T: both tiles K-major; 4 K-steps in the main parts + 1 in the tails (d 64..79, 72.. zero)
+      auto issue_score = [&](uint32_t d, uint32_t x, uint32_t y) {
+        const uint64_t xd = make_smem_desc(x, 16, 1024, kLayoutSW128);
+        const uint64_t yd = make_smem_desc(y, 16, 1024, kLayoutSW128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(d, xd + 2 * k, yd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        const uint64_t xt = make_smem_desc(x + kBMain, 16, 1024, kLayoutSW128);
+        const uint64_t yt = make_smem_desc(y + kBMain, 16, 1024, kLayoutSW128);
+        umma_ss(d, xt, yt, idesc_s, 1u);
+      };
+      // gradient product acc += A Y: A = bf16 P' / dS' in TMEM (K-step k of 16 streamed rows at packed columns
+      // 64 (k / 4) + 8 (k % 4): each column half holds its own 32 packed columns), Y MN-major (main + tail atoms LBO apart)
+      auto issue_grad = [&](uint32_t acc, uint32_t a_tmem, uint32_t y, bool first) {
+        const uint64_t yd = make_smem_desc(y, kBMain, 1024, kLayoutSW128);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ts(acc, a_tmem + 64 * (k >> 2) + 8 * (k & 3), yd + (uint64_t)(k * (2048 >> 4)), idesc_g, (first && k == 0) ? 0u : 1u);
+      };
+      mbar_wait(x_full, 0);
+      for (int it = 0; it < n_iter; ++it) {
+        const int stage = it % kBStages;
+        mbar_wait(&y_full[stage], (it / kBStages) & 1);
+        tc_fence_after();
+        const uint32_t y1 = sbase + kBOffY + stage * 2 * kBTile;
+        const uint32_t y2 = y1 + kBTile;
+        issue_score(t_s, sbase + kBOffX1, y1);
+        issue_score(t_dp, sbase + kBOffX2, y2);
+        umma_commit(s_full);
+        mbar_wait(p_full, it & 1);
+        tc_fence_after();
+        if (kDKV) issue_grad(tmem_base + kBColAcc1, t_s, y2, it == 0);          // dV += P' dO
+        issue_grad(tmem_base + kBColAcc2, t_dp, y1, it == 0);                   // dK += dS' Q   /   dQ += dS' K
+        umma_commit(&y_empty[stage]);
+      }
+      umma_commit(acc_full);
+    }
+  } else if (warp >= 4) {
+    // ================================================================ elementwise stage + epilogue
+    const int tid = threadIdx.x - 128;             // 0..255
+    const int half = (warp - 4) >> 2;              // column half of the 128 streamed rows
+    const int qd = warp & 3;                       // TMEM sub-partition this warp may access
+    const int row = qd * 32 + lane;                // stationary row (TMEM lane)
+    const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t t_s = tmem_base + kBColS + lane_sel + 64 * half;
+    const uint32_t t_dp = tmem_base + kBColDP + lane_sel + 64 * half;
+    const float sl2 = p.scale_log2;
+    const size_t stat_base = ((size_t)b * p.H + h) * p.Nq;
+    float lse_r = 0.f, delta_r = 0.f;
+    if (!kDKV) {                                   // statistics of this thread's query row
+      const int qrow = min(t0 + row, p.Nq - 1);
+      lse_r = p.lse[stat_base + qrow];
+      delta_r = p.delta[stat_base + qrow];
+    } else if (n_iter > 0) {                       // statistics of the first streamed query tile -> smem buffer 0
+      stat[tid] = tid < 128 ? p.lse[stat_base + tid] : p.delta[stat_base + tid - 128];
+      named_bar_sync(1, 256);
+    }
+
+    for (int it = 0; it < n_iter; ++it) {
+      float nxt = 0.f;
+      if (kDKV && it + 1 < n_iter) {               // next tile's statistics: global load in flight during this tile
+        const size_t o = stat_base + (size_t)(it + 1) * kBT + (tid & 127);
+        nxt = tid < 128 ? p.lse[o] : p.delta[o];
+      }
+      const float* st = stat + (it & 1) * 256 + 64 * half;      // lse of this thread's 64 columns; delta 128 floats further
+      // dQ pass: streamed rows are keys, the sample's last tile may be partial
+      const int rem = kDKV ? (1 << 30) : kv_len - it * kBT - 64 * half;
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t vs[32], vd[32];
+        tmem_ld_32x32b_x32_pair(t_s + 32 * c, vs, t_dp + 32 * c, vd);
+        uint32_t pp[16], pd[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float4 l4, d4;
+          if (kDKV) {
+            l4 = *reinterpret_cast<const float4*>(st + 32 * c + i);
+            d4 = *reinterpret_cast<const float4*>(st + 128 + 32 * c + i);
+          } else {
+            l4 = make_float4(lse_r, lse_r, lse_r, lse_r);
+            d4 = make_float4(delta_r, delta_r, delta_r, delta_r);
+          }
+          const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
+          const float ds[4] = {d4.x, d4.y, d4.z, d4.w};
+          float pr[4], gr[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float pv = fast_exp2(fmaf(__uint_as_float(vs[i + e]), sl2, -ls[e]));
+            if (32 * c + i + e >= rem) pv = 0.f;
+            pr[e] = pv;
+            gr[e] = pv * (__uint_as_float(vd[i + e]) - ds[e]);
+          }
+          pp[i / 2] = pack_bf16x2(pr[0], pr[1]);
+          pp[i / 2 + 1] = pack_bf16x2(pr[2], pr[3]);
+          pd[i / 2] = pack_bf16x2(gr[0], gr[1]);
+          pd[i / 2 + 1] = pack_bf16x2(gr[2], gr[3]);
+        }
+        // bf16 results over the fp32 columns this thread has already consumed (its own half: no cross-warp hazard)
+        if (kDKV) tmem_st_32x32b_x16(t_s + 16 * c, pp);
+        tmem_st_32x32b_x16(t_dp + 16 * c, pd);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full);
+      if (kDKV) {
+        if (it + 1 < n_iter) stat[((it + 1) & 1) * 256 + tid] = nxt;
+        named_bar_sync(1, 256);
+      }
+    }
+
+    // ---- epilogue: half 0 writes acc2 (dK / dQ, times the softmax scale), half 1 writes acc1 (dV, dKV pass only)
+    if (n_iter > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+    }
+    if (half == 0 || kDKV) {
+      const uint32_t t_acc = tmem_base + (half == 0 ? kBColAcc2 : kBColAcc1) + lane_sel;
+      const float mul = half == 0 ? p.scale : 1.0f;
+      const bool row_ok = kDKV ? (t0 + row < kv_len) : (t0 + row < p.Nq);
+      __nv_bfloat16* base = half == 0 ? p.d2 : p.d1;
+      const long long sn = half == 0 ? p.d2_sn : p.d1_sn;
+      const long long sh = half == 0 ? p.d2_sh : p.d1_sh;
+      uint4* d4p = reinterpret_cast<uint4*>(base + (size_t)(x_row0 + row) * sn + (size_t)h * sh);
+#pragma unroll
+      for (int piece = 0; piece < 3; ++piece) {       // columns 0..31, 32..63, 64..71
+        uint32_t o[32];
+        if (n_iter > 0) {
+          if (piece < 2) {
+            tmem_ld_32x32b_x32(t_acc + 32 * piece, o);
+          } else {
+            uint32_t o8[8];
+            tmem_ld_32x32b_x8(t_acc + 64, o8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = o8[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = 0u;
+        }
+        if (row_ok) {
+          const int nvec = piece < 2 ? 4 : 1;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c < nvec)
+              d4p[4 * piece + c] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * c]) * mul, __uint_as_float(o[8 * c + 1]) * mul),
+                                              pack_bf16x2(__uint_as_float(o[8 * c + 2]) * mul, __uint_as_float(o[8 * c + 3]) * mul),
+                                              pack_bf16x2(__uint_as_float(o[8 * c + 4]) * mul, __uint_as_float(o[8 * c + 5]) * mul),
+                                              pack_bf16x2(__uint_as_float(o[8 * c + 6]) * mul, __uint_as_float(o[8 * c + 7]) * mul));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// main (d 0..63) and 64-wide tail (d 64..127, zero past 71) maps of a [rows, H, 72] bf16 view, both 128B-swizzled
+static int make_bwd_maps(CUtensorMap* main_map, CUtensorMap* tail_map, const void* base, int H, long long rows, long long s_row,
+                         long long s_head) {
+  uint64_t dims[3] = {72, (uint64_t)H, (uint64_t)rows};
+  uint64_t str[2] = {(uint64_t)s_head * 2, (uint64_t)s_row * 2};
+  uint32_t box[3] = {64, 1, 128};
+  int rc = make_tmap_bf16(main_map, base, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  return make_tmap_bf16(tail_map, base, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+}  // namespace pxa
+
+
+extern "C" int pxa_flash_attn_d72_bwd_bf16(const PxaAttnBwdArgs* args, void* stream) {
+  using namespace pxa;
+  if (!args) return fail(PXA_ERR_ARG, "null args");
+  const PxaAttnBwdArgs& a = *args;
+  if (!a.q || !a.k || !a.v || !a.o || !a.d_o || !a.lse || !a.delta || !a.dq || !a.dk || !a.dv)
+    return fail(PXA_ERR_ARG, "null pointer");
+  if (a.B <= 0 || a.H <= 0 || a.Nq <= 0 || a.Nk <= 0 || a.kv_rows <= 0) return fail(PXA_ERR_ARG, "bad B/H/Nq/Nk/kv_rows");
+  if (a.Nq % 128) return fail(PXA_ERR_ARG, "the attention backward needs Nq %% 128 == 0 (got %d)", a.Nq);
+  const int64_t strides[] = {a.q_sn, a.q_sh, a.k_sn, a.k_sh, a.v_sn, a.v_sh, a.ldo, a.lddo,
+                             a.dq_sn, a.dq_sh, a.dk_sn, a.dk_sh, a.dv_sn, a.dv_sh};
+  for (int64_t s : strides)
+    if (s & 7) return fail(PXA_ERR_ALIGN, "strides must be multiples of 8 elements");
+  if ((reinterpret_cast<uintptr_t>(a.dq) | reinterpret_cast<uintptr_t>(a.dk) | reinterpret_cast<uintptr_t>(a.dv) |
+       reinterpret_cast<uintptr_t>(a.o) | reinterpret_cast<uintptr_t>(a.d_o)) & 15)
+    return fail(PXA_ERR_ALIGN, "o / dO / dq / dk / dv must be 16-byte aligned");
+  PXA_REQUIRE_SM100();
+  int rc = pxa_attn_delta_d72(a.o, a.d_o, a.delta, a.B, a.H, a.Nq, a.ldo, a.lddo, stream);
+  if (rc) return rc;
+  CUtensorMap qm, qt, km, kt, vm, vt, gm, gt;
+  const long long q_rows = (long long)a.B * a.Nq;
+  if ((rc = make_bwd_maps(&qm, &qt, a.q, a.H, q_rows, a.q_sn, a.q_sh))) return rc;
+  if ((rc = make_bwd_maps(&km, &kt, a.k, a.H, a.kv_rows, a.k_sn, a.k_sh))) return rc;
+  if ((rc = make_bwd_maps(&vm, &vt, a.v, a.H, a.kv_rows, a.v_sn, a.v_sh))) return rc;
+  if ((rc = make_bwd_maps(&gm, &gt, a.d_o, a.H, q_rows, a.lddo, 72))) return rc;
+  AttnBwdParams p;
+  p.lse = a.lse; p.delta = a.delta;
+  p.kv_len = a.kv_len; p.kv_off = a.kv_off;
+  p.B = a.B; p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk;
+  p.scale = a.scale;
+  p.scale_log2 = a.scale * 1.4426950408889634f;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  {  // dK, dV
+    auto kern = flash_attn_d72_bwd_kernel<true>;
+    PXA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+    p.d2 = reinterpret_cast<__nv_bfloat16*>(a.dk); p.d2_sn = a.dk_sn; p.d2_sh = a.dk_sh;
+    p.d1 = reinterpret_cast<__nv_bfloat16*>(a.dv); p.d1_sn = a.dv_sn; p.d1_sh = a.dv_sh;
+    dim3 grid((a.Nk + kBT - 1) / kBT, a.H, a.B);
+    kern<<<grid, kBwdThreads, kBwdSmem, s>>>(km, kt, vm, vt, qm, qt, gm, gt, p);
+    launch_counter()++;
+    PXA_CHECK_CUDA(cudaGetLastError());
+  }
+  {  // dQ
+    auto kern = flash_attn_d72_bwd_kernel<false>;
+    PXA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+    p.d2 = reinterpret_cast<__nv_bfloat16*>(a.dq); p.d2_sn = a.dq_sn; p.d2_sh = a.dq_sh;
+    p.d1 = nullptr; p.d1_sn = p.d1_sh = 0;
+    dim3 grid(a.Nq / kBT, a.H, a.B);
+    kern<<<grid, kBwdThreads, kBwdSmem, s>>>(qm, qt, gm, gt, km, kt, vm, vt, p);
+    launch_counter()++;
+    PXA_CHECK_CUDA(cudaGetLastError());
+  }
+  return PXA_OK;
+}

@@ -75,6 +75,7 @@ constexpr uint32_t kColL = 336;     // L_A at 336, L_B at 464: row sums of P (16
 
 struct AttnParams {
   __nv_bfloat16* out;
+  float* lse;           // optional [B, H, Nq]: log2-domain log-sum-exp of the scaled scores (training: consumed by the backward)
   const int* kv_len;
   const int* kv_off;
   int B, H, Nq, Nk, ldo;
@@ -442,6 +443,8 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
 #endif
     }
     const float inv = row_sum > 0.f ? 1.0f / row_sum : 0.f;      // n_blocks == 0 (no keys): zeros
+    if (p.lse != nullptr && qrow < p.Nq)                          // P = exp2(S * scale_log2 - lse) in the backward
+      p.lse[((size_t)b * p.H + h) * p.Nq + qrow] = row_sum > 0.f ? fmaf(m_ref, sl2, log2f(row_sum)) : 0.f;
     uint4* d4 = reinterpret_cast<uint4*>(p.out + (size_t)(b * p.Nq + qrow) * p.ldo + h * kD);
     const bool row_ok = qrow < p.Nq;
 #pragma unroll
@@ -526,6 +529,7 @@ extern "C" int pxa_flash_attn_d72_bf16(const PxaAttnArgs* args, void* stream) {
   if ((rc = make_qkv_maps(&vm, &vt, a.v, a.H, a.kv_rows, a.v_sn, a.v_sh, true))) return rc;
   AttnParams p;
   p.out = reinterpret_cast<__nv_bfloat16*>(a.out);
+  p.lse = a.lse;
   p.kv_len = a.kv_len;
   p.kv_off = a.kv_off;
   p.B = a.B; p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk; p.ldo = a.ldo;

@@ -1,0 +1,439 @@
+// HBM-bound kernels of the training backward pass (train_scripts/train.py:180-220 runs
+// loss.backward() through the block; these replace the autograd kernels of torch's LayerNorm / GELU / mul / add / sum and
+// the transposes its matmul backward performs implicitly):
+//   transpose_bf16        A[R, C] -> A^T[C, R]   (operands of the dgrad / wgrad GEMMs, which take K-contiguous inputs)
+//   gelu_fwd / gelu_bwd   h = gelu_tanh(pre);  dpre = dh * gelu_tanh'(pre)
+//   gate_residual_fwd/bwd out = x + gate[b] * y;  dy = dout * gate[b],  dgate[b] += sum_rows dout * y
+//   ln_modulate_bwd       dx = LN-backward((1 + scale[b]) * dxn);  dshift[b] += sum dxn;  dscale[b] += sum dxn * xhat
+//   colsum_bf16           out[c] += sum_rows a[r, c]           (bias gradients)
+//   attn_delta            delta[b, h, i] = sum_d dO[b,i,h,d] * O[b,i,h,d]   (row term of the softmax backward)
+// One pass over the data each, 128-bit accesses, fp32 arithmetic; the per-sample / per-column reductions accumulate
+// in registers over a block of rows and finish with fp32 atomics.
+#include "host_common.cuh"
+#include "ptx.cuh"
+
+namespace pxa {
+
+PXA_DEVICE float warp_sum_b(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------- transpose
+// 64 x 64 tile through smem (padded rows); reads and writes are 128-byte row segments.  kPairs: 32-bit accesses (needs
+// even R, C, ldi, ldo and 4-byte aligned bases); otherwise element-wise accesses (odd row counts such as packed captions).
+template <bool kPairs>
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in,
+                                                             __nv_bfloat16* __restrict__ out, int R, int C, long long ldi,
+                                                             long long ldo) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + ty + 8 * i;
+    const int c = c0 + 2 * tx;
+    if constexpr (kPairs) {
+      uint32_t v = 0u;
+      if (r < R && c < C) v = *reinterpret_cast<const uint32_t*>(in + (size_t)r * ldi + c);
+      *reinterpret_cast<uint32_t*>(&tile[ty + 8 * i][2 * tx]) = v;
+    } else {
+      const __nv_bfloat16 z = __float2bfloat16(0.f);
+      tile[ty + 8 * i][2 * tx] = (r < R && c < C) ? in[(size_t)r * ldi + c] : z;
+      tile[ty + 8 * i][2 * tx + 1] = (r < R && c + 1 < C) ? in[(size_t)r * ldi + c + 1] : z;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + ty + 8 * i;          // output row
+    const int r = r0 + 2 * tx;              // output column pair
+    if (c < C && r < R) {
+      if constexpr (kPairs) {
+        __nv_bfloat162 v;
+        v.x = tile[2 * tx][ty + 8 * i];
+        v.y = tile[2 * tx + 1][ty + 8 * i];
+        *reinterpret_cast<__nv_bfloat162*>(out + (size_t)c * ldo + r) = v;
+      } else {
+        out[(size_t)c * ldo + r] = tile[2 * tx][ty + 8 * i];
+        if (r + 1 < R) out[(size_t)c * ldo + r + 1] = tile[2 * tx + 1][ty + 8 * i];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- GELU(tanh)
+PXA_DEVICE float gelu_tanh_grad(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float x2 = x * x;
+  const float u = k0 * x * fmaf(k1, x2, 1.0f);
+  const float t = fast_tanh(u);
+  const float du = k0 * fmaf(3.0f * k1, x2, 1.0f);
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
+}
+
+template <bool kBwd>
+__global__ void __launch_bounds__(256) gelu_kernel(const uint4* __restrict__ pre, const uint4* __restrict__ dh,
+                                                   uint4* __restrict__ out, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 p = pre[i];
+    uint4 g = make_uint4(0u, 0u, 0u, 0u);
+    if (kBwd) g = dh[i];
+    const uint32_t pw[4] = {p.x, p.y, p.z, p.w};
+    const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a = bf16_lo(pw[k]), b = bf16_hi(pw[k]);
+      if (kBwd) ow[k] = pack_bf16x2(bf16_lo(gw[k]) * gelu_tanh_grad(a), bf16_hi(gw[k]) * gelu_tanh_grad(b));
+      else ow[k] = pack_bf16x2(gelu_tanh(a), gelu_tanh(b));
+    }
+    out[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- gate + residual
+// out[r, :] = x[r, :] + gate[b, :] * y[r, :]        (fp32 stream, bf16 branch output; gate NULL -> 1)
+__global__ void __launch_bounds__(256) gate_residual_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ y,
+                                                                const float* __restrict__ gate, float* __restrict__ out,
+                                                                long long gate_bs, int rows_per_batch, int M, int C) {
+  const int c4 = C >> 2;
+  const long long total = (long long)M * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(i / c4);
+    const int col = (int)(i - (long long)row * c4) * 4;
+    const size_t off = (size_t)row * C + col;
+    const float4 xv = *reinterpret_cast<const float4*>(x + off);
+    const uint2 yv = *reinterpret_cast<const uint2*>(y + off);
+    float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (gate != nullptr) g = __ldg(reinterpret_cast<const float4*>(gate + (size_t)(row / rows_per_batch) * gate_bs + col));
+    float4 o;
+    o.x = fmaf(g.x, bf16_lo(yv.x), xv.x);
+    o.y = fmaf(g.y, bf16_hi(yv.x), xv.y);
+    o.z = fmaf(g.z, bf16_lo(yv.y), xv.z);
+    o.w = fmaf(g.w, bf16_hi(yv.y), xv.w);
+    *reinterpret_cast<float4*>(out + off) = o;
+  }
+}
+
+// dy[r, :] = bf16(dout[r, :] * gate[b, :]);  dgate[b, :] += sum_{r in b} dout[r, :] * y[r, :]
+// One CTA = kRows consecutive rows x C columns; thread t owns columns 4t..4t+3 (C/4 threads).
+constexpr int kGateRows = 32;
+__global__ void __launch_bounds__(288) gate_residual_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ y,
+                                                                const float* __restrict__ gate, __nv_bfloat16* __restrict__ dy,
+                                                                float* __restrict__ dgate, long long gate_bs,
+                                                                int rows_per_batch, int M, int C) {
+  const int col = threadIdx.x * 4;
+  if (col >= C) return;
+  const int r0 = blockIdx.x * kGateRows;
+  const int r1 = min(r0 + kGateRows, M);
+  int cur_b = -1;
+  float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int row = r0; row < r1; ++row) {
+    const int b = row / rows_per_batch;
+    if (b != cur_b) {
+      if (cur_b >= 0 && dgate != nullptr) {
+        float* dg = dgate + (size_t)cur_b * C + col;
+        atomicAdd(dg + 0, acc.x); atomicAdd(dg + 1, acc.y); atomicAdd(dg + 2, acc.z); atomicAdd(dg + 3, acc.w);
+      }
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      cur_b = b;
+      if (gate != nullptr) g = __ldg(reinterpret_cast<const float4*>(gate + (size_t)b * gate_bs + col));
+    }
+    const size_t off = (size_t)row * C + col;
+    const float4 d = *reinterpret_cast<const float4*>(dout + off);
+    if (dgate != nullptr) {
+      const uint2 yv = *reinterpret_cast<const uint2*>(y + off);
+      acc.x = fmaf(d.x, bf16_lo(yv.x), acc.x);
+      acc.y = fmaf(d.y, bf16_hi(yv.x), acc.y);
+      acc.z = fmaf(d.z, bf16_lo(yv.y), acc.z);
+      acc.w = fmaf(d.w, bf16_hi(yv.y), acc.w);
+    }
+    *reinterpret_cast<uint2*>(dy + off) = make_uint2(pack_bf16x2(d.x * g.x, d.y * g.y), pack_bf16x2(d.z * g.z, d.w * g.w));
+  }
+  if (cur_b >= 0 && dgate != nullptr) {
+    float* dg = dgate + (size_t)cur_b * C + col;
+    atomicAdd(dg + 0, acc.x); atomicAdd(dg + 1, acc.y); atomicAdd(dg + 2, acc.z); atomicAdd(dg + 3, acc.w);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- LN + modulate backward
+// xn = xhat * (1 + scale[b]) + shift[b],  xhat = (x - mean) * rstd.   With g = dxn * (1 + scale[b]):
+//   dx = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat));  dshift[b] += dxn;  dscale[b] += dxn * xhat.
+// One warp walks kLnRows consecutive rows (same layout as the forward kernel: lane owns float4 groups g*32 + lane), the
+// per-sample column sums stay in registers and are flushed with atomics when the sample changes / at the end.
+constexpr int kLnRows = 16;
+template <int kVec>
+__global__ void __launch_bounds__(256) ln_modulate_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dxn,
+                                                              const float* __restrict__ scale, float* __restrict__ dx,
+                                                              float* __restrict__ dshift, float* __restrict__ dscale,
+                                                              long long mod_bs, int rows_per_batch, int M, float eps) {
+  constexpr int C = kVec * 128;
+  const int warp_global = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int r0 = warp_global * kLnRows;
+  if (r0 >= M) return;
+  const int r1 = min(r0 + kLnRows, M);
+  float4 a_sh[kVec], a_sc[kVec];
+#pragma unroll
+  for (int g = 0; g < kVec; ++g) a_sh[g] = a_sc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cur_b = -1;
+  auto flush = [&]() {
+    if (cur_b < 0) return;
+#pragma unroll
+    for (int g = 0; g < kVec; ++g) {
+      const int col = (g * 32 + lane) * 4;
+      float* ps = dshift + (size_t)cur_b * C + col;
+      float* pc = dscale + (size_t)cur_b * C + col;
+      atomicAdd(ps + 0, a_sh[g].x); atomicAdd(ps + 1, a_sh[g].y); atomicAdd(ps + 2, a_sh[g].z); atomicAdd(ps + 3, a_sh[g].w);
+      atomicAdd(pc + 0, a_sc[g].x); atomicAdd(pc + 1, a_sc[g].y); atomicAdd(pc + 2, a_sc[g].z); atomicAdd(pc + 3, a_sc[g].w);
+      a_sh[g] = a_sc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  for (int row = r0; row < r1; ++row) {
+    const int b = row / rows_per_batch;
+    if (b != cur_b) {
+      flush();
+      cur_b = b;
+    }
+    float4 v[kVec], d[kVec];
+    const float* xr = x + (size_t)row * C;
+    const __nv_bfloat16* dr = dxn + (size_t)row * C;
+#pragma unroll
+    for (int g = 0; g < kVec; ++g) {
+      const int col = (g * 32 + lane) * 4;
+      v[g] = *reinterpret_cast<const float4*>(xr + col);
+      const uint2 u = *reinterpret_cast<const uint2*>(dr + col);
+      d[g] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < kVec; ++g) s += (v[g].x + v[g].y) + (v[g].z + v[g].w);
+    const float mean = warp_sum_b(s) * (1.0f / C);
+    float ss = 0.f;
+#pragma unroll
+    for (int g = 0; g < kVec; ++g) {
+      const float a = v[g].x - mean, bq = v[g].y - mean, c = v[g].z - mean, e = v[g].w - mean;
+      ss += (a * a + bq * bq) + (c * c + e * e);
+    }
+    const float rstd = rsqrtf(warp_sum_b(ss) * (1.0f / C) + eps);
+    const float* sc = scale + (size_t)b * mod_bs;
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int g = 0; g < kVec; ++g) {
+      const int col = (g * 32 + lane) * 4;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(sc + col));
+      // v <- xhat, d <- g = dxn * (1 + scale); column sums use dxn
+      const float4 xh = make_float4((v[g].x - mean) * rstd, (v[g].y - mean) * rstd, (v[g].z - mean) * rstd, (v[g].w - mean) * rstd);
+      a_sh[g].x += d[g].x; a_sh[g].y += d[g].y; a_sh[g].z += d[g].z; a_sh[g].w += d[g].w;
+      a_sc[g].x = fmaf(d[g].x, xh.x, a_sc[g].x); a_sc[g].y = fmaf(d[g].y, xh.y, a_sc[g].y);
+      a_sc[g].z = fmaf(d[g].z, xh.z, a_sc[g].z); a_sc[g].w = fmaf(d[g].w, xh.w, a_sc[g].w);
+      const float4 gg = make_float4(d[g].x * (1.0f + a.x), d[g].y * (1.0f + a.y), d[g].z * (1.0f + a.z), d[g].w * (1.0f + a.w));
+      sg += (gg.x + gg.y) + (gg.z + gg.w);
+      sgx += (gg.x * xh.x + gg.y * xh.y) + (gg.z * xh.z + gg.w * xh.w);
+      v[g] = xh;
+      d[g] = gg;
+    }
+    const float mg = warp_sum_b(sg) * (1.0f / C);
+    const float mgx = warp_sum_b(sgx) * (1.0f / C);
+    float* orow = dx + (size_t)row * C;
+#pragma unroll
+    for (int g = 0; g < kVec; ++g) {
+      const int col = (g * 32 + lane) * 4;
+      float4 o;
+      o.x = rstd * (d[g].x - mg - v[g].x * mgx);
+      o.y = rstd * (d[g].y - mg - v[g].y * mgx);
+      o.z = rstd * (d[g].z - mg - v[g].z * mgx);
+      o.w = rstd * (d[g].w - mg - v[g].w * mgx);
+      *reinterpret_cast<float4*>(orow + col) = o;
+    }
+  }
+  flush();
+}
+
+// ------------------------------------------------------------------------------------------------- column sums
+// out[c] += sum_r a[r, c]; one thread owns 8 columns (one 16-byte load per row), blockIdx.y walks 256-row slabs.
+constexpr int kColsumRows = 256;
+__global__ void __launch_bounds__(128) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ a, float* __restrict__ out, int M,
+                                                          int N, long long lda) {
+  const int col = (blockIdx.x * 128 + threadIdx.x) * 8;
+  if (col >= N) return;
+  const int r0 = blockIdx.y * kColsumRows;
+  const int r1 = min(r0 + kColsumRows, M);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const uint4 u = *reinterpret_cast<const uint4*>(a + (size_t)r * lda + col);
+    acc[0] += bf16_lo(u.x); acc[1] += bf16_hi(u.x); acc[2] += bf16_lo(u.y); acc[3] += bf16_hi(u.y);
+    acc[4] += bf16_lo(u.z); acc[5] += bf16_hi(u.z); acc[6] += bf16_lo(u.w); acc[7] += bf16_hi(u.w);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) atomicAdd(out + col + i, acc[i]);
+}
+
+// ------------------------------------------------------------------------------------------------- attention delta
+// delta[(b*H + h)*Nq + i] = sum_d dO[b,i,h,d] * O[b,i,h,d]; one thread per (row, head): 9 x 16-byte loads from each.
+__global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                                                         float* __restrict__ delta, int B, int H, int Nq, long long ldo,
+                                                         long long lddo) {
+  const long long total = (long long)B * Nq * H;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int h = (int)(i % H);
+  const long long row = i / H;               // b*Nq + q
+  const uint4* po = reinterpret_cast<const uint4*>(o + (size_t)row * ldo + h * 72);
+  const uint4* pd = reinterpret_cast<const uint4*>(d_o + (size_t)row * lddo + h * 72);
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < 9; ++c) {
+    const uint4 a = po[c], g = pd[c];
+    s = fmaf(bf16_lo(a.x), bf16_lo(g.x), s); s = fmaf(bf16_hi(a.x), bf16_hi(g.x), s);
+    s = fmaf(bf16_lo(a.y), bf16_lo(g.y), s); s = fmaf(bf16_hi(a.y), bf16_hi(g.y), s);
+    s = fmaf(bf16_lo(a.z), bf16_lo(g.z), s); s = fmaf(bf16_hi(a.z), bf16_hi(g.z), s);
+    s = fmaf(bf16_lo(a.w), bf16_lo(g.w), s); s = fmaf(bf16_hi(a.w), bf16_hi(g.w), s);
+  }
+  const int b = (int)(row / Nq), q = (int)(row % Nq);
+  delta[((size_t)b * H + h) * Nq + q] = s;
+}
+
+static inline int grid_for(long long work_items, int threads) {
+  long long g = (work_items + threads - 1) / threads;
+  const long long cap = (long long)device_info().sms * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace pxa
+
+#define PXA_ALIGNED16(p) ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
+
+extern "C" int pxa_transpose_bf16(const void* in, void* out, int32_t R, int32_t C, int64_t ldi, int64_t ldo, void* stream) {
+  using namespace pxa;
+  if (!in || !out) return fail(PXA_ERR_ARG, "null pointer");
+  if (R <= 0 || C <= 0) return fail(PXA_ERR_ARG, "bad shape R=%d C=%d", R, C);
+  PXA_REQUIRE_SM100();
+  dim3 grid((C + 63) / 64, (R + 63) / 64);
+  const bool pairs = !((R & 1) || (C & 1) || (ldi & 1) || (ldo & 1) ||
+                       ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 3));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* pi = reinterpret_cast<const __nv_bfloat16*>(in);
+  __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(out);
+  if (pairs) transpose_bf16_kernel<true><<<grid, 256, 0, s>>>(pi, po, R, C, ldi, ldo);
+  else transpose_bf16_kernel<false><<<grid, 256, 0, s>>>(pi, po, R, C, ldi, ldo);
+  launch_counter()++;
+  PXA_CHECK_CUDA(cudaGetLastError());
+  return PXA_OK;
+}
+
+extern "C" int pxa_gelu_tanh_bf16(const void* pre, const void* dh, void* out, int64_t n, void* stream) {
+  using namespace pxa;
+  if (!pre || !out) return fail(PXA_ERR_ARG, "null pointer");
+  if (n <= 0 || (n & 7)) return fail(PXA_ERR_ARG, "n must be a positive multiple of 8 (got %lld)", (long long)n);
+  if (!PXA_ALIGNED16(pre) || !PXA_ALIGNED16(out) || !PXA_ALIGNED16(dh)) return fail(PXA_ERR_ALIGN, "pointers must be 16-byte aligned");
+  PXA_REQUIRE_SM100();
+  const long long n8 = n / 8;
+  const int grid = grid_for(n8, 256);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dh)
+    gelu_kernel<true><<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(pre), reinterpret_cast<const uint4*>(dh),
+                                           reinterpret_cast<uint4*>(out), n8);
+  else
+    gelu_kernel<false><<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(pre), nullptr, reinterpret_cast<uint4*>(out), n8);
+  launch_counter()++;
+  PXA_CHECK_CUDA(cudaGetLastError());
+  return PXA_OK;
+}
+
+extern "C" int pxa_gate_residual_fwd(const PxaGateResidualArgs* args, void* stream) {
+  using namespace pxa;
+  if (!args) return fail(PXA_ERR_ARG, "null args");
+  const PxaGateResidualArgs& a = *args;
+  if (!a.x || !a.y || !a.out) return fail(PXA_ERR_ARG, "null pointer");
+  if (a.M <= 0 || a.C <= 0 || (a.C & 3) || a.rows_per_batch <= 0) return fail(PXA_ERR_ARG, "bad M / C / rows_per_batch");
+  if (!PXA_ALIGNED16(a.x) || !PXA_ALIGNED16(a.y) || !PXA_ALIGNED16(a.out) || !PXA_ALIGNED16(a.gate) || (a.gate_batch_stride & 3))
+    return fail(PXA_ERR_ALIGN, "pointers must be 16-byte aligned, gate_batch_stride a multiple of 4");
+  PXA_REQUIRE_SM100();
+  const int grid = grid_for((long long)a.M * (a.C / 4), 256);
+  gate_residual_fwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float*>(a.x), reinterpret_cast<const __nv_bfloat16*>(a.y), a.gate, reinterpret_cast<float*>(a.out),
+      a.gate_batch_stride, a.rows_per_batch, a.M, a.C);
+  launch_counter()++;
+  PXA_CHECK_CUDA(cudaGetLastError());
+  return PXA_OK;
+}
+
+extern "C" int pxa_gate_residual_bwd(const PxaGateResidualArgs* args, void* stream) {
+  using namespace pxa;
+  if (!args) return fail(PXA_ERR_ARG, "null args");
+  const PxaGateResidualArgs& a = *args;
+  // x = dout (fp32), out = dy (bf16); y / dgate only when a gate gradient is wanted
+  if (!a.x || !a.out) return fail(PXA_ERR_ARG, "null pointer");
+  if (a.dgate && !a.y) return fail(PXA_ERR_ARG, "dgate needs y");
+  if (a.M <= 0 || a.C <= 0 || (a.C & 3) || a.C > 288 * 4 || a.rows_per_batch <= 0) return fail(PXA_ERR_ARG, "bad M / C (<= 1152) / rows_per_batch");
+  if (!PXA_ALIGNED16(a.x) || !PXA_ALIGNED16(a.y) || !PXA_ALIGNED16(a.out) || !PXA_ALIGNED16(a.gate) || !PXA_ALIGNED16(a.dgate) ||
+      (a.gate_batch_stride & 3))
+    return fail(PXA_ERR_ALIGN, "pointers must be 16-byte aligned, gate_batch_stride a multiple of 4");
+  PXA_REQUIRE_SM100();
+  const int grid = (a.M + kGateRows - 1) / kGateRows;
+  gate_residual_bwd_kernel<<<grid, 288, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float*>(a.x), reinterpret_cast<const __nv_bfloat16*>(a.y), a.gate,
+      reinterpret_cast<__nv_bfloat16*>(a.out), a.dgate, a.gate_batch_stride, a.rows_per_batch, a.M, a.C);
+  launch_counter()++;
+  PXA_CHECK_CUDA(cudaGetLastError());
+  return PXA_OK;
+}
+
+extern "C" int pxa_ln_modulate_bwd(const PxaLnModBwdArgs* args, void* stream) {
+  using namespace pxa;
+  if (!args) return fail(PXA_ERR_ARG, "null args");
+  const PxaLnModBwdArgs& a = *args;
+  if (!a.x || !a.dxn || !a.scale || !a.dx || !a.dshift || !a.dscale) return fail(PXA_ERR_ARG, "null pointer");
+  if (a.C != 1152) return fail(PXA_ERR_ARG, "pxa_ln_modulate_bwd is specialised for C=1152 (got %d)", a.C);
+  if (a.M <= 0 || a.rows_per_batch <= 0) return fail(PXA_ERR_ARG, "bad M / rows_per_batch");
+  if (a.mod_batch_stride & 3) return fail(PXA_ERR_ALIGN, "mod_batch_stride must be a multiple of 4");
+  if (!PXA_ALIGNED16(a.x) || !PXA_ALIGNED16(a.dxn) || !PXA_ALIGNED16(a.scale) || !PXA_ALIGNED16(a.dx) || !PXA_ALIGNED16(a.dshift) ||
+      !PXA_ALIGNED16(a.dscale))
+    return fail(PXA_ERR_ALIGN, "pointers must be 16-byte aligned");
+  PXA_REQUIRE_SM100();
+  const int warps = (a.M + kLnRows - 1) / kLnRows;
+  const int grid = (warps + 7) / 8;
+  ln_modulate_bwd_kernel<9><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float*>(a.x), reinterpret_cast<const __nv_bfloat16*>(a.dxn), a.scale, reinterpret_cast<float*>(a.dx),
+      a.dshift, a.dscale, a.mod_batch_stride, a.rows_per_batch, a.M, a.eps);
+  launch_counter()++;
+  PXA_CHECK_CUDA(cudaGetLastError());
+  return PXA_OK;
+}
+
+extern "C" int pxa_colsum_bf16(const void* a, float* out, int32_t M, int32_t N, int64_t lda, void* stream) {
+  using namespace pxa;
+  if (!a || !out) return fail(PXA_ERR_ARG, "null pointer");
+  if (M <= 0 || N <= 0 || (N & 7) || (lda & 7)) return fail(PXA_ERR_ARG, "M > 0, N and lda positive multiples of 8 required");
+  if (!PXA_ALIGNED16(a) || (reinterpret_cast<uintptr_t>(out) & 3)) return fail(PXA_ERR_ALIGN, "a must be 16-byte aligned");
+  PXA_REQUIRE_SM100();
+  dim3 grid((N / 8 + 127) / 128, (M + kColsumRows - 1) / kColsumRows);
+  colsum_bf16_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(a), out, M, N, lda);
+  launch_counter()++;
+  PXA_CHECK_CUDA(cudaGetLastError());
+  return PXA_OK;
+}
+
+extern "C" int pxa_attn_delta_d72(const void* o, const void* d_o, float* delta, int32_t B, int32_t H, int32_t Nq, int64_t ldo,
+                                  int64_t lddo, void* stream) {
+  using namespace pxa;
+  if (!o || !d_o || !delta) return fail(PXA_ERR_ARG, "null pointer");
+  if (B <= 0 || H <= 0 || Nq <= 0) return fail(PXA_ERR_ARG, "bad B / H / Nq");
+  if ((ldo & 7) || (lddo & 7) || !PXA_ALIGNED16(o) || !PXA_ALIGNED16(d_o)) return fail(PXA_ERR_ALIGN, "o / dO rows must be 16-byte aligned");
+  PXA_REQUIRE_SM100();
+  const long long total = (long long)B * Nq * H;
+  const int grid = (int)((total + 255) / 256);
+  attn_delta_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(o), reinterpret_cast<const __nv_bfloat16*>(d_o), delta, B, H, Nq, ldo, lddo);
+  launch_counter()++;
+  PXA_CHECK_CUDA(cudaGetLastError());
+  return PXA_OK;
+}

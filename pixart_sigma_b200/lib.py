@@ -45,7 +45,7 @@ class AttnArgs(C.Structure):
                 ("k_sn", C.c_int64), ("k_sh", C.c_int64), ("v_sn", C.c_int64), ("v_sh", C.c_int64),
                 ("kv_rows", C.c_int64),
                 ("B", C.c_int32), ("H", C.c_int32), ("Nq", C.c_int32), ("Nk", C.c_int32),
-                ("ldo", C.c_int32), ("scale", C.c_float), ("debug_trace", C.c_void_p)]
+                ("ldo", C.c_int32), ("scale", C.c_float), ("debug_trace", C.c_void_p), ("lse", C.c_void_p)]
 
 
 class KvCompressArgs(C.Structure):
@@ -67,7 +67,32 @@ class DpmStepArgs(C.Structure):
                 ("a", C.c_float), ("b", C.c_float), ("c", C.c_float)]
 
 
-EXPORTS = ("pxa_version", "pxa_last_error", "pxa_launch_count", "pxa_gemm_bf16", "pxa_ln_modulate",
+class GateResidualArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("gate", C.c_void_p), ("out", C.c_void_p), ("dgate", C.c_void_p),
+                ("gate_batch_stride", C.c_int64), ("rows_per_batch", C.c_int32), ("M", C.c_int32), ("C", C.c_int32)]
+
+
+class LnModBwdArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("dxn", C.c_void_p), ("scale", C.c_void_p), ("dx", C.c_void_p), ("dshift", C.c_void_p),
+                ("dscale", C.c_void_p), ("mod_batch_stride", C.c_int64), ("rows_per_batch", C.c_int32),
+                ("M", C.c_int32), ("C", C.c_int32), ("eps", C.c_float)]
+
+
+class AttnBwdArgs(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p), ("d_o", C.c_void_p),
+                ("lse", C.c_void_p), ("delta", C.c_void_p), ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
+                ("kv_len", C.c_void_p), ("kv_off", C.c_void_p),
+                ("q_sn", C.c_int64), ("q_sh", C.c_int64), ("k_sn", C.c_int64), ("k_sh", C.c_int64),
+                ("v_sn", C.c_int64), ("v_sh", C.c_int64),
+                ("dq_sn", C.c_int64), ("dq_sh", C.c_int64), ("dk_sn", C.c_int64), ("dk_sh", C.c_int64),
+                ("dv_sn", C.c_int64), ("dv_sh", C.c_int64),
+                ("ldo", C.c_int64), ("lddo", C.c_int64), ("kv_rows", C.c_int64),
+                ("B", C.c_int32), ("H", C.c_int32), ("Nq", C.c_int32), ("Nk", C.c_int32), ("scale", C.c_float)]
+
+
+EXPORTS = ("pxa_transpose_bf16", "pxa_gelu_tanh_bf16", "pxa_gate_residual_fwd", "pxa_gate_residual_bwd",
+           "pxa_ln_modulate_bwd", "pxa_colsum_bf16", "pxa_attn_delta_d72", "pxa_flash_attn_d72_bwd_bf16",
+           "pxa_version", "pxa_last_error", "pxa_launch_count", "pxa_gemm_bf16", "pxa_ln_modulate",
            "pxa_flash_attn_d72_bf16", "pxa_kv_compress_conv2_ln", "pxa_conv3x3_nhwc_bf16", "pxa_dpm_solver_pp_step")
 
 _lib = None
@@ -89,6 +114,20 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(struct), C.c_void_p]
+        for name, struct in (("pxa_gate_residual_fwd", GateResidualArgs), ("pxa_gate_residual_bwd", GateResidualArgs),
+                             ("pxa_ln_modulate_bwd", LnModBwdArgs), ("pxa_flash_attn_d72_bwd_bf16", AttnBwdArgs)):
+            fn = getattr(lib, name)
+            fn.restype = C.c_int
+            fn.argtypes = [C.POINTER(struct), C.c_void_p]
+        lib.pxa_transpose_bf16.restype = C.c_int
+        lib.pxa_transpose_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p]
+        lib.pxa_gelu_tanh_bf16.restype = C.c_int
+        lib.pxa_gelu_tanh_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        lib.pxa_colsum_bf16.restype = C.c_int
+        lib.pxa_colsum_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]
+        lib.pxa_attn_delta_d72.restype = C.c_int
+        lib.pxa_attn_delta_d72.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
+                                           C.c_int64, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -160,7 +199,7 @@ def ln_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, out: 
 def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, B: int, H: int, Nq: int,
                Nk: int, kv_rows: int, kv_len: Optional[torch.Tensor] = None, kv_off: Optional[torch.Tensor] = None,
                q_strides=None, k_strides=None, v_strides=None, scale: Optional[float] = None,
-               debug_trace: Optional[torch.Tensor] = None) -> torch.Tensor:
+               debug_trace: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Head-dim-72 attention. q/k/v are bf16 *views*; strides are (row, head) in elements, e.g. slices of the
     (rows, 3, H, 72) qkv GEMM output. out is (B*Nq, H*72) bf16."""
     assert q.dtype == k.dtype == v.dtype == out.dtype == torch.bfloat16
@@ -171,7 +210,9 @@ def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Ten
                     q_sn=q_strides[0], q_sh=q_strides[1], k_sn=k_strides[0], k_sh=k_strides[1],
                     v_sn=v_strides[0], v_sh=v_strides[1], kv_rows=kv_rows, B=B, H=H, Nq=Nq, Nk=Nk,
                     ldo=out.stride(0), scale=scale if scale is not None else 72 ** -0.5,
-                    debug_trace=_ptr(debug_trace))
+                    debug_trace=_ptr(debug_trace), lse=_ptr(lse))
+    if lse is not None:
+        assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == B * H * Nq
     _check(load().pxa_flash_attn_d72_bf16(C.byref(args), _stream()), "pxa_flash_attn_d72_bf16")
     return out
 
@@ -213,3 +254,92 @@ def dpm_solver_pp_step(model_out: torch.Tensor, x: torch.Tensor, x0_prev: torch.
                        inv_alpha_s=1.0 / alpha_s, a=a, b=b, c=c)
     _check(load().pxa_dpm_solver_pp_step(C.byref(args), _stream()), "pxa_dpm_solver_pp_step")
     return x
+
+
+# ------------------------------------------------------------------------------------------------- training backward
+def transpose(a: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out (C, R) = a (R, C)^T, bf16; a may be a row-strided view (e.g. a column slice)."""
+    assert a.dtype == torch.bfloat16 and a.dim() == 2 and a.stride(1) == 1
+    R, Cc = a.shape
+    if out is None:
+        out = torch.empty((Cc, R), dtype=torch.bfloat16, device=a.device)
+    assert out.shape == (Cc, R) and out.stride(1) == 1
+    _check(load().pxa_transpose_bf16(_ptr(a), _ptr(out), R, Cc, a.stride(0), out.stride(0), _stream()), "pxa_transpose_bf16")
+    return out
+
+
+def gelu_tanh(pre: torch.Tensor, out: Optional[torch.Tensor] = None, dh: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dh None: out = gelu_tanh(pre); else out = dh * gelu_tanh'(pre). Contiguous bf16 tensors."""
+    assert pre.dtype == torch.bfloat16 and pre.is_contiguous()
+    if out is None:
+        out = torch.empty_like(pre)
+    assert out.is_contiguous() and out.dtype == torch.bfloat16 and (dh is None or (dh.is_contiguous() and dh.dtype == torch.bfloat16))
+    _check(load().pxa_gelu_tanh_bf16(_ptr(pre), _ptr(dh), _ptr(out), pre.numel(), _stream()), "pxa_gelu_tanh_bf16")
+    return out
+
+
+def gate_residual_fwd(x: torch.Tensor, y: torch.Tensor, gate: Optional[torch.Tensor], out: torch.Tensor, *,
+                      gate_batch_stride: int = 0, rows_per_batch: int = 0) -> torch.Tensor:
+    """out = x + gate[b] * y on the fp32 residual stream (x, out fp32 (M, C); y bf16; gate fp32 view or None)."""
+    assert x.dtype == out.dtype == torch.float32 and y.dtype == torch.bfloat16
+    assert x.is_contiguous() and y.is_contiguous() and out.is_contiguous() and x.shape == y.shape == out.shape
+    M, Cc = x.shape
+    args = GateResidualArgs(x=_ptr(x), y=_ptr(y), gate=_ptr(gate), out=_ptr(out), dgate=None,
+                            gate_batch_stride=gate_batch_stride, rows_per_batch=rows_per_batch or M, M=M, C=Cc)
+    _check(load().pxa_gate_residual_fwd(C.byref(args), _stream()), "pxa_gate_residual_fwd")
+    return out
+
+
+def gate_residual_bwd(dout: torch.Tensor, y: Optional[torch.Tensor], gate: Optional[torch.Tensor], dy: torch.Tensor,
+                      dgate: Optional[torch.Tensor], *, gate_batch_stride: int = 0, rows_per_batch: int = 0) -> torch.Tensor:
+    """dy = bf16(dout * gate[b]); dgate[b] += sum_rows dout * y (dgate fp32 (B, C) contiguous, pre-zeroed by the caller)."""
+    assert dout.dtype == torch.float32 and dout.is_contiguous() and dy.dtype == torch.bfloat16 and dy.is_contiguous()
+    assert dgate is None or (dgate.dtype == torch.float32 and dgate.is_contiguous() and y is not None and y.is_contiguous())
+    M, Cc = dout.shape
+    args = GateResidualArgs(x=_ptr(dout), y=_ptr(y), gate=_ptr(gate), out=_ptr(dy), dgate=_ptr(dgate),
+                            gate_batch_stride=gate_batch_stride, rows_per_batch=rows_per_batch or M, M=M, C=Cc)
+    _check(load().pxa_gate_residual_bwd(C.byref(args), _stream()), "pxa_gate_residual_bwd")
+    return dy
+
+
+def ln_modulate_bwd(x: torch.Tensor, dxn: torch.Tensor, scale: torch.Tensor, dx: torch.Tensor, dshift: torch.Tensor,
+                    dscale: torch.Tensor, *, mod_batch_stride: int, rows_per_batch: int, eps: float = 1e-6) -> None:
+    """Backward of ln_modulate: dx written, dshift / dscale (B, C) fp32 accumulated."""
+    assert x.dtype == dx.dtype == torch.float32 and dxn.dtype == torch.bfloat16
+    assert x.is_contiguous() and dxn.is_contiguous() and dx.is_contiguous() and dshift.is_contiguous() and dscale.is_contiguous()
+    assert dshift.dtype == dscale.dtype == scale.dtype == torch.float32
+    M, Cc = x.shape
+    args = LnModBwdArgs(x=_ptr(x), dxn=_ptr(dxn), scale=_ptr(scale), dx=_ptr(dx), dshift=_ptr(dshift), dscale=_ptr(dscale),
+                        mod_batch_stride=mod_batch_stride, rows_per_batch=rows_per_batch, M=M, C=Cc, eps=eps)
+    _check(load().pxa_ln_modulate_bwd(C.byref(args), _stream()), "pxa_ln_modulate_bwd")
+
+
+def colsum(a: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[c] += sum_r a[r, c]; a bf16 (M, N) row-strided view, out fp32 (N,)."""
+    assert a.dtype == torch.bfloat16 and a.dim() == 2 and a.stride(1) == 1 and out.dtype == torch.float32 and out.is_contiguous()
+    M, N = a.shape
+    assert out.numel() == N
+    _check(load().pxa_colsum_bf16(_ptr(a), _ptr(out), M, N, a.stride(0), _stream()), "pxa_colsum_bf16")
+    return out
+
+
+def flash_attn_bwd(q, k, v, o, d_o, lse, dq, dk, dv, *, B: int, H: int, Nq: int, Nk: int, kv_rows: int,
+                   kv_len: Optional[torch.Tensor] = None, kv_off: Optional[torch.Tensor] = None, q_strides, k_strides,
+                   v_strides, dq_strides, dk_strides, dv_strides, scale: Optional[float] = None,
+                   delta: Optional[torch.Tensor] = None) -> None:
+    """Backward of flash_attn. q/k/v/dq/dk/dv bf16 views with (row, head) strides; o, d_o (B*Nq, H*72) bf16 row-strided;
+    lse (B, H, Nq) fp32 from the forward."""
+    for t in (q, k, v, o, d_o, dq, dk, dv):
+        assert t.dtype == torch.bfloat16 and t.is_cuda
+    assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == B * H * Nq
+    assert o.stride(1) == 1 and d_o.stride(1) == 1
+    if delta is None:
+        delta = torch.empty(B * H * Nq, dtype=torch.float32, device=q.device)
+    args = AttnBwdArgs(q=_ptr(q), k=_ptr(k), v=_ptr(v), o=_ptr(o), d_o=_ptr(d_o), lse=_ptr(lse), delta=_ptr(delta),
+                       dq=_ptr(dq), dk=_ptr(dk), dv=_ptr(dv), kv_len=_ptr(kv_len), kv_off=_ptr(kv_off),
+                       q_sn=q_strides[0], q_sh=q_strides[1], k_sn=k_strides[0], k_sh=k_strides[1],
+                       v_sn=v_strides[0], v_sh=v_strides[1], dq_sn=dq_strides[0], dq_sh=dq_strides[1],
+                       dk_sn=dk_strides[0], dk_sh=dk_strides[1], dv_sn=dv_strides[0], dv_sh=dv_strides[1],
+                       ldo=o.stride(0), lddo=d_o.stride(0), kv_rows=kv_rows, B=B, H=H, Nq=Nq, Nk=Nk,
+                       scale=scale if scale is not None else 72 ** -0.5)
+    _check(load().pxa_flash_attn_d72_bwd_bf16(C.byref(args), _stream()), "pxa_flash_attn_d72_bwd_bf16")

@@ -206,6 +206,14 @@ class _Workspace:
         return t
 
 
+def _wants_grad(module: nn.Module, *inputs) -> bool:
+    """True when autograd will record this call: grad mode on and a parameter or an input requires grad."""
+    if not torch.is_grad_enabled():
+        return False
+    return any(p.requires_grad for p in module.parameters()) or any(
+        isinstance(t, torch.Tensor) and t.requires_grad for t in inputs)
+
+
 def _require_kernel_ready(p: torch.Tensor, what: str) -> None:
     if not p.is_cuda:
         raise RuntimeError(f"{what}: parameters are on {p.device}; pixart_sigma_b200 has no CPU path "
@@ -321,9 +329,6 @@ class PixArtMSBlock(nn.Module):
     # -- reference call signature -------------------------------------------------------------------------------
     def forward(self, x, y, t, mask=None, HW=None, **kwargs):
         """x (B,N,C), y (1, sum(y_lens), C) packed caption tokens, t (B, 6C), mask = list y_lens (PixArtMS.py:71,206)."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("PixArtMSBlock: the backward kernels are not implemented yet; run under "
-                                      "torch.no_grad() (inference)")
         B, N, C = x.shape
         if HW is None:
             HW = (int(N ** 0.5),) * 2
@@ -336,7 +341,11 @@ class PixArtMSBlock(nn.Module):
         kv_off = torch.tensor([sum(lens[:i]) for i in range(B)], dtype=torch.int32, device=x.device)
         mod = (self.scale_shift_table.float()[None] + t.reshape(B, 6, C).float()).contiguous()
         x32 = x.reshape(B * N, C).float().contiguous()
-        out = self.run_kernels(x32, cond, kv_len, kv_off, max(max(lens), 1), mod, B, N, tuple(HW), self._ws)
+        if _wants_grad(self, x, y, t):                                     # training: differentiable kernel ops
+            from .autograd import block_forward_train
+            out = block_forward_train(self, x32, cond, kv_len, kv_off, max(max(lens), 1), mod, B, N)
+        else:
+            out = self.run_kernels(x32, cond, kv_len, kv_off, max(max(lens), 1), mod, B, N, tuple(HW), self._ws)
         return out.view(B, N, C).to(x.dtype)
 
 
@@ -439,9 +448,9 @@ class PixArtMS(nn.Module):
         """x (B, 4, H, W) latents, timestep (B,), y (B, 1, L, 4096) T5 features, mask (n, L) | (B,1,1,L) | None
         -> (B, 8, H, W)   (PixArtMS.py:165-211)."""
         w0 = self.blocks[0].attn.qkv.weight
+        if _wants_grad(self, x, y):
+            return self._forward_train(x, timestep, y, mask=mask, data_info=data_info)
         _require_kernel_ready(w0, "PixArtMS.forward")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("PixArtMS: backward kernels are not implemented yet; call under torch.no_grad()")
         dt, dev, C, p = self.dtype, w0.device, self.hidden_size, self.patch_size
         B = x.shape[0]
         x = x.to(device=dev, dtype=dt)
@@ -474,6 +483,64 @@ class PixArtMS(nn.Module):
         fmod = (fl.scale_shift_table.float()[None] + t[:, None]).contiguous()                  # (B, 2, C): shift, scale
         xn = self._ws.get("xn", (B * N, C), torch.bfloat16, dev)
         lib.ln_modulate(x32, fmod[:, 0], fmod[:, 1], xn, mod_batch_stride=fmod.stride(0), rows_per_batch=N)
+        out = F.linear(xn.float(), fl.linear.weight.float(), fl.linear.bias.float()).view(B, N, -1)
+        return self.unpatchify(out).to(self.output_dtype or dt)
+
+    def _forward_train(self, x, timestep, y, mask=None, data_info=None):
+        """The same forward recorded for autograd (train_scripts/train.py:189-197): every block op is a
+        `torch.autograd.Function` over the sm_100a kernels (autograd.py), blocks marked by `set_grad_checkpoint`
+        (diffusion/model/utils.py:28-45) are activation-checkpointed like PixArtMS.py:206.  Parameters may be fp32
+        (mixed precision: the kernels read cached bf16 shadows) or bf16."""
+        from torch.utils.checkpoint import checkpoint
+        from . import autograd as ag
+        w0 = self.blocks[0].attn.qkv.weight
+        if not w0.is_cuda:
+            raise RuntimeError(f"PixArtMS: parameters are on {w0.device}; pixart_sigma_b200 has no CPU path")
+        dt, dev, C, p = self.dtype, w0.device, self.hidden_size, self.patch_size
+        B = x.shape[0]
+        x = x.to(device=dev)
+        timestep = timestep.to(device=dev, dtype=dt if self.round_timestep_to_dtype else torch.float32)
+        y = y.to(device=dev)
+        self.h, self.w = x.shape[-2] // p, x.shape[-1] // p
+        N = self.h * self.w
+        pe = self.x_embedder.proj
+        tok = F.conv2d(x.float(), pe.weight.float(), pe.bias.float(), stride=p).flatten(2).transpose(1, 2)
+        x32 = (tok + _pos_embed_fp32(C, self.h, self.w, self.pe_interpolation, self.base_size, dev)[None])
+        x32 = x32.reshape(B * N, C).contiguous()
+        t = self.t_embedder.embed_fp32(timestep)
+        if self.micro_conditioning:
+            csize = self.csize_embedder.embed_fp32(data_info["img_hw"].to(dev, dt), B)
+            ar = self.ar_embedder.embed_fp32(data_info["aspect_ratio"].to(dev, dt), B)
+            t = t + torch.cat([csize, ar], dim=1)
+        t0 = F.linear(F.silu(t), self.t_block[1].weight.float(), self.t_block[1].bias.float())
+        t0 = t0.view(B, 6, C)
+
+        ye = self.y_embedder                                                # caption projector (PixArt_blocks.py:400-407)
+        L = y.shape[2]
+        if self.training and ye.uncond_prob > 0:
+            y = ye.token_drop(y)
+        rows = y.reshape(B * L, -1).to(torch.bfloat16)
+        cond = ag.linear(ag.GeluFn.apply(ag.linear(rows, ye.y_proj.fc1)), ye.y_proj.fc2)
+        kv_len = None
+        if mask is not None:
+            mask = mask.to(device=dev)
+            if mask.shape[0] != B:
+                mask = mask.repeat(B // mask.shape[0], *([1] * (mask.dim() - 1)))
+            valid = mask.reshape(B, L) != 0
+            order = torch.argsort((~valid).to(torch.uint8), dim=1, stable=True)
+            cond = torch.gather(cond.view(B, L, C), 1, order[..., None].expand(B, L, C)).reshape(B * L, C)
+            kv_len = valid.sum(dim=1).to(torch.int32)
+
+        for blk in self.blocks:
+            mod = blk.scale_shift_table.float()[None] + t0
+            if getattr(blk, "grad_checkpointing", False):
+                x32 = checkpoint(ag.block_forward_train, blk, x32, cond, kv_len, None, L, mod, B, N, use_reentrant=False)
+            else:
+                x32 = ag.block_forward_train(blk, x32, cond, kv_len, None, L, mod, B, N)
+
+        fl = self.final_layer
+        fmod = (fl.scale_shift_table.float()[None] + t[:, None]).contiguous()
+        xn = ag.LnModulateFn.apply(x32, fmod, 0, 1, N)
         out = F.linear(xn.float(), fl.linear.weight.float(), fl.linear.bias.float()).view(B, N, -1)
         return self.unpatchify(out).to(self.output_dtype or dt)
 

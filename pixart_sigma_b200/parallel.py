@@ -1,4 +1,5 @@
-"""Multi-GPU host logic: batch-sharded inference (independent replicas).
+"""Multi-GPU host logic: batch-sharded inference (independent replicas) and the data-parallel
+gradient all-reduce of training (`GradBucketReducer`).
 
 Images are independent, so rank r denoises images [lo, hi) with its own full weight replica and the whole sampling
 loop runs with NO collective; the only communication is an optional gather of the final latents.  CFG pairs stay on
@@ -49,3 +50,78 @@ def gather_batch(local: torch.Tensor, n_items: int, group=None) -> torch.Tensor:
 def rank_seed(base_seed: int, image_index: int) -> int:
     """Per-image noise seed that does not depend on how images are sharded, so an N-GPU run reproduces the 1-GPU run."""
     return (base_seed * 1_000_003 + image_index) % (2 ** 31 - 1)
+
+
+# ------------------------------------------------------------------------------------------------- training: DDP all-reduce
+class GradBucketReducer:
+    """Bucketed, backward-overlapped gradient all-reduce (mean over ranks) -- what accelerate -> torch DDP does for the
+    reference (`train_scripts/train.py:180,486`), laid out for this model: ONE bucket per PixArtMSBlock (21.3 M
+    parameters, 85 MB fp32) plus one for everything else, each a flat fp32 buffer that the parameters' `.grad` are views
+    of.  Blocks finish their backward in reverse order, so bucket i's all-reduce (NCCL over NVLink / NVSwitch, issued
+    asynchronously the moment its last gradient has been accumulated) runs behind the backward of blocks i-1 .. 0;
+    `finish()` waits for the stragglers.  No copy in or out of the buckets, no per-parameter collectives.
+
+    The collective is the only data-path exchange of the training step: nothing else is sharded.
+    """
+
+    def __init__(self, model: torch.nn.Module, group=None, bucket_of=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        params = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        if bucket_of is None:
+            def bucket_of(name: str) -> str:
+                parts = name.split(".")
+                return ".".join(parts[:2]) if parts[0] == "blocks" and len(parts) > 2 else "rest"
+        groups = {}
+        for n, p in params:
+            groups.setdefault(bucket_of(n), []).append(p)
+        self.buckets = []
+        for key, ps in groups.items():
+            total = sum(p.numel() for p in ps)
+            flat = torch.zeros(total, dtype=ps[0].dtype, device=ps[0].device)
+            off = 0
+            for p in ps:
+                assert p.dtype == flat.dtype and p.device == flat.device, "one dtype / device per bucket"
+                p.grad = flat[off: off + p.numel()].view_as(p)            # gradient accumulates straight into the bucket
+                off += p.numel()
+            self.buckets.append({"key": key, "flat": flat, "params": ps, "pending": 0, "work": None})
+        self._hooks = []
+        for b in self.buckets:
+            for p in b["params"]:
+                self._hooks.append(p.register_post_accumulate_grad_hook(lambda _p, b=b: self._ready(b)))
+        self.start()
+
+    def start(self) -> None:
+        """Arm the buckets for one backward pass (gradients are NOT zeroed: call `zero_grad()` between optimizer steps)."""
+        for b in self.buckets:
+            b["pending"], b["work"] = len(b["params"]), None
+
+    def zero_grad(self) -> None:
+        for b in self.buckets:
+            b["flat"].zero_()
+
+    def _ready(self, b) -> None:
+        b["pending"] -= 1
+        if b["pending"] == 0 and self.world > 1:
+            b["flat"].div_(self.world)
+            b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def finish(self) -> None:
+        """Block until every bucket has been reduced; buckets whose parameters got no gradient this step (unused
+        parameters) are reduced here so that all ranks issue the same collectives."""
+        if self.world == 1:
+            return
+        for b in self.buckets:
+            if b["work"] is None:
+                b["flat"].div_(self.world)
+                b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        for b in self.buckets:
+            b["work"].wait()
+
+    def grad_bytes(self) -> int:
+        return sum(b["flat"].numel() * b["flat"].element_size() for b in self.buckets)
+
+    def remove(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

@@ -1,0 +1,202 @@
+"""GPU parity tests (-m gpu) of the training-backward kernels through the C-ABI, each against torch autograd of the
+fp32 op on the same bf16-rounded inputs (the attention oracle is oracle.pixart_oracle's softmax(QK^T)V restatement).
+
+Tolerances (normwise ||a-b||/||b||): bf16 outputs 4e-3 (attention gradients 1e-2: P and dS are rounded to bf16 before
+the gradient MMAs, as in every flash-attention backward), fp32 outputs / atomically reduced sums 1e-3 or better.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import pixart_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from pixart_sigma_b200 import lib
+DEV = "cuda"
+
+
+def _randn(*shape, seed=0, scale=1.0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+@pytest.mark.parametrize("R,C", [(64, 64), (300, 1152), (4096, 3456), (1152, 4608), (130, 72), (377, 1152), (65, 33)])
+def test_transpose(R, C):
+    a = _randn(R, C, seed=1)
+    out = lib.transpose(a)
+    assert torch.equal(out, a.t().contiguous())
+
+
+def test_transpose_of_a_column_slice():
+    a = _randn(512, 3456, seed=2)
+    out = lib.transpose(a[:, 1152:2304])
+    assert torch.equal(out, a[:, 1152:2304].t().contiguous())
+
+
+def test_gelu_forward_and_backward():
+    pre = _randn(1024, 4608, seed=3, scale=1.5)
+    dh = _randn(1024, 4608, seed=4)
+    h = lib.gelu_tanh(pre)
+    x = pre.float().requires_grad_(True)
+    want = F.gelu(x, approximate="tanh")
+    assert po.rel_err(h.float(), want.detach()) < 4e-3
+    want.backward(dh.float())
+    dpre = lib.gelu_tanh(pre, dh=dh)
+    assert po.rel_err(dpre.float(), x.grad) < 4e-3
+
+
+@pytest.mark.parametrize("gated", [True, False])
+def test_gate_residual_forward_and_backward(gated):
+    B, N, C = 3, 160, 1152
+    M = B * N
+    x = _randn(M, C, seed=5, dtype=torch.float32)
+    y = _randn(M, C, seed=6)
+    mod = _randn(B, 6, C, seed=7, dtype=torch.float32)
+    gate = mod[:, 2] if gated else None
+    out = torch.empty_like(x)
+    lib.gate_residual_fwd(x, y, gate, out, gate_batch_stride=mod.stride(0), rows_per_batch=N)
+    g = (gate if gated else torch.ones(B, C, device=DEV)).detach().clone().requires_grad_(True)
+    yf = y.float().requires_grad_(True)
+    want = x.view(B, N, C) + g[:, None] * yf.view(B, N, C)
+    assert po.rel_err(out, want.detach().view(M, C)) < 1e-6
+    dout = _randn(M, C, seed=8, dtype=torch.float32)
+    want.backward(dout.view(B, N, C))
+    dy = torch.empty(M, C, dtype=torch.bfloat16, device=DEV)
+    dgate = torch.zeros(B, C, dtype=torch.float32, device=DEV) if gated else None
+    lib.gate_residual_bwd(dout, y if gated else None, gate, dy, dgate, gate_batch_stride=mod.stride(0), rows_per_batch=N)
+    assert po.rel_err(dy.float(), yf.grad) < 4e-3
+    if gated:
+        assert po.rel_err(dgate, g.grad) < 1e-4
+
+
+@pytest.mark.parametrize("B,N", [(2, 256), (3, 50), (1, 1024)])
+def test_ln_modulate_backward(B, N):
+    C, M = 1152, B * N
+    x = _randn(M, C, seed=9, dtype=torch.float32) * 2 + 0.3
+    mod = _randn(B, 6, C, seed=10, dtype=torch.float32, scale=0.5)
+    dxn = _randn(M, C, seed=11)
+    xr = x.clone().requires_grad_(True)
+    sh = mod[:, 0].clone().requires_grad_(True)
+    sc = mod[:, 1].clone().requires_grad_(True)
+    xn = F.layer_norm(xr.view(B, N, C), (C,), eps=1e-6) * (1 + sc[:, None]) + sh[:, None]
+    xn.backward(dxn.float().view(B, N, C))
+    dx = torch.empty_like(x)
+    dshift = torch.zeros(B, C, dtype=torch.float32, device=DEV)
+    dscale = torch.zeros(B, C, dtype=torch.float32, device=DEV)
+    lib.ln_modulate_bwd(x, dxn, mod[:, 1], dx, dshift, dscale, mod_batch_stride=mod.stride(0), rows_per_batch=N)
+    assert po.rel_err(dx, xr.grad) < 1e-4
+    assert po.rel_err(dshift, sh.grad) < 1e-4
+    assert po.rel_err(dscale, sc.grad) < 1e-4
+
+
+def test_colsum_accumulates():
+    a = _randn(1000, 3456, seed=12)
+    out = torch.ones(1152, dtype=torch.float32, device=DEV)
+    lib.colsum(a[:, 1152:2304], out)
+    assert po.rel_err(out, 1 + a[:, 1152:2304].float().sum(0)) < 1e-5
+
+
+def test_linear_backward_on_the_forward_gemm():
+    """dX = dY W (gemm on W^T) and dW += dY^T X (gemm on the transposes, fp32 reduce-add epilogue into the gradient)."""
+    M, N, K = 2048, 1152, 4608
+    x, w = _randn(M, K, seed=13), _randn(N, K, seed=14, scale=K ** -0.5)
+    dy = _randn(M, N, seed=15)
+    dx = torch.empty(M, K, dtype=torch.bfloat16, device=DEV)
+    lib.gemm(dy, lib.transpose(w), None, dx)
+    assert po.rel_err(dx.float(), dy.float() @ w.float()) < 4e-3
+    dw = torch.full((N, K), 0.5, dtype=torch.float32, device=DEV)
+    lib.gemm(lib.transpose(dy), lib.transpose(x), None, dw, epilogue=lib.EPI_BIAS_RESIDUAL, residual=dw)
+    assert po.rel_err(dw - 0.5, dy.float().t() @ x.float()) < 2e-4
+
+
+def _attn_ref(q, k, v, lens, scale):
+    """fp32 autograd reference: q (B,Nq,H,D), k/v (B,Nk,H,D) padded, sample b sees keys < lens[b]."""
+    outs = []
+    for b in range(q.shape[0]):
+        L = lens[b]
+        s = torch.einsum("qhd,khd->hqk", q[b], k[b, :L]) * scale
+        outs.append(torch.einsum("hqk,khd->qhd", s.softmax(-1), v[b, :L]))
+    return torch.stack(outs)
+
+
+@pytest.mark.parametrize("B,H,Nq,Nk,lens", [
+    (1, 2, 128, 128, None), (2, 3, 256, 256, None), (1, 16, 1024, 1024, None), (2, 2, 256, 64, None),
+    (2, 2, 128, 300, [300, 77]), (3, 4, 256, 300, [5, 130, 256]),
+])
+def test_flash_attn_backward(B, H, Nq, Nk, lens):
+    D, C = 72, H * 72
+    scale = D ** -0.5
+    q, k, v = _randn(B * Nq, H, D, seed=20), _randn(B * Nk, H, D, seed=21), _randn(B * Nk, H, D, seed=22)
+    d_o = _randn(B * Nq, C, seed=23)
+    kv_len = None if lens is None else torch.tensor(lens, dtype=torch.int32, device=DEV)
+    o = torch.empty(B * Nq, C, dtype=torch.bfloat16, device=DEV)
+    lse = torch.empty(B, H, Nq, dtype=torch.float32, device=DEV)
+    strides = (C, D)
+    lib.flash_attn(q, k, v, o, B=B, H=H, Nq=Nq, Nk=Nk, kv_rows=B * Nk, kv_len=kv_len, q_strides=strides, k_strides=strides,
+                   v_strides=strides, scale=scale, lse=lse)
+    qf, kf, vf = (t.float().view(B, -1, H, D).requires_grad_(True) for t in (q, k, v))
+    ll = lens or [Nk] * B
+    want = _attn_ref(qf, kf, vf, ll, scale)
+    assert po.rel_err(o.float().view(B, Nq, H, D), want.detach()) < 6e-3
+    # lse: natural-log logsumexp of the scaled scores, times log2(e)
+    s = torch.einsum("bqhd,bkhd->bhqk", qf.detach(), kf.detach()) * scale
+    for b in range(B):
+        want_lse = torch.logsumexp(s[b, :, :, :ll[b]], dim=-1) * 1.4426950408889634
+        assert (lse[b] - want_lse).abs().max() < 2e-2
+    want.backward(d_o.float().view(B, Nq, H, D))
+    dq, dk, dv = (torch.full_like(t, float("nan")) for t in (q, k, v))
+    lib.flash_attn_bwd(q, k, v, o, d_o, lse, dq, dk, dv, B=B, H=H, Nq=Nq, Nk=Nk, kv_rows=B * Nk, kv_len=kv_len,
+                       q_strides=strides, k_strides=strides, v_strides=strides, dq_strides=strides, dk_strides=strides,
+                       dv_strides=strides, scale=scale)
+    assert po.rel_err(dq.float().view(B, Nq, H, D), qf.grad) < 1e-2
+    for b in range(B):      # rows of keys >= kv_len[b] are not written
+        L = ll[b]
+        assert po.rel_err(dk.float().view(B, Nk, H, D)[b, :L], kf.grad[b, :L]) < 1e-2
+        assert po.rel_err(dv.float().view(B, Nk, H, D)[b, :L], vf.grad[b, :L]) < 1e-2
+
+
+def test_flash_attn_backward_interleaved_qkv_and_packed_cross_keys():
+    """The layouts the block uses: q/k/v and dq/dk/dv are slices of (rows, 3, H, 72) buffers; cross-attention keys are
+    packed (kv_off) rows of a (sum L, 2, H, 72) buffer."""
+    B, H, N, D = 2, 16, 256, 72
+    C = H * D
+    scale = D ** -0.5
+    qkv = _randn(B * N, 3, H, D, seed=30)
+    d_o = _randn(B * N, C, seed=31)
+    o = torch.empty(B * N, C, dtype=torch.bfloat16, device=DEV)
+    lse = torch.empty(B, H, N, dtype=torch.float32, device=DEV)
+    st = (3 * C, D)
+    lib.flash_attn(qkv[:, 0], qkv[:, 1], qkv[:, 2], o, B=B, H=H, Nq=N, Nk=N, kv_rows=B * N, q_strides=st, k_strides=st,
+                   v_strides=st, scale=scale, lse=lse)
+    dqkv = torch.empty_like(qkv)
+    lib.flash_attn_bwd(qkv[:, 0], qkv[:, 1], qkv[:, 2], o, d_o, lse, dqkv[:, 0], dqkv[:, 1], dqkv[:, 2], B=B, H=H, Nq=N,
+                       Nk=N, kv_rows=B * N, q_strides=st, k_strides=st, v_strides=st, dq_strides=st, dk_strides=st,
+                       dv_strides=st, scale=scale)
+    f = qkv.float().view(B, N, 3, H, D).requires_grad_(True)
+    want = _attn_ref(f[:, :, 0], f[:, :, 1], f[:, :, 2], [N] * B, scale)
+    want.backward(d_o.float().view(B, N, H, D))
+    assert po.rel_err(dqkv.float().view(B, N, 3, H, D), f.grad) < 1e-2
+
+    lens = [77, 300]
+    kv = _randn(sum(lens), 2, H, D, seed=32)
+    q = _randn(B * N, C, seed=33)
+    kv_len = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    kv_off = torch.tensor([0, 77], dtype=torch.int32, device=DEV)
+    lib.flash_attn(q, kv[:, 0], kv[:, 1], o, B=B, H=H, Nq=N, Nk=300, kv_rows=sum(lens), kv_len=kv_len, kv_off=kv_off,
+                   q_strides=(C, D), k_strides=(2 * C, D), v_strides=(2 * C, D), scale=scale, lse=lse)
+    dq = torch.empty_like(q)
+    dkv = torch.empty_like(kv)
+    lib.flash_attn_bwd(q, kv[:, 0], kv[:, 1], o, d_o, lse, dq, dkv[:, 0], dkv[:, 1], B=B, H=H, Nq=N, Nk=300,
+                       kv_rows=sum(lens), kv_len=kv_len, kv_off=kv_off, q_strides=(C, D), k_strides=(2 * C, D),
+                       v_strides=(2 * C, D), dq_strides=(C, D), dk_strides=(2 * C, D), dv_strides=(2 * C, D), scale=scale)
+    qf = q.float().view(B, N, H, D).requires_grad_(True)
+    kvf = kv.float().requires_grad_(True)
+    outs = []
+    for b, (off, L) in enumerate(zip([0, 77], lens)):
+        s = torch.einsum("qhd,khd->hqk", qf[b], kvf[off:off + L, 0]) * scale
+        outs.append(torch.einsum("hqk,khd->qhd", s.softmax(-1), kvf[off:off + L, 1]))
+    torch.stack(outs).backward(d_o.float().view(B, N, H, D))
+    assert po.rel_err(dq.float().view(B, N, H, D), qf.grad) < 1e-2
+    assert po.rel_err(dkv.float(), kvf.grad) < 1e-2

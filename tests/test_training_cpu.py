@@ -1,0 +1,128 @@
+"""CPU tests (-m "not gpu") of the training host logic:
+  * `IDDPMLoss` against the loss terms of the unmodified reference (tests/golden/train_loss_only.pt);
+  * the oracle's autograd (oracle.forward_grad + the loss) against the reference's gradients (train_d2_b2.pt) -- this is
+    what pins the gradient oracle the GPU tests compare the backward kernels with;
+  * `GradBucketReducer`: world-size-2 gloo run reproduces the single-process gradient of the concatenated batch.
+"""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import pixart_oracle as po
+from oracle.gen_golden_train import fingerprint_positions, train_inputs
+from pixart_sigma_b200.parallel import GradBucketReducer
+from pixart_sigma_b200.training import IDDPMLoss
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_iddpm_loss_matches_reference_terms(golden_dir):
+    fix = torch.load(os.path.join(golden_dir, "train_loss_only.pt"))
+    loss = IDDPMLoss()
+    assert torch.allclose(loss.q_sample(fix["x0"], fix["t"], fix["noise"]), fix["x_t"], rtol=1e-6, atol=1e-6)
+    terms = loss.training_losses(lambda x, timestep, **kw: fix["fake"], fix["x0"], fix["t"], {}, noise=fix["noise"])
+    for k in ("mse", "vb", "loss"):
+        assert torch.allclose(terms[k], fix["terms"][k], rtol=1e-5, atol=1e-6), (k, terms[k], fix["terms"][k])
+
+
+def test_iddpm_loss_gradient_does_not_reach_the_mean_through_vb():
+    """The vb term sees a detached epsilon (gaussian_diffusion.py:808): d vb / d eps == 0."""
+    loss = IDDPMLoss()
+    g = torch.Generator().manual_seed(0)
+    out = torch.randn(2, 8, 8, 8, generator=g, requires_grad=True)
+    x0, noise = torch.randn(2, 4, 8, 8, generator=g), torch.randn(2, 4, 8, 8, generator=g)
+    terms = loss.training_losses(lambda x, timestep, **kw: out, x0, torch.tensor([3, 700]), {}, noise=noise)
+    terms["vb"].sum().backward()
+    assert float(out.grad[:, :4].abs().max()) == 0.0 and float(out.grad[:, 4:].abs().max()) > 0.0
+
+
+@pytest.mark.slow
+def test_oracle_autograd_matches_reference_gradients(golden_dir):
+    fix = torch.load(os.path.join(golden_dir, "train_d2_b2.pt"))
+    cfg = po.OracleConfig(**fix["cfg"])
+    sd = {k: v.requires_grad_(v.is_floating_point()) for k, v in po.synthetic_state_dict(cfg, seed=0).items()}
+    x0, t, y, mask, noise = train_inputs(cfg, fix["batch"], tuple(fix["hw"]), fix["t"], fix["lens"])
+    model = lambda x, timestep, **kw: po.forward_grad(sd, cfg, x, timestep.float(), kw["y"], mask=kw["mask"])
+    terms = IDDPMLoss().training_losses(model, x0, t, dict(y=y, mask=mask, data_info=None), noise=noise)
+    for k in ("mse", "vb", "loss"):
+        assert torch.allclose(terms[k], fix["terms"][k], rtol=1e-4, atol=1e-5), k
+    terms["loss"].mean().backward()
+    worst = 0.0
+    for name, ref in fix["grads"].items():
+        g = sd[name].grad.flatten()
+        vals = g[fingerprint_positions(g.numel())]
+        worst = max(worst, abs(float(g.norm()) - float(ref["norm"])) / float(ref["norm"]), po.rel_err(vals, ref["vals"]))
+    assert worst < 2e-3, worst            # fp32 vs fp32, different summation orders
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class _Tiny(torch.nn.Module):
+    """Same naming scheme as the model (blocks.<i>.* + others) so the default bucketing rule is exercised."""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(3)
+        self.blocks = torch.nn.ModuleList([torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.Tanh(), torch.nn.Linear(8, 8))
+                                           for _ in range(3)])
+        self.head = torch.nn.Linear(8, 2)
+        self.unused = torch.nn.Parameter(torch.zeros(3))
+
+    def forward(self, x):
+        for b in self.blocks:
+            x = x + b(x)
+        return self.head(x)
+
+
+def _ddp_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        m = _Tiny()
+        red = GradBucketReducer(m)
+        assert len(red.buckets) == 4 and {b["key"] for b in red.buckets} == {"blocks.0", "blocks.1", "blocks.2", "rest"}
+        x = torch.randn(8, 8, generator=torch.Generator().manual_seed(9))
+        lo, hi = rank * 4, rank * 4 + 4
+        for step in range(2):                                    # two steps: buckets re-arm, zero_grad keeps the views
+            red.zero_grad()
+            red.start()
+            m(x[lo:hi]).pow(2).mean().backward()
+            red.finish()
+        torch.save({n: p.grad.clone() for n, p in m.named_parameters()}, os.path.join(out_dir, f"g{rank}.pt"))
+        assert all(p.grad.data_ptr() >= b["flat"].data_ptr() for b in red.buckets for p in b["params"])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grad_bucket_reducer_gloo_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_ddp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    g0, g1 = torch.load(tmp_path / "g0.pt"), torch.load(tmp_path / "g1.pt")
+    m = _Tiny()
+    x = torch.randn(8, 8, generator=torch.Generator().manual_seed(9))
+    m(x).pow(2).mean().backward()                                # mean over the global batch == mean of the rank means
+    for n, p in m.named_parameters():
+        want = p.grad if p.grad is not None else torch.zeros_like(p)
+        assert torch.allclose(g0[n], want, rtol=1e-5, atol=1e-7), n
+        assert torch.equal(g0[n], g1[n]), n
+
+
+def test_grad_bucket_reducer_single_process_is_a_noop_reduce():
+    m = _Tiny()
+    red = GradBucketReducer(m)
+    m(torch.ones(2, 8)).sum().backward()
+    red.finish()
+    assert red.grad_bytes() == sum(p.numel() for p in m.parameters()) * 4
+    assert float(m.head.weight.grad.abs().sum()) > 0
