@@ -19,30 +19,35 @@ parameter dtype.  There is no eager fallback: a missing library or a non-sm_100 
 """
 from __future__ import annotations
 
-from typing import Dict, Optional, Tuple
+from typing import Optional
 
 import torch
 
 from . import lib
 
-_SHADOW: Dict[Tuple[int, str], Tuple[int, torch.Tensor]] = {}
-
-
-def _shadow(p: torch.Tensor, kind: str) -> torch.Tensor:
-    """bf16 copy ('w') or bf16 transposed copy ('t') of a parameter, rebuilt only when the parameter was updated."""
-    key = (id(p), kind)
-    hit = _SHADOW.get(key)
-    if hit is not None and hit[0] == p._version and hit[1].device == p.device:
+def _shadow(mod: torch.nn.Module, kind: str) -> Optional[torch.Tensor]:
+    """bf16 copy of `mod.weight` ('w'), its bf16 transpose ('t') or the bf16 bias ('b'), cached ON THE MODULE and
+    rebuilt only when the parameter changed (in-place optimizer update / load_state_dict bump `_version`; `.to()` moves
+    the storage).  Keyed by the owning module, not by tensor identity: under activation checkpointing autograd hands the
+    backward detached aliases of the parameters, whose ids are recycled."""
+    p = mod.bias if kind == "b" else mod.weight
+    if p is None:
+        return None
+    cache = mod.__dict__.setdefault("_pxa_shadow", {})
+    tag = (p._version, p.data_ptr(), p.dtype, p.device)
+    hit = cache.get(kind)
+    if hit is not None and hit[0] == tag:
         return hit[1]
     src = p.detach()
-    w16 = src if src.dtype == torch.bfloat16 else src.to(torch.bfloat16)
-    val = w16.contiguous() if kind == "w" else lib.transpose(w16.contiguous())
-    _SHADOW[key] = (p._version, val)
+    w16 = (src if src.dtype == torch.bfloat16 else src.to(torch.bfloat16)).contiguous()
+    val = lib.transpose(w16) if kind == "t" else w16
+    cache[kind] = (tag, val)
     return val
 
 
-def clear_shadow_cache() -> None:
-    _SHADOW.clear()
+def clear_shadow_cache(model: torch.nn.Module) -> None:
+    for m in model.modules():
+        m.__dict__.pop("_pxa_shadow", None)
 
 
 def _t_pad8(a: torch.Tensor) -> torch.Tensor:
@@ -57,25 +62,30 @@ def _t_pad8(a: torch.Tensor) -> torch.Tensor:
 
 
 class LinearFn(torch.autograd.Function):
+    """y = x W^T + b of `mod` (an nn.Linear: the owner of the bf16 shadows); weight / bias are passed as tensors too so
+    that autograd routes their gradients."""
+
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, mod):
         assert x.dtype == torch.bfloat16 and x.dim() == 2
         x = x.contiguous()
         out = torch.empty((x.shape[0], weight.shape[0]), dtype=torch.bfloat16, device=x.device)
-        lib.gemm(x, _shadow(weight, "w"), None if bias is None else _shadow(bias, "w"), out)
+        lib.gemm(x, _shadow(mod, "w"), _shadow(mod, "b"), out)
         ctx.save_for_backward(x, weight, bias)
+        ctx.mod = mod
         return out
 
     @staticmethod
     def backward(ctx, dy):
         x, weight, bias = ctx.saved_tensors
+        mod = ctx.mod
         dy = dy.contiguous()
         M, K = x.shape
         N = weight.shape[0]
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty((M, K), dtype=torch.bfloat16, device=x.device)
-            lib.gemm(dy, _shadow(weight, "t"), None, dx)                       # dX = dY . W   (W^T is K-contiguous in N)
+            lib.gemm(dy, _shadow(mod, "t"), None, dx)                          # dX = dY . W   (W^T is K-contiguous in N)
         if ctx.needs_input_grad[1]:
             dw32 = torch.zeros((N, K), dtype=torch.float32, device=x.device)
             lib.gemm(_t_pad8(dy), _t_pad8(x), None, dw32, epilogue=lib.EPI_BIAS_RESIDUAL, residual=dw32)   # dW += dY^T . X
@@ -84,7 +94,7 @@ class LinearFn(torch.autograd.Function):
             db32 = torch.zeros((N,), dtype=torch.float32, device=x.device)
             lib.colsum(dy, db32)
             db = db32 if bias.dtype == torch.float32 else db32.to(bias.dtype)
-        return dx, dw, db
+        return dx, dw, db, None
 
 
 class LnModulateFn(torch.autograd.Function):
@@ -237,7 +247,7 @@ class CrossAttnFn(torch.autograd.Function):
 
 
 def linear(x: torch.Tensor, mod: torch.nn.Linear) -> torch.Tensor:
-    return LinearFn.apply(x, mod.weight, mod.bias)
+    return LinearFn.apply(x, mod.weight, mod.bias, mod)
 
 
 def block_forward_train(blk, x32: torch.Tensor, cond: torch.Tensor, kv_len: Optional[torch.Tensor],
