@@ -446,8 +446,9 @@ def run_train(args, wl):
     timer = KernelTimer(lib)
     timer.recs["attn_bwd"] = []
     timer.install()
-    _ab = lib.flash_attn_bwd
+    _ab, _wg = lib.flash_attn_bwd, lib.gemm_wgrad
     lib.flash_attn_bwd = lambda *a, **k: timer._wrap("attn_bwd", _ab, a, k)
+    lib.gemm_wgrad = lambda *a, **k: timer._wrap("gemm", _wg, a, k)
     for i in range(max(args.warmup, 3)):
         loss0 = step_resident(i)
     step_e2e(0)
@@ -471,7 +472,7 @@ def run_train(args, wl):
         gemm_tf = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else None
         afw_ms, afw_n = tt["attn"]
         abw_ms, abw_n = tt["attn_bwd"]
-        afw_tf = (1 + recompute) * f_attn * args.steps / (afw_ms / 1000.0) / 1e12 if afw_ms > 0 else None
+        afw_tf = f_attn * args.steps / (afw_ms / 1000.0) / 1e12 if afw_ms > 0 else None   # recomputation reuses (o, lse)
         abw_tf = 3.5 * f_attn * args.steps / (abw_ms / 1000.0) / 1e12 if abw_ms > 0 else None     # 14 N Nk d executed (10 model)
         model_tf = 3 * fwd / (ms_step / 1000.0) / 1e12
         roof = {"bound": "tensor", "kernel": "pxa::gemm_bf16_kernel (forward, recompute, dgrad and wgrad GEMMs)",

@@ -68,6 +68,13 @@ typedef struct PxaGemmArgs {
   int32_t max_ctas;     /* 0 = one CTA per SM; >0 caps the persistent grid (tests)                  */
   int32_t cta_pair;     /* 0 = auto, 1 = single-CTA UMMA (128 x BN tiles), 2 = CTA-pair UMMA (256 x BN tiles) */
   int64_t* debug_trace; /* NULL in production. Else device int64[4096]: cycle stamps of CTA 0's epilogue issuer thread */
+  int32_t operands_mn_major; /* 1: weight-gradient form out[M, N] += A^T . W with a = [K, M] (row stride lda) and
+                                w = [K, N] (row stride ldw), i.e. the contraction runs over the ROWS of both operands
+                                (dW = dY^T X straight from the activations' natural layouts; no transposes).  Requires
+                                EPI_BIAS_RESIDUAL, fp32 out, residual == out (in-place accumulate), no bias / gate / aux. */
+  int32_t k_splits;     /* operands_mn_major only: 0 = auto (fill the 148 SMs), else the number of K splits        */
+  int32_t aux_is_branch; /* EPI_BIAS_RESIDUAL with out_aux_bf16: 1 = the aux output receives acc + bias (the un-gated
+                            branch output, which the backward of the gate needs) instead of a bf16 copy of out          */
 } PxaGemmArgs;
 int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream);
 

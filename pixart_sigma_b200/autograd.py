@@ -4,9 +4,9 @@ The reference trains through torch autograd (`train_scripts/train.py:197 acceler
 activation checkpointing (`diffusion/model/utils.py:28-45`, call site `PixArtMS.py:206`).  Here autograd is only the
 tape: every node below calls into libpixart_sm100.so in both directions --
 
-  LinearFn        y = x W^T + b           bwd: dX = dY W and dW += dY^T X on the tcgen05 GEMM (pxa_gemm_bf16 over
-                                          pxa_transpose_bf16'd operands; dW accumulates in fp32 through the TMA
-                                          reduce-add epilogue), db by pxa_colsum_bf16
+  LinearFn        y = x W^T + b           bwd: dX = dY W (pxa_gemm_bf16 on the cached W^T) and dW += dY^T X (the GEMM's
+                                          weight-gradient form: both activations consumed MN-major in their natural
+                                          layouts, split-K, fp32 TMA reduce-add epilogue), db by pxa_colsum_bf16
   LnModulateFn    LN(x)(1+scale)+shift    bwd: pxa_ln_modulate_bwd (dx, d shift, d scale)            PixArtMS.py:75,77
   GateResidualFn  x + gate * y            bwd: pxa_gate_residual_bwd (dy, d gate)                    PixArtMS.py:75-77
   GeluFn          gelu_tanh(pre)          bwd: pxa_gelu_tanh_bf16 with dh                            timm Mlp.act
@@ -50,17 +50,6 @@ def clear_shadow_cache(model: torch.nn.Module) -> None:
         m.__dict__.pop("_pxa_shadow", None)
 
 
-def _t_pad8(a: torch.Tensor) -> torch.Tensor:
-    """a (R, C) bf16 -> a^T as a (C, roundup(R, 8)) K-contiguous GEMM operand (zero columns past R)."""
-    R, Cc = a.shape
-    Rp = (R + 7) // 8 * 8
-    if Rp == R:
-        return lib.transpose(a)
-    buf = torch.zeros((Cc, Rp), dtype=torch.bfloat16, device=a.device)
-    lib.transpose(a, buf[:, :R])
-    return buf
-
-
 class LinearFn(torch.autograd.Function):
     """y = x W^T + b of `mod` (an nn.Linear: the owner of the bf16 shadows); weight / bias are passed as tensors too so
     that autograd routes their gradients."""
@@ -78,23 +67,67 @@ class LinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, weight, bias = ctx.saved_tensors
-        mod = ctx.mod
-        dy = dy.contiguous()
-        M, K = x.shape
-        N = weight.shape[0]
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty((M, K), dtype=torch.bfloat16, device=x.device)
-            lib.gemm(dy, _shadow(mod, "t"), None, dx)                          # dX = dY . W   (W^T is K-contiguous in N)
-        if ctx.needs_input_grad[1]:
-            dw32 = torch.zeros((N, K), dtype=torch.float32, device=x.device)
-            lib.gemm(_t_pad8(dy), _t_pad8(x), None, dw32, epilogue=lib.EPI_BIAS_RESIDUAL, residual=dw32)   # dW += dY^T . X
-            dw = dw32 if weight.dtype == torch.float32 else dw32.to(weight.dtype)
-        if bias is not None and ctx.needs_input_grad[2]:
-            db32 = torch.zeros((N,), dtype=torch.float32, device=x.device)
-            lib.colsum(dy, db32)
-            db = db32 if bias.dtype == torch.float32 else db32.to(bias.dtype)
+        dx, dw, db = _linear_backward(ctx.needs_input_grad[:3], x, weight, bias, ctx.mod, dy.contiguous())
         return dx, dw, db, None
+
+
+def _linear_backward(ctx_needs, x, weight, bias, mod, dy):
+    """(dx, dw, db) of y = x W^T + b for the incoming dy (bf16, contiguous); ctx_needs = needs_input_grad of (x, W, b)."""
+    M, K = x.shape
+    N = weight.shape[0]
+    dx = dw = db = None
+    if ctx_needs[0]:
+        dx = torch.empty((M, K), dtype=torch.bfloat16, device=x.device)
+        lib.gemm(dy, _shadow(mod, "t"), None, dx)                              # dX = dY . W   (W^T is K-contiguous in N)
+    if ctx_needs[1]:
+        dw32 = torch.zeros((N, K), dtype=torch.float32, device=x.device)
+        lib.gemm_wgrad(dy, x, dw32)                                            # dW += dY^T . X  (MN-major operands, split-K)
+        dw = dw32 if weight.dtype == torch.float32 else dw32.to(weight.dtype)
+    if bias is not None and ctx_needs[2]:
+        db32 = torch.zeros((N,), dtype=torch.float32, device=x.device)
+        lib.colsum(dy, db32)
+        db = db32 if bias.dtype == torch.float32 else db32.to(bias.dtype)
+    return dx, dw, db
+
+
+class LinearGateResidualFn(torch.autograd.Function):
+    """out = x32 + tab[:, i_gate] * (a W^T + b) in ONE GEMM launch (fp32 residual epilogue, PixArtMS.py:75-77): the
+    branch output never makes a separate pass; with a gate it is kept (bf16 aux output of the epilogue) because the
+    gate's gradient is sum_rows dout * branch."""
+
+    @staticmethod
+    def forward(ctx, a, weight, bias, mod, x32, tab, i_gate, rows_per_batch):
+        a, x32 = a.contiguous(), x32.contiguous()
+        M, N = a.shape[0], weight.shape[0]
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+        gated = i_gate >= 0
+        y = torch.empty((M, N), dtype=torch.bfloat16, device=a.device) if gated else None
+        lib.gemm(a, _shadow(mod, "w"), _shadow(mod, "b"), out, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x32,
+                 gate=tab[:, i_gate] if gated else None, gate_batch_stride=tab.stride(0) if gated else 0,
+                 rows_per_batch=rows_per_batch, out_aux=y, aux_is_branch=True)
+        ctx.save_for_backward(a, weight, bias, y, tab if gated else None)
+        ctx.mod, ctx.idx = mod, (i_gate, rows_per_batch)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        a, weight, bias, y, tab = ctx.saved_tensors
+        i_gate, rpb = ctx.idx
+        dout = dout.contiguous()
+        dy = torch.empty(dout.shape, dtype=torch.bfloat16, device=dout.device)
+        dtab = None
+        if tab is not None:
+            want = ctx.needs_input_grad[5]
+            dg = torch.zeros((tab.shape[0], tab.shape[2]), dtype=torch.float32, device=dout.device) if want else None
+            lib.gate_residual_bwd(dout, y if want else None, tab[:, i_gate], dy, dg, gate_batch_stride=tab.stride(0),
+                                  rows_per_batch=rpb)
+            if want:
+                dtab = torch.zeros_like(tab)
+                dtab[:, i_gate] = dg
+        else:
+            lib.gate_residual_bwd(dout, None, None, dy, None, rows_per_batch=rpb)
+        da, dw, db = _linear_backward(ctx.needs_input_grad[:3], a, weight, bias, ctx.mod, dy)
+        return da, dw, db, None, dout, dtab, None, None
 
 
 class LnModulateFn(torch.autograd.Function):
@@ -180,17 +213,23 @@ class SelfAttnFn(torch.autograd.Function):
     """o (B*N, C) = attention over the q/k/v slices of the qkv GEMM output (B*N, 3C) (PixArt_blocks.py:130-153)."""
 
     @staticmethod
-    def forward(ctx, qkv, B, H, N, scale):
+    def forward(ctx, qkv, B, H, N, scale, keep):
         qkv = qkv.contiguous()
         M, C3 = qkv.shape
         C = C3 // 3
         D = C // H
         q3 = qkv.view(M, 3, H, D)
-        o = torch.empty((M, C), dtype=torch.bfloat16, device=qkv.device)
-        lse = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device)
-        st = (3 * C, D)
-        lib.flash_attn(q3[:, 0], q3[:, 1], q3[:, 2], o, B=B, H=H, Nq=N, Nk=N, kv_rows=M, q_strides=st, k_strides=st,
-                       v_strides=st, scale=scale, lse=lse)
+        hit = keep.pop("self", None) if keep is not None and keep.get("replay") else None
+        if hit is not None:                           # recomputation of a checkpointed block: (o, lse) were kept
+            o, lse = hit
+        else:
+            o = torch.empty((M, C), dtype=torch.bfloat16, device=qkv.device)
+            lse = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device)
+            st = (3 * C, D)
+            lib.flash_attn(q3[:, 0], q3[:, 1], q3[:, 2], o, B=B, H=H, Nq=N, Nk=N, kv_rows=M, q_strides=st, k_strides=st,
+                           v_strides=st, scale=scale, lse=lse)
+            if keep is not None and not keep.get("replay"):
+                keep["self"] = (o, lse)
         ctx.save_for_backward(qkv, o, lse)
         ctx.geom = (B, H, N, scale)
         return o
@@ -209,22 +248,28 @@ class SelfAttnFn(torch.autograd.Function):
         lib.flash_attn_bwd(q3[:, 0], q3[:, 1], q3[:, 2], o, d_o.contiguous(), lse, d3[:, 0], d3[:, 1], d3[:, 2], B=B, H=H,
                            Nq=N, Nk=N, kv_rows=M, q_strides=st, k_strides=st, v_strides=st, dq_strides=st, dk_strides=st,
                            dv_strides=st, scale=scale)
-        return dqkv, None, None, None, None
+        return dqkv, None, None, None, None, None
 
 
 class CrossAttnFn(torch.autograd.Function):
     """o (B*N, C) = var-len attention of q (B*N, C) over the caption keys kv (rows, 2C) (PixArt_blocks.py:43-58)."""
 
     @staticmethod
-    def forward(ctx, q, kv, kv_len, kv_off, B, H, N, max_keys, scale):
+    def forward(ctx, q, kv, kv_len, kv_off, B, H, N, max_keys, scale, keep):
         q, kv = q.contiguous(), kv.contiguous()
         M, C = q.shape
         D = C // H
         kv4 = kv.view(-1, 2, H, D)
-        o = torch.empty((M, C), dtype=torch.bfloat16, device=q.device)
-        lse = torch.empty((B, H, N), dtype=torch.float32, device=q.device)
-        lib.flash_attn(q, kv4[:, 0], kv4[:, 1], o, B=B, H=H, Nq=N, Nk=max_keys, kv_rows=kv.shape[0], kv_len=kv_len,
-                       kv_off=kv_off, q_strides=(C, D), k_strides=(2 * C, D), v_strides=(2 * C, D), scale=scale, lse=lse)
+        hit = keep.pop("cross", None) if keep is not None and keep.get("replay") else None
+        if hit is not None:
+            o, lse = hit
+        else:
+            o = torch.empty((M, C), dtype=torch.bfloat16, device=q.device)
+            lse = torch.empty((B, H, N), dtype=torch.float32, device=q.device)
+            lib.flash_attn(q, kv4[:, 0], kv4[:, 1], o, B=B, H=H, Nq=N, Nk=max_keys, kv_rows=kv.shape[0], kv_len=kv_len,
+                           kv_off=kv_off, q_strides=(C, D), k_strides=(2 * C, D), v_strides=(2 * C, D), scale=scale, lse=lse)
+            if keep is not None and not keep.get("replay"):
+                keep["cross"] = (o, lse)
         ctx.save_for_backward(q, kv, o, lse, kv_len, kv_off)
         ctx.geom = (B, H, N, max_keys, scale)
         return o
@@ -243,7 +288,7 @@ class CrossAttnFn(torch.autograd.Function):
                            Nk=max_keys, kv_rows=kv.shape[0], kv_len=kv_len, kv_off=kv_off, q_strides=(C, D),
                            k_strides=(2 * C, D), v_strides=(2 * C, D), dq_strides=(C, D), dk_strides=(2 * C, D),
                            dv_strides=(2 * C, D), scale=scale)
-        return dq, dkv, None, None, None, None, None, None, None
+        return dq, dkv, None, None, None, None, None, None, None, None
 
 
 def linear(x: torch.Tensor, mod: torch.nn.Linear) -> torch.Tensor:
@@ -251,9 +296,13 @@ def linear(x: torch.Tensor, mod: torch.nn.Linear) -> torch.Tensor:
 
 
 def block_forward_train(blk, x32: torch.Tensor, cond: torch.Tensor, kv_len: Optional[torch.Tensor],
-                        kv_off: Optional[torch.Tensor], max_keys: int, mod: torch.Tensor, B: int, N: int) -> torch.Tensor:
+                        kv_off: Optional[torch.Tensor], max_keys: int, mod: torch.Tensor, B: int, N: int,
+                        keep: Optional[dict] = None) -> torch.Tensor:
     """One PixArtMSBlock (PixArtMS.py:71-79) on the differentiable kernel ops; same arguments as `run_kernels`, but
-    out of place (returns the new fp32 residual stream) so autograd / activation checkpointing can replay it."""
+    out of place (returns the new fp32 residual stream) so autograd / activation checkpointing can replay it.
+    `keep`: per-call dict used with activation checkpointing -- the first pass stores the two attention outputs and
+    their softmax statistics in it (76 MB per block at 4 x 4096 tokens), the recomputation pass (keep["replay"] set)
+    takes them back instead of re-running the attention kernels."""
     a, ca, mlp = blk.attn, blk.cross_attn, blk.mlp
     H = a.num_heads
     if a.sr_ratio > 1:
@@ -265,15 +314,17 @@ def block_forward_train(blk, x32: torch.Tensor, cond: torch.Tensor, kv_len: Opti
     mod = mod.contiguous()
     # (1) x += gate_msa * proj(attn(LN(x) * (1 + scale_msa) + shift_msa))                         PixArtMS.py:75
     xn = LnModulateFn.apply(x32, mod, 0, 1, N)
-    ao = SelfAttnFn.apply(linear(xn, a.qkv), B, H, N, a.scale)
-    x32 = GateResidualFn.apply(x32, linear(ao, a.proj), mod, 2, N)
+    ao = SelfAttnFn.apply(linear(xn, a.qkv), B, H, N, a.scale, keep)
+    x32 = LinearGateResidualFn.apply(ao, a.proj.weight, a.proj.bias, a.proj, x32, mod, 2, N)
     # (2) x += proj(cross_attn(x, cond))                                                          PixArtMS.py:76
     qx = linear(x32.to(torch.bfloat16), ca.q_linear)
     kv = linear(cond, ca.kv_linear)
-    ao = CrossAttnFn.apply(qx, kv, kv_len, kv_off, B, H, N, max_keys, ca.head_dim ** -0.5)
-    x32 = GateResidualFn.apply(x32, linear(ao, ca.proj), mod, -1, N)
+    ao = CrossAttnFn.apply(qx, kv, kv_len, kv_off, B, H, N, max_keys, ca.head_dim ** -0.5, keep)
+    x32 = LinearGateResidualFn.apply(ao, ca.proj.weight, ca.proj.bias, ca.proj, x32, mod, -1, N)
     # (3) x += gate_mlp * fc2(gelu_tanh(fc1(LN(x) * (1 + scale_mlp) + shift_mlp)))               PixArtMS.py:77
     xn = LnModulateFn.apply(x32, mod, 3, 4, N)
     h = GeluFn.apply(linear(xn, mlp.fc1))
-    x32 = GateResidualFn.apply(x32, linear(h, mlp.fc2), mod, 5, N)
+    x32 = LinearGateResidualFn.apply(h, mlp.fc2.weight, mlp.fc2.bias, mlp.fc2, x32, mod, 5, N)
+    if keep is not None:
+        keep["replay"] = True            # the next call with this dict is the recomputation
     return x32

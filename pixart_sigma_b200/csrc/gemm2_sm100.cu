@@ -274,6 +274,8 @@ static int launch_gemm2(const PxaGemmArgs& a, cudaStream_t stream) {
   p.num_m_tiles = (a.M + 2 * kBM - 1) / (2 * kBM);
   p.num_n_tiles = (a.N + BN - 1) / BN;
   p.trace = reinterpret_cast<long long*>(a.debug_trace);
+  p.k_splits = 1;
+  p.aux_branch = a.aux_is_branch;
   auto kern = gemm2_bf16_kernel<BN, EPI, OutT>;
   PXA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
   int clusters = device_info().sms / 2;

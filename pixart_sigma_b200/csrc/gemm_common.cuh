@@ -22,6 +22,8 @@ struct GemmParams {
   int M, N, K, ldo;
   int num_m_tiles, num_n_tiles;
   long long* trace;     // debug only (NULL in production)
+  int k_splits;         // > 1: split-K over tiles (reduce-add epilogue only)
+  int aux_branch;       // residual epilogue: the bf16 aux output receives acc + bias (the branch output) instead of out
   // implicit-GEMM 3x3 convolution mode (kConv): A is an NHWC image read through a 4-D tensor map
   int conv_H, conv_W, conv_tile_w, conv_tile_h, conv_cin_blocks;
 };
@@ -187,10 +189,11 @@ PXA_DEVICE void epilogue_chunk_residual(uint32_t (&v)[32], const ResFrag& res, c
     if (grow < p.M && col_ok) {
       const size_t off = (size_t)grow * p.ldo + gcol;
       float4 o;
-      o.x = fmaf(g[it].x, a.x + b0, res.r[it].x);
-      o.y = fmaf(g[it].y, a.y + b1, res.r[it].y);
-      o.z = fmaf(g[it].z, a.z + b2, res.r[it].z);
-      o.w = fmaf(g[it].w, a.w + b3, res.r[it].w);
+      const float4 yb = make_float4(a.x + b0, a.y + b1, a.z + b2, a.w + b3);     // the branch output
+      o.x = fmaf(g[it].x, yb.x, res.r[it].x);
+      o.y = fmaf(g[it].y, yb.y, res.r[it].y);
+      o.z = fmaf(g[it].z, yb.z, res.r[it].z);
+      o.w = fmaf(g[it].w, yb.w, res.r[it].w);
       if constexpr (sizeof(OutT) == 4) {
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = o;
       } else {
@@ -198,7 +201,8 @@ PXA_DEVICE void epilogue_chunk_residual(uint32_t (&v)[32], const ResFrag& res, c
             make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
       }
       if (p.out_aux != nullptr) {
-        *reinterpret_cast<uint2*>(p.out_aux + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        const float4 ax = p.aux_branch ? yb : o;
+        *reinterpret_cast<uint2*>(p.out_aux + off) = make_uint2(pack_bf16x2(ax.x, ax.y), pack_bf16x2(ax.z, ax.w));
       }
     }
   }
@@ -289,13 +293,16 @@ PXA_DEVICE void residual_chunk_row_c(uint32_t (&v)[32], const GemmParams& p, con
     float4 g = gp[c];
     if (per_row_gate) g = (gcol0 + 4 * c < p.N) ? __ldg(reinterpret_cast<const float4*>(gg + 4 * c)) : make_float4(1.f, 1.f, 1.f, 1.f);
     float4 o;
-    o.x = fmaf(g.x, __uint_as_float(v[4 * c + 0]) + b.x, res[c].x);
-    o.y = fmaf(g.y, __uint_as_float(v[4 * c + 1]) + b.y, res[c].y);
-    o.z = fmaf(g.z, __uint_as_float(v[4 * c + 2]) + b.z, res[c].z);
-    o.w = fmaf(g.w, __uint_as_float(v[4 * c + 3]) + b.w, res[c].w);
+    const float4 yb = make_float4(__uint_as_float(v[4 * c + 0]) + b.x, __uint_as_float(v[4 * c + 1]) + b.y,
+                                  __uint_as_float(v[4 * c + 2]) + b.z, __uint_as_float(v[4 * c + 3]) + b.w);
+    o.x = fmaf(g.x, yb.x, res[c].x);
+    o.y = fmaf(g.y, yb.y, res[c].y);
+    o.z = fmaf(g.z, yb.z, res[c].z);
+    o.w = fmaf(g.w, yb.w, res[c].w);
     res[c] = o;
-    aux[2 * c] = pack_bf16x2(o.x, o.y);
-    aux[2 * c + 1] = pack_bf16x2(o.z, o.w);
+    const float4 ax = p.aux_branch ? yb : o;
+    aux[2 * c] = pack_bf16x2(ax.x, ax.y);
+    aux[2 * c + 1] = pack_bf16x2(ax.z, ax.w);
   }
 #pragma unroll
   for (int c = 0; c < 8; ++c) *reinterpret_cast<float4*>(rrow + ((c ^ sw) << 4)) = res[c];           // then all stores

@@ -16,7 +16,12 @@
 namespace pxa {
 
 // ------------------------------------------------------------------------------------------------- kernel
-template <int BN, int EPI, typename OutT, bool kConv = false>
+// kMn: both operands are given MN-major -- A as [K, M] (M contiguous), W as [K, N] (N contiguous) -- the layout of the
+// weight-gradient product dW[N, K] = dY[M, N]^T X[M, K], whose contraction runs over the token dimension.  Each K-block
+// is staged as 64-wide swizzle atoms of 64 k-rows (two for the 128 rows of A, BN / 64 for W) and consumed through
+// MN-major UMMA descriptors (atoms LBO apart, 16 k-rows = 2048 B per K-step).  With p.k_splits > 1 the K range is split
+// across tiles (split-K); legal only with the TMA reduce-add epilogue, which makes the partial sums add up in L2.
+template <int BN, int EPI, typename OutT, bool kConv = false, bool kMn = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out,
@@ -58,8 +63,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int mn_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_tiles = mn_tiles * p.k_splits;
   const int num_kb = (p.K + kBK - 1) / kBK;
+  // tile -> (k split, m tile, n tile), n fastest; K-blocks [kb_lo, kb_hi) of split ks
+  auto kb_lo = [&](int tile) { return (int)((long long)(tile / mn_tiles) * num_kb / p.k_splits); };
+  auto kb_hi = [&](int tile) { return (int)((long long)(tile / mn_tiles + 1) * num_kb / p.k_splits); };
 
   if (warp == 0) {
     // ================================================================ TMA producer
@@ -67,8 +76,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.num_n_tiles) * kBM;
-        const int n0 = (tile % p.num_n_tiles) * BN;
+        const int m0 = ((tile % mn_tiles) / p.num_n_tiles) * kBM;
+        const int n0 = ((tile % mn_tiles) % p.num_n_tiles) * BN;
         if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
           // pull this tile's residual block into L2 now: the epilogue reads it one mainloop (~7k cycles) later
           if constexpr (kTmaRes) {
@@ -78,11 +87,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             tma_prefetch_l2_2d(&tmap_res, n0, m0);
           }
         }
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb_lo(tile); kb < kb_hi(tile); ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStage;
           uint8_t* sb = sa + Cfg::kStageA;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStage);
+          if constexpr (kMn) {
+#pragma unroll
+            for (int i = 0; i < kBM / 64; ++i) tma_load_2d(sa + i * 8192, &tmap_a, &full_bar[stage], m0 + 64 * i, kb * kBK, kEvictNormal);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmap_w, &full_bar[stage], n0 + 64 * j, kb * kBK, kEvictNormal);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if constexpr (kConv) {
             // implicit GEMM: K-block kb = (tap, 64-channel slice); the A tile is the tile's pixel block shifted by the
             // tap offset -- zero padding comes for free from TMA out-of-bounds fill on the W / H dimensions
@@ -104,7 +121,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp == 1) {
     // ================================================================ MMA issuer
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, kMn ? 1 : 0, kMn ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -113,16 +130,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = kb_lo(tile), kb1 = kb_hi(tile);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStage);
-          const uint64_t adesc = make_smem_desc(sa, 16, 1024, kLayoutSW128);
-          const uint64_t bdesc = make_smem_desc(sa + Cfg::kStageA, 16, 1024, kLayoutSW128);
+          // K-major: 8-row groups 1024 B apart; MN-major: 64-wide atoms 8192 B apart (LBO), 8 k-rows = 1024 B (SBO)
+          const uint64_t adesc = make_smem_desc(sa, kMn ? 8192 : 16, 1024, kLayoutSW128);
+          const uint64_t bdesc = make_smem_desc(sa + Cfg::kStageA, kMn ? 8192 : 16, 1024, kLayoutSW128);
+          // one K-step = 16 elements along K: 32 B inside the swizzle atom (K-major) / 16 rows of 128 B (MN-major)
+          constexpr int kStep = kMn ? (2048 >> 4) : 2;
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
-            // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_ss(d_tmem, adesc + kStep * k, bdesc + kStep * k, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -155,8 +175,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int l_tile = blockIdx.x, l_cc = 0, l_g = 0;                   // issuer: next residual chunk to request
     auto request_next = [&]() {
       if (l_tile >= num_tiles) return;
-      const int lm0 = (l_tile / p.num_n_tiles) * kBM;
-      const int ln0 = (l_tile % p.num_n_tiles) * BN;
+      const int lm0 = ((l_tile % mn_tiles) / p.num_n_tiles) * kBM;
+      const int ln0 = ((l_tile % mn_tiles) % p.num_n_tiles) * BN;
       const int buf = l_g % kResBufs;
       mbar_arrive_expect_tx(&res_full[buf], kResChunkBytes);
       tma_load_2d(rbufs + buf * kResChunkBytes, &tmap_res, &res_full[buf], ln0 + l_cc * 32, lm0, kEvictFirst);
@@ -177,8 +197,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     };
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
-      const int m0 = (tile / p.num_n_tiles) * kBM;
-      const int n0 = (tile % p.num_n_tiles) * BN;
+      const int m0 = ((tile % mn_tiles) / p.num_n_tiles) * kBM;
+      const int n0 = ((tile % mn_tiles) % p.num_n_tiles) * BN;
       const int nch = chunks_of_tile<BN>(p, n0);
       EpiConst* cb = consts + (titer & 1);
       stage_epi_consts<BN>(cb, p, tid, m0, n0);                  // global loads hide under this tile's MMAs
@@ -269,10 +289,19 @@ struct ConvGeom {
   int B, H, W, Cin, tile_w, tile_h;
 };
 
-template <int BN, int EPI, typename OutT, bool kConv = false>
-static int launch_gemm(const PxaGemmArgs& a, cudaStream_t stream, const ConvGeom* cg = nullptr) {
+template <int BN, int EPI, typename OutT, bool kConv = false, bool kMn = false>
+static int launch_gemm(const PxaGemmArgs& a, cudaStream_t stream, const ConvGeom* cg = nullptr, int k_splits = 1) {
   CUtensorMap ta, tw;
-  if constexpr (kConv) {
+  if constexpr (kMn) {
+    // A stored [K, M] (row stride lda), W stored [K, N] (row stride ldw): 64 x 64 boxes, M / N the contiguous dimension
+    uint64_t dims_a[2] = {(uint64_t)a.M, (uint64_t)a.K}, dims_w[2] = {(uint64_t)a.N, (uint64_t)a.K};
+    uint64_t str_a[1] = {(uint64_t)a.lda * 2}, str_w[1] = {(uint64_t)a.ldw * 2};
+    uint32_t box[2] = {64, kBK};
+    int rc = make_tmap_bf16(&ta, a.a, 2, dims_a, str_a, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tw, a.w, 2, dims_w, str_w, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  } else if constexpr (kConv) {
     // NHWC image as a 4-D tensor (c, x, y, b); one A tile = tile_h rows x tile_w pixels x 64 channels
     uint64_t dims[4] = {(uint64_t)cg->Cin, (uint64_t)cg->W, (uint64_t)cg->H, (uint64_t)cg->B};
     uint64_t str[3] = {(uint64_t)cg->Cin * 2, (uint64_t)cg->W * cg->Cin * 2, (uint64_t)cg->H * cg->W * cg->Cin * 2};
@@ -286,7 +315,7 @@ static int launch_gemm(const PxaGemmArgs& a, cudaStream_t stream, const ConvGeom
     int rc = make_tmap_bf16(&ta, a.a, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  {
+  if constexpr (!kMn) {
     uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.N};
     uint64_t str[1] = {(uint64_t)a.ldw * 2};
     uint32_t box[2] = {kBK, (uint32_t)BN};
@@ -328,16 +357,18 @@ static int launch_gemm(const PxaGemmArgs& a, cudaStream_t stream, const ConvGeom
   p.num_m_tiles = (a.M + kBM - 1) / kBM;
   p.num_n_tiles = (a.N + BN - 1) / BN;
   p.trace = reinterpret_cast<long long*>(a.debug_trace);
+  p.k_splits = k_splits;
+  p.aux_branch = a.aux_is_branch;
   p.conv_H = p.conv_W = p.conv_tile_w = p.conv_tile_h = p.conv_cin_blocks = 0;
   if constexpr (kConv) {
     p.conv_H = cg->H; p.conv_W = cg->W; p.conv_tile_w = cg->tile_w; p.conv_tile_h = cg->tile_h;
     p.conv_cin_blocks = cg->Cin / kBK;
   }
-  auto kern = gemm_bf16_kernel<BN, EPI, OutT, kConv>;
+  auto kern = gemm_bf16_kernel<BN, EPI, OutT, kConv, kMn>;
   PXA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
   int grid = device_info().sms;
   if (a.max_ctas > 0 && a.max_ctas < grid) grid = a.max_ctas;
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;
   if (tiles < grid) grid = tiles;
   kern<<<grid, kGemmThreads, Cfg::kSmem, stream>>>(ta, tw, tr, to, tx, p);
   launch_counter()++;
@@ -364,6 +395,27 @@ static int dispatch_epi(const PxaGemmArgs& a, cudaStream_t s) {
 }
 
 int gemm_pair_dispatch(const PxaGemmArgs& a, int bn, cudaStream_t s);   // gemm2_sm100.cu
+
+// Weight-gradient form: out[M, N] += A^T W with A [K, M], W [K, N] (both MN-major), fp32 out accumulated in place through
+// the TMA reduce-add epilogue, K split over tiles so that the persistent grid is evenly loaded (the layer shapes give
+// only 54 .. 216 output tiles against 148 SMs; each tile's K loop is thousands of blocks long).
+template <int BN>
+static int launch_wgrad(const PxaGemmArgs& a, cudaStream_t s) {
+  const int tiles = ((a.M + kBM - 1) / kBM) * ((a.N + BN - 1) / BN);
+  const int num_kb = (a.K + kBK - 1) / kBK;
+  int sms = device_info().sms;
+  if (a.max_ctas > 0 && a.max_ctas < sms) sms = a.max_ctas;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int ks = 1; ks <= 16 && num_kb / ks >= 8; ++ks) {
+    const int t = tiles * ks;
+    const double eff = (double)t / (double)(((t + sms - 1) / sms) * sms);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = ks; }
+  }
+  if (a.k_splits > 0) best = a.k_splits;
+  if (best > num_kb) best = num_kb;
+  return launch_gemm<BN, PXA_EPI_BIAS_RESIDUAL, float, false, true>(a, s, nullptr, best);
+}
 
 template <int BN>
 static int dispatch_conv(const PxaGemmArgs& a, cudaStream_t s, const ConvGeom& cg) {
@@ -410,9 +462,11 @@ extern "C" int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream) {
   const PxaGemmArgs& a = *args;
   if (!a.a || !a.w || !a.out) return fail(PXA_ERR_ARG, "null a / w / out");
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return fail(PXA_ERR_ARG, "bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
-  if ((a.N & 7) || (a.K & 7) || (a.lda & 7) || (a.ldw & 7) || (a.ldo & 7))
-    return fail(PXA_ERR_ALIGN, "N, K, lda, ldw, ldo must be multiples of 8 (N=%d K=%d lda=%d ldw=%d ldo=%d)", a.N, a.K,
-                a.lda, a.ldw, a.ldo);
+  if ((a.N & 7) || (!a.operands_mn_major && (a.K & 7)) || (a.operands_mn_major && (a.M & 7)) || (a.lda & 7) ||
+      (a.ldw & 7) || (a.ldo & 7))
+    return fail(PXA_ERR_ALIGN, "N, the contiguous operand dimension (K; M for operands_mn_major), lda, ldw, ldo must be "
+                               "multiples of 8 (M=%d N=%d K=%d lda=%d ldw=%d ldo=%d)", a.M, a.N, a.K, a.lda, a.ldw, a.ldo);
+  if (a.k_splits < 0 || (a.k_splits > 1 && !a.operands_mn_major)) return fail(PXA_ERR_ARG, "k_splits needs operands_mn_major");
   if ((reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(a.bias) |
        reinterpret_cast<uintptr_t>(a.residual) | reinterpret_cast<uintptr_t>(a.gate) |
        reinterpret_cast<uintptr_t>(a.out_aux_bf16)) & 15)
@@ -422,6 +476,18 @@ extern "C" int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream) {
   int bn = a.block_n;
   if (bn == 0) bn = (a.N % 192 == 0) ? 192 : ((a.N % 256 == 0) ? 256 : (a.N >= 192 ? 192 : 128));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (a.operands_mn_major) {
+    if (a.epilogue != PXA_EPI_BIAS_RESIDUAL || a.out_dtype != PXA_DTYPE_F32 || a.residual != a.out || a.bias || a.gate ||
+        a.out_aux_bf16)
+      return fail(PXA_ERR_ARG, "operands_mn_major is the weight-gradient form: EPI_BIAS_RESIDUAL, fp32 out, residual == out, "
+                               "no bias / gate / aux");
+    switch (bn) {
+      case 128: return launch_wgrad<128>(a, s);
+      case 192: return launch_wgrad<192>(a, s);
+      case 256: return launch_wgrad<256>(a, s);
+      default: return fail(PXA_ERR_ARG, "block_n must be 0, 128, 192 or 256 (got %d)", bn);
+    }
+  }
   if (a.epilogue == PXA_EPI_BIAS_RESIDUAL && a.residual == nullptr) return fail(PXA_ERR_ARG, "EPI_BIAS_RESIDUAL needs residual");
   if (a.epilogue != PXA_EPI_BIAS_RESIDUAL && a.out_dtype != PXA_DTYPE_BF16)
     return fail(PXA_ERR_ARG, "EPI_BIAS / EPI_BIAS_GELU write bf16 only");

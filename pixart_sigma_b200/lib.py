@@ -29,7 +29,8 @@ class GemmArgs(C.Structure):
                 ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
                 ("lda", C.c_int32), ("ldw", C.c_int32), ("ldo", C.c_int32),
                 ("epilogue", C.c_int32), ("out_dtype", C.c_int32), ("block_n", C.c_int32), ("max_ctas", C.c_int32),
-                ("cta_pair", C.c_int32), ("debug_trace", C.c_void_p)]
+                ("cta_pair", C.c_int32), ("debug_trace", C.c_void_p), ("operands_mn_major", C.c_int32),
+                ("k_splits", C.c_int32), ("aux_is_branch", C.c_int32)]
 
 
 class LnModArgs(C.Structure):
@@ -160,7 +161,8 @@ def _dt(dtype: torch.dtype) -> int:
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, *,
          epilogue: int = EPI_BIAS, residual: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
          gate_batch_stride: int = 0, rows_per_batch: int = 0, out_aux: Optional[torch.Tensor] = None,
-         block_n: int = 0, max_ctas: int = 0, cta_pair: int = 0, debug_trace: Optional[torch.Tensor] = None) -> torch.Tensor:
+         block_n: int = 0, max_ctas: int = 0, cta_pair: int = 0, debug_trace: Optional[torch.Tensor] = None,
+         aux_is_branch: bool = False) -> torch.Tensor:
     """out = epilogue(a @ w.T + bias). a (M,K) bf16, w (N,K) bf16 (nn.Linear layout), both K-contiguous."""
     assert a.is_cuda and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1 and out.dim() == 2 and out.stride(1) == 1
@@ -179,7 +181,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
                     residual=_ptr(residual), gate=_ptr(gate), gate_batch_stride=gate_batch_stride,
                     rows_per_batch=rows_per_batch or M, M=M, N=N, K=K, lda=a.stride(0), ldw=w.stride(0),
                     ldo=out.stride(0), epilogue=epilogue, out_dtype=_dt(out.dtype), block_n=block_n, max_ctas=max_ctas,
-                    cta_pair=cta_pair, debug_trace=_ptr(debug_trace))
+                    cta_pair=cta_pair, debug_trace=_ptr(debug_trace), operands_mn_major=0, k_splits=0,
+                    aux_is_branch=int(aux_is_branch))
     _check(load().pxa_gemm_bf16(C.byref(args), _stream()), "pxa_gemm_bf16")
     return out
 
@@ -343,3 +346,21 @@ def flash_attn_bwd(q, k, v, o, d_o, lse, dq, dk, dv, *, B: int, H: int, Nq: int,
                        ldo=o.stride(0), lddo=d_o.stride(0), kv_rows=kv_rows, B=B, H=H, Nq=Nq, Nk=Nk,
                        scale=scale if scale is not None else 72 ** -0.5)
     _check(load().pxa_flash_attn_d72_bwd_bf16(C.byref(args), _stream()), "pxa_flash_attn_d72_bwd_bf16")
+
+
+def gemm_wgrad(a_t: torch.Tensor, w_t: torch.Tensor, out: torch.Tensor, *, block_n: int = 0, k_splits: int = 0,
+               max_ctas: int = 0) -> torch.Tensor:
+    """out (M, N) fp32 += a_t^T @ w_t with a_t (K, M) and w_t (K, N) bf16 row-major -- the weight gradient
+    dW (N_out, K_in) += dY (rows, N_out)^T @ X (rows, K_in) straight from the activations (MN-major UMMA operands, split-K,
+    TMA reduce-add into `out`)."""
+    assert a_t.dtype == w_t.dtype == torch.bfloat16 and out.dtype == torch.float32
+    assert a_t.dim() == 2 and w_t.dim() == 2 and a_t.stride(1) == 1 and w_t.stride(1) == 1 and out.stride(1) == 1
+    K, M = a_t.shape
+    N = w_t.shape[1]
+    assert w_t.shape[0] == K and out.shape == (M, N)
+    args = GemmArgs(a=_ptr(a_t), w=_ptr(w_t), bias=None, out=_ptr(out), out_aux_bf16=None, residual=_ptr(out), gate=None,
+                    gate_batch_stride=0, rows_per_batch=M, M=M, N=N, K=K, lda=a_t.stride(0), ldw=w_t.stride(0),
+                    ldo=out.stride(0), epilogue=EPI_BIAS_RESIDUAL, out_dtype=DTYPE_F32, block_n=block_n, max_ctas=max_ctas,
+                    cta_pair=1, debug_trace=None, operands_mn_major=1, k_splits=k_splits, aux_is_branch=0)
+    _check(load().pxa_gemm_bf16(C.byref(args), _stream()), "pxa_gemm_bf16 (wgrad)")
+    return out

@@ -534,7 +534,9 @@ class PixArtMS(nn.Module):
         for blk in self.blocks:
             mod = blk.scale_shift_table.float()[None] + t0
             if getattr(blk, "grad_checkpointing", False):
-                x32 = checkpoint(ag.block_forward_train, blk, x32, cond, kv_len, None, L, mod, B, N, use_reentrant=False)
+                # per-call dict: lets the recomputation reuse the attention outputs of the first pass (autograd.py)
+                x32 = checkpoint(ag.block_forward_train, blk, x32, cond, kv_len, None, L, mod, B, N, {},
+                                 use_reentrant=False)
             else:
                 x32 = ag.block_forward_train(blk, x32, cond, kv_len, None, L, mod, B, N)
 

@@ -111,6 +111,43 @@ def test_linear_backward_on_the_forward_gemm():
     assert po.rel_err(dw - 0.5, dy.float().t() @ x.float()) < 2e-4
 
 
+@pytest.mark.parametrize("rows,n_out,k_in,bn,ks", [
+    (2048, 1152, 1152, 0, 0), (2048, 3456, 1152, 0, 1), (4096, 1152, 4608, 256, 0), (377, 2304, 1152, 0, 0),
+    (1200, 1152, 4096, 128, 3), (16384, 1152, 1152, 192, 0), (64, 128, 64, 128, 0), (8192, 4608, 1152, 0, 5),
+])
+def test_gemm_weight_gradient_form(rows, n_out, k_in, bn, ks):
+    """dW (n_out, k_in) += dY (rows, n_out)^T X (rows, k_in): MN-major operands straight from the activations, split-K."""
+    dy, x = _randn(rows, n_out, seed=40), _randn(rows, k_in, seed=41)
+    dw = torch.full((n_out, k_in), 0.25, dtype=torch.float32, device=DEV)
+    lib.gemm_wgrad(dy, x, dw, block_n=bn, k_splits=ks)
+    assert po.rel_err(dw - 0.25, dy.float().t() @ x.float()) < 2e-4
+    dy3 = _randn(rows, 3 * n_out, seed=42)                      # operands may be column slices (row-strided views)
+    dw.zero_()
+    lib.gemm_wgrad(dy3[:, n_out:2 * n_out], x, dw, block_n=bn, k_splits=ks)
+    assert po.rel_err(dw, dy3[:, n_out:2 * n_out].float().t() @ x.float()) < 2e-4
+
+
+@pytest.mark.parametrize("K", [1152, 4608])
+def test_gemm_residual_epilogue_keeps_the_branch_output(K):
+    """Training forward of `x + gate * (a W^T + b)`: out-of-place fp32 residual epilogue whose bf16 aux output is the
+    un-gated branch (needed by the gate's backward); K=1152 takes the TMA-streamed single-CTA kernel, 4608 the CTA pair."""
+    B, N, C = 2, 1024, 1152
+    M = B * N
+    a, w, bias = _randn(M, K, seed=50), _randn(C, K, seed=51, scale=K ** -0.5), _randn(C, seed=52, scale=0.1)
+    x = _randn(M, C, seed=53, dtype=torch.float32)
+    mod = _randn(B, 6, C, seed=54, dtype=torch.float32)
+    out = torch.empty_like(x)
+    y = torch.empty(M, C, dtype=torch.bfloat16, device=DEV)
+    x_before = x.clone()
+    lib.gemm(a, w, bias, out, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x, gate=mod[:, 2], gate_batch_stride=mod.stride(0),
+             rows_per_batch=N, out_aux=y, aux_is_branch=True)
+    branch = F.linear(a.float(), w.float(), bias.float())
+    want = x_before.view(B, N, C) + mod[:, 2][:, None] * branch.view(B, N, C)
+    assert torch.equal(x, x_before)                                  # the residual input is not touched
+    assert po.rel_err(out, want.view(M, C)) < 2e-4
+    assert po.rel_err(y.float(), branch) < 4e-3
+
+
 def _attn_ref(q, k, v, lens, scale):
     """fp32 autograd reference: q (B,Nq,H,D), k/v (B,Nk,H,D) padded, sample b sees keys < lens[b]."""
     outs = []

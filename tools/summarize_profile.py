@@ -4,9 +4,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
-lines = [f"# ncu summary {tag}", "", "Command: `bench.py --steps 2 --warmup 3` (launch list) / `--steps 1` (`--set full`, GEMM + attention kernels), "
-         "workload c3 (1024px, forward batch 8), one B200, `--clock-control none`. Per-launch times under ncu are cold-cache and "
-         "serialised: compare SHARES.", ""]
+if tag.startswith("c5"):
+    lines = [f"# ncu summary {tag} (training step)", "", "Command: `tools/train_profile.py --depth 4` (launch list of ONE training step: IDDPM loss "
+             "fwd + bwd, activation checkpointing, 1024px, 4 images, 4096 tokens) / `--depth 1` (`--set full` on the backward "
+             "kernels), one B200, `--clock-control none`, `--profile-from-start off`. Per-launch times under ncu are cold-cache "
+             "and serialised: compare SHARES.", ""]
+else:
+    lines = [f"# ncu summary {tag}", "", "Command: `bench.py --steps 2 --warmup 3` (launch list) / `--steps 1` (`--set full`, GEMM + attention kernels), "
+             "workload c3 (1024px, forward batch 8), one B200, `--clock-control none`. Per-launch times under ncu are cold-cache and "
+             "serialised: compare SHARES.", ""]
 lp = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
 if os.path.exists(lp):
     rows = [l for l in open(lp) if not l.startswith("==")]
@@ -20,7 +26,7 @@ if os.path.exists(lp):
         agg[k][0] += 1; agg[k][1] += v
     tot = sum(v[1] for v in agg.values())
     lines += ["## Launch list (gpu__time_duration.sum)", "", "| share | launches | avg us | kernel |", "|---|---|---|---|"]
-    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:12]:
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:24 if tag.startswith('c5') else 12]:
         lines.append(f"| {100 * v[1] / tot:.2f}% | {v[0]} | {v[1] / v[0]:.1f} | `{k}` |")
     lines.append(f"\nTotal {tot / 1e3:.2f} ms over {sum(v[0] for v in agg.values())} launches.\n")
     with open(os.path.join(out_dir, f"{tag}_launches.csv"), "w") as f:
@@ -52,7 +58,7 @@ if os.path.exists(rp):
         v = float(v.replace(",", ""))
         return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
     gem = [r for r in rows[2:] if "gemm" in r[idx["Kernel Name"]]]
-    if gem:
+    if gem and not tag.startswith("c5"):
         import json
         tot = [to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) +
                to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]]) for r in gem]
