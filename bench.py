@@ -428,12 +428,16 @@ def run_train(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = {}
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t_host = time.perf_counter()
         for i in range(steps):
             fn(i)
+        host_ms[fn.__name__] = (time.perf_counter() - t_host) * 1000.0 / steps     # host time to ENQUEUE a step (no sync)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -496,7 +500,8 @@ def run_train(args, wl):
                                           f"{len(reducer.buckets)} buckets, overlapped with backward)",
                            "grad_checkpointing": not args.no_checkpoint, "optimizer_step": "not included (fwd + bwd + all-reduce, as configs[4] states)",
                            "l2": "working set (2.4 GB fp32 weights + activations) larger than L2; no flush needed",
-                           "tflop_model_per_step_per_gpu": 3 * fwd / 1e12, "peak_mem_gib": peak_mem, "loss": float(loss0)},
+                           "tflop_model_per_step_per_gpu": 3 * fwd / 1e12, "peak_mem_gib": peak_mem, "loss": float(loss0),
+                           "host_enqueue_ms_per_step": host_ms.get("step_resident")},
                 "e2e": {"value": imgs * world * args.steps / (ms_e2e / 1000.0), "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": None}

@@ -17,7 +17,7 @@
 // columns they came from) with the streamed tile consumed MN-major in its natural [row, d] layout (N = 80: main + tail).
 //
 // 384 threads: warp 0 TMA producer, warp 1 MMA issuer (one elected thread), warp 2 TMEM allocator, warps 4-11 the
-// elementwise stage: thread = (TMEM lane, column half) -> 32 columns of S' and dP' per sub-block.
+// elementwise stage (8 or 16 warps): thread = (TMEM lane, column slice) -> 64 / kBEw columns of S' and dP' per sub-block.
 // The unit of work is a 64-row SUB-BLOCK of the stream (one TMA stage, 4-deep ring).  S' and dP' each have two 64-column
 // TMEM buffers used as a double buffer, exactly like the forward kernel: while the elementwise threads turn S'(n), dP'(n)
 // into P'(n), dS'(n), the tensor pipe already computes the scores of sub-block n+1 into the other buffer, and as soon as
@@ -28,12 +28,22 @@
 //
 // Algorithmic work: dKV pass 8 * Nq * Nk * 72 FLOP, dQ pass 6 * Nq * Nk * 72 FLOP per (sample, head) (model FLOPs of the
 // attention backward: 10 * Nq * Nk * 72 -- the difference is the recomputation).  Requires Nq % 128 == 0.
+#include <type_traits>
+
 #include "host_common.cuh"
 #include "ptx.cuh"
 
 namespace pxa {
 
-constexpr int kBwdThreads = 384;
+// Elementwise warps per TMEM sub-partition (2 or 4): thread = (TMEM lane, 64 / kBEw column slice).  4 warps per
+// sub-partition hide the TMEM load / MUFU / TMEM store latencies of the slice-serial elementwise stage much better than 2.
+#ifndef PXA_BWD_EW
+#define PXA_BWD_EW 4
+#endif
+constexpr int kBEw = PXA_BWD_EW;
+constexpr int kBEwThreads = 128 * kBEw;        // elementwise threads
+constexpr int kBCols = 64 / kBEw;      // score columns per thread per sub-block
+constexpr int kBwdThreads = 128 + kBEwThreads;
 constexpr int kBT = 128;                       // rows per tile (both stationary and streamed)
 constexpr int kBSub = 64;                      // streamed rows per sub-block (= TMA stage)
 constexpr int kBMain = 128 * 128;              // stationary: 128 rows x 64 bf16
@@ -48,10 +58,16 @@ constexpr int kBOffStat = kBOffY + kBStages * 2 * kBYTile;  // 2 buffers x (lse[
 constexpr int kBOffBars = kBOffStat + 1024;
 constexpr int kBwdSmem = kBOffBars + 256 + 1024;            // + alignment slack
 
-constexpr uint32_t kBColS = 0;       // S'  two 64-column buffers; bf16 P' over the first 16 columns of each 32-column half
+constexpr uint32_t kBColS = 0;       // S'  two 64-column buffers; each thread's bf16 P' over the first half of its own column slice
 constexpr uint32_t kBColDP = 128;    // dP' (same, dS')
 constexpr uint32_t kBColAcc2 = 256;  // dK (dKV pass) / dQ (dQ pass): 80 columns
 constexpr uint32_t kBColAcc1 = 384;  // dV (dKV pass): 80 columns
+
+// size-overloaded TMEM accessors so that the elementwise stage is written once for 32 or 16 columns per thread
+PXA_DEVICE void ld_scores(uint32_t t0, uint32_t (&a)[32], uint32_t t1, uint32_t (&b)[32]) { tmem_ld_32x32b_x32_pair(t0, a, t1, b); }
+PXA_DEVICE void ld_scores(uint32_t t0, uint32_t (&a)[16], uint32_t t1, uint32_t (&b)[16]) { tmem_ld_32x32b_x16_pair(t0, a, t1, b); }
+PXA_DEVICE void st_packed(uint32_t t, const uint32_t (&r)[16]) { tmem_st_32x32b_x16(t, r); }
+PXA_DEVICE void st_packed(uint32_t t, const uint32_t (&r)[8]) { tmem_st_32x32b_x8(t, r); }
 
 struct AttnBwdParams {
   const float* lse;        // [B, H, Nq] log2-domain log-sum-exp written by the forward kernel
@@ -79,10 +95,10 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
   uint64_t* y_full = bars + 1;                 // [kBStages]  TMA -> MMA
   uint64_t* y_empty = y_full + kBStages;       // [kBStages]  MMA -> TMA
   uint64_t* s_full = y_empty + kBStages;       // [2]  MMA -> elementwise: S' and dP' of a sub-block are in buffer hh
-  uint64_t* p_full = s_full + 2;               // [2]  elementwise -> MMA: P' / dS' written over buffer hh (256 arrivals)
+  uint64_t* p_full = s_full + 2;               // [2]  elementwise -> MMA: P' / dS' written over buffer hh (kBEwThreads arrivals)
   uint64_t* acc_full = p_full + 2;             // [1]  MMA -> epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
-  float* stat = reinterpret_cast<float*>(smem + kBOffStat);     // [2][128]: lse[64] | delta[64] of a streamed q sub-block
+  float* stat = reinterpret_cast<float*>(smem + kBOffStat);     // [2][128]: -lse[64] | delta[64] of a streamed q sub-block
 
   const int warp = warp_idx_sync();
   const int lane = threadIdx.x & 31;
@@ -107,7 +123,7 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 256);
+      mbar_init(&p_full[i], kBEwThreads);
     }
     mbar_init(acc_full, 1);
     fence_mbar_init();
@@ -157,13 +173,15 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
         const uint64_t yt = make_smem_desc(y + kBYMain, 16, 1024, kLayoutSW128);
         umma_ss(d, xt, yt, idesc_s, 1u);
       };
-      // gradient product acc += A Y: A = bf16 P' / dS' in TMEM (K-step k of 16 streamed rows at packed columns
-      // 32 (k / 2) + 8 (k % 2): each 32-column half holds its own 16 packed columns), Y MN-major (main + tail atoms LBO apart)
+      // gradient product acc += A Y: A = bf16 P' / dS' in TMEM (K-step k of 16 streamed rows at packed column offset
+      // kBCols * (16 k / kBCols) + (16 k % kBCols) / 2: each thread's column slice holds its own packed columns at its
+      // start), Y MN-major (main + tail atoms LBO apart)
       auto issue_grad = [&](uint32_t acc, uint32_t a_tmem, uint32_t y, bool first) {
         const uint64_t yd = make_smem_desc(y, kBYMain, 1024, kLayoutSW128);
 #pragma unroll
         for (int k = 0; k < kBSub / 16; ++k)
-          umma_ts(acc, a_tmem + 32 * (k >> 1) + 8 * (k & 1), yd + (uint64_t)(k * (2048 >> 4)), idesc_g, (first && k == 0) ? 0u : 1u);
+          umma_ts(acc, a_tmem + kBCols * ((16 * k) / kBCols) + ((16 * k) % kBCols) / 2, yd + (uint64_t)(k * (2048 >> 4)), idesc_g,
+                  (first && k == 0) ? 0u : 1u);
       };
       // S'(n), dP'(n) into score buffer n & 1
       auto issue_scores = [&](int n) {
@@ -192,83 +210,92 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
     }
   } else if (warp >= 4) {
     // ================================================================ elementwise stage + epilogue
-    const int tid = threadIdx.x - 128;             // 0..255
-    const int half = (warp - 4) >> 2;              // which 32 of a sub-block's 64 streamed rows (score columns)
+    const int tid = threadIdx.x - 128;             // 0 .. kBEwThreads - 1
+    const int half = (warp - 4) >> 2;              // which kBCols-wide slice of a sub-block's 64 score columns
     const int qd = warp & 3;                       // TMEM sub-partition this warp may access
     const int row = qd * 32 + lane;                // stationary row (TMEM lane)
     const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
     const float sl2 = p.scale_log2;
     const size_t stat_base = ((size_t)b * p.H + h) * p.Nq;
-    float lse_r = 0.f, delta_r = 0.f;
-    if (!kDKV) {                                   // statistics of this thread's query row
+    const uint64_t sl2x2 = f32x2(sl2, sl2);
+    uint64_t nlse2 = 0, delta2 = 0;                // dQ pass: (-lse, -lse) and (delta, delta) of this thread's query row
+    if (!kDKV) {
       const int qrow = min(t0 + row, p.Nq - 1);
-      lse_r = p.lse[stat_base + qrow];
-      delta_r = p.delta[stat_base + qrow];
-    } else if (n_iter > 0) {                       // statistics of the first streamed query sub-block -> smem buffer 0
-      if (tid < 128) stat[tid] = tid < 64 ? p.lse[stat_base + tid] : p.delta[stat_base + tid - 64];
-      named_bar_sync(1, 256);
+      const float l = -p.lse[stat_base + qrow], d = p.delta[stat_base + qrow];
+      nlse2 = f32x2(l, l);
+      delta2 = f32x2(d, d);
+    } else if (n_iter > 0) {                       // -lse | delta of the first streamed query sub-block -> smem buffer 0
+      if (tid < 128) stat[tid] = tid < 64 ? -p.lse[stat_base + tid] : p.delta[stat_base + tid - 64];
+      named_bar_sync(1, kBEwThreads);
     }
 
     for (int n = 0; n < n_iter; ++n) {
       const int hh = n & 1;
-      const uint32_t t_s = tmem_base + kBColS + lane_sel + kBSub * hh + 32 * half;
-      const uint32_t t_dp = tmem_base + kBColDP + lane_sel + kBSub * hh + 32 * half;
+      const uint32_t t_s = tmem_base + kBColS + lane_sel + kBSub * hh + kBCols * half;
+      const uint32_t t_dp = tmem_base + kBColDP + lane_sel + kBSub * hh + kBCols * half;
       float nxt = 0.f;
       if (kDKV && n + 1 < n_iter && tid < 128) {   // next sub-block's statistics: global load in flight during this one
         const size_t o = stat_base + (size_t)(n + 1) * kBSub + (tid & 63);
-        nxt = tid < 64 ? p.lse[o] : p.delta[o];
+        nxt = tid < 64 ? -p.lse[o] : p.delta[o];
       }
-      const float* st = stat + (n & 1) * 128 + 32 * half;      // lse of this thread's 32 columns; delta 64 floats further
+      const float* st = stat + (n & 1) * 128 + kBCols * half;  // lse of this thread's columns; delta 64 floats further
       // dQ pass: streamed rows are keys, the sample's last sub-block may be partial
-      const int rem = kDKV ? (1 << 30) : kv_len - n * kBSub - 32 * half;
+      const int rem = kDKV ? (1 << 30) : kv_len - n * kBSub - kBCols * half;
       mbar_wait(&s_full[hh], (n >> 1) & 1);
       tc_fence_after();
-      uint32_t vs[32], vd[32];
-      tmem_ld_32x32b_x32_pair(t_s, vs, t_dp, vd);
-      uint32_t pp[16], pd[16];
+      uint32_t vs[kBCols], vd[kBCols];
+      ld_scores(t_s, vs, t_dp, vd);
+      uint32_t pp[kBCols / 2], pd[kBCols / 2];
+      // packed fp32 pairs (FFMA2 / FADD2 / FMUL2: one issue slot for two elements), exp2 on the MUFU pipe.  The masking
+      // selects exist only in the copy of the loop taken by a partial last sub-block of the dQ pass.
+      auto compute = [&](auto masked_tag) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        float4 l4, d4;
-        if (kDKV) {
-          l4 = *reinterpret_cast<const float4*>(st + i);
-          d4 = *reinterpret_cast<const float4*>(st + 64 + i);
-        } else {
-          l4 = make_float4(lse_r, lse_r, lse_r, lse_r);
-          d4 = make_float4(delta_r, delta_r, delta_r, delta_r);
+        for (int i = 0; i < kBCols; i += 2) {
+          uint64_t nl, dl;
+          if (kDKV) {
+            const float2 l2 = *reinterpret_cast<const float2*>(st + i);          // -lse of the two columns
+            const float2 d2 = *reinterpret_cast<const float2*>(st + 64 + i);     // delta
+            nl = f32x2(l2.x, l2.y);
+            dl = f32x2(d2.x, d2.y);
+          } else {
+            nl = nlse2;
+            dl = delta2;
+          }
+          const uint64_t x = fma2(f32x2(__uint_as_float(vs[i]), __uint_as_float(vs[i + 1])), sl2x2, nl);
+          float x0, x1;
+          f32x2_split(x, x0, x1);
+          float e0 = fast_exp2(x0), e1 = fast_exp2(x1);
+          if constexpr (decltype(masked_tag)::value) {
+            if (i >= rem) e0 = 0.f;
+            if (i + 1 >= rem) e1 = 0.f;
+          }
+          const uint64_t g = mul2(f32x2(e0, e1), sub2(f32x2(__uint_as_float(vd[i]), __uint_as_float(vd[i + 1])), dl));
+          float g0, g1;
+          f32x2_split(g, g0, g1);
+          pp[i / 2] = pack_bf16x2(e0, e1);
+          pd[i / 2] = pack_bf16x2(g0, g1);
         }
-        const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
-        const float ds[4] = {d4.x, d4.y, d4.z, d4.w};
-        float pr[4], gr[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float pv = fast_exp2(fmaf(__uint_as_float(vs[i + e]), sl2, -ls[e]));
-          if (i + e >= rem) pv = 0.f;
-          pr[e] = pv;
-          gr[e] = pv * (__uint_as_float(vd[i + e]) - ds[e]);
-        }
-        pp[i / 2] = pack_bf16x2(pr[0], pr[1]);
-        pp[i / 2 + 1] = pack_bf16x2(pr[2], pr[3]);
-        pd[i / 2] = pack_bf16x2(gr[0], gr[1]);
-        pd[i / 2 + 1] = pack_bf16x2(gr[2], gr[3]);
-      }
-      // bf16 results over the fp32 columns this thread has just consumed (its own 32 columns: no cross-warp hazard)
-      if (kDKV) tmem_st_32x32b_x16(t_s, pp);
-      tmem_st_32x32b_x16(t_dp, pd);
+      };
+      if (!kDKV && rem < kBCols) compute(std::true_type{});
+      else compute(std::false_type{});
+      // bf16 results over the fp32 columns this thread has just consumed (its own slice: no cross-warp hazard)
+      if (kDKV) st_packed(t_s, pp);
+      st_packed(t_dp, pd);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[hh]);
       if (kDKV) {
         if (n + 1 < n_iter && tid < 128) stat[((n + 1) & 1) * 128 + tid] = nxt;
-        named_bar_sync(1, 256);
+        named_bar_sync(1, kBEwThreads);
       }
     }
 
-    // ---- epilogue: half 0 writes acc2 (dK / dQ, times the softmax scale), half 1 writes acc1 (dV, dKV pass only)
+    // ---- epilogue: column slice 0 writes acc2 (dK / dQ, times the softmax scale), slice 1 writes acc1 (dV, dKV pass only)
     if (n_iter > 0) {
       mbar_wait(acc_full, 0);
       tc_fence_after();
     }
-    if (half == 0 || kDKV) {
+    if (half == 0 || (kDKV && half == 1)) {
       const uint32_t t_acc = tmem_base + (half == 0 ? kBColAcc2 : kBColAcc1) + lane_sel;
       const float mul = half == 0 ? p.scale : 1.0f;
       const bool row_ok = kDKV ? (t0 + row < kv_len) : (t0 + row < p.Nq);
