@@ -414,12 +414,21 @@ def run_train(args, wl):
     h_noise = torch.randn(imgs, 4, side, side, generator=g).pin_memory()
     d_x, d_y, d_mask, d_t, d_noise = (v.to(dev) for v in (h_x, h_y, h_mask, h_t, h_noise))
 
+    graphed = None
+    if args.cuda_graph:
+        from pixart_sigma_b200.training import GraphedTrainStep
+        graphed = GraphedTrainStep(model, loss_fn, reducer, (d_x, d_t, d_y, d_mask, d_noise))
+
     def step_resident(i):
+        if graphed is not None:
+            return graphed(d_x, d_t, d_y, d_mask, d_noise)
         reducer.zero_grad()
         return train_step(model, loss_fn, d_x, d_t, d_y, d_mask, noise=d_noise, reducer=reducer)
 
     def step_e2e(i):
         x, y, mk, t, nz = (v.to(dev, non_blocking=True) for v in (h_x, h_y, h_mask, h_t, h_noise))
+        if graphed is not None:
+            return float(graphed(x, t, y, mk, nz))
         reducer.zero_grad()
         return float(train_step(model, loss_fn, x, t, y, mk, noise=nz, reducer=reducer))     # loss read back: D2H + sync
 
@@ -453,15 +462,21 @@ def run_train(args, wl):
     _ab, _wg = lib.flash_attn_bwd, lib.gemm_wgrad
     lib.flash_attn_bwd = lambda *a, **k: timer._wrap("attn_bwd", _ab, a, k)
     lib.gemm_wgrad = lambda *a, **k: timer._wrap("gemm", _wg, a, k)
+    n_pre = lib.launch_count()
+    reducer.zero_grad()
+    train_step(model, loss_fn, d_x, d_t, d_y, d_mask, noise=d_noise, reducer=reducer)     # eager: kernel launches of one step
+    launches_eager = lib.launch_count() - n_pre
     for i in range(max(args.warmup, 3)):
         loss0 = step_resident(i)
     step_e2e(0)
     sampler = ClockSampler(local) if rank == 0 else None
     n0 = lib.launch_count()
-    timer.on = True
+    timer.on = graphed is None                      # per-kernel events are not available inside a graph replay
     ms = timed(step_resident, args.steps)
     timer.on = False
     launches = lib.launch_count() - n0
+    if graphed is not None:
+        launches = launches_eager * args.steps       # graph replays bypass the library's host-side counter
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if sampler else None
     peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
@@ -498,7 +513,7 @@ def run_train(args, wl):
                 "config": {"workload": f"c5: {desc}", "images_per_gpu": imgs, "tokens_per_sample": n_tok, "text_tokens": L,
                            "parallelism": f"ddp{world} (bucketed NCCL all-reduce of {reducer.grad_bytes() / 1e9:.2f} GB fp32 grads, "
                                           f"{len(reducer.buckets)} buckets, overlapped with backward)",
-                           "grad_checkpointing": not args.no_checkpoint, "optimizer_step": "not included (fwd + bwd + all-reduce, as configs[4] states)",
+                           "grad_checkpointing": not args.no_checkpoint, "cuda_graph": bool(args.cuda_graph), "optimizer_step": "not included (fwd + bwd + all-reduce, as configs[4] states)",
                            "l2": "working set (2.4 GB fp32 weights + activations) larger than L2; no flush needed",
                            "tflop_model_per_step_per_gpu": 3 * fwd / 1e12, "peak_mem_gib": peak_mem, "loss": float(loss0),
                            "host_enqueue_ms_per_step": host_ms.get("step_resident")},

@@ -229,6 +229,23 @@ typedef struct PxaLnModBwdArgs {
 } PxaLnModBwdArgs;
 int pxa_ln_modulate_bwd(const PxaLnModBwdArgs* args, void* stream);
 
+/* Backward of pxa_kv_compress_conv2_ln (depthwise conv k=s=2 + LayerNorm(affine) on K and V, PixArt_blocks.py:84-89,
+ * 115-117): input gradients written to the 4 input rows of every output token, parameter gradients (shared by K and V)
+ * ACCUMULATED into fp32 buffers (atomics).  The LN bias does not influence any gradient and is not needed. */
+typedef struct PxaKvCompressBwdArgs {
+  const void* k_in; const void* v_in;     /* bf16 forward inputs, token row stride ld_in                           */
+  const void* dk_out; const void* dv_out; /* bf16 [B, (H/2)*(W/2), C] gradients of the compressed K / V             */
+  void* dk_in; void* dv_in;               /* bf16 gradients of the inputs, token row stride ld_din (written)        */
+  const void* conv_w; const void* conv_b; const void* ln_w;   /* bf16 parameters as in the forward                  */
+  float* d_conv_w;      /* fp32 [C, 1, 2, 2] accumulated */
+  float* d_conv_b;      /* fp32 [C] accumulated           */
+  float* d_ln_w;        /* fp32 [C] accumulated           */
+  float* d_ln_b;        /* fp32 [C] accumulated           */
+  int32_t B, H, W, C, ld_in, ld_din;
+  float eps;
+} PxaKvCompressBwdArgs;
+int pxa_kv_compress_conv2_ln_bwd(const PxaKvCompressBwdArgs* args, void* stream);
+
 /* out[c] += sum_r a[r, c]  (bias gradients; a bf16 [M, N] row stride lda, N % 8 == 0; out fp32 [N], atomics). */
 int pxa_colsum_bf16(const void* a, float* out, int32_t M, int32_t N, int64_t lda, void* stream);
 
@@ -238,7 +255,7 @@ int pxa_attn_delta_d72(const void* o, const void* d_o, float* delta, int32_t B, 
 
 /* Backward of pxa_flash_attn_d72_bf16: dq, dk, dv from (q, k, v, o, dO, lse).  Flash-attention-2 recomputation on
  * tcgen05 (two passes: dK/dV per key tile, dQ per query tile); nothing N x N reaches HBM.  Same addressing as the
- * forward (strided bf16 views, packed var-len keys through kv_off / kv_len).  Requires Nq % 128 == 0.
+ * forward (strided bf16 views, packed var-len keys through kv_off / kv_len), any Nq / Nk.
  * dk / dv rows of keys >= kv_len[b] are not written.  `delta` is caller-owned workspace.                         */
 typedef struct PxaAttnBwdArgs {
   const void* q; const void* k; const void* v;   /* as PxaAttnArgs                                              */

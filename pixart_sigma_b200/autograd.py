@@ -10,8 +10,9 @@ tape: every node below calls into libpixart_sm100.so in both directions --
   LnModulateFn    LN(x)(1+scale)+shift    bwd: pxa_ln_modulate_bwd (dx, d shift, d scale)            PixArtMS.py:75,77
   GateResidualFn  x + gate * y            bwd: pxa_gate_residual_bwd (dy, d gate)                    PixArtMS.py:75-77
   GeluFn          gelu_tanh(pre)          bwd: pxa_gelu_tanh_bf16 with dh                            timm Mlp.act
-  SelfAttnFn / CrossAttnFn                bwd: pxa_flash_attn_d72_bwd_bf16 (flash-attention-2 recomputation from lse)
+  SelfAttnFn / CrossAttnFn / AttnKVFn     bwd: pxa_flash_attn_d72_bwd_bf16 (flash-attention-2 recomputation from lse)
                                                                                                 PixArt_blocks.py:52-53,153
+  KvCompressFn    LN(conv2x2s2(k | v))    bwd: pxa_kv_compress_conv2_ln_bwd                       PixArt_blocks.py:97-121
 
 Parameters may be fp32 (mixed-precision training, `train.py:369` accelerator mixed_precision) or bf16; the kernels
 always consume bf16 shadows, cached per parameter version, and gradients are produced in fp32 and cast to the
@@ -39,10 +40,41 @@ def _shadow(mod: torch.nn.Module, kind: str) -> Optional[torch.Tensor]:
     if hit is not None and hit[0] == tag:
         return hit[1]
     src = p.detach()
-    w16 = (src if src.dtype == torch.bfloat16 else src.to(torch.bfloat16)).contiguous()
-    val = lib.transpose(w16) if kind == "t" else w16
+    old = hit[1] if hit is not None and hit[1].device == p.device and hit[1].data_ptr() != p.data_ptr() else None
+    if kind == "t":
+        w16 = (src if src.dtype == torch.bfloat16 else src.to(torch.bfloat16)).contiguous()
+        val = lib.transpose(w16, old if old is not None and old.shape == (w16.shape[1], w16.shape[0]) else None)
+    elif src.dtype == torch.bfloat16 and src.is_contiguous():
+        val = src                                         # a bf16 parameter is its own shadow
+    elif old is not None and old.shape == src.shape:
+        val = old.copy_(src)                              # refresh in place: buffers stay valid for captured graphs
+    else:
+        val = src.to(torch.bfloat16).contiguous()
     cache[kind] = (tag, val)
     return val
+
+
+def refresh_shadows(model: torch.nn.Module) -> None:
+    """Recompute every existing bf16 shadow IN PLACE from its parameter (same buffers, new values).  Used as the first
+    node of a captured training step (`training.GraphedTrainStep`): replays then see optimizer updates without any
+    host-side version check."""
+    tag = lambda p: (p._version, p.data_ptr(), p.dtype, p.device)
+    for m in model.modules():
+        cache = m.__dict__.get("_pxa_shadow")
+        if not cache:
+            continue
+        for kind in ("w", "b"):
+            if kind in cache:
+                p = m.bias if kind == "b" else m.weight
+                val = cache[kind][1]
+                if val.data_ptr() != p.data_ptr():        # a real copy (fp32 parameter); bf16 parameters are their own shadow
+                    val.copy_(p.detach())
+                cache[kind] = (tag(p), val)
+        if "t" in cache:
+            p, val = m.weight, cache["t"][1]
+            w16 = cache["w"][1] if "w" in cache else p.detach().to(torch.bfloat16).contiguous()
+            lib.transpose(w16, val)
+            cache["t"] = (tag(p), val)
 
 
 def clear_shadow_cache(model: torch.nn.Module) -> None:
@@ -251,6 +283,74 @@ class SelfAttnFn(torch.autograd.Function):
         return dqkv, None, None, None, None, None
 
 
+class KvCompressFn(torch.autograd.Function):
+    """(kc, vc) = LN(conv2x2s2(k)), LN(conv2x2s2(v)) on the k / v slices of the qkv GEMM output (PixArt_blocks.py:97-121,
+    'conv' sampling, scale factor 2).  sr = the depthwise Conv2d, norm = the LayerNorm (owners of the bf16 shadows)."""
+
+    @staticmethod
+    def forward(ctx, qkv, sr_w, sr_b, ln_w, ln_b, sr, norm, B, Hh, Ww):
+        qkv = qkv.contiguous()
+        M, C3 = qkv.shape
+        C = C3 // 3
+        n_out = (Hh // 2) * (Ww // 2)
+        kc = torch.empty((B * n_out, C), dtype=torch.bfloat16, device=qkv.device)
+        vc = torch.empty_like(kc)
+        lib.kv_compress(qkv[:, C:2 * C], qkv[:, 2 * C:], kc.view(B, n_out, C), vc.view(B, n_out, C), _shadow(sr, "w"), _shadow(sr, "b"),
+                        _shadow(norm, "w"), _shadow(norm, "b"), B=B, H=Hh, W=Ww, ld_in=C3, eps=norm.eps)
+        ctx.save_for_backward(qkv, sr_w, sr_b, ln_w, ln_b)
+        ctx.mods, ctx.geom = (sr, norm), (B, Hh, Ww)
+        return kc, vc
+
+    @staticmethod
+    def backward(ctx, dkc, dvc):
+        qkv, sr_w, sr_b, ln_w, ln_b = ctx.saved_tensors
+        sr, norm = ctx.mods
+        B, Hh, Ww = ctx.geom
+        M, C3 = qkv.shape
+        C = C3 // 3
+        dqkv = torch.zeros_like(qkv)                    # the q slice gets its gradient from the attention node
+        f32 = dict(dtype=torch.float32, device=qkv.device)
+        g_w, g_b = torch.zeros(sr_w.shape, **f32), torch.zeros(sr_b.shape, **f32)
+        g_lw, g_lb = torch.zeros(ln_w.shape, **f32), torch.zeros(ln_b.shape, **f32)
+        lib.kv_compress_bwd(qkv[:, C:2 * C], qkv[:, 2 * C:], dkc.contiguous(), dvc.contiguous(), dqkv[:, C:2 * C], dqkv[:, 2 * C:],
+                            _shadow(sr, "w"), _shadow(sr, "b"), _shadow(norm, "w"), g_w, g_b, g_lw, g_lb, B=B, H=Hh, W=Ww,
+                            ld_in=C3, ld_din=C3, eps=norm.eps)
+        return (dqkv, g_w.to(sr_w.dtype), g_b.to(sr_b.dtype), g_lw.to(ln_w.dtype), g_lb.to(ln_b.dtype), None, None, None, None, None)
+
+
+class AttnKVFn(torch.autograd.Function):
+    """o = attention of the q slice of qkv (B*N, 3C) over separate, already compressed keys / values (B*Nk, C)
+    (KV-compressed self-attention, PixArt_blocks.py:137-153)."""
+
+    @staticmethod
+    def forward(ctx, qkv, kc, vc, B, H, N, Nk, scale):
+        qkv, kc, vc = qkv.contiguous(), kc.contiguous(), vc.contiguous()
+        M, C3 = qkv.shape
+        C = C3 // 3
+        D = C // H
+        o = torch.empty((M, C), dtype=torch.bfloat16, device=qkv.device)
+        lse = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device)
+        lib.flash_attn(qkv[:, :C], kc, vc, o, B=B, H=H, Nq=N, Nk=Nk, kv_rows=B * Nk, q_strides=(C3, D), k_strides=(C, D),
+                       v_strides=(C, D), scale=scale, lse=lse)
+        ctx.save_for_backward(qkv, kc, vc, o, lse)
+        ctx.geom = (B, H, N, Nk, scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        qkv, kc, vc, o, lse = ctx.saved_tensors
+        B, H, N, Nk, scale = ctx.geom
+        M, C3 = qkv.shape
+        C = C3 // 3
+        D = C // H
+        dqkv = torch.zeros_like(qkv)                    # k / v slices: gradient arrives through the compression node
+        dkc, dvc = torch.empty_like(kc), torch.empty_like(vc)
+        lib.flash_attn_bwd(qkv[:, :C], kc, vc, o, d_o.contiguous(), lse, dqkv[:, :C], dkc, dvc, B=B, H=H, Nq=N, Nk=Nk,
+                           kv_rows=B * Nk, q_strides=(C3, D), k_strides=(C, D), v_strides=(C, D), dq_strides=(C3, D),
+                           dk_strides=(C, D), dv_strides=(C, D), scale=scale)
+        return dqkv, dkc, dvc, None, None, None, None, None
+
+
 class CrossAttnFn(torch.autograd.Function):
     """o (B*N, C) = var-len attention of q (B*N, C) over the caption keys kv (rows, 2C) (PixArt_blocks.py:43-58)."""
 
@@ -295,9 +395,28 @@ def linear(x: torch.Tensor, mod: torch.nn.Linear) -> torch.Tensor:
     return LinearFn.apply(x, mod.weight, mod.bias, mod)
 
 
+def _compressed_self_attention(a, qkv: torch.Tensor, B: int, H: int, N: int, HW) -> torch.Tensor:
+    """Self-attention over compressed keys / values (PixArt_blocks.py:97-121): 'conv' (scale factor 2) runs the fused
+    conv + LN kernel and its backward; the parameter-free samplings are strided picks (pure data movement, torch)."""
+    C = qkv.shape[1] // 3
+    Hh, Ww = HW
+    sr = a.sr_ratio
+    if a.sampling == "conv":
+        if sr != 2:
+            raise NotImplementedError("conv KV compression kernel is specialised for scale_factor 2")
+        kc, vc = KvCompressFn.apply(qkv, a.sr.weight, a.sr.bias, a.norm.weight, a.norm.bias, a.sr, a.norm, B, Hh, Ww)
+    elif a.sampling == "uniform_every":
+        kc, vc = (qkv[:, i * C:(i + 1) * C].reshape(B, N, C)[:, ::sr].reshape(-1, C) for i in (1, 2))
+    elif a.sampling in ("uniform", "ave"):
+        kc, vc = (qkv[:, i * C:(i + 1) * C].reshape(B, Hh, Ww, C)[:, ::sr, ::sr].reshape(-1, C) for i in (1, 2))
+    else:
+        raise ValueError(a.sampling)
+    return AttnKVFn.apply(qkv, kc, vc, B, H, N, kc.shape[0] // B, a.scale)
+
+
 def block_forward_train(blk, x32: torch.Tensor, cond: torch.Tensor, kv_len: Optional[torch.Tensor],
                         kv_off: Optional[torch.Tensor], max_keys: int, mod: torch.Tensor, B: int, N: int,
-                        keep: Optional[dict] = None) -> torch.Tensor:
+                        keep: Optional[dict] = None, HW=None) -> torch.Tensor:
     """One PixArtMSBlock (PixArtMS.py:71-79) on the differentiable kernel ops; same arguments as `run_kernels`, but
     out of place (returns the new fp32 residual stream) so autograd / activation checkpointing can replay it.
     `keep`: per-call dict used with activation checkpointing -- the first pass stores the two attention outputs and
@@ -305,8 +424,8 @@ def block_forward_train(blk, x32: torch.Tensor, cond: torch.Tensor, kv_len: Opti
     takes them back instead of re-running the attention kernels."""
     a, ca, mlp = blk.attn, blk.cross_attn, blk.mlp
     H = a.num_heads
-    if a.sr_ratio > 1:
-        raise NotImplementedError("training with KV compression (sr_ratio > 1) has no backward kernel yet")
+    if HW is None:
+        HW = (int(N ** 0.5),) * 2
     if blk.training and blk.drop_path_rate > 0:
         raise NotImplementedError("stochastic depth (drop_path > 0) is not supported by the kernel block")
     if not isinstance(a.q_norm, torch.nn.Identity):
@@ -314,7 +433,10 @@ def block_forward_train(blk, x32: torch.Tensor, cond: torch.Tensor, kv_len: Opti
     mod = mod.contiguous()
     # (1) x += gate_msa * proj(attn(LN(x) * (1 + scale_msa) + shift_msa))                         PixArtMS.py:75
     xn = LnModulateFn.apply(x32, mod, 0, 1, N)
-    ao = SelfAttnFn.apply(linear(xn, a.qkv), B, H, N, a.scale, keep)
+    if a.sr_ratio > 1:                                                       # KV token compression, PixArt_blocks.py:137-139
+        ao = _compressed_self_attention(a, linear(xn, a.qkv), B, H, N, HW)
+    else:
+        ao = SelfAttnFn.apply(linear(xn, a.qkv), B, H, N, a.scale, keep)
     x32 = LinearGateResidualFn.apply(ao, a.proj.weight, a.proj.bias, a.proj, x32, mod, 2, N)
     # (2) x += proj(cross_attn(x, cond))                                                          PixArtMS.py:76
     qx = linear(x32.to(torch.bfloat16), ca.q_linear)

@@ -27,7 +27,7 @@
 // TMA out-of-bounds handling), both 128B-swizzled, so one staging serves the K-major and the MN-major use.
 //
 // Algorithmic work: dKV pass 8 * Nq * Nk * 72 FLOP, dQ pass 6 * Nq * Nk * 72 FLOP per (sample, head) (model FLOPs of the
-// attention backward: 10 * Nq * Nk * 72 -- the difference is the recomputation).  Requires Nq % 128 == 0.
+// attention backward: 10 * Nq * Nk * 72 -- the difference is the recomputation).  Any Nq / Nk (partial last tiles are masked).
 #include <type_traits>
 
 #include "host_common.cuh"
@@ -111,7 +111,7 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
   if (kDKV && t0 >= kv_len) return;            // block-uniform: this key tile holds no keys of the sample
   const int x_row0 = kDKV ? kv_row0 + t0 : b * p.Nq + t0;
   const int y_row0 = kDKV ? b * p.Nq : kv_row0;
-  const int n_iter = kDKV ? p.Nq / kBSub : (kv_len + kBSub - 1) / kBSub;     // 64-row sub-blocks of the stream
+  const int n_iter = ((kDKV ? p.Nq : kv_len) + kBSub - 1) / kBSub;          // 64-row sub-blocks of the stream
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tm_x1m); prefetch_tmap(&tm_x1t); prefetch_tmap(&tm_x2m); prefetch_tmap(&tm_x2t);
@@ -225,7 +225,10 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
       nlse2 = f32x2(l, l);
       delta2 = f32x2(d, d);
     } else if (n_iter > 0) {                       // -lse | delta of the first streamed query sub-block -> smem buffer 0
-      if (tid < 128) stat[tid] = tid < 64 ? -p.lse[stat_base + tid] : p.delta[stat_base + tid - 64];
+      if (tid < 128) {
+        const int qi = min(tid & 63, p.Nq - 1);
+        stat[tid] = tid < 64 ? -p.lse[stat_base + qi] : p.delta[stat_base + qi];
+      }
       named_bar_sync(1, kBEwThreads);
     }
 
@@ -235,12 +238,12 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
       const uint32_t t_dp = tmem_base + kBColDP + lane_sel + kBSub * hh + kBCols * half;
       float nxt = 0.f;
       if (kDKV && n + 1 < n_iter && tid < 128) {   // next sub-block's statistics: global load in flight during this one
-        const size_t o = stat_base + (size_t)(n + 1) * kBSub + (tid & 63);
+        const size_t o = stat_base + min((n + 1) * kBSub + (tid & 63), p.Nq - 1);    // the last sub-block may be partial
         nxt = tid < 64 ? -p.lse[o] : p.delta[o];
       }
       const float* st = stat + (n & 1) * 128 + kBCols * half;  // lse of this thread's columns; delta 64 floats further
-      // dQ pass: streamed rows are keys, the sample's last sub-block may be partial
-      const int rem = kDKV ? (1 << 30) : kv_len - n * kBSub - kBCols * half;
+      // the last sub-block of the stream (queries in the dKV pass, keys in the dQ pass) may be partial
+      const int rem = (kDKV ? p.Nq : kv_len) - n * kBSub - kBCols * half;
       mbar_wait(&s_full[hh], (n >> 1) & 1);
       tc_fence_after();
       uint32_t vs[kBCols], vd[kBCols];
@@ -276,7 +279,7 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
           pd[i / 2] = pack_bf16x2(g0, g1);
         }
       };
-      if (!kDKV && rem < kBCols) compute(std::true_type{});
+      if (rem < kBCols) compute(std::true_type{});
       else compute(std::false_type{});
       // bf16 results over the fp32 columns this thread has just consumed (its own slice: no cross-warp hazard)
       if (kDKV) st_packed(t_s, pp);
@@ -363,7 +366,6 @@ extern "C" int pxa_flash_attn_d72_bwd_bf16(const PxaAttnBwdArgs* args, void* str
   if (!a.q || !a.k || !a.v || !a.o || !a.d_o || !a.lse || !a.delta || !a.dq || !a.dk || !a.dv)
     return fail(PXA_ERR_ARG, "null pointer");
   if (a.B <= 0 || a.H <= 0 || a.Nq <= 0 || a.Nk <= 0 || a.kv_rows <= 0) return fail(PXA_ERR_ARG, "bad B/H/Nq/Nk/kv_rows");
-  if (a.Nq % 128) return fail(PXA_ERR_ARG, "the attention backward needs Nq %% 128 == 0 (got %d)", a.Nq);
   const int64_t strides[] = {a.q_sn, a.q_sh, a.k_sn, a.k_sh, a.v_sn, a.v_sh, a.ldo, a.lddo,
                              a.dq_sn, a.dq_sh, a.dk_sn, a.dk_sh, a.dv_sn, a.dv_sh};
   for (int64_t s : strides)
@@ -407,7 +409,7 @@ extern "C" int pxa_flash_attn_d72_bwd_bf16(const PxaAttnBwdArgs* args, void* str
     PXA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
     p.d2 = reinterpret_cast<__nv_bfloat16*>(a.dq); p.d2_sn = a.dq_sn; p.d2_sh = a.dq_sh;
     p.d1 = nullptr; p.d1_sn = p.d1_sh = 0;
-    dim3 grid(a.Nq / kBT, a.H, a.B);
+    dim3 grid((a.Nq + kBT - 1) / kBT, a.H, a.B);
     kern<<<grid, kBwdThreads, kBwdSmem, s>>>(qm, qt, gm, gt, kms, kts, vms, vts, p);
     launch_counter()++;
     PXA_CHECK_CUDA(cudaGetLastError());

@@ -299,6 +299,132 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
   delta[((size_t)b * H + h) * Nq + q] = s;
 }
 
+// ------------------------------------------------------------------------------------------------- KV compress backward
+// Backward of kv_compress_kernel (depthwise 2x2 / stride-2 conv + bias, LayerNorm(affine)) for K and V in one launch
+// (blockIdx.y).  One warp per OUTPUT token (same lane <-> channel mapping as the forward); the conv output is recomputed
+// from the 4 input rows into a per-warp smem row (keeps the register footprint small: the channel loops stay rolled).
+// Input gradients go straight to the 4 input rows (stride == kernel: every input token belongs to exactly one output
+// token).  The parameter gradients (conv weight [C,4], conv bias, LN weight, LN bias -- shared by K and V) are accumulated
+// per CTA in shared memory and flushed with one fp32 atomic per element per CTA.
+constexpr int kKvcRows = 4;     // output tokens per warp
+constexpr int kKvcSmem = (7 + 8) * 1152 * 4;
+PXA_DEVICE void conv_taps(const __nv_bfloat16* conv_w, int col, float (&wt)[4][4]) {
+  const uint4 w01 = __ldg(reinterpret_cast<const uint4*>(conv_w + col * 4));
+  const uint4 w23 = __ldg(reinterpret_cast<const uint4*>(conv_w + col * 4 + 8));
+  wt[0][0] = bf16_lo(w01.x); wt[0][1] = bf16_hi(w01.x); wt[0][2] = bf16_lo(w01.y); wt[0][3] = bf16_hi(w01.y);
+  wt[1][0] = bf16_lo(w01.z); wt[1][1] = bf16_hi(w01.z); wt[1][2] = bf16_lo(w01.w); wt[1][3] = bf16_hi(w01.w);
+  wt[2][0] = bf16_lo(w23.x); wt[2][1] = bf16_hi(w23.x); wt[2][2] = bf16_lo(w23.y); wt[2][3] = bf16_hi(w23.y);
+  wt[3][0] = bf16_lo(w23.z); wt[3][1] = bf16_hi(w23.z); wt[3][2] = bf16_lo(w23.w); wt[3][3] = bf16_hi(w23.w);
+}
+template <int kVec>
+__global__ void __launch_bounds__(256) kv_compress_bwd_kernel(const __nv_bfloat16* __restrict__ k_in, const __nv_bfloat16* __restrict__ v_in,
+                                                              const __nv_bfloat16* __restrict__ dk_out, const __nv_bfloat16* __restrict__ dv_out,
+                                                              __nv_bfloat16* __restrict__ dk_in, __nv_bfloat16* __restrict__ dv_in,
+                                                              const __nv_bfloat16* __restrict__ conv_w, const __nv_bfloat16* __restrict__ conv_b,
+                                                              const __nv_bfloat16* __restrict__ ln_w, float* __restrict__ d_conv_w,
+                                                              float* __restrict__ d_conv_b, float* __restrict__ d_ln_w,
+                                                              float* __restrict__ d_ln_b, int B, int H, int W, int ld_in, int ld_din,
+                                                              float eps) {
+  constexpr int C = kVec * 128;
+  extern __shared__ float kvc_smem[];
+  float* acc = kvc_smem;        // [0,4C) conv weight (c*4 + t), [4C,5C) conv bias, [5C,6C) LN weight, [6C,7C) LN bias
+  float* wa = kvc_smem + 7 * C + (threadIdx.x >> 5) * C;     // this warp's conv-output row
+  for (int i = threadIdx.x; i < 7 * C; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  const int Ho = H >> 1, Wo = W >> 1;
+  const int n_out = B * Ho * Wo;
+  const int lane = threadIdx.x & 31;
+  const __nv_bfloat16* in = blockIdx.y == 0 ? k_in : v_in;
+  const __nv_bfloat16* dout = blockIdx.y == 0 ? dk_out : dv_out;
+  __nv_bfloat16* din = blockIdx.y == 0 ? dk_in : dv_in;
+  const int o0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * kKvcRows;
+  for (int orow = o0; orow < min(o0 + kKvcRows, n_out); ++orow) {
+    const int b = orow / (Ho * Wo);
+    const int p = orow % (Ho * Wo);
+    const int py = p / Wo, px = p % Wo;
+    const size_t tok0 = (size_t)b * H * W + (size_t)(2 * py) * W + 2 * px;
+    float sm = 0.f;
+#pragma unroll 1
+    for (int g = 0; g < kVec; ++g) {                        // conv output -> smem row
+      const int col = (g * 32 + lane) * 4;
+      float wt[4][4];
+      conv_taps(conv_w, col, wt);
+      const uint2 bb = __ldg(reinterpret_cast<const uint2*>(conv_b + col));
+      float4 s = make_float4(bf16_lo(bb.x), bf16_hi(bb.x), bf16_lo(bb.y), bf16_hi(bb.y));
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const uint2 u = *reinterpret_cast<const uint2*>(in + (tok0 + (size_t)(t >> 1) * W + (t & 1)) * ld_in + col);
+        s.x = fmaf(wt[0][t], bf16_lo(u.x), s.x);
+        s.y = fmaf(wt[1][t], bf16_hi(u.x), s.y);
+        s.z = fmaf(wt[2][t], bf16_lo(u.y), s.z);
+        s.w = fmaf(wt[3][t], bf16_hi(u.y), s.w);
+      }
+      *reinterpret_cast<float4*>(wa + col) = s;
+      sm += (s.x + s.y) + (s.z + s.w);
+    }
+    const float mean = warp_sum_b(sm) * (1.0f / C);
+    float ss = 0.f;
+#pragma unroll 1
+    for (int g = 0; g < kVec; ++g) {
+      const float4 s = *reinterpret_cast<const float4*>(wa + (g * 32 + lane) * 4);
+      const float e0 = s.x - mean, e1 = s.y - mean, e2 = s.z - mean, e3 = s.w - mean;
+      ss += (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
+    }
+    const float rstd = rsqrtf(warp_sum_b(ss) * (1.0f / C) + eps);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll 1
+    for (int g = 0; g < kVec; ++g) {                        // LN parameter gradients, row statistics of g = dy * gamma
+      const int col = (g * 32 + lane) * 4;
+      const float4 s = *reinterpret_cast<const float4*>(wa + col);
+      const uint2 du = *reinterpret_cast<const uint2*>(dout + (size_t)orow * C + col);
+      const float4 dy = make_float4(bf16_lo(du.x), bf16_hi(du.x), bf16_lo(du.y), bf16_hi(du.y));
+      const uint2 gw = __ldg(reinterpret_cast<const uint2*>(ln_w + col));
+      const float4 xh = make_float4((s.x - mean) * rstd, (s.y - mean) * rstd, (s.z - mean) * rstd, (s.w - mean) * rstd);
+      atomicAdd(&acc[5 * C + col + 0], dy.x * xh.x); atomicAdd(&acc[5 * C + col + 1], dy.y * xh.y);
+      atomicAdd(&acc[5 * C + col + 2], dy.z * xh.z); atomicAdd(&acc[5 * C + col + 3], dy.w * xh.w);
+      atomicAdd(&acc[6 * C + col + 0], dy.x); atomicAdd(&acc[6 * C + col + 1], dy.y);
+      atomicAdd(&acc[6 * C + col + 2], dy.z); atomicAdd(&acc[6 * C + col + 3], dy.w);
+      const float4 gg = make_float4(dy.x * bf16_lo(gw.x), dy.y * bf16_hi(gw.x), dy.z * bf16_lo(gw.y), dy.w * bf16_hi(gw.y));
+      sg += (gg.x + gg.y) + (gg.z + gg.w);
+      sgx += (gg.x * xh.x + gg.y * xh.y) + (gg.z * xh.z + gg.w * xh.w);
+    }
+    const float mg = warp_sum_b(sg) * (1.0f / C), mgx = warp_sum_b(sgx) * (1.0f / C);
+#pragma unroll 1
+    for (int g = 0; g < kVec; ++g) {                        // gradient of the conv output -> conv parameters, input rows
+      const int col = (g * 32 + lane) * 4;
+      const float4 s = *reinterpret_cast<const float4*>(wa + col);
+      const uint2 du = *reinterpret_cast<const uint2*>(dout + (size_t)orow * C + col);
+      const uint2 gw = __ldg(reinterpret_cast<const uint2*>(ln_w + col));
+      const float4 gg = make_float4(bf16_lo(du.x) * bf16_lo(gw.x), bf16_hi(du.x) * bf16_hi(gw.x), bf16_lo(du.y) * bf16_lo(gw.y),
+                                    bf16_hi(du.y) * bf16_hi(gw.y));
+      const float4 da = make_float4(rstd * (gg.x - mg - (s.x - mean) * rstd * mgx), rstd * (gg.y - mg - (s.y - mean) * rstd * mgx),
+                                    rstd * (gg.z - mg - (s.z - mean) * rstd * mgx), rstd * (gg.w - mg - (s.w - mean) * rstd * mgx));
+      atomicAdd(&acc[4 * C + col + 0], da.x); atomicAdd(&acc[4 * C + col + 1], da.y);
+      atomicAdd(&acc[4 * C + col + 2], da.z); atomicAdd(&acc[4 * C + col + 3], da.w);
+      float wt[4][4];
+      conv_taps(conv_w, col, wt);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const size_t off = (tok0 + (size_t)(t >> 1) * W + (t & 1));
+        const uint2 u = *reinterpret_cast<const uint2*>(in + off * ld_in + col);                  // L1 / L2 hit
+        atomicAdd(&acc[(col + 0) * 4 + t], da.x * bf16_lo(u.x)); atomicAdd(&acc[(col + 1) * 4 + t], da.y * bf16_hi(u.x));
+        atomicAdd(&acc[(col + 2) * 4 + t], da.z * bf16_lo(u.y)); atomicAdd(&acc[(col + 3) * 4 + t], da.w * bf16_hi(u.y));
+        *reinterpret_cast<uint2*>(din + off * ld_din + col) =
+            make_uint2(pack_bf16x2(da.x * wt[0][t], da.y * wt[1][t]), pack_bf16x2(da.z * wt[2][t], da.w * wt[3][t]));
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 7 * C; i += blockDim.x) {
+    const float v = acc[i];
+    if (v != 0.f) {
+      float* dst = i < 4 * C ? d_conv_w + i : (i < 5 * C ? d_conv_b + (i - 4 * C) : (i < 6 * C ? d_ln_w + (i - 5 * C) : d_ln_b + (i - 6 * C)));
+      atomicAdd(dst, v);
+    }
+  }
+}
+
 static inline int grid_for(long long work_items, int threads) {
   long long g = (work_items + threads - 1) / threads;
   const long long cap = (long long)device_info().sms * 16;
@@ -433,6 +559,34 @@ extern "C" int pxa_attn_delta_d72(const void* o, const void* d_o, float* delta, 
   const int grid = (int)((total + 255) / 256);
   attn_delta_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(o), reinterpret_cast<const __nv_bfloat16*>(d_o), delta, B, H, Nq, ldo, lddo);
+  launch_counter()++;
+  PXA_CHECK_CUDA(cudaGetLastError());
+  return PXA_OK;
+}
+
+extern "C" int pxa_kv_compress_conv2_ln_bwd(const PxaKvCompressBwdArgs* args, void* stream) {
+  using namespace pxa;
+  if (!args) return fail(PXA_ERR_ARG, "null args");
+  const PxaKvCompressBwdArgs& a = *args;
+  if (!a.k_in || !a.v_in || !a.dk_out || !a.dv_out || !a.dk_in || !a.dv_in || !a.conv_w || !a.conv_b || !a.ln_w || !a.d_conv_w ||
+      !a.d_conv_b || !a.d_ln_w || !a.d_ln_b)
+    return fail(PXA_ERR_ARG, "null pointer");
+  if (a.C != 1152) return fail(PXA_ERR_ARG, "specialised for C=1152 (got %d)", a.C);
+  if (a.B <= 0 || a.H < 2 || a.W < 2 || (a.H & 1) || (a.W & 1)) return fail(PXA_ERR_ARG, "bad B/H/W (H, W even)");
+  if ((a.ld_in & 7) || (a.ld_din & 7)) return fail(PXA_ERR_ALIGN, "ld_in / ld_din must be multiples of 8");
+  if (!PXA_ALIGNED16(a.k_in) || !PXA_ALIGNED16(a.v_in) || !PXA_ALIGNED16(a.dk_out) || !PXA_ALIGNED16(a.dv_out) ||
+      !PXA_ALIGNED16(a.dk_in) || !PXA_ALIGNED16(a.dv_in) || !PXA_ALIGNED16(a.conv_w) || !PXA_ALIGNED16(a.conv_b) || !PXA_ALIGNED16(a.ln_w))
+    return fail(PXA_ERR_ALIGN, "pointers must be 16-byte aligned");
+  PXA_REQUIRE_SM100();
+  const int rows = a.B * (a.H / 2) * (a.W / 2);
+  dim3 grid((rows + 8 * kKvcRows - 1) / (8 * kKvcRows), 2);
+  PXA_CHECK_CUDA(cudaFuncSetAttribute(kv_compress_bwd_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvcSmem));
+  kv_compress_bwd_kernel<9><<<grid, 256, kKvcSmem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(a.k_in), reinterpret_cast<const __nv_bfloat16*>(a.v_in),
+      reinterpret_cast<const __nv_bfloat16*>(a.dk_out), reinterpret_cast<const __nv_bfloat16*>(a.dv_out),
+      reinterpret_cast<__nv_bfloat16*>(a.dk_in), reinterpret_cast<__nv_bfloat16*>(a.dv_in),
+      reinterpret_cast<const __nv_bfloat16*>(a.conv_w), reinterpret_cast<const __nv_bfloat16*>(a.conv_b),
+      reinterpret_cast<const __nv_bfloat16*>(a.ln_w), a.d_conv_w, a.d_conv_b, a.d_ln_w, a.d_ln_b, a.B, a.H, a.W, a.ld_in, a.ld_din, a.eps);
   launch_counter()++;
   PXA_CHECK_CUDA(cudaGetLastError());
   return PXA_OK;

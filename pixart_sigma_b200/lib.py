@@ -79,6 +79,14 @@ class LnModBwdArgs(C.Structure):
                 ("M", C.c_int32), ("C", C.c_int32), ("eps", C.c_float)]
 
 
+class KvCompressBwdArgs(C.Structure):
+    _fields_ = [("k_in", C.c_void_p), ("v_in", C.c_void_p), ("dk_out", C.c_void_p), ("dv_out", C.c_void_p),
+                ("dk_in", C.c_void_p), ("dv_in", C.c_void_p), ("conv_w", C.c_void_p), ("conv_b", C.c_void_p),
+                ("ln_w", C.c_void_p), ("d_conv_w", C.c_void_p), ("d_conv_b", C.c_void_p), ("d_ln_w", C.c_void_p),
+                ("d_ln_b", C.c_void_p), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
+                ("ld_in", C.c_int32), ("ld_din", C.c_int32), ("eps", C.c_float)]
+
+
 class AttnBwdArgs(C.Structure):
     _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p), ("d_o", C.c_void_p),
                 ("lse", C.c_void_p), ("delta", C.c_void_p), ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
@@ -92,7 +100,7 @@ class AttnBwdArgs(C.Structure):
 
 
 EXPORTS = ("pxa_transpose_bf16", "pxa_gelu_tanh_bf16", "pxa_gate_residual_fwd", "pxa_gate_residual_bwd",
-           "pxa_ln_modulate_bwd", "pxa_colsum_bf16", "pxa_attn_delta_d72", "pxa_flash_attn_d72_bwd_bf16",
+           "pxa_ln_modulate_bwd", "pxa_colsum_bf16", "pxa_attn_delta_d72", "pxa_flash_attn_d72_bwd_bf16", "pxa_kv_compress_conv2_ln_bwd",
            "pxa_version", "pxa_last_error", "pxa_launch_count", "pxa_gemm_bf16", "pxa_ln_modulate",
            "pxa_flash_attn_d72_bf16", "pxa_kv_compress_conv2_ln", "pxa_conv3x3_nhwc_bf16", "pxa_dpm_solver_pp_step")
 
@@ -116,7 +124,8 @@ def load() -> C.CDLL:
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(struct), C.c_void_p]
         for name, struct in (("pxa_gate_residual_fwd", GateResidualArgs), ("pxa_gate_residual_bwd", GateResidualArgs),
-                             ("pxa_ln_modulate_bwd", LnModBwdArgs), ("pxa_flash_attn_d72_bwd_bf16", AttnBwdArgs)):
+                             ("pxa_ln_modulate_bwd", LnModBwdArgs), ("pxa_flash_attn_d72_bwd_bf16", AttnBwdArgs),
+                             ("pxa_kv_compress_conv2_ln_bwd", KvCompressBwdArgs)):
             fn = getattr(lib, name)
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(struct), C.c_void_p]
@@ -364,3 +373,17 @@ def gemm_wgrad(a_t: torch.Tensor, w_t: torch.Tensor, out: torch.Tensor, *, block
                     cta_pair=1, debug_trace=None, operands_mn_major=1, k_splits=k_splits, aux_is_branch=0)
     _check(load().pxa_gemm_bf16(C.byref(args), _stream()), "pxa_gemm_bf16 (wgrad)")
     return out
+
+
+def kv_compress_bwd(k_in, v_in, dk_out, dv_out, dk_in, dv_in, conv_w, conv_b, ln_w, d_conv_w, d_conv_b, d_ln_w, d_ln_b, *,
+                    B: int, H: int, W: int, ld_in: int, ld_din: int, eps: float = 1e-5) -> None:
+    """Backward of kv_compress: dk_in / dv_in (bf16 views, row stride ld_din) written, the four fp32 parameter gradients
+    accumulated."""
+    for t in (d_conv_w, d_conv_b, d_ln_w, d_ln_b):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    assert dk_out.is_contiguous() and dv_out.is_contiguous() and dk_out.dtype == torch.bfloat16
+    args = KvCompressBwdArgs(k_in=_ptr(k_in), v_in=_ptr(v_in), dk_out=_ptr(dk_out), dv_out=_ptr(dv_out), dk_in=_ptr(dk_in),
+                             dv_in=_ptr(dv_in), conv_w=_ptr(conv_w), conv_b=_ptr(conv_b), ln_w=_ptr(ln_w),
+                             d_conv_w=_ptr(d_conv_w), d_conv_b=_ptr(d_conv_b), d_ln_w=_ptr(d_ln_w), d_ln_b=_ptr(d_ln_b),
+                             B=B, H=H, W=W, C=dk_out.shape[-1], ld_in=ld_in, ld_din=ld_din, eps=eps)
+    _check(load().pxa_kv_compress_conv2_ln_bwd(C.byref(args), _stream()), "pxa_kv_compress_conv2_ln_bwd")

@@ -343,7 +343,7 @@ class PixArtMSBlock(nn.Module):
         x32 = x.reshape(B * N, C).float().contiguous()
         if _wants_grad(self, x, y, t):                                     # training: differentiable kernel ops
             from .autograd import block_forward_train
-            out = block_forward_train(self, x32, cond, kv_len, kv_off, max(max(lens), 1), mod, B, N)
+            out = block_forward_train(self, x32, cond, kv_len, kv_off, max(max(lens), 1), mod, B, N, None, tuple(HW))
         else:
             out = self.run_kernels(x32, cond, kv_len, kv_off, max(max(lens), 1), mod, B, N, tuple(HW), self._ws)
         return out.view(B, N, C).to(x.dtype)
@@ -535,10 +535,12 @@ class PixArtMS(nn.Module):
             mod = blk.scale_shift_table.float()[None] + t0
             if getattr(blk, "grad_checkpointing", False):
                 # per-call dict: lets the recomputation reuse the attention outputs of the first pass (autograd.py)
-                x32 = checkpoint(ag.block_forward_train, blk, x32, cond, kv_len, None, L, mod, B, N, {},
-                                 use_reentrant=False)
+                # preserve_rng_state=False: the block draws no random numbers, and stashing the RNG state reads the device
+                # (not capturable in a CUDA graph)
+                x32 = checkpoint(ag.block_forward_train, blk, x32, cond, kv_len, None, L, mod, B, N, {}, (self.h, self.w),
+                                 use_reentrant=False, preserve_rng_state=False)
             else:
-                x32 = ag.block_forward_train(blk, x32, cond, kv_len, None, L, mod, B, N)
+                x32 = ag.block_forward_train(blk, x32, cond, kv_len, None, L, mod, B, N, None, (self.h, self.w))
 
         fl = self.final_layer
         fmod = (fl.scale_shift_table.float()[None] + t[:, None]).contiguous()

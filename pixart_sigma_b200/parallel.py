@@ -86,6 +86,7 @@ class GradBucketReducer:
                 off += p.numel()
             self.buckets.append({"key": key, "flat": flat, "params": ps, "pending": 0, "work": None})
         self._hooks = []
+        self.overlap = True        # False: no collective from the hooks (CUDA-graph capture); finish() reduces every bucket
         for b in self.buckets:
             for p in b["params"]:
                 self._hooks.append(p.register_post_accumulate_grad_hook(lambda _p, b=b: self._ready(b)))
@@ -102,7 +103,7 @@ class GradBucketReducer:
 
     def _ready(self, b) -> None:
         b["pending"] -= 1
-        if b["pending"] == 0 and self.world > 1:
+        if b["pending"] == 0 and self.world > 1 and self.overlap:
             b["flat"].div_(self.world)
             b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 

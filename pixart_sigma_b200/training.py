@@ -99,3 +99,60 @@ def train_step(model, loss_fn: IDDPMLoss, x_start, timestep, y, mask, data_info=
     if reducer is not None:
         reducer.finish()
     return loss.detach()
+
+
+class GraphedTrainStep:
+    """One training step (gradient zeroing + loss forward + backward through the kernels) captured as ONE CUDA graph.
+
+    Measured on B200 (bench.py --workload c5): the eager step is bound by the HOST -- ~10 k kernel launches through
+    Python / autograd take as long to enqueue as the GPU needs to run them -- so the step is captured once with static
+    input buffers and replayed; the library never allocates or synchronises and autograd's backward runs on the capture
+    stream, so fwd + bwd capture as they are.  Every replay first refreshes the bf16 weight shadows IN PLACE from the
+    (optimizer-updated) fp32 parameters (`autograd.refresh_shadows`, part of the graph), so an optimizer step between
+    replays is seen.  The gradient all-reduce stays outside the graph: `reducer.finish()` reduces the flat buckets after
+    the replay (no overlap with the backward in this mode).
+
+    Fixed shapes only (one graph per batch geometry); activation checkpointing is captured as well (the recomputation is
+    just more kernels on the stream; torch's RNG-state stashing, which reads the device, is disabled).
+    """
+
+    def __init__(self, model, loss_fn: IDDPMLoss, reducer, example, warmup: int = 2):
+        from . import autograd as ag
+        self.model, self.loss_fn, self.reducer = model, loss_fn, reducer
+        reducer.overlap = False                      # collectives stay outside the graph
+        dev = next(model.parameters()).device
+        self.static = [None if v is None else torch.empty_like(v, device=dev) for v in example]
+        self._copy_in(example)
+        x0, t, y, mask, noise = self.static
+
+        def step():
+            ag.refresh_shadows(model)
+            reducer.zero_grad()
+            terms = loss_fn.training_losses(model, x0, t, dict(y=y, mask=mask, data_info=None), noise=noise)
+            loss = terms["loss"].mean()
+            loss.backward()
+            return loss.detach()
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                       # eager: allocator warm-up, shadows and caches created
+                step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = step()
+
+    def _copy_in(self, batch):
+        for dst, src in zip(self.static, batch):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+
+    def __call__(self, x_start, timestep, y, mask, noise) -> torch.Tensor:
+        self._copy_in((x_start, timestep, y, mask, noise))
+        self.reducer.start()
+        self.graph.replay()
+        if self.reducer.world > 1:
+            self.reducer.finish()
+        return self.loss

@@ -160,7 +160,8 @@ def _attn_ref(q, k, v, lens, scale):
 
 @pytest.mark.parametrize("B,H,Nq,Nk,lens", [
     (1, 2, 128, 128, None), (2, 3, 256, 256, None), (1, 16, 1024, 1024, None), (2, 2, 256, 64, None),
-    (2, 2, 128, 300, [300, 77]), (3, 4, 256, 300, [5, 130, 256]),
+    (2, 2, 128, 300, [300, 77]), (3, 4, 256, 300, [5, 130, 256]), (2, 2, 200, 200, None), (1, 3, 4032, 4032, None),
+    (2, 2, 72, 300, [300, 41]),
 ])
 def test_flash_attn_backward(B, H, Nq, Nk, lens):
     D, C = 72, H * 72
@@ -237,3 +238,30 @@ def test_flash_attn_backward_interleaved_qkv_and_packed_cross_keys():
     torch.stack(outs).backward(d_o.float().view(B, N, H, D))
     assert po.rel_err(dq.float().view(B, N, H, D), qf.grad) < 1e-2
     assert po.rel_err(dkv.float(), kvf.grad) < 1e-2
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 16, 16), (1, 8, 24)])
+def test_kv_compress_backward(B, H, W):
+    """Depthwise conv 2x2/s2 + LayerNorm(affine) backward vs torch autograd (fp32) of the same op on K and V."""
+    C = 1152
+    qkv = _randn(B * H * W, 3 * C, seed=60)
+    conv_w = _randn(C, 1, 2, 2, seed=61, scale=0.5) + 0.25
+    conv_b, ln_w, ln_b = _randn(C, seed=62, scale=0.1), _randn(C, seed=63, scale=0.2) + 1.0, _randn(C, seed=64, scale=0.1)
+    n_out = (H // 2) * (W // 2)
+    dkc, dvc = _randn(B * n_out, C, seed=65), _randn(B * n_out, C, seed=66)
+    dqkv = torch.zeros_like(qkv)
+    g = [torch.zeros(C, 1, 2, 2, device=DEV), torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)]
+    lib.kv_compress_bwd(qkv[:, C:2 * C], qkv[:, 2 * C:], dkc, dvc, dqkv[:, C:2 * C], dqkv[:, 2 * C:], conv_w, conv_b, ln_w, *g,
+                        B=B, H=H, W=W, ld_in=3 * C, ld_din=3 * C)
+    f = qkv.float().requires_grad_(True)
+    pw, pb, pg, pbeta = (t.float().requires_grad_(True) for t in (conv_w, conv_b, ln_w, ln_b))
+    outs = []
+    for i in (1, 2):
+        img = f[:, i * C:(i + 1) * C].reshape(B, H, W, C).permute(0, 3, 1, 2)
+        y = F.conv2d(img, pw, pb, stride=2, groups=C).reshape(B, C, -1).permute(0, 2, 1)
+        outs.append(F.layer_norm(y, (C,), pg, pbeta, eps=1e-5).reshape(B * n_out, C))
+    (outs[0] * dkc.float()).sum().add((outs[1] * dvc.float()).sum()).backward()
+    assert float(dqkv[:, :C].abs().max()) == 0.0
+    assert po.rel_err(dqkv[:, C:].float(), f.grad[:, C:]) < 4e-3
+    for got, want in zip(g, (pw.grad, pb.grad, pg.grad, pbeta.grad)):
+        assert po.rel_err(got, want) < 1e-3

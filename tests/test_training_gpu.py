@@ -21,7 +21,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 if torch.cuda.is_available():
     from pixart_sigma_b200 import PixArtMS, build_model
-    from pixart_sigma_b200.training import IDDPMLoss, train_step
+    from pixart_sigma_b200.parallel import GradBucketReducer
+    from pixart_sigma_b200.training import GraphedTrainStep, IDDPMLoss, train_step
 
 
 def _log(line):
@@ -75,6 +76,41 @@ def test_block_gradients_match_oracle(B, hw, lens):
     for n, p in blk.named_parameters():
         errs[n] = po.rel_err(p.grad.float().cpu(), sdo["blocks.0." + n].grad)
     _log(f"block grads B={B} hw={hw} lens={lens}: " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
+    assert max(errs.values()) < 2e-2, errs
+
+
+@pytest.mark.parametrize("sampling", ["conv", "uniform"])
+def test_kv_compressed_block_gradients_match_oracle(sampling):
+    """Training through a KV-compressed block (PixArt_blocks.py:97-121, 137-139): conv + LN compression kernel and its
+    backward, attention backward with Nk = N / 4."""
+    B, hw, lens, C = 2, (16, 16), [300, 9], 1152
+    N = hw[0] * hw[1]
+    cfg = po.OracleConfig(depth=1, kv_sampling=sampling, kv_scale_factor=2, kv_compress_layer=[0])
+    sd = _rounded(po.synthetic_state_dict(cfg, seed=7))
+    kw = dict(type="PixArtMS", depth=1, input_size=32, pe_interpolation=0.5, model_max_length=300,
+              kv_compress_config=dict(sampling=sampling, scale_factor=2, kv_compress_layer=[0]))
+    with torch.device("cuda"):
+        m = build_model(kw)
+    m.load_state_dict(sd, strict=False)
+    blk = m.float().train().blocks[0]
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, N, C, generator=g)
+    t0 = torch.randn(B, 6 * C, generator=g) * 0.3
+    ycat = torch.randn(sum(lens), C, generator=g).to(torch.bfloat16).float()
+    dout = torch.randn(B, N, C, generator=g)
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith("blocks.0.")}
+    xo = x.clone().requires_grad_(True)
+    want = po.block_forward(sdo, "blocks.0", xo, ycat[None], t0, lens, hw, 16, 2, sampling)
+    want.backward(dout)
+    xk = x.clone().cuda().requires_grad_(True)
+    got = blk(xk, ycat.cuda()[None], t0.cuda(), lens, hw)
+    ferr = po.rel_err(got.detach().cpu(), want.detach())
+    assert ferr < 2e-3, ferr
+    got.backward(dout.cuda())
+    errs = {"x": po.rel_err(xk.grad.cpu(), xo.grad)}
+    for n, p in blk.named_parameters():
+        errs[n] = po.rel_err(p.grad.float().cpu(), sdo["blocks.0." + n].grad)
+    _log(f"kv-compressed ({sampling}) block grads: fwd={ferr:.2e} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
     assert max(errs.values()) < 2e-2, errs
 
 
@@ -133,3 +169,38 @@ def test_checkpointing_and_bf16_parameters_give_the_same_gradients():
     for n in grads[0]:
         assert torch.equal(grads[0][n], grads[1][n]) or po.rel_err(grads[1][n], grads[0][n]) < 1e-5, n   # atomics reorder sums
         assert po.rel_err(grads[2][n], grads[0][n]) < 2e-2, n                                          # bf16 grads / params
+
+
+@pytest.mark.parametrize("ckpt", [False, True])
+def test_graphed_train_step_equals_eager_and_sees_parameter_updates(ckpt):
+    """The whole step (zero-grad + loss fwd + bwd, with or without activation checkpointing) replayed from one CUDA
+    graph gives the eager gradients, also after the parameters were updated in place between replays."""
+    cfg = po.OracleConfig(depth=2, input_size=32, pe_interpolation=0.5)
+    sd = _rounded(po.synthetic_state_dict(cfg, seed=0))
+    x0, t, y, mask, noise = train_inputs(cfg, 2, (32, 32), [10, 600], [300, 50])
+    batch = tuple(v.cuda() for v in (x0, t, y.to(torch.bfloat16), mask, noise))
+    m = _build_train(cfg, sd, checkpoint=ckpt)
+    red = GradBucketReducer(m)
+    loss = IDDPMLoss()
+
+    def eager():
+        red.zero_grad()
+        lv = train_step(m, loss, batch[0], batch[1], batch[2], batch[3], noise=batch[4], reducer=red)
+        return lv.clone(), {n: p.grad.clone() for n, p in m.named_parameters()}
+
+    l0, g0 = eager()
+    step = GraphedTrainStep(m, loss, red, batch)
+    lg = step(*batch).clone()
+    assert po.rel_err(lg, l0) < 1e-5
+    for n, p in m.named_parameters():
+        assert po.rel_err(p.grad, g0[n]) < 1e-4, n              # atomics reorder fp32 sums
+    with torch.no_grad():                                       # an "optimizer step"
+        for p in m.parameters():
+            p.add_(0.01 * torch.randn_like(p))
+    lg2 = step(*batch).clone()
+    g2 = {n: p.grad.clone() for n, p in m.named_parameters()}
+    l1, g1 = eager()
+    assert abs(float(l1) - float(l0)) > 1e-6                    # the update changed the loss ...
+    assert po.rel_err(lg2, l1) < 1e-5                           # ... and the replay saw it (shadows refreshed in place)
+    for n in g1:
+        assert po.rel_err(g2[n], g1[n]) < 1e-4, n
