@@ -47,11 +47,15 @@ struct EpiConst {
 constexpr int kEpiConstBytes = 2 * sizeof(EpiConst);    // 6176 B
 
 // kTmaRes: fp32 residual epilogue streamed through smem by TMA (see the end of this file)
-template <int BN, bool kTmaRes = false> struct GemmCfg {
+// kReduceOnly: the weight-gradient form only ever runs the reduce-add epilogue (no residual loads, no aux copy): two chunk
+// buffers are enough, which leaves room for one more operand stage (its K loop is thousands of blocks long).
+template <int BN, bool kTmaRes = false, bool kReduceOnly = false> struct GemmCfg {
   static constexpr int kStageA = kBM * kBK * 2;                 // 16 KB
   static constexpr int kStageB = BN * kBK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kEpiBufs = kTmaRes ? kResEpiSmem : 4 * 32 * 32 * 4;   // else 4 epilogue warps x (32 rows x 128 B)
+  static constexpr int kResRing = kReduceOnly ? 2 : kResBufs;                // chunk buffers of the TMA residual epilogue
+  static constexpr int kEpiBufs = kTmaRes ? (kReduceOnly ? 2 * kResChunkBytes : kResEpiSmem)
+                                          : 4 * 32 * 32 * 4;                 // else 4 epilogue warps x (32 rows x 128 B)
   static constexpr int kEpiSmem = kEpiBufs + ((kEpiConstBytes + 127) / 128) * 128;
   static constexpr int kBarBytes = 256;
   static constexpr int kMaxStages = (kSmemBudget - kEpiSmem - kBarBytes - 1024) / kStage;

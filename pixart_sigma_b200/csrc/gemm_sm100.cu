@@ -27,8 +27,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                  const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out,
                  const __grid_constant__ CUtensorMap tmap_aux, const GemmParams p) {
   constexpr bool kTmaRes = (EPI == PXA_EPI_BIAS_RESIDUAL) && sizeof(OutT) == 4;
-  using Cfg = GemmCfg<BN, kTmaRes>;
+  using Cfg = GemmCfg<BN, kTmaRes, kMn>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int kRing = Cfg::kResRing;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_smem = smem + kStages * Cfg::kStage;
@@ -163,7 +164,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // TMA-streamed fp32 residual path state (unused otherwise)
     const int r = q * 32 + lane;                                  // row of the 128-row tile owned by this thread
     uint8_t* rbufs = epi_smem;
-    uint8_t* abufs = epi_smem + kResBufs * kResChunkBytes;
+    uint8_t* abufs = epi_smem + kRing * kResChunkBytes;          // (unused by the reduce-only configuration)
     // One thread of the first epilogue warp owns every TMA op of the epilogue.  It is picked with elect.sync inside a
     // warp-uniform branch (always the same lane for a full warp), so the TMA / mbarrier operands stay in uniform
     // registers; `issuer_warp` guards the converged regions, `issuer` the elected lane (bulk groups are per thread).
@@ -177,7 +178,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (l_tile >= num_tiles) return;
       const int lm0 = ((l_tile % mn_tiles) / p.num_n_tiles) * kBM;
       const int ln0 = ((l_tile % mn_tiles) % p.num_n_tiles) * BN;
-      const int buf = l_g % kResBufs;
+      const int buf = l_g % kRing;
       mbar_arrive_expect_tx(&res_full[buf], kResChunkBytes);
       tma_load_2d(rbufs + buf * kResChunkBytes, &tmap_res, &res_full[buf], ln0 + l_cc * 32, lm0, kEvictFirst);
       ++l_g;
@@ -185,7 +186,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     };
     if (issuer_warp && !reduce) {
       if (elect_one()) {
-        for (int i = 0; i < kResBufs - 1; ++i) request_next();
+        for (int i = 0; i < kRing - 1; ++i) request_next();
       }
     }
     int g = 0;
@@ -212,11 +213,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // one chunk: v = this thread's 32 accumulator columns [cc*32, +32)
       auto process = [&](uint32_t (&v)[32], int cc) {
         if constexpr (kTmaRes) {
-          const int buf = g % kResBufs;
+          const int buf = g % kRing;
           uint8_t* rb = rbufs + buf * kResChunkBytes;
           uint8_t* ab = p.out_aux != nullptr ? abufs + (g & 1) * kAuxChunkBytes : nullptr;
           stamp();                                                  // chunk: acc in registers
-          if (!reduce) mbar_wait(&res_full[buf], (g / kResBufs) & 1);   // residual chunk has landed in smem
+          if (!reduce) mbar_wait(&res_full[buf], (g / kRing) & 1);   // residual chunk has landed in smem
           stamp();                                                  // chunk: residual landed
           residual_chunk_row_c(v, p, cb, rb, ab, r, cc * 32, m0 + r, n0 + cc * 32, reduce);
           fence_proxy_async_smem();                                 // generic-proxy writes -> visible to the TMA store
@@ -323,7 +324,7 @@ static int launch_gemm(const PxaGemmArgs& a, cudaStream_t stream, const ConvGeom
     if (rc) return rc;
   }
   constexpr bool kTmaRes = (EPI == PXA_EPI_BIAS_RESIDUAL) && sizeof(OutT) == 4;
-  using Cfg = GemmCfg<BN, kTmaRes>;
+  using Cfg = GemmCfg<BN, kTmaRes, kMn>;
   CUtensorMap tr = ta, to = ta, tx = ta;   // residual / out / aux maps: only meaningful for EPI_BIAS_RESIDUAL
   if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
     uint64_t dims[2] = {(uint64_t)a.N, (uint64_t)a.M};

@@ -32,8 +32,10 @@ if os.path.exists(lp):
     with open(os.path.join(out_dir, f"{tag}_launches.csv"), "w") as f:
         f.writelines(rows)
 rp = os.path.join(ROOT, "gpurun_out", f"prof_{tag}.ncu-rep")
-if os.path.exists(rp):
-    raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rcsv = os.path.join(ROOT, "gpurun_out", f"prof_{tag}_raw.csv")      # already converted on the GPU box (run_gpu_ncu.sh)
+if os.path.exists(rp) or os.path.exists(rcsv):
+    raw = open(rcsv).read() if os.path.exists(rcsv) else \
+        subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
