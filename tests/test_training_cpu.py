@@ -126,3 +126,25 @@ def test_grad_bucket_reducer_single_process_is_a_noop_reduce():
     red.finish()
     assert red.grad_bytes() == sum(p.numel() for p in m.parameters()) * 4
     assert float(m.head.weight.grad.abs().sum()) > 0
+
+
+def test_bf16_shadow_cache_semantics():
+    """`autograd._shadow`: bf16 copies live on the owning module, are reused while the parameter is unchanged, refreshed IN
+    PLACE after an in-place update (same buffer: captured CUDA graphs keep pointing at it), rebuilt when the storage moves,
+    and a bf16 parameter is its own shadow."""
+    from pixart_sigma_b200 import autograd as ag
+    lin = torch.nn.Linear(16, 8)
+    w1 = ag._shadow(lin, "w")
+    assert w1.dtype == torch.bfloat16 and torch.equal(w1, lin.weight.detach().to(torch.bfloat16))
+    assert ag._shadow(lin, "w") is w1 and ag._shadow(lin, "b").shape == (8,)
+    with torch.no_grad():
+        lin.weight.add_(1.0)                                     # optimizer-style in-place update bumps _version
+    w2 = ag._shadow(lin, "w")
+    assert w2.data_ptr() == w1.data_ptr() and torch.equal(w2, lin.weight.detach().to(torch.bfloat16))
+    lin.weight.data = lin.weight.data.clone()                    # storage moved (e.g. module.to()): new shadow values
+    assert torch.equal(ag._shadow(lin, "w"), lin.weight.detach().to(torch.bfloat16))
+    lin16 = torch.nn.Linear(16, 8).to(torch.bfloat16)
+    assert ag._shadow(lin16, "w").data_ptr() == lin16.weight.data_ptr()
+    assert ag._shadow(torch.nn.Linear(4, 4, bias=False), "b") is None
+    ag.clear_shadow_cache(lin)
+    assert "_pxa_shadow" not in lin.__dict__
