@@ -29,6 +29,9 @@ CASES = {
     "train_d2_b2": dict(cfg=dict(depth=2, input_size=32, pe_interpolation=0.5), batch=2, hw=(32, 32), t=[0, 731], lens=[300, 41]),
     "train_d2_b3_512": dict(cfg=dict(depth=2, input_size=64, pe_interpolation=1.0), batch=3, hw=(64, 64), t=[999, 5, 250],
                             lens=[120, 300, 7]),
+    # KV-compressed second block (conv sr=2 + LayerNorm, PixArt_blocks.py:84-89): pins the gradients of attn.sr / attn.norm
+    "train_d2_kvconv": dict(cfg=dict(depth=2, input_size=32, pe_interpolation=0.5, kv_sampling="conv", kv_scale_factor=2,
+                                     kv_compress_layer=[1]), batch=2, hw=(32, 32), t=[400, 90], lens=[64, 300]),
 }
 
 

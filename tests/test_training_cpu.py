@@ -42,8 +42,9 @@ def test_iddpm_loss_gradient_does_not_reach_the_mean_through_vb():
 
 
 @pytest.mark.slow
-def test_oracle_autograd_matches_reference_gradients(golden_dir):
-    fix = torch.load(os.path.join(golden_dir, "train_d2_b2.pt"))
+@pytest.mark.parametrize("name", ["train_d2_b2", "train_d2_kvconv"])
+def test_oracle_autograd_matches_reference_gradients(golden_dir, name):
+    fix = torch.load(os.path.join(golden_dir, name + ".pt"))
     cfg = po.OracleConfig(**fix["cfg"])
     sd = {k: v.requires_grad_(v.is_floating_point()) for k, v in po.synthetic_state_dict(cfg, seed=0).items()}
     x0, t, y, mask, noise = train_inputs(cfg, fix["batch"], tuple(fix["hw"]), fix["t"], fix["lens"])
