@@ -103,15 +103,18 @@ def test_library_exports_every_symbol_the_header_declares():
 def test_ctypes_structs_match_header_sizes():
     """Field-by-field size check of the POD argument structs against a compile of the header with gcc."""
     import subprocess, tempfile
-    src = '#include <stdio.h>\n#include "pixart_sm100.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(PxaGemmArgs),' \
+    src = '#include <stdio.h>\n#include "pixart_sm100.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(PxaGemmArgs),' \
           ' sizeof(PxaLnModArgs), sizeof(PxaAttnArgs), sizeof(PxaKvCompressArgs), sizeof(PxaConv3x3Args),' \
-          ' sizeof(PxaDpmStepArgs));return 0;}\n'
+          ' sizeof(PxaDpmStepArgs), sizeof(PxaGateResidualArgs), sizeof(PxaLnModBwdArgs), sizeof(PxaAttnBwdArgs),' \
+          ' sizeof(PxaKvCompressBwdArgs));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
         sizes = [int(v) for v in subprocess.check_output([os.path.join(d, "s")]).split()]
     assert sizes == [ctypes.sizeof(lib.GemmArgs), ctypes.sizeof(lib.LnModArgs), ctypes.sizeof(lib.AttnArgs),
-                     ctypes.sizeof(lib.KvCompressArgs), ctypes.sizeof(lib.Conv3x3Args), ctypes.sizeof(lib.DpmStepArgs)]
+                     ctypes.sizeof(lib.KvCompressArgs), ctypes.sizeof(lib.Conv3x3Args), ctypes.sizeof(lib.DpmStepArgs),
+                     ctypes.sizeof(lib.GateResidualArgs), ctypes.sizeof(lib.LnModBwdArgs), ctypes.sizeof(lib.AttnBwdArgs),
+                     ctypes.sizeof(lib.KvCompressBwdArgs)]
 
 
 def test_product_never_imports_the_oracle():
