@@ -141,6 +141,32 @@ def cpu_reference_sample(side: int, pe: float, kv: bool, threads: int):
     return 1.0 / (fixed + DEPTH * per_block), t2 + t6
 
 
+def cpu_reference_train_sample(side: int, pe: float, threads: int):
+    """Training counterpart of `cpu_reference_sample` (workload c5): the oracle port of the reference forward with autograd
+    + the IDDPM loss + backward (fp32, CPU), ONE image, through a 1-block and a 3-block slice of the 28-block model;
+    per-block time = (t3 - t1) / 2, fixed = t1 - per-block, full step = fixed + 28 x per-block.  Returns (images/s, seconds)."""
+    from oracle import pixart_oracle as po            # bench.py may use the oracle ONLY in the cpu baseline / reference arms
+    from pixart_sigma_b200.training import IDDPMLoss
+    torch.set_num_threads(threads)
+
+    def run(depth):
+        cfg = po.OracleConfig(depth=depth, input_size=side, pe_interpolation=pe)
+        sd = {k: v.requires_grad_(v.is_floating_point()) for k, v in po.synthetic_state_dict(cfg, seed=0).items()}
+        x, _, y, mask = po.synthetic_inputs(cfg, 1, (side, side), lens=[300])
+        model = lambda xx, timestep, **kw: po.forward_grad(sd, cfg, xx, timestep.float(), kw["y"], mask=kw["mask"])
+        t0 = time.perf_counter()
+        terms = IDDPMLoss().training_losses(model, x * 0.5, torch.tensor([500]), dict(y=y, mask=mask, data_info=None),
+                                            noise=torch.randn_like(x))
+        terms["loss"].mean().backward()
+        return time.perf_counter() - t0
+
+    run(0)                                             # warm-up (embedders, thread pool)
+    t1, t3 = run(1), run(3)
+    per_block = max((t3 - t1) / 2.0, 1e-9)
+    fixed = max(t1 - per_block, 0.0)
+    return 1.0 / (fixed + DEPTH * per_block), t1 + t3
+
+
 def pick_cpu_threads() -> int:
     """torch CPU GEMMs of this size stop scaling (and regress) long before 128 threads: calibrate on a 1024x1152x4608
     fp32 matmul and keep the fastest of {all cores, 64, 32, 16}."""
@@ -165,23 +191,33 @@ def run_reference_arm(args, wl):
     if rank != 0:
         return
     threads = pick_cpu_threads()
+    train = args.workload == "c5"
+    sample_fn = (lambda: cpu_reference_train_sample(side, pe, threads)) if train else (lambda: cpu_reference_sample(side, pe, kv, threads))
     for _ in range(max(args.warmup, 0) and 1):
-        cpu_reference_sample(side, pe, kv, threads)
+        sample_fn()
     vals, t_all = [], 0.0
     for _ in range(max(1, min(args.steps, 3))):
-        v, dt = cpu_reference_sample(side, pe, kv, threads)
+        v, dt = sample_fn()
         vals.append(v); t_all += dt
     value = statistics.median(vals)
-    sample = (f"oracle port of the reference PixArtMS.forward (fp32, torch CPU, {threads} threads) at {side * 8}px, forward "
-              f"batch 2 (one image with CFG): 2-block and 6-block slices timed, full 28-block forward = fixed + 28 x "
-              f"per-block; median of {len(vals)} samples, {t_all:.1f} s of CPU work")
-    line = {"impl": "reference", "metric": "denoise-steps/sec", "value": value, "unit": "image-steps/s",
+    if train:
+        sample = (f"oracle port of the reference training step (PixArtMS.forward with autograd + IDDPM loss + backward, fp32, torch "
+                  f"CPU, {threads} threads) at {side * 8}px, ONE image: 1-block and 3-block slices timed, full 28-block step = "
+                  f"fixed + 28 x per-block; median of {len(vals)} samples, {t_all:.1f} s of CPU work")
+    else:
+        sample = (f"oracle port of the reference PixArtMS.forward (fp32, torch CPU, {threads} threads) at {side * 8}px, forward "
+                  f"batch 2 (one image with CFG): 2-block and 6-block slices timed, full 28-block forward = fixed + 28 x "
+                  f"per-block; median of {len(vals)} samples, {t_all:.1f} s of CPU work")
+    line = {"impl": "reference", "metric": "train-images/sec" if train else "denoise-steps/sec", "value": value,
+            "unit": "images/s" if train else "image-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "note": "reference is pure Python; its CPU path timed via the oracle port "
                        "(the reference itself cannot travel to the GPU box)"},
-            "cpu_baseline": {"value": value, "unit": "image-steps/s", "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": "image-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "cpu_baseline": {"value": value, "unit": "images/s" if train else "image-steps/s", "cores": threads, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "images/s" if train else "image-steps/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     _emit(line)
 
@@ -520,6 +556,13 @@ def run_train(args, wl):
                 "e2e": {"value": imgs * world * args.steps / (ms_e2e / 1000.0), "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": None}
+        if world == 1 and not args.no_cpu_baseline:
+            threads = pick_cpu_threads()
+            v, dt = cpu_reference_train_sample(side, pe, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
+                                    "sample": f"oracle port of the reference training step (forward with autograd + IDDPM loss + "
+                                              f"backward, fp32 torch CPU), {side * 8}px, one image: 1- and 3-block slices timed "
+                                              f"({dt:.1f} s), full step = fixed + 28 x per-block"}
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
