@@ -8,7 +8,8 @@ tape: every node below calls into libpixart_sm100.so in both directions --
                                           weight-gradient form: both activations consumed MN-major in their natural
                                           layouts, split-K, fp32 TMA reduce-add epilogue), db by pxa_colsum_bf16
   LnModulateFn    LN(x)(1+scale)+shift    bwd: pxa_ln_modulate_bwd (dx, d shift, d scale)            PixArtMS.py:75,77
-  GateResidualFn  x + gate * y            bwd: pxa_gate_residual_bwd (dy, d gate)                    PixArtMS.py:75-77
+  LinearGateResidualFn  x + gate*(aW^T+b) one GEMM launch (fp32 residual epilogue, aux = branch); bwd: pxa_gate_residual_bwd
+                                          (d branch, d gate) then the Linear backward            PixArtMS.py:75-77
   GeluFn          gelu_tanh(pre)          bwd: pxa_gelu_tanh_bf16 with dh                            timm Mlp.act
   SelfAttnFn / CrossAttnFn / AttnKVFn     bwd: pxa_flash_attn_d72_bwd_bf16 (flash-attention-2 recomputation from lse)
                                                                                                 PixArt_blocks.py:52-53,153
@@ -191,41 +192,6 @@ class LnModulateFn(torch.autograd.Function):
             dmod[:, i_shift] = dsh
             dmod[:, i_scale] = dsc
         return dx, dmod, None, None, None
-
-
-class GateResidualFn(torch.autograd.Function):
-    """out = x + mod[:, i_gate] * y (i_gate < 0: no gate); x, out fp32 (B*N, C), y bf16."""
-
-    @staticmethod
-    def forward(ctx, x32, y, mod, i_gate, rows_per_batch):
-        x32, y = x32.contiguous(), y.contiguous()
-        out = torch.empty_like(x32)
-        gate = mod[:, i_gate] if i_gate >= 0 else None
-        lib.gate_residual_fwd(x32, y, gate, out, gate_batch_stride=mod.stride(0) if gate is not None else 0,
-                              rows_per_batch=rows_per_batch)
-        ctx.save_for_backward(y, mod if gate is not None else None)
-        ctx.idx = (i_gate, rows_per_batch)
-        return out
-
-    @staticmethod
-    def backward(ctx, dout):
-        y, mod = ctx.saved_tensors
-        i_gate, rpb = ctx.idx
-        dout = dout.contiguous()
-        dy = torch.empty(dout.shape, dtype=torch.bfloat16, device=dout.device)
-        dmod = None
-        if mod is not None:
-            B, G, C = mod.shape
-            want_dgate = ctx.needs_input_grad[2]
-            dg = torch.zeros((B, C), dtype=torch.float32, device=dout.device) if want_dgate else None
-            lib.gate_residual_bwd(dout, y if want_dgate else None, mod[:, i_gate], dy, dg, gate_batch_stride=mod.stride(0),
-                                  rows_per_batch=rpb)
-            if want_dgate:
-                dmod = torch.zeros_like(mod)
-                dmod[:, i_gate] = dg
-        else:
-            lib.gate_residual_bwd(dout, None, None, dy, None, rows_per_batch=rpb)
-        return dout, dy, dmod, None, None
 
 
 class GeluFn(torch.autograd.Function):

@@ -449,7 +449,10 @@ class PixArtMS(nn.Module):
         -> (B, 8, H, W)   (PixArtMS.py:165-211)."""
         w0 = self.blocks[0].attn.qkv.weight
         if _wants_grad(self, x, y):
-            return self._forward_train(x, timestep, y, mask=mask, data_info=data_info)
+            # the kernels fix their own precisions (bf16 operands, fp32 accumulation / statistics / residual stream); an
+            # ambient autocast (accelerate's mixed precision, train.py:369) must not down-cast the fp32 torch glue around them
+            with torch.autocast(device_type="cuda", enabled=False):
+                return self._forward_train(x, timestep, y, mask=mask, data_info=data_info)
         _require_kernel_ready(w0, "PixArtMS.forward")
         dt, dev, C, p = self.dtype, w0.device, self.hidden_size, self.patch_size
         B = x.shape[0]
