@@ -40,6 +40,12 @@ namespace pxa {
 #ifndef PXA_BWD_EW
 #define PXA_BWD_EW 4
 #endif
+// Experiment switch (round 2; default 0 = the validated kernel): the TMA producer brings lse / delta of every streamed query
+// sub-block into the stage (two 1-D bulk copies on the stage's full barrier) instead of the elementwise warps loading them
+// and handing them over through a per-sub-block 512-thread named barrier.  Needs Nq % 4 == 0 (16-byte aligned copies).
+#ifndef PXA_BWD_TMA_STATS
+#define PXA_BWD_TMA_STATS 0
+#endif
 constexpr int kBEw = PXA_BWD_EW;
 constexpr int kBEwThreads = 128 * kBEw;        // elementwise threads
 constexpr int kBCols = 64 / kBEw;      // score columns per thread per sub-block
@@ -54,8 +60,8 @@ constexpr int kBStages = 4;
 constexpr int kBOffX1 = 0;
 constexpr int kBOffX2 = kBTile;
 constexpr int kBOffY = 2 * kBTile;             // stage s: Y1 at kBOffY + s * 2 * kBYTile, Y2 right behind it
-constexpr int kBOffStat = kBOffY + kBStages * 2 * kBYTile;  // 2 buffers x (lse[64] | delta[64]) fp32
-constexpr int kBOffBars = kBOffStat + 1024;
+constexpr int kBOffStat = kBOffY + kBStages * 2 * kBYTile;  // 2 buffers x (lse[64] | delta[64]) fp32 (one per stage with TMA stats)
+constexpr int kBOffBars = kBOffStat + (PXA_BWD_TMA_STATS ? kBStages * 512 : 1024);
 constexpr int kBwdSmem = kBOffBars + 256 + 1024;            // + alignment slack
 
 constexpr uint32_t kBColS = 0;       // S'  two 64-column buffers; each thread's bf16 P' over the first half of its own column slice
@@ -149,6 +155,16 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
         uint8_t* y1 = smem + kBOffY + stage * 2 * kBYTile;
         uint8_t* y2 = y1 + kBYTile;
         const int yrow = y_row0 + it * kBSub;
+#if PXA_BWD_TMA_STATS
+        if (kDKV) {
+          const uint32_t sb = (uint32_t)min(kBSub, p.Nq - it * kBSub) * 4u;            // bytes of lse (and of delta) in this sub-block
+          const size_t so = ((size_t)b * p.H + h) * p.Nq + (size_t)it * kBSub;
+          float* sdst = reinterpret_cast<float*>(smem + kBOffStat) + stage * 128;
+          mbar_arrive_expect_tx(&y_full[stage], 2 * kBYTile + 2 * sb);
+          tma_load_1d(sdst, p.lse + so, sb, &y_full[stage]);
+          tma_load_1d(sdst + 64, p.delta + so, sb, &y_full[stage]);
+        } else
+#endif
         mbar_arrive_expect_tx(&y_full[stage], 2 * kBYTile);
         tma_load_3d(y1, &tm_y1m, &y_full[stage], 0, h, yrow, kEvictLast);
         tma_load_3d(y1 + kBYMain, &tm_y1t, &y_full[stage], 64, h, yrow, kEvictLast);
@@ -224,24 +240,32 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
       const float l = -p.lse[stat_base + qrow], d = p.delta[stat_base + qrow];
       nlse2 = f32x2(l, l);
       delta2 = f32x2(d, d);
-    } else if (n_iter > 0) {                       // -lse | delta of the first streamed query sub-block -> smem buffer 0
+    }
+#if !PXA_BWD_TMA_STATS
+    else if (n_iter > 0) {                         // -lse | delta of the first streamed query sub-block -> smem buffer 0
       if (tid < 128) {
         const int qi = min(tid & 63, p.Nq - 1);
         stat[tid] = tid < 64 ? -p.lse[stat_base + qi] : p.delta[stat_base + qi];
       }
       named_bar_sync(1, kBEwThreads);
     }
+#endif
 
     for (int n = 0; n < n_iter; ++n) {
       const int hh = n & 1;
       const uint32_t t_s = tmem_base + kBColS + lane_sel + kBSub * hh + kBCols * half;
       const uint32_t t_dp = tmem_base + kBColDP + lane_sel + kBSub * hh + kBCols * half;
+#if PXA_BWD_TMA_STATS
+      const float* st = stat + (n % kBStages) * 128 + kBCols * half;   // +lse | delta of the stage, landed with the tiles
+      if (kDKV) mbar_wait(&y_full[n % kBStages], (n / kBStages) & 1);  // (complete long ago) acquire the TMA-written stats
+#else
       float nxt = 0.f;
       if (kDKV && n + 1 < n_iter && tid < 128) {   // next sub-block's statistics: global load in flight during this one
         const size_t o = stat_base + min((n + 1) * kBSub + (tid & 63), p.Nq - 1);    // the last sub-block may be partial
         nxt = tid < 64 ? -p.lse[o] : p.delta[o];
       }
       const float* st = stat + (n & 1) * 128 + kBCols * half;  // lse of this thread's columns; delta 64 floats further
+#endif
       // the last sub-block of the stream (queries in the dKV pass, keys in the dQ pass) may be partial
       const int rem = (kDKV ? p.Nq : kv_len) - n * kBSub - kBCols * half;
       mbar_wait(&s_full[hh], (n >> 1) & 1);
@@ -256,9 +280,13 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
         for (int i = 0; i < kBCols; i += 2) {
           uint64_t nl, dl;
           if (kDKV) {
-            const float2 l2 = *reinterpret_cast<const float2*>(st + i);          // -lse of the two columns
+            const float2 l2 = *reinterpret_cast<const float2*>(st + i);          // -lse (+lse with TMA stats) of the two columns
             const float2 d2 = *reinterpret_cast<const float2*>(st + 64 + i);     // delta
+#if PXA_BWD_TMA_STATS
+            nl = f32x2(-l2.x, -l2.y);
+#else
             nl = f32x2(l2.x, l2.y);
+#endif
             dl = f32x2(d2.x, d2.y);
           } else {
             nl = nlse2;
@@ -287,10 +315,12 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[hh]);
+#if !PXA_BWD_TMA_STATS
       if (kDKV) {
         if (n + 1 < n_iter && tid < 128) stat[((n + 1) & 1) * 128 + tid] = nxt;
         named_bar_sync(1, kBEwThreads);
       }
+#endif
     }
 
     // ---- epilogue: column slice 0 writes acc2 (dK / dQ, times the softmax scale), slice 1 writes acc1 (dV, dKV pass only)
@@ -373,6 +403,9 @@ extern "C" int pxa_flash_attn_d72_bwd_bf16(const PxaAttnBwdArgs* args, void* str
   if ((reinterpret_cast<uintptr_t>(a.dq) | reinterpret_cast<uintptr_t>(a.dk) | reinterpret_cast<uintptr_t>(a.dv) |
        reinterpret_cast<uintptr_t>(a.o) | reinterpret_cast<uintptr_t>(a.d_o)) & 15)
     return fail(PXA_ERR_ALIGN, "o / dO / dq / dk / dv must be 16-byte aligned");
+#if PXA_BWD_TMA_STATS
+  if (a.Nq % 4) return fail(PXA_ERR_ARG, "PXA_BWD_TMA_STATS build: Nq must be a multiple of 4 (got %d)", a.Nq);
+#endif
   PXA_REQUIRE_SM100();
   int rc = pxa_attn_delta_d72(a.o, a.d_o, a.delta, a.B, a.H, a.Nq, a.ldo, a.lddo, stream);
   if (rc) return rc;

@@ -119,6 +119,12 @@ PXA_DEVICE void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
                "r"(c0), "r"(c1)
                : "memory");
 }
+// 1-D bulk copy global -> smem (no tensor map): `bytes` a multiple of 16, both addresses 16-byte aligned; completes on `bar`.
+PXA_DEVICE void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gmem_src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 PXA_DEVICE void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint64_t hint) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
