@@ -46,6 +46,11 @@ namespace pxa {
 #ifndef PXA_BWD_TMA_STATS
 #define PXA_BWD_TMA_STATS 0
 #endif
+// Experiment switch (round 2; default 0): split-phase TMEM loads -- S'(n+1) / dP'(n+1) are requested as soon as the registers
+// of sub-block n are free, behind the TMEM store + fence + arrive of n, instead of at the top of the next iteration.
+#ifndef PXA_BWD_PREFETCH
+#define PXA_BWD_PREFETCH 0
+#endif
 constexpr int kBEw = PXA_BWD_EW;
 constexpr int kBEwThreads = 128 * kBEw;        // elementwise threads
 constexpr int kBCols = 64 / kBEw;      // score columns per thread per sub-block
@@ -72,6 +77,16 @@ constexpr uint32_t kBColAcc1 = 384;  // dV (dKV pass): 80 columns
 // size-overloaded TMEM accessors so that the elementwise stage is written once for 32 or 16 columns per thread
 PXA_DEVICE void ld_scores(uint32_t t0, uint32_t (&a)[32], uint32_t t1, uint32_t (&b)[32]) { tmem_ld_32x32b_x32_pair(t0, a, t1, b); }
 PXA_DEVICE void ld_scores(uint32_t t0, uint32_t (&a)[16], uint32_t t1, uint32_t (&b)[16]) { tmem_ld_32x32b_x16_pair(t0, a, t1, b); }
+PXA_DEVICE void ld_scores_nowait(uint32_t t0, uint32_t (&a)[32], uint32_t t1, uint32_t (&b)[32]) {
+  tmem_ld_32x32b_x32_nowait(t0, a);
+  tmem_ld_32x32b_x32_nowait(t1, b);
+}
+PXA_DEVICE void ld_scores_nowait(uint32_t t0, uint32_t (&a)[16], uint32_t t1, uint32_t (&b)[16]) {
+  tmem_ld_32x32b_x16_nowait(t0, a);
+  tmem_ld_32x32b_x16_nowait(t1, b);
+}
+PXA_DEVICE void ld_scores_wait(uint32_t (&a)[32], uint32_t (&b)[32]) { tmem_ld_wait_x32(a); tmem_ld_wait_x32(b); }
+PXA_DEVICE void ld_scores_wait(uint32_t (&a)[16], uint32_t (&b)[16]) { tmem_ld_wait_x16(a); tmem_ld_wait_x16(b); }
 PXA_DEVICE void st_packed(uint32_t t, const uint32_t (&r)[16]) { tmem_st_32x32b_x16(t, r); }
 PXA_DEVICE void st_packed(uint32_t t, const uint32_t (&r)[8]) { tmem_st_32x32b_x8(t, r); }
 
@@ -251,6 +266,14 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
     }
 #endif
 
+#if PXA_BWD_PREFETCH
+    uint32_t vs[kBCols], vd[kBCols];               // scores of the current sub-block (requested one sub-block ahead)
+    if (n_iter > 0) {
+      mbar_wait(&s_full[0], 0);
+      tc_fence_after();
+      ld_scores_nowait(tmem_base + kBColS + lane_sel + kBCols * half, vs, tmem_base + kBColDP + lane_sel + kBCols * half, vd);
+    }
+#endif
     for (int n = 0; n < n_iter; ++n) {
       const int hh = n & 1;
       const uint32_t t_s = tmem_base + kBColS + lane_sel + kBSub * hh + kBCols * half;
@@ -268,10 +291,14 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
 #endif
       // the last sub-block of the stream (queries in the dKV pass, keys in the dQ pass) may be partial
       const int rem = (kDKV ? p.Nq : kv_len) - n * kBSub - kBCols * half;
+#if PXA_BWD_PREFETCH
+      ld_scores_wait(vs, vd);
+#else
       mbar_wait(&s_full[hh], (n >> 1) & 1);
       tc_fence_after();
       uint32_t vs[kBCols], vd[kBCols];
       ld_scores(t_s, vs, t_dp, vd);
+#endif
       uint32_t pp[kBCols / 2], pd[kBCols / 2];
       // packed fp32 pairs (FFMA2 / FADD2 / FMUL2: one issue slot for two elements), exp2 on the MUFU pipe.  The masking
       // selects exist only in the copy of the loop taken by a partial last sub-block of the dQ pass.
@@ -309,6 +336,14 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
       };
       if (rem < kBCols) compute(std::true_type{});
       else compute(std::false_type{});
+#if PXA_BWD_PREFETCH
+      if (n + 1 < n_iter) {                        // S'(n+1) / dP'(n+1) sit in the other buffer (normally complete long ago)
+        const uint32_t off = kBSub * (hh ^ 1) + kBCols * half;
+        mbar_wait(&s_full[hh ^ 1], ((n + 1) >> 1) & 1);
+        tc_fence_after();
+        ld_scores_nowait(tmem_base + kBColS + lane_sel + off, vs, tmem_base + kBColDP + lane_sel + off, vd);
+      }
+#endif
       // bf16 results over the fp32 columns this thread has just consumed (its own slice: no cross-warp hazard)
       if (kDKV) st_packed(t_s, pp);
       st_packed(t_dp, pd);
