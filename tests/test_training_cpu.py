@@ -149,3 +149,62 @@ def test_bf16_shadow_cache_semantics():
     assert ag._shadow(torch.nn.Linear(4, 4, bias=False), "b") is None
     ag.clear_shadow_cache(lin)
     assert "_pxa_shadow" not in lin.__dict__
+
+
+class _ToyDenoiser(torch.nn.Module):
+    """CPU stand-in with the denoiser's call signature (x, timestep, y, mask, data_info) -> (n, 8, h, w) and the model's
+    parameter naming (blocks.<i>.*), so `train_step` + `IDDPMLoss` + `GradBucketReducer` run end to end without a GPU."""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(5)
+        self.inp = torch.nn.Conv2d(4, 8, 1)
+        self.blocks = torch.nn.ModuleList([torch.nn.Conv2d(8, 8, 3, padding=1) for _ in range(2)])
+        self.t_proj = torch.nn.Linear(1, 8)
+        self.y_proj = torch.nn.Linear(16, 8)
+
+    def forward(self, x, timestep, y, mask=None, data_info=None):
+        h = self.inp(x) + self.t_proj(timestep.float()[:, None] / 1000.0)[:, :, None, None]
+        cond = (self.y_proj(y.squeeze(1)) * mask.reshape(x.shape[0], -1, 1).float()).sum(1)
+        for b in self.blocks:
+            h = h + torch.tanh(b(h + cond[:, :, None, None]))
+        return h
+
+
+def _train_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pixart_sigma_b200.training import train_step
+        m = _ToyDenoiser()
+        red = GradBucketReducer(m)
+        g = torch.Generator().manual_seed(21)
+        x0, noise = torch.randn(4, 4, 8, 8, generator=g) * 0.5, torch.randn(4, 4, 8, 8, generator=g)
+        y, t = torch.randn(4, 1, 6, 16, generator=g), torch.tensor([0, 250, 600, 999])
+        mask = (torch.arange(6)[None] < torch.tensor([6, 2, 4, 1])[:, None]).long().view(4, 1, 1, 6)
+        lo, hi = rank * 2, rank * 2 + 2                                        # this rank's images
+        red.zero_grad()
+        loss = train_step(m, IDDPMLoss(), x0[lo:hi], t[lo:hi], y[lo:hi], mask[lo:hi], noise=noise[lo:hi], reducer=red)
+        torch.save({"loss": loss, "grads": {n: p.grad.clone() for n, p in m.named_parameters()}}, os.path.join(out_dir, f"t{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_train_step_gloo_world2(tmp_path):
+    """N = 2 training step on CPU (gloo): per-rank IDDPM loss + backward + bucketed all-reduce equals the single-process
+    step on the whole batch (the reducer averages; equal per-rank batch sizes)."""
+    from pixart_sigma_b200.training import train_step
+    port = _free_port()
+    mp.spawn(_train_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "t0.pt"), torch.load(tmp_path / "t1.pt")
+    m = _ToyDenoiser()
+    g = torch.Generator().manual_seed(21)
+    x0, noise = torch.randn(4, 4, 8, 8, generator=g) * 0.5, torch.randn(4, 4, 8, 8, generator=g)
+    y, t = torch.randn(4, 1, 6, 16, generator=g), torch.tensor([0, 250, 600, 999])
+    mask = (torch.arange(6)[None] < torch.tensor([6, 2, 4, 1])[:, None]).long().view(4, 1, 1, 6)
+    loss = train_step(m, IDDPMLoss(), x0, t, y, mask, noise=noise)
+    assert torch.allclose((r0["loss"] + r1["loss"]) / 2, loss, rtol=1e-5)
+    for n, p in m.named_parameters():
+        assert torch.allclose(r0["grads"][n], p.grad, rtol=1e-4, atol=1e-6), n
+        assert torch.equal(r0["grads"][n], r1["grads"][n]), n
