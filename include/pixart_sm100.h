@@ -49,6 +49,11 @@ uint64_t pxa_launch_count(void);
 #define PXA_EPI_BIAS 0          /* out = acc + bias                                   */
 #define PXA_EPI_BIAS_GELU 1     /* out = gelu_tanh(acc + bias)                        */
 #define PXA_EPI_BIAS_RESIDUAL 2 /* out = residual + gate[row/rows_per_batch, n] * (acc + bias); gate NULL -> 1 */
+/* Training fusions of the MLP (timm Mlp, PixArtMS.py:67,77).  EXPERIMENTAL: compiled, but not yet validated on a B200 --
+ * no default path calls them (pixart_sigma_b200.autograd uses them only with PXA_EXPERIMENTAL_FUSED_MLP=1) and their
+ * GPU tests are skipped unless PXA_EXPERIMENTAL=1. */
+#define PXA_EPI_BIAS_GELU_AUX 3 /* out = gelu_tanh(acc + bias), out_aux_bf16 = acc + bias (pre-activation kept for the backward) */
+#define PXA_EPI_MUL_DGELU 4     /* out = acc * gelu_tanh'(pre), pre = `residual` as bf16 [M, N] row stride ldo; bias must be NULL  */
 
 typedef struct PxaGemmArgs {
   const void* a;        /* bf16 [M, K], row stride lda (elements)                                   */

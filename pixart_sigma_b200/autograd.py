@@ -25,7 +25,11 @@ from typing import Optional
 
 import torch
 
+import os
+
 from . import lib
+
+_FUSED_MLP = os.environ.get("PXA_EXPERIMENTAL_FUSED_MLP", "0") == "1"      # off: the validated op sequence
 
 def _shadow(mod: torch.nn.Module, kind: str) -> Optional[torch.Tensor]:
     """bf16 copy of `mod.weight` ('w'), its bf16 transpose ('t') or the bf16 bias ('b'), cached ON THE MODULE and
@@ -161,6 +165,49 @@ class LinearGateResidualFn(torch.autograd.Function):
             lib.gate_residual_bwd(dout, None, None, dy, None, rows_per_batch=rpb)
         da, dw, db = _linear_backward(ctx.needs_input_grad[:3], a, weight, bias, ctx.mod, dy)
         return da, dw, db, None, dout, dtab, None, None
+
+
+class MlpGateResidualFn(torch.autograd.Function):
+    """EXPERIMENTAL (PXA_EXPERIMENTAL_FUSED_MLP=1; not yet validated on a B200): the whole MLP branch
+    out = x32 + gate * fc2(gelu(fc1(xn))) in TWO GEMM launches -- fc1 with the GELU epilogue that also keeps the
+    pre-activation (EPI_BIAS_GELU_AUX), fc2 with the gated residual epilogue -- and a backward whose fc2 dgrad GEMM applies
+    gelu'(pre) in its epilogue (EPI_MUL_DGELU): no separate GELU forward / backward passes over the [M, 4C] hidden."""
+
+    @staticmethod
+    def forward(ctx, xn, w1, b1, w2, b2, fc1, fc2, x32, tab, i_gate, rows_per_batch):
+        xn, x32 = xn.contiguous(), x32.contiguous()
+        M, Hd, N = xn.shape[0], w1.shape[0], w2.shape[0]
+        bf = dict(dtype=torch.bfloat16, device=xn.device)
+        h, pre = torch.empty((M, Hd), **bf), torch.empty((M, Hd), **bf)
+        lib.gemm(xn, _shadow(fc1, "w"), _shadow(fc1, "b"), h, epilogue=lib.EPI_BIAS_GELU_AUX, out_aux=pre)
+        out = torch.empty((M, N), dtype=torch.float32, device=xn.device)
+        y = torch.empty((M, N), **bf)
+        lib.gemm(h, _shadow(fc2, "w"), _shadow(fc2, "b"), out, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x32, gate=tab[:, i_gate],
+                 gate_batch_stride=tab.stride(0), rows_per_batch=rows_per_batch, out_aux=y, aux_is_branch=True)
+        ctx.save_for_backward(xn, pre, h, y, tab, w1, b1, w2, b2)
+        ctx.mods, ctx.idx = (fc1, fc2), (i_gate, rows_per_batch)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xn, pre, h, y, tab, w1, b1, w2, b2 = ctx.saved_tensors
+        fc1, fc2 = ctx.mods
+        i_gate, rpb = ctx.idx
+        dout = dout.contiguous()
+        dev = dout.device
+        dy = torch.empty(dout.shape, dtype=torch.bfloat16, device=dev)
+        want = ctx.needs_input_grad[8]
+        dg = torch.zeros((tab.shape[0], tab.shape[2]), dtype=torch.float32, device=dev) if want else None
+        lib.gate_residual_bwd(dout, y if want else None, tab[:, i_gate], dy, dg, gate_batch_stride=tab.stride(0), rows_per_batch=rpb)
+        dtab = None
+        if want:
+            dtab = torch.zeros_like(tab)
+            dtab[:, i_gate] = dg
+        _, dw2, db2 = _linear_backward((False, True, True), h, w2, b2, fc2, dy)
+        dpre = torch.empty_like(pre)
+        lib.gemm(dy, _shadow(fc2, "t"), None, dpre, epilogue=lib.EPI_MUL_DGELU, residual=pre)     # dh * gelu'(pre) in the epilogue
+        dxn, dw1, db1 = _linear_backward((True, True, True), xn, w1, b1, fc1, dpre)
+        return dxn, dw1, db1, dw2, db2, None, None, dout, dtab, None, None
 
 
 class LnModulateFn(torch.autograd.Function):
@@ -411,8 +458,11 @@ def block_forward_train(blk, x32: torch.Tensor, cond: torch.Tensor, kv_len: Opti
     x32 = LinearGateResidualFn.apply(ao, ca.proj.weight, ca.proj.bias, ca.proj, x32, mod, -1, N)
     # (3) x += gate_mlp * fc2(gelu_tanh(fc1(LN(x) * (1 + scale_mlp) + shift_mlp)))               PixArtMS.py:77
     xn = LnModulateFn.apply(x32, mod, 3, 4, N)
-    h = GeluFn.apply(linear(xn, mlp.fc1))
-    x32 = LinearGateResidualFn.apply(h, mlp.fc2.weight, mlp.fc2.bias, mlp.fc2, x32, mod, 5, N)
+    if _FUSED_MLP:                                    # experimental, see MlpGateResidualFn
+        x32 = MlpGateResidualFn.apply(xn, mlp.fc1.weight, mlp.fc1.bias, mlp.fc2.weight, mlp.fc2.bias, mlp.fc1, mlp.fc2, x32, mod, 5, N)
+    else:
+        h = GeluFn.apply(linear(xn, mlp.fc1))
+        x32 = LinearGateResidualFn.apply(h, mlp.fc2.weight, mlp.fc2.bias, mlp.fc2, x32, mod, 5, N)
     if keep is not None:
         keep["replay"] = True            # the next call with this dict is the recomputation
     return x32

@@ -64,15 +64,6 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16
 }
 
 // ------------------------------------------------------------------------------------------------- GELU(tanh)
-PXA_DEVICE float gelu_tanh_grad(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  const float x2 = x * x;
-  const float u = k0 * x * fmaf(k1, x2, 1.0f);
-  const float t = fast_tanh(u);
-  const float du = k0 * fmaf(3.0f * k1, x2, 1.0f);
-  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
-}
-
 template <bool kBwd>
 __global__ void __launch_bounds__(256) gelu_kernel(const uint4* __restrict__ pre, const uint4* __restrict__ dh,
                                                    uint4* __restrict__ out, long long n8) {

@@ -295,6 +295,10 @@ static int dispatch_epi2(const PxaGemmArgs& a, cudaStream_t s) {
       return launch_gemm2<BN, PXA_EPI_BIAS, __nv_bfloat16>(a, s);
     case PXA_EPI_BIAS_GELU:
       return launch_gemm2<BN, PXA_EPI_BIAS_GELU, __nv_bfloat16>(a, s);
+    case PXA_EPI_BIAS_GELU_AUX:
+      return launch_gemm2<BN, PXA_EPI_BIAS_GELU_AUX, __nv_bfloat16>(a, s);
+    case PXA_EPI_MUL_DGELU:
+      return launch_gemm2<BN, PXA_EPI_MUL_DGELU, __nv_bfloat16>(a, s);
     case PXA_EPI_BIAS_RESIDUAL:
       if (a.out_dtype == PXA_DTYPE_F32) return launch_gemm2<BN, PXA_EPI_BIAS_RESIDUAL, float>(a, s);
       return launch_gemm2<BN, PXA_EPI_BIAS_RESIDUAL, __nv_bfloat16>(a, s);

@@ -231,19 +231,40 @@ PXA_DEVICE void stage_epi_consts(EpiConst* cb, const GemmParams& p, int tid, int
   if (tid == 0) cb->row_split = (b0 + 1) * p.rows_per_batch - m0;
 }
 
-// bf16 output (EPI 0/1) with staged constants: bias from smem (LDS broadcast).
+// bf16 output (EPI 0/1/3/4) with staged constants: bias from smem (LDS broadcast).
+//   PXA_EPI_BIAS_GELU_AUX: out = gelu(acc + bias) and, through the same smem transpose, out_aux = acc + bias (the
+//                          pre-activation the GELU backward needs) -- the MLP's first GEMM in training;
+//   PXA_EPI_MUL_DGELU:     out = acc * gelu'(pre), pre = p.residual read as bf16 [M, N] (row stride ldo) -- the dgrad GEMM of
+//                          the MLP's second layer producing the gradient of the pre-activation directly.
 template <int EPI>
 PXA_DEVICE void epilogue_chunk_bf16_c(uint32_t (&v)[32], const GemmParams& p, const EpiConst* cb, uint8_t* stile, int lane,
                                       int row0, int col0, int ccol) {
   uint32_t pk[16];
+  [[maybe_unused]] uint32_t pk2[16];
   const float4* bp = reinterpret_cast<const float4*>(cb->bias + ccol);
+  [[maybe_unused]] uint4 pre[4];
+  if constexpr (EPI == PXA_EPI_MUL_DGELU) {
+    const __nv_bfloat16* pr = reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)(row0 + lane) * p.ldo + col0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      pre[i] = (row0 + lane < p.M && col0 + 8 * i < p.N) ? *reinterpret_cast<const uint4*>(pr + 8 * i) : make_uint4(0u, 0u, 0u, 0u);
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float4 b = bp[i];
     float x0 = __uint_as_float(v[4 * i]) + b.x, x1 = __uint_as_float(v[4 * i + 1]) + b.y;
     float x2 = __uint_as_float(v[4 * i + 2]) + b.z, x3 = __uint_as_float(v[4 * i + 3]) + b.w;
-    if (EPI == PXA_EPI_BIAS_GELU) {
+    if constexpr (EPI == PXA_EPI_BIAS_GELU_AUX) {
+      pk2[2 * i] = pack_bf16x2(x0, x1);
+      pk2[2 * i + 1] = pack_bf16x2(x2, x3);
+    }
+    if (EPI == PXA_EPI_BIAS_GELU || EPI == PXA_EPI_BIAS_GELU_AUX) {
       x0 = gelu_tanh(x0); x1 = gelu_tanh(x1); x2 = gelu_tanh(x2); x3 = gelu_tanh(x3);
+    }
+    if constexpr (EPI == PXA_EPI_MUL_DGELU) {
+      const uint32_t w0 = (i & 1) ? pre[i >> 1].z : pre[i >> 1].x, w1 = (i & 1) ? pre[i >> 1].w : pre[i >> 1].y;
+      x0 *= gelu_tanh_grad(bf16_lo(w0)); x1 *= gelu_tanh_grad(bf16_hi(w0));
+      x2 *= gelu_tanh_grad(bf16_lo(w1)); x3 *= gelu_tanh_grad(bf16_hi(w1));
     }
     pk[2 * i] = pack_bf16x2(x0, x1);
     pk[2 * i + 1] = pack_bf16x2(x2, x3);
@@ -270,6 +291,22 @@ PXA_DEVICE void epilogue_chunk_bf16_c(uint32_t (&v)[32], const GemmParams& p, co
     if (grow < p.M && gcol < p.N) *reinterpret_cast<uint4*>(out + (size_t)grow * p.ldo + gcol) = u[it];
   }
   __syncwarp();
+  if constexpr (EPI == PXA_EPI_BIAS_GELU_AUX) {              // second pass of the same transpose for the pre-activation
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc)
+      *reinterpret_cast<uint4*>(stile + lane * 64 + ((cc ^ sw) << 4)) = make_uint4(pk2[4 * cc], pk2[4 * cc + 1], pk2[4 * cc + 2], pk2[4 * cc + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + (lane >> 2);
+      const uint4 w = *reinterpret_cast<const uint4*>(stile + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+      const int grow = row0 + r;
+      const int gcol = col0 + c * 8;
+      if (grow < p.M && gcol < p.N) *reinterpret_cast<uint4*>(p.out_aux + (size_t)grow * p.ldo + gcol) = w;
+    }
+    __syncwarp();
+  }
 }
 
 // One residual chunk for the calling thread (row r of the 128-row tile) with staged constants.

@@ -386,6 +386,10 @@ static int dispatch_epi(const PxaGemmArgs& a, cudaStream_t s) {
     case PXA_EPI_BIAS_GELU:
       if (a.out_dtype != PXA_DTYPE_BF16) return fail(PXA_ERR_ARG, "EPI_BIAS_GELU writes bf16 only");
       return launch_gemm<BN, PXA_EPI_BIAS_GELU, __nv_bfloat16>(a, s);
+    case PXA_EPI_BIAS_GELU_AUX:
+      return launch_gemm<BN, PXA_EPI_BIAS_GELU_AUX, __nv_bfloat16>(a, s);
+    case PXA_EPI_MUL_DGELU:
+      return launch_gemm<BN, PXA_EPI_MUL_DGELU, __nv_bfloat16>(a, s);
     case PXA_EPI_BIAS_RESIDUAL:
       if (a.residual == nullptr) return fail(PXA_ERR_ARG, "EPI_BIAS_RESIDUAL needs residual");
       if (a.out_dtype == PXA_DTYPE_F32) return launch_gemm<BN, PXA_EPI_BIAS_RESIDUAL, float>(a, s);
@@ -492,6 +496,9 @@ extern "C" int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream) {
   if (a.epilogue == PXA_EPI_BIAS_RESIDUAL && a.residual == nullptr) return fail(PXA_ERR_ARG, "EPI_BIAS_RESIDUAL needs residual");
   if (a.epilogue != PXA_EPI_BIAS_RESIDUAL && a.out_dtype != PXA_DTYPE_BF16)
     return fail(PXA_ERR_ARG, "EPI_BIAS / EPI_BIAS_GELU write bf16 only");
+  if (a.epilogue == PXA_EPI_BIAS_GELU_AUX && a.out_aux_bf16 == nullptr) return fail(PXA_ERR_ARG, "EPI_BIAS_GELU_AUX needs out_aux_bf16");
+  if (a.epilogue == PXA_EPI_MUL_DGELU && (a.residual == nullptr || a.bias != nullptr))
+    return fail(PXA_ERR_ARG, "EPI_MUL_DGELU needs the pre-activation in `residual` and no bias");
   if (a.cta_pair < 0 || a.cta_pair > 2) return fail(PXA_ERR_ARG, "cta_pair must be 0, 1 or 2");
   // auto (measured at M = 32768, tools/gemm_bench.py): the CTA pair with 256 x 256 tiles wins for every bias / GELU
   // GEMM; the fp32 residual epilogue is HBM-bound at K = 1152 and streams through TMA chunk buffers on the single-CTA

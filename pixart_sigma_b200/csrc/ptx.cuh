@@ -421,4 +421,14 @@ PXA_DEVICE float gelu_tanh(float x) {
   return 0.5f * x * (1.0f + fast_tanh(u));
 }
 
+// d/dx gelu_tanh(x)  (same tanh.approx as the forward)
+PXA_DEVICE float gelu_tanh_grad(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float x2 = x * x;
+  const float u = k0 * x * fmaf(k1, x2, 1.0f);
+  const float t = fast_tanh(u);
+  const float du = k0 * fmaf(3.0f * k1, x2, 1.0f);
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
+}
+
 }  // namespace pxa

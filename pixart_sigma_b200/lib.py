@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PXA_LIB_PATH") or os.path.join(_HERE, "libpixart_sm100.so")   # override: experiment builds only
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
+EPI_BIAS_GELU_AUX, EPI_MUL_DGELU = 3, 4      # experimental MLP training fusions (include/pixart_sm100.h)
 DTYPE_BF16, DTYPE_F32 = 0, 1
 
 
