@@ -54,6 +54,18 @@ uint64_t pxa_launch_count(void);
  * GPU tests are skipped unless PXA_EXPERIMENTAL=1. */
 #define PXA_EPI_BIAS_GELU_AUX 3 /* out = gelu_tanh(acc + bias), out_aux_bf16 = acc + bias (pre-activation kept for the backward) */
 #define PXA_EPI_MUL_DGELU 4     /* out = acc * gelu_tanh'(pre), pre = `residual` as bf16 [M, N] row stride ldo; bias must be NULL  */
+/* adaLN-single modulate FUSED into the projection that follows it (norm1 + t2i_modulate + attn.qkv, PixArtMS.py:75 with
+ * PixArt_blocks.py:24-25,130; norm2 + t2i_modulate + mlp.fc1, PixArtMS.py:77): the LayerNorm'ed, modulated activations
+ * are never materialised.  With mu_r / rstd_r the LayerNorm statistics of row r of the fp32 residual stream x and
+ * (shift_b, scale_b) the modulation of its sample b,
+ *     sum_k [ (x[r,k] - mu_r) rstd_r (1 + scale_b[k]) + shift_b[k] ] W[n,k] + bias[n]
+ *   = rstd_r * ( acc[r,n] - mu_r * u_b[n] ) + v_b[n],     acc = A W^T,  A[r,k] = bf16( x[r,k] (1 + scale_b[k]) ),
+ *     u_b[n] = sum_k (1 + scale_b[k]) W[n,k],   v_b[n] = sum_k shift_b[k] W[n,k] + bias[n].
+ * A and the per-row statistics are by-products of the residual epilogue that produced x (`aux_scale`, `row_stats_out`
+ * below) or of pxa_ln_prepare; u_b / v_b are two tiny per-sample GEMVs per forward. */
+#define PXA_EPI_LN_BIAS 5       /* out = rstd*(acc - mu*u) + v            (`ln_*` fields; bias must be NULL: it is inside v) */
+#define PXA_EPI_LN_BIAS_GELU 6  /* out = gelu_tanh(rstd*(acc - mu*u) + v)                                                   */
+#define PXA_LN_STAT_PARTS 8     /* row statistics are kept as 8 partial (sum x, sum x^2) pairs per row: fp32 [M][8][2]      */
 
 typedef struct PxaGemmArgs {
   const void* a;        /* bf16 [M, K], row stride lda (elements)                                   */
@@ -80,6 +92,21 @@ typedef struct PxaGemmArgs {
   int32_t k_splits;     /* operands_mn_major only: 0 = auto (fill the 148 SMs), else the number of K splits        */
   int32_t aux_is_branch; /* EPI_BIAS_RESIDUAL with out_aux_bf16: 1 = the aux output receives acc + bias (the un-gated
                             branch output, which the backward of the gate needs) instead of a bf16 copy of out          */
+  /* --- producer side of the fused LayerNorm-modulate (EPI_BIAS_RESIDUAL, fp32 out, out_aux_bf16 set) */
+  const float* aux_scale;   /* fp32 or NULL: the bf16 aux copy becomes out[r,n] * aux_scale[b*aux_scale_batch_stride + n]
+                               (pass 1 + scale of the NEXT modulate: the aux output is then the A operand above)          */
+  int64_t aux_scale_batch_stride;
+  float* row_stats_out;     /* fp32 [M][PXA_LN_STAT_PARTS][2] or NULL: partial (sum, sum of squares) of each row of `out`
+                               over the columns of one output tile, part = the tile's column index; unused parts zeroed     */
+  /* --- consumer side (EPI_LN_BIAS / EPI_LN_BIAS_GELU) */
+  const float* ln_stats;    /* fp32 [M][PXA_LN_STAT_PARTS][2] partial sums of the rows of x (row_stats_out / pxa_ln_prepare) */
+  const float* ln_u;        /* fp32, u_b[n] at ln_u[b*ln_uv_batch_stride + n]                                                */
+  const float* ln_v;        /* fp32, v_b[n] at ln_v[b*ln_uv_batch_stride + n]                                                */
+  int64_t ln_uv_batch_stride;
+  int32_t ln_dim;           /* row length C of x the statistics were taken over                                              */
+  float ln_eps;
+  int32_t res_epilogue;     /* EPI_BIAS_RESIDUAL, fp32 out, CTA pair: 0 = auto, 1 = register-staged residual (coalesced
+                               loads, smem transpose), 2 = residual tile streamed through smem by TMA (row per thread)       */
 } PxaGemmArgs;
 int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream);
 
@@ -100,6 +127,28 @@ typedef struct PxaLnModArgs {
   float eps;
 } PxaLnModArgs;
 int pxa_ln_modulate(const PxaLnModArgs* args, void* stream);
+
+/* First link of the fused LayerNorm-modulate chain (see PXA_EPI_LN_BIAS): for the residual stream x as the patch embedding
+ * leaves it (PixArtMS.py:184), writes the A operand  a[r,:] = bf16( x[r,:] * (1 + scale[b,:]) )  and the row statistics
+ * stats[r][0] = (sum_k x[r,k], sum_k x[r,k]^2), stats[r][1..7] = 0  that the QKV GEMM of block 0 consumes.  Later links
+ * get both from the residual epilogues (PxaGemmArgs.aux_scale / row_stats_out).  HBM-bound: one read of x, one bf16 write.
+ */
+typedef struct PxaLnPrepareArgs {
+  const float* x;       /* fp32 [M, C] row stride ldx                 */
+  void* a_out;          /* bf16 [M, C] contiguous                     */
+  float* stats_out;     /* fp32 [M][PXA_LN_STAT_PARTS][2]             */
+  const float* scale;   /* fp32, (b, c) at scale[b*mod_batch_stride + c] */
+  int64_t mod_batch_stride;
+  int32_t rows_per_batch;
+  int32_t M, C, ldx;
+} PxaLnPrepareArgs;
+int pxa_ln_prepare(const PxaLnPrepareArgs* args, void* stream);
+
+/* In-place LayerNorm(C = 1152, affine weight / bias bf16, fp32 statistics) on M bf16 rows of stride ld (elements):
+ * q_norm / k_norm of AttentionKVCompress (`qk_norm=True`, PixArt_blocks.py:91-95,133-134) on the q and k column slices
+ * of the qkv GEMM output.  HBM-bound: one read and one write of the slice. */
+int pxa_layernorm_affine_bf16(void* x, const void* weight, const void* bias, int32_t M, int32_t C, int64_t ld, float eps,
+                              void* stream);
 
 /* ------------------------------------------------------------------------------------------- attention
  * out[b, i, h, :] = softmax_j( q[b,i,h,:] . k[b,j,h,:] * scale ) v[b,j,h,:],  j < kv_len[b],  head_dim 72.

@@ -29,7 +29,9 @@ import os
 
 from . import lib
 
-_FUSED_MLP = os.environ.get("PXA_EXPERIMENTAL_FUSED_MLP", "0") == "1"      # off: the validated op sequence
+# MLP branch as two GEMM launches with the GELU forward / backward inside their epilogues (MlpGateResidualFn); validated on
+# B200 in round 2 (tests/test_training_gpu.py, test_backward_gpu.py).  PXA_FUSED_MLP=0 restores the separate GELU passes.
+_FUSED_MLP = os.environ.get("PXA_FUSED_MLP", "1") == "1"
 
 def _shadow(mod: torch.nn.Module, kind: str) -> Optional[torch.Tensor]:
     """bf16 copy of `mod.weight` ('w'), its bf16 transpose ('t') or the bf16 bias ('b'), cached ON THE MODULE and
@@ -168,7 +170,7 @@ class LinearGateResidualFn(torch.autograd.Function):
 
 
 class MlpGateResidualFn(torch.autograd.Function):
-    """EXPERIMENTAL (PXA_EXPERIMENTAL_FUSED_MLP=1; not yet validated on a B200): the whole MLP branch
+    """The whole MLP branch
     out = x32 + gate * fc2(gelu(fc1(xn))) in TWO GEMM launches -- fc1 with the GELU epilogue that also keeps the
     pre-activation (EPI_BIAS_GELU_AUX), fc2 with the gated residual epilogue -- and a backward whose fc2 dgrad GEMM applies
     gelu'(pre) in its epilogue (EPI_MUL_DGELU): no separate GELU forward / backward passes over the [M, 4C] hidden."""

@@ -40,11 +40,13 @@ namespace pxa {
 #ifndef PXA_BWD_EW
 #define PXA_BWD_EW 4
 #endif
-// Experiment switch (round 2; default 0 = the validated kernel): the TMA producer brings lse / delta of every streamed query
-// sub-block into the stage (two 1-D bulk copies on the stage's full barrier) instead of the elementwise warps loading them
-// and handing them over through a per-sub-block 512-thread named barrier.  Needs Nq % 4 == 0 (16-byte aligned copies).
+// kTmaStats (template parameter of the kernel; PXA_BWD_TMA_STATS=0 forces it off): the TMA producer brings lse / delta of
+// every streamed query sub-block into the stage (two 1-D bulk copies on the stage's full barrier) instead of the
+// elementwise warps loading them and handing them over through a per-sub-block 512-thread named barrier.  Measured on
+// B200 (round 2, 4 x 16 x 4096): 1.249 ms vs 1.354 ms.  Needs Nq % 4 == 0 (16-byte aligned copies); other token counts
+// take the kTmaStats = false instantiation.
 #ifndef PXA_BWD_TMA_STATS
-#define PXA_BWD_TMA_STATS 0
+#define PXA_BWD_TMA_STATS 1
 #endif
 // Experiment switch (round 2; default 0): split-phase TMEM loads -- S'(n+1) / dP'(n+1) are requested as soon as the registers
 // of sub-block n are free, behind the TMEM store + fence + arrive of n, instead of at the top of the next iteration.
@@ -66,7 +68,7 @@ constexpr int kBOffX1 = 0;
 constexpr int kBOffX2 = kBTile;
 constexpr int kBOffY = 2 * kBTile;             // stage s: Y1 at kBOffY + s * 2 * kBYTile, Y2 right behind it
 constexpr int kBOffStat = kBOffY + kBStages * 2 * kBYTile;  // 2 buffers x (lse[64] | delta[64]) fp32 (one per stage with TMA stats)
-constexpr int kBOffBars = kBOffStat + (PXA_BWD_TMA_STATS ? kBStages * 512 : 1024);
+constexpr int kBOffBars = kBOffStat + kBStages * 512;
 constexpr int kBwdSmem = kBOffBars + 256 + 1024;            // + alignment slack
 
 constexpr uint32_t kBColS = 0;       // S'  two 64-column buffers; each thread's bf16 P' over the first half of its own column slice
@@ -102,7 +104,7 @@ struct AttnBwdParams {
   float scale, scale_log2;
 };
 
-template <bool kDKV>
+template <bool kDKV, bool kTmaStats>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __grid_constant__ CUtensorMap tm_x1t,
                           const __grid_constant__ CUtensorMap tm_x2m, const __grid_constant__ CUtensorMap tm_x2t,
@@ -170,17 +172,16 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
         uint8_t* y1 = smem + kBOffY + stage * 2 * kBYTile;
         uint8_t* y2 = y1 + kBYTile;
         const int yrow = y_row0 + it * kBSub;
-#if PXA_BWD_TMA_STATS
-        if (kDKV) {
+        if constexpr (kDKV && kTmaStats) {
           const uint32_t sb = (uint32_t)min(kBSub, p.Nq - it * kBSub) * 4u;            // bytes of lse (and of delta) in this sub-block
           const size_t so = ((size_t)b * p.H + h) * p.Nq + (size_t)it * kBSub;
           float* sdst = reinterpret_cast<float*>(smem + kBOffStat) + stage * 128;
           mbar_arrive_expect_tx(&y_full[stage], 2 * kBYTile + 2 * sb);
           tma_load_1d(sdst, p.lse + so, sb, &y_full[stage]);
           tma_load_1d(sdst + 64, p.delta + so, sb, &y_full[stage]);
-        } else
-#endif
-        mbar_arrive_expect_tx(&y_full[stage], 2 * kBYTile);
+        } else {
+          mbar_arrive_expect_tx(&y_full[stage], 2 * kBYTile);
+        }
         tma_load_3d(y1, &tm_y1m, &y_full[stage], 0, h, yrow, kEvictLast);
         tma_load_3d(y1 + kBYMain, &tm_y1t, &y_full[stage], 64, h, yrow, kEvictLast);
         tma_load_3d(y2, &tm_y2m, &y_full[stage], 0, h, yrow, kEvictLast);
@@ -256,15 +257,13 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
       nlse2 = f32x2(l, l);
       delta2 = f32x2(d, d);
     }
-#if !PXA_BWD_TMA_STATS
-    else if (n_iter > 0) {                         // -lse | delta of the first streamed query sub-block -> smem buffer 0
+    else if (!kTmaStats && n_iter > 0) {           // -lse | delta of the first streamed query sub-block -> smem buffer 0
       if (tid < 128) {
         const int qi = min(tid & 63, p.Nq - 1);
         stat[tid] = tid < 64 ? -p.lse[stat_base + qi] : p.delta[stat_base + qi];
       }
       named_bar_sync(1, kBEwThreads);
     }
-#endif
 
 #if PXA_BWD_PREFETCH
     uint32_t vs[kBCols], vd[kBCols];               // scores of the current sub-block (requested one sub-block ahead)
@@ -278,17 +277,17 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
       const int hh = n & 1;
       const uint32_t t_s = tmem_base + kBColS + lane_sel + kBSub * hh + kBCols * half;
       const uint32_t t_dp = tmem_base + kBColDP + lane_sel + kBSub * hh + kBCols * half;
-#if PXA_BWD_TMA_STATS
-      const float* st = stat + (n % kBStages) * 128 + kBCols * half;   // +lse | delta of the stage, landed with the tiles
-      if (kDKV) mbar_wait(&y_full[n % kBStages], (n / kBStages) & 1);  // (complete long ago) acquire the TMA-written stats
-#else
-      float nxt = 0.f;
-      if (kDKV && n + 1 < n_iter && tid < 128) {   // next sub-block's statistics: global load in flight during this one
-        const size_t o = stat_base + min((n + 1) * kBSub + (tid & 63), p.Nq - 1);    // the last sub-block may be partial
-        nxt = tid < 64 ? -p.lse[o] : p.delta[o];
+      // kTmaStats: +lse | delta of the stage, landed with the tiles; else -lse | delta handed over through smem buffer n & 1
+      const float* st = stat + (kTmaStats ? (n % kBStages) : (n & 1)) * 128 + kBCols * half;
+      [[maybe_unused]] float nxt = 0.f;
+      if constexpr (kTmaStats) {
+        if (kDKV) mbar_wait(&y_full[n % kBStages], (n / kBStages) & 1);  // (complete long ago) acquire the TMA-written stats
+      } else {
+        if (kDKV && n + 1 < n_iter && tid < 128) {   // next sub-block's statistics: global load in flight during this one
+          const size_t o = stat_base + min((n + 1) * kBSub + (tid & 63), p.Nq - 1);    // the last sub-block may be partial
+          nxt = tid < 64 ? -p.lse[o] : p.delta[o];
+        }
       }
-      const float* st = stat + (n & 1) * 128 + kBCols * half;  // lse of this thread's columns; delta 64 floats further
-#endif
       // the last sub-block of the stream (queries in the dKV pass, keys in the dQ pass) may be partial
       const int rem = (kDKV ? p.Nq : kv_len) - n * kBSub - kBCols * half;
 #if PXA_BWD_PREFETCH
@@ -309,11 +308,7 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
           if (kDKV) {
             const float2 l2 = *reinterpret_cast<const float2*>(st + i);          // -lse (+lse with TMA stats) of the two columns
             const float2 d2 = *reinterpret_cast<const float2*>(st + 64 + i);     // delta
-#if PXA_BWD_TMA_STATS
-            nl = f32x2(-l2.x, -l2.y);
-#else
-            nl = f32x2(l2.x, l2.y);
-#endif
+            nl = kTmaStats ? f32x2(-l2.x, -l2.y) : f32x2(l2.x, l2.y);
             dl = f32x2(d2.x, d2.y);
           } else {
             nl = nlse2;
@@ -350,12 +345,12 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[hh]);
-#if !PXA_BWD_TMA_STATS
-      if (kDKV) {
-        if (n + 1 < n_iter && tid < 128) stat[((n + 1) & 1) * 128 + tid] = nxt;
-        named_bar_sync(1, kBEwThreads);
+      if constexpr (!kTmaStats) {
+        if (kDKV) {
+          if (n + 1 < n_iter && tid < 128) stat[((n + 1) & 1) * 128 + tid] = nxt;
+          named_bar_sync(1, kBEwThreads);
+        }
       }
-#endif
     }
 
     // ---- epilogue: column slice 0 writes acc2 (dK / dQ, times the softmax scale), slice 1 writes acc1 (dV, dKV pass only)
@@ -438,9 +433,7 @@ extern "C" int pxa_flash_attn_d72_bwd_bf16(const PxaAttnBwdArgs* args, void* str
   if ((reinterpret_cast<uintptr_t>(a.dq) | reinterpret_cast<uintptr_t>(a.dk) | reinterpret_cast<uintptr_t>(a.dv) |
        reinterpret_cast<uintptr_t>(a.o) | reinterpret_cast<uintptr_t>(a.d_o)) & 15)
     return fail(PXA_ERR_ALIGN, "o / dO / dq / dk / dv must be 16-byte aligned");
-#if PXA_BWD_TMA_STATS
-  if (a.Nq % 4) return fail(PXA_ERR_ARG, "PXA_BWD_TMA_STATS build: Nq must be a multiple of 4 (got %d)", a.Nq);
-#endif
+  const bool tma_stats = PXA_BWD_TMA_STATS && a.Nq % 4 == 0;      // 16-byte aligned bulk copies of lse / delta
   PXA_REQUIRE_SM100();
   int rc = pxa_attn_delta_d72(a.o, a.d_o, a.delta, a.B, a.H, a.Nq, a.ldo, a.lddo, stream);
   if (rc) return rc;
@@ -463,7 +456,7 @@ extern "C" int pxa_flash_attn_d72_bwd_bf16(const PxaAttnBwdArgs* args, void* str
   p.scale_log2 = a.scale * 1.4426950408889634f;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   {  // dK, dV
-    auto kern = flash_attn_d72_bwd_kernel<true>;
+    auto kern = tma_stats ? flash_attn_d72_bwd_kernel<true, true> : flash_attn_d72_bwd_kernel<true, false>;
     PXA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
     p.d2 = reinterpret_cast<__nv_bfloat16*>(a.dk); p.d2_sn = a.dk_sn; p.d2_sh = a.dk_sh;
     p.d1 = reinterpret_cast<__nv_bfloat16*>(a.dv); p.d1_sn = a.dv_sn; p.d1_sh = a.dv_sh;
@@ -473,7 +466,7 @@ extern "C" int pxa_flash_attn_d72_bwd_bf16(const PxaAttnBwdArgs* args, void* str
     PXA_CHECK_CUDA(cudaGetLastError());
   }
   {  // dQ
-    auto kern = flash_attn_d72_bwd_kernel<false>;
+    auto kern = flash_attn_d72_bwd_kernel<false, false>;
     PXA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
     p.d2 = reinterpret_cast<__nv_bfloat16*>(a.dq); p.d2_sn = a.dq_sn; p.d2_sh = a.dq_sh;
     p.d1 = nullptr; p.d1_sn = p.d1_sh = 0;

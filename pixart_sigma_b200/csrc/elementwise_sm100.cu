@@ -268,3 +268,118 @@ extern "C" int pxa_dpm_solver_pp_step(const PxaDpmStepArgs* args, void* stream) 
   PXA_CHECK_CUDA(cudaGetLastError());
   return PXA_OK;
 }
+
+namespace pxa {
+
+// ------------------------------------------------------------------------------------------------- fused-LN chain: first link
+// a = bf16(x * (1 + scale[b])), stats[row][0] = (sum x, sum x^2), stats[row][1..] = 0 (see PXA_EPI_LN_BIAS in the header).
+// One warp per row like ln_modulate: reads x once (fp32), writes a once (bf16): (4 + 2) * C bytes per row.
+template <int kVec>
+__global__ void __launch_bounds__(256) ln_prepare_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a_out,
+                                                         float* __restrict__ stats, const float* __restrict__ scale,
+                                                         long long mod_bs, int rows_per_batch, int M, int ldx) {
+  constexpr int C = kVec * 128;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + (size_t)row * ldx;
+  const float* sc = scale + (size_t)(row / rows_per_batch) * mod_bs;
+  __nv_bfloat16* orow = a_out + (size_t)row * C;
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int g = 0; g < kVec; ++g) {
+    const int col = (g * 32 + lane) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(xr + col);
+    const float4 e = __ldg(reinterpret_cast<const float4*>(sc + col));
+    s += (v.x + v.y) + (v.z + v.w);
+    q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, q))));
+    *reinterpret_cast<uint2*>(orow + col) = make_uint2(pack_bf16x2(v.x * (1.0f + e.x), v.y * (1.0f + e.y)),
+                                                       pack_bf16x2(v.z * (1.0f + e.z), v.w * (1.0f + e.w)));
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if (lane < PXA_LN_STAT_PARTS)
+    reinterpret_cast<float2*>(stats)[(size_t)row * PXA_LN_STAT_PARTS + lane] = lane == 0 ? make_float2(s, q) : make_float2(0.f, 0.f);
+}
+
+}  // namespace pxa
+
+extern "C" int pxa_ln_prepare(const PxaLnPrepareArgs* args, void* stream) {
+  using namespace pxa;
+  if (!args) return fail(PXA_ERR_ARG, "null args");
+  const PxaLnPrepareArgs& a = *args;
+  if (!a.x || !a.a_out || !a.stats_out || !a.scale) return fail(PXA_ERR_ARG, "null pointer");
+  if (a.M <= 0 || a.rows_per_batch <= 0) return fail(PXA_ERR_ARG, "bad M / rows_per_batch");
+  if (a.C != 1152) return fail(PXA_ERR_ARG, "pxa_ln_prepare is specialised for C = 1152 (got %d)", a.C);
+  if ((a.ldx & 3) || (a.mod_batch_stride & 3) ||
+      ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.a_out) | reinterpret_cast<uintptr_t>(a.stats_out) |
+        reinterpret_cast<uintptr_t>(a.scale)) & 15))
+    return fail(PXA_ERR_ALIGN, "pointers must be 16-byte aligned, ldx / mod_batch_stride multiples of 4");
+  PXA_REQUIRE_SM100();
+  ln_prepare_kernel<9><<<(a.M + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      a.x, reinterpret_cast<__nv_bfloat16*>(a.a_out), a.stats_out, a.scale, a.mod_batch_stride, a.rows_per_batch, a.M, a.ldx);
+  launch_counter()++;
+  PXA_CHECK_CUDA(cudaGetLastError());
+  return PXA_OK;
+}
+
+namespace pxa {
+
+// ------------------------------------------------------------------------------------------------- q / k LayerNorm (qk_norm)
+// In-place LayerNorm(C = 1152, affine, fp32 statistics) on bf16 rows of stride ld: the q_norm / k_norm of
+// AttentionKVCompress (PixArt_blocks.py:91-95, 133-134) applied to the q and k column slices of the qkv GEMM output.
+template <int kVec>
+__global__ void __launch_bounds__(256) layernorm_affine_kernel(__nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                                               const __nv_bfloat16* __restrict__ b, int M, long long ld, float eps) {
+  constexpr int C = kVec * 128;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  __nv_bfloat16* xr = x + (size_t)row * ld;
+  float4 v[kVec];
+  float s = 0.f;
+#pragma unroll
+  for (int g = 0; g < kVec; ++g) {
+    const uint2 u = *reinterpret_cast<const uint2*>(xr + (g * 32 + lane) * 4);
+    v[g] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+    s += (v[g].x + v[g].y) + (v[g].z + v[g].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / C);
+  float ss = 0.f;
+#pragma unroll
+  for (int g = 0; g < kVec; ++g) {
+    const float a0 = v[g].x - mean, a1 = v[g].y - mean, a2 = v[g].z - mean, a3 = v[g].w - mean;
+    ss += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / C) + eps);
+#pragma unroll
+  for (int g = 0; g < kVec; ++g) {
+    const int col = (g * 32 + lane) * 4;
+    const uint2 wu = __ldg(reinterpret_cast<const uint2*>(w + col));
+    const uint2 bu = __ldg(reinterpret_cast<const uint2*>(b + col));
+    const float y0 = fmaf((v[g].x - mean) * rstd, bf16_lo(wu.x), bf16_lo(bu.x));
+    const float y1 = fmaf((v[g].y - mean) * rstd, bf16_hi(wu.x), bf16_hi(bu.x));
+    const float y2 = fmaf((v[g].z - mean) * rstd, bf16_lo(wu.y), bf16_lo(bu.y));
+    const float y3 = fmaf((v[g].w - mean) * rstd, bf16_hi(wu.y), bf16_hi(bu.y));
+    *reinterpret_cast<uint2*>(xr + col) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+  }
+}
+
+}  // namespace pxa
+
+extern "C" int pxa_layernorm_affine_bf16(void* x, const void* weight, const void* bias, int32_t M, int32_t C, int64_t ld,
+                                         float eps, void* stream) {
+  using namespace pxa;
+  if (!x || !weight || !bias) return fail(PXA_ERR_ARG, "null pointer");
+  if (M <= 0) return fail(PXA_ERR_ARG, "bad M");
+  if (C != 1152) return fail(PXA_ERR_ARG, "pxa_layernorm_affine_bf16 is specialised for C = 1152 (got %d)", C);
+  if ((ld & 3) || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(bias)) & 7))
+    return fail(PXA_ERR_ALIGN, "x / weight / bias must be 8-byte aligned, ld a multiple of 4");
+  PXA_REQUIRE_SM100();
+  layernorm_affine_kernel<9><<<(M + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<__nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(weight),
+      reinterpret_cast<const __nv_bfloat16*>(bias), M, ld, eps);
+  launch_counter()++;
+  PXA_CHECK_CUDA(cudaGetLastError());
+  return PXA_OK;
+}

@@ -17,11 +17,13 @@
 
 namespace pxa {
 
-template <int BN> struct Gemm2Cfg {
+// kTmaRes: the fp32 residual epilogue streams the residual tile through smem by TMA (gemm_common.cuh tma_res_epilogue);
+// its 64 KB of chunk buffers cost two operand stages at BN = 192 (5 instead of 7).
+template <int BN, bool kTmaRes = false> struct Gemm2Cfg {
   static constexpr int kStageA = kBM * kBK * 2;                 // 16 KB: this CTA's 128 rows of A
   static constexpr int kStageB = (BN / 2) * kBK * 2;            // this CTA's BN/2 rows of W
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kEpiBufs = 4 * 32 * 32 * 4;
+  static constexpr int kEpiBufs = kTmaRes ? kResEpiSmem : 4 * 32 * 32 * 4;
   static constexpr int kEpiSmem = kEpiBufs + ((kEpiConstBytes + 127) / 128) * 128;
   static constexpr int kBarBytes = 256;
   static constexpr int kStages = (227 * 1024 - kEpiSmem - kBarBytes - 1024) / kStage > 8
@@ -65,15 +67,6 @@ PXA_DEVICE void umma2_commit_mc(uint64_t* bar, uint16_t mask) {
       "h"(mask)
       : "memory");
 }
-// Arrive on the barrier at the same smem offset in CTA `rank` of the cluster.
-PXA_DEVICE void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
-      "r"(rank)
-      : "memory");
-}
 template <uint32_t kCols> PXA_DEVICE void tmem_alloc_pair(uint32_t* dst_smem) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(dst_smem)), "n"(kCols)
                : "memory");
@@ -83,11 +76,13 @@ template <uint32_t kCols> PXA_DEVICE void tmem_dealloc_pair(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "n"(kCols) : "memory");
 }
 
-template <int BN, int EPI, typename OutT>
+template <int BN, int EPI, typename OutT, bool kTmaRes = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                  const __grid_constant__ CUtensorMap tmap_res, const GemmParams p) {
-  using Cfg = Gemm2Cfg<BN>;
+                  const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out,
+                  const __grid_constant__ CUtensorMap tmap_aux, const GemmParams p) {
+  static_assert(!kTmaRes || (EPI == PXA_EPI_BIAS_RESIDUAL && sizeof(OutT) == 4), "TMA residual epilogue: fp32 stream only");
+  using Cfg = Gemm2Cfg<BN, kTmaRes>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -97,7 +92,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint64_t* empty_bar = bars + kStages;           // [kStages] per CTA: leader's MMA commit (multicast) frees the slot
   uint64_t* tfull_bar = bars + 2 * kStages;       // [2] per CTA: accumulator ready (multicast commit)
   uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2] leader's: 256 arrivals (both CTAs' epilogue threads)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* res_full = bars + 2 * kStages + 4;    // [kResBufs] per CTA: TMA residual chunk landed (kTmaRes only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4 + kResBufs);
 
   const int warp = warp_idx_sync();
   const int lane = threadIdx.x & 31;
@@ -115,6 +111,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 2 * kNumEpiThreads);
     }
+    for (int s = 0; s < kResBufs; ++s) mbar_init(&res_full[s], 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
@@ -136,7 +133,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m0 = (tile / p.num_n_tiles) * (2 * kBM) + rank * kBM;
         const int n0 = (tile % p.num_n_tiles) * BN;
-        if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) tma_prefetch_l2_2d(&tmap_res, n0, m0);
+        if constexpr (kTmaRes) {
+          // pull this tile's residual block into L2 now: the epilogue reads it one mainloop later
+          if (!(p.out_aux == nullptr && p.residual == p.out && p.row_stats_out == nullptr))
+            for (int c = 0; c < BN / 32; ++c) tma_prefetch_l2_2d(&tmap_res, n0 + c * 32, m0);
+        } else if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
+          tma_prefetch_l2_2d(&tmap_res, n0, m0);
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStage;
@@ -179,51 +182,65 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   } else if (warp >= kEpiWarp0) {
     // ================================================================ epilogue (both CTAs, own 128 rows)
-    const int q = warp & 3;
-    const int tid = threadIdx.x - kEpiWarp0 * 32;
-    uint8_t* stile = epi_smem + (warp - kEpiWarp0) * 4096;
     EpiConst* consts = reinterpret_cast<EpiConst*>(epi_smem + Cfg::kEpiBufs);
-    int as = 0;
-    uint32_t aphase = 0;
-    int titer = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++titer) {
-      const int m0 = (tile / p.num_n_tiles) * (2 * kBM) + rank * kBM;
-      const int n0 = (tile % p.num_n_tiles) * BN;
-      const int nch = chunks_of_tile<BN>(p, n0);
-      EpiConst* cb = consts + (titer & 1);
-      stage_epi_consts<BN>(cb, p, tid, m0, n0);
-      named_bar_sync(2, kNumEpiThreads);
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
-      const uint32_t t_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
-      auto process = [&](uint32_t (&v)[32], int cc) {
-        if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
-          ResFrag res;
-          load_residual_frag<OutT>(res, p, lane, m0 + q * 32, n0 + cc * 32);
-          epilogue_chunk_residual<OutT>(v, res, p, stile, lane, m0 + q * 32, n0 + cc * 32);
-        } else {
-          epilogue_chunk_bf16_c<EPI>(v, p, cb, stile, lane, m0 + q * 32, n0 + cc * 32, cc * 32);
-        }
-      };
-      auto release_acc = [&]() {
-        tc_fence_before();
-        mbar_arrive_cluster(&tempty_bar[as], 0);       // the leader's MMA thread owns the accumulator hand-off
-      };
-      uint32_t va[32], vb[32];
-      tmem_ld_32x32b_x32_nowait(t_acc, va);
+    if constexpr (kTmaRes) {
+      TileWalk tw;
+      tw.first = cluster_id; tw.stride = num_clusters; tw.count = num_tiles;
+      tw.mn_tiles = num_tiles; tw.num_n_tiles = p.num_n_tiles; tw.m_mult = 2 * kBM; tw.m_off = rank * kBM;
+      tma_res_epilogue<BN, kResBufs, true>(p, tw, epi_smem, consts, tfull_bar, tempty_bar, res_full, tmem_base, &tmap_res,
+                                           &tmap_out, &tmap_aux, warp, lane);
+    } else {
+      constexpr bool kLn = (EPI == PXA_EPI_LN_BIAS || EPI == PXA_EPI_LN_BIAS_GELU);
+      const int q = warp & 3;
+      const int tid = threadIdx.x - kEpiWarp0 * 32;
+      uint8_t* stile = epi_smem + (warp - kEpiWarp0) * 4096;
+      int as = 0;
+      uint32_t aphase = 0;
+      int titer = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++titer) {
+        const int m0 = (tile / p.num_n_tiles) * (2 * kBM) + rank * kBM;
+        const int n0 = (tile % p.num_n_tiles) * BN;
+        const int nch = chunks_of_tile<BN>(p, n0);
+        EpiConst* cb = consts + (titer & 1);
+        stage_epi_consts<BN, kLn>(cb, p, tid, m0, n0);
+        [[maybe_unused]] float2 ln = make_float2(1.f, 0.f);
+        if constexpr (kLn) ln = ln_row_coeffs(p, m0 + q * 32 + lane);
+        named_bar_sync(2, kNumEpiThreads);
+        [[maybe_unused]] const bool second = q * 32 + lane >= cb->row_split;
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        const uint32_t t_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
+        auto process = [&](uint32_t (&v)[32], int cc) {
+          if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
+            ResFrag res;
+            load_residual_frag<OutT>(res, p, lane, m0 + q * 32, n0 + cc * 32);
+            epilogue_chunk_residual<OutT>(v, res, p, stile, lane, m0 + q * 32, n0 + cc * 32);
+          } else if constexpr (kLn) {
+            epilogue_chunk_bf16_c<EPI>(v, p, cb, stile, lane, m0 + q * 32, n0 + cc * 32, cc * 32, ln, second);
+          } else {
+            epilogue_chunk_bf16_c<EPI>(v, p, cb, stile, lane, m0 + q * 32, n0 + cc * 32, cc * 32);
+          }
+        };
+        auto release_acc = [&]() {
+          tc_fence_before();
+          mbar_arrive_cluster(&tempty_bar[as], 0);       // the leader's MMA thread owns the accumulator hand-off
+        };
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32b_x32_nowait(t_acc, va);
 #pragma unroll 1
-      for (int cc = 0; cc < nch; cc += 2) {
-        tmem_ld_wait_x32(va);
-        if (cc + 1 < nch) tmem_ld_32x32b_x32_nowait(t_acc + (cc + 1) * 32, vb); else release_acc();
-        process(va, cc);
-        if (cc + 1 < nch) {
-          tmem_ld_wait_x32(vb);
-          if (cc + 2 < nch) tmem_ld_32x32b_x32_nowait(t_acc + (cc + 2) * 32, va); else release_acc();
-          process(vb, cc + 1);
+        for (int cc = 0; cc < nch; cc += 2) {
+          tmem_ld_wait_x32(va);
+          if (cc + 1 < nch) tmem_ld_32x32b_x32_nowait(t_acc + (cc + 1) * 32, vb); else release_acc();
+          process(va, cc);
+          if (cc + 1 < nch) {
+            tmem_ld_wait_x32(vb);
+            if (cc + 2 < nch) tmem_ld_32x32b_x32_nowait(t_acc + (cc + 2) * 32, va); else release_acc();
+            process(vb, cc + 1);
+          }
         }
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
       }
-      as ^= 1;
-      if (as == 0) aphase ^= 1;
     }
   }
 
@@ -235,9 +252,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
 }
 
-template <int BN, int EPI, typename OutT>
+template <int BN, int EPI, typename OutT, bool kTmaRes = false>
 static int launch_gemm2(const PxaGemmArgs& a, cudaStream_t stream) {
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = Gemm2Cfg<BN, kTmaRes>;
   CUtensorMap ta, tw;
   {
     uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
@@ -253,8 +270,21 @@ static int launch_gemm2(const PxaGemmArgs& a, cudaStream_t stream) {
     int rc = make_tmap_bf16(&tw, a.w, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  CUtensorMap tr = ta;
-  if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
+  CUtensorMap tr = ta, to = ta, tx = ta;
+  if constexpr (kTmaRes) {
+    uint64_t dims[2] = {(uint64_t)a.N, (uint64_t)a.M};
+    uint64_t str[1] = {(uint64_t)a.ldo * 4};
+    uint32_t box[2] = {32, kBM};           // 32 fp32 = 128 B rows: one TMA 128B-swizzle atom per row
+    int rc = make_tmap(&tr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a.residual, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_tmap(&to, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a.out, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    if (a.out_aux_bf16 != nullptr) {
+      uint64_t astr[1] = {(uint64_t)a.ldo * 2};
+      rc = make_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.out_aux_bf16, 2, dims, astr, box, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+    }
+  } else if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
     uint64_t dims[2] = {(uint64_t)a.N, (uint64_t)a.M};
     uint64_t str[1] = {(uint64_t)a.ldo * sizeof(OutT)};
     uint32_t box[2] = {(uint32_t)BN, kBM};
@@ -276,13 +306,14 @@ static int launch_gemm2(const PxaGemmArgs& a, cudaStream_t stream) {
   p.trace = reinterpret_cast<long long*>(a.debug_trace);
   p.k_splits = 1;
   p.aux_branch = a.aux_is_branch;
-  auto kern = gemm2_bf16_kernel<BN, EPI, OutT>;
+  fill_ln_params(p, a);
+  auto kern = gemm2_bf16_kernel<BN, EPI, OutT, kTmaRes>;
   PXA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
   int clusters = device_info().sms / 2;
   if (a.max_ctas > 0 && a.max_ctas / 2 < clusters) clusters = a.max_ctas / 2 > 0 ? a.max_ctas / 2 : 1;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   if (tiles < clusters) clusters = tiles;
-  kern<<<2 * clusters, kGemmThreads, Cfg::kSmem, stream>>>(ta, tw, tr, p);
+  kern<<<2 * clusters, kGemmThreads, Cfg::kSmem, stream>>>(ta, tw, tr, to, tx, p);
   launch_counter()++;
   PXA_CHECK_CUDA(cudaGetLastError());
   return PXA_OK;
@@ -299,8 +330,17 @@ static int dispatch_epi2(const PxaGemmArgs& a, cudaStream_t s) {
       return launch_gemm2<BN, PXA_EPI_BIAS_GELU_AUX, __nv_bfloat16>(a, s);
     case PXA_EPI_MUL_DGELU:
       return launch_gemm2<BN, PXA_EPI_MUL_DGELU, __nv_bfloat16>(a, s);
+    case PXA_EPI_LN_BIAS:
+      return launch_gemm2<BN, PXA_EPI_LN_BIAS, __nv_bfloat16>(a, s);
+    case PXA_EPI_LN_BIAS_GELU:
+      return launch_gemm2<BN, PXA_EPI_LN_BIAS_GELU, __nv_bfloat16>(a, s);
     case PXA_EPI_BIAS_RESIDUAL:
-      if (a.out_dtype == PXA_DTYPE_F32) return launch_gemm2<BN, PXA_EPI_BIAS_RESIDUAL, float>(a, s);
+      if (a.out_dtype == PXA_DTYPE_F32) {
+        // the TMA-streamed epilogue is required for the fused LayerNorm by-products (scaled aux copy, row statistics)
+        const bool tma = a.res_epilogue == 2 || (a.res_epilogue == 0 && (a.aux_scale != nullptr || a.row_stats_out != nullptr));
+        if (tma) return launch_gemm2<BN, PXA_EPI_BIAS_RESIDUAL, float, true>(a, s);
+        return launch_gemm2<BN, PXA_EPI_BIAS_RESIDUAL, float>(a, s);
+      }
       return launch_gemm2<BN, PXA_EPI_BIAS_RESIDUAL, __nv_bfloat16>(a, s);
     default:
       return fail(PXA_ERR_ARG, "unknown epilogue %d", a.epilogue);

@@ -24,9 +24,31 @@ struct GemmParams {
   long long* trace;     // debug only (NULL in production)
   int k_splits;         // > 1: split-K over tiles (reduce-add epilogue only)
   int aux_branch;       // residual epilogue: the bf16 aux output receives acc + bias (the branch output) instead of out
+  // fused LayerNorm-modulate, producer side (fp32 residual epilogue): aux = out * aux_scale[b], row partial sums of out
+  const float* aux_scale;
+  long long aux_scale_batch_stride;
+  float* row_stats_out;
+  // consumer side (PXA_EPI_LN_BIAS / _GELU): out = rstd * (acc - mu * u[b]) + v[b]
+  const float* ln_stats;
+  const float* ln_u;
+  const float* ln_v;
+  long long ln_uv_batch_stride;
+  float ln_inv_dim, ln_eps;
   // implicit-GEMM 3x3 convolution mode (kConv): A is an NHWC image read through a 4-D tensor map
   int conv_H, conv_W, conv_tile_w, conv_tile_h, conv_cin_blocks;
 };
+
+inline void fill_ln_params(GemmParams& p, const PxaGemmArgs& a) {
+  p.aux_scale = a.aux_scale;
+  p.aux_scale_batch_stride = a.aux_scale_batch_stride;
+  p.row_stats_out = a.row_stats_out;
+  p.ln_stats = a.ln_stats;
+  p.ln_u = a.ln_u;
+  p.ln_v = a.ln_v;
+  p.ln_uv_batch_stride = a.ln_uv_batch_stride;
+  p.ln_inv_dim = a.ln_dim > 0 ? 1.0f / (float)a.ln_dim : 0.f;
+  p.ln_eps = a.ln_eps;
+}
 
 constexpr int kResBufs = 3;
 constexpr int kResChunkBytes = 128 * 32 * 4;     // 16 KB: 128 rows x 32 fp32 columns
@@ -38,13 +60,15 @@ constexpr int kSmemBudget = 227 * 1024;
 // two) samples a 128-row tile can span.  Reading them per chunk is then an LDS broadcast instead of a chain of L2-latency
 // global loads in the epilogue's critical path.  Double-buffered by tile parity.
 struct EpiConst {
-  float bias[256];
-  float gate0[256];    // gate of the sample of the tile's first row (1.0 when there is no gate)
+  float bias[256];     // LN consumer epilogue: v of the first sample
+  float gate0[256];    // gate of the sample of the tile's first row (1.0 when there is no gate); LN consumer: v of the last sample
   float gate1[256];    // gate of the sample of the tile's last row
+  float ex0[256];      // aux_scale of the first / last sample (1.0 when there is none); LN consumer: u of the first / last sample
+  float ex1[256];
   int row_split;       // tile rows >= row_split belong to the second sample
   int pad[3];
 };
-constexpr int kEpiConstBytes = 2 * sizeof(EpiConst);    // 6176 B
+constexpr int kEpiConstBytes = 2 * sizeof(EpiConst);    // 10272 B
 
 // kTmaRes: fp32 residual epilogue streamed through smem by TMA (see the end of this file)
 // kReduceOnly: the weight-gradient form only ever runs the reduce-add epilogue (no residual loads, no aux copy): two chunk
@@ -215,7 +239,7 @@ PXA_DEVICE void epilogue_chunk_residual(uint32_t (&v)[32], const ResFrag& res, c
 
 
 // Called by the 128 epilogue threads (tid 0..127) at the start of a tile; followed by a named barrier.
-template <int BN>
+template <int BN, bool kLn = false>
 PXA_DEVICE void stage_epi_consts(EpiConst* cb, const GemmParams& p, int tid, int m0, int n0) {
   const int b0 = m0 / p.rows_per_batch;
   const int last = (m0 + kBM - 1 < p.M ? m0 + kBM - 1 : p.M - 1);
@@ -224,11 +248,39 @@ PXA_DEVICE void stage_epi_consts(EpiConst* cb, const GemmParams& p, int tid, int
   for (int c = tid; c < BN; c += kNumEpiThreads) {
     const int col = n0 + c;
     const bool ok = col < p.N;
-    cb->bias[c] = (ok && p.bias != nullptr) ? __bfloat162float(p.bias[col]) : 0.f;
-    cb->gate0[c] = (ok && p.gate != nullptr) ? __ldg(p.gate + (size_t)b0 * p.gate_batch_stride + col) : 1.f;
-    cb->gate1[c] = (ok && p.gate != nullptr) ? __ldg(p.gate + (size_t)b1 * p.gate_batch_stride + col) : 1.f;
+    if constexpr (kLn) {
+      cb->bias[c] = ok ? __ldg(p.ln_v + (size_t)b0 * p.ln_uv_batch_stride + col) : 0.f;
+      cb->gate0[c] = ok ? __ldg(p.ln_v + (size_t)b1 * p.ln_uv_batch_stride + col) : 0.f;
+      cb->ex0[c] = ok ? __ldg(p.ln_u + (size_t)b0 * p.ln_uv_batch_stride + col) : 0.f;
+      cb->ex1[c] = ok ? __ldg(p.ln_u + (size_t)b1 * p.ln_uv_batch_stride + col) : 0.f;
+    } else {
+      cb->bias[c] = (ok && p.bias != nullptr) ? __bfloat162float(p.bias[col]) : 0.f;
+      cb->gate0[c] = (ok && p.gate != nullptr) ? __ldg(p.gate + (size_t)b0 * p.gate_batch_stride + col) : 1.f;
+      cb->gate1[c] = (ok && p.gate != nullptr) ? __ldg(p.gate + (size_t)b1 * p.gate_batch_stride + col) : 1.f;
+      cb->ex0[c] = (ok && p.aux_scale != nullptr) ? __ldg(p.aux_scale + (size_t)b0 * p.aux_scale_batch_stride + col) : 1.f;
+      cb->ex1[c] = (ok && p.aux_scale != nullptr) ? __ldg(p.aux_scale + (size_t)b1 * p.aux_scale_batch_stride + col) : 1.f;
+    }
   }
   if (tid == 0) cb->row_split = (b0 + 1) * p.rows_per_batch - m0;
+}
+
+// LayerNorm statistics of row `row` from its PXA_LN_STAT_PARTS partial (sum, sum of squares) pairs:
+// returns (rstd, -rstd * mean), so that the normalised accumulator is fma(rstd, acc, fma(-rstd*mean, u, v)).
+PXA_DEVICE float2 ln_row_coeffs(const GemmParams& p, int row) {
+  float s = 0.f, q = 0.f;
+  if (row < p.M) {
+    const float4* sp = reinterpret_cast<const float4*>(p.ln_stats + (size_t)row * (2 * PXA_LN_STAT_PARTS));
+#pragma unroll
+    for (int i = 0; i < PXA_LN_STAT_PARTS / 2; ++i) {
+      const float4 t = __ldg(sp + i);
+      s += t.x + t.z;
+      q += t.y + t.w;
+    }
+  }
+  const float mean = s * p.ln_inv_dim;
+  const float var = fmaxf(q * p.ln_inv_dim - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + p.ln_eps);
+  return make_float2(rstd, -rstd * mean);
 }
 
 // bf16 output (EPI 0/1/3/4) with staged constants: bias from smem (LDS broadcast).
@@ -236,12 +288,16 @@ PXA_DEVICE void stage_epi_consts(EpiConst* cb, const GemmParams& p, int tid, int
 //                          pre-activation the GELU backward needs) -- the MLP's first GEMM in training;
 //   PXA_EPI_MUL_DGELU:     out = acc * gelu'(pre), pre = p.residual read as bf16 [M, N] (row stride ldo) -- the dgrad GEMM of
 //                          the MLP's second layer producing the gradient of the pre-activation directly.
+//   PXA_EPI_LN_BIAS(_GELU): out = [gelu](rstd * (acc - mu * u) + v) -- the fused LayerNorm-modulate (see the header); `ln` =
+//                          (rstd, -rstd * mu) of this thread's row, u / v of the row's sample from the staged constants.
 template <int EPI>
 PXA_DEVICE void epilogue_chunk_bf16_c(uint32_t (&v)[32], const GemmParams& p, const EpiConst* cb, uint8_t* stile, int lane,
-                                      int row0, int col0, int ccol) {
+                                      int row0, int col0, int ccol, float2 ln = make_float2(1.f, 0.f), bool second = false) {
+  constexpr bool kLn = (EPI == PXA_EPI_LN_BIAS || EPI == PXA_EPI_LN_BIAS_GELU);
   uint32_t pk[16];
   [[maybe_unused]] uint32_t pk2[16];
-  const float4* bp = reinterpret_cast<const float4*>(cb->bias + ccol);
+  const float4* bp = reinterpret_cast<const float4*>((kLn && second ? cb->gate0 : cb->bias) + ccol);
+  [[maybe_unused]] const float4* up = reinterpret_cast<const float4*>((second ? cb->ex1 : cb->ex0) + ccol);
   [[maybe_unused]] uint4 pre[4];
   if constexpr (EPI == PXA_EPI_MUL_DGELU) {
     const __nv_bfloat16* pr = reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)(row0 + lane) * p.ldo + col0;
@@ -252,13 +308,22 @@ PXA_DEVICE void epilogue_chunk_bf16_c(uint32_t (&v)[32], const GemmParams& p, co
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float4 b = bp[i];
-    float x0 = __uint_as_float(v[4 * i]) + b.x, x1 = __uint_as_float(v[4 * i + 1]) + b.y;
-    float x2 = __uint_as_float(v[4 * i + 2]) + b.z, x3 = __uint_as_float(v[4 * i + 3]) + b.w;
+    float x0, x1, x2, x3;
+    if constexpr (kLn) {
+      const float4 u = up[i];
+      x0 = fmaf(ln.x, __uint_as_float(v[4 * i]), fmaf(ln.y, u.x, b.x));
+      x1 = fmaf(ln.x, __uint_as_float(v[4 * i + 1]), fmaf(ln.y, u.y, b.y));
+      x2 = fmaf(ln.x, __uint_as_float(v[4 * i + 2]), fmaf(ln.y, u.z, b.z));
+      x3 = fmaf(ln.x, __uint_as_float(v[4 * i + 3]), fmaf(ln.y, u.w, b.w));
+    } else {
+      x0 = __uint_as_float(v[4 * i]) + b.x; x1 = __uint_as_float(v[4 * i + 1]) + b.y;
+      x2 = __uint_as_float(v[4 * i + 2]) + b.z; x3 = __uint_as_float(v[4 * i + 3]) + b.w;
+    }
     if constexpr (EPI == PXA_EPI_BIAS_GELU_AUX) {
       pk2[2 * i] = pack_bf16x2(x0, x1);
       pk2[2 * i + 1] = pack_bf16x2(x2, x3);
     }
-    if (EPI == PXA_EPI_BIAS_GELU || EPI == PXA_EPI_BIAS_GELU_AUX) {
+    if (EPI == PXA_EPI_BIAS_GELU || EPI == PXA_EPI_BIAS_GELU_AUX || EPI == PXA_EPI_LN_BIAS_GELU) {
       x0 = gelu_tanh(x0); x1 = gelu_tanh(x1); x2 = gelu_tanh(x2); x3 = gelu_tanh(x3);
     }
     if constexpr (EPI == PXA_EPI_MUL_DGELU) {
@@ -312,8 +377,10 @@ PXA_DEVICE void epilogue_chunk_bf16_c(uint32_t (&v)[32], const GemmParams& p, co
 // One residual chunk for the calling thread (row r of the 128-row tile) with staged constants.
 // `reduce`: the chunk buffer receives only the update gate*(acc+bias); the TMA engine adds it into the residual stream
 // in global memory (no residual read at all).
+// `st` accumulates this row's (sum, sum of squares) of the new residual values over the chunks of a tile (the fused
+// LayerNorm's statistics, p.row_stats_out); with p.aux_scale the bf16 aux copy is out * (1 + scale of the next modulate).
 PXA_DEVICE void residual_chunk_row_c(uint32_t (&v)[32], const GemmParams& p, const EpiConst* cb, uint8_t* rbuf, uint8_t* abuf,
-                                     int r, int ccol, int grow, int gcol0, bool reduce = false) {
+                                     int r, int ccol, int grow, int gcol0, bool reduce, float2& st) {
   const int sw = r & 7;
   uint8_t* rrow = rbuf + r * 128;
   float4 res[8];
@@ -322,6 +389,8 @@ PXA_DEVICE void residual_chunk_row_c(uint32_t (&v)[32], const GemmParams& p, con
     res[c] = reduce ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(rrow + ((c ^ sw) << 4));
   const float4* bp = reinterpret_cast<const float4*>(cb->bias + ccol);
   const float4* gp = reinterpret_cast<const float4*>((r >= cb->row_split ? cb->gate1 : cb->gate0) + ccol);
+  const float4* ep = reinterpret_cast<const float4*>((r >= cb->row_split ? cb->ex1 : cb->ex0) + ccol);
+  const bool scaled_aux = p.aux_scale != nullptr;
   // samples shorter than a tile (rows_per_batch < 128, tiny images): a tile may span more than two samples, so the
   // gate row is looked up per thread in global memory instead of the two staged rows
   const bool per_row_gate = p.gate != nullptr && p.rows_per_batch < kBM;
@@ -341,7 +410,13 @@ PXA_DEVICE void residual_chunk_row_c(uint32_t (&v)[32], const GemmParams& p, con
     o.z = fmaf(g.z, yb.z, res[c].z);
     o.w = fmaf(g.w, yb.w, res[c].w);
     res[c] = o;
-    const float4 ax = p.aux_branch ? yb : o;
+    st.x += (o.x + o.y) + (o.z + o.w);
+    st.y = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, st.y))));
+    float4 ax = p.aux_branch ? yb : o;
+    if (scaled_aux) {
+      const float4 e = ep[c];
+      ax = make_float4(ax.x * e.x, ax.y * e.y, ax.z * e.z, ax.w * e.w);
+    }
     aux[2 * c] = pack_bf16x2(ax.x, ax.y);
     aux[2 * c + 1] = pack_bf16x2(ax.z, ax.w);
   }
@@ -373,55 +448,148 @@ PXA_DEVICE int chunks_of_tile(const GemmParams& p, int n0) {
   return rem < BN / 32 ? rem : BN / 32;
 }
 
-// One chunk for the calling thread (row `r` of the 128-row tile): v = acc of 32 columns.
-PXA_DEVICE void residual_chunk_row(uint32_t (&v)[32], const GemmParams& p, uint8_t* rbuf, uint8_t* abuf, int r, int grow,
-                                   int col0) {
-  // bias / gate: 32 consecutive columns, same for the whole warp except across a sample boundary (L1 broadcast hits)
-  float b[32];
-  if (p.bias != nullptr) {
-    const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 u = make_uint4(0u, 0u, 0u, 0u);
-      if (col0 + 8 * i < p.N) u = __ldg(bp + i);
-      b[8 * i + 0] = bf16_lo(u.x); b[8 * i + 1] = bf16_hi(u.x);
-      b[8 * i + 2] = bf16_lo(u.y); b[8 * i + 3] = bf16_hi(u.y);
-      b[8 * i + 4] = bf16_lo(u.z); b[8 * i + 5] = bf16_hi(u.z);
-      b[8 * i + 6] = bf16_lo(u.w); b[8 * i + 7] = bf16_hi(u.w);
+// Arrive on the barrier at the same smem offset in CTA `rank` of the cluster (CTA-pair kernels).
+PXA_DEVICE void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+
+// Which output tiles a CTA walks, shared by the single-CTA kernel (128 x BN tiles, one per CTA) and the CTA-pair kernel
+// (256 x BN tiles per cluster: m_mult = 256, this CTA's rows start m_off = rank * 128 into the tile).
+struct TileWalk {
+  int first, stride, count;          // tile ids first, first + stride, ... < count
+  int mn_tiles, num_n_tiles;         // tile id % mn_tiles -> (m tile, n tile), n fastest
+  int m_mult, m_off;
+  PXA_DEVICE int m0(int tile) const { return ((tile % mn_tiles) / num_n_tiles) * m_mult + m_off; }
+  PXA_DEVICE int ntile(int tile) const { return (tile % mn_tiles) % num_n_tiles; }
+};
+
+// The whole epilogue-warp loop of the TMA-streamed fp32 residual epilogue (called by the 4 epilogue warps of either GEMM
+// kernel): per tile, per 32-column chunk: accumulator chunk TMEM -> registers (split-phase), residual chunk smem (TMA) ->
+// out = residual + gate * (acc + bias) in place in smem -> TMA store (+ bf16 aux chunk), or, with `reduce`, update only +
+// TMA reduce-add into global memory.  One elected thread of the first epilogue warp owns every TMA / bulk-group operation.
+template <int BN, int kRing, bool kPair>
+PXA_DEVICE void tma_res_epilogue(const GemmParams& p, const TileWalk& tw, uint8_t* epi_smem, EpiConst* consts,
+                                 uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* res_full, uint32_t tmem_base,
+                                 const CUtensorMap* tmap_res, const CUtensorMap* tmap_out, const CUtensorMap* tmap_aux,
+                                 int warp, int lane) {
+  const int q = warp & 3;                                       // TMEM sub-partition of this warp
+  const int tid = threadIdx.x - kEpiWarp0 * 32;                 // 0..127
+  const int r = q * 32 + lane;                                  // row of the 128-row tile owned by this thread
+  uint8_t* rbufs = epi_smem;
+  uint8_t* abufs = epi_smem + kRing * kResChunkBytes;           // (unused by the reduce-only configuration)
+  // The issuer is picked with elect.sync inside a warp-uniform branch (always the same lane for a full warp), so the TMA /
+  // mbarrier operands stay in uniform registers; `issuer_warp` guards the converged regions, `issuer` the elected lane.
+  const bool issuer_warp = warp == kEpiWarp0;
+  bool issuer = false;
+  if (issuer_warp) issuer = elect_one() != 0;
+  // In-place update without a bf16 copy or statistics: skip the residual read and let TMA reduce-add the update into x.
+  const bool reduce = p.out_aux == nullptr && p.residual == p.out && p.row_stats_out == nullptr;
+  int l_tile = tw.first, l_cc = 0, l_g = 0;                     // issuer: next residual chunk to request
+  auto request_next = [&]() {
+    if (l_tile >= tw.count) return;
+    const int lm0 = tw.m0(l_tile);
+    const int ln0 = tw.ntile(l_tile) * BN;
+    const int buf = l_g % kRing;
+    mbar_arrive_expect_tx(&res_full[buf], kResChunkBytes);
+    tma_load_2d(rbufs + buf * kResChunkBytes, tmap_res, &res_full[buf], ln0 + l_cc * 32, lm0, kEvictFirst);
+    ++l_g;
+    if (++l_cc == chunks_of_tile<BN>(p, ln0)) { l_cc = 0; l_tile += tw.stride; }
+  };
+  if (issuer_warp && !reduce) {
+    if (elect_one()) {
+      for (int i = 0; i < kRing - 1; ++i) request_next();
     }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) b[i] = 0.f;
   }
-  const float* gp = nullptr;
-  if (p.gate != nullptr) {
-    const int row_c = grow < p.M ? grow : p.M - 1;
-    gp = p.gate + (size_t)(row_c / p.rows_per_batch) * p.gate_batch_stride + col0;
+  int g = 0, as = 0, titer = 0;
+  uint32_t aphase = 0;
+  const bool tracing = issuer && p.trace != nullptr && blockIdx.x == 0;   // debug only (tools/gemm_trace.py)
+  int tcnt = 0;
+  auto stamp = [&]() {
+    if (tracing && tcnt < 4096) p.trace[tcnt++] = clock64();
+  };
+
+  for (int tile = tw.first; tile < tw.count; tile += tw.stride, ++titer) {
+    const int m0 = tw.m0(tile);
+    const int nt = tw.ntile(tile);
+    const int n0 = nt * BN;
+    const int nch = chunks_of_tile<BN>(p, n0);
+    EpiConst* cb = consts + (titer & 1);
+    stage_epi_consts<BN>(cb, p, tid, m0, n0);                   // global loads hide under this tile's MMAs
+    named_bar_sync(2, kNumEpiThreads);
+    stamp();                                                    // tile: start waiting for the accumulator
+    mbar_wait(&tfull_bar[as], aphase);
+    stamp();                                                    // tile: accumulator ready
+    tc_fence_after();
+    const uint32_t t_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
+    float2 st = make_float2(0.f, 0.f);                          // this row's (sum, sum of squares) over the tile
+
+    auto process = [&](uint32_t (&v)[32], int cc) {
+      const int buf = g % kRing;
+      uint8_t* rb = rbufs + buf * kResChunkBytes;
+      uint8_t* ab = p.out_aux != nullptr ? abufs + (g & 1) * kAuxChunkBytes : nullptr;
+      stamp();                                                  // chunk: acc in registers
+      if (!reduce) mbar_wait(&res_full[buf], (g / kRing) & 1);  // residual chunk has landed in smem
+      stamp();                                                  // chunk: residual landed
+      residual_chunk_row_c(v, p, cb, rb, ab, r, cc * 32, m0 + r, n0 + cc * 32, reduce, st);
+      fence_proxy_async_smem();                                 // generic-proxy writes -> visible to the TMA store
+      stamp();                                                  // chunk: computed
+      if (issuer_warp) {
+        if (elect_one()) tma_store_wait_read<0>();              // earlier stores have drained their buffers
+      }
+      stamp();                                                  // chunk: previous store drained
+      named_bar_sync(1, kNumEpiThreads);
+      stamp();                                                  // chunk: barrier passed
+      if (issuer_warp) {
+        if (elect_one()) {
+          if (reduce) {
+            tma_reduce_add_2d(tmap_out, rb, n0 + cc * 32, m0);
+            tma_store_commit();
+          } else {
+            tma_store_2d(tmap_out, rb, n0 + cc * 32, m0);
+            if (ab != nullptr) tma_store_2d(tmap_aux, ab, n0 + cc * 32, m0);
+            tma_store_commit();
+            request_next();                                     // refills the buffer chunk g-1 has just left
+          }
+        }
+      }
+      ++g;
+    };
+    auto release_acc = [&]() {                                  // all TMEM reads of this accumulator are done
+      tc_fence_before();
+      if constexpr (kPair) mbar_arrive_cluster(&tempty_bar[as], 0);   // the leader's MMA thread owns the hand-off
+      else mbar_arrive(&tempty_bar[as]);
+    };
+
+    // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed
+    uint32_t va[32], vb[32];
+    tmem_ld_32x32b_x32_nowait(t_acc, va);
+#pragma unroll 1
+    for (int cc = 0; cc < nch; cc += 2) {
+      tmem_ld_wait_x32(va);
+      if (cc + 1 < nch) tmem_ld_32x32b_x32_nowait(t_acc + (cc + 1) * 32, vb); else release_acc();
+      process(va, cc);
+      if (cc + 1 < nch) {
+        tmem_ld_wait_x32(vb);
+        if (cc + 2 < nch) tmem_ld_32x32b_x32_nowait(t_acc + (cc + 2) * 32, va); else release_acc();
+        process(vb, cc + 1);
+      }
+    }
+    if (p.row_stats_out != nullptr && m0 + r < p.M) {           // partial LayerNorm statistics of this row: part = n tile
+      float2* sp = reinterpret_cast<float2*>(p.row_stats_out) + (size_t)(m0 + r) * PXA_LN_STAT_PARTS;
+      sp[nt] = st;
+      if (nt == tw.num_n_tiles - 1)
+        for (int i = tw.num_n_tiles; i < PXA_LN_STAT_PARTS; ++i) sp[i] = make_float2(0.f, 0.f);
+    }
+    as ^= 1;
+    if (as == 0) aphase ^= 1;
   }
-  const int sw = r & 7;
-  uint8_t* rrow = rbuf + r * 128;
-  uint32_t aux[16];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (gp != nullptr && col0 + 4 * c < p.N) g = __ldg(reinterpret_cast<const float4*>(gp + 4 * c));
-    float4* slot = reinterpret_cast<float4*>(rrow + ((c ^ sw) << 4));
-    const float4 res = *slot;
-    float4 o;
-    o.x = fmaf(g.x, __uint_as_float(v[4 * c + 0]) + b[4 * c + 0], res.x);
-    o.y = fmaf(g.y, __uint_as_float(v[4 * c + 1]) + b[4 * c + 1], res.y);
-    o.z = fmaf(g.z, __uint_as_float(v[4 * c + 2]) + b[4 * c + 2], res.z);
-    o.w = fmaf(g.w, __uint_as_float(v[4 * c + 3]) + b[4 * c + 3], res.w);
-    *slot = o;
-    aux[2 * c] = pack_bf16x2(o.x, o.y);
-    aux[2 * c + 1] = pack_bf16x2(o.z, o.w);
-  }
-  if (abuf != nullptr) {
-    const int sw2 = (r >> 1) & 3;
-    uint8_t* arow = abuf + r * 64;
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-      *reinterpret_cast<uint4*>(arow + ((c ^ sw2) << 4)) = make_uint4(aux[4 * c], aux[4 * c + 1], aux[4 * c + 2], aux[4 * c + 3]);
+  if (issuer_warp) {
+    if (elect_one()) tma_store_wait_all<0>();
   }
 }
 

@@ -82,7 +82,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
           // pull this tile's residual block into L2 now: the epilogue reads it one mainloop (~7k cycles) later
           if constexpr (kTmaRes) {
-            if (!(p.out_aux == nullptr && p.residual == p.out))
+            if (!(p.out_aux == nullptr && p.residual == p.out && p.row_stats_out == nullptr))
               for (int c = 0; c < BN / 32; ++c) tma_prefetch_l2_2d(&tmap_res, n0 + c * 32, m0);
           } else {
             tma_prefetch_l2_2d(&tmap_res, n0, m0);
@@ -155,125 +155,67 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp >= kEpiWarp0) {
     // ================================================================ epilogue
-    const int q = warp & 3;                         // TMEM sub-partition of this warp
-    const int tid = threadIdx.x - kEpiWarp0 * 32;   // 0..127
     EpiConst* consts = reinterpret_cast<EpiConst*>(epi_smem + Cfg::kEpiBufs);
-    int as = 0;
-    uint32_t aphase = 0;
-    int titer = 0;
-    // TMA-streamed fp32 residual path state (unused otherwise)
-    const int r = q * 32 + lane;                                  // row of the 128-row tile owned by this thread
-    uint8_t* rbufs = epi_smem;
-    uint8_t* abufs = epi_smem + kRing * kResChunkBytes;          // (unused by the reduce-only configuration)
-    // One thread of the first epilogue warp owns every TMA op of the epilogue.  It is picked with elect.sync inside a
-    // warp-uniform branch (always the same lane for a full warp), so the TMA / mbarrier operands stay in uniform
-    // registers; `issuer_warp` guards the converged regions, `issuer` the elected lane (bulk groups are per thread).
-    const bool issuer_warp = kTmaRes && (warp == kEpiWarp0);
-    bool issuer = false;
-    if (issuer_warp) issuer = elect_one() != 0;
-    // In-place update without a bf16 copy: skip the residual read altogether and let TMA reduce-add the update into x.
-    const bool reduce = kTmaRes && p.out_aux == nullptr && p.residual == p.out;
-    int l_tile = blockIdx.x, l_cc = 0, l_g = 0;                   // issuer: next residual chunk to request
-    auto request_next = [&]() {
-      if (l_tile >= num_tiles) return;
-      const int lm0 = ((l_tile % mn_tiles) / p.num_n_tiles) * kBM;
-      const int ln0 = ((l_tile % mn_tiles) % p.num_n_tiles) * BN;
-      const int buf = l_g % kRing;
-      mbar_arrive_expect_tx(&res_full[buf], kResChunkBytes);
-      tma_load_2d(rbufs + buf * kResChunkBytes, &tmap_res, &res_full[buf], ln0 + l_cc * 32, lm0, kEvictFirst);
-      ++l_g;
-      if (++l_cc == chunks_of_tile<BN>(p, ln0)) { l_cc = 0; l_tile += gridDim.x; }
-    };
-    if (issuer_warp && !reduce) {
-      if (elect_one()) {
-        for (int i = 0; i < kRing - 1; ++i) request_next();
-      }
-    }
-    int g = 0;
-    uint8_t* stile = epi_smem + (warp - kEpiWarp0) * 4096;       // bf16 paths: per-warp transpose tile
-    const bool tracing = issuer && p.trace != nullptr && blockIdx.x == 0;   // debug only (tools/gemm_trace.py)
-    int tcnt = 0;
-    auto stamp = [&]() {
-      if (tracing && tcnt < 4096) p.trace[tcnt++] = clock64();
-    };
-
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
-      const int m0 = ((tile % mn_tiles) / p.num_n_tiles) * kBM;
-      const int n0 = ((tile % mn_tiles) % p.num_n_tiles) * BN;
-      const int nch = chunks_of_tile<BN>(p, n0);
-      EpiConst* cb = consts + (titer & 1);
-      stage_epi_consts<BN>(cb, p, tid, m0, n0);                  // global loads hide under this tile's MMAs
-      named_bar_sync(2, kNumEpiThreads);
-      stamp();                                                    // tile: start waiting for the accumulator
-      mbar_wait(&tfull_bar[as], aphase);
-      stamp();                                                    // tile: accumulator ready
-      tc_fence_after();
-      const uint32_t t_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
-
-      // one chunk: v = this thread's 32 accumulator columns [cc*32, +32)
-      auto process = [&](uint32_t (&v)[32], int cc) {
-        if constexpr (kTmaRes) {
-          const int buf = g % kRing;
-          uint8_t* rb = rbufs + buf * kResChunkBytes;
-          uint8_t* ab = p.out_aux != nullptr ? abufs + (g & 1) * kAuxChunkBytes : nullptr;
-          stamp();                                                  // chunk: acc in registers
-          if (!reduce) mbar_wait(&res_full[buf], (g / kRing) & 1);   // residual chunk has landed in smem
-          stamp();                                                  // chunk: residual landed
-          residual_chunk_row_c(v, p, cb, rb, ab, r, cc * 32, m0 + r, n0 + cc * 32, reduce);
-          fence_proxy_async_smem();                                 // generic-proxy writes -> visible to the TMA store
-          stamp();                                                  // chunk: computed
-          if (issuer_warp) {
-            if (elect_one()) tma_store_wait_read<0>();              // earlier stores have drained their buffers
+    if constexpr (kTmaRes) {
+      // fp32 residual stream: TMA-streamed residual chunks, row per thread (gemm_common.cuh)
+      TileWalk tw;
+      tw.first = blockIdx.x; tw.stride = gridDim.x; tw.count = num_tiles;
+      tw.mn_tiles = mn_tiles; tw.num_n_tiles = p.num_n_tiles; tw.m_mult = kBM; tw.m_off = 0;
+      tma_res_epilogue<BN, kRing, false>(p, tw, epi_smem, consts, tfull_bar, tempty_bar, res_full, tmem_base, &tmap_res,
+                                         &tmap_out, &tmap_aux, warp, lane);
+    } else {
+      constexpr bool kLn = (EPI == PXA_EPI_LN_BIAS || EPI == PXA_EPI_LN_BIAS_GELU);
+      const int q = warp & 3;                         // TMEM sub-partition of this warp
+      const int tid = threadIdx.x - kEpiWarp0 * 32;   // 0..127
+      int as = 0;
+      uint32_t aphase = 0;
+      int titer = 0;
+      uint8_t* stile = epi_smem + (warp - kEpiWarp0) * 4096;       // per-warp transpose tile
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
+        const int m0 = ((tile % mn_tiles) / p.num_n_tiles) * kBM;
+        const int n0 = ((tile % mn_tiles) % p.num_n_tiles) * BN;
+        const int nch = chunks_of_tile<BN>(p, n0);
+        EpiConst* cb = consts + (titer & 1);
+        stage_epi_consts<BN, kLn>(cb, p, tid, m0, n0);             // global loads hide under this tile's MMAs
+        [[maybe_unused]] float2 ln = make_float2(1.f, 0.f);
+        if constexpr (kLn) ln = ln_row_coeffs(p, m0 + q * 32 + lane);
+        named_bar_sync(2, kNumEpiThreads);
+        [[maybe_unused]] const bool second = q * 32 + lane >= cb->row_split;
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        const uint32_t t_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
+        auto process = [&](uint32_t (&v)[32], int cc) {
+          if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
+            ResFrag res;                                            // bf16 residual stream (VAE convolutions): simple path
+            load_residual_frag<OutT>(res, p, lane, m0 + q * 32, n0 + cc * 32);
+            epilogue_chunk_residual<OutT>(v, res, p, stile, lane, m0 + q * 32, n0 + cc * 32);
+          } else if constexpr (kLn) {
+            epilogue_chunk_bf16_c<EPI>(v, p, cb, stile, lane, m0 + q * 32, n0 + cc * 32, cc * 32, ln, second);
+          } else {
+            epilogue_chunk_bf16_c<EPI>(v, p, cb, stile, lane, m0 + q * 32, n0 + cc * 32, cc * 32);
           }
-          stamp();                                                  // chunk: previous store drained
-          named_bar_sync(1, kNumEpiThreads);
-          stamp();                                                  // chunk: barrier passed
-          if (issuer_warp) {
-            if (elect_one()) {
-              if (reduce) {
-                tma_reduce_add_2d(&tmap_out, rb, n0 + cc * 32, m0);
-                tma_store_commit();
-              } else {
-                tma_store_2d(&tmap_out, rb, n0 + cc * 32, m0);
-                if (ab != nullptr) tma_store_2d(&tmap_aux, ab, n0 + cc * 32, m0);
-                tma_store_commit();
-                request_next();                                     // refills the buffer chunk g-1 has just left
-              }
-            }
-          }
-          ++g;
-        } else if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
-          ResFrag res;                                              // bf16 residual stream (rarely used): simple path
-          load_residual_frag<OutT>(res, p, lane, m0 + q * 32, n0 + cc * 32);
-          epilogue_chunk_residual<OutT>(v, res, p, stile, lane, m0 + q * 32, n0 + cc * 32);
-        } else {
-          epilogue_chunk_bf16_c<EPI>(v, p, cb, stile, lane, m0 + q * 32, n0 + cc * 32, cc * 32);
-        }
-      };
-      auto release_acc = [&]() {                                    // all TMEM reads of this accumulator are done
-        tc_fence_before();
-        mbar_arrive(&tempty_bar[as]);
-      };
-
-      // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed
-      uint32_t va[32], vb[32];
-      tmem_ld_32x32b_x32_nowait(t_acc, va);
+        };
+        auto release_acc = [&]() {                                  // all TMEM reads of this accumulator are done
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[as]);
+        };
+        // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32b_x32_nowait(t_acc, va);
 #pragma unroll 1
-      for (int cc = 0; cc < nch; cc += 2) {
-        tmem_ld_wait_x32(va);
-        if (cc + 1 < nch) tmem_ld_32x32b_x32_nowait(t_acc + (cc + 1) * 32, vb); else release_acc();
-        process(va, cc);
-        if (cc + 1 < nch) {
-          tmem_ld_wait_x32(vb);
-          if (cc + 2 < nch) tmem_ld_32x32b_x32_nowait(t_acc + (cc + 2) * 32, va); else release_acc();
-          process(vb, cc + 1);
+        for (int cc = 0; cc < nch; cc += 2) {
+          tmem_ld_wait_x32(va);
+          if (cc + 1 < nch) tmem_ld_32x32b_x32_nowait(t_acc + (cc + 1) * 32, vb); else release_acc();
+          process(va, cc);
+          if (cc + 1 < nch) {
+            tmem_ld_wait_x32(vb);
+            if (cc + 2 < nch) tmem_ld_32x32b_x32_nowait(t_acc + (cc + 2) * 32, va); else release_acc();
+            process(vb, cc + 1);
+          }
         }
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
       }
-      as ^= 1;
-      if (as == 0) aphase ^= 1;
-    }
-    if (issuer_warp) {
-      if (elect_one()) tma_store_wait_all<0>();
     }
   }
 
@@ -360,6 +302,7 @@ static int launch_gemm(const PxaGemmArgs& a, cudaStream_t stream, const ConvGeom
   p.trace = reinterpret_cast<long long*>(a.debug_trace);
   p.k_splits = k_splits;
   p.aux_branch = a.aux_is_branch;
+  fill_ln_params(p, a);
   p.conv_H = p.conv_W = p.conv_tile_w = p.conv_tile_h = p.conv_cin_blocks = 0;
   if constexpr (kConv) {
     p.conv_H = cg->H; p.conv_W = cg->W; p.conv_tile_w = cg->tile_w; p.conv_tile_h = cg->tile_h;
@@ -390,6 +333,10 @@ static int dispatch_epi(const PxaGemmArgs& a, cudaStream_t s) {
       return launch_gemm<BN, PXA_EPI_BIAS_GELU_AUX, __nv_bfloat16>(a, s);
     case PXA_EPI_MUL_DGELU:
       return launch_gemm<BN, PXA_EPI_MUL_DGELU, __nv_bfloat16>(a, s);
+    case PXA_EPI_LN_BIAS:
+      return launch_gemm<BN, PXA_EPI_LN_BIAS, __nv_bfloat16>(a, s);
+    case PXA_EPI_LN_BIAS_GELU:
+      return launch_gemm<BN, PXA_EPI_LN_BIAS_GELU, __nv_bfloat16>(a, s);
     case PXA_EPI_BIAS_RESIDUAL:
       if (a.residual == nullptr) return fail(PXA_ERR_ARG, "EPI_BIAS_RESIDUAL needs residual");
       if (a.out_dtype == PXA_DTYPE_F32) return launch_gemm<BN, PXA_EPI_BIAS_RESIDUAL, float>(a, s);
@@ -500,6 +447,26 @@ extern "C" int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream) {
   if (a.epilogue == PXA_EPI_MUL_DGELU && (a.residual == nullptr || a.bias != nullptr))
     return fail(PXA_ERR_ARG, "EPI_MUL_DGELU needs the pre-activation in `residual` and no bias");
   if (a.cta_pair < 0 || a.cta_pair > 2) return fail(PXA_ERR_ARG, "cta_pair must be 0, 1 or 2");
+  // fused LayerNorm-modulate: consumer epilogues and the producer by-products of the fp32 residual epilogue
+  const bool ln_epi = a.epilogue == PXA_EPI_LN_BIAS || a.epilogue == PXA_EPI_LN_BIAS_GELU;
+  const int rpb = a.rows_per_batch > 0 ? a.rows_per_batch : a.M;
+  if (ln_epi) {
+    if (!a.ln_stats || !a.ln_u || !a.ln_v || a.ln_dim <= 0 || a.bias)
+      return fail(PXA_ERR_ARG, "EPI_LN_*: ln_stats / ln_u / ln_v / ln_dim required and bias must be NULL (it is part of ln_v)");
+    if ((reinterpret_cast<uintptr_t>(a.ln_stats) | reinterpret_cast<uintptr_t>(a.ln_u) | reinterpret_cast<uintptr_t>(a.ln_v)) & 15)
+      return fail(PXA_ERR_ALIGN, "ln_stats / ln_u / ln_v must be 16-byte aligned");
+  }
+  if (a.aux_scale || a.row_stats_out) {
+    if (a.epilogue != PXA_EPI_BIAS_RESIDUAL || a.out_dtype != PXA_DTYPE_F32)
+      return fail(PXA_ERR_ARG, "aux_scale / row_stats_out belong to the fp32 residual epilogue");
+    if (a.aux_scale && !a.out_aux_bf16) return fail(PXA_ERR_ARG, "aux_scale needs out_aux_bf16");
+    if (a.res_epilogue == 1) return fail(PXA_ERR_ARG, "aux_scale / row_stats_out need the TMA-streamed residual epilogue");
+    if ((reinterpret_cast<uintptr_t>(a.aux_scale) | reinterpret_cast<uintptr_t>(a.row_stats_out)) & 15)
+      return fail(PXA_ERR_ALIGN, "aux_scale / row_stats_out must be 16-byte aligned");
+  }
+  if ((ln_epi || a.aux_scale) && rpb < kBM && a.M > rpb)
+    return fail(PXA_ERR_ARG, "the fused LayerNorm-modulate needs rows_per_batch >= %d (a tile may span two samples at most)", kBM);
+  if (a.res_epilogue < 0 || a.res_epilogue > 2) return fail(PXA_ERR_ARG, "res_epilogue must be 0, 1 or 2");
   // auto (measured at M = 32768, tools/gemm_bench.py): the CTA pair with 256 x 256 tiles wins for every bias / GELU
   // GEMM; the fp32 residual epilogue is HBM-bound at K = 1152 and streams through TMA chunk buffers on the single-CTA
   // kernel, while at K >= 2304 it is MMA-bound and the pair kernel's deeper smem ring (7 stages) wins.
@@ -515,6 +482,8 @@ extern "C" int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream) {
       bn = 256;      // fewer, wider tiles: 100 us vs 107 us (BN = 192) at N = K = 1152, even with a half-empty last column tile
     }
   }
+  if (a.row_stats_out && (a.N + bn - 1) / bn > PXA_LN_STAT_PARTS)
+    return fail(PXA_ERR_ARG, "row_stats_out: N / block_n = %d column tiles exceed PXA_LN_STAT_PARTS", (a.N + bn - 1) / bn);
   if (pair) return gemm_pair_dispatch(a, bn, s);
   switch (bn) {
     case 128: return dispatch_epi<128>(a, s);

@@ -15,7 +15,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PXA_LIB_PATH") or os.path.join(_HERE, "libpixart_sm100.so")   # override: experiment builds only
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
-EPI_BIAS_GELU_AUX, EPI_MUL_DGELU = 3, 4      # experimental MLP training fusions (include/pixart_sm100.h)
+EPI_BIAS_GELU_AUX, EPI_MUL_DGELU = 3, 4      # MLP training fusions (include/pixart_sm100.h)
+EPI_LN_BIAS, EPI_LN_BIAS_GELU = 5, 6         # fused LayerNorm-modulate consumer epilogues
+LN_STAT_PARTS = 8
 DTYPE_BF16, DTYPE_F32 = 0, 1
 
 
@@ -31,7 +33,16 @@ class GemmArgs(C.Structure):
                 ("lda", C.c_int32), ("ldw", C.c_int32), ("ldo", C.c_int32),
                 ("epilogue", C.c_int32), ("out_dtype", C.c_int32), ("block_n", C.c_int32), ("max_ctas", C.c_int32),
                 ("cta_pair", C.c_int32), ("debug_trace", C.c_void_p), ("operands_mn_major", C.c_int32),
-                ("k_splits", C.c_int32), ("aux_is_branch", C.c_int32)]
+                ("k_splits", C.c_int32), ("aux_is_branch", C.c_int32),
+                ("aux_scale", C.c_void_p), ("aux_scale_batch_stride", C.c_int64), ("row_stats_out", C.c_void_p),
+                ("ln_stats", C.c_void_p), ("ln_u", C.c_void_p), ("ln_v", C.c_void_p), ("ln_uv_batch_stride", C.c_int64),
+                ("ln_dim", C.c_int32), ("ln_eps", C.c_float), ("res_epilogue", C.c_int32)]
+
+
+class LnPrepareArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("a_out", C.c_void_p), ("stats_out", C.c_void_p), ("scale", C.c_void_p),
+                ("mod_batch_stride", C.c_int64), ("rows_per_batch", C.c_int32), ("M", C.c_int32), ("C", C.c_int32),
+                ("ldx", C.c_int32)]
 
 
 class LnModArgs(C.Structure):
@@ -103,7 +114,8 @@ class AttnBwdArgs(C.Structure):
 EXPORTS = ("pxa_transpose_bf16", "pxa_gelu_tanh_bf16", "pxa_gate_residual_fwd", "pxa_gate_residual_bwd",
            "pxa_ln_modulate_bwd", "pxa_colsum_bf16", "pxa_attn_delta_d72", "pxa_flash_attn_d72_bwd_bf16", "pxa_kv_compress_conv2_ln_bwd",
            "pxa_version", "pxa_last_error", "pxa_launch_count", "pxa_gemm_bf16", "pxa_ln_modulate",
-           "pxa_flash_attn_d72_bf16", "pxa_kv_compress_conv2_ln", "pxa_conv3x3_nhwc_bf16", "pxa_dpm_solver_pp_step")
+           "pxa_flash_attn_d72_bf16", "pxa_kv_compress_conv2_ln", "pxa_conv3x3_nhwc_bf16", "pxa_dpm_solver_pp_step",
+           "pxa_ln_prepare", "pxa_layernorm_affine_bf16")
 
 _lib = None
 
@@ -120,7 +132,8 @@ def load() -> C.CDLL:
         lib.pxa_launch_count.restype = C.c_uint64
         for name, struct in (("pxa_gemm_bf16", GemmArgs), ("pxa_ln_modulate", LnModArgs),
                              ("pxa_flash_attn_d72_bf16", AttnArgs), ("pxa_kv_compress_conv2_ln", KvCompressArgs),
-                             ("pxa_conv3x3_nhwc_bf16", Conv3x3Args), ("pxa_dpm_solver_pp_step", DpmStepArgs)):
+                             ("pxa_conv3x3_nhwc_bf16", Conv3x3Args), ("pxa_dpm_solver_pp_step", DpmStepArgs),
+                             ("pxa_ln_prepare", LnPrepareArgs)):
             fn = getattr(lib, name)
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(struct), C.c_void_p]
@@ -130,6 +143,9 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(struct), C.c_void_p]
+        lib.pxa_layernorm_affine_bf16.restype = C.c_int
+        lib.pxa_layernorm_affine_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_float,
+                                                  C.c_void_p]
         lib.pxa_transpose_bf16.restype = C.c_int
         lib.pxa_transpose_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p]
         lib.pxa_gelu_tanh_bf16.restype = C.c_int
@@ -172,8 +188,15 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
          epilogue: int = EPI_BIAS, residual: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
          gate_batch_stride: int = 0, rows_per_batch: int = 0, out_aux: Optional[torch.Tensor] = None,
          block_n: int = 0, max_ctas: int = 0, cta_pair: int = 0, debug_trace: Optional[torch.Tensor] = None,
-         aux_is_branch: bool = False) -> torch.Tensor:
-    """out = epilogue(a @ w.T + bias). a (M,K) bf16, w (N,K) bf16 (nn.Linear layout), both K-contiguous."""
+         aux_is_branch: bool = False, aux_scale: Optional[torch.Tensor] = None, aux_scale_batch_stride: int = 0,
+         row_stats_out: Optional[torch.Tensor] = None, ln_stats: Optional[torch.Tensor] = None,
+         ln_u: Optional[torch.Tensor] = None, ln_v: Optional[torch.Tensor] = None, ln_uv_batch_stride: int = 0,
+         ln_dim: int = 0, ln_eps: float = 1e-6, res_epilogue: int = 0) -> torch.Tensor:
+    """out = epilogue(a @ w.T + bias). a (M,K) bf16, w (N,K) bf16 (nn.Linear layout), both K-contiguous.
+
+    Fused LayerNorm-modulate (include/pixart_sm100.h, PXA_EPI_LN_BIAS): the fp32 residual epilogue can emit the scaled bf16
+    copy `out_aux = out * aux_scale[b]` and the per-row partial sums `row_stats_out` (M, 8, 2); the EPI_LN_* epilogues
+    consume them (`ln_stats`) together with the per-sample vectors `ln_u`, `ln_v` (fp32 views, row b at b * stride)."""
     assert a.is_cuda and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1 and out.dim() == 2 and out.stride(1) == 1
     M, K = a.shape
@@ -187,14 +210,33 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
         assert gate.dtype == torch.float32
     if out_aux is not None:
         assert out_aux.dtype == torch.bfloat16 and out_aux.shape == out.shape and out_aux.stride() == out.stride()
+    for tns in (aux_scale, ln_u, ln_v):
+        assert tns is None or (tns.dtype == torch.float32 and tns.is_cuda)
+    for tns in (row_stats_out, ln_stats):
+        assert tns is None or (tns.dtype == torch.float32 and tns.is_contiguous() and tns.numel() == M * LN_STAT_PARTS * 2)
     args = GemmArgs(a=_ptr(a), w=_ptr(w), bias=_ptr(bias), out=_ptr(out), out_aux_bf16=_ptr(out_aux),
                     residual=_ptr(residual), gate=_ptr(gate), gate_batch_stride=gate_batch_stride,
                     rows_per_batch=rows_per_batch or M, M=M, N=N, K=K, lda=a.stride(0), ldw=w.stride(0),
                     ldo=out.stride(0), epilogue=epilogue, out_dtype=_dt(out.dtype), block_n=block_n, max_ctas=max_ctas,
                     cta_pair=cta_pair, debug_trace=_ptr(debug_trace), operands_mn_major=0, k_splits=0,
-                    aux_is_branch=int(aux_is_branch))
+                    aux_is_branch=int(aux_is_branch), aux_scale=_ptr(aux_scale), aux_scale_batch_stride=aux_scale_batch_stride,
+                    row_stats_out=_ptr(row_stats_out), ln_stats=_ptr(ln_stats), ln_u=_ptr(ln_u), ln_v=_ptr(ln_v),
+                    ln_uv_batch_stride=ln_uv_batch_stride, ln_dim=ln_dim, ln_eps=ln_eps, res_epilogue=res_epilogue)
     _check(load().pxa_gemm_bf16(C.byref(args), _stream()), "pxa_gemm_bf16")
     return out
+
+
+def ln_prepare(x: torch.Tensor, scale: torch.Tensor, a_out: torch.Tensor, stats_out: torch.Tensor, *, mod_batch_stride: int,
+               rows_per_batch: int) -> None:
+    """First link of the fused LayerNorm-modulate chain: a_out = bf16(x * (1 + scale[b])), stats_out (M, 8, 2) = partial
+    (sum, sum of squares) of each row of x (part 0; the rest zero).  x (M, C) fp32, scale an fp32 view (row b at b*stride)."""
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1 and scale.dtype == torch.float32
+    M, Cc = x.shape
+    assert a_out.dtype == torch.bfloat16 and a_out.is_contiguous() and a_out.shape == (M, Cc)
+    assert stats_out.dtype == torch.float32 and stats_out.is_contiguous() and stats_out.numel() == M * LN_STAT_PARTS * 2
+    args = LnPrepareArgs(x=_ptr(x), a_out=_ptr(a_out), stats_out=_ptr(stats_out), scale=_ptr(scale),
+                         mod_batch_stride=mod_batch_stride, rows_per_batch=rows_per_batch, M=M, C=Cc, ldx=x.stride(0))
+    _check(load().pxa_ln_prepare(C.byref(args), _stream()), "pxa_ln_prepare")
 
 
 def ln_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, out: torch.Tensor, *,
@@ -207,6 +249,15 @@ def ln_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, out: 
                      rows_per_batch=rows_per_batch, M=M, C=Cc, ldx=x.stride(0), x_dtype=_dt(x.dtype), eps=eps)
     _check(load().pxa_ln_modulate(C.byref(args), _stream()), "pxa_ln_modulate")
     return out
+
+
+def layernorm_affine_(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """In-place LayerNorm with affine parameters on the rows of a bf16 (M, 1152) view with unit column stride (qk_norm)."""
+    assert x.dtype == weight.dtype == bias.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    assert weight.is_contiguous() and bias.is_contiguous() and weight.numel() == bias.numel() == x.shape[1]
+    _check(load().pxa_layernorm_affine_bf16(_ptr(x), _ptr(weight), _ptr(bias), x.shape[0], x.shape[1], x.stride(0), eps,
+                                            _stream()), "pxa_layernorm_affine_bf16")
+    return x
 
 
 def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, B: int, H: int, Nq: int,

@@ -206,6 +206,87 @@ class _Workspace:
         return t
 
 
+_LN_FUSE_MIN_ROWS = 128      # a 128-row GEMM tile may span at most two samples (include/pixart_sm100.h)
+
+
+def _ln_ctx(u: torch.Tensor, v: torch.Tensor, one_plus: torch.Tensor, i: int, stats: torch.Tensor) -> dict:
+    """`ln` argument of PixArtMSBlock.run_kernels for block i of a chain (see _LnFusion.prepare)."""
+    return {"stats": stats, "u": u[i], "v": v[i], "uv_stride": u.stride(1), "one_plus": one_plus[i], "prepare": i == 0,
+            "next_one_plus": one_plus[i + 1] if i + 1 < one_plus.shape[0] else None}
+
+
+class _LnFusion:
+    """Per-forward conditioning of the FUSED LayerNorm-modulate (include/pixart_sm100.h, PXA_EPI_LN_BIAS).
+
+    norm1 + t2i_modulate + attn.qkv (PixArtMS.py:75; PixArt_blocks.py:24-25,130) and norm2 + t2i_modulate + mlp.fc1
+    (PixArtMS.py:77) are evaluated as  rstd_r * (A W^T - mu_r u_b) + v_b  in the GEMM epilogue, where A = bf16(x (1 + scale_b))
+    and the row statistics come out of the residual epilogue that produced x.  This object owns what depends on the
+    weights and the timestep only:
+        u[i, b] = W_i (1 + scale_{i,b}),   v[i, b] = W_i shift_{i,b} + bias_i        for W_i in (qkv_i | fc1_i), fp32,
+    with scale / shift = scale_shift_table_i + t0_b (adaLN-single: ONE t0 for all blocks).  The table part is static and
+    computed once per weight version; the t0 part is ONE skinny GEMM per forward against the row-stacked weights of all
+    blocks (a bf16 copy, 0.52 GB at depth 28), operands split into bf16 hi + lo parts so the result is fp32-accurate."""
+
+    def __init__(self, blocks):
+        self.blocks = list(blocks)
+        self.key = None
+        self.wstack = self.s_u = self.s_v = None
+
+    def _weights(self):
+        for blk in self.blocks:
+            yield blk.attn.qkv
+            yield blk.mlp.fc1
+
+    @staticmethod
+    def _split(t: torch.Tensor):
+        hi = t.to(torch.bfloat16)
+        return hi, (t - hi.float()).to(torch.bfloat16)
+
+    def _skinny(self, rows: torch.Tensor, w: torch.Tensor, name: str, ws: "_Workspace") -> torch.Tensor:
+        """fp32 (rows @ w.T) for a few fp32 rows: hi / lo bf16 split of the rows, one GEMM, reduce-add into a zeroed buffer."""
+        hi, lo = self._split(rows)
+        a = torch.cat([hi, lo], dim=0).contiguous()
+        out = ws.get(name, (a.shape[0], w.shape[0]), torch.float32, w.device)
+        out.zero_()
+        lib.gemm(a, w, None, out, epilogue=lib.EPI_BIAS_RESIDUAL, residual=out)
+        return out[: rows.shape[0]] + out[rows.shape[0]:]
+
+    def _static(self, ws: "_Workspace"):
+        mods = list(self._weights())
+        key = tuple((m.weight._version, m.weight.data_ptr(), m.bias._version) for m in mods) + tuple(
+            (b.scale_shift_table._version, b.scale_shift_table.data_ptr()) for b in self.blocks)
+        if key == self.key:
+            return
+        w0 = mods[0].weight
+        self.n1, self.n2 = mods[0].weight.shape[0], mods[1].weight.shape[0]
+        self.ntot = self.n1 + self.n2
+        self.wstack = torch.cat([m.weight.detach() for m in mods], dim=0).contiguous()          # (depth * ntot, C) bf16
+        s_u, s_v = [], []
+        for blk in self.blocks:
+            tab = blk.scale_shift_table.detach().float()                                          # (6, C)
+            for lin, i_shift, i_scale in ((blk.attn.qkv, 0, 1), (blk.mlp.fc1, 3, 4)):
+                r = self._skinny(torch.stack([1.0 + tab[i_scale], tab[i_shift]]), lin.weight.detach(), "ln_static", ws)
+                s_u.append(r[0].clone())
+                s_v.append(r[1] + lin.bias.detach().float())
+        depth = len(self.blocks)
+        self.s_u = torch.cat(s_u).view(depth, self.ntot)
+        self.s_v = torch.cat(s_v).view(depth, self.ntot)
+        self.key = key
+
+    def prepare(self, t0: torch.Tensor, mod_all: torch.Tensor, ws: "_Workspace"):
+        """t0 (B, 6, C) fp32 (the t_block output), mod_all (depth, B, 6, C) = tables + t0.
+        Returns u, v (depth, B, ntot) fp32 and one_plus (depth, B, 2, C) = 1 + (scale_msa | scale_mlp)."""
+        self._static(ws)
+        depth, B = mod_all.shape[0], mod_all.shape[1]
+        rows = t0[:, [0, 1, 3, 4]].permute(1, 0, 2).reshape(4 * B, -1)            # kind-major: shift_msa, scale_msa, shift_mlp, scale_mlp
+        g = self._skinny(rows, self.wstack, "ln_dyn", ws).view(4, B, depth, self.ntot)
+        n1 = self.n1
+        u = torch.cat([g[1, :, :, :n1], g[3, :, :, n1:]], dim=-1).permute(1, 0, 2) + self.s_u[:, None]
+        v = torch.cat([g[0, :, :, :n1], g[2, :, :, n1:]], dim=-1).permute(1, 0, 2) + self.s_v[:, None]
+        one_plus = (1.0 + mod_all[:, :, [1, 4]]).contiguous()
+        return u.contiguous(), v.contiguous(), one_plus
+
+
 def _wants_grad(module: nn.Module, *inputs) -> bool:
     """True when autograd will record this call: grad mode on and a parameter or an input requires grad."""
     if not torch.is_grad_enabled():
@@ -241,17 +322,21 @@ class PixArtMSBlock(nn.Module):
         self.drop_path = nn.Identity()
         self.scale_shift_table = nn.Parameter(torch.randn(6, hidden_size) / hidden_size ** 0.5)
         self._ws = _Workspace()
+        self.__dict__["_ln_fusion"] = None        # built lazily by a stand-alone forward (not a submodule / state)
 
     # -- the fused path ---------------------------------------------------------------------------------------
     def run_kernels(self, x32: torch.Tensor, cond: torch.Tensor, kv_len: Optional[torch.Tensor],
                     kv_off: Optional[torch.Tensor], max_keys: int, mod: torch.Tensor, B: int, N: int,
-                    HW: Tuple[int, int], ws: _Workspace) -> torch.Tensor:
+                    HW: Tuple[int, int], ws: _Workspace, ln: Optional[dict] = None) -> torch.Tensor:
         """One block on the kernels, in place on the fp32 residual stream.
 
         x32  (B*N, C) fp32 residual stream (updated in place and returned)
         cond (rows, C) bf16 embedded caption tokens; sample b's keys are rows kv_off[b] .. +kv_len[b]
              (kv_off None -> b*max_keys, kv_len None -> max_keys)
         mod  (B, 6, C) fp32 = scale_shift_table + t0  (shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp)
+        ln   None: norm + modulate as a stand-alone pass (pxa_ln_modulate) before the QKV / fc1 GEMMs.
+             dict (from `_ln_ctx`): the FUSED form -- LayerNorm + t2i_modulate evaluated inside the QKV / fc1 GEMM epilogues
+             from the scaled bf16 copy of x and the row statistics that the preceding residual epilogue left behind.
         """
         C, H = self.hidden_size, self.attn.num_heads
         M, dev = B * N, x32.device
@@ -259,18 +344,29 @@ class PixArtMSBlock(nn.Module):
         _require_kernel_ready(a.qkv.weight, "PixArtMSBlock")
         if self.training and self.drop_path_rate > 0:
             raise NotImplementedError("stochastic depth (drop_path > 0) is not supported by the fused block")
-        if not isinstance(a.q_norm, nn.Identity):
-            raise NotImplementedError("qk_norm=True is not supported by the fused block yet")
         bf = torch.bfloat16
         xn = ws.get("xn", (M, C), bf, dev)
         qkv = ws.get("qkv", (M, 3 * C), bf, dev)
         ao = ws.get("attn_o", (M, C), bf, dev)
         xb = ws.get("x_bf16", (M, C), bf, dev)
         ms = mod.stride(0)
+        fused = ln is not None
+        if fused:
+            stats, u, v, one_plus, uvs = ln["stats"], ln["u"], ln["v"], ln["one_plus"], ln["uv_stride"]
+            n1 = a.qkv.out_features
+            lnkw = dict(ln_stats=stats, ln_uv_batch_stride=uvs, ln_dim=C, ln_eps=self.norm1.eps)
 
         # (1) x += gate_msa * proj(attn(LN(x) * (1 + scale_msa) + shift_msa))                     PixArtMS.py:75
-        lib.ln_modulate(x32, mod[:, 0], mod[:, 1], xn, mod_batch_stride=ms, rows_per_batch=N)
-        lib.gemm(xn, a.qkv.weight, a.qkv.bias, qkv)
+        if fused:
+            if ln["prepare"]:                       # first link of the chain: nobody has produced A / statistics for this x yet
+                lib.ln_prepare(x32, one_plus[:, 0], xn, stats, mod_batch_stride=one_plus.stride(0), rows_per_batch=N)
+            lib.gemm(xn, a.qkv.weight, None, qkv, epilogue=lib.EPI_LN_BIAS, rows_per_batch=N, ln_u=u[:, :n1], ln_v=v[:, :n1], **lnkw)
+        else:
+            lib.ln_modulate(x32, mod[:, 0], mod[:, 1], xn, mod_batch_stride=ms, rows_per_batch=N)
+            lib.gemm(xn, a.qkv.weight, a.qkv.bias, qkv)
+        if not isinstance(a.q_norm, nn.Identity):                                            # PixArt_blocks.py:133-134
+            lib.layernorm_affine_(qkv[:, :C], a.q_norm.weight, a.q_norm.bias, eps=a.q_norm.eps)
+            lib.layernorm_affine_(qkv[:, C:2 * C], a.k_norm.weight, a.k_norm.bias, eps=a.k_norm.eps)
         q3 = qkv.view(M, 3, H, C // H)
         k_src, v_src, k_str, n_keys = q3[:, 1], q3[:, 2], (3 * C, C // H), N
         if a.sr_ratio > 1:                                                                   # PixArt_blocks.py:137-139
@@ -290,14 +386,28 @@ class PixArtMSBlock(nn.Module):
         lib.flash_attn(qx, kv4[:, 0], kv4[:, 1], ao, B=B, H=H, Nq=N, Nk=max_keys, kv_rows=cond.shape[0],
                        kv_len=kv_len, kv_off=kv_off, q_strides=(C, C // H), k_strides=(2 * C, C // H),
                        v_strides=(2 * C, C // H), scale=(C // H) ** -0.5)
-        lib.gemm(ao, ca.proj.weight, ca.proj.bias, x32, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x32)
+        if fused:       # the epilogue that produces x also leaves A = bf16(x (1 + scale_mlp)) and the row statistics of x
+            lib.gemm(ao, ca.proj.weight, ca.proj.bias, x32, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x32, rows_per_batch=N,
+                     out_aux=xn, aux_scale=one_plus[:, 1], aux_scale_batch_stride=one_plus.stride(0), row_stats_out=stats)
+        else:
+            lib.gemm(ao, ca.proj.weight, ca.proj.bias, x32, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x32)
 
         # (3) x += gate_mlp * fc2(gelu_tanh(fc1(LN(x) * (1 + scale_mlp) + shift_mlp)))           PixArtMS.py:77
         hid = ws.get("mlp_hidden", (M, mlp.fc1.out_features), bf, dev)
-        lib.ln_modulate(x32, mod[:, 3], mod[:, 4], xn, mod_batch_stride=ms, rows_per_batch=N)
-        lib.gemm(xn, mlp.fc1.weight, mlp.fc1.bias, hid, epilogue=lib.EPI_BIAS_GELU)
-        lib.gemm(hid, mlp.fc2.weight, mlp.fc2.bias, x32, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x32, gate=mod[:, 5],
-                 gate_batch_stride=ms, rows_per_batch=N)
+        if fused:
+            lib.gemm(xn, mlp.fc1.weight, None, hid, epilogue=lib.EPI_LN_BIAS_GELU, rows_per_batch=N, ln_u=u[:, n1:], ln_v=v[:, n1:],
+                     **lnkw)
+        else:
+            lib.ln_modulate(x32, mod[:, 3], mod[:, 4], xn, mod_batch_stride=ms, rows_per_batch=N)
+            lib.gemm(xn, mlp.fc1.weight, mlp.fc1.bias, hid, epilogue=lib.EPI_BIAS_GELU)
+        nxt = ln.get("next_one_plus") if fused else None
+        if nxt is not None:                         # ... and here A / statistics for the NEXT block's norm1
+            lib.gemm(hid, mlp.fc2.weight, mlp.fc2.bias, x32, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x32, gate=mod[:, 5],
+                     gate_batch_stride=ms, rows_per_batch=N, out_aux=xn, aux_scale=nxt[:, 0], aux_scale_batch_stride=nxt.stride(0),
+                     row_stats_out=stats)
+        else:
+            lib.gemm(hid, mlp.fc2.weight, mlp.fc2.bias, x32, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x32, gate=mod[:, 5],
+                     gate_batch_stride=ms, rows_per_batch=N)
         return x32
 
     def _compress_kv(self, qkv, B, N, HW, ws):
@@ -345,7 +455,13 @@ class PixArtMSBlock(nn.Module):
             from .autograd import block_forward_train
             out = block_forward_train(self, x32, cond, kv_len, kv_off, max(max(lens), 1), mod, B, N, None, tuple(HW))
         else:
-            out = self.run_kernels(x32, cond, kv_len, kv_off, max(max(lens), 1), mod, B, N, tuple(HW), self._ws)
+            ln = None
+            if N >= _LN_FUSE_MIN_ROWS:
+                if self._ln_fusion is None:
+                    self.__dict__["_ln_fusion"] = _LnFusion([self])
+                u, v, one_plus = self._ln_fusion.prepare(t.reshape(B, 6, C).float(), mod[None], self._ws)
+                ln = _ln_ctx(u, v, one_plus, 0, self._ws.get("ln_stats", (B * N, lib.LN_STAT_PARTS, 2), torch.float32, x.device))
+            out = self.run_kernels(x32, cond, kv_len, kv_off, max(max(lens), 1), mod, B, N, tuple(HW), self._ws, ln)
         return out.view(B, N, C).to(x.dtype)
 
 
@@ -412,6 +528,9 @@ class PixArtMS(nn.Module):
         # the DPM-Solver time 749.25 into 748 and moves the output by up to 5e-2.  Default: keep the
         # timestep in fp32 like the fp32 reference does; set True to reproduce the bf16 cast bit for bit.
         self.round_timestep_to_dtype = False
+        # LayerNorm + t2i_modulate inside the QKV / fc1 GEMM epilogues (no stand-alone norm pass); False = pxa_ln_modulate
+        self.fuse_ln_modulate = True
+        self.__dict__["_ln_fusion"] = None
         self._ws = _Workspace()
         self.initialize()
 
@@ -479,8 +598,15 @@ class PixArtMS(nn.Module):
         mod_all = (tables[:, None] + t0.view(1, B, 6, C)).contiguous()                          # (depth, B, 6, C)
 
         cond, kv_len, max_keys = self._condition(y, mask, B)
+        fused = self.fuse_ln_modulate and N >= _LN_FUSE_MIN_ROWS and len(self.blocks) > 0
+        if fused:
+            if self._ln_fusion is None:
+                self.__dict__["_ln_fusion"] = _LnFusion(self.blocks)
+            u, v, one_plus = self._ln_fusion.prepare(t0.view(B, 6, C), mod_all, self._ws)
+            stats = self._ws.get("ln_stats", (B * N, lib.LN_STAT_PARTS, 2), torch.float32, dev)
         for i, blk in enumerate(self.blocks):
-            blk.run_kernels(x32, cond, kv_len, None, max_keys, mod_all[i], B, N, (self.h, self.w), self._ws)
+            blk.run_kernels(x32, cond, kv_len, None, max_keys, mod_all[i], B, N, (self.h, self.w), self._ws,
+                            _ln_ctx(u, v, one_plus, i, stats) if fused else None)
 
         fl = self.final_layer                                                                  # uses t, not t0 (:208)
         fmod = (fl.scale_shift_table.float()[None] + t[:, None]).contiguous()                  # (B, 2, C): shift, scale

@@ -148,11 +148,6 @@ def test_gemm_residual_epilogue_keeps_the_branch_output(K):
     assert po.rel_err(y.float(), branch) < 4e-3
 
 
-experimental = pytest.mark.skipif(__import__("os").environ.get("PXA_EXPERIMENTAL", "0") != "1",
-                                  reason="experimental kernels: compiled but not yet validated on a B200 (set PXA_EXPERIMENTAL=1)")
-
-
-@experimental
 @pytest.mark.parametrize("M,N,K,pair", [(2048, 4608, 1152, 0), (512, 256, 128, 1), (1000, 4608, 1152, 2)])
 def test_gemm_gelu_epilogue_keeps_the_pre_activation(M, N, K, pair):
     a, w, bias = _randn(M, K, seed=70), _randn(N, K, seed=71, scale=K ** -0.5), _randn(N, seed=72, scale=0.1)
@@ -164,7 +159,6 @@ def test_gemm_gelu_epilogue_keeps_the_pre_activation(M, N, K, pair):
     assert po.rel_err(h.float(), F.gelu(want, approximate="tanh")) < 4e-3
 
 
-@experimental
 @pytest.mark.parametrize("M,N,K,pair", [(2048, 4608, 1152, 0), (512, 256, 128, 1), (1000, 4608, 1152, 2)])
 def test_gemm_dgelu_epilogue(M, N, K, pair):
     """dgrad GEMM of the MLP's second layer with gelu'(pre) applied in the epilogue: out = (dy W) * gelu'(pre)."""
@@ -190,7 +184,7 @@ def _attn_ref(q, k, v, lens, scale):
 @pytest.mark.parametrize("B,H,Nq,Nk,lens", [
     (1, 2, 128, 128, None), (2, 3, 256, 256, None), (1, 16, 1024, 1024, None), (2, 2, 256, 64, None),
     (2, 2, 128, 300, [300, 77]), (3, 4, 256, 300, [5, 130, 256]), (2, 2, 200, 200, None), (1, 3, 4032, 4032, None),
-    (2, 2, 72, 300, [300, 41]),
+    (2, 2, 72, 300, [300, 41]), (2, 2, 201, 130, None), (1, 3, 1089, 1089, None),     # Nq % 4 != 0: no TMA copies of lse / delta
 ])
 def test_flash_attn_backward(B, H, Nq, Nk, lens):
     D, C = 72, H * 72

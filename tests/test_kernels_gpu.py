@@ -169,6 +169,118 @@ def test_ln_modulate(xdtype):
     assert po.rel_err(out.float(), want) < 4e-3
 
 
+# ------------------------------------------------------------------------------------------------- fused LN-modulate chain
+def _ln_reference(x, shift, scale, w, bias, rows_per_batch, gelu):
+    """F.linear(LN(x) * (1 + scale_b) + shift_b, w, bias) in fp32 -- what norm + t2i_modulate + Linear compute
+    (PixArtMS.py:75,77; PixArt_blocks.py:24-25)."""
+    B = x.shape[0] // rows_per_batch
+    xn = po.ln_modulate(x.view(B, rows_per_batch, -1), shift[:, None], scale[:, None]).reshape(x.shape)
+    y = F.linear(xn, w.float(), bias.float())
+    return F.gelu(y, approximate="tanh") if gelu else y
+
+
+def _uv(w, bias, shift, scale):
+    """u_b = W (1 + scale_b), v_b = W shift_b + bias in fp32 (the per-sample vectors of PXA_EPI_LN_BIAS)."""
+    return (1.0 + scale) @ w.float().T, shift @ w.float().T + bias.float()
+
+
+def test_ln_prepare_scaled_copy_and_row_sums():
+    B, Ntok, Cc = 3, 200, 1152
+    x = _randn(B * Ntok, Cc, seed=50, dtype=torch.float32) * 2 + 0.3
+    mod = _randn(B, 6, Cc, seed=51, dtype=torch.float32) * 0.3
+    a = torch.empty(B * Ntok, Cc, dtype=torch.bfloat16, device=DEV)
+    stats = torch.full((B * Ntok, lib.LN_STAT_PARTS, 2), float("nan"), device=DEV)
+    lib.ln_prepare(x, mod[:, 4], a, stats, mod_batch_stride=6 * Cc, rows_per_batch=Ntok)
+    want = x * (1 + mod[:, 4].repeat_interleave(Ntok, 0))
+    assert po.rel_err(a.float(), want) < 4e-3
+    assert po.rel_err(stats.sum(1)[:, 0], x.sum(1)) < 1e-5 and po.rel_err(stats.sum(1)[:, 1], (x * x).sum(1)) < 1e-5
+    assert torch.equal(stats[:, 1:], torch.zeros_like(stats[:, 1:]))
+
+
+@pytest.mark.parametrize("N,gelu,pair,rpb", [(3456, False, 0, 1024), (4608, True, 0, 1024), (3456, False, 1, 200),
+                                            (1152, True, 2, 333), (384, False, 0, 2048)])
+def test_gemm_ln_epilogue_matches_norm_modulate_linear(N, gelu, pair, rpb):
+    """EPI_LN_BIAS(_GELU): LayerNorm + modulate folded into the GEMM epilogue vs the unfused fp32 computation.  Row groups of
+    200 / 333 rows put sample boundaries inside 128-row tiles (two staged u / v rows per tile)."""
+    B, K = 2, 1152
+    M = B * rpb
+    x = _randn(M, K, seed=52, dtype=torch.float32) * 1.7 + _randn(M, 1, seed=53, dtype=torch.float32) * 0.5
+    shift = _randn(B, K, seed=54, dtype=torch.float32) * 0.3
+    scale = _randn(B, K, seed=55, dtype=torch.float32) * 0.3
+    w, bias = _randn(N, K, seed=56, scale=K ** -0.5), _randn(N, seed=57, scale=0.1)
+    a = torch.empty(M, K, dtype=torch.bfloat16, device=DEV)
+    stats = torch.empty(M, lib.LN_STAT_PARTS, 2, device=DEV)
+    lib.ln_prepare(x, scale, a, stats, mod_batch_stride=K, rows_per_batch=rpb)
+    u, v = _uv(w, bias, shift, scale)
+    out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV)
+    lib.gemm(a, w, None, out, epilogue=lib.EPI_LN_BIAS_GELU if gelu else lib.EPI_LN_BIAS, rows_per_batch=rpb, cta_pair=pair,
+             ln_stats=stats, ln_u=u.contiguous(), ln_v=v.contiguous(), ln_uv_batch_stride=N, ln_dim=K, ln_eps=1e-6)
+    want = _ln_reference(x, shift, scale, w, bias, rpb, gelu)
+    assert torch.isfinite(out.float()).all()
+    assert po.rel_err(out.float(), want) < 4e-3
+
+
+@pytest.mark.parametrize("K,pair,res_epi", [(1152, 1, 0), (1152, 2, 2), (4608, 0, 0), (4608, 2, 2), (4608, 2, 1)])
+def test_gemm_residual_epilogue_scaled_aux_and_row_stats(K, pair, res_epi):
+    """The fp32 residual epilogue as the PRODUCER of the fused LayerNorm: x_new = x + gate (a W^T + b) (checked as before),
+    out_aux = bf16(x_new * aux_scale_b), row_stats_out = per-column-tile partial (sum, sum of squares) of x_new.
+    res_epi 1 = the register-staged epilogue of the CTA-pair kernel (no by-products): result only."""
+    B, rpb, N = 3, 1000, 1152
+    M = B * rpb
+    a, w, bias = _randn(M, K, seed=60), _randn(N, K, seed=61, scale=K ** -0.5), _randn(N, seed=62, scale=0.1)
+    x = _randn(M, N, seed=63, dtype=torch.float32)
+    gate = _randn(B, 6, N, seed=64, dtype=torch.float32)
+    asc = 1 + _randn(B, 2, N, seed=65, dtype=torch.float32) * 0.3
+    want = x + gate[:, 2].repeat_interleave(rpb, 0) * F.linear(a.float(), w.float(), bias.float())
+    byp = res_epi != 1
+    aux = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV) if byp else None
+    stats = torch.full((M, lib.LN_STAT_PARTS, 2), float("nan"), device=DEV) if byp else None
+    lib.gemm(a, w, bias, x, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x, gate=gate[:, 2], gate_batch_stride=6 * N,
+             rows_per_batch=rpb, cta_pair=pair, res_epilogue=res_epi, out_aux=aux, aux_scale=asc[:, 1] if byp else None,
+             aux_scale_batch_stride=2 * N, row_stats_out=stats)
+    assert po.rel_err(x, want) < 2e-4
+    if byp:
+        assert po.rel_err(aux.float(), want * asc[:, 1].repeat_interleave(rpb, 0)) < 4e-3
+        assert torch.isfinite(stats).all()
+        assert po.rel_err(stats.sum(1)[:, 0], want.sum(1)) < 1e-3           # sums of ~N(0,1) values: absolute error ~1e-4
+        assert po.rel_err(stats.sum(1)[:, 1], (want * want).sum(1)) < 1e-4
+
+
+def test_fused_ln_chain_producer_to_consumer():
+    """Producer epilogue -> consumer epilogue end to end: (x + a W1^T) normalised, modulated and projected by W2 without a
+    stand-alone LayerNorm pass, against the fp32 computation of the same two layers."""
+    B, rpb, C, N2 = 2, 1024, 1152, 4608
+    M = B * rpb
+    a, w1, b1 = _randn(M, C, seed=70), _randn(C, C, seed=71, scale=C ** -0.5), _randn(C, seed=72, scale=0.1)
+    w2, b2 = _randn(N2, C, seed=73, scale=C ** -0.5), _randn(N2, seed=74, scale=0.1)
+    x = _randn(M, C, seed=75, dtype=torch.float32) + 0.4
+    shift, scale = _randn(B, C, seed=76, dtype=torch.float32) * 0.3, _randn(B, C, seed=77, dtype=torch.float32) * 0.3
+    x_new = x + F.linear(a.float(), w1.float(), b1.float())
+    want = _ln_reference(x_new, shift, scale, w2, b2, rpb, True)
+    xs = torch.empty(M, C, dtype=torch.bfloat16, device=DEV)
+    stats = torch.empty(M, lib.LN_STAT_PARTS, 2, device=DEV)
+    lib.gemm(a, w1, b1, x, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x, rows_per_batch=rpb, out_aux=xs,
+             aux_scale=(1 + scale).contiguous(), aux_scale_batch_stride=C, row_stats_out=stats)
+    u, v = _uv(w2, b2, shift, scale)
+    out = torch.empty(M, N2, dtype=torch.bfloat16, device=DEV)
+    lib.gemm(xs, w2, None, out, epilogue=lib.EPI_LN_BIAS_GELU, rows_per_batch=rpb, ln_stats=stats, ln_u=u.contiguous(),
+             ln_v=v.contiguous(), ln_uv_batch_stride=N2, ln_dim=C)
+    assert po.rel_err(x, x_new) < 2e-4
+    assert po.rel_err(out.float(), want) < 5e-3
+
+
+def test_layernorm_affine_inplace_on_qkv_slices():
+    """qk_norm (PixArt_blocks.py:133-134): LayerNorm(C, affine, eps 1e-5) on the q and k column slices of the qkv buffer."""
+    M, Cc = 777, 1152
+    qkv = _randn(M, 3 * Cc, seed=80) * 2
+    w, b = (1 + _randn(Cc, seed=81, scale=0.1).float()).to(torch.bfloat16), _randn(Cc, seed=82, scale=0.1)
+    want_q = F.layer_norm(qkv[:, :Cc].float(), (Cc,), w.float(), b.float(), eps=1e-5)
+    v_before = qkv[:, 2 * Cc:].clone()
+    lib.layernorm_affine_(qkv[:, :Cc], w, b, eps=1e-5)
+    assert po.rel_err(qkv[:, :Cc].float(), want_q) < 4e-3
+    assert torch.equal(qkv[:, 2 * Cc:], v_before)
+
+
 # ------------------------------------------------------------------------------------------------- attention
 def _attn_ref(q, k, v, lens):
     """oracle sdpa per sample on fp32 copies; q (B,Nq,H,72), k/v (B,Nk,H,72); lens = valid keys per sample."""
