@@ -1,22 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- denoise-steps/sec of the PixArt-Sigma-XL/2 denoiser hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4|c5] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4|c5] [--impl ours|reference] [--no-extras]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-A *step* is one pass of the hot path over one batch: one `PixArtMS.forward` of the CFG-batched latents of the
-images a GPU holds (workload c3: 4 images/GPU at 1024px -> forward batch 8, 4096 tokens/sample), i.e. one DPM-Solver
-model evaluation.  `value` = image-denoise-steps per second over all ranks (an image-step = one forward at batch 2,
-reference diffusion/model/dpm_solver.py:328-331), inputs resident in HBM, CUDA-event timed, max over ranks.
-`e2e` is the same metric through the public API with pinned HOST inputs copied H2D and the eps result copied D2H
-inside every timed step.  Weak scaling: per-GPU work is fixed, ranks are independent replicas (no collective in the
-data path).  The working set per step (1.2 GB of weights + >1 GB of activations) is far larger than
-the 126 MB L2, so no explicit L2 flush is needed between iterations.
+Headline (`value`, workload c3 = BASELINE configs[2]'s per-GPU slice): a *step* is one pass of the hot path over one batch --
+one `PixArtMS.forward` of the CFG-batched latents of the images a GPU holds (4 images/GPU at 1024px -> forward batch 8,
+4096 tokens/sample), i.e. one DPM-Solver model evaluation.  `value` = image-denoise-steps per second over all ranks (an
+image-step = one forward at batch 2, reference diffusion/model/dpm_solver.py:328-331), inputs resident in HBM, CUDA-event
+timed, max over ranks.  `e2e` is the same metric through the public API with pinned HOST inputs copied H2D and the eps result
+copied D2H inside every timed step.  Weak scaling: per-GPU work is fixed, ranks are independent replicas (no collective in
+the data path).  The working set per step (1.2 GB of weights + >1 GB of activations) is far larger than the
+126 MB L2, so no explicit L2 flush is needed between iterations.
 
-`--workload c5` (BASELINE configs[4]) times the TRAINING step instead: IDDPM loss forward + backward through the
-forward/backward kernels with per-block activation checkpointing + the bucketed gradient all-reduce (NCCL) overlapped
-with the backward, 1024px, 4 images per GPU, fp32 master weights; `value` = trained images per second over all ranks.
+Nothing but the forward runs inside the timed region of `value`: the per-kernel CUDA events behind `roofline` are taken in a
+SEPARATE pass afterwards, and after the timed regions rank 0 checks what it timed -- `parity` = rel. error of one
+PixArtMSBlock at the benchmarked geometry (and, at N = 1, of the whole 28-block forward of one image) against the oracle
+evaluated on the host.
+
+The same invocation also puts BASELINE configs[4] (training step: IDDPM loss fwd + bwd + DDP gradient all-reduce, key
+`train`) and configs[3] (2K, KV-compress sr=2, key `c4`) under the same clock at the same N (skip with --no-extras), so that
+the scaling harness sees the NCCL gradient all-reduce too.
 
 One JSON line is printed by rank 0.
 """
@@ -36,19 +41,18 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 C, L, HEADS, DEPTH = 1152, 300, 16, 28
+CPU_THREADS = 32            # fixed: torch CPU GEMMs of this size stop scaling long before the box's core count
 WORKLOADS = {
     # name: (description, latent side, images per GPU, pe_interpolation, kv-compress)
-    "c2": ("PixArt-Sigma-XL/2 512px, 4 images/GPU (forward batch 8, CFG pairs), 1024 tokens", 64, 4, 1.0, False),
-    "c3": ("PixArt-Sigma-XL/2 1024-MS, 4 images/GPU (forward batch 8, CFG pairs), 4096 tokens "
+    "c2": ("c2: PixArt-Sigma-XL/2 512px, 4 images/GPU (forward batch 8, CFG pairs), 1024 tokens", 64, 4, 1.0, False),
+    "c3": ("c3: PixArt-Sigma-XL/2 1024-MS, 4 images/GPU (forward batch 8, CFG pairs), 4096 tokens "
            "[BASELINE configs[2]: batch 32 sharded over 8 GPUs]", 128, 4, 2.0, False),
-    "c4": ("PixArt-Sigma-XL/2 2K-MS kv-compress sr=2 layers 14-27, 1 image/GPU (forward batch 2), 16384 tokens",
-           256, 1, 4.0, True),
+    "c4": ("c4: PixArt-Sigma-XL/2 2K-MS kv-compress sr=2 layers 14-27, 1 image/GPU (forward batch 2), 16384 tokens "
+           "[BASELINE configs[3]]", 256, 1, 4.0, True),
+    "c5": ("c5: PixArt-Sigma-XL/2 1024-MS training step: IDDPM loss fwd + bwd (per-block activation checkpointing) + "
+           "bucketed gradient all-reduce, 4 images/GPU, 4096 tokens, fp32 master weights / bf16 kernels "
+           "[BASELINE configs[4]]", 128, 4, 2.0, False),
 }
-
-
-TRAIN_WORKLOAD = ("PixArt-Sigma-XL/2 1024-MS training step: IDDPM loss fwd + bwd (per-block activation checkpointing) + "
-                  "bucketed gradient all-reduce, 4 images/GPU, 4096 tokens, fp32 master weights / bf16 kernels "
-                  "[BASELINE configs[4]]", 128, 4, 2.0, False)
 
 
 def flops_per_forward(n_tok: int, batch: int, kv_compress: bool):
@@ -115,39 +119,86 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(rows), "reasons": sorted(reasons)}
 
 
-# --------------------------------------------------------------------------------------------- CPU arms (oracle)
-def cpu_reference_sample(side: int, pe: float, kv: bool, threads: int):
-    """Time the oracle port of the reference forward (fp32, CPU) on a bounded sample of the workload: forward batch 2
-    (= one image with CFG) through a 2-block and a 6-block slice of the 28-block model; per-block time = (t6-t2)/4,
-    fixed (embedders + final layer) = t2 - 2*per-block, full forward = fixed + 28*per-block.  Returns
-    (image-steps/s, seconds of CPU work measured)."""
-    from oracle import pixart_oracle as po            # bench.py may use the oracle ONLY here (cpu baseline arm)
-    torch.set_num_threads(threads)
+# --------------------------------------------------------------------------------------------- distributed context
+class Ctx:
+    def __init__(self, gpus: int):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank, self.world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world == 1 and gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
 
-    def run(depth):
-        layers = list(range(depth // 2, depth)) if kv else []
-        cfg = po.OracleConfig(depth=depth, input_size=side, pe_interpolation=pe, kv_sampling="conv" if kv else None,
-                              kv_scale_factor=2 if kv else 1, kv_compress_layer=layers)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, steps: int) -> float:
+        """EXACTLY `steps` calls between two CUDA events, barrier + synchronize on both sides, max over ranks (ms)."""
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            tt = torch.tensor([ms], device=self.dev)
+            self.dist.all_reduce(tt, op=self.dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------- CPU arm (oracle)
+def _oracle_cfg(po, side, pe, kv, depth=DEPTH):
+    layers = list(range(14, 28)) if kv else []
+    return po.OracleConfig(depth=depth, input_size=side, pe_interpolation=pe, kv_sampling="conv" if kv else None,
+                           kv_scale_factor=2 if kv else 1, kv_compress_layer=layers)
+
+
+def cpu_reference_forward(side: int, pe: float, kv: bool, sd=None, inputs=None, reps: int = 1):
+    """ONE REAL timed forward of the oracle port of the reference `PixArtMS.forward` (fp32, torch CPU, CPU_THREADS threads)
+    at the workload's resolution: forward batch 2 = one image with CFG, all 28 blocks.  With `sd` / `inputs`
+    it runs on the benchmarked model's own (bf16-valued) weights and inputs so that its output doubles as the parity
+    reference of the GPU forward.  Returns (image-steps/s, seconds per forward, output)."""
+    from oracle import pixart_oracle as po            # bench.py may use the oracle ONLY in the CPU arms / parity check
+    torch.set_num_threads(min(os.cpu_count() or 1, CPU_THREADS))
+    cfg = _oracle_cfg(po, side, pe, kv)
+    if sd is None:
         sd = po.synthetic_state_dict(cfg, seed=0)
+    if inputs is None:
         x, t, y, mask = po.synthetic_inputs(cfg, 2, (side, side), lens=[300, 300])
-        po.forward(sd, po.OracleConfig(depth=0, input_size=side, pe_interpolation=pe), x, t, y, mask=mask)  # warm-up
-        t0 = time.perf_counter()
-        po.forward(sd, cfg, x, t, y, mask=mask)
-        return time.perf_counter() - t0
+    else:
+        x, t, y, mask = inputs
+    with torch.no_grad():
+        po.forward(sd, _oracle_cfg(po, side, pe, kv, depth=0), x, t, y, mask=mask)      # warm-up: embedders, thread pool
+        times, out = [], None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            out = po.forward(sd, cfg, x, t, y, mask=mask)
+            times.append(time.perf_counter() - t0)
+    sec = statistics.median(times)
+    return 1.0 / sec, sec, out
 
-    t2, t6 = run(2), run(6)
-    per_block = max((t6 - t2) / 4.0, 1e-9)
-    fixed = max(t2 - 2.0 * per_block, 0.0)
-    return 1.0 / (fixed + DEPTH * per_block), t2 + t6
 
-
-def cpu_reference_train_sample(side: int, pe: float, threads: int):
-    """Training counterpart of `cpu_reference_sample` (workload c5): the oracle port of the reference forward with autograd
-    + the IDDPM loss + backward (fp32, CPU), ONE image, through a 1-block and a 3-block slice of the 28-block model;
-    per-block time = (t3 - t1) / 2, fixed = t1 - per-block, full step = fixed + 28 x per-block.  Returns (images/s, seconds)."""
-    from oracle import pixart_oracle as po            # bench.py may use the oracle ONLY in the cpu baseline / reference arms
+def cpu_reference_train_sample(side: int, pe: float):
+    """Training counterpart (workload c5): the oracle port of the reference forward with autograd + the IDDPM loss +
+    backward (fp32, CPU), ONE image, through a 1-block and a 3-block slice of the 28-block model; per-block time =
+    (t3 - t1) / 2, fixed = t1 - per-block, full step = fixed + 28 x per-block (a full fwd + bwd of one image would take
+    minutes).  Returns (images/s, seconds measured)."""
+    from oracle import pixart_oracle as po
     from pixart_sigma_b200.training import IDDPMLoss
-    torch.set_num_threads(threads)
+    torch.set_num_threads(min(os.cpu_count() or 1, CPU_THREADS))
 
     def run(depth):
         cfg = po.OracleConfig(depth=depth, input_size=side, pe_interpolation=pe)
@@ -167,107 +218,103 @@ def cpu_reference_train_sample(side: int, pe: float, threads: int):
     return 1.0 / (fixed + DEPTH * per_block), t1 + t3
 
 
-def pick_cpu_threads() -> int:
-    """torch CPU GEMMs of this size stop scaling (and regress) long before 128 threads: calibrate on a 1024x1152x4608
-    fp32 matmul and keep the fastest of {all cores, 64, 32, 16}."""
-    cores = os.cpu_count() or 1
-    a, b = torch.randn(1024, 1152), torch.randn(1152, 4608)
-    best, best_t = cores, None
-    for n in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16)}, reverse=True):
-        torch.set_num_threads(n)
-        a @ b
-        t0 = time.perf_counter()
-        for _ in range(5):
-            a @ b
-        dt = time.perf_counter() - t0
-        if best_t is None or dt < best_t:
-            best, best_t = n, dt
-    return best
-
-
 def run_reference_arm(args, wl):
+    """`--impl reference`: the reference's own CPU path (its oracle port: the reference is pure Python and cannot travel),
+    same workload string / metric / unit as our arm; every step is one REAL forward of one image (forward batch 2)."""
     desc, side, imgs, pe, kv = wl
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    threads = pick_cpu_threads()
+    threads = min(os.cpu_count() or 1, CPU_THREADS)
     train = args.workload == "c5"
-    sample_fn = (lambda: cpu_reference_train_sample(side, pe, threads)) if train else (lambda: cpu_reference_sample(side, pe, kv, threads))
-    for _ in range(max(args.warmup, 0) and 1):
-        sample_fn()
-    vals, t_all = [], 0.0
-    for _ in range(max(1, min(args.steps, 3))):
-        v, dt = sample_fn()
-        vals.append(v); t_all += dt
-    value = statistics.median(vals)
+    timed = max(1, min(args.steps, 3))
     if train:
-        sample = (f"oracle port of the reference training step (PixArtMS.forward with autograd + IDDPM loss + backward, fp32, torch "
-                  f"CPU, {threads} threads) at {side * 8}px, ONE image: 1-block and 3-block slices timed, full 28-block step = "
-                  f"fixed + 28 x per-block; median of {len(vals)} samples, {t_all:.1f} s of CPU work")
+        vals = [cpu_reference_train_sample(side, pe) for _ in range(timed)]
+        value, sec = statistics.median(v for v, _ in vals), sum(s for _, s in vals)
+        sample = (f"oracle port of the reference training step (forward with autograd + IDDPM loss + backward, fp32 torch CPU, "
+                  f"{threads} threads), {side * 8}px, one image: 1- and 3-block slices timed, full step = fixed + 28 x "
+                  f"per-block; median of {timed}, {sec:.1f} s of CPU work")
     else:
-        sample = (f"oracle port of the reference PixArtMS.forward (fp32, torch CPU, {threads} threads) at {side * 8}px, forward "
-                  f"batch 2 (one image with CFG): 2-block and 6-block slices timed, full 28-block forward = fixed + 28 x "
-                  f"per-block; median of {len(vals)} samples, {t_all:.1f} s of CPU work")
-    line = {"impl": "reference", "metric": "train-images/sec" if train else "denoise-steps/sec", "value": value,
-            "unit": "images/s" if train else "image-steps/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value,
+        value, sec, _ = cpu_reference_forward(side, pe, kv, reps=timed)
+        sample = (f"oracle port of the reference PixArtMS.forward (fp32, torch CPU, {threads} threads), {side * 8}px: {timed} "
+                  f"REAL full forward(s) of one image with CFG (forward batch 2, 28 blocks), median {sec:.2f} s each")
+    unit = "images/s" if train else "image-steps/s"
+    line = {"impl": "reference", "metric": "train-images/sec" if train else "denoise-steps/sec", "value": value, "unit": unit,
+            "n_gpus": args.gpus, "steps": timed, "warmup": 1, "steps_requested": args.steps, "ms_per_step": 1000.0 / value,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "note": "reference is pure Python; its CPU path timed via the oracle port "
-                       "(the reference itself cannot travel to the GPU box)"},
-            "cpu_baseline": {"value": value, "unit": "images/s" if train else "image-steps/s", "cores": threads, "kind": "port",
-                             "sample": sample},
-            "e2e": {"value": value, "unit": "images/s" if train else "image-steps/s", "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": 0},
+            "config": {"workload": desc, "note": "reference is pure Python; its CPU path timed via the oracle port (the "
+                       "reference itself cannot travel to the GPU box); per-image throughput of one host, not scaled by n_gpus"},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     _emit(line)
 
 
-# --------------------------------------------------------------------------------------------- our arm
+# --------------------------------------------------------------------------------------------- our arm: inference
 class KernelTimer:
-    """CUDA-event timing of every GEMM / attention launch on the launching stream, inside the timed region."""
+    """CUDA-event timing of every GEMM / attention launch on the launching stream (the separate roofline pass)."""
 
-    def __init__(self, lib):
-        self.lib, self.recs, self.on = lib, {"gemm": [], "attn": []}, False
-        self._g, self._a = lib.gemm, lib.flash_attn
+    def __init__(self, lib, names):
+        self.lib, self.on = lib, False
+        self.recs = {k: [] for k, _ in names}
+        self._orig = {}
+        for kind, fn_name in names:
+            self._orig[fn_name] = getattr(lib, fn_name)
+            setattr(lib, fn_name, self._make(kind, self._orig[fn_name]))
 
-    def install(self):
-        def g(*a, **k):
-            return self._wrap("gemm", self._g, a, k)
+    def _make(self, kind, fn):
+        def wrapped(*a, **k):
+            if not self.on:
+                return fn(*a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            self.recs[kind].append((e0, e1))
+            return r
+        return wrapped
 
-        def f(*a, **k):
-            return self._wrap("attn", self._a, a, k)
-        self.lib.gemm, self.lib.flash_attn = g, f
-
-    def _wrap(self, kind, fn, a, k):
-        if not self.on:
-            return fn(*a, **k)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        r = fn(*a, **k)
-        e1.record()
-        self.recs[kind].append((e0, e1))
-        return r
+    def restore(self):
+        for name, fn in self._orig.items():
+            setattr(self.lib, name, fn)
 
     def totals_ms(self):
         return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in self.recs.items()}
 
 
-def run_ours(args, wl, wl_name):
-    import torch.distributed as dist
+def _block_parity(model, B, side, lens_cfg, dev):
+    """One PixArtMSBlock of the benchmarked model at the benchmarked geometry (fused path, the kernels the timed region
+    ran) against the oracle block on the host, on seeded inputs.  Returns the normwise rel. error of the block output."""
+    from oracle import pixart_oracle as po
+    from pixart_sigma_b200.model import _LnFusion, _ln_ctx, _LN_FUSE_MIN_ROWS
+    blk = model.blocks[0]
+    hw = (side // 2, side // 2)
+    N = hw[0] * hw[1]
+    sr = blk.attn.sr_ratio
+    g = torch.Generator().manual_seed(2024)
+    x = torch.randn(B, N, C, generator=g)
+    t0 = torch.randn(B, 6 * C, generator=g) * 0.3
+    lens = [int(v) for v in lens_cfg]
+    ycat = torch.randn(sum(lens), C, generator=g).to(torch.bfloat16)
+    sd = {"blocks.0." + k: v.detach().float().cpu() for k, v in blk.state_dict().items()}
+    mod = (sd["blocks.0.scale_shift_table"][None] + t0.view(B, 6, C)).to(dev).contiguous()
+    kv_len = torch.tensor(lens, dtype=torch.int32, device=dev)
+    kv_off = torch.tensor([sum(lens[:i]) for i in range(B)], dtype=torch.int32, device=dev)
+    ln = None
+    if model.fuse_ln_modulate and N >= _LN_FUSE_MIN_ROWS:
+        u, v, one_plus = _LnFusion([blk]).prepare(t0.view(B, 6, C).to(dev), mod[None], blk._ws)
+        ln = _ln_ctx(u, v, one_plus, 0, torch.empty(B * N, 8, 2, device=dev))
+    with torch.no_grad():
+        got = blk.run_kernels(x.reshape(B * N, C).to(dev).contiguous(), ycat.to(dev), kv_len, kv_off, max(lens), mod, B, N, hw,
+                              blk._ws, ln).view(B, N, C).cpu()
+        torch.set_num_threads(min(os.cpu_count() or 1, 64))
+        want = po.block_forward(sd, "blocks.0", x, ycat.float()[None], t0, lens, hw, HEADS, sr, blk.attn.sampling if sr > 1 else None)
+    return po.rel_err(got, want), po.rel_err(got - x, want - x)
+
+
+def measure_inference(args, ctx: Ctx, wl_name: str, headline: bool):
     from pixart_sigma_b200 import PixArtMS_XL_2, lib
-
-    desc, side, imgs, pe, kv = wl
-    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    lib.load()
-
+    desc, side, imgs, pe, kv = WORKLOADS[wl_name]
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
     torch.manual_seed(1234 + rank)
     kvc = dict(sampling="conv", scale_factor=2, kv_compress_layer=list(range(14, 28))) if kv else None
     with torch.device(dev):
@@ -309,59 +356,39 @@ def run_ours(args, wl, wl_name):
         h_out.copy_(eps, non_blocking=True)
         return eps
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn(i)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            tt = torch.tensor([ms], device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ms = float(tt.item())
-        return ms
-
-    timer = KernelTimer(lib)
-    timer.install()
+    warm = max(args.warmup, 3)
     with torch.no_grad():
         n_pre = lib.launch_count()
         model.forward_with_dpmsolver(d_x, d_ts[0], d_y, None, mask=d_mask)          # eager: kernel launches of one forward
         launches_per_forward = lib.launch_count() - n_pre
-        for i in range(max(args.warmup, 3)):
+        for i in range(warm):
             step_resident(i)
         step_e2e(0)
-        sampler = ClockSampler(local) if rank == 0 else None
-        n0 = lib.launch_count()
-        timer.on = True
-        ms = timed(step_resident, args.steps)
-        timer.on = False
-        launches = lib.launch_count() - n0
-        if graphed is not None:
-            launches = launches_per_forward * args.steps       # graph replays bypass the library's host-side counter
-        ms_e2e = timed(step_e2e, args.steps)
+        sampler = ClockSampler(ctx.local) if rank == 0 else None
+        ms = ctx.timed(step_resident, args.steps)                                   # <- `value`: nothing else in here
+        ms_e2e = ctx.timed(step_e2e, args.steps)
         clocks = sampler.stop() if sampler else None
+        # ---- separate pass: per-kernel CUDA events for the roofline (2 steps; not part of value / e2e)
+        timer = KernelTimer(lib, [("gemm", "gemm"), ("attn", "flash_attn")])
+        timer.on = True
+        roof_steps = 2
+        ms_roof = ctx.timed(lambda i: model.forward_with_dpmsolver(d_x, d_ts[i % 20], d_y, None, mask=d_mask), roof_steps)
+        timer.on = False
+        timer.restore()
         loop = None
         if args.sampling_loop:
             # the caller of the path: a full 20-step DPM-Solver++ CFG sampling run of `imgs` images
-            # through pixart_sigma_b200.sampler (fused step kernel; whole loop as one CUDA graph with --cuda-graph)
             from pixart_sigma_b200.sampler import DPMS
             cond, null = d_y[imgs:], d_y[:imgs]
             solver = DPMS(model.forward_with_dpmsolver, condition=cond, uncondition=null, cfg_scale=4.5,
                           model_kwargs=dict(data_info=None, mask=d_mask))
             z = d_x[:imgs].float()
             solver.sample(z, steps=20, cuda_graph=args.cuda_graph)                 # warm-up (and graph capture)
-            ms_loop = timed(lambda i: solver.sample(z, steps=20, cuda_graph=args.cuda_graph), 1)
+            ms_loop = ctx.timed(lambda i: solver.sample(z, steps=20, cuda_graph=args.cuda_graph), 1)
             loop = {"steps": 20, "images": imgs * world, "ms": ms_loop, "images_per_s": imgs * world / (ms_loop / 1000.0),
                     "denoise_steps_per_s": imgs * world * 20 / (ms_loop / 1000.0), "cuda_graph": bool(args.cuda_graph)}
 
+    line = None
     if rank == 0:
         tot, f_gemm, f_attn = flops_per_forward(n_tok, B, kv)
         ms_step = ms / args.steps
@@ -371,74 +398,93 @@ def run_ours(args, wl, wl_name):
         tt = timer.totals_ms()
         gemm_ms, gemm_n = tt["gemm"]
         attn_ms, attn_n = tt["attn"]
-        gemm_tf = f_gemm * args.steps / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else None
-        attn_tf = f_attn * args.steps / (attn_ms / 1000.0) / 1e12 if attn_ms > 0 else None
-        traffic = None
+        gemm_tf = f_gemm * roof_steps / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else None
+        attn_tf = f_attn * roof_steps / (attn_ms / 1000.0) / 1e12 if attn_ms > 0 else None
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "latest_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("gemm_dram_bytes_per_launch")
-        roof = {"bound": "tensor", "kernel": "pxa::gemm_bf16_kernel (all 7 GEMMs of the block; %.0f%% of the FLOPs)"
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj.get("gemm_dram_bytes_per_launch"), tj.get("source")
+        roof = {"bound": "tensor", "kernel": "pxa::gemm_bf16_kernel / gemm2_bf16_kernel (all GEMMs of the block; %.0f%% of the FLOPs)"
                 % (100.0 * f_gemm / tot),
                 "achieved": gemm_tf, "peak": sus, "unit": "TFLOP/s", "frac": (gemm_tf / sus) if gemm_tf else None,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src})", "traffic": traffic,
+                "traffic_source": traffic_src,
+                "timing": f"CUDA events around every launch in a separate {roof_steps}-step pass after the timed regions "
+                          f"({ms_roof / roof_steps:.2f} ms/step with the events)",
                 "launches_timed": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
-                "flops_per_launch_avg": f_gemm * args.steps / max(gemm_n, 1),
-                "step_share": gemm_ms / ms if ms > 0 else None,
+                "flops_per_launch_avg": f_gemm * roof_steps / max(gemm_n, 1),
+                "step_share": gemm_ms / ms_roof if ms_roof > 0 else None,
                 "attention": {"kernel": "pxa::flash_attn_d72_kernel", "achieved": attn_tf, "frac": (attn_tf / sus) if attn_tf else None,
-                              "launches_timed": attn_n, "step_share": attn_ms / ms if ms > 0 else None},
+                              "launches_timed": attn_n, "step_share": attn_ms / ms_roof if ms_roof > 0 else None},
                 "whole_step": {"achieved": tot / (ms_step / 1000.0) / 1e12, "frac": tot / (ms_step / 1000.0) / 1e12 / sus}}
+        # ---- what was timed is checked: one block at the benchmarked geometry vs the oracle on the host
+        parity = None
+        if not args.no_parity:
+            blk_lens = torch.cat([lens, lens]).tolist()
+            e_blk, e_upd = _block_parity(model, B, side, blk_lens, dev)
+            parity = {"block_rel_err": e_blk, "block_update_rel_err": e_upd,
+                      "block": f"PixArtMSBlock 0 of the benchmarked model, B={B}, {n_tok} tokens, caption lengths {blk_lens}, vs "
+                               "oracle.block_forward (fp32, host) on the same bf16-valued weights", "bar": 1e-3 if not kv else 1.5e-3}
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            threads = pick_cpu_threads()
-            v, dt = cpu_reference_sample(side, pe, kv, threads)
-            cpu = {"value": v, "unit": "image-steps/s", "cores": threads, "kind": "port",
-                   "sample": f"oracle port of the reference forward, fp32 torch CPU, {side * 8}px, forward batch 2: 2- and "
-                             f"6-block slices timed ({dt:.1f} s), full forward = fixed + 28 x per-block"}
+        if world == 1 and not args.no_cpu_baseline and headline:
+            # one REAL forward of the reference port on this box's cores, on the benchmarked model's weights and the first
+            # image's inputs; its output is also the parity reference of the whole GPU forward
+            sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+            t_in = torch.full((2,), tgrid[0])
+            xin, yin = torch.cat([h_x[:1], h_x[imgs:imgs + 1]]), torch.cat([h_y[:1], h_y[imgs:imgs + 1]]).float()
+            v, sec, want = cpu_reference_forward(side, pe, kv, sd=sd, inputs=(xin.to(torch.bfloat16).float(), t_in, yin, h_mask[:1]))
+            cpu = {"value": v, "unit": "image-steps/s", "cores": min(os.cpu_count() or 1, CPU_THREADS), "kind": "port",
+                   "sample": f"oracle port of the reference PixArtMS.forward, fp32 torch CPU, {side * 8}px: ONE real full forward "
+                             f"of one image with CFG (forward batch 2, 28 blocks) in {sec:.2f} s"}
+            if parity is not None:
+                from oracle import pixart_oracle as po
+                model.output_dtype = torch.float32
+                with torch.no_grad():
+                    got = model(xin.to(dev), t_in.to(dev), yin.to(dev).to(torch.bfloat16), mask=h_mask[:1].to(dev)).cpu()
+                model.output_dtype = None
+                parity["forward_rel_err"] = po.rel_err(got, want)
+                parity["forward"] = "whole 28-block forward of image 0 (forward batch 2) vs the oracle forward above; bar 1e-2"
         h2d = h_x.numel() * 4 + h_y.numel() * 2 + h_mask.numel() * 8 + h_t.numel() * 4
+        launches = launches_per_forward * args.steps
         line = {"metric": "denoise-steps/sec", "value": value, "unit": "image-steps/s", "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "steps": args.steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": f"{wl_name}: {desc}", "images_per_gpu": imgs, "forward_batch_per_gpu": B,
+                "config": {"workload": desc, "images_per_gpu": imgs, "forward_batch_per_gpu": B,
                            "tokens_per_sample": n_tok, "text_tokens": L, "parallelism": f"dp{world} (batch-sharded replicas)",
                            "l2": "inputs larger than L2 (weights 1.2 GB + activations per step); no flush needed",
-                           "cuda_graph": bool(args.cuda_graph),
+                           "cuda_graph": bool(args.cuda_graph), "fused_ln_modulate": bool(model.fuse_ln_modulate),
                            "tflop_per_step_per_gpu": tot / 1e12},
                 "e2e": {"value": e2e_v, "unit": "image-steps/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h_out.numel() * 2},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity}
         if loop is not None:
             line["sampling_loop"] = loop
-        _emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    del model
+    torch.cuda.empty_cache()
+    return line
 
 
-def run_train(args, wl):
-    """BASELINE configs[4]: one training step = zero_grad + IDDPM loss forward + backward + gradient all-reduce."""
-    import torch.distributed as dist
+# --------------------------------------------------------------------------------------------- our arm: training step
+def measure_train(args, ctx: Ctx, mode: str, checkpoint: bool, cpu_baseline: bool):
+    """BASELINE configs[4]: one training step = zero_grad + IDDPM loss forward + backward + gradient all-reduce.
+    mode: 'eager' (bucket all-reduces overlap the backward), 'graph' (whole step replayed from one CUDA graph, all-reduce
+    after the replay), 'graph-overlap' (collectives captured inside the graph)."""
     from pixart_sigma_b200 import build_model, lib
     from pixart_sigma_b200.parallel import GradBucketReducer
-    from pixart_sigma_b200.training import IDDPMLoss, train_step
+    from pixart_sigma_b200.training import GraphedTrainStep, IDDPMLoss, train_step
 
-    desc, side, imgs, pe, _ = wl
-    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world == 1 and args.gpus > 1:
-        raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    lib.load()
+    desc, side, imgs, pe, _ = WORKLOADS["c5"]
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
     torch.manual_seed(1234)                                   # same initial weights on every rank (DDP replicas)
     with torch.device(dev):
         model = build_model(dict(type="PixArtMS_XL_2", input_size=side, pe_interpolation=pe, model_max_length=L),
-                            use_grad_checkpoint=not args.no_checkpoint)
+                            use_grad_checkpoint=checkpoint)
         for blk in model.blocks:
             torch.nn.init.normal_(blk.cross_attn.proj.weight, std=0.02)
         torch.nn.init.normal_(model.final_layer.linear.weight, std=0.02)
     model = model.float().train()
-    reducer = GradBucketReducer(model)
+    reducer = GradBucketReducer(model, compress="bf16" if args.bf16_reduce else None)
     loss_fn = IDDPMLoss()
     n_tok = (side // 2) ** 2
     g = torch.Generator().manual_seed(7 + rank)
@@ -450,10 +496,14 @@ def run_train(args, wl):
     h_noise = torch.randn(imgs, 4, side, side, generator=g).pin_memory()
     d_x, d_y, d_mask, d_t, d_noise = (v.to(dev) for v in (h_x, h_y, h_mask, h_t, h_noise))
 
+    n_pre = lib.launch_count()
+    reducer.zero_grad()
+    train_step(model, loss_fn, d_x, d_t, d_y, d_mask, noise=d_noise, reducer=reducer)     # eager: kernel launches of one step
+    launches_eager = lib.launch_count() - n_pre
     graphed = None
-    if args.cuda_graph:
-        from pixart_sigma_b200.training import GraphedTrainStep
-        graphed = GraphedTrainStep(model, loss_fn, reducer, (d_x, d_t, d_y, d_mask, d_noise))
+    if mode != "eager":
+        graphed = GraphedTrainStep(model, loss_fn, reducer, (d_x, d_t, d_y, d_mask, d_noise),
+                                   capture_collectives=(mode == "graph-overlap"))
 
     def step_resident(i):
         if graphed is not None:
@@ -468,104 +518,84 @@ def run_train(args, wl):
         reducer.zero_grad()
         return float(train_step(model, loss_fn, x, t, y, mk, noise=nz, reducer=reducer))     # loss read back: D2H + sync
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    host_ms = {}
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        t_host = time.perf_counter()
-        for i in range(steps):
-            fn(i)
-        host_ms[fn.__name__] = (time.perf_counter() - t_host) * 1000.0 / steps     # host time to ENQUEUE a step (no sync)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            tt = torch.tensor([ms], device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ms = float(tt.item())
-        return ms
-
-    timer = KernelTimer(lib)
-    timer.recs["attn_bwd"] = []
-    timer.install()
-    _ab, _wg = lib.flash_attn_bwd, lib.gemm_wgrad
-    lib.flash_attn_bwd = lambda *a, **k: timer._wrap("attn_bwd", _ab, a, k)
-    lib.gemm_wgrad = lambda *a, **k: timer._wrap("gemm", _wg, a, k)
-    n_pre = lib.launch_count()
-    reducer.zero_grad()
-    train_step(model, loss_fn, d_x, d_t, d_y, d_mask, noise=d_noise, reducer=reducer)     # eager: kernel launches of one step
-    launches_eager = lib.launch_count() - n_pre
-    for i in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for i in range(warm):
         loss0 = step_resident(i)
     step_e2e(0)
-    sampler = ClockSampler(local) if rank == 0 else None
-    n0 = lib.launch_count()
-    timer.on = graphed is None                      # per-kernel events are not available inside a graph replay
-    ms = timed(step_resident, args.steps)
-    timer.on = False
-    launches = lib.launch_count() - n0
-    if graphed is not None:
-        launches = launches_eager * args.steps       # graph replays bypass the library's host-side counter
-    ms_e2e = timed(step_e2e, args.steps)
+    sampler = ClockSampler(ctx.local) if rank == 0 else None
+    t_host = time.perf_counter()
+    ms = ctx.timed(step_resident, args.steps)
+    host_total_ms = (time.perf_counter() - t_host) * 1000.0
+    ms_e2e = ctx.timed(step_e2e, args.steps)
     clocks = sampler.stop() if sampler else None
+    # exposed part of the gradient all-reduce: the same step with the collective switched off (world > 1 only)
+    exposed = None
+    if world > 1:
+        saved = reducer.world
+        reducer.world = 1
+        for i in range(2):
+            step_resident(i)
+        ms_nocomm = ctx.timed(step_resident, args.steps)
+        reducer.world = saved
+        exposed = {"ms_per_step_without_collective": ms_nocomm / args.steps,
+                   "exposed_allreduce_ms_per_step": (ms - ms_nocomm) / args.steps}
+    # separate pass: per-kernel CUDA events (eager mode only; not available inside a graph replay)
+    tt = None
+    if mode == "eager":
+        timer = KernelTimer(lib, [("gemm", "gemm"), ("gemm_wgrad", "gemm_wgrad"), ("attn", "flash_attn"), ("attn_bwd", "flash_attn_bwd")])
+        timer.on = True
+        ms_roof = ctx.timed(step_resident, 2)
+        timer.on = False
+        timer.restore()
+        tt = timer.totals_ms()
     peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+    line = None
     if rank == 0:
         fwd, f_gemm, f_attn = flops_per_forward(n_tok, imgs, False)
         sus, burst, hbm, src = measured_peaks()
         ms_step = ms / args.steps
-        tt = timer.totals_ms()
-        recompute = 0 if args.no_checkpoint else 1
-        gemm_flops = (3 + recompute) * f_gemm * args.steps            # fwd (+ recompute) + dgrad + wgrad
-        gemm_ms, gemm_n = tt["gemm"]
-        gemm_tf = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else None
-        afw_ms, afw_n = tt["attn"]
-        abw_ms, abw_n = tt["attn_bwd"]
-        afw_tf = f_attn * args.steps / (afw_ms / 1000.0) / 1e12 if afw_ms > 0 else None   # recomputation reuses (o, lse)
-        abw_tf = 3.5 * f_attn * args.steps / (abw_ms / 1000.0) / 1e12 if abw_ms > 0 else None     # 14 N Nk d executed (10 model)
         model_tf = 3 * fwd / (ms_step / 1000.0) / 1e12
-        roof = {"bound": "tensor", "kernel": "pxa::gemm_bf16_kernel (forward, recompute, dgrad and wgrad GEMMs)",
-                "achieved": gemm_tf, "peak": sus, "unit": "TFLOP/s", "frac": (gemm_tf / sus) if gemm_tf else None,
-                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src})", "traffic": None,
-                "launches_timed": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
-                "flops_per_launch_avg": gemm_flops / max(gemm_n, 1), "step_share": gemm_ms / ms,
-                "attention_fwd": {"kernel": "pxa::flash_attn_d72_kernel", "achieved": afw_tf, "frac": afw_tf / sus if afw_tf else None,
-                                  "launches_timed": afw_n, "step_share": afw_ms / ms},
-                "attention_bwd": {"kernel": "pxa::flash_attn_d72_bwd_kernel (dKV + dQ passes + delta)", "achieved": abw_tf,
-                                  "frac": abw_tf / sus if abw_tf else None, "launches_timed": abw_n, "step_share": abw_ms / ms,
-                                  "note": "executed FLOPs (14 N Nk d incl. the dQ-pass recomputation); model FLOPs are 10 N Nk d"},
-                "whole_step": {"model_tflops": model_tf, "frac": model_tf / sus,
-                               "note": "model FLOPs = 3 x forward (no recomputation counted)"}}
+        roof = {"bound": "tensor", "whole_step": {"model_tflops": model_tf, "frac": model_tf / sus,
+                                                   "note": "model FLOPs = 3 x forward (no recomputation counted)"},
+                "peak": sus, "unit": "TFLOP/s", "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src})"}
+        if tt is not None:
+            recompute = 1 if checkpoint else 0
+            gemm_ms = tt["gemm"][0] + tt["gemm_wgrad"][0]
+            gemm_tf = (3 + recompute) * f_gemm * 2 / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else None
+            afw_tf = f_attn * 2 / (tt["attn"][0] / 1000.0) / 1e12 if tt["attn"][0] > 0 else None      # recomputation reuses (o, lse)
+            abw_tf = 3.5 * f_attn * 2 / (tt["attn_bwd"][0] / 1000.0) / 1e12 if tt["attn_bwd"][0] > 0 else None
+            roof.update({"kernel": "pxa GEMM family (forward, recompute, dgrad and wgrad)", "achieved": gemm_tf,
+                         "frac": gemm_tf / sus if gemm_tf else None, "step_share": gemm_ms / ms_roof,
+                         "attention_fwd": {"achieved": afw_tf, "frac": afw_tf / sus if afw_tf else None, "step_share": tt["attn"][0] / ms_roof},
+                         "attention_bwd": {"achieved": abw_tf, "frac": abw_tf / sus if abw_tf else None,
+                                           "step_share": tt["attn_bwd"][0] / ms_roof,
+                                           "note": "executed FLOPs (14 N Nk d incl. the dQ-pass recomputation); model FLOPs are 10 N Nk d"}})
         h2d = h_x.numel() * 4 + h_y.numel() * 2 + h_mask.numel() * 2 + h_t.numel() * 8 + h_noise.numel() * 4
         line = {"metric": "train-images/sec", "value": imgs * world * args.steps / (ms / 1000.0), "unit": "images/s",
-                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+                "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": f"c5: {desc}", "images_per_gpu": imgs, "tokens_per_sample": n_tok, "text_tokens": L,
-                           "parallelism": f"ddp{world} (bucketed NCCL all-reduce of {reducer.grad_bytes() / 1e9:.2f} GB fp32 grads, "
-                                          f"{len(reducer.buckets)} buckets, overlapped with backward)",
-                           "grad_checkpointing": not args.no_checkpoint, "cuda_graph": bool(args.cuda_graph), "optimizer_step": "not included (fwd + bwd + all-reduce, as configs[4] states)",
+                "config": {"workload": desc, "images_per_gpu": imgs, "tokens_per_sample": n_tok, "text_tokens": L,
+                           "parallelism": f"ddp{world} (bucketed NCCL all-reduce of {reducer.grad_bytes() / 1e9:.2f} GB "
+                                          f"{'bf16' if args.bf16_reduce else 'fp32'} gradients per rank, {len(reducer.buckets)} buckets)",
+                           "step_mode": mode, "grad_checkpointing": checkpoint,
+                           "optimizer_step": "not included (fwd + bwd + all-reduce, as configs[4] states)",
                            "l2": "working set (2.4 GB fp32 weights + activations) larger than L2; no flush needed",
                            "tflop_model_per_step_per_gpu": 3 * fwd / 1e12, "peak_mem_gib": peak_mem, "loss": float(loss0),
-                           "host_enqueue_ms_per_step": host_ms.get("step_resident")},
+                           "host_ms_per_step": host_total_ms / args.steps},
                 "e2e": {"value": imgs * world * args.steps / (ms_e2e / 1000.0), "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": None}
-        if world == 1 and not args.no_cpu_baseline:
-            threads = pick_cpu_threads()
-            v, dt = cpu_reference_train_sample(side, pe, threads)
-            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
+                "gpu_launches": launches_eager * args.steps, "clocks": clocks, "roofline": roof, "allreduce": exposed,
+                "cpu_baseline": None}
+        if cpu_baseline:
+            v, dt = cpu_reference_train_sample(side, pe)
+            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": min(os.cpu_count() or 1, CPU_THREADS), "kind": "port",
                                     "sample": f"oracle port of the reference training step (forward with autograd + IDDPM loss + "
                                               f"backward, fp32 torch CPU), {side * 8}px, one image: 1- and 3-block slices timed "
                                               f"({dt:.1f} s), full step = fixed + 28 x per-block"}
-        _emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    reducer.remove()
+    del model, reducer, graphed
+    torch.cuda.empty_cache()
+    return line
 
 
 _JSON_FD = None
@@ -581,30 +611,54 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c5"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extras", action="store_true",
+                    help="headline workload only (default: the c3 line also carries the c5 training step under `train` and "
+                         "the c4 2K forward under `c4`, measured at the same N)")
+    ap.add_argument("--train-mode", default="auto", choices=["auto", "eager", "graph", "graph-overlap"],
+                    help="c5: how the step is issued; auto = one CUDA graph (all-reduce after the replay)")
     ap.add_argument("--no-checkpoint", action="store_true", help="c5: train without per-block activation checkpointing")
+    ap.add_argument("--bf16-reduce", action="store_true", help="c5: gradients travel as bf16 (1.22 GB instead of 2.44 GB)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-run oracle check of one block at the bench geometry")
     ap.add_argument("--sampling-loop", action="store_true",
                     help="also time one full 20-step DPM-Solver++ sampling run through pixart_sigma_b200.sampler "
                          "(extra key `sampling_loop`; not part of the timed region of `value` / `e2e`)")
     ap.add_argument("--cuda-graph", action="store_true",
-                    help="replay the resident-input forward as one CUDA graph (pixart_sigma_b200.graph.GraphedForward); "
-                         "per-kernel event timing (roofline) is unavailable in this mode")
+                    help="replay the resident-input forward as one CUDA graph (pixart_sigma_b200.graph.GraphedForward)")
     args = ap.parse_args()
-    wl = TRAIN_WORKLOAD if args.workload == "c5" else WORKLOADS[args.workload]
     # The contract is ONE JSON line on stdout.  Libraries write banners there too (NCCL prints its version line at the
     # first communicator init), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved fd.
     global _JSON_FD
     sys.stdout.flush()
     _JSON_FD = os.dup(1)
     os.dup2(2, 1)
-    if args.workload == "c5" and args.impl != "reference":
-        run_train(args, wl)
-    elif args.impl == "reference":
-        run_reference_arm(args, wl)
+    if args.impl == "reference":
+        run_reference_arm(args, WORKLOADS[args.workload])
+        return
+    from pixart_sigma_b200 import lib
+    ctx = Ctx(args.gpus)
+    lib.load()
+    train_mode = "graph" if args.train_mode == "auto" else args.train_mode
+    if args.workload == "c5":
+        line = measure_train(args, ctx, train_mode, not args.no_checkpoint, ctx.world == 1 and not args.no_cpu_baseline)
     else:
-        run_ours(args, wl, args.workload)
+        line = measure_inference(args, ctx, args.workload, headline=True)
+        if args.workload == "c3" and not args.no_extras:
+            sub = argparse.Namespace(**vars(args))
+            sub.no_cpu_baseline, sub.sampling_loop = True, False
+            tr = measure_train(sub, ctx, train_mode, not args.no_checkpoint, False)
+            sub.no_parity = True
+            c4 = measure_inference(sub, ctx, "c4", headline=False)
+            if ctx.rank == 0:
+                keep = ("metric", "value", "unit", "ms_per_step", "config", "e2e", "roofline", "allreduce", "clocks", "gpu_launches",
+                        "steps", "warmup")
+                line["train"] = {k: tr[k] for k in keep if k in tr}
+                line["c4"] = {k: c4[k] for k in keep if k in c4}
+    if ctx.rank == 0:
+        _emit(line)
+    ctx.close()
 
 
 if __name__ == "__main__":

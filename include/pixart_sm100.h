@@ -129,7 +129,8 @@ typedef struct PxaLnModArgs {
 int pxa_ln_modulate(const PxaLnModArgs* args, void* stream);
 
 /* First link of the fused LayerNorm-modulate chain (see PXA_EPI_LN_BIAS): for the residual stream x as the patch embedding
- * leaves it (PixArtMS.py:184), writes the A operand  a[r,:] = bf16( x[r,:] * (1 + scale[b,:]) )  and the row statistics
+ * leaves it (PixArtMS.py:184), writes the A operand  a[r,:] = bf16( x[r,:] * mult[b,:] ), mult = 1 + scale (the same
+ * multiplier PxaGemmArgs.aux_scale takes), and the row statistics
  * stats[r][0] = (sum_k x[r,k], sum_k x[r,k]^2), stats[r][1..7] = 0  that the QKV GEMM of block 0 consumes.  Later links
  * get both from the residual epilogues (PxaGemmArgs.aux_scale / row_stats_out).  HBM-bound: one read of x, one bf16 write.
  */
@@ -137,7 +138,7 @@ typedef struct PxaLnPrepareArgs {
   const float* x;       /* fp32 [M, C] row stride ldx                 */
   void* a_out;          /* bf16 [M, C] contiguous                     */
   float* stats_out;     /* fp32 [M][PXA_LN_STAT_PARTS][2]             */
-  const float* scale;   /* fp32, (b, c) at scale[b*mod_batch_stride + c] */
+  const float* scale;   /* fp32 multiplier 1 + scale_b, (b, c) at scale[b*mod_batch_stride + c] */
   int64_t mod_batch_stride;
   int32_t rows_per_batch;
   int32_t M, C, ldx;

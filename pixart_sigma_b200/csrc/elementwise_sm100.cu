@@ -272,7 +272,7 @@ extern "C" int pxa_dpm_solver_pp_step(const PxaDpmStepArgs* args, void* stream) 
 namespace pxa {
 
 // ------------------------------------------------------------------------------------------------- fused-LN chain: first link
-// a = bf16(x * (1 + scale[b])), stats[row][0] = (sum x, sum x^2), stats[row][1..] = 0 (see PXA_EPI_LN_BIAS in the header).
+// a = bf16(x * mult[b]) with mult = 1 + scale, stats[row][0] = (sum x, sum x^2), stats[row][1..] = 0 (see PXA_EPI_LN_BIAS).
 // One warp per row like ln_modulate: reads x once (fp32), writes a once (bf16): (4 + 2) * C bytes per row.
 template <int kVec>
 __global__ void __launch_bounds__(256) ln_prepare_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a_out,
@@ -293,8 +293,7 @@ __global__ void __launch_bounds__(256) ln_prepare_kernel(const float* __restrict
     const float4 e = __ldg(reinterpret_cast<const float4*>(sc + col));
     s += (v.x + v.y) + (v.z + v.w);
     q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, q))));
-    *reinterpret_cast<uint2*>(orow + col) = make_uint2(pack_bf16x2(v.x * (1.0f + e.x), v.y * (1.0f + e.y)),
-                                                       pack_bf16x2(v.z * (1.0f + e.z), v.w * (1.0f + e.w)));
+    *reinterpret_cast<uint2*>(orow + col) = make_uint2(pack_bf16x2(v.x * e.x, v.y * e.y), pack_bf16x2(v.z * e.z, v.w * e.w));
   }
   s = warp_sum(s);
   q = warp_sum(q);

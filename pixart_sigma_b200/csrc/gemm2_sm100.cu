@@ -197,15 +197,26 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       int as = 0;
       uint32_t aphase = 0;
       int titer = 0;
+      EpiRegs<BN> er;                                              // constants / LN statistics of a tile, loaded one tile ahead
+      [[maybe_unused]] LnStatRegs sr;
+      if (cluster_id < num_tiles) {
+        load_epi_consts<BN, kLn>(er, p, tid, ((cluster_id) / p.num_n_tiles) * (2 * kBM) + rank * kBM, ((cluster_id) % p.num_n_tiles) * BN);
+        if constexpr (kLn) load_ln_stats(sr, p, ((cluster_id) / p.num_n_tiles) * (2 * kBM) + rank * kBM + q * 32 + lane);
+      }
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++titer) {
         const int m0 = (tile / p.num_n_tiles) * (2 * kBM) + rank * kBM;
         const int n0 = (tile % p.num_n_tiles) * BN;
         const int nch = chunks_of_tile<BN>(p, n0);
         EpiConst* cb = consts + (titer & 1);
-        stage_epi_consts<BN, kLn>(cb, p, tid, m0, n0);
+        store_epi_consts<BN>(cb, er, tid);
         [[maybe_unused]] float2 ln = make_float2(1.f, 0.f);
-        if constexpr (kLn) ln = ln_row_coeffs(p, m0 + q * 32 + lane);
+        if constexpr (kLn) ln = ln_row_coeffs(p, sr);
         named_bar_sync(2, kNumEpiThreads);
+        if (tile + num_clusters < num_tiles) {                               // next tile's loads: in flight during this tile's chunks
+          const int nt_ = tile + num_clusters;
+          load_epi_consts<BN, kLn>(er, p, tid, (nt_ / p.num_n_tiles) * (2 * kBM) + rank * kBM, (nt_ % p.num_n_tiles) * BN);
+          if constexpr (kLn) load_ln_stats(sr, p, (nt_ / p.num_n_tiles) * (2 * kBM) + rank * kBM + q * 32 + lane);
+        }
         [[maybe_unused]] const bool second = q * 32 + lane >= cb->row_split;
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();

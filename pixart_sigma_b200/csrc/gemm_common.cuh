@@ -238,44 +238,74 @@ PXA_DEVICE void epilogue_chunk_residual(uint32_t (&v)[32], const ResFrag& res, c
 }
 
 
-// Called by the 128 epilogue threads (tid 0..127) at the start of a tile; followed by a named barrier.
+// Per-tile constants in two phases so that their L2 latency hides behind the PREVIOUS tile's epilogue work: the 128
+// epilogue threads issue the global loads of tile i + 1 (load_epi_consts) right after tile i's barrier and park the values in
+// registers; at the top of tile i + 1 they are stored to the tile's EpiConst buffer (store_epi_consts), followed by a named
+// barrier.  (Loading and storing in one go put one L2 round trip, ~1 us, in front of every tile's epilogue.)
+template <int BN> struct EpiRegs {
+  static constexpr int kCols = (BN + kNumEpiThreads - 1) / kNumEpiThreads;
+  float v[kCols][5];
+  int row_split;
+};
+
 template <int BN, bool kLn = false>
-PXA_DEVICE void stage_epi_consts(EpiConst* cb, const GemmParams& p, int tid, int m0, int n0) {
+PXA_DEVICE void load_epi_consts(EpiRegs<BN>& r, const GemmParams& p, int tid, int m0, int n0) {
   const int b0 = m0 / p.rows_per_batch;
   const int last = (m0 + kBM - 1 < p.M ? m0 + kBM - 1 : p.M - 1);
   const int b1 = last / p.rows_per_batch;
 #pragma unroll
-  for (int c = tid; c < BN; c += kNumEpiThreads) {
-    const int col = n0 + c;
-    const bool ok = col < p.N;
+  for (int i = 0; i < EpiRegs<BN>::kCols; ++i) {
+    const int col = n0 + tid + i * kNumEpiThreads;
+    const bool ok = col < p.N && tid + i * kNumEpiThreads < BN;
     if constexpr (kLn) {
-      cb->bias[c] = ok ? __ldg(p.ln_v + (size_t)b0 * p.ln_uv_batch_stride + col) : 0.f;
-      cb->gate0[c] = ok ? __ldg(p.ln_v + (size_t)b1 * p.ln_uv_batch_stride + col) : 0.f;
-      cb->ex0[c] = ok ? __ldg(p.ln_u + (size_t)b0 * p.ln_uv_batch_stride + col) : 0.f;
-      cb->ex1[c] = ok ? __ldg(p.ln_u + (size_t)b1 * p.ln_uv_batch_stride + col) : 0.f;
+      r.v[i][0] = ok ? __ldg(p.ln_v + (size_t)b0 * p.ln_uv_batch_stride + col) : 0.f;
+      r.v[i][1] = ok ? __ldg(p.ln_v + (size_t)b1 * p.ln_uv_batch_stride + col) : 0.f;
+      r.v[i][2] = 1.f;
+      r.v[i][3] = ok ? __ldg(p.ln_u + (size_t)b0 * p.ln_uv_batch_stride + col) : 0.f;
+      r.v[i][4] = ok ? __ldg(p.ln_u + (size_t)b1 * p.ln_uv_batch_stride + col) : 0.f;
     } else {
-      cb->bias[c] = (ok && p.bias != nullptr) ? __bfloat162float(p.bias[col]) : 0.f;
-      cb->gate0[c] = (ok && p.gate != nullptr) ? __ldg(p.gate + (size_t)b0 * p.gate_batch_stride + col) : 1.f;
-      cb->gate1[c] = (ok && p.gate != nullptr) ? __ldg(p.gate + (size_t)b1 * p.gate_batch_stride + col) : 1.f;
-      cb->ex0[c] = (ok && p.aux_scale != nullptr) ? __ldg(p.aux_scale + (size_t)b0 * p.aux_scale_batch_stride + col) : 1.f;
-      cb->ex1[c] = (ok && p.aux_scale != nullptr) ? __ldg(p.aux_scale + (size_t)b1 * p.aux_scale_batch_stride + col) : 1.f;
+      r.v[i][0] = (ok && p.bias != nullptr) ? __bfloat162float(p.bias[col]) : 0.f;
+      r.v[i][1] = (ok && p.gate != nullptr) ? __ldg(p.gate + (size_t)b0 * p.gate_batch_stride + col) : 1.f;
+      r.v[i][2] = (ok && p.gate != nullptr) ? __ldg(p.gate + (size_t)b1 * p.gate_batch_stride + col) : 1.f;
+      r.v[i][3] = (ok && p.aux_scale != nullptr) ? __ldg(p.aux_scale + (size_t)b0 * p.aux_scale_batch_stride + col) : 1.f;
+      r.v[i][4] = (ok && p.aux_scale != nullptr) ? __ldg(p.aux_scale + (size_t)b1 * p.aux_scale_batch_stride + col) : 1.f;
     }
   }
-  if (tid == 0) cb->row_split = (b0 + 1) * p.rows_per_batch - m0;
+  r.row_split = (b0 + 1) * p.rows_per_batch - m0;
 }
 
-// LayerNorm statistics of row `row` from its PXA_LN_STAT_PARTS partial (sum, sum of squares) pairs:
-// returns (rstd, -rstd * mean), so that the normalised accumulator is fma(rstd, acc, fma(-rstd*mean, u, v)).
-PXA_DEVICE float2 ln_row_coeffs(const GemmParams& p, int row) {
-  float s = 0.f, q = 0.f;
-  if (row < p.M) {
-    const float4* sp = reinterpret_cast<const float4*>(p.ln_stats + (size_t)row * (2 * PXA_LN_STAT_PARTS));
+template <int BN>
+PXA_DEVICE void store_epi_consts(EpiConst* cb, const EpiRegs<BN>& r, int tid) {
 #pragma unroll
-    for (int i = 0; i < PXA_LN_STAT_PARTS / 2; ++i) {
-      const float4 t = __ldg(sp + i);
-      s += t.x + t.z;
-      q += t.y + t.w;
+  for (int i = 0; i < EpiRegs<BN>::kCols; ++i) {
+    const int c = tid + i * kNumEpiThreads;
+    if (c < BN) {
+      cb->bias[c] = r.v[i][0];
+      cb->gate0[c] = r.v[i][1];
+      cb->gate1[c] = r.v[i][2];
+      cb->ex0[c] = r.v[i][3];
+      cb->ex1[c] = r.v[i][4];
     }
+  }
+  if (tid == 0) cb->row_split = r.row_split;
+}
+
+// The PXA_LN_STAT_PARTS partial (sum, sum of squares) pairs of row `row` (fused LayerNorm consumer), loaded one tile ahead.
+struct LnStatRegs {
+  float4 t[PXA_LN_STAT_PARTS / 2];
+};
+PXA_DEVICE void load_ln_stats(LnStatRegs& r, const GemmParams& p, int row) {
+  const float4* sp = reinterpret_cast<const float4*>(p.ln_stats + (size_t)(row < p.M ? row : p.M - 1) * (2 * PXA_LN_STAT_PARTS));
+#pragma unroll
+  for (int i = 0; i < PXA_LN_STAT_PARTS / 2; ++i) r.t[i] = __ldg(sp + i);
+}
+// (rstd, -rstd * mean), so that the normalised accumulator is fma(rstd, acc, fma(-rstd * mean, u, v)).
+PXA_DEVICE float2 ln_row_coeffs(const GemmParams& p, const LnStatRegs& r) {
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int i = 0; i < PXA_LN_STAT_PARTS / 2; ++i) {
+    s += r.t[i].x + r.t[i].z;
+    q += r.t[i].y + r.t[i].w;
   }
   const float mean = s * p.ln_inv_dim;
   const float var = fmaxf(q * p.ln_inv_dim - mean * mean, 0.f);
@@ -507,6 +537,8 @@ PXA_DEVICE void tma_res_epilogue(const GemmParams& p, const TileWalk& tw, uint8_
   }
   int g = 0, as = 0, titer = 0;
   uint32_t aphase = 0;
+  EpiRegs<BN> er;                                               // this tile's constants, loaded one tile ahead
+  if (tw.first < tw.count) load_epi_consts<BN>(er, p, tid, tw.m0(tw.first), tw.ntile(tw.first) * BN);
   const bool tracing = issuer && p.trace != nullptr && blockIdx.x == 0;   // debug only (tools/gemm_trace.py)
   int tcnt = 0;
   auto stamp = [&]() {
@@ -519,8 +551,10 @@ PXA_DEVICE void tma_res_epilogue(const GemmParams& p, const TileWalk& tw, uint8_
     const int n0 = nt * BN;
     const int nch = chunks_of_tile<BN>(p, n0);
     EpiConst* cb = consts + (titer & 1);
-    stage_epi_consts<BN>(cb, p, tid, m0, n0);                   // global loads hide under this tile's MMAs
+    store_epi_consts<BN>(cb, er, tid);
     named_bar_sync(2, kNumEpiThreads);
+    if (tile + tw.stride < tw.count)                            // next tile's constants: in flight during this tile's chunks
+      load_epi_consts<BN>(er, p, tid, tw.m0(tile + tw.stride), tw.ntile(tile + tw.stride) * BN);
     stamp();                                                    // tile: start waiting for the accumulator
     mbar_wait(&tfull_bar[as], aphase);
     stamp();                                                    // tile: accumulator ready

@@ -171,15 +171,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t aphase = 0;
       int titer = 0;
       uint8_t* stile = epi_smem + (warp - kEpiWarp0) * 4096;       // per-warp transpose tile
+      EpiRegs<BN> er;                                              // constants / LN statistics of a tile, loaded one tile ahead
+      [[maybe_unused]] LnStatRegs sr;
+      if ((int)blockIdx.x < num_tiles) {
+        const int ft = blockIdx.x;
+        load_epi_consts<BN, kLn>(er, p, tid, ((ft % mn_tiles) / p.num_n_tiles) * kBM, ((ft % mn_tiles) % p.num_n_tiles) * BN);
+        if constexpr (kLn) load_ln_stats(sr, p, ((ft % mn_tiles) / p.num_n_tiles) * kBM + q * 32 + lane);
+      }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
         const int m0 = ((tile % mn_tiles) / p.num_n_tiles) * kBM;
         const int n0 = ((tile % mn_tiles) % p.num_n_tiles) * BN;
         const int nch = chunks_of_tile<BN>(p, n0);
         EpiConst* cb = consts + (titer & 1);
-        stage_epi_consts<BN, kLn>(cb, p, tid, m0, n0);             // global loads hide under this tile's MMAs
+        store_epi_consts<BN>(cb, er, tid);
         [[maybe_unused]] float2 ln = make_float2(1.f, 0.f);
-        if constexpr (kLn) ln = ln_row_coeffs(p, m0 + q * 32 + lane);
+        if constexpr (kLn) ln = ln_row_coeffs(p, sr);
         named_bar_sync(2, kNumEpiThreads);
+        if (tile + gridDim.x < num_tiles) {                               // next tile's loads: in flight during this tile's chunks
+          const int nt_ = tile + gridDim.x;
+          load_epi_consts<BN, kLn>(er, p, tid, ((nt_ % mn_tiles) / p.num_n_tiles) * kBM, ((nt_ % mn_tiles) % p.num_n_tiles) * BN);
+          if constexpr (kLn) load_ln_stats(sr, p, ((nt_ % mn_tiles) / p.num_n_tiles) * kBM + q * 32 + lane);
+        }
         [[maybe_unused]] const bool second = q * 32 + lane >= cb->row_split;
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();

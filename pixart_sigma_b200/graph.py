@@ -14,18 +14,31 @@ import torch
 
 
 class GraphedForward:
+    """`method`: 'forward' or 'forward_with_dpmsolver' (the two entry points whose tensor arguments are x, timestep, y, mask;
+    `forward_with_cfg` takes a guidance scale in that position and is not graphed here).  `data_info` tensors are captured
+    by reference, so their identity is part of the graph key.  The returned tensor is a copy of the graph's static output."""
+
+    METHODS = ("forward", "forward_with_dpmsolver")
+
     def __init__(self, model, method: str = "forward_with_dpmsolver"):
+        if method not in self.METHODS:
+            raise ValueError(f"GraphedForward supports {self.METHODS}, got {method!r}")
         self.model, self.method = model, method
         self._graphs: Dict[Tuple, dict] = {}
 
-    def _key(self, x, y, mask):
-        return (tuple(x.shape), tuple(y.shape), None if mask is None else tuple(mask.shape))
+    @staticmethod
+    def _key(x, y, mask, data_info):
+        di = None
+        if data_info is not None:
+            di = tuple(sorted((k, (v.data_ptr(), tuple(v.shape)) if isinstance(v, torch.Tensor) else repr(v))
+                              for k, v in data_info.items()))
+        return (tuple(x.shape), tuple(y.shape), None if mask is None else tuple(mask.shape), di)
 
     @torch.no_grad()
     def __call__(self, x: torch.Tensor, timestep: torch.Tensor, y: torch.Tensor, mask: Optional[torch.Tensor] = None,
                  data_info=None) -> torch.Tensor:
         dev = next(self.model.parameters()).device
-        key = self._key(x, y, mask)
+        key = self._key(x, y, mask, data_info)
         g = self._graphs.get(key)
         if g is None:
             st = {"x": torch.empty(x.shape, dtype=torch.float32, device=dev),
@@ -34,8 +47,10 @@ class GraphedForward:
                   "mask": None if mask is None else torch.empty(mask.shape, dtype=torch.long, device=dev)}
             self._copy_in(st, x, timestep, y, mask)
             fn = getattr(self.model, self.method)
-            call = (lambda: fn(st["x"], st["t"], st["y"], data_info, mask=st["mask"])) if self.method != "forward" else \
-                   (lambda: fn(st["x"], st["t"], st["y"], mask=st["mask"], data_info=data_info))
+            if self.method == "forward":
+                call = lambda: fn(st["x"], st["t"], st["y"], mask=st["mask"], data_info=data_info)
+            else:
+                call = lambda: fn(st["x"], st["t"], st["y"], data_info=data_info, mask=st["mask"])
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
@@ -49,7 +64,7 @@ class GraphedForward:
             self._graphs[key] = g
         self._copy_in(g["static"], x, timestep, y, mask)
         g["graph"].replay()
-        return g["out"]
+        return g["out"].clone()
 
     @staticmethod
     def _copy_in(st, x, t, y, mask):

@@ -226,10 +226,12 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
     return out
 
 
-def ln_prepare(x: torch.Tensor, scale: torch.Tensor, a_out: torch.Tensor, stats_out: torch.Tensor, *, mod_batch_stride: int,
+def ln_prepare(x: torch.Tensor, mult: torch.Tensor, a_out: torch.Tensor, stats_out: torch.Tensor, *, mod_batch_stride: int,
                rows_per_batch: int) -> None:
-    """First link of the fused LayerNorm-modulate chain: a_out = bf16(x * (1 + scale[b])), stats_out (M, 8, 2) = partial
-    (sum, sum of squares) of each row of x (part 0; the rest zero).  x (M, C) fp32, scale an fp32 view (row b at b*stride)."""
+    """First link of the fused LayerNorm-modulate chain: a_out = bf16(x * mult[b]) with mult = 1 + scale (the multiplier
+    `gemm(aux_scale=...)` takes), stats_out (M, 8, 2) = partial (sum, sum of squares) of each row of x (part 0; the rest
+    zero).  x (M, C) fp32, mult an fp32 view (row b at b*stride)."""
+    scale = mult
     assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1 and scale.dtype == torch.float32
     M, Cc = x.shape
     assert a_out.dtype == torch.bfloat16 and a_out.is_contiguous() and a_out.shape == (M, Cc)

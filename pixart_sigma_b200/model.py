@@ -13,6 +13,7 @@ There is deliberately no CPU / eager fallback: `forward` requires CUDA bf16 para
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -278,12 +279,14 @@ class _LnFusion:
         Returns u, v (depth, B, ntot) fp32 and one_plus (depth, B, 2, C) = 1 + (scale_msa | scale_mlp)."""
         self._static(ws)
         depth, B = mod_all.shape[0], mod_all.shape[1]
-        rows = t0[:, [0, 1, 3, 4]].permute(1, 0, 2).reshape(4 * B, -1)            # kind-major: shift_msa, scale_msa, shift_mlp, scale_mlp
+        # kind-major rows: shift_msa, scale_msa, shift_mlp, scale_mlp (plain slices: list indexing would copy an index tensor
+        # from the host, which a CUDA-graph capture forbids)
+        rows = torch.stack([t0[:, 0], t0[:, 1], t0[:, 3], t0[:, 4]]).reshape(4 * B, -1)
         g = self._skinny(rows, self.wstack, "ln_dyn", ws).view(4, B, depth, self.ntot)
         n1 = self.n1
         u = torch.cat([g[1, :, :, :n1], g[3, :, :, n1:]], dim=-1).permute(1, 0, 2) + self.s_u[:, None]
         v = torch.cat([g[0, :, :, :n1], g[2, :, :, n1:]], dim=-1).permute(1, 0, 2) + self.s_v[:, None]
-        one_plus = (1.0 + mod_all[:, :, [1, 4]]).contiguous()
+        one_plus = 1.0 + torch.stack([mod_all[:, :, 1], mod_all[:, :, 4]], dim=2)
         return u.contiguous(), v.contiguous(), one_plus
 
 
@@ -455,6 +458,7 @@ class PixArtMSBlock(nn.Module):
             from .autograd import block_forward_train
             out = block_forward_train(self, x32, cond, kv_len, kv_off, max(max(lens), 1), mod, B, N, None, tuple(HW))
         else:
+            _require_kernel_ready(self.attn.qkv.weight, "PixArtMSBlock")
             ln = None
             if N >= _LN_FUSE_MIN_ROWS:
                 if self._ln_fusion is None:
@@ -529,7 +533,7 @@ class PixArtMS(nn.Module):
         # timestep in fp32 like the fp32 reference does; set True to reproduce the bf16 cast bit for bit.
         self.round_timestep_to_dtype = False
         # LayerNorm + t2i_modulate inside the QKV / fc1 GEMM epilogues (no stand-alone norm pass); False = pxa_ln_modulate
-        self.fuse_ln_modulate = True
+        self.fuse_ln_modulate = os.environ.get("PXA_FUSE_LN", "1") != "0"
         self.__dict__["_ln_fusion"] = None
         self._ws = _Workspace()
         self.initialize()
@@ -572,6 +576,15 @@ class PixArtMS(nn.Module):
             # ambient autocast (accelerate's mixed precision, train.py:369) must not down-cast the fp32 torch glue around them
             with torch.autocast(device_type="cuda", enabled=False):
                 return self._forward_train(x, timestep, y, mask=mask, data_info=data_info)
+        if w0.is_cuda and w0.dtype == torch.float16:
+            # scripts/inference.py:161 loads the checkpoint as fp16 (`weight_dtype = torch.float16`).  The sm_100a kernels
+            # take bf16 operands, so the parameters are cast ONCE, in place; inputs / outputs keep the caller's fp16.
+            import warnings
+            warnings.warn("pixart_sigma_b200: fp16 parameters cast to bf16 for the sm_100a kernels (outputs stay fp16)")
+            if self.output_dtype is None:
+                self.output_dtype = torch.float16
+            self.to(torch.bfloat16)
+            w0 = self.blocks[0].attn.qkv.weight
         _require_kernel_ready(w0, "PixArtMS.forward")
         dt, dev, C, p = self.dtype, w0.device, self.hidden_size, self.patch_size
         B = x.shape[0]

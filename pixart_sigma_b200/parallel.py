@@ -64,7 +64,13 @@ class GradBucketReducer:
     The collective is the only data-path exchange of the training step: nothing else is sharded.
     """
 
-    def __init__(self, model: torch.nn.Module, group=None, bucket_of=None):
+    def __init__(self, model: torch.nn.Module, group=None, bucket_of=None, compress: Optional[str] = None):
+        """compress: None = all-reduce the fp32 buckets as they are (what torch DDP does for the reference, 2.44 GB per step
+        at XL/2); "bf16" = each bucket travels as a bf16 copy (1.22 GB; torch DDP's bf16_compress_hook semantics: cast,
+        sum in bf16 on the wire, cast back) -- SURVEY.md 8e / 8f.3."""
+        if compress not in (None, "bf16"):
+            raise ValueError("compress must be None or 'bf16'")
+        self.compress = compress
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         params = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
@@ -84,7 +90,8 @@ class GradBucketReducer:
                 assert p.dtype == flat.dtype and p.device == flat.device, "one dtype / device per bucket"
                 p.grad = flat[off: off + p.numel()].view_as(p)            # gradient accumulates straight into the bucket
                 off += p.numel()
-            self.buckets.append({"key": key, "flat": flat, "params": ps, "pending": 0, "work": None})
+            wire = torch.empty(total, dtype=torch.bfloat16, device=flat.device) if compress == "bf16" else None
+            self.buckets.append({"key": key, "flat": flat, "params": ps, "pending": 0, "work": None, "wire": wire})
         self._hooks = []
         self.overlap = True        # False: no collective from the hooks (CUDA-graph capture); finish() reduces every bucket
         for b in self.buckets:
@@ -92,8 +99,27 @@ class GradBucketReducer:
                 self._hooks.append(p.register_post_accumulate_grad_hook(lambda _p, b=b: self._ready(b)))
         self.start()
 
+    def check_views(self) -> None:
+        """Every parameter's `.grad` must still be its view into the flat bucket.  `optimizer.zero_grad()` /
+        `model.zero_grad()` with the torch default set_to_none=True (or any code that rebinds `.grad`) silently detaches
+        them; the buckets would then be reduced stale while the optimizer sees other tensors.  Detached gradients are
+        re-attached when empty (None); a foreign tensor is an error."""
+        for b in self.buckets:
+            lo = b["flat"].data_ptr()
+            hi = lo + b["flat"].numel() * b["flat"].element_size()
+            off = 0
+            for p in b["params"]:
+                if p.grad is None:
+                    p.grad = b["flat"][off: off + p.numel()].view_as(p)
+                    p.grad.zero_()
+                elif not (lo <= p.grad.data_ptr() < hi):
+                    raise RuntimeError("GradBucketReducer: a parameter's .grad no longer aliases its gradient bucket (was .grad "
+                                       "re-assigned?); zero gradients with reducer.zero_grad() or zero_grad(set_to_none=False)")
+                off += p.numel()
+
     def start(self) -> None:
         """Arm the buckets for one backward pass (gradients are NOT zeroed: call `zero_grad()` between optimizer steps)."""
+        self.check_views()
         for b in self.buckets:
             b["pending"], b["work"] = len(b["params"]), None
 
@@ -101,11 +127,17 @@ class GradBucketReducer:
         for b in self.buckets:
             b["flat"].zero_()
 
+    def _launch(self, b) -> None:
+        b["flat"].div_(self.world)
+        buf = b["flat"]
+        if b["wire"] is not None:
+            buf = b["wire"].copy_(b["flat"])
+        b["work"] = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
     def _ready(self, b) -> None:
         b["pending"] -= 1
         if b["pending"] == 0 and self.world > 1 and self.overlap:
-            b["flat"].div_(self.world)
-            b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._launch(b)
 
     def finish(self) -> None:
         """Block until every bucket has been reduced; buckets whose parameters got no gradient this step (unused
@@ -114,13 +146,16 @@ class GradBucketReducer:
             return
         for b in self.buckets:
             if b["work"] is None:
-                b["flat"].div_(self.world)
-                b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                self._launch(b)
         for b in self.buckets:
             b["work"].wait()
+            if b["wire"] is not None:
+                b["flat"].copy_(b["wire"])
 
     def grad_bytes(self) -> int:
-        return sum(b["flat"].numel() * b["flat"].element_size() for b in self.buckets)
+        """Bytes handed to the collective per step (per rank)."""
+        return sum((b["wire"] if b["wire"] is not None else b["flat"]).numel() *
+                   (b["wire"] if b["wire"] is not None else b["flat"]).element_size() for b in self.buckets)
 
     def remove(self) -> None:
         for h in self._hooks:

@@ -151,7 +151,12 @@ class DPMSolverPP:
         return (out, inter) if return_intermediate else out
 
     def _sample_graphed(self, x, plan, t_dev, cond):
-        key = (tuple(x.shape), len(plan), x.device.index)
+        # every per-step scalar (sigma_s, alpha_s, a, b, c), the step orders and t_input are baked into the captured kernel
+        # arguments, and `cond` / model_kwargs tensors into the captured forward: all of them are part of the key
+        kw_id = tuple(sorted((k, (v.data_ptr(), tuple(v.shape)) if isinstance(v, torch.Tensor) else repr(v))
+                             for k, v in (self.model_kwargs or {}).items()))
+        key = (tuple(x.shape), x.device.index, float(self.cfg_scale), cond.data_ptr(), tuple(cond.shape), kw_id,
+               tuple((st["t_input"], st["sigma_s"], st["alpha_s"], st["a"], st["b"], st["c"], st.get("order")) for st in plan))
         if key not in self._graphs:
             x_static = x.to(torch.float32).contiguous().clone()
             x0_prev = torch.empty_like(x_static)

@@ -87,10 +87,14 @@ class IDDPMLoss:
 
 
 def train_step(model, loss_fn: IDDPMLoss, x_start, timestep, y, mask, data_info=None, noise=None, reducer=None,
-               loss_scale: float = 1.0) -> torch.Tensor:
+               loss_scale: float = 1.0, refresh_shadows: bool = True) -> torch.Tensor:
     """One fwd + bwd of `train_scripts/train.py:186-197` (the optimizer step stays the caller's): returns the mean loss
     (detached).  With `reducer` (parallel.GradBucketReducer) the gradient all-reduce runs bucket by bucket behind the
-    backward and is complete when this returns."""
+    backward and is complete when this returns.  `refresh_shadows`: re-derive the cached bf16 weight shadows from the
+    parameters at the start of the step (0.6 ms at XL/2), which makes in-place `.data` updates between steps safe."""
+    if refresh_shadows:
+        from . import autograd as ag
+        ag.refresh_shadows(model)           # `.data` writes (fused / ZeRO optimizers, EMA copies) do not bump `_version`
     if reducer is not None:
         reducer.start()
     terms = loss_fn.training_losses(model, x_start, timestep, dict(y=y, mask=mask, data_info=data_info), noise=noise)
@@ -109,17 +113,20 @@ class GraphedTrainStep:
     input buffers and replayed; the library never allocates or synchronises and autograd's backward runs on the capture
     stream, so fwd + bwd capture as they are.  Every replay first refreshes the bf16 weight shadows IN PLACE from the
     (optimizer-updated) fp32 parameters (`autograd.refresh_shadows`, part of the graph), so an optimizer step between
-    replays is seen.  The gradient all-reduce stays outside the graph: `reducer.finish()` reduces the flat buckets after
-    the replay (no overlap with the backward in this mode).
+    replays is seen.  The gradient all-reduce: by default it stays outside the graph -- `reducer.finish()` reduces the flat
+    buckets after the replay (exposed, no overlap with the backward); with `capture_collectives=True` the bucket all-reduces
+    are captured too, on NCCL's stream, forked from the backward where each bucket completes and joined at the end of the
+    graph, so replays overlap them with the rest of the backward exactly like the eager path does.
 
     Fixed shapes only (one graph per batch geometry); activation checkpointing is captured as well (the recomputation is
     just more kernels on the stream; torch's RNG-state stashing, which reads the device, is disabled).
     """
 
-    def __init__(self, model, loss_fn: IDDPMLoss, reducer, example, warmup: int = 2):
+    def __init__(self, model, loss_fn: IDDPMLoss, reducer, example, warmup: int = 2, capture_collectives: bool = False):
         from . import autograd as ag
         self.model, self.loss_fn, self.reducer = model, loss_fn, reducer
-        reducer.overlap = False                      # collectives stay outside the graph
+        self.captured = bool(capture_collectives) and reducer.world > 1
+        reducer.overlap = self.captured              # False: collectives stay outside the graph
         dev = next(model.parameters()).device
         self.static = [None if v is None else torch.empty_like(v, device=dev) for v in example]
         self._copy_in(example)
@@ -128,9 +135,13 @@ class GraphedTrainStep:
         def step():
             ag.refresh_shadows(model)
             reducer.zero_grad()
+            if self.captured:
+                reducer.start()
             terms = loss_fn.training_losses(model, x0, t, dict(y=y, mask=mask, data_info=None), noise=noise)
             loss = terms["loss"].mean()
             loss.backward()
+            if self.captured:
+                reducer.finish()
             return loss.detach()
 
         side = torch.cuda.Stream(device=dev)
@@ -141,7 +152,8 @@ class GraphedTrainStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread_local: NCCL's watchdog thread may query events while this thread captures
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local" if self.captured else "global"):
             self.loss = step()
 
     def _copy_in(self, batch):
@@ -151,6 +163,10 @@ class GraphedTrainStep:
 
     def __call__(self, x_start, timestep, y, mask, noise) -> torch.Tensor:
         self._copy_in((x_start, timestep, y, mask, noise))
+        if self.captured:
+            self.reducer.check_views()
+            self.graph.replay()
+            return self.loss
         self.reducer.start()
         self.graph.replay()
         if self.reducer.world > 1:

@@ -191,7 +191,7 @@ def test_ln_prepare_scaled_copy_and_row_sums():
     a = torch.empty(B * Ntok, Cc, dtype=torch.bfloat16, device=DEV)
     stats = torch.full((B * Ntok, lib.LN_STAT_PARTS, 2), float("nan"), device=DEV)
     lib.ln_prepare(x, mod[:, 4], a, stats, mod_batch_stride=6 * Cc, rows_per_batch=Ntok)
-    want = x * (1 + mod[:, 4].repeat_interleave(Ntok, 0))
+    want = x * mod[:, 4].repeat_interleave(Ntok, 0)
     assert po.rel_err(a.float(), want) < 4e-3
     assert po.rel_err(stats.sum(1)[:, 0], x.sum(1)) < 1e-5 and po.rel_err(stats.sum(1)[:, 1], (x * x).sum(1)) < 1e-5
     assert torch.equal(stats[:, 1:], torch.zeros_like(stats[:, 1:]))
@@ -210,7 +210,7 @@ def test_gemm_ln_epilogue_matches_norm_modulate_linear(N, gelu, pair, rpb):
     w, bias = _randn(N, K, seed=56, scale=K ** -0.5), _randn(N, seed=57, scale=0.1)
     a = torch.empty(M, K, dtype=torch.bfloat16, device=DEV)
     stats = torch.empty(M, lib.LN_STAT_PARTS, 2, device=DEV)
-    lib.ln_prepare(x, scale, a, stats, mod_batch_stride=K, rows_per_batch=rpb)
+    lib.ln_prepare(x, (1 + scale).contiguous(), a, stats, mod_batch_stride=K, rows_per_batch=rpb)
     u, v = _uv(w, bias, shift, scale)
     out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV)
     lib.gemm(a, w, None, out, epilogue=lib.EPI_LN_BIAS_GELU if gelu else lib.EPI_LN_BIAS, rows_per_batch=rpb, cta_pair=pair,
@@ -375,3 +375,36 @@ def test_kv_compress_conv2_ln():
         src = qkv[:, col * Cc:(col + 1) * Cc].float().view(B, Hh * Ww, Cc)
         want = po.kv_downsample(sdf, "a", src, Hh, Ww, 2, "conv")
         assert po.rel_err(got.float(), want) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------- skinny GEMMs (M < one tile)
+@pytest.mark.parametrize("M,N", [(4, 3456), (16, 8064), (64, 16128), (130, 4608)])
+def test_gemm_few_rows_fp32_accumulate_in_place(M, N):
+    """The per-forward conditioning GEMMs of the fused LayerNorm (model._LnFusion): a handful of rows against tall weight
+    stacks, fp32 result accumulated in place through the TMA reduce-add epilogue."""
+    K = 1152
+    a, w = _randn(M, K, seed=90), _randn(N, K, seed=91, scale=K ** -0.5)
+    out = torch.zeros(M, N, device=DEV)
+    lib.gemm(a, w, None, out, epilogue=lib.EPI_BIAS_RESIDUAL, residual=out)
+    want = a.float() @ w.float().T
+    assert po.rel_err(out, want) < 1e-5
+    lib.gemm(a, w, None, out, epilogue=lib.EPI_BIAS_RESIDUAL, residual=out)          # accumulates
+    assert po.rel_err(out, 2 * want) < 1e-5
+
+
+def test_ln_fusion_conditioning_vectors_match_fp32():
+    """model._LnFusion.prepare: u = W (1 + scale), v = W shift + bias for (qkv | fc1) of every block, against fp32 torch."""
+    from pixart_sigma_b200.model import PixArtMSBlock, _LnFusion, _Workspace
+    torch.manual_seed(3)
+    with torch.device(DEV):
+        blocks = [PixArtMSBlock(1152, 16).to(torch.bfloat16) for _ in range(2)]
+    B, Cc = 3, 1152
+    t0 = _randn(B, 6, Cc, seed=92, dtype=torch.float32) * 0.3
+    mod_all = torch.stack([b.scale_shift_table.float()[None] + t0 for b in blocks])
+    u, v, one_plus = _LnFusion(blocks).prepare(t0, mod_all, _Workspace())
+    for i, b in enumerate(blocks):
+        for lin, sl, i_shift, i_scale in ((b.attn.qkv, slice(0, 3456), 0, 1), (b.mlp.fc1, slice(3456, 8064), 3, 4)):
+            want_u = (1 + mod_all[i, :, i_scale]) @ lin.weight.float().T
+            want_v = mod_all[i, :, i_shift] @ lin.weight.float().T + lin.bias.float()
+            assert po.rel_err(u[i][:, sl], want_u) < 1e-5 and po.rel_err(v[i][:, sl], want_v) < 1e-5
+    assert torch.equal(one_plus[:, :, 0], 1 + mod_all[:, :, 1]) and torch.equal(one_plus[:, :, 1], 1 + mod_all[:, :, 4])
