@@ -598,6 +598,87 @@ def measure_train(args, ctx: Ctx, mode: str, checkpoint: bool, cpu_baseline: boo
     return line
 
 
+# --------------------------------------------------------------------------------------------- our arm: VAE decoder convs
+VAE_STACK = (  # SDXL-VAE decoder (block_out 128/256/512/512, 2+1 ResBlocks per up block) for a 1024 x 1024 image: latent 128 x 128
+    [("res", 512, 512)] * 2 +                                   # mid block (its single-head attention is not ours)
+    [("res", 512, 512)] * 3 + [("up", 512, 512)] +              # up block 0  @128^2 -> 256^2
+    [("res", 512, 512)] * 3 + [("up", 512, 512)] +              # up block 1  @256^2 -> 512^2
+    [("res", 512, 256), ("res", 256, 256), ("res", 256, 256), ("up", 256, 256)] +   # up block 2  @512^2 -> 1024^2
+    [("res", 256, 128), ("res", 128, 128), ("res", 128, 128)])  # up block 3  @1024^2
+
+
+def measure_vae(args, ctx: Ctx):
+    """the convolution-bearing part of the SDXL-VAE decode of ONE 1024 x 1024 image per GPU --
+    17 ResnetBlock2D (GroupNorm+SiLU -> conv3x3 twice, 1x1 shortcut where the width changes) and 3 upsample convolutions,
+    random weights (diffusers' VAE weights are not available offline).  value = images/s over all ranks."""
+    from pixart_sigma_b200 import lib
+    from pixart_sigma_b200.vae import DecoderResBlock, UpsampleConv
+    dev, rank, world = ctx.dev, ctx.rank, ctx.world
+    torch.manual_seed(5 + rank)
+    mods, flops, side = [], 0.0, 128
+    with torch.device(dev):
+        for kind, cin, cout in VAE_STACK:
+            if kind == "res":
+                m = DecoderResBlock(cin, cout)
+                flops += 2.0 * side * side * 9 * (cin * cout + cout * cout) + (2.0 * side * side * cin * cout if cin != cout else 0.0)
+            else:
+                m = UpsampleConv(cin)
+                side *= 2
+                flops += 2.0 * side * side * 9 * cin * cout
+            mods.append(m.to(torch.bfloat16))
+    x0 = torch.randn(1, 512, 128, 128, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+
+    def step(i):
+        h = x0
+        for m in mods:
+            h = m(h)
+        return h
+
+    warm = max(args.warmup, 3)
+    for i in range(warm):
+        step(i)
+    sampler = ClockSampler(ctx.local) if rank == 0 else None
+    n0 = lib.launch_count()
+    ms = ctx.timed(step, args.steps)
+    launches = lib.launch_count() - n0
+    clocks = sampler.stop() if sampler else None
+    timer = KernelTimer(lib, [("conv", "conv3x3_nhwc"), ("gn", "groupnorm_silu_nhwc"), ("gemm", "gemm")])
+    timer.on = True
+    ms_roof = ctx.timed(step, 2)
+    timer.on = False
+    timer.restore()
+    line = None
+    if rank == 0:
+        sus, burst, hbm, src = measured_peaks()
+        tt = timer.totals_ms()
+        conv_ms, conv_n = tt["conv"]
+        conv_flops = flops - sum(2.0 * (128 * 2 ** j) ** 2 * a * b for j, a, b in ((2, 512, 256), (3, 256, 128)))   # minus the two 1x1 shortcuts
+        conv_tf = conv_flops * 2 / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else None
+        # GroupNorm+SiLU: 2 reads + 1 write of every normalised NHWC image (bf16)
+        gn_bytes, sd = 0.0, 128
+        for kind, cin, cout in VAE_STACK:
+            if kind == "res":
+                gn_bytes += 6.0 * sd * sd * (cin + cout)
+            else:
+                sd *= 2
+        gn_ms = tt["gn"][0]
+        line = {"metric": "vae-decoder-conv-stack images/sec", "value": world * args.steps / (ms / 1000.0), "unit": "images/s",
+                "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "vae: SDXL-VAE decoder ResBlock + upsample convolutions of one 1024x1024 image per GPU "
+                                       "(17 ResnetBlock2D + 3 upsample convs, GroupNorm+SiLU kernels, random weights)",
+                           "tflop_per_step_per_gpu": flops / 1e12, "l2": "activations up to 268 MB per layer: larger than L2"},
+                "gpu_launches": launches, "clocks": clocks,
+                "roofline": {"bound": "tensor", "kernel": "pxa::gemm_bf16_kernel<kConv> (implicit-GEMM 3x3 convolution, 4-D TMA)",
+                             "achieved": conv_tf, "peak": sus, "unit": "TFLOP/s", "frac": conv_tf / sus if conv_tf else None,
+                             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src})", "launches_timed": conv_n,
+                             "step_share": conv_ms / ms_roof, "traffic": None,
+                             "groupnorm_silu": {"bound": "hbm", "achieved_gbs": gn_bytes * 2 / (gn_ms / 1000.0) / 1e9 if gn_ms > 0 else None,
+                                                "peak_gbs": hbm, "step_share": gn_ms / ms_roof},
+                             "whole_step_tflops": flops / (ms / args.steps / 1000.0) / 1e12}}
+    return line
+
+
 _JSON_FD = None
 
 
@@ -611,7 +692,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["vae"])
     ap.add_argument("--no-extras", action="store_true",
                     help="headline workload only (default: the c3 line also carries the c5 training step under `train` and "
                          "the c4 2K forward under `c4`, measured at the same N)")
@@ -635,13 +716,18 @@ def main():
     _JSON_FD = os.dup(1)
     os.dup2(2, 1)
     if args.impl == "reference":
+        if args.workload == "vae":
+            _emit({"impl": "reference", "unavailable": "the VAE decoder (diffusers AutoencoderKL) is not part of the reference tree"})
+            return
         run_reference_arm(args, WORKLOADS[args.workload])
         return
     from pixart_sigma_b200 import lib
     ctx = Ctx(args.gpus)
     lib.load()
     train_mode = "graph" if args.train_mode == "auto" else args.train_mode
-    if args.workload == "c5":
+    if args.workload == "vae":
+        line = measure_vae(args, ctx)
+    elif args.workload == "c5":
         line = measure_train(args, ctx, train_mode, not args.no_checkpoint, ctx.world == 1 and not args.no_cpu_baseline)
     else:
         line = measure_inference(args, ctx, args.workload, headline=True)

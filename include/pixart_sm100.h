@@ -107,6 +107,7 @@ typedef struct PxaGemmArgs {
   float ln_eps;
   int32_t res_epilogue;     /* EPI_BIAS_RESIDUAL, fp32 out, CTA pair: 0 = auto, 1 = register-staged residual (coalesced
                                loads, smem transpose), 2 = residual tile streamed through smem by TMA (row per thread)       */
+  int32_t epi_warps;        /* CTA pair, bf16 epilogues: 0 = auto (8: two epilogue warps per TMEM lane quarter), 4 or 8     */
 } PxaGemmArgs;
 int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream);
 
@@ -150,6 +151,14 @@ int pxa_ln_prepare(const PxaLnPrepareArgs* args, void* stream);
  * of the qkv GEMM output.  HBM-bound: one read and one write of the slice. */
 int pxa_layernorm_affine_bf16(void* x, const void* weight, const void* bias, int32_t M, int32_t C, int64_t ld, float eps,
                               void* stream);
+
+/* GroupNorm (+ SiLU) on an NHWC bf16 image: the prologue of each 3x3 convolution of the SDXL-VAE decoder ResnetBlock2D
+ * (diffusers GroupNorm(32, eps 1e-6) -> SiLU; reference call site scripts/inference.py:136).  out[b,p,c] =
+ * silu((x[b,p,c] - mean[b,g]) * rstd[b,g] * gamma[c] + beta[c]), g = c / (C / groups), statistics over the HW pixels and the
+ * C / groups channels of the group (fp32).  stats_ws: caller-owned fp32 [B][groups][2] scratch (zeroed by the call, on the
+ * stream).  Two launches: statistics, apply.  HBM-bound: 2 reads + 1 write of the image. */
+int pxa_groupnorm_silu_nhwc_bf16(const void* x, void* out, const void* gamma, const void* beta, float* stats_ws, int32_t B,
+                                 int32_t HW, int32_t C, int32_t groups, float eps, int32_t silu, void* stream);
 
 /* ------------------------------------------------------------------------------------------- attention
  * out[b, i, h, :] = softmax_j( q[b,i,h,:] . k[b,j,h,:] * scale ) v[b,j,h,:],  j < kv_len[b],  head_dim 72.

@@ -353,19 +353,22 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       }
       const float nm = -m_ref * sl2;
       const uint64_t nm2 = f32x2(nm, nm);
+      [[maybe_unused]] const float a_sat = -sl2 * (1.0f / 128.0f), b_sat = (8.0f - nm) * (1.0f / 128.0f);   // fma_exp2_x2
       // exp2 on packed fp32 pairs (FFMA2 / FADD2: one issue slot for two lane-ops).  PXA_POLY_OF8 of every 8 pairs take
       // the polynomial exp2 (FMA pipe) instead of MUFU (16 results/clk/SM), so that both pipes and the issue port end up
       // about equally loaded.
       uint32_t pk[32];
       // one pair of scores -> exp2 -> running packed sum + bf16x2 P word; `pair` (0..31) selects MUFU or polynomial
       auto exp_pair = [&](float s0, float s1, int pair, [[maybe_unused]] uint64_t& acc, uint32_t& packed) {
-        const uint64_t x = fma2(f32x2(s0, s1), sl2x2, nm2);
-        uint64_t e;
+        [[maybe_unused]] uint64_t e;
         float e0, e1;
-        if (((pair * PXA_POLY_OF8) & 7) < PXA_POLY_OF8) {
-          e = poly_exp2_x2(x);
-          f32x2_split(e, e0, e1);
+        if (PXA_POLY_OF8 > 0 && ((pair * PXA_POLY_OF8) & 7) < PXA_POLY_OF8) {
+          fma_exp2_x2(s0, s1, a_sat, b_sat, e0, e1);              // FMA-pipe exp2: keeps the MUFU pipe for the other pairs
+#if !PXA_SUM_MMA
+          e = f32x2(e0, e1);
+#endif
         } else {
+          const uint64_t x = fma2(f32x2(s0, s1), sl2x2, nm2);
           float x0, x1;
           f32x2_split(x, x0, x1);
           e0 = fast_exp2(x0);

@@ -382,3 +382,138 @@ extern "C" int pxa_layernorm_affine_bf16(void* x, const void* weight, const void
   PXA_CHECK_CUDA(cudaGetLastError());
   return PXA_OK;
 }
+
+namespace pxa {
+
+// ------------------------------------------------------------------------------------------------- GroupNorm (+ SiLU), NHWC
+// SDXL-VAE decoder ResnetBlock2D prologue (diffusers GroupNorm(32, eps 1e-6) -> SiLU in front of each 3x3 convolution;
+// reference call site scripts/inference.py:136).  Two passes over an NHWC bf16 image: (1) per (sample, group) sum / sum of
+// squares -- each thread walks pixels for a fixed 8-channel slice, CTA-level reduction in smem, one atomic per group and
+// CTA; (2) y = silu((x - mean_g) rstd_g gamma_c + beta_c).  Algorithmic bytes: 2 reads + 1 write of the image (6 B/element).
+constexpr int kGnThreads = 256;
+constexpr int kGnMaxGroups = 64;
+
+__global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ stats,
+                                                              int HW, int C, int groups, int pix_per_cta) {
+  __shared__ float sh[kGnMaxGroups][2];
+  const int b = blockIdx.y;
+  const int slices = C >> 3;                                    // 8-channel slices per pixel
+  const int slice = threadIdx.x % slices, prow = threadIdx.x / slices, prows = kGnThreads / slices;
+  const int cpg = C / groups;
+  for (int i = threadIdx.x; i < groups * 2; i += kGnThreads) (&sh[0][0])[i] = 0.f;
+  __syncthreads();
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(p0 + pix_per_cta, HW);
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  if (prow < prows) {
+    const __nv_bfloat16* base = x + ((size_t)b * HW) * C + slice * 8;
+    for (int p = p0 + prow; p < p1; p += prows) {
+      const uint4 u = *reinterpret_cast<const uint4*>(base + (size_t)p * C);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float a = bf16_lo(w[i]), c = bf16_hi(w[i]);
+        s[2 * i] += a; q[2 * i] = fmaf(a, a, q[2 * i]);
+        s[2 * i + 1] += c; q[2 * i + 1] = fmaf(c, c, q[2 * i + 1]);
+      }
+    }
+    // fold the 8 channels into their groups (cpg >= 8: one group; cpg = 4: two; cpg = 2 / 1: four / eight)
+    const int c0 = slice * 8;
+    int g_prev = c0 / cpg;
+    float as = 0.f, aq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (c0 + i) / cpg;
+      if (g != g_prev) {
+        atomicAdd(&sh[g_prev][0], as); atomicAdd(&sh[g_prev][1], aq);
+        as = aq = 0.f; g_prev = g;
+      }
+      as += s[i]; aq += q[i];
+    }
+    atomicAdd(&sh[g_prev][0], as); atomicAdd(&sh[g_prev][1], aq);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < groups * 2; i += kGnThreads) atomicAdd(stats + (size_t)b * groups * 2 + i, (&sh[0][0])[i]);
+}
+
+template <bool kSilu>
+__global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                              const float* __restrict__ stats, const __nv_bfloat16* __restrict__ gamma,
+                                                              const __nv_bfloat16* __restrict__ beta, int HW, int C, int groups,
+                                                              float eps, long long total_slices) {
+  const int slices = C >> 3;
+  const int cpg = C / groups;
+  const float inv_n = 1.0f / ((float)HW * (float)cpg);
+  for (long long i = blockIdx.x * (long long)kGnThreads + threadIdx.x; i < total_slices; i += (long long)gridDim.x * kGnThreads) {
+    const int slice = (int)(i % slices);
+    const long long pix = i / slices;                            // b * HW + p
+    const int b = (int)(pix / HW);
+    const int c0 = slice * 8;
+    const uint4 u = *reinterpret_cast<const uint4*>(x + pix * C + c0);
+    const uint4 gu = __ldg(reinterpret_cast<const uint4*>(gamma + c0));
+    const uint4 bu = __ldg(reinterpret_cast<const uint4*>(beta + c0));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w}, gw[4] = {gu.x, gu.y, gu.z, gu.w}, bw[4] = {bu.x, bu.y, bu.z, bu.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float y[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = c0 + 2 * k + h;
+        const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + (size_t)b * groups + c / cpg);
+        const float mean = st.x * inv_n;
+        const float rstd = rsqrtf(fmaxf(st.y * inv_n - mean * mean, 0.f) + eps);
+        const float xv = h ? bf16_hi(w[k]) : bf16_lo(w[k]);
+        const float gv = h ? bf16_hi(gw[k]) : bf16_lo(gw[k]);
+        const float bv = h ? bf16_hi(bw[k]) : bf16_lo(bw[k]);
+        float v = fmaf((xv - mean) * rstd, gv, bv);
+        if (kSilu) v = v / (1.0f + __expf(-v));
+        y[h] = v;
+      }
+      o[k] = pack_bf16x2(y[0], y[1]);
+    }
+    *reinterpret_cast<uint4*>(out + pix * C + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+}  // namespace pxa
+
+extern "C" int pxa_groupnorm_silu_nhwc_bf16(const void* x, void* out, const void* gamma, const void* beta, float* stats_ws,
+                                            int32_t B, int32_t HW, int32_t C, int32_t groups, float eps, int32_t silu,
+                                            void* stream) {
+  using namespace pxa;
+  if (!x || !out || !gamma || !beta || !stats_ws) return fail(PXA_ERR_ARG, "null pointer");
+  if (B <= 0 || HW <= 0 || C <= 0 || groups <= 0 || groups > kGnMaxGroups || C % groups || C % 8 || (C >> 3) > kGnThreads)
+    return fail(PXA_ERR_ARG, "bad B / HW / C / groups (C %% 8 == 0, C %% groups == 0, groups <= %d, C <= %d)", kGnMaxGroups,
+                8 * kGnThreads);
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gamma) |
+       reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(stats_ws)) & 15)
+    return fail(PXA_ERR_ALIGN, "pointers must be 16-byte aligned");
+  PXA_REQUIRE_SM100();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  PXA_CHECK_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * B * groups, s));
+  const int sms = device_info().sms;
+  int ctas_x = (4 * sms + B - 1) / B;                            // ~4 CTAs per SM over the whole batch
+  int pix_per_cta = (HW + ctas_x - 1) / ctas_x;
+  const int prows = kGnThreads / (C >> 3);
+  if (pix_per_cta < prows) pix_per_cta = prows;
+  ctas_x = (HW + pix_per_cta - 1) / pix_per_cta;
+  gn_stats_kernel<<<dim3(ctas_x, B), kGnThreads, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), stats_ws, HW, C, groups, pix_per_cta);
+  launch_counter()++;
+  const long long total = (long long)B * HW * (C >> 3);
+  long long blocks = (total + kGnThreads - 1) / kGnThreads;
+  if (blocks > 16LL * sms) blocks = 16LL * sms;
+  if (silu)
+    gn_apply_kernel<true><<<(int)blocks, kGnThreads, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out),
+                                                             stats_ws, reinterpret_cast<const __nv_bfloat16*>(gamma),
+                                                             reinterpret_cast<const __nv_bfloat16*>(beta), HW, C, groups, eps, total);
+  else
+    gn_apply_kernel<false><<<(int)blocks, kGnThreads, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out),
+                                                              stats_ws, reinterpret_cast<const __nv_bfloat16*>(gamma),
+                                                              reinterpret_cast<const __nv_bfloat16*>(beta), HW, C, groups, eps, total);
+  launch_counter()++;
+  PXA_CHECK_CUDA(cudaGetLastError());
+  return PXA_OK;
+}

@@ -76,8 +76,12 @@ template <uint32_t kCols> PXA_DEVICE void tmem_dealloc_pair(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "n"(kCols) : "memory");
 }
 
-template <int BN, int EPI, typename OutT, bool kTmaRes = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+// kEpiWarps = 8 (bf16 epilogues): TWO epilogue warps per TMEM lane quarter take alternate 32-column chunks of a tile.
+// Measured in round 2 (tools/gemm_bench2.py): with 4 epilogue warps the bias / GELU epilogue of a 256 x 256 tile takes about
+// as long as the tile's mainloop under the power cap, so every instruction added to it (e.g. the fused LayerNorm algebra)
+// showed up 1:1 in the kernel time; halving it makes these GEMMs mainloop-bound again.
+template <int BN, int EPI, typename OutT, bool kTmaRes = false, int kEpiWarps = 4>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * kEpiWarps, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out,
                   const __grid_constant__ CUtensorMap tmap_aux, const GemmParams p) {
@@ -109,7 +113,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 2 * kNumEpiThreads);
+      mbar_init(&tempty_bar[s], 2 * 32 * kEpiWarps);
     }
     for (int s = 0; s < kResBufs; ++s) mbar_init(&res_full[s], 1);
     fence_mbar_init();
@@ -191,16 +195,20 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                                            &tmap_out, &tmap_aux, warp, lane);
     } else {
       constexpr bool kLn = (EPI == PXA_EPI_LN_BIAS || EPI == PXA_EPI_LN_BIAS_GELU);
-      const int q = warp & 3;
-      const int tid = threadIdx.x - kEpiWarp0 * 32;
-      uint8_t* stile = epi_smem + (warp - kEpiWarp0) * 4096;
+      static_assert(kEpiWarps == 4 || (kEpiWarps == 8 && EPI != PXA_EPI_BIAS_RESIDUAL), "8 epilogue warps: bf16 epilogues only");
+      constexpr int kStep = kEpiWarps / 4;                         // this warp takes chunks half, half + kStep, ...
+      const int q = warp & 3;                                      // TMEM lane quarter (warp % 4)
+      const int half = (warp - kEpiWarp0) >> 2;                    // 0, or 0 / 1 with 8 epilogue warps
+      const int tid = threadIdx.x - kEpiWarp0 * 32;                // 0 .. 32 * kEpiWarps - 1; the first 128 stage the constants
+      uint8_t* stile = epi_smem + (warp - kEpiWarp0) * (4096 / kStep);   // per-warp transpose tile (bf16: 2 KB is enough)
       int as = 0;
       uint32_t aphase = 0;
       int titer = 0;
       EpiRegs<BN> er;                                              // constants / LN statistics of a tile, loaded one tile ahead
       [[maybe_unused]] LnStatRegs sr;
       if (cluster_id < num_tiles) {
-        load_epi_consts<BN, kLn>(er, p, tid, ((cluster_id) / p.num_n_tiles) * (2 * kBM) + rank * kBM, ((cluster_id) % p.num_n_tiles) * BN);
+        if (tid < kNumEpiThreads)
+          load_epi_consts<BN, kLn>(er, p, tid, ((cluster_id) / p.num_n_tiles) * (2 * kBM) + rank * kBM, ((cluster_id) % p.num_n_tiles) * BN);
         if constexpr (kLn) load_ln_stats(sr, p, ((cluster_id) / p.num_n_tiles) * (2 * kBM) + rank * kBM + q * 32 + lane);
       }
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++titer) {
@@ -208,13 +216,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int n0 = (tile % p.num_n_tiles) * BN;
         const int nch = chunks_of_tile<BN>(p, n0);
         EpiConst* cb = consts + (titer & 1);
-        store_epi_consts<BN>(cb, er, tid);
+        if (tid < kNumEpiThreads) store_epi_consts<BN>(cb, er, tid);
         [[maybe_unused]] float2 ln = make_float2(1.f, 0.f);
         if constexpr (kLn) ln = ln_row_coeffs(p, sr);
-        named_bar_sync(2, kNumEpiThreads);
-        if (tile + num_clusters < num_tiles) {                               // next tile's loads: in flight during this tile's chunks
+        named_bar_sync(2, 32 * kEpiWarps);
+        if (tile + num_clusters < num_tiles) {                     // next tile's loads: in flight during this tile's chunks
           const int nt_ = tile + num_clusters;
-          load_epi_consts<BN, kLn>(er, p, tid, (nt_ / p.num_n_tiles) * (2 * kBM) + rank * kBM, (nt_ % p.num_n_tiles) * BN);
+          if (tid < kNumEpiThreads)
+            load_epi_consts<BN, kLn>(er, p, tid, (nt_ / p.num_n_tiles) * (2 * kBM) + rank * kBM, (nt_ % p.num_n_tiles) * BN);
           if constexpr (kLn) load_ln_stats(sr, p, (nt_ / p.num_n_tiles) * (2 * kBM) + rank * kBM + q * 32 + lane);
         }
         [[maybe_unused]] const bool second = q * 32 + lane >= cb->row_split;
@@ -236,17 +245,18 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           tc_fence_before();
           mbar_arrive_cluster(&tempty_bar[as], 0);       // the leader's MMA thread owns the accumulator hand-off
         };
+        // software pipeline: the TMEM load of this warp's next chunk is in flight while the current one is processed
         uint32_t va[32], vb[32];
-        tmem_ld_32x32b_x32_nowait(t_acc, va);
+        if (half < nch) tmem_ld_32x32b_x32_nowait(t_acc + half * 32, va); else release_acc();
 #pragma unroll 1
-        for (int cc = 0; cc < nch; cc += 2) {
+        for (int cc = half; cc < nch; cc += 2 * kStep) {
           tmem_ld_wait_x32(va);
-          if (cc + 1 < nch) tmem_ld_32x32b_x32_nowait(t_acc + (cc + 1) * 32, vb); else release_acc();
+          if (cc + kStep < nch) tmem_ld_32x32b_x32_nowait(t_acc + (cc + kStep) * 32, vb); else release_acc();
           process(va, cc);
-          if (cc + 1 < nch) {
+          if (cc + kStep < nch) {
             tmem_ld_wait_x32(vb);
-            if (cc + 2 < nch) tmem_ld_32x32b_x32_nowait(t_acc + (cc + 2) * 32, va); else release_acc();
-            process(vb, cc + 1);
+            if (cc + 2 * kStep < nch) tmem_ld_32x32b_x32_nowait(t_acc + (cc + 2 * kStep) * 32, va); else release_acc();
+            process(vb, cc + kStep);
           }
         }
         as ^= 1;
@@ -263,7 +273,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
 }
 
-template <int BN, int EPI, typename OutT, bool kTmaRes = false>
+template <int BN, int EPI, typename OutT, bool kTmaRes = false, int kEpiWarps = 4>
 static int launch_gemm2(const PxaGemmArgs& a, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN, kTmaRes>;
   CUtensorMap ta, tw;
@@ -318,33 +328,40 @@ static int launch_gemm2(const PxaGemmArgs& a, cudaStream_t stream) {
   p.k_splits = 1;
   p.aux_branch = a.aux_is_branch;
   fill_ln_params(p, a);
-  auto kern = gemm2_bf16_kernel<BN, EPI, OutT, kTmaRes>;
+  auto kern = gemm2_bf16_kernel<BN, EPI, OutT, kTmaRes, kEpiWarps>;
   PXA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
   int clusters = device_info().sms / 2;
   if (a.max_ctas > 0 && a.max_ctas / 2 < clusters) clusters = a.max_ctas / 2 > 0 ? a.max_ctas / 2 : 1;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   if (tiles < clusters) clusters = tiles;
-  kern<<<2 * clusters, kGemmThreads, Cfg::kSmem, stream>>>(ta, tw, tr, to, tx, p);
+  kern<<<2 * clusters, 128 + 32 * kEpiWarps, Cfg::kSmem, stream>>>(ta, tw, tr, to, tx, p);
   launch_counter()++;
   PXA_CHECK_CUDA(cudaGetLastError());
   return PXA_OK;
+}
+
+// bf16 epilogues: 8 epilogue warps unless the caller asks for 4 (PxaGemmArgs.epi_warps; A/B measurements)
+template <int BN, int EPI>
+static int launch_gemm2_bf16(const PxaGemmArgs& a, cudaStream_t s) {
+  if (a.epi_warps == 4) return launch_gemm2<BN, EPI, __nv_bfloat16, false, 4>(a, s);
+  return launch_gemm2<BN, EPI, __nv_bfloat16, false, 8>(a, s);
 }
 
 template <int BN>
 static int dispatch_epi2(const PxaGemmArgs& a, cudaStream_t s) {
   switch (a.epilogue) {
     case PXA_EPI_BIAS:
-      return launch_gemm2<BN, PXA_EPI_BIAS, __nv_bfloat16>(a, s);
+      return launch_gemm2_bf16<BN, PXA_EPI_BIAS>(a, s);
     case PXA_EPI_BIAS_GELU:
-      return launch_gemm2<BN, PXA_EPI_BIAS_GELU, __nv_bfloat16>(a, s);
+      return launch_gemm2_bf16<BN, PXA_EPI_BIAS_GELU>(a, s);
     case PXA_EPI_BIAS_GELU_AUX:
-      return launch_gemm2<BN, PXA_EPI_BIAS_GELU_AUX, __nv_bfloat16>(a, s);
+      return launch_gemm2_bf16<BN, PXA_EPI_BIAS_GELU_AUX>(a, s);
     case PXA_EPI_MUL_DGELU:
-      return launch_gemm2<BN, PXA_EPI_MUL_DGELU, __nv_bfloat16>(a, s);
+      return launch_gemm2_bf16<BN, PXA_EPI_MUL_DGELU>(a, s);
     case PXA_EPI_LN_BIAS:
-      return launch_gemm2<BN, PXA_EPI_LN_BIAS, __nv_bfloat16>(a, s);
+      return launch_gemm2_bf16<BN, PXA_EPI_LN_BIAS>(a, s);
     case PXA_EPI_LN_BIAS_GELU:
-      return launch_gemm2<BN, PXA_EPI_LN_BIAS_GELU, __nv_bfloat16>(a, s);
+      return launch_gemm2_bf16<BN, PXA_EPI_LN_BIAS_GELU>(a, s);
     case PXA_EPI_BIAS_RESIDUAL:
       if (a.out_dtype == PXA_DTYPE_F32) {
         // the TMA-streamed epilogue is required for the fused LayerNorm by-products (scaled aux copy, row statistics)

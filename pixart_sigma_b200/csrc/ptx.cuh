@@ -409,6 +409,39 @@ PXA_DEVICE uint64_t poly_exp2_x2(uint64_t x) {
   return f32x2(__int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23)),
                __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23)));
 }
+// ---- exp2 on the FMA pipe (round 2): see tools/micro/exp_mix.cu for the derivation and the measurements.
+// z = fma.rn.sat(s, -scale/128, (8 - nm)/128) in [0, 1] encodes x' = clamp(x - 8, -128, 0) = -128 z for x = s*scale + nm <= 8
+// (the clamp rides on FFMA.SAT for free); floor / fraction by the round-down magic-number add, 2^frac as a degree-3
+// polynomial (max rel. error 8.8e-5, far below the bf16 rounding of P), exponent inserted with one LEA.  Everything else
+// is on the FMA pipe (6 packed FFMA2 / FADD2 per PAIR): no MUFU, and -- unlike round 1's poly_exp2 -- no ALU-pipe range
+// reduction (2 FMNMX + SHL + IADD per element were as expensive as the MUFU.EX2 they replaced).
+PXA_DEVICE float fma_sat(float a, float b, float c) {
+  float r;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;\n" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+PXA_DEVICE uint64_t fma2_rm(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rm.f32x2 %0, %1, %2, %3;\n" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+constexpr float kExpMagic = 12582912.0f + 8.0f;     // 1.5 * 2^23 + 8: floor(x') + 8 lands in the low mantissa bits
+// (e0, e1) = 2^(s0*scale + nm), 2^(s1*scale + nm) given a_sat = -scale/128, b_sat = (8 - nm)/128; results in [2^-120, 2^8].
+PXA_DEVICE void fma_exp2_x2(float s0, float s1, float a_sat, float b_sat, float& e0, float& e1) {
+  const uint64_t z = f32x2(fma_sat(s0, a_sat, b_sat), fma_sat(s1, a_sat, b_sat));
+  const uint64_t m128 = f32x2(-128.0f, -128.0f), mg = f32x2(kExpMagic, kExpMagic);
+  const uint64_t r = fma2_rm(z, m128, mg);
+  const uint64_t f = fma2(z, m128, sub2(mg, r));
+  uint64_t p = fma2(f32x2(0.077119089663028717041015625f, 0.077119089663028717041015625f), f,
+                    f32x2(0.227564394474029541015625f, 0.227564394474029541015625f));
+  p = fma2(p, f, f32x2(0.695146143436431884765625f, 0.695146143436431884765625f));
+  p = fma2(p, f, f32x2(1.0f, 1.0f));
+  float p0, p1, r0, r1;
+  f32x2_split(p, p0, p1);
+  f32x2_split(r, r0, r1);
+  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
+}
 PXA_DEVICE float fast_tanh(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;\n" : "=f"(y) : "f"(x));

@@ -36,7 +36,7 @@ class GemmArgs(C.Structure):
                 ("k_splits", C.c_int32), ("aux_is_branch", C.c_int32),
                 ("aux_scale", C.c_void_p), ("aux_scale_batch_stride", C.c_int64), ("row_stats_out", C.c_void_p),
                 ("ln_stats", C.c_void_p), ("ln_u", C.c_void_p), ("ln_v", C.c_void_p), ("ln_uv_batch_stride", C.c_int64),
-                ("ln_dim", C.c_int32), ("ln_eps", C.c_float), ("res_epilogue", C.c_int32)]
+                ("ln_dim", C.c_int32), ("ln_eps", C.c_float), ("res_epilogue", C.c_int32), ("epi_warps", C.c_int32)]
 
 
 class LnPrepareArgs(C.Structure):
@@ -115,7 +115,7 @@ EXPORTS = ("pxa_transpose_bf16", "pxa_gelu_tanh_bf16", "pxa_gate_residual_fwd", 
            "pxa_ln_modulate_bwd", "pxa_colsum_bf16", "pxa_attn_delta_d72", "pxa_flash_attn_d72_bwd_bf16", "pxa_kv_compress_conv2_ln_bwd",
            "pxa_version", "pxa_last_error", "pxa_launch_count", "pxa_gemm_bf16", "pxa_ln_modulate",
            "pxa_flash_attn_d72_bf16", "pxa_kv_compress_conv2_ln", "pxa_conv3x3_nhwc_bf16", "pxa_dpm_solver_pp_step",
-           "pxa_ln_prepare", "pxa_layernorm_affine_bf16")
+           "pxa_ln_prepare", "pxa_layernorm_affine_bf16", "pxa_groupnorm_silu_nhwc_bf16")
 
 _lib = None
 
@@ -146,6 +146,9 @@ def load() -> C.CDLL:
         lib.pxa_layernorm_affine_bf16.restype = C.c_int
         lib.pxa_layernorm_affine_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_float,
                                                   C.c_void_p]
+        lib.pxa_groupnorm_silu_nhwc_bf16.restype = C.c_int
+        lib.pxa_groupnorm_silu_nhwc_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                                     C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_void_p]
         lib.pxa_transpose_bf16.restype = C.c_int
         lib.pxa_transpose_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p]
         lib.pxa_gelu_tanh_bf16.restype = C.c_int
@@ -191,7 +194,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
          aux_is_branch: bool = False, aux_scale: Optional[torch.Tensor] = None, aux_scale_batch_stride: int = 0,
          row_stats_out: Optional[torch.Tensor] = None, ln_stats: Optional[torch.Tensor] = None,
          ln_u: Optional[torch.Tensor] = None, ln_v: Optional[torch.Tensor] = None, ln_uv_batch_stride: int = 0,
-         ln_dim: int = 0, ln_eps: float = 1e-6, res_epilogue: int = 0) -> torch.Tensor:
+         ln_dim: int = 0, ln_eps: float = 1e-6, res_epilogue: int = 0, epi_warps: int = 0) -> torch.Tensor:
     """out = epilogue(a @ w.T + bias). a (M,K) bf16, w (N,K) bf16 (nn.Linear layout), both K-contiguous.
 
     Fused LayerNorm-modulate (include/pixart_sm100.h, PXA_EPI_LN_BIAS): the fp32 residual epilogue can emit the scaled bf16
@@ -221,7 +224,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
                     cta_pair=cta_pair, debug_trace=_ptr(debug_trace), operands_mn_major=0, k_splits=0,
                     aux_is_branch=int(aux_is_branch), aux_scale=_ptr(aux_scale), aux_scale_batch_stride=aux_scale_batch_stride,
                     row_stats_out=_ptr(row_stats_out), ln_stats=_ptr(ln_stats), ln_u=_ptr(ln_u), ln_v=_ptr(ln_v),
-                    ln_uv_batch_stride=ln_uv_batch_stride, ln_dim=ln_dim, ln_eps=ln_eps, res_epilogue=res_epilogue)
+                    ln_uv_batch_stride=ln_uv_batch_stride, ln_dim=ln_dim, ln_eps=ln_eps, res_epilogue=res_epilogue,
+                    epi_warps=epi_warps)
     _check(load().pxa_gemm_bf16(C.byref(args), _stream()), "pxa_gemm_bf16")
     return out
 
@@ -302,6 +306,20 @@ def conv3x3_nhwc(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.T
     args = Conv3x3Args(x=_ptr(x), w=_ptr(w_packed), bias=_ptr(bias), out=_ptr(out), residual=_ptr(residual), B=B, H=H, W=W,
                        Cin=Cin, Cout=Cout)
     _check(load().pxa_conv3x3_nhwc_bf16(C.byref(args), _stream()), "pxa_conv3x3_nhwc_bf16")
+    return out
+
+
+def groupnorm_silu_nhwc(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, *, groups: int = 32,
+                        eps: float = 1e-6, silu: bool = True, stats_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm (+ SiLU) on an NHWC bf16 image x (B, H, W, C) -> out (same shape); statistics in fp32."""
+    assert x.dtype == out.dtype == gamma.dtype == beta.dtype == torch.bfloat16 and x.is_contiguous() and out.is_contiguous()
+    B, H, W, Cc = x.shape
+    assert out.shape == x.shape and gamma.numel() == beta.numel() == Cc and gamma.is_contiguous() and beta.is_contiguous()
+    if stats_ws is None:
+        stats_ws = torch.empty(B * groups * 2, dtype=torch.float32, device=x.device)
+    assert stats_ws.dtype == torch.float32 and stats_ws.numel() >= B * groups * 2
+    _check(load().pxa_groupnorm_silu_nhwc_bf16(_ptr(x), _ptr(out), _ptr(gamma), _ptr(beta), _ptr(stats_ws), B, H * W, Cc, groups,
+                                               eps, int(silu), _stream()), "pxa_groupnorm_silu_nhwc_bf16")
     return out
 
 

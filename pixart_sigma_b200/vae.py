@@ -4,7 +4,8 @@ The reference decodes latents with diffusers' `AutoencoderKL` (scripts/inference
 vendored in the reference and not installed here, so this module mirrors the public `ResnetBlock2D` of the SDXL-VAE
 decoder -- parameter names `norm1, conv1, norm2, conv2, conv_shortcut`, GroupNorm(32, eps 1e-6) -> SiLU -> Conv3x3 twice,
 1x1 shortcut when the channel count changes -- with both 3x3 convolutions (68 % of the decoder FLOPs) on
-`pxa_conv3x3_nhwc_bf16`.  GroupNorm + SiLU stay PyTorch, as the north_star scopes it.
+`pxa_conv3x3_nhwc_bf16` and GroupNorm + SiLU in front of each as one NHWC kernel pair (`pxa_groupnorm_silu_nhwc_bf16`:
+statistics, apply), so a block is 2 convolutions + 2 x 2 light passes with no layout copies in between.
 """
 from __future__ import annotations
 
@@ -44,15 +45,14 @@ class DecoderResBlock(nn.Module):
         if not x.is_cuda or self.conv1.weight.dtype != torch.bfloat16:
             raise RuntimeError("DecoderResBlock runs on the sm_100a kernels only: CUDA tensors and bf16 weights required")
         B, Cc, H, W = x.shape
-        x = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        x = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)     # no copy when the caller already is NHWC
         x_nhwc = x.permute(0, 2, 3, 1)                                          # contiguous (B, H, W, C) view
-        h = F.silu(F.group_norm(x, self.norm1.num_groups, self.norm1.weight, self.norm1.bias, self.norm1.eps))
-        h = h.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
+        h = lib.groupnorm_silu_nhwc(x_nhwc, self.norm1.weight, self.norm1.bias, torch.empty_like(x_nhwc),
+                                    groups=self.norm1.num_groups, eps=self.norm1.eps)
         h1 = torch.empty(B, H, W, self.out_channels, dtype=torch.bfloat16, device=x.device)
         lib.conv3x3_nhwc(h, self._pack(self.conv1), self.conv1.bias, h1)
-        h1c = h1.permute(0, 3, 1, 2)                                            # NCHW logical view, channels_last memory
-        h2 = F.silu(F.group_norm(h1c, self.norm2.num_groups, self.norm2.weight, self.norm2.bias, self.norm2.eps))
-        h2 = h2.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
+        h2 = lib.groupnorm_silu_nhwc(h1, self.norm2.weight, self.norm2.bias, torch.empty_like(h1),
+                                     groups=self.norm2.num_groups, eps=self.norm2.eps)
         if self.conv_shortcut is not None:
             sc = torch.empty(B * H * W, self.out_channels, dtype=torch.bfloat16, device=x.device)
             lib.gemm(x_nhwc.reshape(B * H * W, Cc), self.conv_shortcut.weight.view(self.out_channels, Cc),

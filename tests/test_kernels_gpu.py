@@ -41,11 +41,13 @@ def test_gemm_bias_bf16(M, N, K, bn):
 @pytest.mark.parametrize("M,N,K,bn", [(256, 192, 64, 192), (512, 384, 1152, 192), (1000, 1152, 1152, 192),
                                       (4096, 3456, 1152, 192), (300, 2304, 1152, 0), (640, 4608, 1152, 256),
                                       (384, 256, 128, 128), (200, 200, 200, 192)])
-def test_gemm_cta_pair_bias_bf16(M, N, K, bn):
-    """CTA-pair (tcgen05.mma.cta_group::2, 256 x BN tiles) variant of the same GEMM."""
+@pytest.mark.parametrize("epi_warps", [8, 4])
+def test_gemm_cta_pair_bias_bf16(M, N, K, bn, epi_warps):
+    """CTA-pair (tcgen05.mma.cta_group::2, 256 x BN tiles) variant of the same GEMM, with two (default) or one epilogue
+    warp per TMEM lane quarter."""
     a, w, bias = _randn(M, K, seed=1), _randn(N, K, seed=2, scale=K ** -0.5), _randn(N, seed=3, scale=0.1)
     out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV)
-    lib.gemm(a, w, bias, out, epilogue=lib.EPI_BIAS, block_n=bn, cta_pair=2)
+    lib.gemm(a, w, bias, out, epilogue=lib.EPI_BIAS, block_n=bn, cta_pair=2, epi_warps=epi_warps)
     want = F.linear(a.float(), w.float(), bias.float())
     assert po.rel_err(out.float(), want) < 4e-3
 

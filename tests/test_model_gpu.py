@@ -198,3 +198,30 @@ def test_cuda_graph_replay_equals_eager():
         assert torch.equal(got, eager)
         outs.append(got)
     assert not torch.equal(outs[0], outs[1])
+
+
+def test_fp16_checkpoint_is_cast_to_bf16_once_and_keeps_fp16_io():
+    """scripts/inference.py:161 loads the model as fp16 (`weight_dtype = torch.float16`): the first forward casts the
+    parameters to bf16 in place (with a warning), later calls are silent, outputs stay fp16."""
+    import warnings
+    cfg = po.OracleConfig(depth=2, input_size=32, pe_interpolation=0.5)
+    sd = po.synthetic_state_dict(cfg, seed=1)
+    x, t, y, mask = po.synthetic_inputs(cfg, 2, (32, 32), lens=[300, 20])
+    ref = _build(cfg, sd)
+    with torch.no_grad():
+        want = ref(x.cuda(), t.cuda(), y.cuda(), mask=mask.cuda()).float()
+    with torch.device("cuda"):
+        m = PixArtMS(depth=2, input_size=32, pe_interpolation=0.5, model_max_length=300)
+    m.load_state_dict(sd, strict=False)
+    m = m.half().eval()
+    with torch.no_grad(), warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        got = m(x.cuda().half(), t.cuda(), y.cuda().half(), mask=mask.cuda())
+        assert any("fp16 parameters cast to bf16" in str(w.message) for w in rec)
+    assert got.dtype == torch.float16 and m.dtype == torch.bfloat16
+    with torch.no_grad(), warnings.catch_warnings(record=True) as rec2:
+        warnings.simplefilter("always")
+        got2 = m(x.cuda().half(), t.cuda(), y.cuda().half(), mask=mask.cuda())
+        assert not rec2
+    assert torch.equal(got, got2)
+    assert po.rel_err(got.float(), want) < 1e-2        # fp16-rounded inputs / output on top of the bf16 model

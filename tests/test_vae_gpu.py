@@ -36,6 +36,20 @@ def test_conv3x3_matches_torch(B, H, W, Cin, Cout, with_res):
     assert po.rel_err(out.float(), want) < 4e-3
 
 
+@pytest.mark.parametrize("B,H,W,Cc,silu", [(2, 32, 32, 128, True), (1, 64, 48, 256, True), (3, 16, 16, 512, False),
+                                            (1, 5, 7, 64, True)])
+def test_groupnorm_silu_nhwc_matches_torch(B, H, W, Cc, silu):
+    x = (_rand(B, H, W, Cc, seed=7).float() * 2 + 0.5).to(torch.bfloat16).cuda()
+    gamma = (1 + _rand(Cc, seed=8, scale=0.1).float()).to(torch.bfloat16).cuda()
+    beta = _rand(Cc, seed=9, scale=0.1).cuda()
+    out = torch.full_like(x, float("nan"))
+    lib.groupnorm_silu_nhwc(x, gamma, beta, out, groups=32, eps=1e-6, silu=silu)
+    want = F.group_norm(x.float().permute(0, 3, 1, 2), 32, gamma.float(), beta.float(), 1e-6)
+    want = (F.silu(want) if silu else want).permute(0, 2, 3, 1)
+    assert torch.isfinite(out.float()).all()
+    assert po.rel_err(out.float(), want) < 4e-3
+
+
 @pytest.mark.parametrize("Cin,Cout,H,W", [(128, 128, 64, 64), (256, 128, 32, 128), (512, 512, 16, 16)])
 def test_decoder_resblock_matches_oracle(Cin, Cout, H, W):
     torch.manual_seed(0)

@@ -45,7 +45,7 @@ def resid(K, pair, res_epi, aux, byprod, bn=0, gate=True):
     return ms, 2.0 * M * N * K / ms / 1e9
 
 
-def plain(N, K, epi, ln):
+def plain(N, K, epi, ln, epi_warps=0):
     a = torch.randn(M, K, device=dev).to(torch.bfloat16)
     w = (torch.randn(N, K, device=dev) * K ** -0.5).to(torch.bfloat16)
     b = torch.randn(N, device=dev).to(torch.bfloat16)
@@ -55,9 +55,9 @@ def plain(N, K, epi, ln):
         st[:, :, 1] += 1000.0
         u, v = torch.randn(8, N, device=dev), torch.randn(8, N, device=dev)
         fn = lambda: lib.gemm(a, w, None, out, epilogue=epi, rows_per_batch=RPB, ln_stats=st, ln_u=u, ln_v=v,
-                              ln_uv_batch_stride=N, ln_dim=K)
+                              ln_uv_batch_stride=N, ln_dim=K, epi_warps=epi_warps)
     else:
-        fn = lambda: lib.gemm(a, w, b, out, epilogue=epi)
+        fn = lambda: lib.gemm(a, w, b, out, epilogue=epi, epi_warps=epi_warps)
     ms = timeit(fn)
     return ms, 2.0 * M * N * K / ms / 1e9
 
@@ -81,5 +81,10 @@ for K in (1152, 4608):
 print("== bias / GELU GEMMs vs their fused-LayerNorm forms, K = 1152")
 for N, e0, e1 in ((3456, lib.EPI_BIAS, lib.EPI_LN_BIAS), (4608, lib.EPI_BIAS_GELU, lib.EPI_LN_BIAS_GELU)):
     for ln, epi in ((False, e0), (True, e1)):
-        ms, tf = plain(N, 1152, epi, ln)
-        print(f"N={N} {'LN-fused epilogue' if ln else 'plain epilogue   '}: {ms * 1e3:8.1f} us {tf:7.1f} TF", flush=True)
+        for ew in (4, 8):
+            ms, tf = plain(N, 1152, epi, ln, ew)
+            print(f"N={N} {'LN-fused epilogue' if ln else 'plain epilogue   '} {ew} epilogue warps: {ms * 1e3:8.1f} us {tf:7.1f} TF", flush=True)
+for N in (1152, 2304):
+    for ew in (4, 8):
+        ms, tf = plain(N, 1152, lib.EPI_BIAS, False, ew)
+        print(f"N={N} plain epilogue    {ew} epilogue warps: {ms * 1e3:8.1f} us {tf:7.1f} TF", flush=True)
