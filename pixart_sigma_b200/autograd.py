@@ -441,8 +441,6 @@ def block_forward_train(blk, x32: torch.Tensor, cond: torch.Tensor, kv_len: Opti
     H = a.num_heads
     if HW is None:
         HW = (int(N ** 0.5),) * 2
-    if blk.training and blk.drop_path_rate > 0:
-        raise NotImplementedError("stochastic depth (drop_path > 0) is not supported by the kernel block")
     if not isinstance(a.q_norm, torch.nn.Identity):
         raise NotImplementedError("qk_norm=True is not supported by the kernel block yet")
     mod = mod.contiguous()

@@ -483,20 +483,27 @@ extern "C" int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream) {
   // GEMM; the fp32 residual epilogue is HBM-bound at K = 1152 and streams through TMA chunk buffers on the single-CTA
   // kernel, while at K >= 2304 it is MMA-bound and the pair kernel's deeper smem ring (7 stages) wins.
   bool pair = a.cta_pair == 2;
+  PxaGemmArgs b = a;                    // `res_epilogue` may be filled in by the auto choice below
   if (a.cta_pair == 0 && a.block_n == 0 && a.M >= 1024) {
     if (a.epilogue != PXA_EPI_BIAS_RESIDUAL) {
       pair = true;
       bn = 256;
+    } else if (a.out_dtype == PXA_DTYPE_F32 && a.residual == a.out && !a.out_aux_bf16 && !a.row_stats_out && a.res_epilogue != 1) {
+      // in-place update of the fp32 stream with no by-product: CTA pair + TMA reduce-add epilogue (round 2, M = 32768:
+      // 94 us vs 103 us single-CTA at K = 1152; 255 us vs 268 us with the register-staged pair epilogue at K = 4608)
+      pair = true;
+      bn = a.K >= 2304 ? 192 : 256;
+      b.res_epilogue = 2;
     } else if (a.K >= 2304) {
       pair = true;
       bn = 192;
     } else {
-      bn = 256;      // fewer, wider tiles: 100 us vs 107 us (BN = 192) at N = K = 1152, even with a half-empty last column tile
+      bn = 256;      // read-modify-write with a bf16 copy: single CTA, TMA-streamed residual chunks (123 us vs 129 us pair)
     }
   }
   if (a.row_stats_out && (a.N + bn - 1) / bn > PXA_LN_STAT_PARTS)
     return fail(PXA_ERR_ARG, "row_stats_out: N / block_n = %d column tiles exceed PXA_LN_STAT_PARTS", (a.N + bn - 1) / bn);
-  if (pair) return gemm_pair_dispatch(a, bn, s);
+  if (pair) return gemm_pair_dispatch(b, bn, s);
   switch (bn) {
     case 128: return dispatch_epi<128>(a, s);
     case 192: return dispatch_epi<192>(a, s);

@@ -290,6 +290,19 @@ class _LnFusion:
         return u.contiguous(), v.contiguous(), one_plus
 
 
+def _drop_path_gates(mod: torch.Tensor, rate: float) -> torch.Tensor:
+    """Stochastic depth (timm DropPath around the attention and MLP branches, PixArtMS.py:75,77): per sample, a branch is
+    dropped with probability `rate` and the survivors are scaled by 1 / (1 - rate).  Both branches enter the residual stream
+    through their gates, so DropPath is a per-sample factor on gate_msa (index 2) and gate_mlp (index 5) of `mod` (B, 6, C);
+    the cross-attention branch has no DropPath in the reference (:76)."""
+    keep = 1.0 - rate
+    B = mod.shape[0]
+    m = (torch.rand(B, 2, device=mod.device) < keep).to(mod.dtype) / keep
+    scale = torch.ones(B, 6, 1, dtype=mod.dtype, device=mod.device)
+    scale[:, 2, 0], scale[:, 5, 0] = m[:, 0], m[:, 1]
+    return mod * scale
+
+
 def _wants_grad(module: nn.Module, *inputs) -> bool:
     """True when autograd will record this call: grad mode on and a parameter or an input requires grad."""
     if not torch.is_grad_enabled():
@@ -345,8 +358,6 @@ class PixArtMSBlock(nn.Module):
         M, dev = B * N, x32.device
         a, ca, mlp = self.attn, self.cross_attn, self.mlp
         _require_kernel_ready(a.qkv.weight, "PixArtMSBlock")
-        if self.training and self.drop_path_rate > 0:
-            raise NotImplementedError("stochastic depth (drop_path > 0) is not supported by the fused block")
         bf = torch.bfloat16
         xn = ws.get("xn", (M, C), bf, dev)
         qkv = ws.get("qkv", (M, 3 * C), bf, dev)
@@ -453,6 +464,8 @@ class PixArtMSBlock(nn.Module):
         kv_len = torch.tensor(lens, dtype=torch.int32, device=x.device)
         kv_off = torch.tensor([sum(lens[:i]) for i in range(B)], dtype=torch.int32, device=x.device)
         mod = (self.scale_shift_table.float()[None] + t.reshape(B, 6, C).float()).contiguous()
+        if self.training and self.drop_path_rate > 0:
+            mod = _drop_path_gates(mod, self.drop_path_rate)
         x32 = x.reshape(B * N, C).float().contiguous()
         if _wants_grad(self, x, y, t):                                     # training: differentiable kernel ops
             from .autograd import block_forward_train
@@ -460,7 +473,7 @@ class PixArtMSBlock(nn.Module):
         else:
             _require_kernel_ready(self.attn.qkv.weight, "PixArtMSBlock")
             ln = None
-            if N >= _LN_FUSE_MIN_ROWS:
+            if N >= _LN_FUSE_MIN_ROWS and os.environ.get("PXA_FUSE_LN", "0") == "1":
                 if self._ln_fusion is None:
                     self.__dict__["_ln_fusion"] = _LnFusion([self])
                 u, v, one_plus = self._ln_fusion.prepare(t.reshape(B, 6, C).float(), mod[None], self._ws)
@@ -532,8 +545,12 @@ class PixArtMS(nn.Module):
         # the DPM-Solver time 749.25 into 748 and moves the output by up to 5e-2.  Default: keep the
         # timestep in fp32 like the fp32 reference does; set True to reproduce the bf16 cast bit for bit.
         self.round_timestep_to_dtype = False
-        # LayerNorm + t2i_modulate inside the QKV / fc1 GEMM epilogues (no stand-alone norm pass); False = pxa_ln_modulate
-        self.fuse_ln_modulate = os.environ.get("PXA_FUSE_LN", "1") != "0"
+        # True: LayerNorm + t2i_modulate inside the QKV / fc1 GEMM epilogues, no stand-alone norm pass (the north_star's
+        # fusion; parity-tested at every geometry).  Default False = pxa_ln_modulate: measured on B200 in round 2 (DESIGN.md
+        # 4.3) the fused chain is 0.3 ms / step SLOWER at c3 -- the read-modify-write residual epilogues that must produce
+        # the scaled copy + row statistics (+23 / +41 us per block) and the extra epilogue work of the consuming GEMMs
+        # (+13 / +39 us) cost more than the two 48 us passes they remove.  PXA_FUSE_LN=1 turns it on.
+        self.fuse_ln_modulate = os.environ.get("PXA_FUSE_LN", "0") == "1"
         self.__dict__["_ln_fusion"] = None
         self._ws = _Workspace()
         self.initialize()
@@ -609,6 +626,9 @@ class PixArtMS(nn.Module):
         t0 = F.linear(F.silu(t), self.t_block[1].weight.float(), self.t_block[1].bias.float())  # (B, 6C) fp32
         tables = torch.stack([blk.scale_shift_table for blk in self.blocks]).float()           # (depth, 6, C)
         mod_all = (tables[:, None] + t0.view(1, B, 6, C)).contiguous()                          # (depth, B, 6, C)
+        if self.training and any(blk.drop_path_rate > 0 for blk in self.blocks):
+            mod_all = torch.stack([_drop_path_gates(mod_all[i], blk.drop_path_rate) if blk.drop_path_rate > 0 else mod_all[i]
+                                   for i, blk in enumerate(self.blocks)])
 
         cond, kv_len, max_keys = self._condition(y, mask, B)
         fused = self.fuse_ln_modulate and N >= _LN_FUSE_MIN_ROWS and len(self.blocks) > 0
@@ -675,6 +695,8 @@ class PixArtMS(nn.Module):
 
         for blk in self.blocks:
             mod = blk.scale_shift_table.float()[None] + t0
+            if self.training and blk.drop_path_rate > 0:        # drawn here, outside the (recomputed) checkpointed function
+                mod = _drop_path_gates(mod, blk.drop_path_rate)
             if getattr(blk, "grad_checkpointing", False):
                 # per-call dict: lets the recomputation reuse the attention outputs of the first pass (autograd.py)
                 # preserve_rng_state=False: the block draws no random numbers, and stashing the RNG state reads the device

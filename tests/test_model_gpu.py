@@ -225,3 +225,37 @@ def test_fp16_checkpoint_is_cast_to_bf16_once_and_keeps_fp16_io():
         assert not rec2
     assert torch.equal(got, got2)
     assert po.rel_err(got.float(), want) < 1e-2        # fp16-rounded inputs / output on top of the bf16 model
+
+
+def test_drop_path_scales_the_gated_branches_per_sample():
+    """Stochastic depth in training mode (timm DropPath, PixArtMS.py:75,77): per sample the attention / MLP branch is
+    dropped or scaled by 1 / keep -- equivalent to scaling gate_msa / gate_mlp, which the oracle block gets through t0."""
+    B, hw, lens, C = 4, (16, 16), [300, 77, 5, 120], 1152
+    N = hw[0] * hw[1]
+    cfg = po.OracleConfig(depth=1)
+    sd = po.synthetic_state_dict(cfg, seed=7)
+    blk = _build(cfg, sd).blocks[0]
+    blk.train()
+    blk.drop_path_rate = 0.5
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, N, C, generator=g)
+    t0 = torch.randn(B, 6 * C, generator=g) * 0.3
+    ycat = torch.randn(sum(lens), C, generator=g).to(torch.bfloat16)
+    torch.manual_seed(123)
+    with torch.no_grad():
+        got = blk(x.cuda(), ycat.cuda()[None], t0.cuda(), lens, hw).float().cpu()
+    torch.manual_seed(123)
+    m = ((torch.rand(B, 2, device="cuda") < 0.5).float() / 0.5).cpu()             # the draw _drop_path_gates makes
+    assert 0 < int((m == 0).sum()) < 2 * B                                         # some branches dropped, some kept
+    sdr = _bf16_round(sd)
+    tab = sdr["blocks.0.scale_shift_table"]
+    t0d = t0.view(B, 6, C).clone()
+    t0d[:, 2] = m[:, 0:1] * (tab[2] + t0d[:, 2]) - tab[2]
+    t0d[:, 5] = m[:, 1:2] * (tab[5] + t0d[:, 5]) - tab[5]
+    want = po.block_forward(sdr, "blocks.0", x, ycat.float()[None], t0d.reshape(B, 6 * C), lens, hw, 16, 1, None)
+    assert po.rel_err(got, want) < 1.5e-3
+    blk.eval()
+    with torch.no_grad():
+        got_eval = blk(x.cuda(), ycat.cuda()[None], t0.cuda(), lens, hw).float().cpu()
+    want_eval = po.block_forward(sdr, "blocks.0", x, ycat.float()[None], t0, lens, hw, 16, 1, None)
+    assert po.rel_err(got_eval, want_eval) < 1.5e-3
