@@ -183,6 +183,8 @@ typedef struct PxaAttnArgs {
   int64_t* debug_trace; /* NULL in production. Else device int64[16 warps + 2][kTraceMax] cycle stamps of CTA (0,0,0) */
   float* lse;       /* optional fp32 [B, H, Nq]: log2-domain log-sum-exp of the scaled scores, the softmax statistic the
                        backward pass recomputes P from (training); NULL for inference                              */
+  int32_t variant;  /* 0 = auto, 2 = two 128-row query tiles per CTA with a double-buffered S (attn_sm100.cu), 3 = three tiles
+                       with a single S buffer each: three softmax warps per SM sub-partition (attn3_sm100.cu)                */
 } PxaAttnArgs;
 int pxa_flash_attn_d72_bf16(const PxaAttnArgs* args, void* stream);
 

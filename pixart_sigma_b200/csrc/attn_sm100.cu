@@ -511,6 +511,8 @@ static int make_qkv_maps(CUtensorMap* main_map, CUtensorMap* tail_map, const voi
   return make_tmap_bf16(tail_map, base, 3, dims, str, box_tail, CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
+int flash_attn_d72_x3_launch(const PxaAttnArgs& a, cudaStream_t stream);   // attn3_sm100.cu
+
 }  // namespace pxa
 
 extern "C" int pxa_flash_attn_d72_bf16(const PxaAttnArgs* args, void* stream) {
@@ -525,6 +527,8 @@ extern "C" int pxa_flash_attn_d72_bf16(const PxaAttnArgs* args, void* stream) {
   if (reinterpret_cast<uintptr_t>(a.out) & 15) return fail(PXA_ERR_ALIGN, "out must be 16-byte aligned");
   if (a.H * kD > a.ldo) return fail(PXA_ERR_ARG, "ldo smaller than H*72");
   PXA_REQUIRE_SM100();
+  if (a.variant != 0 && a.variant != 2 && a.variant != 3) return fail(PXA_ERR_ARG, "variant must be 0, 2 or 3");
+  if (a.variant == 3 && !a.debug_trace) return flash_attn_d72_x3_launch(a, reinterpret_cast<cudaStream_t>(stream));
   CUtensorMap qm, qt, km, kt, vm, vt;
   int rc;
   if ((rc = make_qkv_maps(&qm, &qt, a.q, a.H, (long long)a.B * a.Nq, a.q_sn, a.q_sh))) return rc;

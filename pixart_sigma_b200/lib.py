@@ -58,7 +58,8 @@ class AttnArgs(C.Structure):
                 ("k_sn", C.c_int64), ("k_sh", C.c_int64), ("v_sn", C.c_int64), ("v_sh", C.c_int64),
                 ("kv_rows", C.c_int64),
                 ("B", C.c_int32), ("H", C.c_int32), ("Nq", C.c_int32), ("Nk", C.c_int32),
-                ("ldo", C.c_int32), ("scale", C.c_float), ("debug_trace", C.c_void_p), ("lse", C.c_void_p)]
+                ("ldo", C.c_int32), ("scale", C.c_float), ("debug_trace", C.c_void_p), ("lse", C.c_void_p),
+                ("variant", C.c_int32)]
 
 
 class KvCompressArgs(C.Structure):
@@ -257,6 +258,9 @@ def ln_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, out: 
     return out
 
 
+_ATTN_VARIANT = int(os.environ.get("PXA_ATTN_VARIANT", "0"))      # A/B switch for the attention forward (0 = library default)
+
+
 def layernorm_affine_(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
     """In-place LayerNorm with affine parameters on the rows of a bf16 (M, 1152) view with unit column stride (qk_norm)."""
     assert x.dtype == weight.dtype == bias.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
@@ -269,7 +273,8 @@ def layernorm_affine_(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
 def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, B: int, H: int, Nq: int,
                Nk: int, kv_rows: int, kv_len: Optional[torch.Tensor] = None, kv_off: Optional[torch.Tensor] = None,
                q_strides=None, k_strides=None, v_strides=None, scale: Optional[float] = None,
-               debug_trace: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None) -> torch.Tensor:
+               debug_trace: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None,
+               variant: int = 0) -> torch.Tensor:
     """Head-dim-72 attention. q/k/v are bf16 *views*; strides are (row, head) in elements, e.g. slices of the
     (rows, 3, H, 72) qkv GEMM output. out is (B*Nq, H*72) bf16."""
     assert q.dtype == k.dtype == v.dtype == out.dtype == torch.bfloat16
@@ -280,7 +285,7 @@ def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Ten
                     q_sn=q_strides[0], q_sh=q_strides[1], k_sn=k_strides[0], k_sh=k_strides[1],
                     v_sn=v_strides[0], v_sh=v_strides[1], kv_rows=kv_rows, B=B, H=H, Nq=Nq, Nk=Nk,
                     ldo=out.stride(0), scale=scale if scale is not None else 72 ** -0.5,
-                    debug_trace=_ptr(debug_trace), lse=_ptr(lse))
+                    debug_trace=_ptr(debug_trace), lse=_ptr(lse), variant=variant or _ATTN_VARIANT)
     if lse is not None:
         assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == B * H * Nq
     _check(load().pxa_flash_attn_d72_bf16(C.byref(args), _stream()), "pxa_flash_attn_d72_bf16")

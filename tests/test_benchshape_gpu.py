@@ -84,8 +84,9 @@ def test_block_at_bench_geometry_matches_oracle(name, B, hw, lens, sr, fused):
     assert max(per_sample) < 2e-3, per_sample
 
 
+@pytest.mark.parametrize("variant", [2, 3])
 @pytest.mark.parametrize("B,H,Nq,Nk", [(8, 16, 4096, 4096), (2, 16, 16384, 4096)])
-def test_flash_attn_at_bench_geometry(B, H, Nq, Nk):
+def test_flash_attn_at_bench_geometry(B, H, Nq, Nk, variant):
     g = torch.Generator().manual_seed(30)
     q = torch.randn(B, Nq, H, 72, generator=g).to(torch.bfloat16)
     k = torch.randn(B, Nk, H, 72, generator=g).to(torch.bfloat16)
@@ -94,7 +95,7 @@ def test_flash_attn_at_bench_geometry(B, H, Nq, Nk):
     lse = torch.empty(B, H, Nq, dtype=torch.float32, device="cuda")
     st = (H * 72, 72)
     lib.flash_attn(q.cuda(), k.cuda(), v.cuda(), out, B=B, H=H, Nq=Nq, Nk=Nk, kv_rows=B * Nk, q_strides=st, k_strides=st,
-                   v_strides=st, lse=lse)
+                   v_strides=st, lse=lse, variant=variant)
     got = out.float().cpu().view(B, Nq, H, 72)
     assert torch.isfinite(got).all()
     torch.set_num_threads(min(os.cpu_count() or 1, 64))
@@ -105,7 +106,7 @@ def test_flash_attn_at_bench_geometry(B, H, Nq, Nk):
         s = torch.einsum("qhd,khd->hqk", q[b, :256].float(), k[b].float()) * (72 ** -0.5)
         want_lse = torch.logsumexp(s, dim=-1) * 1.4426950408889634      # the kernel keeps log2-domain statistics
         assert po.rel_err(lse[b, :, :256].cpu(), want_lse) < 1e-4
-    _log(f"bench-geometry flash_attn B={B} H={H} Nq={Nq} Nk={Nk}: worst per-sample rel_err={worst:.3e}")
+    _log(f"bench-geometry flash_attn B={B} H={H} Nq={Nq} Nk={Nk} variant={variant}: worst per-sample rel_err={worst:.3e}")
     assert worst < 6e-3
 
 

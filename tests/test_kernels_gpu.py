@@ -297,31 +297,34 @@ def _attn_ref(q, k, v, lens):
 
 @pytest.mark.parametrize("B,H,Nq,Nk", [(1, 1, 128, 128), (1, 2, 256, 256), (2, 16, 1024, 1024), (1, 16, 1000, 1000),
                                        (2, 4, 1024, 256), (1, 3, 300, 77)])
-def test_flash_attn_self_from_qkv_layout(B, H, Nq, Nk):
+@pytest.mark.parametrize("variant", [2, 3])
+def test_flash_attn_self_from_qkv_layout(B, H, Nq, Nk, variant):
     """q/k/v are strided views of a (B*N, 3, H, 72)-style buffer exactly as the QKV GEMM leaves them."""
     q = _randn(B, Nq, H, 72, seed=30)
     k = _randn(B, Nk, H, 72, seed=31)
     v = _randn(B, Nk, H, 72, seed=32)
     out = torch.full((B * Nq, H * 72), float("nan"), dtype=torch.bfloat16, device=DEV)
     lib.flash_attn(q, k, v, out, B=B, H=H, Nq=Nq, Nk=Nk, kv_rows=B * Nk,
-                   q_strides=(H * 72, 72), k_strides=(H * 72, 72), v_strides=(H * 72, 72))
+                   q_strides=(H * 72, 72), k_strides=(H * 72, 72), v_strides=(H * 72, 72), variant=variant)
     want = _attn_ref(q, k, v, [Nk] * B).reshape(B * Nq, H * 72)
     assert torch.isfinite(out.float()).all()
     assert po.rel_err(out.float(), want) < 6e-3
 
 
-def test_flash_attn_interleaved_qkv_buffer():
+@pytest.mark.parametrize("variant", [2, 3])
+def test_flash_attn_interleaved_qkv_buffer(variant):
     B, H, N = 2, 16, 512
     qkv = _randn(B * N, 3, H, 72, seed=33)
     out = torch.empty(B * N, H * 72, dtype=torch.bfloat16, device=DEV)
     lib.flash_attn(qkv[:, 0], qkv[:, 1], qkv[:, 2], out, B=B, H=H, Nq=N, Nk=N, kv_rows=B * N,
-                   q_strides=(3 * H * 72, 72), k_strides=(3 * H * 72, 72), v_strides=(3 * H * 72, 72))
+                   q_strides=(3 * H * 72, 72), k_strides=(3 * H * 72, 72), v_strides=(3 * H * 72, 72), variant=variant)
     r = qkv.view(B, N, 3, H, 72)
     want = _attn_ref(r[:, :, 0], r[:, :, 1], r[:, :, 2], [N] * B).reshape(B * N, H * 72)
     assert po.rel_err(out.float(), want) < 6e-3
 
 
-def test_flash_attn_large_logits_trigger_rescale():
+@pytest.mark.parametrize("variant", [2, 3])
+def test_flash_attn_large_logits_trigger_rescale(variant):
     """Keys ordered so the running max keeps growing by > 2^8 between blocks: exercises the lazy O rescale."""
     B, H, N = 1, 2, 512
     q = _randn(B, N, H, 72, seed=34)
@@ -331,12 +334,13 @@ def test_flash_attn_large_logits_trigger_rescale():
     v = _randn(B, N, H, 72, seed=36)
     out = torch.empty(B * N, H * 72, dtype=torch.bfloat16, device=DEV)
     lib.flash_attn(q, k, v, out, B=B, H=H, Nq=N, Nk=N, kv_rows=B * N, q_strides=(H * 72, 72), k_strides=(H * 72, 72),
-                   v_strides=(H * 72, 72))
+                   v_strides=(H * 72, 72), variant=variant)
     want = _attn_ref(q, k, v, [N]).reshape(B * N, H * 72)
     assert po.rel_err(out.float(), want) < 8e-3
 
 
-def test_flash_attn_cross_packed_varlen():
+@pytest.mark.parametrize("variant", [2, 3])
+def test_flash_attn_cross_packed_varlen(variant):
     """T5 cross-attention: packed keys (1, sum L, 2, H, 72) with BlockDiagonalMask semantics, incl. an empty sample."""
     H, Nq = 16, 384
     lens = [300, 8, 0, 129, 128, 77]
@@ -348,7 +352,7 @@ def test_flash_attn_cross_packed_varlen():
     ln = torch.tensor(lens, dtype=torch.int32, device=DEV)
     out = torch.full((B * Nq, H * 72), float("nan"), dtype=torch.bfloat16, device=DEV)
     lib.flash_attn(q, kv[:, 0], kv[:, 1], out, B=B, H=H, Nq=Nq, Nk=300, kv_rows=tot, kv_len=ln, kv_off=off,
-                   q_strides=(H * 72, 72), k_strides=(2 * H * 72, 72), v_strides=(2 * H * 72, 72))
+                   q_strides=(H * 72, 72), k_strides=(2 * H * 72, 72), v_strides=(2 * H * 72, 72), variant=variant)
     wants, o = [], 0
     for b, L in enumerate(lens):
         if L == 0:
