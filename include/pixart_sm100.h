@@ -108,6 +108,9 @@ typedef struct PxaGemmArgs {
   int32_t res_epilogue;     /* EPI_BIAS_RESIDUAL, fp32 out, CTA pair: 0 = auto, 1 = register-staged residual (coalesced
                                loads, smem transpose), 2 = residual tile streamed through smem by TMA (row per thread)       */
   int32_t epi_warps;        /* CTA pair, bf16 epilogues: 0 = auto (8: two epilogue warps per TMEM lane quarter), 4 or 8     */
+  int32_t reverse_tiles;    /* 1: visit the output tiles from the LAST row block to the first.  A GEMM whose A operand was
+                               written front to back by the previous kernel (mlp.fc2 after mlp.fc1) then starts on the rows
+                               that are still in the 126 MB L2 instead of the ones already evicted to HBM                   */
 } PxaGemmArgs;
 int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream);
 
@@ -183,6 +186,8 @@ typedef struct PxaAttnArgs {
   int64_t* debug_trace; /* NULL in production. Else device int64[16 warps + 2][kTraceMax] cycle stamps of CTA (0,0,0) */
   float* lse;       /* optional fp32 [B, H, Nq]: log2-domain log-sum-exp of the scaled scores, the softmax statistic the
                        backward pass recomputes P from (training); NULL for inference                              */
+  int32_t reverse_batch; /* 1: CTAs take the samples from the last to the first (same L2 argument as PxaGemmArgs.reverse_tiles:
+                            the qkv rows of the last samples are the ones the QKV GEMM has just written)                   */
   int32_t variant;  /* 0 = auto, 2 = two 128-row query tiles per CTA with a double-buffered S (attn_sm100.cu), 3 = three tiles
                        with a single S buffer each: three softmax warps per SM sub-partition (attn3_sm100.cu)                */
 } PxaAttnArgs;

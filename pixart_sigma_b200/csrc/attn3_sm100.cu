@@ -56,6 +56,7 @@ struct Attn3Params {
   const int* kv_off;
   int B, H, Nq, Nk, ldo;
   float scale_log2;
+  int reverse_batch;
 };
 
 __global__ void __launch_bounds__(k3Threads, 1)
@@ -79,7 +80,7 @@ flash_attn_d72_x3_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __
 
   const int warp = warp_idx_sync();
   const int lane = threadIdx.x & 31;
-  const int b = blockIdx.z, h = blockIdx.y;
+  const int b = p.reverse_batch ? p.B - 1 - (int)blockIdx.z : (int)blockIdx.z, h = blockIdx.y;
   const int q0 = blockIdx.x * (k3Tiles * k3TileQ);
   // tiles of this CTA that hold at least one query row (the last CTA of a sample may own fewer than three)
   const int n_tiles = min(k3Tiles, (p.Nq - q0 + k3TileQ - 1) / k3TileQ);
@@ -371,6 +372,7 @@ int flash_attn_d72_x3_launch(const PxaAttnArgs& a, cudaStream_t stream) {
   p.kv_off = a.kv_off;
   p.B = a.B; p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk; p.ldo = a.ldo;
   p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.reverse_batch = a.reverse_batch ? 1 : 0;
   PXA_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_d72_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k3Smem));
   dim3 grid((a.Nq + k3Tiles * k3TileQ - 1) / (k3Tiles * k3TileQ), a.H, a.B);
   flash_attn_d72_x3_kernel<<<grid, k3Threads, k3Smem, stream>>>(qm, qt, km, kt, vm, vt, p);

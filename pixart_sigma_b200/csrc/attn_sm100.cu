@@ -80,6 +80,7 @@ struct AttnParams {
   const int* kv_off;
   int B, H, Nq, Nk, ldo;
   float scale_log2;
+  int reverse_batch;    // CTAs take the samples from the last to the first (L2 reuse of the freshly written qkv rows)
   long long* trace;     // debug only (NULL in production): cycle stamps of CTA (0,0,0), see PXA_TRACE
 };
 
@@ -111,7 +112,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
 
   const int warp = warp_idx_sync();
   const int lane = threadIdx.x & 31;
-  const int b = blockIdx.z, h = blockIdx.y;
+  const int b = p.reverse_batch ? p.B - 1 - (int)blockIdx.z : (int)blockIdx.z, h = blockIdx.y;
   const int q0 = blockIdx.x * (2 * kTileQ);
 
   int kv_len = p.kv_len ? p.kv_len[b] : p.Nk;
@@ -541,6 +542,7 @@ extern "C" int pxa_flash_attn_d72_bf16(const PxaAttnArgs* args, void* stream) {
   p.kv_off = a.kv_off;
   p.B = a.B; p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk; p.ldo = a.ldo;
   p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.reverse_batch = a.reverse_batch ? 1 : 0;
   p.trace = reinterpret_cast<long long*>(a.debug_trace);
   PXA_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_d72_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
   dim3 grid((a.Nq + 2 * kTileQ - 1) / (2 * kTileQ), a.H, a.B);

@@ -409,6 +409,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __nv_bfloat1
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   if (prow < prows) {
     const __nv_bfloat16* base = x + ((size_t)b * HW) * C + slice * 8;
+#pragma unroll 4
     for (int p = p0 + prow; p < p1; p += prows) {
       const uint4 u = *reinterpret_cast<const uint4*>(base + (size_t)p * C);
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -438,6 +439,8 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __nv_bfloat1
   for (int i = threadIdx.x; i < groups * 2; i += kGnThreads) atomicAdd(stats + (size_t)b * groups * 2 + i, (&sh[0][0])[i]);
 }
 
+// The grid-stride is a multiple of the slices per pixel (a power of two <= 64 divides 256 x gridDim), so a thread keeps ONE
+// 8-channel slice: gamma / beta are loaded once, and per pixel only the sample's (mean, rstd) of the slice's group(s) change.
 template <bool kSilu>
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                               const float* __restrict__ stats, const __nv_bfloat16* __restrict__ gamma,
@@ -446,33 +449,54 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __nv_bfloat1
   const int slices = C >> 3;
   const int cpg = C / groups;
   const float inv_n = 1.0f / ((float)HW * (float)cpg);
-  for (long long i = blockIdx.x * (long long)kGnThreads + threadIdx.x; i < total_slices; i += (long long)gridDim.x * kGnThreads) {
-    const int slice = (int)(i % slices);
-    const long long pix = i / slices;                            // b * HW + p
-    const int b = (int)(pix / HW);
-    const int c0 = slice * 8;
-    const uint4 u = *reinterpret_cast<const uint4*>(x + pix * C + c0);
+  const long long i0 = blockIdx.x * (long long)kGnThreads + threadIdx.x;
+  const int slice = (int)(i0 % slices);
+  const int c0 = slice * 8;
+  float gm[8], bt[8];
+  {
     const uint4 gu = __ldg(reinterpret_cast<const uint4*>(gamma + c0));
     const uint4 bu = __ldg(reinterpret_cast<const uint4*>(beta + c0));
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w}, gw[4] = {gu.x, gu.y, gu.z, gu.w}, bw[4] = {bu.x, bu.y, bu.z, bu.w};
+    const uint32_t gw[4] = {gu.x, gu.y, gu.z, gu.w}, bw[4] = {bu.x, bu.y, bu.z, bu.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      gm[2 * k] = bf16_lo(gw[k]); gm[2 * k + 1] = bf16_hi(gw[k]);
+      bt[2 * k] = bf16_lo(bw[k]); bt[2 * k + 1] = bf16_hi(bw[k]);
+    }
+  }
+  int b_prev = -1;
+  float a[8], d[8];                                                // y = x * a + d  with a = rstd * gamma, d = beta - mean * a
+  for (long long i = i0; i < total_slices; i += (long long)gridDim.x * kGnThreads) {
+    const long long pix = i / slices;                              // b * HW + p
+    const int b = (int)(pix / HW);
+    if (b != b_prev) {                                             // new sample: fold its group statistics into (a, d)
+      b_prev = b;
+      int g_prev = -1;
+      float mean = 0.f, rstd = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int g = (c0 + k) / cpg;
+        if (g != g_prev) {
+          g_prev = g;
+          const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + (size_t)b * groups + g);
+          mean = st.x * inv_n;
+          rstd = rsqrtf(fmaxf(st.y * inv_n - mean * mean, 0.f) + eps);
+        }
+        a[k] = rstd * gm[k];
+        d[k] = fmaf(-mean, a[k], bt[k]);
+      }
+    }
+    const uint4 u = *reinterpret_cast<const uint4*>(x + pix * C + c0);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
     uint32_t o[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float y[2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c = c0 + 2 * k + h;
-        const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + (size_t)b * groups + c / cpg);
-        const float mean = st.x * inv_n;
-        const float rstd = rsqrtf(fmaxf(st.y * inv_n - mean * mean, 0.f) + eps);
-        const float xv = h ? bf16_hi(w[k]) : bf16_lo(w[k]);
-        const float gv = h ? bf16_hi(gw[k]) : bf16_lo(gw[k]);
-        const float bv = h ? bf16_hi(bw[k]) : bf16_lo(bw[k]);
-        float v = fmaf((xv - mean) * rstd, gv, bv);
-        if (kSilu) v = v / (1.0f + __expf(-v));
-        y[h] = v;
+      float y0 = fmaf(bf16_lo(w[k]), a[2 * k], d[2 * k]);
+      float y1 = fmaf(bf16_hi(w[k]), a[2 * k + 1], d[2 * k + 1]);
+      if (kSilu) {
+        y0 = __fdividef(y0, 1.0f + __expf(-y0));
+        y1 = __fdividef(y1, 1.0f + __expf(-y1));
       }
-      o[k] = pack_bf16x2(y[0], y[1]);
+      o[k] = pack_bf16x2(y0, y1);
     }
     *reinterpret_cast<uint4*>(out + pix * C + c0) = make_uint4(o[0], o[1], o[2], o[3]);
   }
@@ -485,9 +509,10 @@ extern "C" int pxa_groupnorm_silu_nhwc_bf16(const void* x, void* out, const void
                                             void* stream) {
   using namespace pxa;
   if (!x || !out || !gamma || !beta || !stats_ws) return fail(PXA_ERR_ARG, "null pointer");
-  if (B <= 0 || HW <= 0 || C <= 0 || groups <= 0 || groups > kGnMaxGroups || C % groups || C % 8 || (C >> 3) > kGnThreads)
-    return fail(PXA_ERR_ARG, "bad B / HW / C / groups (C %% 8 == 0, C %% groups == 0, groups <= %d, C <= %d)", kGnMaxGroups,
-                8 * kGnThreads);
+  if (B <= 0 || HW <= 0 || C <= 0 || groups <= 0 || groups > kGnMaxGroups || C % groups || C % 8 || (C >> 3) > kGnThreads ||
+      kGnThreads % (C >> 3))
+    return fail(PXA_ERR_ARG, "bad B / HW / C / groups (C / 8 must divide %d, C %% groups == 0, groups <= %d)", kGnThreads,
+                kGnMaxGroups);
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gamma) |
        reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(stats_ws)) & 15)
     return fail(PXA_ERR_ALIGN, "pointers must be 16-byte aligned");
@@ -504,7 +529,7 @@ extern "C" int pxa_groupnorm_silu_nhwc_bf16(const void* x, void* out, const void
   launch_counter()++;
   const long long total = (long long)B * HW * (C >> 3);
   long long blocks = (total + kGnThreads - 1) / kGnThreads;
-  if (blocks > 16LL * sms) blocks = 16LL * sms;
+  if (blocks > 32LL * sms) blocks = 32LL * sms;
   if (silu)
     gn_apply_kernel<true><<<(int)blocks, kGnThreads, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out),
                                                              stats_ws, reinterpret_cast<const __nv_bfloat16*>(gamma),

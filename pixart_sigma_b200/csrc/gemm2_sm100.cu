@@ -128,6 +128,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int num_kb = (p.K + kBK - 1) / kBK;
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
+  // tile id -> tile: front to back, or back to front (p.reverse_tiles: start on the rows of A that are still in L2)
+  auto eff = [&](int t) { return p.reverse_tiles ? num_tiles - 1 - t : t; };
 
   if (warp == 0) {
     // ================================================================ TMA producer (both CTAs)
@@ -135,8 +137,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m0 = (tile / p.num_n_tiles) * (2 * kBM) + rank * kBM;
-        const int n0 = (tile % p.num_n_tiles) * BN;
+        const int m0 = (eff(tile) / p.num_n_tiles) * (2 * kBM) + rank * kBM;
+        const int n0 = (eff(tile) % p.num_n_tiles) * BN;
         if constexpr (kTmaRes) {
           // pull this tile's residual block into L2 now: the epilogue reads it one mainloop later
           if (!(p.out_aux == nullptr && p.residual == p.out && p.row_stats_out == nullptr))
@@ -191,6 +193,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       TileWalk tw;
       tw.first = cluster_id; tw.stride = num_clusters; tw.count = num_tiles;
       tw.mn_tiles = num_tiles; tw.num_n_tiles = p.num_n_tiles; tw.m_mult = 2 * kBM; tw.m_off = rank * kBM;
+      tw.reverse = p.reverse_tiles;
       tma_res_epilogue<BN, kResBufs, true>(p, tw, epi_smem, consts, tfull_bar, tempty_bar, res_full, tmem_base, &tmap_res,
                                            &tmap_out, &tmap_aux, warp, lane);
     } else {
@@ -208,12 +211,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       [[maybe_unused]] LnStatRegs sr;
       if (cluster_id < num_tiles) {
         if (tid < kNumEpiThreads)
-          load_epi_consts<BN, kLn>(er, p, tid, ((cluster_id) / p.num_n_tiles) * (2 * kBM) + rank * kBM, ((cluster_id) % p.num_n_tiles) * BN);
-        if constexpr (kLn) load_ln_stats(sr, p, ((cluster_id) / p.num_n_tiles) * (2 * kBM) + rank * kBM + q * 32 + lane);
+          load_epi_consts<BN, kLn>(er, p, tid, (eff(cluster_id) / p.num_n_tiles) * (2 * kBM) + rank * kBM, (eff(cluster_id) % p.num_n_tiles) * BN);
+        if constexpr (kLn) load_ln_stats(sr, p, (eff(cluster_id) / p.num_n_tiles) * (2 * kBM) + rank * kBM + q * 32 + lane);
       }
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++titer) {
-        const int m0 = (tile / p.num_n_tiles) * (2 * kBM) + rank * kBM;
-        const int n0 = (tile % p.num_n_tiles) * BN;
+        const int m0 = (eff(tile) / p.num_n_tiles) * (2 * kBM) + rank * kBM;
+        const int n0 = (eff(tile) % p.num_n_tiles) * BN;
         const int nch = chunks_of_tile<BN>(p, n0);
         EpiConst* cb = consts + (titer & 1);
         if (tid < kNumEpiThreads) store_epi_consts<BN>(cb, er, tid);
@@ -221,7 +224,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if constexpr (kLn) ln = ln_row_coeffs(p, sr);
         named_bar_sync(2, 32 * kEpiWarps);
         if (tile + num_clusters < num_tiles) {                     // next tile's loads: in flight during this tile's chunks
-          const int nt_ = tile + num_clusters;
+          const int nt_ = eff(tile + num_clusters);
           if (tid < kNumEpiThreads)
             load_epi_consts<BN, kLn>(er, p, tid, (nt_ / p.num_n_tiles) * (2 * kBM) + rank * kBM, (nt_ % p.num_n_tiles) * BN);
           if constexpr (kLn) load_ln_stats(sr, p, (nt_ / p.num_n_tiles) * (2 * kBM) + rank * kBM + q * 32 + lane);

@@ -24,6 +24,7 @@ struct GemmParams {
   long long* trace;     // debug only (NULL in production)
   int k_splits;         // > 1: split-K over tiles (reduce-add epilogue only)
   int aux_branch;       // residual epilogue: the bf16 aux output receives acc + bias (the branch output) instead of out
+  int reverse_tiles;    // visit the tiles from the last row block to the first (L2 reuse of a just-written A operand)
   // fused LayerNorm-modulate, producer side (fp32 residual epilogue): aux = out * aux_scale[b], row partial sums of out
   const float* aux_scale;
   long long aux_scale_batch_stride;
@@ -48,6 +49,7 @@ inline void fill_ln_params(GemmParams& p, const PxaGemmArgs& a) {
   p.ln_uv_batch_stride = a.ln_uv_batch_stride;
   p.ln_inv_dim = a.ln_dim > 0 ? 1.0f / (float)a.ln_dim : 0.f;
   p.ln_eps = a.ln_eps;
+  p.reverse_tiles = a.reverse_tiles ? 1 : 0;
 }
 
 constexpr int kResBufs = 3;
@@ -494,8 +496,10 @@ struct TileWalk {
   int first, stride, count;          // tile ids first, first + stride, ... < count
   int mn_tiles, num_n_tiles;         // tile id % mn_tiles -> (m tile, n tile), n fastest
   int m_mult, m_off;
-  PXA_DEVICE int m0(int tile) const { return ((tile % mn_tiles) / num_n_tiles) * m_mult + m_off; }
-  PXA_DEVICE int ntile(int tile) const { return (tile % mn_tiles) % num_n_tiles; }
+  int reverse;                       // 1: tile id t stands for tile count - 1 - t
+  PXA_DEVICE int eff(int tile) const { return reverse ? count - 1 - tile : tile; }
+  PXA_DEVICE int m0(int tile) const { return ((eff(tile) % mn_tiles) / num_n_tiles) * m_mult + m_off; }
+  PXA_DEVICE int ntile(int tile) const { return (eff(tile) % mn_tiles) % num_n_tiles; }
 };
 
 // The whole epilogue-warp loop of the TMA-streamed fp32 residual epilogue (called by the 4 epilogue warps of either GEMM

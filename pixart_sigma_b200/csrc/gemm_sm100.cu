@@ -161,6 +161,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       TileWalk tw;
       tw.first = blockIdx.x; tw.stride = gridDim.x; tw.count = num_tiles;
       tw.mn_tiles = mn_tiles; tw.num_n_tiles = p.num_n_tiles; tw.m_mult = kBM; tw.m_off = 0;
+      tw.reverse = 0;                 // (reverse_tiles is a CTA-pair kernel option)
       tma_res_epilogue<BN, kRing, false>(p, tw, epi_smem, consts, tfull_bar, tempty_bar, res_full, tmem_base, &tmap_res,
                                          &tmap_out, &tmap_aux, warp, lane);
     } else {

@@ -36,7 +36,8 @@ class GemmArgs(C.Structure):
                 ("k_splits", C.c_int32), ("aux_is_branch", C.c_int32),
                 ("aux_scale", C.c_void_p), ("aux_scale_batch_stride", C.c_int64), ("row_stats_out", C.c_void_p),
                 ("ln_stats", C.c_void_p), ("ln_u", C.c_void_p), ("ln_v", C.c_void_p), ("ln_uv_batch_stride", C.c_int64),
-                ("ln_dim", C.c_int32), ("ln_eps", C.c_float), ("res_epilogue", C.c_int32), ("epi_warps", C.c_int32)]
+                ("ln_dim", C.c_int32), ("ln_eps", C.c_float), ("res_epilogue", C.c_int32), ("epi_warps", C.c_int32),
+                ("reverse_tiles", C.c_int32)]
 
 
 class LnPrepareArgs(C.Structure):
@@ -59,7 +60,7 @@ class AttnArgs(C.Structure):
                 ("kv_rows", C.c_int64),
                 ("B", C.c_int32), ("H", C.c_int32), ("Nq", C.c_int32), ("Nk", C.c_int32),
                 ("ldo", C.c_int32), ("scale", C.c_float), ("debug_trace", C.c_void_p), ("lse", C.c_void_p),
-                ("variant", C.c_int32)]
+                ("reverse_batch", C.c_int32), ("variant", C.c_int32)]
 
 
 class KvCompressArgs(C.Structure):
@@ -195,7 +196,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
          aux_is_branch: bool = False, aux_scale: Optional[torch.Tensor] = None, aux_scale_batch_stride: int = 0,
          row_stats_out: Optional[torch.Tensor] = None, ln_stats: Optional[torch.Tensor] = None,
          ln_u: Optional[torch.Tensor] = None, ln_v: Optional[torch.Tensor] = None, ln_uv_batch_stride: int = 0,
-         ln_dim: int = 0, ln_eps: float = 1e-6, res_epilogue: int = 0, epi_warps: int = 0) -> torch.Tensor:
+         ln_dim: int = 0, ln_eps: float = 1e-6, res_epilogue: int = 0, epi_warps: int = 0,
+         reverse_tiles: bool = False) -> torch.Tensor:
     """out = epilogue(a @ w.T + bias). a (M,K) bf16, w (N,K) bf16 (nn.Linear layout), both K-contiguous.
 
     Fused LayerNorm-modulate (include/pixart_sm100.h, PXA_EPI_LN_BIAS): the fp32 residual epilogue can emit the scaled bf16
@@ -226,7 +228,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
                     aux_is_branch=int(aux_is_branch), aux_scale=_ptr(aux_scale), aux_scale_batch_stride=aux_scale_batch_stride,
                     row_stats_out=_ptr(row_stats_out), ln_stats=_ptr(ln_stats), ln_u=_ptr(ln_u), ln_v=_ptr(ln_v),
                     ln_uv_batch_stride=ln_uv_batch_stride, ln_dim=ln_dim, ln_eps=ln_eps, res_epilogue=res_epilogue,
-                    epi_warps=epi_warps)
+                    epi_warps=epi_warps, reverse_tiles=int(reverse_tiles))
     _check(load().pxa_gemm_bf16(C.byref(args), _stream()), "pxa_gemm_bf16")
     return out
 
@@ -274,7 +276,7 @@ def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Ten
                Nk: int, kv_rows: int, kv_len: Optional[torch.Tensor] = None, kv_off: Optional[torch.Tensor] = None,
                q_strides=None, k_strides=None, v_strides=None, scale: Optional[float] = None,
                debug_trace: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None,
-               variant: int = 0) -> torch.Tensor:
+               variant: int = 0, reverse_batch: bool = False) -> torch.Tensor:
     """Head-dim-72 attention. q/k/v are bf16 *views*; strides are (row, head) in elements, e.g. slices of the
     (rows, 3, H, 72) qkv GEMM output. out is (B*Nq, H*72) bf16."""
     assert q.dtype == k.dtype == v.dtype == out.dtype == torch.bfloat16
@@ -285,7 +287,8 @@ def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Ten
                     q_sn=q_strides[0], q_sh=q_strides[1], k_sn=k_strides[0], k_sh=k_strides[1],
                     v_sn=v_strides[0], v_sh=v_strides[1], kv_rows=kv_rows, B=B, H=H, Nq=Nq, Nk=Nk,
                     ldo=out.stride(0), scale=scale if scale is not None else 72 ** -0.5,
-                    debug_trace=_ptr(debug_trace), lse=_ptr(lse), variant=variant or _ATTN_VARIANT)
+                    debug_trace=_ptr(debug_trace), lse=_ptr(lse), variant=variant or _ATTN_VARIANT,
+                    reverse_batch=int(reverse_batch))
     if lse is not None:
         assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == B * H * Nq
     _check(load().pxa_flash_attn_d72_bf16(C.byref(args), _stream()), "pxa_flash_attn_d72_bf16")

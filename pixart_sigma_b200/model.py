@@ -207,6 +207,8 @@ class _Workspace:
         return t
 
 
+_L2_CHAIN = os.environ.get("PXA_L2_CHAIN", "1") != "0"      # consumer kernels start on the rows their producer wrote last
+
 _LN_FUSE_MIN_ROWS = 128      # a 128-row GEMM tile may span at most two samples (include/pixart_sm100.h)
 
 
@@ -386,8 +388,10 @@ class PixArtMSBlock(nn.Module):
         if a.sr_ratio > 1:                                                                   # PixArt_blocks.py:137-139
             k_src, v_src, n_keys = self._compress_kv(qkv, B, N, HW, ws)
             k_str = (C, C // H)
+        # L2 chaining (126 MB): each kernel starts on the rows its producer wrote last -- the QKV GEMM runs front to back, the
+        # attention back to front (so attn.proj, front to back again, finds the first samples' outputs still cached)
         lib.flash_attn(q3[:, 0], k_src, v_src, ao, B=B, H=H, Nq=N, Nk=n_keys, kv_rows=B * n_keys,
-                       q_strides=(3 * C, C // H), k_strides=k_str, v_strides=k_str, scale=a.scale)
+                       q_strides=(3 * C, C // H), k_strides=k_str, v_strides=k_str, scale=a.scale, reverse_batch=_L2_CHAIN)
         lib.gemm(ao, a.proj.weight, a.proj.bias, x32, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x32, gate=mod[:, 2],
                  gate_batch_stride=ms, rows_per_batch=N, out_aux=xb)
 
@@ -419,9 +423,9 @@ class PixArtMSBlock(nn.Module):
             lib.gemm(hid, mlp.fc2.weight, mlp.fc2.bias, x32, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x32, gate=mod[:, 5],
                      gate_batch_stride=ms, rows_per_batch=N, out_aux=xn, aux_scale=nxt[:, 0], aux_scale_batch_stride=nxt.stride(0),
                      row_stats_out=stats)
-        else:
+        else:       # back to front: the hidden rows fc1 wrote last (302 MB in all at c3) are the ones still in L2
             lib.gemm(hid, mlp.fc2.weight, mlp.fc2.bias, x32, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x32, gate=mod[:, 5],
-                     gate_batch_stride=ms, rows_per_batch=N)
+                     gate_batch_stride=ms, rows_per_batch=N, reverse_tiles=_L2_CHAIN)
         return x32
 
     def _compress_kv(self, qkv, B, N, HW, ws):

@@ -414,3 +414,41 @@ def test_ln_fusion_conditioning_vectors_match_fp32():
             want_v = mod_all[i, :, i_shift] @ lin.weight.float().T + lin.bias.float()
             assert po.rel_err(u[i][:, sl], want_u) < 1e-5 and po.rel_err(v[i][:, sl], want_v) < 1e-5
     assert torch.equal(one_plus[:, :, 0], 1 + mod_all[:, :, 1]) and torch.equal(one_plus[:, :, 1], 1 + mod_all[:, :, 4])
+
+
+# ------------------------------------------------------------------------------------------------- L2 chaining options
+@pytest.mark.parametrize("epi", ["bias", "residual"])
+def test_gemm_reverse_tile_order_gives_identical_results(epi):
+    """reverse_tiles only changes the order in which the persistent grid visits the tiles (last row block first)."""
+    M, N, K = 2304, 1152, 4608
+    a, w, bias = _randn(M, K, seed=100), _randn(N, K, seed=101, scale=K ** -0.5), _randn(N, seed=102, scale=0.1)
+    outs = []
+    for rev in (False, True):
+        if epi == "bias":
+            out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV)
+            lib.gemm(a, w, bias, out, reverse_tiles=rev)
+        else:
+            out = _randn(M, N, seed=103, dtype=torch.float32)
+            gate = _randn(2, N, seed=104, dtype=torch.float32)
+            lib.gemm(a, w, bias, out, epilogue=lib.EPI_BIAS_RESIDUAL, residual=out, gate=gate, gate_batch_stride=N,
+                     rows_per_batch=M // 2, reverse_tiles=rev)
+        outs.append(out)
+    assert torch.isfinite(outs[1].float()).all()
+    if epi == "bias":
+        assert torch.equal(outs[0], outs[1])
+    else:
+        assert po.rel_err(outs[1], outs[0]) < 1e-6        # TMA reduce-add: same addends, L2 adds them in arrival order
+
+
+@pytest.mark.parametrize("variant", [2, 3])
+def test_flash_attn_reverse_batch_order_gives_identical_results(variant):
+    B, H, N = 3, 4, 640
+    q, k, v = _randn(B, N, H, 72, seed=110), _randn(B, N, H, 72, seed=111), _randn(B, N, H, 72, seed=112)
+    lens = torch.tensor([640, 77, 300], dtype=torch.int32, device=DEV)
+    outs = []
+    for rev in (False, True):
+        out = torch.full((B * N, H * 72), float("nan"), dtype=torch.bfloat16, device=DEV)
+        lib.flash_attn(q, k, v, out, B=B, H=H, Nq=N, Nk=N, kv_rows=B * N, kv_len=lens, q_strides=(H * 72, 72),
+                       k_strides=(H * 72, 72), v_strides=(H * 72, 72), variant=variant, reverse_batch=rev)
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
