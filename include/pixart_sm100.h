@@ -129,6 +129,8 @@ typedef struct PxaLnModArgs {
   int32_t M, C, ldx;
   int32_t x_dtype;      /* PXA_DTYPE_* */
   float eps;
+  int32_t reverse_rows; /* 1: CTAs take the rows from the last to the first (start on the rows of x that the front-to-back
+                           residual GEMM before it wrote last, i.e. the ones still in L2)                        */
 } PxaLnModArgs;
 int pxa_ln_modulate(const PxaLnModArgs* args, void* stream);
 
@@ -162,6 +164,23 @@ int pxa_layernorm_affine_bf16(void* x, const void* weight, const void* bias, int
  * stream).  Two launches: statistics, apply.  HBM-bound: 2 reads + 1 write of the image. */
 int pxa_groupnorm_silu_nhwc_bf16(const void* x, void* out, const void* gamma, const void* beta, float* stats_ws, int32_t B,
                                  int32_t HW, int32_t C, int32_t groups, float eps, int32_t silu, void* stream);
+
+/* AdamW on a flat fp32 bucket (torch.optim.AdamW semantics: decoupled weight decay, bias-corrected moments) -- the optimizer
+ * the reference trains with (configs/PixArt_xl2_internal.py:48 `AdamW(lr=2e-5, weight_decay=3e-2, eps=1e-10)`, built by
+ * diffusion/utils/optimizer.py:236-245), applied to the gradient buckets of pixart_sigma_b200.parallel.GradBucketReducer in one
+ * launch per bucket; optionally writes the bf16 copy of the updated parameters that the GEMMs read.  All pointers device. */
+typedef struct PxaAdamWArgs {
+  float* param;          /* fp32 [n], updated in place          */
+  const float* grad;     /* fp32 [n]                            */
+  float* exp_avg;        /* fp32 [n], updated in place          */
+  float* exp_avg_sq;     /* fp32 [n], updated in place          */
+  void* shadow_bf16;     /* bf16 [n] or NULL                    */
+  int64_t n;             /* multiple of 4                       */
+  int32_t step;          /* 1-based step count (bias correction) */
+  float lr, beta1, beta2, eps, weight_decay;
+  float grad_scale;      /* gradients are multiplied by this first (1 / loss scale, or 1) */
+} PxaAdamWArgs;
+int pxa_adamw_flat(const PxaAdamWArgs* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------- attention
  * out[b, i, h, :] = softmax_j( q[b,i,h,:] . k[b,j,h,:] * scale ) v[b,j,h,:],  j < kv_len[b],  head_dim 72.

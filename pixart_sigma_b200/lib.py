@@ -46,10 +46,17 @@ class LnPrepareArgs(C.Structure):
                 ("ldx", C.c_int32)]
 
 
+class AdamWArgs(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("shadow_bf16", C.c_void_p), ("n", C.c_int64), ("step", C.c_int32), ("lr", C.c_float), ("beta1", C.c_float),
+                ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float), ("grad_scale", C.c_float)]
+
+
 class LnModArgs(C.Structure):
     _fields_ = [("x", C.c_void_p), ("out", C.c_void_p), ("shift", C.c_void_p), ("scale", C.c_void_p),
                 ("mod_batch_stride", C.c_int64), ("rows_per_batch", C.c_int32),
-                ("M", C.c_int32), ("C", C.c_int32), ("ldx", C.c_int32), ("x_dtype", C.c_int32), ("eps", C.c_float)]
+                ("M", C.c_int32), ("C", C.c_int32), ("ldx", C.c_int32), ("x_dtype", C.c_int32), ("eps", C.c_float),
+                ("reverse_rows", C.c_int32)]
 
 
 class AttnArgs(C.Structure):
@@ -117,7 +124,7 @@ EXPORTS = ("pxa_transpose_bf16", "pxa_gelu_tanh_bf16", "pxa_gate_residual_fwd", 
            "pxa_ln_modulate_bwd", "pxa_colsum_bf16", "pxa_attn_delta_d72", "pxa_flash_attn_d72_bwd_bf16", "pxa_kv_compress_conv2_ln_bwd",
            "pxa_version", "pxa_last_error", "pxa_launch_count", "pxa_gemm_bf16", "pxa_ln_modulate",
            "pxa_flash_attn_d72_bf16", "pxa_kv_compress_conv2_ln", "pxa_conv3x3_nhwc_bf16", "pxa_dpm_solver_pp_step",
-           "pxa_ln_prepare", "pxa_layernorm_affine_bf16", "pxa_groupnorm_silu_nhwc_bf16")
+           "pxa_ln_prepare", "pxa_layernorm_affine_bf16", "pxa_groupnorm_silu_nhwc_bf16", "pxa_adamw_flat")
 
 _lib = None
 
@@ -135,7 +142,7 @@ def load() -> C.CDLL:
         for name, struct in (("pxa_gemm_bf16", GemmArgs), ("pxa_ln_modulate", LnModArgs),
                              ("pxa_flash_attn_d72_bf16", AttnArgs), ("pxa_kv_compress_conv2_ln", KvCompressArgs),
                              ("pxa_conv3x3_nhwc_bf16", Conv3x3Args), ("pxa_dpm_solver_pp_step", DpmStepArgs),
-                             ("pxa_ln_prepare", LnPrepareArgs)):
+                             ("pxa_ln_prepare", LnPrepareArgs), ("pxa_adamw_flat", AdamWArgs)):
             fn = getattr(lib, name)
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(struct), C.c_void_p]
@@ -249,13 +256,14 @@ def ln_prepare(x: torch.Tensor, mult: torch.Tensor, a_out: torch.Tensor, stats_o
 
 
 def ln_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, out: torch.Tensor, *,
-                mod_batch_stride: int, rows_per_batch: int, eps: float = 1e-6) -> torch.Tensor:
+                mod_batch_stride: int, rows_per_batch: int, eps: float = 1e-6, reverse_rows: bool = False) -> torch.Tensor:
     """out = LN(x) * (1 + scale[b]) + shift[b]; x (M,C) fp32/bf16, shift/scale fp32 views (row b at b*stride)."""
     assert x.dim() == 2 and x.stride(1) == 1 and out.is_contiguous() and out.dtype == torch.bfloat16
     assert shift.dtype == torch.float32 and scale.dtype == torch.float32
     M, Cc = x.shape
     args = LnModArgs(x=_ptr(x), out=_ptr(out), shift=_ptr(shift), scale=_ptr(scale), mod_batch_stride=mod_batch_stride,
-                     rows_per_batch=rows_per_batch, M=M, C=Cc, ldx=x.stride(0), x_dtype=_dt(x.dtype), eps=eps)
+                     rows_per_batch=rows_per_batch, M=M, C=Cc, ldx=x.stride(0), x_dtype=_dt(x.dtype), eps=eps,
+                     reverse_rows=int(reverse_rows))
     _check(load().pxa_ln_modulate(C.byref(args), _stream()), "pxa_ln_modulate")
     return out
 
@@ -317,6 +325,20 @@ def conv3x3_nhwc(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.T
     return out
 
 
+def adamw_flat(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, *, step: int, lr: float,
+               betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2, grad_scale: float = 1.0,
+               shadow: Optional[torch.Tensor] = None) -> None:
+    """torch.optim.AdamW's update on flat fp32 tensors of equal length (a multiple of 4), in place; `shadow` (bf16, same
+    length) receives the bf16 copy of the new parameters."""
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        assert t.dtype == torch.float32 and t.is_cuda and t.is_contiguous() and t.numel() == param.numel()
+    assert shadow is None or (shadow.dtype == torch.bfloat16 and shadow.is_contiguous() and shadow.numel() == param.numel())
+    args = AdamWArgs(param=_ptr(param), grad=_ptr(grad), exp_avg=_ptr(exp_avg), exp_avg_sq=_ptr(exp_avg_sq), shadow_bf16=_ptr(shadow),
+                     n=param.numel(), step=step, lr=lr, beta1=betas[0], beta2=betas[1], eps=eps, weight_decay=weight_decay,
+                     grad_scale=grad_scale)
+    _check(load().pxa_adamw_flat(C.byref(args), _stream()), "pxa_adamw_flat")
+
+
 def groupnorm_silu_nhwc(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, *, groups: int = 32,
                         eps: float = 1e-6, silu: bool = True, stats_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
     """GroupNorm (+ SiLU) on an NHWC bf16 image x (B, H, W, C) -> out (same shape); statistics in fp32."""
@@ -327,7 +349,7 @@ def groupnorm_silu_nhwc(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor
         stats_ws = torch.empty(B * groups * 2, dtype=torch.float32, device=x.device)
     assert stats_ws.dtype == torch.float32 and stats_ws.numel() >= B * groups * 2
     _check(load().pxa_groupnorm_silu_nhwc_bf16(_ptr(x), _ptr(out), _ptr(gamma), _ptr(beta), _ptr(stats_ws), B, H * W, Cc, groups,
-                                               eps, int(silu), _stream()), "pxa_groupnorm_silu_nhwc_bf16")
+                                               eps, int(silu), _stream()), "pxa_groupnorm_silu_nhwc_bf16", "pxa_adamw_flat")
     return out
 
 

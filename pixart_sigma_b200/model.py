@@ -416,7 +416,8 @@ class PixArtMSBlock(nn.Module):
             lib.gemm(xn, mlp.fc1.weight, None, hid, epilogue=lib.EPI_LN_BIAS_GELU, rows_per_batch=N, ln_u=u[:, n1:], ln_v=v[:, n1:],
                      **lnkw)
         else:
-            lib.ln_modulate(x32, mod[:, 3], mod[:, 4], xn, mod_batch_stride=ms, rows_per_batch=N)
+            # back to front: the rows of x the (front-to-back) cross-attention projection wrote last are still in L2
+            lib.ln_modulate(x32, mod[:, 3], mod[:, 4], xn, mod_batch_stride=ms, rows_per_batch=N, reverse_rows=_L2_CHAIN)
             lib.gemm(xn, mlp.fc1.weight, mlp.fc1.bias, hid, epilogue=lib.EPI_BIAS_GELU)
         nxt = ln.get("next_one_plus") if fused else None
         if nxt is not None:                         # ... and here A / statistics for the NEXT block's norm1

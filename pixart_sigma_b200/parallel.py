@@ -83,7 +83,7 @@ class GradBucketReducer:
             groups.setdefault(bucket_of(n), []).append(p)
         self.buckets = []
         for key, ps in groups.items():
-            total = sum(p.numel() for p in ps)
+            total = (sum(p.numel() for p in ps) + 3) // 4 * 4               # padded to 16 bytes (flat optimizer kernels)
             flat = torch.zeros(total, dtype=ps[0].dtype, device=ps[0].device)
             off = 0
             for p in ps:
@@ -98,6 +98,21 @@ class GradBucketReducer:
             for p in b["params"]:
                 self._hooks.append(p.register_post_accumulate_grad_hook(lambda _p, b=b: self._ready(b)))
         self.start()
+
+    def flatten_params(self) -> None:
+        """Make every parameter's storage a view of one flat buffer per bucket (same layout as the gradient buckets), so that
+        an optimizer can update a whole bucket in one launch (`optim.FlatAdamW`).  Values are preserved; idempotent."""
+        for b in self.buckets:
+            if b.get("flat_param") is not None:
+                continue
+            fp = torch.zeros_like(b["flat"])
+            off = 0
+            for p in b["params"]:
+                view = fp[off: off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                off += p.numel()
+            b["flat_param"] = fp
 
     def check_views(self) -> None:
         """Every parameter's `.grad` must still be its view into the flat bucket.  `optimizer.zero_grad()` /

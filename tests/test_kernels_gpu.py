@@ -169,6 +169,9 @@ def test_ln_modulate(xdtype):
     lib.ln_modulate(x, mod[:, 3], mod[:, 4], out, mod_batch_stride=6 * Cc, rows_per_batch=Ntok)
     want = po.ln_modulate(x.float().view(B, Ntok, Cc), mod[:, 3:4], mod[:, 4:5]).view(-1, Cc)
     assert po.rel_err(out.float(), want) < 4e-3
+    out2 = torch.empty_like(out)
+    lib.ln_modulate(x, mod[:, 3], mod[:, 4], out2, mod_batch_stride=6 * Cc, rows_per_batch=Ntok, reverse_rows=True)
+    assert torch.equal(out, out2)                                   # row order only
 
 
 # ------------------------------------------------------------------------------------------------- fused LN-modulate chain

@@ -127,7 +127,9 @@ def test_grad_bucket_reducer_single_process_is_a_noop_reduce():
     red = GradBucketReducer(m)
     m(torch.ones(2, 8)).sum().backward()
     red.finish()
-    assert red.grad_bytes() == sum(p.numel() for p in m.parameters()) * 4
+    # one flat fp32 buffer per bucket, each padded to a multiple of 4 elements (16-byte granules of the flat optimizer kernel)
+    assert red.grad_bytes() == sum((sum(p.numel() for p in b["params"]) + 3) // 4 * 4 for b in red.buckets) * 4
+    assert sum(p.numel() for p in m.parameters()) * 4 <= red.grad_bytes() < sum(p.numel() for p in m.parameters()) * 4 + 16 * len(red.buckets)
     assert float(m.head.weight.grad.abs().sum()) > 0
 
 

@@ -204,3 +204,36 @@ def test_graphed_train_step_equals_eager_and_sees_parameter_updates(ckpt):
     assert po.rel_err(lg2, l1) < 1e-5                           # ... and the replay saw it (shadows refreshed in place)
     for n in g1:
         assert po.rel_err(g2[n], g1[n]) < 1e-4, n
+
+
+def test_flat_adamw_matches_torch_adamw():
+    """`optim.FlatAdamW` (one pxa_adamw_flat launch per gradient bucket, parameters flattened in place) against
+    torch.optim.AdamW with the reference's hyper-parameters (configs/PixArt_xl2_internal.py:48), three steps."""
+    from pixart_sigma_b200.optim import FlatAdamW
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.blocks = torch.nn.ModuleList([torch.nn.Linear(37, 53) for _ in range(2)])
+            self.head = torch.nn.Linear(53, 7)
+
+    torch.manual_seed(0)
+    a, b = Tiny().cuda(), Tiny().cuda()
+    b.load_state_dict(a.state_dict())
+    red = GradBucketReducer(a)
+    opt = FlatAdamW(red, lr=2e-3, eps=1e-10, weight_decay=3e-2)
+    ref = torch.optim.AdamW(b.parameters(), lr=2e-3, eps=1e-10, weight_decay=3e-2)
+    for (_, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert torch.equal(pa, pb)                                # flattening kept the values
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for step in range(3):
+        for pa, pb in zip(a.parameters(), b.parameters()):
+            gr = torch.randn(pa.shape, device="cuda", generator=g)
+            pa.grad.copy_(gr)                                     # the bucket view
+            pb.grad = gr.clone()
+        opt.step()
+        ref.step()
+        for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+            assert po.rel_err(pa, pb) < 1e-6, (step, n)
+    sd = opt.state_dict()
+    assert sd["step"] == 3 and len(sd["state"]) == len(red.buckets)
