@@ -316,6 +316,8 @@ typedef struct PxaLnModBwdArgs {
   int32_t rows_per_batch;
   int32_t M, C;
   float eps;
+  const float* add_in;  /* optional fp32 [M, C]: dx = add_in + (gradient through the LayerNorm): the gradient of the residual
+                           stream that by-passes the norm (x feeds both the norm and the residual add), folded in       */
 } PxaLnModBwdArgs;
 int pxa_ln_modulate_bwd(const PxaLnModBwdArgs* args, void* stream);
 

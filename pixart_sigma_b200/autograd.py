@@ -32,6 +32,8 @@ from . import lib
 # MLP branch as two GEMM launches with the GELU forward / backward inside their epilogues (MlpGateResidualFn); validated on
 # B200 in round 2 (tests/test_training_gpu.py, test_backward_gpu.py).  PXA_FUSED_MLP=0 restores the separate GELU passes.
 _FUSED_MLP = os.environ.get("PXA_FUSED_MLP", "1") == "1"
+# weight / bias gradients are accumulated by the kernels directly into an existing fp32 .grad (PXA_DIRECT_GRAD=0: via autograd)
+_DIRECT_GRAD = os.environ.get("PXA_DIRECT_GRAD", "1") == "1"
 
 def _shadow(mod: torch.nn.Module, kind: str) -> Optional[torch.Tensor]:
     """bf16 copy of `mod.weight` ('w'), its bf16 transpose ('t') or the bf16 bias ('b'), cached ON THE MODULE and
@@ -119,14 +121,45 @@ def _linear_backward(ctx_needs, x, weight, bias, mod, dy):
         dx = torch.empty((M, K), dtype=torch.bfloat16, device=x.device)
         lib.gemm(dy, _shadow(mod, "t"), None, dx)                              # dX = dY . W   (W^T is K-contiguous in N)
     if ctx_needs[1]:
-        dw32 = torch.zeros((N, K), dtype=torch.float32, device=x.device)
-        lib.gemm_wgrad(dy, x, dw32)                                            # dW += dY^T . X  (MN-major operands, split-K)
-        dw = dw32 if weight.dtype == torch.float32 else dw32.to(weight.dtype)
+        acc = _grad_accumulator(mod.weight)
+        if acc is not None:
+            # the weight-gradient GEMM's TMA reduce-add epilogue accumulates STRAIGHT into the parameter's fp32 .grad (a view
+            # of its gradient bucket): no zero-filled temporary, no autograd accumulation pass (~10 GB of HBM traffic / step)
+            lib.gemm_wgrad(dy, x, acc)
+            _grad_landed(mod.weight)
+        else:
+            dw32 = torch.zeros((N, K), dtype=torch.float32, device=x.device)
+            lib.gemm_wgrad(dy, x, dw32)                                        # dW += dY^T . X  (MN-major operands, split-K)
+            dw = dw32 if weight.dtype == torch.float32 else dw32.to(weight.dtype)
     if bias is not None and ctx_needs[2]:
-        db32 = torch.zeros((N,), dtype=torch.float32, device=x.device)
-        lib.colsum(dy, db32)
-        db = db32 if bias.dtype == torch.float32 else db32.to(bias.dtype)
+        acc = _grad_accumulator(mod.bias)
+        if acc is not None:
+            lib.colsum(dy, acc)
+            _grad_landed(mod.bias)
+        else:
+            db32 = torch.zeros((N,), dtype=torch.float32, device=x.device)
+            lib.colsum(dy, db32)
+            db = db32 if bias.dtype == torch.float32 else db32.to(bias.dtype)
     return dx, dw, db
+
+
+def _grad_accumulator(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """The tensor a backward kernel may accumulate a parameter gradient into directly: the parameter's existing fp32,
+    contiguous `.grad` (e.g. its view into a `parallel.GradBucketReducer` bucket).  None -> hand the gradient to autograd."""
+    if p is None or not _DIRECT_GRAD:
+        return None
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.device != p.device or g.shape != p.shape:
+        return None
+    return g
+
+
+def _grad_landed(p: torch.Tensor) -> None:
+    """Tell whoever tracks gradient readiness (GradBucketReducer) that p.grad has received this backward's contribution --
+    the job autograd's post-accumulate hook does for gradients that go through autograd."""
+    cb = getattr(p, "_pxa_grad_ready", None)
+    if cb is not None:
+        cb()
 
 
 class LinearGateResidualFn(torch.autograd.Function):
@@ -466,3 +499,166 @@ def block_forward_train(blk, x32: torch.Tensor, cond: torch.Tensor, kv_len: Opti
     if keep is not None:
         keep["replay"] = True            # the next call with this dict is the recomputation
     return x32
+
+
+# ------------------------------------------------------------------------------------------------- the whole block as ONE node
+_BLOCK_FN = os.environ.get("PXA_BLOCK_FN", "1") == "1"
+
+
+def _block_params(blk):
+    a, ca, mlp = blk.attn, blk.cross_attn, blk.mlp
+    mods = (a.qkv, a.proj, ca.q_linear, ca.kv_linear, ca.proj, mlp.fc1, mlp.fc2)
+    return mods, tuple(t for m in mods for t in (m.weight, m.bias))
+
+
+def _block_forward_kernels(blk, x32, cond, mod, kv_len, kv_off, max_keys, B, N, kept=None):
+    """The block's forward on the kernels, out of place, returning every intermediate the backward reads.  `kept` = the two
+    attention outputs + softmax statistics of an earlier pass (activation checkpointing: they are not recomputed)."""
+    a, ca, mlp = blk.attn, blk.cross_attn, blk.mlp
+    C, H = blk.hidden_size, a.num_heads
+    D, M, dev = C // H, B * N, x32.device
+    bf = dict(dtype=torch.bfloat16, device=dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    ms = mod.stride(0)
+    t = {}
+    t["xn1"] = lib.ln_modulate(x32, mod[:, 0], mod[:, 1], torch.empty((M, C), **bf), mod_batch_stride=ms, rows_per_batch=N)
+    t["qkv"] = lib.gemm(t["xn1"], _shadow(a.qkv, "w"), _shadow(a.qkv, "b"), torch.empty((M, 3 * C), **bf))
+    q3 = t["qkv"].view(M, 3, H, D)
+    st = (3 * C, D)
+    if kept is None:
+        t["ao1"], t["lse1"] = torch.empty((M, C), **bf), torch.empty((B, H, N), **f32)
+        lib.flash_attn(q3[:, 0], q3[:, 1], q3[:, 2], t["ao1"], B=B, H=H, Nq=N, Nk=N, kv_rows=M, q_strides=st, k_strides=st,
+                       v_strides=st, scale=a.scale, lse=t["lse1"])
+    else:
+        t["ao1"], t["lse1"] = kept[0], kept[1]
+    t["x1"], t["y1"] = torch.empty((M, C), **f32), torch.empty((M, C), **bf)
+    lib.gemm(t["ao1"], _shadow(a.proj, "w"), _shadow(a.proj, "b"), t["x1"], epilogue=lib.EPI_BIAS_RESIDUAL, residual=x32,
+             gate=mod[:, 2], gate_batch_stride=ms, rows_per_batch=N, out_aux=t["y1"], aux_is_branch=True)
+    t["xb"] = t["x1"].to(torch.bfloat16)
+    t["qx"] = lib.gemm(t["xb"], _shadow(ca.q_linear, "w"), _shadow(ca.q_linear, "b"), torch.empty((M, C), **bf))
+    t["kv"] = lib.gemm(cond, _shadow(ca.kv_linear, "w"), _shadow(ca.kv_linear, "b"), torch.empty((cond.shape[0], 2 * C), **bf))
+    kv4 = t["kv"].view(-1, 2, H, D)
+    if kept is None:
+        t["ao2"], t["lse2"] = torch.empty((M, C), **bf), torch.empty((B, H, N), **f32)
+        lib.flash_attn(t["qx"], kv4[:, 0], kv4[:, 1], t["ao2"], B=B, H=H, Nq=N, Nk=max_keys, kv_rows=cond.shape[0], kv_len=kv_len,
+                       kv_off=kv_off, q_strides=(C, D), k_strides=(2 * C, D), v_strides=(2 * C, D), scale=ca.head_dim ** -0.5,
+                       lse=t["lse2"])
+    else:
+        t["ao2"], t["lse2"] = kept[2], kept[3]
+    t["x2"] = torch.empty((M, C), **f32)
+    lib.gemm(t["ao2"], _shadow(ca.proj, "w"), _shadow(ca.proj, "b"), t["x2"], epilogue=lib.EPI_BIAS_RESIDUAL, residual=t["x1"],
+             rows_per_batch=N)
+    t["xn2"] = lib.ln_modulate(t["x2"], mod[:, 3], mod[:, 4], torch.empty((M, C), **bf), mod_batch_stride=ms, rows_per_batch=N)
+    Hd = mlp.fc1.out_features
+    t["h"], t["pre"] = torch.empty((M, Hd), **bf), torch.empty((M, Hd), **bf)
+    lib.gemm(t["xn2"], _shadow(mlp.fc1, "w"), _shadow(mlp.fc1, "b"), t["h"], epilogue=lib.EPI_BIAS_GELU_AUX, out_aux=t["pre"])
+    t["x3"], t["y3"] = torch.empty((M, C), **f32), torch.empty((M, C), **bf)
+    lib.gemm(t["h"], _shadow(mlp.fc2, "w"), _shadow(mlp.fc2, "b"), t["x3"], epilogue=lib.EPI_BIAS_RESIDUAL, residual=t["x2"],
+             gate=mod[:, 5], gate_batch_stride=ms, rows_per_batch=N, out_aux=t["y3"], aux_is_branch=True)
+    return t
+
+
+_SAVED = ("xn1", "qkv", "ao1", "lse1", "y1", "x1", "xb", "qx", "kv", "ao2", "lse2", "x2", "xn2", "h", "pre", "y3")
+_KEPT = ("ao1", "lse1", "ao2", "lse2")
+
+
+class BlockFn(torch.autograd.Function):
+    """One PixArtMSBlock (PixArtMS.py:71-79, no KV compression / qk_norm) as a SINGLE autograd node: the forward is the
+    kernel sequence of `_block_forward_kernels`, the backward the explicit reverse sequence of backward kernels.
+
+    Round 2: with one autograd node per op (the functions above) the training step carried ~100 small torch kernels per
+    block -- zero fills and slice assignments for the modulation gradients, the gradient additions where the residual
+    stream forks, bf16 casts, the accumulation of every weight gradient (`profiles/c5_r2a_summary.md`: 13 % of the step).
+    Here the residual-stream gradient is threaded through the backward kernels (`ln_modulate_bwd(add_in=...)`,
+    `gate_residual_fwd` as the fp32 + bf16 add), the six modulation gradients land in slices of ONE (6, B, C) buffer, and
+    the weight / bias gradients go straight into their bucket views.  Activation checkpointing is built in (`ckpt`): only
+    the block input, the conditioning and the two attention outputs + statistics are kept, the rest is recomputed here."""
+
+    @staticmethod
+    def forward(ctx, blk, x32, cond, mod, kv_len, kv_off, max_keys, B, N, ckpt, *params):
+        x32, cond, mod = x32.contiguous(), cond.contiguous(), mod.contiguous()
+        t = _block_forward_kernels(blk, x32, cond, mod, kv_len, kv_off, max_keys, B, N)
+        names = _KEPT if ckpt else _SAVED
+        ctx.save_for_backward(x32, cond, mod, kv_len, kv_off, *[t[k] for k in names], *params)
+        ctx.meta = (blk, max_keys, B, N, bool(ckpt), len(names))
+        return t["x3"]
+
+    @staticmethod
+    def backward(ctx, dout):
+        blk, max_keys, B, N, ckpt, n_names = ctx.meta
+        saved = ctx.saved_tensors
+        x32, cond, mod, kv_len, kv_off = saved[:5]
+        vals = saved[5:5 + n_names]
+        params = saved[5 + n_names:]
+        if ckpt:
+            t = _block_forward_kernels(blk, x32, cond, mod, kv_len, kv_off, max_keys, B, N, kept=vals)
+        else:
+            t = dict(zip(_SAVED, vals))
+        a, ca, mlp = blk.attn, blk.cross_attn, blk.mlp
+        C, H = blk.hidden_size, a.num_heads
+        D, M, dev = C // H, B * N, x32.device
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        ms = mod.stride(0)
+        dout = dout.contiguous()
+        dm = torch.zeros((6, B, C), **f32)                # d(shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp)
+        (w_qkv, b_qkv, w_p, b_p, w_q, b_q, w_kv, b_kv, w_cp, b_cp, w_1, b_1, w_2, b_2) = params
+        grads = {}
+
+        def lin_bwd(tag, x, weight, bias, lin_mod, dy, need_dx=True):
+            dx, dw, db = _linear_backward((need_dx, True, True), x, weight, bias, lin_mod, dy)
+            grads[tag] = (dw, db)
+            return dx
+
+        # (3) x3 = x2 + gate_mlp * (fc2(gelu(fc1(xn2))) + b2)
+        dy3 = torch.empty((M, C), **bf)
+        lib.gate_residual_bwd(dout, t["y3"], mod[:, 5], dy3, dm[5], gate_batch_stride=ms, rows_per_batch=N)
+        lin_bwd("fc2", t["h"], w_2, b_2, mlp.fc2, dy3, need_dx=False)
+        dpre = torch.empty_like(t["pre"])
+        lib.gemm(dy3, _shadow(mlp.fc2, "t"), None, dpre, epilogue=lib.EPI_MUL_DGELU, residual=t["pre"])
+        dxn2 = lin_bwd("fc1", t["xn2"], w_1, b_1, mlp.fc1, dpre)
+        dx2 = torch.empty((M, C), **f32)                  # = dout (the residual path) + the gradient through norm2
+        lib.ln_modulate_bwd(t["x2"], dxn2, mod[:, 4], dx2, dm[3], dm[4], mod_batch_stride=ms, rows_per_batch=N, add_in=dout)
+        # (2) x2 = x1 + cross_proj(cross_attn(q_linear(bf16(x1)), kv_linear(cond)))
+        dy2 = torch.empty((M, C), **bf)
+        lib.gate_residual_bwd(dx2, None, None, dy2, None, rows_per_batch=N)
+        dao2 = lin_bwd("cproj", t["ao2"], w_cp, b_cp, ca.proj, dy2)
+        dq, dkv = torch.empty((M, C), **bf), torch.zeros_like(t["kv"])      # padding key rows get no gradient
+        kv4, d4 = t["kv"].view(-1, 2, H, D), dkv.view(-1, 2, H, D)
+        lib.flash_attn_bwd(t["qx"], kv4[:, 0], kv4[:, 1], t["ao2"], dao2, t["lse2"], dq, d4[:, 0], d4[:, 1], B=B, H=H, Nq=N,
+                           Nk=max_keys, kv_rows=t["kv"].shape[0], kv_len=kv_len, kv_off=kv_off, q_strides=(C, D),
+                           k_strides=(2 * C, D), v_strides=(2 * C, D), dq_strides=(C, D), dk_strides=(2 * C, D),
+                           dv_strides=(2 * C, D), scale=ca.head_dim ** -0.5)
+        dxb = lin_bwd("q", t["xb"], w_q, b_q, ca.q_linear, dq)
+        dcond = lin_bwd("kv", cond, w_kv, b_kv, ca.kv_linear, dkv)
+        dx1 = torch.empty((M, C), **f32)
+        lib.gate_residual_fwd(dx2, dxb, None, dx1, rows_per_batch=N)          # dx1 = dx2 + float(dxb)
+        # (1) x1 = x + gate_msa * (proj(attn(qkv(xn1))) + b)
+        dy1 = torch.empty((M, C), **bf)
+        lib.gate_residual_bwd(dx1, t["y1"], mod[:, 2], dy1, dm[2], gate_batch_stride=ms, rows_per_batch=N)
+        dao1 = lin_bwd("proj", t["ao1"], w_p, b_p, a.proj, dy1)
+        dqkv = torch.empty_like(t["qkv"])
+        q3, g3 = t["qkv"].view(M, 3, H, D), dqkv.view(M, 3, H, D)
+        st = (3 * C, D)
+        lib.flash_attn_bwd(q3[:, 0], q3[:, 1], q3[:, 2], t["ao1"], dao1, t["lse1"], g3[:, 0], g3[:, 1], g3[:, 2], B=B, H=H, Nq=N,
+                           Nk=N, kv_rows=M, q_strides=st, k_strides=st, v_strides=st, dq_strides=st, dk_strides=st, dv_strides=st,
+                           scale=a.scale)
+        dxn1 = lin_bwd("qkv", t["xn1"], w_qkv, b_qkv, a.qkv, dqkv)
+        dx = torch.empty((M, C), **f32)
+        lib.ln_modulate_bwd(x32, dxn1, mod[:, 1], dx, dm[0], dm[1], mod_batch_stride=ms, rows_per_batch=N, add_in=dx1)
+        pg = [g for tag in ("qkv", "proj", "q", "kv", "cproj", "fc1", "fc2") for g in grads[tag]]
+        return (None, dx, dcond, dm.permute(1, 0, 2), None, None, None, None, None, None, *pg)
+
+
+def block_train(blk, x32, cond, kv_len, kv_off, max_keys, mod, B, N, HW, ckpt: bool):
+    """Training forward of one block: the single-node form where it applies, else the per-op functions (with torch's
+    activation checkpointing around them when `ckpt`)."""
+    plain = blk.attn.sr_ratio == 1 and isinstance(blk.attn.q_norm, torch.nn.Identity)
+    if _BLOCK_FN and plain:
+        _, params = _block_params(blk)
+        return BlockFn.apply(blk, x32, cond, mod, kv_len, kv_off, max_keys, B, N, ckpt, *params)
+    if ckpt:
+        from torch.utils.checkpoint import checkpoint
+        return checkpoint(block_forward_train, blk, x32, cond, kv_len, kv_off, max_keys, mod, B, N, {}, HW, use_reentrant=False,
+                          preserve_rng_state=False)
+    return block_forward_train(blk, x32, cond, kv_len, kv_off, max_keys, mod, B, N, None, HW)

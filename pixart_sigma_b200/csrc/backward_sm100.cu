@@ -160,7 +160,8 @@ template <int kVec>
 __global__ void __launch_bounds__(256) ln_modulate_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dxn,
                                                               const float* __restrict__ scale, float* __restrict__ dx,
                                                               float* __restrict__ dshift, float* __restrict__ dscale,
-                                                              long long mod_bs, int rows_per_batch, int M, float eps) {
+                                                              long long mod_bs, int rows_per_batch, int M, float eps,
+                                                              const float* __restrict__ add_in) {
   constexpr int C = kVec * 128;
   const int warp_global = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -238,6 +239,10 @@ __global__ void __launch_bounds__(256) ln_modulate_bwd_kernel(const float* __res
       o.y = rstd * (d[g].y - mg - v[g].y * mgx);
       o.z = rstd * (d[g].z - mg - v[g].z * mgx);
       o.w = rstd * (d[g].w - mg - v[g].w * mgx);
+      if (add_in != nullptr) {
+        const float4 r = *reinterpret_cast<const float4*>(add_in + (size_t)row * C + col);
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
       *reinterpret_cast<float4*>(orow + col) = o;
     }
   }
@@ -547,7 +552,7 @@ extern "C" int pxa_ln_modulate_bwd(const PxaLnModBwdArgs* args, void* stream) {
   const int grid = (warps + 7) / 8;
   ln_modulate_bwd_kernel<9><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float*>(a.x), reinterpret_cast<const __nv_bfloat16*>(a.dxn), a.scale, reinterpret_cast<float*>(a.dx),
-      a.dshift, a.dscale, a.mod_batch_stride, a.rows_per_batch, a.M, a.eps);
+      a.dshift, a.dscale, a.mod_batch_stride, a.rows_per_batch, a.M, a.eps, a.add_in);
   launch_counter()++;
   PXA_CHECK_CUDA(cudaGetLastError());
   return PXA_OK;

@@ -97,7 +97,7 @@ class GateResidualArgs(C.Structure):
 class LnModBwdArgs(C.Structure):
     _fields_ = [("x", C.c_void_p), ("dxn", C.c_void_p), ("scale", C.c_void_p), ("dx", C.c_void_p), ("dshift", C.c_void_p),
                 ("dscale", C.c_void_p), ("mod_batch_stride", C.c_int64), ("rows_per_batch", C.c_int32),
-                ("M", C.c_int32), ("C", C.c_int32), ("eps", C.c_float)]
+                ("M", C.c_int32), ("C", C.c_int32), ("eps", C.c_float), ("add_in", C.c_void_p)]
 
 
 class KvCompressBwdArgs(C.Structure):
@@ -417,14 +417,18 @@ def gate_residual_bwd(dout: torch.Tensor, y: Optional[torch.Tensor], gate: Optio
 
 
 def ln_modulate_bwd(x: torch.Tensor, dxn: torch.Tensor, scale: torch.Tensor, dx: torch.Tensor, dshift: torch.Tensor,
-                    dscale: torch.Tensor, *, mod_batch_stride: int, rows_per_batch: int, eps: float = 1e-6) -> None:
-    """Backward of ln_modulate: dx written, dshift / dscale (B, C) fp32 accumulated."""
+                    dscale: torch.Tensor, *, mod_batch_stride: int, rows_per_batch: int, eps: float = 1e-6,
+                    add_in: Optional[torch.Tensor] = None) -> None:
+    """Backward of ln_modulate: dx written (= add_in + the gradient through the norm when add_in is given; add_in may be dx
+    itself), dshift / dscale (B, C) fp32 accumulated."""
+    assert add_in is None or (add_in.dtype == torch.float32 and add_in.is_contiguous() and add_in.shape == x.shape)
     assert x.dtype == dx.dtype == torch.float32 and dxn.dtype == torch.bfloat16
     assert x.is_contiguous() and dxn.is_contiguous() and dx.is_contiguous() and dshift.is_contiguous() and dscale.is_contiguous()
     assert dshift.dtype == dscale.dtype == scale.dtype == torch.float32
     M, Cc = x.shape
     args = LnModBwdArgs(x=_ptr(x), dxn=_ptr(dxn), scale=_ptr(scale), dx=_ptr(dx), dshift=_ptr(dshift), dscale=_ptr(dscale),
-                        mod_batch_stride=mod_batch_stride, rows_per_batch=rows_per_batch, M=M, C=Cc, eps=eps)
+                        mod_batch_stride=mod_batch_stride, rows_per_batch=rows_per_batch, M=M, C=Cc, eps=eps,
+                        add_in=_ptr(add_in))
     _check(load().pxa_ln_modulate_bwd(C.byref(args), _stream()), "pxa_ln_modulate_bwd")
 
 

@@ -473,8 +473,9 @@ class PixArtMSBlock(nn.Module):
             mod = _drop_path_gates(mod, self.drop_path_rate)
         x32 = x.reshape(B * N, C).float().contiguous()
         if _wants_grad(self, x, y, t):                                     # training: differentiable kernel ops
-            from .autograd import block_forward_train
-            out = block_forward_train(self, x32, cond, kv_len, kv_off, max(max(lens), 1), mod, B, N, None, tuple(HW))
+            from .autograd import block_train
+            out = block_train(self, x32, cond, kv_len, kv_off, max(max(lens), 1), mod, B, N, tuple(HW),
+                              bool(getattr(self, "grad_checkpointing", False)))
         else:
             _require_kernel_ready(self.attn.qkv.weight, "PixArtMSBlock")
             ln = None
@@ -702,14 +703,9 @@ class PixArtMS(nn.Module):
             mod = blk.scale_shift_table.float()[None] + t0
             if self.training and blk.drop_path_rate > 0:        # drawn here, outside the (recomputed) checkpointed function
                 mod = _drop_path_gates(mod, blk.drop_path_rate)
-            if getattr(blk, "grad_checkpointing", False):
-                # per-call dict: lets the recomputation reuse the attention outputs of the first pass (autograd.py)
-                # preserve_rng_state=False: the block draws no random numbers, and stashing the RNG state reads the device
-                # (not capturable in a CUDA graph)
-                x32 = checkpoint(ag.block_forward_train, blk, x32, cond, kv_len, None, L, mod, B, N, {}, (self.h, self.w),
-                                 use_reentrant=False, preserve_rng_state=False)
-            else:
-                x32 = ag.block_forward_train(blk, x32, cond, kv_len, None, L, mod, B, N, None, (self.h, self.w))
+            # one autograd node per block (autograd.BlockFn, activation checkpointing built in) where it applies
+            x32 = ag.block_train(blk, x32, cond, kv_len, None, L, mod, B, N, (self.h, self.w),
+                                 bool(getattr(blk, "grad_checkpointing", False)))
 
         fl = self.final_layer
         fmod = (fl.scale_shift_table.float()[None] + t[:, None]).contiguous()

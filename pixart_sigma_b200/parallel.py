@@ -97,6 +97,8 @@ class GradBucketReducer:
         for b in self.buckets:
             for p in b["params"]:
                 self._hooks.append(p.register_post_accumulate_grad_hook(lambda _p, b=b: self._ready(b)))
+                # backward kernels that accumulate straight into p.grad (autograd.py) bypass autograd's hook: same signal
+                p._pxa_grad_ready = (lambda b=b: self._ready(b))
         self.start()
 
     def flatten_params(self) -> None:
@@ -176,3 +178,7 @@ class GradBucketReducer:
         for h in self._hooks:
             h.remove()
         self._hooks = []
+        for b in self.buckets:
+            for p in b["params"]:
+                if hasattr(p, "_pxa_grad_ready"):
+                    del p._pxa_grad_ready

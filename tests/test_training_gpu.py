@@ -237,3 +237,24 @@ def test_flat_adamw_matches_torch_adamw():
             assert po.rel_err(pa, pb) < 1e-6, (step, n)
     sd = opt.state_dict()
     assert sd["step"] == 3 and len(sd["state"]) == len(red.buckets)
+
+
+def test_direct_gradient_accumulation_equals_autograd_accumulation():
+    """With a GradBucketReducer the weight / bias gradient kernels accumulate straight into the bucket views (no autograd
+    accumulation pass); the result must equal the gradients autograd accumulates without a reducer, also over two
+    accumulation steps, and the reducer must have seen every bucket complete."""
+    cfg = po.OracleConfig(depth=2, input_size=32, pe_interpolation=0.5)
+    sd = _rounded(po.synthetic_state_dict(cfg, seed=0))
+    x0, t, y, mask, noise = train_inputs(cfg, 2, (32, 32), [10, 600], [300, 50])
+    args = (x0.cuda(), t.cuda(), y.cuda(), mask.cuda())
+    plain = _build_train(cfg, sd, checkpoint=True)
+    for _ in range(2):
+        train_step(plain, IDDPMLoss(), *args, noise=noise.cuda())
+    direct = _build_train(cfg, sd, checkpoint=True)
+    red = GradBucketReducer(direct)
+    red.zero_grad()
+    for _ in range(2):
+        train_step(direct, IDDPMLoss(), *args, noise=noise.cuda(), reducer=red)
+        assert all(b["pending"] == 0 for b in red.buckets)          # every parameter reported its gradient
+    for (n, pa), (_, pb) in zip(plain.named_parameters(), direct.named_parameters()):
+        assert po.rel_err(pb.grad, pa.grad) < 1e-4, n
