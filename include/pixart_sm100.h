@@ -114,6 +114,35 @@ typedef struct PxaGemmArgs {
 } PxaGemmArgs;
 int pxa_gemm_bf16(const PxaGemmArgs* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------- fused Mlp
+ * x32[r, :] += gate[b, :] * ( gelu_tanh(x[r, :] W1^T + b1) W2^T + b2 )        b = r / rows_per_batch
+ * The timm Mlp of PixArtMSBlock with its gate and residual (PixArtMS.py:67,77) as ONE persistent kernel: both GEMMs in one
+ * tile list, the second one group of 256-row panels behind the first, the [M, N1] hidden activations kept in a small ring
+ * (hidden_ws) that lives in L2 instead of streaming through HBM (mlp_sm100.cu).  x = the normalised, modulated bf16
+ * activations (pxa_ln_modulate output); x32 = the fp32 residual stream, updated in place (TMA reduce-add).
+ */
+typedef struct PxaMlpArgs {
+  const void* x;         /* bf16 [M, K1], row stride ldx                                   */
+  const void* w1;        /* bf16 [N1, K1] (mlp.fc1.weight), row stride ldw1                 */
+  const void* b1;        /* bf16 [N1] or NULL                                              */
+  const void* w2;        /* bf16 [N2, N1] (mlp.fc2.weight), row stride ldw2                 */
+  const void* b2;        /* bf16 [N2] or NULL                                              */
+  float* x32;            /* fp32 [M, N2], row stride ldo: residual stream, updated in place */
+  const float* gate;     /* fp32 (b, n) at gate[b*gate_batch_stride + n], or NULL           */
+  int64_t gate_batch_stride;
+  void* hidden_ws;       /* bf16 scratch, >= ring * group * 256 * N1 elements               */
+  int64_t hidden_ws_bytes;
+  void* flags_ws;        /* int32 scratch, >= 2 * ceil(M/256) + ceil(ceil(M/256)/group) ints (zeroed by the call) */
+  int64_t flags_ws_bytes;
+  int32_t rows_per_batch;
+  int32_t M, K1, N1, N2; /* N1 % 256 == 0, N2 % 192 == 0                                   */
+  int32_t ldx, ldw1, ldw2, ldo;
+  int32_t group;         /* 256-row panels per group (0 = 4)                               */
+  int32_t ring;          /* groups held by hidden_ws (0 = 3)                               */
+  int32_t max_ctas;      /* 0 = one CTA per SM; > 0 caps the persistent grid (tests)       */
+} PxaMlpArgs;
+int pxa_mlp_fused_bf16(const PxaMlpArgs* args, void* stream);
+
 /* ------------------------------------------------------------------------------------ LayerNorm + modulate
  * out[r,:] = LN(x[r,:]; eps, no affine) * (1 + scale[b,:]) + shift[b,:]  with b = r / rows_per_batch, bf16 out.
  * Replaces norm1/norm2 + t2i_modulate (PixArtMS.py:58,64,75,77; PixArt_blocks.py:24-25) and the final-layer

@@ -46,6 +46,14 @@ class LnPrepareArgs(C.Structure):
                 ("ldx", C.c_int32)]
 
 
+class MlpArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("x32", C.c_void_p),
+                ("gate", C.c_void_p), ("gate_batch_stride", C.c_int64), ("hidden_ws", C.c_void_p), ("hidden_ws_bytes", C.c_int64),
+                ("flags_ws", C.c_void_p), ("flags_ws_bytes", C.c_int64), ("rows_per_batch", C.c_int32), ("M", C.c_int32),
+                ("K1", C.c_int32), ("N1", C.c_int32), ("N2", C.c_int32), ("ldx", C.c_int32), ("ldw1", C.c_int32), ("ldw2", C.c_int32),
+                ("ldo", C.c_int32), ("group", C.c_int32), ("ring", C.c_int32), ("max_ctas", C.c_int32)]
+
+
 class AdamWArgs(C.Structure):
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
                 ("shadow_bf16", C.c_void_p), ("n", C.c_int64), ("step", C.c_int32), ("lr", C.c_float), ("beta1", C.c_float),
@@ -124,7 +132,7 @@ EXPORTS = ("pxa_transpose_bf16", "pxa_gelu_tanh_bf16", "pxa_gate_residual_fwd", 
            "pxa_ln_modulate_bwd", "pxa_colsum_bf16", "pxa_attn_delta_d72", "pxa_flash_attn_d72_bwd_bf16", "pxa_kv_compress_conv2_ln_bwd",
            "pxa_version", "pxa_last_error", "pxa_launch_count", "pxa_gemm_bf16", "pxa_ln_modulate",
            "pxa_flash_attn_d72_bf16", "pxa_kv_compress_conv2_ln", "pxa_conv3x3_nhwc_bf16", "pxa_dpm_solver_pp_step",
-           "pxa_ln_prepare", "pxa_layernorm_affine_bf16", "pxa_groupnorm_silu_nhwc_bf16", "pxa_adamw_flat")
+           "pxa_ln_prepare", "pxa_layernorm_affine_bf16", "pxa_groupnorm_silu_nhwc_bf16", "pxa_adamw_flat", "pxa_mlp_fused_bf16")
 
 _lib = None
 
@@ -142,7 +150,8 @@ def load() -> C.CDLL:
         for name, struct in (("pxa_gemm_bf16", GemmArgs), ("pxa_ln_modulate", LnModArgs),
                              ("pxa_flash_attn_d72_bf16", AttnArgs), ("pxa_kv_compress_conv2_ln", KvCompressArgs),
                              ("pxa_conv3x3_nhwc_bf16", Conv3x3Args), ("pxa_dpm_solver_pp_step", DpmStepArgs),
-                             ("pxa_ln_prepare", LnPrepareArgs), ("pxa_adamw_flat", AdamWArgs)):
+                             ("pxa_ln_prepare", LnPrepareArgs), ("pxa_adamw_flat", AdamWArgs),
+                             ("pxa_mlp_fused_bf16", MlpArgs)):
             fn = getattr(lib, name)
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(struct), C.c_void_p]
@@ -325,6 +334,36 @@ def conv3x3_nhwc(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.T
     return out
 
 
+MLP_GROUP, MLP_RING = 4, 3
+
+
+def mlp_fused_workspace(M: int, n_hidden: int, device, group: int = MLP_GROUP, ring: int = MLP_RING):
+    """(hidden ring, flag array) for `mlp_fused` at M rows."""
+    panels = (M + 255) // 256
+    hidden = torch.empty(ring * group * 256 * n_hidden, dtype=torch.bfloat16, device=device)
+    flags = torch.empty(2 * panels + (panels + group - 1) // group + 4, dtype=torch.int32, device=device)
+    return hidden, flags
+
+
+def mlp_fused(x: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: torch.Tensor, b2: Optional[torch.Tensor],
+              x32: torch.Tensor, *, gate: Optional[torch.Tensor] = None, gate_batch_stride: int = 0, rows_per_batch: int = 0,
+              hidden_ws: torch.Tensor, flags_ws: torch.Tensor, group: int = MLP_GROUP, ring: int = MLP_RING, max_ctas: int = 0) -> torch.Tensor:
+    """x32 += gate[b] * (gelu_tanh(x @ w1.T + b1) @ w2.T + b2) in ONE persistent kernel (include/pixart_sm100.h, PxaMlpArgs)."""
+    assert x.dtype == w1.dtype == w2.dtype == torch.bfloat16 and x32.dtype == torch.float32 and x.is_cuda
+    assert x.dim() == 2 and x.stride(1) == 1 and w1.stride(1) == 1 and w2.stride(1) == 1 and x32.stride(1) == 1
+    M, K1 = x.shape
+    N1, N2 = w1.shape[0], w2.shape[0]
+    assert w1.shape[1] == K1 and w2.shape[1] == N1 and x32.shape == (M, N2)
+    assert hidden_ws.dtype == torch.bfloat16 and hidden_ws.is_contiguous() and flags_ws.dtype == torch.int32 and flags_ws.is_contiguous()
+    args = MlpArgs(x=_ptr(x), w1=_ptr(w1), b1=_ptr(b1), w2=_ptr(w2), b2=_ptr(b2), x32=_ptr(x32), gate=_ptr(gate),
+                   gate_batch_stride=gate_batch_stride, hidden_ws=_ptr(hidden_ws), hidden_ws_bytes=hidden_ws.numel() * 2,
+                   flags_ws=_ptr(flags_ws), flags_ws_bytes=flags_ws.numel() * 4, rows_per_batch=rows_per_batch or M, M=M, K1=K1,
+                   N1=N1, N2=N2, ldx=x.stride(0), ldw1=w1.stride(0), ldw2=w2.stride(0), ldo=x32.stride(0), group=group, ring=ring,
+                   max_ctas=max_ctas)
+    _check(load().pxa_mlp_fused_bf16(C.byref(args), _stream()), "pxa_mlp_fused_bf16")
+    return x32
+
+
 def adamw_flat(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, *, step: int, lr: float,
                betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2, grad_scale: float = 1.0,
                shadow: Optional[torch.Tensor] = None) -> None:
@@ -349,7 +388,7 @@ def groupnorm_silu_nhwc(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor
         stats_ws = torch.empty(B * groups * 2, dtype=torch.float32, device=x.device)
     assert stats_ws.dtype == torch.float32 and stats_ws.numel() >= B * groups * 2
     _check(load().pxa_groupnorm_silu_nhwc_bf16(_ptr(x), _ptr(out), _ptr(gamma), _ptr(beta), _ptr(stats_ws), B, H * W, Cc, groups,
-                                               eps, int(silu), _stream()), "pxa_groupnorm_silu_nhwc_bf16", "pxa_adamw_flat")
+                                               eps, int(silu), _stream()), "pxa_groupnorm_silu_nhwc_bf16", "pxa_adamw_flat", "pxa_mlp_fused_bf16")
     return out
 
 

@@ -207,6 +207,7 @@ class _Workspace:
         return t
 
 
+_MLP_FUSED = os.environ.get("PXA_MLP_FUSED", "0") == "1"   # Mlp branch as one persistent kernel (mlp_sm100.cu)
 _L2_CHAIN = os.environ.get("PXA_L2_CHAIN", "1") != "0"      # consumer kernels start on the rows their producer wrote last
 
 _LN_FUSE_MIN_ROWS = 128      # a 128-row GEMM tile may span at most two samples (include/pixart_sm100.h)
@@ -411,6 +412,14 @@ class PixArtMSBlock(nn.Module):
             lib.gemm(ao, ca.proj.weight, ca.proj.bias, x32, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x32)
 
         # (3) x += gate_mlp * fc2(gelu_tanh(fc1(LN(x) * (1 + scale_mlp) + shift_mlp)))           PixArtMS.py:77
+        if self._mlp_one_kernel(N, M) and not fused:
+            # the whole Mlp branch as ONE persistent GEMM -> GELU -> GEMM kernel, hidden activations resident in L2 (mlp_sm100.cu)
+            lib.ln_modulate(x32, mod[:, 3], mod[:, 4], xn, mod_batch_stride=ms, rows_per_batch=N, reverse_rows=_L2_CHAIN)
+            hws = ws.get("mlp_ring", (lib.MLP_RING * lib.MLP_GROUP * 256 * mlp.fc1.out_features,), bf, dev)
+            fws = ws.get("mlp_flags", (2 * ((M + 255) // 256) + (M + 255) // 256 // lib.MLP_GROUP + 8,), torch.int32, dev)
+            lib.mlp_fused(xn, mlp.fc1.weight, mlp.fc1.bias, mlp.fc2.weight, mlp.fc2.bias, x32, gate=mod[:, 5], gate_batch_stride=ms,
+                          rows_per_batch=N, hidden_ws=hws, flags_ws=fws)
+            return x32
         hid = ws.get("mlp_hidden", (M, mlp.fc1.out_features), bf, dev)
         if fused:
             lib.gemm(xn, mlp.fc1.weight, None, hid, epilogue=lib.EPI_LN_BIAS_GELU, rows_per_batch=N, ln_u=u[:, n1:], ln_v=v[:, n1:],
@@ -428,6 +437,10 @@ class PixArtMSBlock(nn.Module):
             lib.gemm(hid, mlp.fc2.weight, mlp.fc2.bias, x32, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x32, gate=mod[:, 5],
                      gate_batch_stride=ms, rows_per_batch=N, reverse_tiles=_L2_CHAIN)
         return x32
+
+    def _mlp_one_kernel(self, N: int, M: int) -> bool:
+        """Use pxa_mlp_fused_bf16 for the Mlp branch?  (PXA_MLP_FUSED=1; shapes the kernel is built for)"""
+        return (_MLP_FUSED and N >= 128 and self.mlp.fc1.out_features % 256 == 0 and self.mlp.fc2.out_features % 192 == 0)
 
     def _compress_kv(self, qkv, B, N, HW, ws):
         """K / V token compression (PixArt_blocks.py:97-121). 'conv' sr=2 runs the fused conv+LN kernel; the

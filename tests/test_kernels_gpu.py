@@ -455,3 +455,34 @@ def test_flash_attn_reverse_batch_order_gives_identical_results(variant):
                        k_strides=(H * 72, 72), v_strides=(H * 72, 72), variant=variant, reverse_batch=rev)
         outs.append(out)
     assert torch.equal(outs[0], outs[1])
+
+
+# ------------------------------------------------------------------------------------------------- fused Mlp (one persistent kernel)
+@pytest.mark.parametrize("M,rpb,max_ctas,group,ring", [
+    (256, 256, 0, 4, 3), (2304, 1152, 0, 4, 3), (1000, 500, 0, 2, 2), (4096, 1024, 6, 2, 2), (8192, 4096, 0, 4, 3),
+    (5120, 1024, 20, 1, 2),
+])
+def test_mlp_fused_matches_two_gemms(M, rpb, max_ctas, group, ring):
+    """pxa_mlp_fused_bf16 (GEMM -> GELU -> GEMM in one launch, hidden ring in L2, cross-CTA dependency counters) against the
+    fp32 computation.  Few clusters (max_ctas) and small rings / groups make the tile list's dependencies bite: fc2 tiles
+    really wait for fc1 tiles of other clusters and ring slots are really recycled."""
+    C, Hd = 1152, 4608
+    B = M // rpb
+    xn = _randn(M, C, seed=120)
+    w1, b1 = _randn(Hd, C, seed=121, scale=C ** -0.5), _randn(Hd, seed=122, scale=0.1)
+    w2, b2 = _randn(C, Hd, seed=123, scale=Hd ** -0.5), _randn(C, seed=124, scale=0.1)
+    x32 = _randn(M, C, seed=125, dtype=torch.float32)
+    gate = _randn(B, 6, C, seed=126, dtype=torch.float32)
+    hid = F.gelu(F.linear(xn.float(), w1.float(), b1.float()), approximate="tanh").to(torch.bfloat16).float()
+    want = x32 + gate[:, 5].repeat_interleave(rpb, 0) * F.linear(hid, w2.float(), b2.float())
+    hws, fws = lib.mlp_fused_workspace(M, Hd, DEV, group=group, ring=ring)
+    hws.fill_(float("nan"))
+    lib.mlp_fused(xn, w1, b1, w2, b2, x32, gate=gate[:, 5], gate_batch_stride=6 * C, rows_per_batch=rpb, hidden_ws=hws,
+                  flags_ws=fws, group=group, ring=ring, max_ctas=max_ctas)
+    torch.cuda.synchronize()
+    assert torch.isfinite(x32).all()
+    assert po.rel_err(x32, want) < 2e-4
+    lib.mlp_fused(xn, w1, b1, w2, b2, x32, gate=gate[:, 5], gate_batch_stride=6 * C, rows_per_batch=rpb, hidden_ws=hws,
+                  flags_ws=fws, group=group, ring=ring, max_ctas=max_ctas)        # the counters are reset by every call
+    want2 = want + gate[:, 5].repeat_interleave(rpb, 0) * F.linear(hid, w2.float(), b2.float())
+    assert po.rel_err(x32, want2) < 2e-4
