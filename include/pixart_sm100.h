@@ -138,8 +138,12 @@ typedef struct PxaMlpArgs {
   int32_t M, K1, N1, N2; /* N1 % 256 == 0, N2 % 192 == 0                                   */
   int32_t ldx, ldw1, ldw2, ldo;
   int32_t group;         /* 256-row panels per group (0 = 4)                               */
-  int32_t ring;          /* groups held by hidden_ws (0 = 3)                               */
+  int32_t ring;          /* groups held by hidden_ws (0 = lag + 2)                         */
   int32_t max_ctas;      /* 0 = one CTA per SM; > 0 caps the persistent grid (tests)       */
+  int32_t lag;           /* fc2 runs `lag` groups behind fc1 in the tile list (0 = 1); ring > lag, ring >= lag + 2 keeps
+                            fc1 from waiting on the slot it is about to overwrite (ring 0 = lag + 2)                      */
+  int32_t k_splits;      /* fc2 tiles reduce over N1 / k_splits each and are summed by the reduce-add epilogue (0 = auto:
+                            the split that makes a fc2 tile cost what a fc1 tile costs, 3 for 1152 -> 4608 -> 1152)        */
 } PxaMlpArgs;
 int pxa_mlp_fused_bf16(const PxaMlpArgs* args, void* stream);
 

@@ -45,8 +45,10 @@ static_assert(kMlpStages >= 4, "smem ring too shallow");
 struct MlpParams {
   GemmParams p1;     // fc1: bias = b1, out = hidden ring (bf16, ldo = N1), M = ring rows, N = N1, K = K1
   GemmParams p2;     // fc2: bias = b2, gate, out = residual = x32 (fp32, ldo = N2), M, N = N2, K = N1
-  int panels, group, ring, ngroups;
-  int t1, t2;        // tiles per panel
+  GemmParams p2nb;   // fc2 without the bias: K-splits 1.. of an output tile add only gate * acc
+  int panels, group, ring, ngroups, lag;
+  int ksplit;        // fc2 tiles cover N1 / ksplit of the reduction each (the reduce-add epilogue sums them)
+  int t1, t2;        // tiles per panel (t2 = N2 / 192 * ksplit, K-split fastest)
   int* flags;        // [panels][2]
   int* done2;        // [ngroups]
 };
@@ -58,26 +60,41 @@ struct MlpTile {
 
 PXA_DEVICE int mlp_group_panels(const MlpParams& q, int g) { return min(q.group, q.panels - g * q.group); }
 
-// tile list position -> tile: fc1(g0) | fc1(g1) fc2(g0) | ... | fc2(g_last)
+// tile list position -> tile.  Segment s (0 <= s < ngroups + lag) holds fc1(group s) if s < ngroups, then fc2(group s - lag)
+// if s >= lag: for lag = 1   fc1(g0) | fc1(g1) fc2(g0) | ... | fc2(g_last).  Every group but the last is full, so the head
+// (fc1 only) and the regular middle segments are found by division and only the <= lag + 1 segments around the ragged last
+// group are walked.
 PXA_DEVICE MlpTile mlp_decode(const MlpParams& q, int t) {
   MlpTile r;
-  int a0 = mlp_group_panels(q, 0) * q.t1;
-  if (t < a0) {
-    r.kind = 0; r.grp = 0; r.panel = t / q.t1; r.n = t % q.t1;
+  const int G1 = q.group * q.t1, G2 = q.group * q.t2;
+  const int nh = min(q.lag, q.ngroups - 1);          // full fc1-only segments
+  if (t < nh * G1) {
+    r.kind = 0; r.grp = t / G1; r.panel = t / q.t1; r.n = t % q.t1;
     return r;
   }
-  t -= a0;
-  for (int s = 1; s < q.ngroups; ++s) {
-    const int a = mlp_group_panels(q, s) * q.t1, b = mlp_group_panels(q, s - 1) * q.t2;
-    if (t < a + b) {
-      if (t < a) { r.kind = 0; r.grp = s; r.panel = s * q.group + t / q.t1; r.n = t % q.t1; }
-      else { t -= a; r.kind = 1; r.grp = s - 1; r.panel = (s - 1) * q.group + t / q.t2; r.n = t % q.t2; }
+  t -= nh * G1;
+  int s = nh;
+  if (q.lag < q.ngroups - 1) {
+    const int nm = q.ngroups - 1 - q.lag;            // regular segments fc1(s) fc2(s - lag), both groups full
+    if (t < nm * (G1 + G2)) {
+      const int k = t / (G1 + G2);
+      s += k;
+      t -= k * (G1 + G2);
+      if (t < G1) { r.kind = 0; r.grp = s; r.panel = s * q.group + t / q.t1; r.n = t % q.t1; }
+      else { t -= G1; r.kind = 1; r.grp = s - q.lag; r.panel = r.grp * q.group + t / q.t2; r.n = t % q.t2; }
       return r;
     }
-    t -= a + b;
+    t -= nm * (G1 + G2);
+    s += nm;
   }
-  r.kind = 1; r.grp = q.ngroups - 1; r.panel = (q.ngroups - 1) * q.group + t / q.t2; r.n = t % q.t2;
-  return r;
+  for (;; ++s) {
+    const int a = s < q.ngroups ? mlp_group_panels(q, s) * q.t1 : 0;
+    const int b = s >= q.lag ? mlp_group_panels(q, s - q.lag) * q.t2 : 0;
+    if (t < a) { r.kind = 0; r.grp = s; r.panel = s * q.group + t / q.t1; r.n = t % q.t1; return r; }
+    t -= a;
+    if (t < b || s == q.ngroups + q.lag - 1) { r.kind = 1; r.grp = s - q.lag; r.panel = r.grp * q.group + t / q.t2; r.n = t % q.t2; return r; }
+    t -= b;
+  }
 }
 // first row of panel `panel` inside the hidden ring
 PXA_DEVICE int mlp_ring_row(const MlpParams& q, int panel) {
@@ -134,7 +151,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   const int num_tiles = q.panels * (q.t1 + q.t2);
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
-  const int nkb1 = (q.p1.K + kBK - 1) / kBK, nkb2 = (q.p2.K + kBK - 1) / kBK;
+  const int nkb1 = (q.p1.K + kBK - 1) / kBK, nkb2 = q.p2.K / kBK / q.ksplit;      // k-blocks per tile
 
   if (warp == 0) {
     // ================================================================ TMA producer (both CTAs)
@@ -161,12 +178,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           // order the async-proxy (TMA) reads behind the acquire
           spin_until(q.flags + tl.panel * 2 + rank, q.t1);
           fence_proxy_async_all();
-          for (int kb = 0; kb < nkb2; ++kb) {
+          const int n2 = tl.n / q.ksplit, kb0 = (tl.n % q.ksplit) * nkb2;
+          for (int kb = kb0; kb < kb0 + nkb2; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * kMlpStage;
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (kMlpStageA + (kMlpBN2 / 2) * kBK * 2));
             tma_load_2d_pair(sa, &tm_h, &full_bar[stage], kb * kBK, hrow, kEvictNormal);
-            tma_load_2d_pair(sa + kMlpStageA, &tm_w2, &full_bar[stage], kb * kBK, tl.n * kMlpBN2 + rank * (kMlpBN2 / 2), kEvictLast);
+            tma_load_2d_pair(sa + kMlpStageA, &tm_w2, &full_bar[stage], kb * kBK, n2 * kMlpBN2 + rank * (kMlpBN2 / 2), kEvictLast);
             if (++stage == kMlpStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -222,8 +240,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       const MlpTile tl = mlp_decode(q, tile);
       const int m0 = tl.panel * (2 * kBM) + rank * kBM;
       const int hrow = mlp_ring_row(q, tl.panel) + rank * kBM;
-      const GemmParams& p = tl.kind == 0 ? q.p1 : q.p2;
-      const int n0 = tl.n * (tl.kind == 0 ? kMlpBN1 : kMlpBN2);
+      const GemmParams& p = tl.kind == 0 ? q.p1 : (tl.n % q.ksplit == 0 ? q.p2 : q.p2nb);
+      const int n0 = tl.kind == 0 ? tl.n * kMlpBN1 : (tl.n / q.ksplit) * kMlpBN2;
       const int nch = (tl.kind == 0 ? kMlpBN1 : kMlpBN2) / 32;
       EpiConst* cb = consts + (titer & 1);
       if (tid < kNumEpiThreads) {
@@ -338,11 +356,20 @@ extern "C" int pxa_mlp_fused_bf16(const PxaMlpArgs* args, void* stream) {
   MlpParams q;
   q.panels = (a.M + 2 * kBM - 1) / (2 * kBM);
   q.group = a.group > 0 ? a.group : 4;
-  q.ring = a.ring > 0 ? a.ring : 3;
-  if (q.ring < 2) return fail(PXA_ERR_ARG, "ring must be >= 2");
   q.ngroups = (q.panels + q.group - 1) / q.group;
+  q.lag = a.lag > 0 ? a.lag : 1;
+  if (q.lag > q.ngroups) q.lag = q.ngroups;          // all of fc1, then all of fc2
+  q.ring = a.ring > 0 ? a.ring : q.lag + 2;
+  // fc1(g) reuses the slot of group g - ring, whose fc2 tiles sit in segment g - ring + lag: that must be an EARLIER segment
+  if (q.ring < q.lag + 1) return fail(PXA_ERR_ARG, "ring (%d) must be > lag (%d)", q.ring, q.lag);
   q.t1 = a.N1 / kMlpBN1;
-  q.t2 = a.N2 / kMlpBN2;
+  // K-split of fc2 so that its 256 x 192 tiles cost what a 256 x 256 fc1 tile costs (N1 / ksplit * 192 ~ K1 * 256): a static
+  // round-robin over a list that mixes tiles of 1x and 3x duration leaves the clusters badly balanced
+  q.ksplit = a.k_splits > 0 ? a.k_splits : (int)((2LL * a.N1 * kMlpBN2 + (long long)a.K1 * kMlpBN1) / (2LL * a.K1 * kMlpBN1));
+  if (q.ksplit < 1) q.ksplit = 1;
+  while (q.ksplit > 1 && (a.N1 / kBK) % q.ksplit) --q.ksplit;
+  if (a.N1 % kBK) return fail(PXA_ERR_ARG, "N1 must be a multiple of 64");
+  q.t2 = a.N2 / kMlpBN2 * q.ksplit;
   const long long ring_rows = (long long)q.ring * q.group * 2 * kBM;
   if (a.hidden_ws_bytes < ring_rows * a.N1 * 2) return fail(PXA_ERR_ARG, "hidden_ws too small: %lld bytes needed", ring_rows * a.N1 * 2);
   const long long flag_ints = (long long)q.panels * 2 + q.ngroups;
@@ -402,6 +429,8 @@ extern "C" int pxa_mlp_fused_bf16(const PxaMlpArgs* args, void* stream) {
   q.p2.gate = a.gate; q.p2.gate_batch_stride = a.gate_batch_stride;
   q.p2.rows_per_batch = rpb;
   q.p2.M = a.M; q.p2.N = a.N2; q.p2.K = a.N1; q.p2.ldo = a.ldo;
+  q.p2nb = q.p2;
+  q.p2nb.bias = nullptr;
   PXA_CHECK_CUDA(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlpSmem));
   int clusters = device_info().sms / 2;
   if (a.max_ctas > 0 && a.max_ctas / 2 < clusters) clusters = a.max_ctas / 2 > 0 ? a.max_ctas / 2 : 1;

@@ -51,7 +51,7 @@ class MlpArgs(C.Structure):
                 ("gate", C.c_void_p), ("gate_batch_stride", C.c_int64), ("hidden_ws", C.c_void_p), ("hidden_ws_bytes", C.c_int64),
                 ("flags_ws", C.c_void_p), ("flags_ws_bytes", C.c_int64), ("rows_per_batch", C.c_int32), ("M", C.c_int32),
                 ("K1", C.c_int32), ("N1", C.c_int32), ("N2", C.c_int32), ("ldx", C.c_int32), ("ldw1", C.c_int32), ("ldw2", C.c_int32),
-                ("ldo", C.c_int32), ("group", C.c_int32), ("ring", C.c_int32), ("max_ctas", C.c_int32)]
+                ("ldo", C.c_int32), ("group", C.c_int32), ("ring", C.c_int32), ("max_ctas", C.c_int32), ("lag", C.c_int32), ("k_splits", C.c_int32)]
 
 
 class AdamWArgs(C.Structure):
@@ -334,7 +334,13 @@ def conv3x3_nhwc(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.T
     return out
 
 
-MLP_GROUP, MLP_RING = 4, 3
+def _env_int(name: str, default: int) -> int:
+    return int(os.environ.get(name, default))
+
+
+# fc2 trails fc1 by LAG groups of GROUP 256-row panels; the ring holds RING = LAG + 2 groups (mlp_sm100.cu)
+MLP_GROUP, MLP_LAG = _env_int("PXA_MLP_GROUP", 2), _env_int("PXA_MLP_LAG", 4)
+MLP_RING = _env_int("PXA_MLP_RING", MLP_LAG + 2)
 
 
 def mlp_fused_workspace(M: int, n_hidden: int, device, group: int = MLP_GROUP, ring: int = MLP_RING):
@@ -347,7 +353,8 @@ def mlp_fused_workspace(M: int, n_hidden: int, device, group: int = MLP_GROUP, r
 
 def mlp_fused(x: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: torch.Tensor, b2: Optional[torch.Tensor],
               x32: torch.Tensor, *, gate: Optional[torch.Tensor] = None, gate_batch_stride: int = 0, rows_per_batch: int = 0,
-              hidden_ws: torch.Tensor, flags_ws: torch.Tensor, group: int = MLP_GROUP, ring: int = MLP_RING, max_ctas: int = 0) -> torch.Tensor:
+              hidden_ws: torch.Tensor, flags_ws: torch.Tensor, group: int = MLP_GROUP, ring: int = MLP_RING, lag: int = MLP_LAG,
+              max_ctas: int = 0, k_splits: int = 0) -> torch.Tensor:
     """x32 += gate[b] * (gelu_tanh(x @ w1.T + b1) @ w2.T + b2) in ONE persistent kernel (include/pixart_sm100.h, PxaMlpArgs)."""
     assert x.dtype == w1.dtype == w2.dtype == torch.bfloat16 and x32.dtype == torch.float32 and x.is_cuda
     assert x.dim() == 2 and x.stride(1) == 1 and w1.stride(1) == 1 and w2.stride(1) == 1 and x32.stride(1) == 1
@@ -359,7 +366,7 @@ def mlp_fused(x: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], w2:
                    gate_batch_stride=gate_batch_stride, hidden_ws=_ptr(hidden_ws), hidden_ws_bytes=hidden_ws.numel() * 2,
                    flags_ws=_ptr(flags_ws), flags_ws_bytes=flags_ws.numel() * 4, rows_per_batch=rows_per_batch or M, M=M, K1=K1,
                    N1=N1, N2=N2, ldx=x.stride(0), ldw1=w1.stride(0), ldw2=w2.stride(0), ldo=x32.stride(0), group=group, ring=ring,
-                   max_ctas=max_ctas)
+                   max_ctas=max_ctas, lag=lag, k_splits=k_splits)
     _check(load().pxa_mlp_fused_bf16(C.byref(args), _stream()), "pxa_mlp_fused_bf16")
     return x32
 

@@ -416,7 +416,7 @@ class PixArtMSBlock(nn.Module):
             # the whole Mlp branch as ONE persistent GEMM -> GELU -> GEMM kernel, hidden activations resident in L2 (mlp_sm100.cu)
             lib.ln_modulate(x32, mod[:, 3], mod[:, 4], xn, mod_batch_stride=ms, rows_per_batch=N, reverse_rows=_L2_CHAIN)
             hws = ws.get("mlp_ring", (lib.MLP_RING * lib.MLP_GROUP * 256 * mlp.fc1.out_features,), bf, dev)
-            fws = ws.get("mlp_flags", (2 * ((M + 255) // 256) + (M + 255) // 256 // lib.MLP_GROUP + 8,), torch.int32, dev)
+            fws = ws.get("mlp_flags", (3 * ((M + 255) // 256) + 8,), torch.int32, dev)
             lib.mlp_fused(xn, mlp.fc1.weight, mlp.fc1.bias, mlp.fc2.weight, mlp.fc2.bias, x32, gate=mod[:, 5], gate_batch_stride=ms,
                           rows_per_batch=N, hidden_ws=hws, flags_ws=fws)
             return x32

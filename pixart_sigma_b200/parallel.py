@@ -96,9 +96,11 @@ class GradBucketReducer:
         self.overlap = True        # False: no collective from the hooks (CUDA-graph capture); finish() reduces every bucket
         for b in self.buckets:
             for p in b["params"]:
-                self._hooks.append(p.register_post_accumulate_grad_hook(lambda _p, b=b: self._ready(b)))
-                # backward kernels that accumulate straight into p.grad (autograd.py) bypass autograd's hook: same signal
-                p._pxa_grad_ready = (lambda b=b: self._ready(b))
+                self._hooks.append(p.register_post_accumulate_grad_hook(lambda _p, b=b: self._ready(b, _p)))
+                # backward kernels that accumulate straight into p.grad (autograd.py) hand autograd no gradient; whether its
+                # post-accumulate hook still fires for such a parameter depends on the torch version, so they signal as well
+                # and `_ready` counts every parameter once per step
+                p._pxa_grad_ready = (lambda b=b, p=p: self._ready(b, p))
         self.start()
 
     def flatten_params(self) -> None:
@@ -138,7 +140,7 @@ class GradBucketReducer:
         """Arm the buckets for one backward pass (gradients are NOT zeroed: call `zero_grad()` between optimizer steps)."""
         self.check_views()
         for b in self.buckets:
-            b["pending"], b["work"] = len(b["params"]), None
+            b["pending"], b["work"], b["seen"] = len(b["params"]), None, set()
 
     def zero_grad(self) -> None:
         for b in self.buckets:
@@ -151,7 +153,10 @@ class GradBucketReducer:
             buf = b["wire"].copy_(b["flat"])
         b["work"] = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
-    def _ready(self, b) -> None:
+    def _ready(self, b, p) -> None:
+        if id(p) in b["seen"]:
+            return
+        b["seen"].add(id(p))
         b["pending"] -= 1
         if b["pending"] == 0 and self.world > 1 and self.overlap:
             self._launch(b)

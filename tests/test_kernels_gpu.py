@@ -458,14 +458,15 @@ def test_flash_attn_reverse_batch_order_gives_identical_results(variant):
 
 
 # ------------------------------------------------------------------------------------------------- fused Mlp (one persistent kernel)
-@pytest.mark.parametrize("M,rpb,max_ctas,group,ring", [
-    (256, 256, 0, 4, 3), (2304, 1152, 0, 4, 3), (1000, 500, 0, 2, 2), (4096, 1024, 6, 2, 2), (8192, 4096, 0, 4, 3),
-    (5120, 1024, 20, 1, 2),
+@pytest.mark.parametrize("M,rpb,max_ctas,group,ring,lag,ks", [
+    (256, 256, 0, 4, 3, 1, 0), (2304, 1152, 0, 4, 3, 1, 1), (1000, 500, 0, 2, 2, 1, 0), (4096, 1024, 6, 2, 2, 1, 0),
+    (8192, 4096, 0, 4, 3, 1, 1), (5120, 1024, 20, 1, 2, 1, 0), (8192, 4096, 0, 2, 6, 4, 0), (5120, 1024, 10, 1, 4, 3, 2),
+    (2304, 1152, 0, 2, 7, 6, 0), (7000, 3500, 0, 3, 3, 2, 6), (16384, 4096, 0, 1, 10, 8, 0),
 ])
-def test_mlp_fused_matches_two_gemms(M, rpb, max_ctas, group, ring):
+def test_mlp_fused_matches_two_gemms(M, rpb, max_ctas, group, ring, lag, ks):
     """pxa_mlp_fused_bf16 (GEMM -> GELU -> GEMM in one launch, hidden ring in L2, cross-CTA dependency counters) against the
     fp32 computation.  Few clusters (max_ctas) and small rings / groups make the tile list's dependencies bite: fc2 tiles
-    really wait for fc1 tiles of other clusters and ring slots are really recycled."""
+    really wait for fc1 tiles of other clusters and ring slots are really recycled; ks = K-splits of fc2 (0 = auto = 3)."""
     C, Hd = 1152, 4608
     B = M // rpb
     xn = _randn(M, C, seed=120)
@@ -478,11 +479,11 @@ def test_mlp_fused_matches_two_gemms(M, rpb, max_ctas, group, ring):
     hws, fws = lib.mlp_fused_workspace(M, Hd, DEV, group=group, ring=ring)
     hws.fill_(float("nan"))
     lib.mlp_fused(xn, w1, b1, w2, b2, x32, gate=gate[:, 5], gate_batch_stride=6 * C, rows_per_batch=rpb, hidden_ws=hws,
-                  flags_ws=fws, group=group, ring=ring, max_ctas=max_ctas)
+                  flags_ws=fws, group=group, ring=ring, lag=lag, max_ctas=max_ctas, k_splits=ks)
     torch.cuda.synchronize()
     assert torch.isfinite(x32).all()
     assert po.rel_err(x32, want) < 2e-4
     lib.mlp_fused(xn, w1, b1, w2, b2, x32, gate=gate[:, 5], gate_batch_stride=6 * C, rows_per_batch=rpb, hidden_ws=hws,
-                  flags_ws=fws, group=group, ring=ring, max_ctas=max_ctas)        # the counters are reset by every call
+                  flags_ws=fws, group=group, ring=ring, lag=lag, max_ctas=max_ctas, k_splits=ks)        # the counters are reset by every call
     want2 = want + gate[:, 5].repeat_interleave(rpb, 0) * F.linear(hid, w2.float(), b2.float())
     assert po.rel_err(x32, want2) < 2e-4

@@ -1,6 +1,6 @@
 """Mlp branch at the c3 shape (M = 8 x 4096): fc1+GELU and fc2+gated-residual as two launches vs pxa_mlp_fused_bf16 (one
-persistent kernel, hidden ring in L2) for a few (group, ring) choices.  CUDA events, L2 flush (256 MB write) before every
-repetition.  usage: python tools/mlp_fused_bench.py [M]"""
+persistent kernel, hidden ring in L2) for a few (group, lag, ring, fc2 K-split) choices.  CUDA events, L2 flush (256 MB write) before every
+repetition.  usage: python tools/mlp_fused_bench.py [M [group,lag,ring,ksplit ...]]"""
 import os
 import sys
 
@@ -44,8 +44,11 @@ def two():
 
 ms = timeit(two)
 print(f"two launches (fc1 + GELU, fc2 + gated residual, L2 chaining): {ms * 1e3:8.1f} us ({4.0 * M * C * HID / ms / 1e9:6.0f} TFLOP/s)", flush=True)
-for group, ring in ((4, 3), (2, 3), (8, 3), (4, 2), (1, 4)):
+cfgs = ((8, 1, 3, 1), (8, 1, 3, 3), (4, 1, 3, 3), (4, 2, 4, 3), (2, 4, 6, 3), (1, 8, 10, 3), (1, 4, 6, 3), (2, 2, 4, 3), (1, 12, 14, 3), (2, 4, 6, 2))
+if len(sys.argv) > 2:
+    cfgs = tuple(tuple(int(v) for v in c.split(",")) for c in sys.argv[2:])
+for group, lag, ring, ks in cfgs:
     hws, fws = lib.mlp_fused_workspace(M, HID, dev, group=group, ring=ring)
-    msf = timeit(lambda: lib.mlp_fused(xn, w1, b1, w2, b2, x32, hidden_ws=hws, flags_ws=fws, group=group, ring=ring, **kw))
-    print(f"one persistent kernel, group {group} ring {ring} ({hws.numel() * 2 / 2 ** 20:5.1f} MiB hidden ring): {msf * 1e3:8.1f} us "
-          f"({4.0 * M * C * HID / msf / 1e9:6.0f} TFLOP/s)", flush=True)
+    msf = timeit(lambda: lib.mlp_fused(xn, w1, b1, w2, b2, x32, hidden_ws=hws, flags_ws=fws, group=group, ring=ring, lag=lag, k_splits=ks, **kw))
+    print(f"one persistent kernel, group {group} lag {lag} ring {ring} fc2 k-splits {ks} ({hws.numel() * 2 / 2 ** 20:5.1f} MiB hidden ring): "
+          f"{msf * 1e3:8.1f} us ({4.0 * M * C * HID / msf / 1e9:6.0f} TFLOP/s)", flush=True)
