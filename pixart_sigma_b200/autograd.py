@@ -331,6 +331,47 @@ class SelfAttnFn(torch.autograd.Function):
         return dqkv, None, None, None, None, None
 
 
+class QkNormFn(torch.autograd.Function):
+    """qkv (M, 3C) bf16 with q_norm / k_norm (nn.LayerNorm(C), affine) applied to the q and k slices (PixArt_blocks.py:133-134).
+    Backward: the LayerNorm-modulate backward kernel with one "sample" spanning all rows, scale = weight - 1, shift = bias --
+    its dscale / dshift column sums are the gradients of weight / bias."""
+
+    @staticmethod
+    def forward(ctx, qkv, qw, qb, kw, kb, eps):
+        out = qkv.clone()
+        C = qkv.shape[1] // 3
+        bf = torch.bfloat16
+        lib.layernorm_affine_(out[:, :C], qw.to(bf), qb.to(bf), eps=eps)
+        lib.layernorm_affine_(out[:, C:2 * C], kw.to(bf), kb.to(bf), eps=eps)
+        ctx.save_for_backward(qkv, qw, kw)
+        ctx.eps = eps
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        qkv, qw, kw = ctx.saved_tensors
+        M, C3 = qkv.shape
+        C = C3 // 3
+        dqkv = d_out.clone()
+        grads = []
+        for i, w in enumerate((qw, kw)):
+            x32 = qkv[:, i * C:(i + 1) * C].float().contiguous()
+            dx = torch.empty_like(x32)
+            dsh = torch.zeros((1, C), dtype=torch.float32, device=qkv.device)
+            dsc = torch.zeros((1, C), dtype=torch.float32, device=qkv.device)
+            lib.ln_modulate_bwd(x32, d_out[:, i * C:(i + 1) * C].contiguous(), (w.float() - 1.0).view(1, C).contiguous(), dx, dsh, dsc,
+                                mod_batch_stride=C, rows_per_batch=M, eps=ctx.eps)
+            dqkv[:, i * C:(i + 1) * C] = dx
+            grads += [dsc.view(C).to(w.dtype), dsh.view(C).to(w.dtype)]
+        return dqkv, grads[0], grads[1], grads[2], grads[3], None
+
+
+def _qk_norm(a, qkv: torch.Tensor) -> torch.Tensor:
+    if isinstance(a.q_norm, torch.nn.Identity):
+        return qkv
+    return QkNormFn.apply(qkv, a.q_norm.weight, a.q_norm.bias, a.k_norm.weight, a.k_norm.bias, a.q_norm.eps)
+
+
 class KvCompressFn(torch.autograd.Function):
     """(kc, vc) = LN(conv2x2s2(k)), LN(conv2x2s2(v)) on the k / v slices of the qkv GEMM output (PixArt_blocks.py:97-121,
     'conv' sampling, scale factor 2).  sr = the depthwise Conv2d, norm = the LayerNorm (owners of the bf16 shadows)."""
@@ -474,15 +515,13 @@ def block_forward_train(blk, x32: torch.Tensor, cond: torch.Tensor, kv_len: Opti
     H = a.num_heads
     if HW is None:
         HW = (int(N ** 0.5),) * 2
-    if not isinstance(a.q_norm, torch.nn.Identity):
-        raise NotImplementedError("qk_norm=True is not supported by the kernel block yet")
     mod = mod.contiguous()
     # (1) x += gate_msa * proj(attn(LN(x) * (1 + scale_msa) + shift_msa))                         PixArtMS.py:75
     xn = LnModulateFn.apply(x32, mod, 0, 1, N)
     if a.sr_ratio > 1:                                                       # KV token compression, PixArt_blocks.py:137-139
-        ao = _compressed_self_attention(a, linear(xn, a.qkv), B, H, N, HW)
+        ao = _compressed_self_attention(a, _qk_norm(a, linear(xn, a.qkv)), B, H, N, HW)
     else:
-        ao = SelfAttnFn.apply(linear(xn, a.qkv), B, H, N, a.scale, keep)
+        ao = SelfAttnFn.apply(_qk_norm(a, linear(xn, a.qkv)), B, H, N, a.scale, keep)
     x32 = LinearGateResidualFn.apply(ao, a.proj.weight, a.proj.bias, a.proj, x32, mod, 2, N)
     # (2) x += proj(cross_attn(x, cond))                                                          PixArtMS.py:76
     qx = linear(x32.to(torch.bfloat16), ca.q_linear)

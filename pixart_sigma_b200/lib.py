@@ -339,7 +339,7 @@ def _env_int(name: str, default: int) -> int:
 
 
 # fc2 trails fc1 by LAG groups of GROUP 256-row panels; the ring holds RING = LAG + 2 groups (mlp_sm100.cu)
-MLP_GROUP, MLP_LAG = _env_int("PXA_MLP_GROUP", 2), _env_int("PXA_MLP_LAG", 4)
+MLP_GROUP, MLP_LAG = _env_int("PXA_MLP_GROUP", 4), _env_int("PXA_MLP_LAG", 1)
 MLP_RING = _env_int("PXA_MLP_RING", MLP_LAG + 2)
 
 

@@ -114,6 +114,44 @@ def test_kv_compressed_block_gradients_match_oracle(sampling):
     assert max(errs.values()) < 2e-2, errs
 
 
+def test_qk_norm_block_gradients_match_oracle():
+    """Training with qk_norm=True (PixArt_blocks.py:133-134): q_norm / k_norm on the qkv GEMM output, their backward through the
+    LayerNorm-modulate backward kernel (autograd.QkNormFn)."""
+    B, hw, lens, C = 2, (16, 16), [300, 40], 1152
+    N = hw[0] * hw[1]
+    cfg = po.OracleConfig(depth=1, qk_norm=True)
+    sd = _rounded(po.synthetic_state_dict(cfg, seed=9))
+    kw = dict(type="PixArtMS", depth=1, input_size=32, pe_interpolation=0.5, model_max_length=300, qk_norm=True)
+    with torch.device("cuda"):
+        m = build_model(kw)
+    m.load_state_dict(sd, strict=False)
+    blk = m.float().train().blocks[0]
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(B, N, C, generator=g)
+    t0 = torch.randn(B, 6 * C, generator=g) * 0.3
+    ycat = torch.randn(sum(lens), C, generator=g).to(torch.bfloat16).float()
+    dout = torch.randn(B, N, C, generator=g)
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith("blocks.0.")}
+    xo = x.clone().requires_grad_(True)
+    want = po.block_forward(sdo, "blocks.0", xo, ycat[None], t0, lens, hw, 16, 1, None, True)
+    want.backward(dout)
+    xk = x.clone().cuda().requires_grad_(True)
+    got = blk(xk, ycat.cuda()[None], t0.cuda(), lens, hw)
+    ferr = po.rel_err(got.detach().cpu(), want.detach())
+    assert ferr < 2e-3, ferr
+    got.backward(dout.cuda())
+    errs = {"x": po.rel_err(xk.grad.cpu(), xo.grad)}
+    for n, p in blk.named_parameters():
+        if n == "attn.k_norm.bias":
+            # a constant added to every key moves all logits of a query by the same amount: the exact gradient is ZERO and both
+            # sides hold rounding noise only -- compare its size with the (real) gradient of q_norm.bias instead
+            errs[n] = (p.grad.float().norm() / blk.attn.q_norm.bias.grad.float().norm()).item()
+            continue
+        errs[n] = po.rel_err(p.grad.float().cpu(), sdo["blocks.0." + n].grad)
+    _log(f"qk_norm block grads: fwd={ferr:.2e} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
+    assert max(errs.values()) < 2e-2, errs
+
+
 def _oracle_step(cfg, sd, x0, t, y, mask, noise):
     sdo = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
     model = lambda x, timestep, **kw: po.forward_grad(sdo, cfg, x, timestep.float(), kw["y"], mask=kw["mask"])
