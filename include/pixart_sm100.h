@@ -240,8 +240,10 @@ typedef struct PxaAttnArgs {
                        backward pass recomputes P from (training); NULL for inference                              */
   int32_t reverse_batch; /* 1: CTAs take the samples from the last to the first (same L2 argument as PxaGemmArgs.reverse_tiles:
                             the qkv rows of the last samples are the ones the QKV GEMM has just written)                   */
-  int32_t variant;  /* 0 = auto, 2 = two 128-row query tiles per CTA with a double-buffered S (attn_sm100.cu), 3 = three tiles
-                       with a single S buffer each: three softmax warps per SM sub-partition (attn3_sm100.cu)                */
+  int32_t variant;  /* 0 = auto (= 4).  Work item = 256 query rows of one (sample, head), two 128-row tiles with a double-buffered S:
+                       4 = persistent grid, one CTA per SM walks the items, the next item's loads and first Q K^T overlap the
+                       current item's output store; 2 = one CTA per item (same arithmetic, bit-identical results).
+                       3 = three tiles per CTA, single S buffer each, three softmax warps per sub-partition (attn3_sm100.cu)  */
 } PxaAttnArgs;
 int pxa_flash_attn_d72_bf16(const PxaAttnArgs* args, void* stream);
 

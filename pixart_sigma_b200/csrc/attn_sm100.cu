@@ -1,6 +1,11 @@
 // pxa_flash_attn_d72_bf16: softmax(Q K^T * scale) V for head_dim 72 on tcgen05 tensor cores (sm_100a).
 //
-// One CTA = one (sample, head) x 256 query rows, processed as two 128-row tiles A / B.  384 threads:
+// One work item = one (sample, head) x 256 query rows, processed as two 128-row tiles A / B.  The grid is PERSISTENT (one
+// CTA per SM walks the items w = blockIdx.x, blockIdx.x + gridDim.x, ...): barrier set-up, the TMEM allocation and the CTA launch
+// happen once, and the producer / MMA warps run ahead into the next item (Q, the first K / V stages and the first two Q K^T)
+// while the softmax threads still write the current item's output -- the ~6 us of per-CTA prologue + epilogue that the
+// one-CTA-per-item launch exposed 14 times per SM (12 % of the self-attention at 4096 keys, half of the 300-key
+// cross-attention) shrink to the output store.  `variant = 2` launches one CTA per item (the round-1 behaviour).  384 threads:
 //   warp 0      TMA producer: Q once, then K / V stages of 128 keys into two 3-deep smem rings
 //   warp 1      MMA issuer (one elected thread): S = Q K^T (SS), O += P V (TS: P read from TMEM)
 //   warp 2      TMEM allocator (512 columns: S_A | S_B | O_A | O_B)
@@ -79,9 +84,13 @@ struct AttnParams {
   const int* kv_len;
   const int* kv_off;
   int B, H, Nq, Nk, ldo;
+  int nx;               // 256-row work items per (sample, head)
   float scale_log2;
   int reverse_batch;    // CTAs take the samples from the last to the first (L2 reuse of the freshly written qkv rows)
   long long* trace;     // debug only (NULL in production): cycle stamps of CTA (0,0,0), see PXA_TRACE
+  int item_trace;       // debug only: stamp item-level events of CTA 0 instead (PXA_ITRACE; variant 4 + debug_trace)
+  int stagger;          // persistent grid: tile B starts every item half an exp2 section behind tile A
+  int wide_stores;      // out and its row stride are 32-byte aligned: 256-bit output stores
 };
 
 constexpr int kTraceMax = 512;
@@ -89,6 +98,12 @@ constexpr int kTraceMax = 512;
 #define PXA_TRACE(who, cnt)                                                                        \
   do {                                                                                             \
     if (tracing && (cnt) < kTraceMax) p.trace[(who) * kTraceMax + (cnt)++] = clock64();            \
+  } while (0)
+
+// Item-level stamps of CTA 0 (slot 0 = first softmax warp, 16 = MMA thread, 17 = TMA thread): 8 per item with keys, 64 items.
+#define PXA_ITRACE(slot, k)                                                                                   \
+  do {                                                                                                        \
+    if (p.item_trace && blockIdx.x == 0 && it < 64) p.trace[(slot) * kTraceMax + 8 * it + (k)] = clock64();  \
   } while (0)
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
@@ -107,20 +122,31 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
   uint64_t* s_full = v_empty + kKVStages;     // [2 tiles][2 halves]  MMA -> softmax: S of a 64-key sub-block ready
   uint64_t* p_full = s_full + 4;              // [2][2]  softmax -> MMA: P written over that S half
   uint64_t* pv_done = p_full + 4;             // [2]     MMA -> softmax: P V of a sub-block done (lazy-rescale path only)
-  uint64_t* o_full = pv_done + 2;             // [1]     MMA -> softmax: all P V done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* o_full = pv_done + 2;             // [1]     MMA -> softmax: all P V of the item done
+  uint64_t* q_empty = o_full + 1;             // [1]     MMA -> TMA: the item's last Q K^T has read the Q tiles
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_empty + 1);
 
   const int warp = warp_idx_sync();
   const int lane = threadIdx.x & 31;
-  const int b = p.reverse_batch ? p.B - 1 - (int)blockIdx.z : (int)blockIdx.z, h = blockIdx.y;
-  const int q0 = blockIdx.x * (2 * kTileQ);
-
-  int kv_len = p.kv_len ? p.kv_len[b] : p.Nk;
-  kv_len = min(max(kv_len, 0), p.Nk);
-  const int kv_row0 = p.kv_off ? p.kv_off[b] : b * p.Nk;
-  const int n_blocks = (kv_len + kTileKV - 1) / kTileKV;     // 128-key TMA stages
-  const int n_sub = (kv_len + kSub - 1) / kSub;              // 64-key sub-blocks (the MMA / softmax unit)
-  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+  // work item w -> (sample, head, first query row); x fastest, so the CTAs running side by side share K / V through L2
+  const int total_items = p.nx * p.H * p.B;
+  struct Item {
+    int b, h, q0, kv_len, kv_row0, n_blocks, n_sub;
+  };
+  auto decode = [&](int w) {
+    Item im;
+    const int x = w % p.nx, yz = w / p.nx;
+    im.h = yz % p.H;
+    const int z = yz / p.H;
+    im.b = p.reverse_batch ? p.B - 1 - z : z;
+    im.q0 = x * (2 * kTileQ);
+    int kv_len = p.kv_len ? p.kv_len[im.b] : p.Nk;
+    im.kv_len = min(max(kv_len, 0), p.Nk);
+    im.kv_row0 = p.kv_off ? p.kv_off[im.b] : im.b * p.Nk;
+    im.n_blocks = (im.kv_len + kTileKV - 1) / kTileKV;     // 128-key TMA stages
+    im.n_sub = (im.kv_len + kSub - 1) / kSub;              // 64-key sub-blocks (the MMA / softmax unit)
+    return im;
+  };
   int tcnt = 0;
 
   if (threadIdx.x == 0) {
@@ -139,6 +165,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
     mbar_init(&pv_done[0], 1);
     mbar_init(&pv_done[1], 1);
     mbar_init(o_full, 1);
+    mbar_init(q_empty, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -156,34 +183,44 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
 
   if (warp == 0) {
     // ================================================================ TMA producer
-    if (n_blocks > 0 && elect_one()) {
-      const int qrow = b * p.Nq + q0;
-      mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
-      for (int t = 0; t < 2; ++t) {
-        // NB: a tile whose rows run past this sample's Nq reads the next sample's rows (finite garbage, never
-        // stored) or TMA zero fill past the end of the tensor.
-        tma_load_3d(smem + kOffQMain + t * kMainBytes, &tm_q_main, q_full, 0, h, qrow + t * kTileQ, kEvictFirst);
-        tma_load_3d(smem + kOffQTail + t * kTailBytes, &tm_q_tail, q_full, 64, h, qrow + t * kTileQ, kEvictFirst);
-      }
+    if (elect_one()) {
       int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < n_blocks; ++j) {
-        const int krow = kv_row0 + j * kTileKV;
-        mbar_wait(&k_empty[stage], phase ^ 1);
-        PXA_TRACE(17, tcnt);
-        mbar_arrive_expect_tx(&k_full[stage], kTileBytes);
-        tma_load_3d(smem + kOffKMain + stage * kMainBytes, &tm_k_main, &k_full[stage], 0, h, krow, kEvictLast);
-        tma_load_3d(smem + kOffKTail + stage * kTailBytes, &tm_k_tail, &k_full[stage], 64, h, krow, kEvictLast);
-        mbar_wait(&v_empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&v_full[stage], kVTileBytes);
-        tma_load_3d(smem + kOffVMain + stage * kMainBytes, &tm_v_main, &v_full[stage], 0, h, krow, kEvictLast);
-        tma_load_3d(smem + kOffVTail + stage * kVTailBytes, &tm_v_tail, &v_full[stage], 64, h, krow, kEvictLast);
-        if (++stage == kKVStages) { stage = 0; phase ^= 1; }
+      uint32_t phase = 0, it = 0;                  // `it` counts the items with keys (the others touch no barrier)
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        const Item im = decode(w);
+        if (im.n_blocks == 0) continue;
+        const bool tracing = p.trace != nullptr && w == 0 && !p.item_trace;
+        const int h = im.h, qrow = im.b * p.Nq + im.q0;
+        PXA_ITRACE(17, 0);
+        mbar_wait(q_empty, (it & 1) ^ 1);          // the previous item's Q K^T are done with the Q tiles
+        PXA_ITRACE(17, 1);
+        mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+        for (int t = 0; t < 2; ++t) {
+          // NB: a tile whose rows run past this sample's Nq reads the next sample's rows (finite garbage, never
+          // stored) or TMA zero fill past the end of the tensor.
+          tma_load_3d(smem + kOffQMain + t * kMainBytes, &tm_q_main, q_full, 0, h, qrow + t * kTileQ, kEvictFirst);
+          tma_load_3d(smem + kOffQTail + t * kTailBytes, &tm_q_tail, q_full, 64, h, qrow + t * kTileQ, kEvictFirst);
+        }
+        for (int j = 0; j < im.n_blocks; ++j) {
+          const int krow = im.kv_row0 + j * kTileKV;
+          mbar_wait(&k_empty[stage], phase ^ 1);
+          PXA_TRACE(17, tcnt);
+          mbar_arrive_expect_tx(&k_full[stage], kTileBytes);
+          tma_load_3d(smem + kOffKMain + stage * kMainBytes, &tm_k_main, &k_full[stage], 0, h, krow, kEvictLast);
+          tma_load_3d(smem + kOffKTail + stage * kTailBytes, &tm_k_tail, &k_full[stage], 64, h, krow, kEvictLast);
+          mbar_wait(&v_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&v_full[stage], kVTileBytes);
+          tma_load_3d(smem + kOffVMain + stage * kMainBytes, &tm_v_main, &v_full[stage], 0, h, krow, kEvictLast);
+          tma_load_3d(smem + kOffVTail + stage * kVTailBytes, &tm_v_tail, &v_full[stage], 64, h, krow, kEvictLast);
+          if (++stage == kKVStages) { stage = 0; phase ^= 1; }
+        }
+        PXA_ITRACE(17, 2);
+        ++it;
       }
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    if (n_sub > 0 && elect_one()) {
+    if (elect_one()) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, kSub, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 80, 0, 1);        // V is MN-major; N = 80 = d 0..79
       const uint32_t sbase = smem_u32(smem);
@@ -223,65 +260,98 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
 #endif
       };
 
-      // prologue: the first two sub-blocks' S for both tiles (the two S halves of a tile are a double buffer)
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      for (int hh = 0; hh < 2 && hh < n_sub; ++hh) {
-        for (int t = 0; t < 2; ++t) {
-          issue_qk(t, 0, hh);
-          umma_commit(&s_full[2 * t + hh]);
-        }
-      }
-      umma_commit(&k_empty[0]);
-
-      for (int n = 0; n < n_sub; ++n) {
-        const int j = n >> 1, hh = n & 1;
-        const int stage = j % kKVStages;
-        if (hh == 0) mbar_wait(&v_full[stage], (j / kKVStages) & 1);
-        const int nn = n + 2;                      // the sub-block that reuses this S half
-        const bool has_next = nn < n_sub;
-        const int nstage = (j + 1) % kKVStages;
-        if (has_next && hh == 0) mbar_wait(&k_full[nstage], ((j + 1) / kKVStages) & 1);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          PXA_TRACE(16, tcnt);                     // [4n+2t]   start waiting for P[t]
-          mbar_wait(&p_full[2 * t + hh], j & 1);
-          PXA_TRACE(16, tcnt);                     // [4n+2t+1] P[t] ready
-          tc_fence_after();
-          issue_pv(t, stage, hh, n == 0);
-          umma_commit(&pv_done[t]);
-          if (has_next) {
-            issue_qk(t, nstage, hh);
+      // Running barrier counts across items: K / V blocks loaded so far (ring stage / phase of block j of this item), completed
+      // uses of S half 0 / 1 (the same for both tiles), items with keys.
+      uint32_t it = 0, kbase = 0, hb0 = 0, hb1 = 0;
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        const Item im = decode(w);
+        if (im.n_blocks == 0) continue;
+        const bool tracing = p.trace != nullptr && w == 0 && !p.item_trace;
+        const int n_sub = im.n_sub;
+        PXA_ITRACE(16, 0);
+        auto kstage = [&](int j) { return (int)((kbase + j) % kKVStages); };
+        auto kphase = [&](int j) { return ((kbase + j) / kKVStages) & 1u; };
+        // prologue: the first two sub-blocks' S for both tiles (the two S halves of a tile are a double buffer).  The S halves
+        // are free: every P of the previous item was consumed by a P V issued earlier on the (in-order) tensor pipe.
+        mbar_wait(q_full, it & 1);
+        mbar_wait(&k_full[kstage(0)], kphase(0));
+        PXA_ITRACE(16, 1);
+        tc_fence_after();
+        for (int hh = 0; hh < 2 && hh < n_sub; ++hh) {
+          for (int t = 0; t < 2; ++t) {
+            issue_qk(t, kstage(0), hh);
             umma_commit(&s_full[2 * t + hh]);
           }
         }
-        if (hh == 1 || n + 1 == n_sub) umma_commit(&v_empty[stage]);            // last P V reading this V stage
-        if (has_next && (hh == 1 || nn + 1 == n_sub)) umma_commit(&k_empty[nstage]);   // last Q K^T reading that K stage
+        umma_commit(&k_empty[kstage(0)]);
+        if (n_sub <= 2) umma_commit(q_empty);
+        PXA_ITRACE(16, 2);
+
+        for (int n = 0; n < n_sub; ++n) {
+          const int j = n >> 1, hh = n & 1;
+          const int stage = kstage(j);
+          if (hh == 0) mbar_wait(&v_full[stage], kphase(j));
+          const int nn = n + 2;                      // the sub-block that reuses this S half
+          const bool has_next = nn < n_sub;
+          const int nstage = kstage(j + 1);
+          if (has_next && hh == 0) mbar_wait(&k_full[nstage], kphase(j + 1));
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            PXA_TRACE(16, tcnt);                     // [4n+2t]   start waiting for P[t]
+            mbar_wait(&p_full[2 * t + hh], ((hh ? hb1 : hb0) + j) & 1);
+            PXA_TRACE(16, tcnt);                     // [4n+2t+1] P[t] ready
+            tc_fence_after();
+            // n == 0 overwrites O / L of the previous item: its softmax threads published this P after their output stores
+            issue_pv(t, stage, hh, n == 0);
+            umma_commit(&pv_done[t]);
+            if (has_next) {
+              issue_qk(t, nstage, hh);
+              umma_commit(&s_full[2 * t + hh]);
+            }
+          }
+          if (hh == 1 || n + 1 == n_sub) umma_commit(&v_empty[stage]);            // last P V reading this V stage
+          if (has_next && (hh == 1 || nn + 1 == n_sub)) umma_commit(&k_empty[nstage]);   // last Q K^T reading that K stage
+          if (has_next && nn + 1 == n_sub) umma_commit(q_empty);                   // ... and the item's last read of Q
+        }
+        umma_commit(o_full);
+        PXA_ITRACE(16, 3);
+        kbase += im.n_blocks;
+        hb0 += (n_sub + 1) >> 1;
+        hb1 += n_sub >> 1;
+        ++it;
       }
-      umma_commit(o_full);
     }
   } else if (warp >= 4) {
     // ================================================================ softmax + epilogue (one thread per query row)
-    const int w = warp - 4;                        // 0..7
-    const int t = w >> 2;                          // tile 0 (A) / 1 (B)
+    const int sw = warp - 4;                       // 0..7
+    const int t = sw >> 2;                         // tile 0 (A) / 1 (B)
     const int qd = warp & 3;                       // TMEM sub-partition a warp may access (= warp % 4)
     const int row_in_tile = qd * 32 + lane;
-    const int qrow = q0 + t * kTileQ + row_in_tile;             // query index within the sample
     const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
     const uint32_t t_s = tmem_base + kColS + t * 128 + lane_sel;   // two 64-column S halves; P (bf16) over the first 32 of each
     const uint32_t t_o = tmem_base + kColO + t * 128 + lane_sel;   // O columns 0..79 (d 0..71 + 8 zero pad)
     const float sl2 = p.scale_log2;
     const uint64_t sl2x2 = f32x2(sl2, sl2);
 
+    const uint32_t t_l = tmem_base + kColL + t * 128 + lane_sel;
+    // running barrier counts across items (see the MMA issuer): uses of S half 0 / 1, P V commits, items with keys
+    uint32_t it = 0, hb0 = 0, hb1 = 0, pvb = 0;
+
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+    const Item im = decode(w);
+    const bool tracing = p.trace != nullptr && w == 0 && lane == 0 && !p.item_trace;
+    const bool itr = sw == 0 && lane == 0 && im.n_blocks > 0;
+    const int b = im.b, h = im.h, kv_len = im.kv_len, n_blocks = im.n_blocks, n_sub = im.n_sub;
+    if (itr) PXA_ITRACE(0, 0);
+    const int qrow = im.q0 + t * kTileQ + row_in_tile;          // query index within the sample
     float m_ref = -INFINITY;     // reference max used in the exponent (raw S units)
     uint64_t sa = f32x2(0.f, 0.f), sb = f32x2(0.f, 0.f);        // running row sum, four partial lanes (!PXA_SUM_MMA)
-    const uint32_t t_l = tmem_base + kColL + t * 128 + lane_sel;
 
     uint32_t va[32], vb[32];       // the 64 scores of this row in the current sub-block
+    if (n_sub > 0 && t == 1 && p.stagger) named_bar_sync(1, 256);           // tile B: half an exp2 section behind tile A (see softmax_sub)
 #if PXA_PREFETCH_S
     if (n_sub > 0) {
-      mbar_wait(&s_full[2 * t], 0);
+      mbar_wait(&s_full[2 * t], hb0 & 1);
       tc_fence_after();
       tmem_ld_32x32b_x32_nowait(t_s, va);
       tmem_ld_32x32b_x32_nowait(t_s + 32, vb);
@@ -289,23 +359,24 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       tmem_ld_wait_x32(vb);
     }
 #endif
+    if (itr) PXA_ITRACE(0, 1);
     auto softmax_sub = [&](const int n, auto masked_tag) {
       [[maybe_unused]] const int j = n >> 1;
       const int hh = n & 1;
       const uint32_t ts = t_s + hh * kSub;
-      PXA_TRACE(w, tcnt);                          // [7n+0] start waiting for S
+      PXA_TRACE(sw, tcnt);                          // [7n+0] start waiting for S
 #if !PXA_PREFETCH_S
-      mbar_wait(&s_full[2 * t + hh], j & 1);
-      PXA_TRACE(w, tcnt);                          // [7n+1] S ready
+      mbar_wait(&s_full[2 * t + hh], ((hh ? hb1 : hb0) + j) & 1);
+      PXA_TRACE(sw, tcnt);                          // [7n+1] S ready
       tc_fence_after();
       tmem_ld_32x32b_x32_nowait(ts, va);
       tmem_ld_32x32b_x32_nowait(ts + 32, vb);
       tmem_ld_wait_x32(va);
       tmem_ld_wait_x32(vb);
 #else
-      PXA_TRACE(w, tcnt);                          // [7n+1] (S was fetched during the previous sub-block)
+      PXA_TRACE(sw, tcnt);                          // [7n+1] (S was fetched during the previous sub-block)
 #endif
-      PXA_TRACE(w, tcnt);                          // [7n+2] S in registers
+      PXA_TRACE(sw, tcnt);                          // [7n+2] S in registers
       // Only the last sub-block of a sample can be partial.  The masking selects are compiled into a separate copy of
       // the body: if-converted into the common path they would cost 64 extra issue slots per thread per sub-block.
       if constexpr (decltype(masked_tag)::value) {
@@ -325,7 +396,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         mx3 = fmax3(mx3, __uint_as_float(vb[4 * i + 2]), __uint_as_float(vb[4 * i + 3]));
       }
       const float m_new = fmaxf(fmax3(mx0, mx1, mx2), fmaxf(mx3, m_ref));
-      PXA_TRACE(w, tcnt);                          // [7n+3] row max known
+      PXA_TRACE(sw, tcnt);                          // [7n+3] row max known
       // Lazy rescale: keep the old reference max unless it is stale by more than 2^8 (P stays <= 256, exact in the
       // fp32 accumulators).  The decision is warp-uniform because the TMEM round trip below is warp-collective.
       const bool stale = (m_new - m_ref) * sl2 > 8.0f;          // true on the first sub-block (m_ref = -inf)
@@ -334,7 +405,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         if (n > 0) {
           // O may only be touched between P V (n-1) and P V (n): the latter waits for this thread's P, the former is
           // awaited here (the S double buffer lets Q K^T run ahead, so "S ready" no longer implies "P V done").
-          mbar_wait(&pv_done[t], (n - 1) & 1);
+          mbar_wait(&pv_done[t], (pvb + n - 1) & 1);
           tc_fence_after();
           // d 0..71 in 9 pieces of 8 columns (rare path: a short register footprint matters more than TMEM round
           // trips); the pad columns 72..79 hold zeros and need no scaling.
@@ -386,13 +457,18 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         exp_pair(__uint_as_float(va[2 * i]), __uint_as_float(va[2 * i + 1]), i, sa, pk[i]);
         exp_pair(__uint_as_float(va[2 * i + 2]), __uint_as_float(va[2 * i + 3]), i + 1, sb, pk[i + 1]);
       }
+      // Persistent grid: at an item boundary both tiles find their first S complete and would start IN PHASE -- and stay
+      // there (1650 instead of 1395 cycles per sub-block, tools/attn_itrace.py): the kernel's good operating point is tile B
+      // about half an exp2 section behind tile A, which is what a fresh CTA falls into because S_A(0) is issued first.  So tile B
+      // starts every item when tile A is half-way through its first exp2 section.
+      if (n == 0 && t == 0 && p.stagger) named_bar_arrive(1, 256);
 #if PXA_PREFETCH_S
       // S of the next sub-block sits in the other S half (normally complete long ago): fetch it into the registers the
       // first 32 scores have just left, behind the second half of this sub-block's exp2 work.
       const bool has_next = n + 1 < n_sub;
       const uint32_t tn = t_s + (hh ^ 1) * kSub;
       if (has_next) {
-        mbar_wait(&s_full[2 * t + (hh ^ 1)], ((n + 1) >> 1) & 1);
+        mbar_wait(&s_full[2 * t + (hh ^ 1)], ((hh ? hb0 : hb1) + ((n + 1) >> 1)) & 1);
         tc_fence_after();
         tmem_ld_32x32b_x32_nowait(tn, va);
       }
@@ -408,11 +484,11 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       if (tracing) {   // debug only: pin the end of the exp2 section for the cycle trace
         asm volatile("" ::"r"(pk[0]), "r"(pk[7]), "r"(pk[15]), "r"(pk[23]), "r"(pk[31]), "l"(sa), "l"(sb) : "memory");
       }
-      PXA_TRACE(w, tcnt);                          // [7n+4] exp2 section done
+      PXA_TRACE(sw, tcnt);                          // [7n+4] exp2 section done
       // P (bf16, 64 keys = 32 packed columns) over the first 32 columns of this S half
       tmem_st_32x32b_x32(ts, pk);
       tmem_st_wait();
-      PXA_TRACE(w, tcnt);                          // [7n+5] P in TMEM
+      PXA_TRACE(sw, tcnt);                          // [7n+5] P in TMEM
       tc_fence_before();
       mbar_arrive(&p_full[2 * t + hh]);
 #if PXA_PREFETCH_S
@@ -421,13 +497,14 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         tmem_ld_wait_x32(vb);
       }
 #endif
-      PXA_TRACE(w, tcnt);                          // [7n+6] P published (and the next S in registers)
+      PXA_TRACE(sw, tcnt);                          // [7n+6] P published (and the next S in registers)
     };
     for (int n = 0; n + 1 < n_sub; ++n) softmax_sub(n, std::false_type{});
     if (n_sub > 0) {
       if (kv_len % kSub != 0) softmax_sub(n_sub - 1, std::true_type{});
       else softmax_sub(n_sub - 1, std::false_type{});
     }
+    if (itr) PXA_ITRACE(0, 2);
     float row_sum;
     {
       float s0, s1, s2, s3;
@@ -438,7 +515,8 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
 
     // ---- epilogue: O / row_sum -> bf16 -> out[(b*Nq + qrow), h*72 .. h*72+71]
     if (n_blocks > 0) {
-      mbar_wait(o_full, 0);
+      mbar_wait(o_full, it & 1);
+      if (itr) PXA_ITRACE(0, 3);
       tc_fence_after();
 #if PXA_SUM_MMA
       uint32_t l[8];
@@ -449,42 +527,58 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
     const float inv = row_sum > 0.f ? 1.0f / row_sum : 0.f;      // n_blocks == 0 (no keys): zeros
     if (p.lse != nullptr && qrow < p.Nq)                          // P = exp2(S * scale_log2 - lse) in the backward
       p.lse[((size_t)b * p.H + h) * p.Nq + qrow] = row_sum > 0.f ? fmaf(m_ref, sl2, log2f(row_sum)) : 0.f;
-    uint4* d4 = reinterpret_cast<uint4*>(p.out + (size_t)(b * p.Nq + qrow) * p.ldo + h * kD);
+    // The row's 72 outputs (144 B) as 36 packed words.  Stores: 32 lanes write 32 different rows, so every store instruction
+    // costs one LSU sector operation per lane whatever its width -- 256-bit stores (4 x 32 B + 1 x 16 B per row, the 16-byte
+    // piece first when h is odd: h * 144 B is then only 16-byte aligned) need 5 per row instead of the 9 of 128-bit stores.
     const bool row_ok = qrow < p.Nq;
+    uint32_t ow[36];
+    if (n_blocks > 0) {
+      uint32_t o8[8];
+      tmem_ld_32x32b_x32_nowait(t_o, va);
+      tmem_ld_32x32b_x32_nowait(t_o + 32, vb);
+      tmem_ld_32x32b_x8(t_o + 64, o8);             // tcgen05.wait::ld covers all three
+      tmem_ld_wait_x32(va);
+      tmem_ld_wait_x32(vb);
 #pragma unroll
-    for (int piece = 0; piece < 2; ++piece) {
-      uint32_t o[32];
-      if (n_blocks > 0) {
-        tmem_ld_32x32b_x32(t_o + 32 * piece, o);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = 0u;
+      for (int i = 0; i < 16; ++i) {
+        ow[i] = pack_bf16x2(__uint_as_float(va[2 * i]) * inv, __uint_as_float(va[2 * i + 1]) * inv);
+        ow[16 + i] = pack_bf16x2(__uint_as_float(vb[2 * i]) * inv, __uint_as_float(vb[2 * i + 1]) * inv);
       }
-      if (row_ok) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ow[32 + i] = pack_bf16x2(__uint_as_float(o8[2 * i]) * inv, __uint_as_float(o8[2 * i + 1]) * inv);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 36; ++i) ow[i] = 0u;
+    }
+    if (row_ok) {
+      __nv_bfloat16* dst = p.out + (size_t)(b * p.Nq + qrow) * p.ldo + h * kD;
+      if (p.wide_stores) {
+        const int lead = (h & 1) ? 4 : 0;          // words in front of the first 32-byte boundary
+        if (lead) *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          d4[4 * piece + c] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv),
-                                         pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv),
-                                         pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv),
-                                         pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv));
+          if (lead)
+            st_global_v8(dst + 8 + 16 * c, ow[4 + 8 * c], ow[5 + 8 * c], ow[6 + 8 * c], ow[7 + 8 * c], ow[8 + 8 * c], ow[9 + 8 * c],
+                         ow[10 + 8 * c], ow[11 + 8 * c]);
+          else
+            st_global_v8(dst + 16 * c, ow[8 * c], ow[8 * c + 1], ow[8 * c + 2], ow[8 * c + 3], ow[8 * c + 4], ow[8 * c + 5],
+                         ow[8 * c + 6], ow[8 * c + 7]);
         }
-      }
-    }
-    {
-      uint32_t o1[8];
-      if (n_blocks > 0) {
-        tmem_ld_32x32b_x8(t_o + 64, o1);
+        if (!lead) *reinterpret_cast<uint4*>(dst + 64) = make_uint4(ow[32], ow[33], ow[34], ow[35]);
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o1[i] = 0u;
-      }
-      if (row_ok) {
-        d4[8] = make_uint4(pack_bf16x2(__uint_as_float(o1[0]) * inv, __uint_as_float(o1[1]) * inv),
-                           pack_bf16x2(__uint_as_float(o1[2]) * inv, __uint_as_float(o1[3]) * inv),
-                           pack_bf16x2(__uint_as_float(o1[4]) * inv, __uint_as_float(o1[5]) * inv),
-                           pack_bf16x2(__uint_as_float(o1[6]) * inv, __uint_as_float(o1[7]) * inv));
+        for (int c = 0; c < 9; ++c)
+          reinterpret_cast<uint4*>(dst)[c] = make_uint4(ow[4 * c], ow[4 * c + 1], ow[4 * c + 2], ow[4 * c + 3]);
       }
     }
+    if (itr) PXA_ITRACE(0, 4);
+    if (n_blocks > 0) {
+      hb0 += (n_sub + 1) >> 1;
+      hb1 += n_sub >> 1;
+      pvb += n_sub;
+      ++it;
+    }
+    }   // items
   }
 
   tc_fence_before();
@@ -528,7 +622,7 @@ extern "C" int pxa_flash_attn_d72_bf16(const PxaAttnArgs* args, void* stream) {
   if (reinterpret_cast<uintptr_t>(a.out) & 15) return fail(PXA_ERR_ALIGN, "out must be 16-byte aligned");
   if (a.H * kD > a.ldo) return fail(PXA_ERR_ARG, "ldo smaller than H*72");
   PXA_REQUIRE_SM100();
-  if (a.variant != 0 && a.variant != 2 && a.variant != 3) return fail(PXA_ERR_ARG, "variant must be 0, 2 or 3");
+  if (a.variant != 0 && (a.variant < 2 || a.variant > 5)) return fail(PXA_ERR_ARG, "variant must be 0, 2, 3, 4 or 5");
   if (a.variant == 3 && !a.debug_trace) return flash_attn_d72_x3_launch(a, reinterpret_cast<cudaStream_t>(stream));
   CUtensorMap qm, qt, km, kt, vm, vt;
   int rc;
@@ -541,13 +635,23 @@ extern "C" int pxa_flash_attn_d72_bf16(const PxaAttnArgs* args, void* stream) {
   p.kv_len = a.kv_len;
   p.kv_off = a.kv_off;
   p.B = a.B; p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk; p.ldo = a.ldo;
+  p.nx = (a.Nq + 2 * kTileQ - 1) / (2 * kTileQ);
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.reverse_batch = a.reverse_batch ? 1 : 0;
   p.trace = reinterpret_cast<long long*>(a.debug_trace);
+  p.wide_stores = ((reinterpret_cast<uintptr_t>(a.out) & 31) == 0 && (a.ldo & 15) == 0) ? 1 : 0;
+  p.item_trace = (a.debug_trace && (a.variant == 4 || a.variant == 5)) ? 1 : 0;
   PXA_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_d72_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-  dim3 grid((a.Nq + 2 * kTileQ - 1) / (2 * kTileQ), a.H, a.B);
-  flash_attn_d72_kernel<<<grid, kAttnThreads, kAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(qm, qt, km, kt, vm,
-                                                                                                  vt, p);
+  // variant 4: persistent grid, one CTA per SM walks the items; 2: one CTA per item (round-1 behaviour); 0 = auto: persistent for
+  // short key sets (the 300-token cross-attention: -24 %), one CTA per item for long ones (persistent measured 12 % SLOWER at
+  // 4096 keys, profiles/r2_attn_persistent.txt)
+  const long long items = (long long)p.nx * a.H * a.B;
+  long long grid = items;
+  const bool persistent = a.variant == 4 || a.variant == 5 || (a.variant == 0 && a.Nk <= 1024);
+  if (persistent && grid > device_info().sms) grid = device_info().sms;
+  p.stagger = (grid < items && a.variant != 5) ? 1 : 0;      // variant 5 (experiments): persistent without the stagger
+  flash_attn_d72_kernel<<<(unsigned)grid, kAttnThreads, kAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(qm, qt, km, kt, vm,
+                                                                                                            vt, p);
   launch_counter()++;
   PXA_CHECK_CUDA(cudaGetLastError());
   return PXA_OK;

@@ -84,7 +84,7 @@ def test_block_at_bench_geometry_matches_oracle(name, B, hw, lens, sr, fused):
     assert max(per_sample) < 2e-3, per_sample
 
 
-@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("variant", [2, 3, 4])
 @pytest.mark.parametrize("B,H,Nq,Nk", [(8, 16, 4096, 4096), (2, 16, 16384, 4096)])
 def test_flash_attn_at_bench_geometry(B, H, Nq, Nk, variant):
     g = torch.Generator().manual_seed(30)

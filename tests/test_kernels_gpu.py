@@ -300,7 +300,7 @@ def _attn_ref(q, k, v, lens):
 
 @pytest.mark.parametrize("B,H,Nq,Nk", [(1, 1, 128, 128), (1, 2, 256, 256), (2, 16, 1024, 1024), (1, 16, 1000, 1000),
                                        (2, 4, 1024, 256), (1, 3, 300, 77)])
-@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("variant", [2, 3, 4])
 def test_flash_attn_self_from_qkv_layout(B, H, Nq, Nk, variant):
     """q/k/v are strided views of a (B*N, 3, H, 72)-style buffer exactly as the QKV GEMM leaves them."""
     q = _randn(B, Nq, H, 72, seed=30)
@@ -314,7 +314,7 @@ def test_flash_attn_self_from_qkv_layout(B, H, Nq, Nk, variant):
     assert po.rel_err(out.float(), want) < 6e-3
 
 
-@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("variant", [2, 3, 4])
 def test_flash_attn_interleaved_qkv_buffer(variant):
     B, H, N = 2, 16, 512
     qkv = _randn(B * N, 3, H, 72, seed=33)
@@ -326,7 +326,7 @@ def test_flash_attn_interleaved_qkv_buffer(variant):
     assert po.rel_err(out.float(), want) < 6e-3
 
 
-@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("variant", [2, 3, 4])
 def test_flash_attn_large_logits_trigger_rescale(variant):
     """Keys ordered so the running max keeps growing by > 2^8 between blocks: exercises the lazy O rescale."""
     B, H, N = 1, 2, 512
@@ -342,7 +342,7 @@ def test_flash_attn_large_logits_trigger_rescale(variant):
     assert po.rel_err(out.float(), want) < 8e-3
 
 
-@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("variant", [2, 3, 4])
 def test_flash_attn_cross_packed_varlen(variant):
     """T5 cross-attention: packed keys (1, sum L, 2, H, 72) with BlockDiagonalMask semantics, incl. an empty sample."""
     H, Nq = 16, 384
@@ -443,7 +443,7 @@ def test_gemm_reverse_tile_order_gives_identical_results(epi):
         assert po.rel_err(outs[1], outs[0]) < 1e-6        # TMA reduce-add: same addends, L2 adds them in arrival order
 
 
-@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("variant", [2, 3, 4])
 def test_flash_attn_reverse_batch_order_gives_identical_results(variant):
     B, H, N = 3, 4, 640
     q, k, v = _randn(B, N, H, 72, seed=110), _randn(B, N, H, 72, seed=111), _randn(B, N, H, 72, seed=112)
@@ -455,6 +455,28 @@ def test_flash_attn_reverse_batch_order_gives_identical_results(variant):
                        k_strides=(H * 72, 72), v_strides=(H * 72, 72), variant=variant, reverse_batch=rev)
         outs.append(out)
     assert torch.equal(outs[0], outs[1])
+
+
+def test_flash_attn_persistent_grid_is_bit_identical_to_one_cta_per_item():
+    """variant 4 / 0 (one CTA per SM walks the work items; barrier phases, K / V ring and TMEM carried from item to item) against
+    variant 2 (one CTA per item) on ragged key sets -- odd and even numbers of sub-blocks, a partial last sub-block, a single
+    sub-block, an EMPTY key set in the middle -- with enough items (6 x 16 x 8 = 768) that every CTA walks 5 or 6 of them."""
+    B, H, N, Nk = 6, 16, 2048, 704
+    q, kv = _randn(B * N, H * 72, seed=130), _randn(B * Nk, 2 * H * 72, seed=131)
+    lens = torch.tensor([704, 65, 0, 300, 128, 449], dtype=torch.int32, device=DEV)
+    off = (torch.arange(B, device=DEV, dtype=torch.int32) * Nk).contiguous()
+    outs, lses = [], []
+    for variant in (2, 4, 0):
+        out = torch.full((B * N, H * 72), float("nan"), dtype=torch.bfloat16, device=DEV)
+        lse = torch.full((B, H, N), float("nan"), dtype=torch.float32, device=DEV)
+        lib.flash_attn(q, kv[:, :H * 72], kv[:, H * 72:], out, B=B, H=H, Nq=N, Nk=Nk, kv_rows=B * Nk, kv_len=lens, kv_off=off,
+                       q_strides=(H * 72, 72), k_strides=(2 * H * 72, 72), v_strides=(2 * H * 72, 72), lse=lse, variant=variant)
+        outs.append(out)
+        lses.append(lse)
+    torch.cuda.synchronize()
+    assert torch.isfinite(outs[0].float()).all() and (outs[0].view(B, N, -1)[2] == 0).all()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert torch.equal(lses[0], lses[1]) and torch.equal(lses[0], lses[2])
 
 
 # ------------------------------------------------------------------------------------------------- fused Mlp (one persistent kernel)

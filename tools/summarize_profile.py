@@ -10,7 +10,7 @@ if tag.startswith("c5"):
              "kernels), one B200, `--clock-control none`, `--profile-from-start off`. Per-launch times under ncu are cold-cache "
              "and serialised: compare SHARES.", ""]
 else:
-    lines = [f"# ncu summary {tag}", "", "Command: `bench.py --steps 2 --warmup 3` (launch list) / `--steps 1` (`--set full`, GEMM + attention kernels), "
+    lines = [f"# ncu summary {tag}", "", "Command: `bench.py --no-cuda-graph --no-extras --no-parity --steps 2 --warmup 3` (launch list) / `--steps 1` (`--set full`, GEMM + attention + norm kernels), "
              "workload c3 (1024px, forward batch 8), one B200, `--clock-control none`. Per-launch times under ncu are cold-cache and "
              "serialised: compare SHARES.", ""]
 lp = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
@@ -65,6 +65,7 @@ if os.path.exists(rp) or os.path.exists(rcsv):
         tot = [to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) +
                to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]]) for r in gem]
         json.dump({"tag": tag, "gemm_launches_captured": len(gem), "gemm_dram_bytes_per_launch": sum(tot) / len(tot),
+                   "source": f"profiles/{tag}_raw.csv (ncu --set full of bench.py c3, GEMM launches of one PixArtMSBlock)",
                    "note": "mean of dram__bytes_read.sum + dram__bytes_write.sum over the GEMM launches of one ncu --set full capture"},
                   open(os.path.join(out_dir, "latest_traffic.json"), "w"), indent=1)
 bp = os.path.join(ROOT, "gpurun_out", f"bench_{tag}.json")
