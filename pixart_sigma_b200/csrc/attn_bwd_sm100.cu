@@ -365,34 +365,41 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
       __nv_bfloat16* base = half == 0 ? p.d2 : p.d1;
       const long long sn = half == 0 ? p.d2_sn : p.d1_sn;
       const long long sh = half == 0 ? p.d2_sh : p.d1_sh;
-      uint4* d4p = reinterpret_cast<uint4*>(base + (size_t)(x_row0 + row) * sn + (size_t)h * sh);
+      __nv_bfloat16* dst = base + (size_t)(x_row0 + row) * sn + (size_t)h * sh;
+      // the row's 72 gradients (144 B) as 36 packed words; 32 lanes write 32 different rows, so a store instruction costs one
+      // LSU sector operation per lane whatever its width: 256-bit stores need 5 per row instead of 9 (attn_sm100.cu)
+      uint32_t ow[36];
+      if (n_iter > 0) {
+        uint32_t oa[32], ob[32], o8[8];
+        tmem_ld_32x32b_x32_nowait(t_acc, oa);
+        tmem_ld_32x32b_x32_nowait(t_acc + 32, ob);
+        tmem_ld_32x32b_x8(t_acc + 64, o8);           // tcgen05.wait::ld covers all three
+        tmem_ld_wait_x32(oa);
+        tmem_ld_wait_x32(ob);
 #pragma unroll
-      for (int piece = 0; piece < 3; ++piece) {       // columns 0..31, 32..63, 64..71
-        uint32_t o[32];
-        if (n_iter > 0) {
-          if (piece < 2) {
-            tmem_ld_32x32b_x32(t_acc + 32 * piece, o);
-          } else {
-            uint32_t o8[8];
-            tmem_ld_32x32b_x8(t_acc + 64, o8);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = o8[i];
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = 0u;
+        for (int i = 0; i < 16; ++i) {
+          ow[i] = pack_bf16x2(__uint_as_float(oa[2 * i]) * mul, __uint_as_float(oa[2 * i + 1]) * mul);
+          ow[16 + i] = pack_bf16x2(__uint_as_float(ob[2 * i]) * mul, __uint_as_float(ob[2 * i + 1]) * mul);
         }
-        if (row_ok) {
-          const int nvec = piece < 2 ? 4 : 1;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c < nvec)
-              d4p[4 * piece + c] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * c]) * mul, __uint_as_float(o[8 * c + 1]) * mul),
-                                              pack_bf16x2(__uint_as_float(o[8 * c + 2]) * mul, __uint_as_float(o[8 * c + 3]) * mul),
-                                              pack_bf16x2(__uint_as_float(o[8 * c + 4]) * mul, __uint_as_float(o[8 * c + 5]) * mul),
-                                              pack_bf16x2(__uint_as_float(o[8 * c + 6]) * mul, __uint_as_float(o[8 * c + 7]) * mul));
-          }
+        for (int i = 0; i < 4; ++i) ow[32 + i] = pack_bf16x2(__uint_as_float(o8[2 * i]) * mul, __uint_as_float(o8[2 * i + 1]) * mul);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 36; ++i) ow[i] = 0u;
+      }
+      if (row_ok) {
+        const int lead = static_cast<int>((reinterpret_cast<uintptr_t>(dst) >> 4) & 1) * 4;   // words before the first 32-byte boundary
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (lead)
+            st_global_v8(dst + 8 + 16 * c, ow[4 + 8 * c], ow[5 + 8 * c], ow[6 + 8 * c], ow[7 + 8 * c], ow[8 + 8 * c], ow[9 + 8 * c],
+                         ow[10 + 8 * c], ow[11 + 8 * c]);
+          else
+            st_global_v8(dst + 16 * c, ow[8 * c], ow[8 * c + 1], ow[8 * c + 2], ow[8 * c + 3], ow[8 * c + 4], ow[8 * c + 5],
+                         ow[8 * c + 6], ow[8 * c + 7]);
         }
+        if (lead) *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        else *reinterpret_cast<uint4*>(dst + 64) = make_uint4(ow[32], ow[33], ow[34], ow[35]);
       }
     }
   }
