@@ -164,6 +164,8 @@ typedef struct PxaLnModArgs {
   float eps;
   int32_t reverse_rows; /* 1: CTAs take the rows from the last to the first (start on the rows of x that the front-to-back
                            residual GEMM before it wrote last, i.e. the ones still in L2)                        */
+  int32_t max_ctas;     /* 0 = auto: a grid-stride launch of two 8-warp CTAs per SM, every warp prefetching its next row;
+                           > 0 caps / widens the grid (M / 8 or more = one row per warp)                               */
 } PxaLnModArgs;
 int pxa_ln_modulate(const PxaLnModArgs* args, void* stream);
 

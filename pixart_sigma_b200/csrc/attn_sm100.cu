@@ -88,7 +88,8 @@ struct AttnParams {
   float scale_log2;
   int reverse_batch;    // CTAs take the samples from the last to the first (L2 reuse of the freshly written qkv rows)
   long long* trace;     // debug only (NULL in production): cycle stamps of CTA (0,0,0), see PXA_TRACE
-  int item_trace;       // debug only: stamp item-level events of CTA 0 instead (PXA_ITRACE; variant 4 + debug_trace)
+  int item_trace;       // debug only: stamp item-level events of CTA 0 instead (PXA_ITRACE; variant 5 + debug_trace)
+  int trace_item;       // debug only: the work item (of CTA 0) whose sub-block stamps PXA_TRACE records
   int stagger;          // persistent grid: tile B starts every item half an exp2 section behind tile A
   int wide_stores;      // out and its row stride are 32-byte aligned: 256-bit output stores
 };
@@ -189,7 +190,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
         const Item im = decode(w);
         if (im.n_blocks == 0) continue;
-        const bool tracing = p.trace != nullptr && w == 0 && !p.item_trace;
+        const bool tracing = p.trace != nullptr && w == p.trace_item && !p.item_trace;
         const int h = im.h, qrow = im.b * p.Nq + im.q0;
         PXA_ITRACE(17, 0);
         mbar_wait(q_empty, (it & 1) ^ 1);          // the previous item's Q K^T are done with the Q tiles
@@ -266,7 +267,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
         const Item im = decode(w);
         if (im.n_blocks == 0) continue;
-        const bool tracing = p.trace != nullptr && w == 0 && !p.item_trace;
+        const bool tracing = p.trace != nullptr && w == p.trace_item && !p.item_trace;
         const int n_sub = im.n_sub;
         PXA_ITRACE(16, 0);
         auto kstage = [&](int j) { return (int)((kbase + j) % kKVStages); };
@@ -339,7 +340,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
 
     for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
     const Item im = decode(w);
-    const bool tracing = p.trace != nullptr && w == 0 && lane == 0 && !p.item_trace;
+    const bool tracing = p.trace != nullptr && w == p.trace_item && lane == 0 && !p.item_trace;
     const bool itr = sw == 0 && lane == 0 && im.n_blocks > 0;
     const int b = im.b, h = im.h, kv_len = im.kv_len, n_blocks = im.n_blocks, n_sub = im.n_sub;
     if (itr) PXA_ITRACE(0, 0);
@@ -640,7 +641,7 @@ extern "C" int pxa_flash_attn_d72_bf16(const PxaAttnArgs* args, void* stream) {
   p.reverse_batch = a.reverse_batch ? 1 : 0;
   p.trace = reinterpret_cast<long long*>(a.debug_trace);
   p.wide_stores = ((reinterpret_cast<uintptr_t>(a.out) & 31) == 0 && (a.ldo & 15) == 0) ? 1 : 0;
-  p.item_trace = (a.debug_trace && (a.variant == 4 || a.variant == 5)) ? 1 : 0;
+  p.item_trace = (a.debug_trace && a.variant == 5) ? 1 : 0;
   PXA_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_d72_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
   // variant 4: persistent grid, one CTA per SM walks the items; 2: one CTA per item (round-1 behaviour); 0 = auto: persistent for
   // short key sets (the 300-token cross-attention: -24 %), one CTA per item for long ones (persistent measured 12 % SLOWER at
@@ -650,6 +651,7 @@ extern "C" int pxa_flash_attn_d72_bf16(const PxaAttnArgs* args, void* stream) {
   const bool persistent = a.variant == 4 || a.variant == 5 || (a.variant == 0 && a.Nk <= 1024);
   if (persistent && grid > device_info().sms) grid = device_info().sms;
   p.stagger = (grid < items && a.variant != 5) ? 1 : 0;      // variant 5 (experiments): persistent without the stagger
+  p.trace_item = grid < items ? (int)(2 * grid) : 0;          // sub-block trace: CTA 0's third item when persistent
   flash_attn_d72_kernel<<<(unsigned)grid, kAttnThreads, kAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(qm, qt, km, kt, vm,
                                                                                                             vt, p);
   launch_counter()++;

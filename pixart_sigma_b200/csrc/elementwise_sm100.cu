@@ -3,6 +3,10 @@
 #include "host_common.cuh"
 #include "ptx.cuh"
 
+#ifndef PXA_LN_CTAS_PER_SM
+#define PXA_LN_CTAS_PER_SM 2
+#endif
+
 namespace pxa {
 
 PXA_DEVICE float warp_sum(float v) {
@@ -14,18 +18,11 @@ PXA_DEVICE float warp_sum(float v) {
 // ------------------------------------------------------------------------------------------------- LN + modulate
 // C = 32 lanes * kVec * 4 elements (1152 -> kVec = 9). Each lane owns kVec float4 groups, group g at column
 // (g*32 + lane)*4, so every warp-level access is a contiguous 512 B (fp32) / 256 B (bf16) segment.
+// Grid-stride over the rows with the NEXT row's loads issued before the current row is reduced: a warp always has one full row
+// (4.6 KB fp32) in flight, and the grid is a fixed number of CTAs per SM instead of M / 8 short-lived ones (round 2: the
+// one-row-per-warp launch ran at 4.4 TB/s).
 template <int kVec, typename XT>
-__global__ void __launch_bounds__(256) ln_modulate_kernel(const XT* __restrict__ x, __nv_bfloat16* __restrict__ out,
-                                                          const float* __restrict__ shift,
-                                                          const float* __restrict__ scale, long long mod_bs,
-                                                          int rows_per_batch, int M, int ldx, float eps, int reverse) {
-  constexpr int C = kVec * 128;
-  int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= M) return;
-  if (reverse) row = M - 1 - row;
-  float4 v[kVec];
-  const XT* xr = x + (size_t)row * ldx;
+PXA_DEVICE void ln_load_row(const XT* __restrict__ xr, int lane, float4 (&v)[kVec]) {
 #pragma unroll
   for (int g = 0; g < kVec; ++g) {
     const int col = (g * 32 + lane) * 4;
@@ -36,31 +33,54 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const XT* __restrict__
       v[g] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
     }
   }
-  float s = 0.f;
+}
+
+template <int kVec, typename XT>
+__global__ void __launch_bounds__(256, 2) ln_modulate_kernel(const XT* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                             const float* __restrict__ shift,
+                                                             const float* __restrict__ scale, long long mod_bs,
+                                                             int rows_per_batch, int M, int ldx, float eps, int reverse) {
+  constexpr int C = kVec * 128;
+  const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * 8;
+  int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= M) return;
+  float4 v[kVec], nxt[kVec];
+  ln_load_row<kVec, XT>(x + (size_t)(reverse ? M - 1 - r : r) * ldx, lane, v);
+  for (; r < M; r += stride) {
+    const int row = reverse ? M - 1 - r : r;
+    const bool more = r + stride < M;
+    if (more) ln_load_row<kVec, XT>(x + (size_t)(reverse ? M - 1 - (r + stride) : r + stride) * ldx, lane, nxt);
+    float s = 0.f;
 #pragma unroll
-  for (int g = 0; g < kVec; ++g) s += (v[g].x + v[g].y) + (v[g].z + v[g].w);
-  const float mean = warp_sum(s) * (1.0f / C);
-  float ss = 0.f;
+    for (int g = 0; g < kVec; ++g) s += (v[g].x + v[g].y) + (v[g].z + v[g].w);
+    const float mean = warp_sum(s) * (1.0f / C);
+    float ss = 0.f;
 #pragma unroll
-  for (int g = 0; g < kVec; ++g) {
-    const float a = v[g].x - mean, b = v[g].y - mean, c = v[g].z - mean, d = v[g].w - mean;
-    ss += (a * a + b * b) + (c * c + d * d);
-  }
-  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / C) + eps);
-  const int bidx = row / rows_per_batch;
-  const float* sh = shift + (size_t)bidx * mod_bs;
-  const float* sc = scale + (size_t)bidx * mod_bs;
-  __nv_bfloat16* orow = out + (size_t)row * C;
+    for (int g = 0; g < kVec; ++g) {
+      const float a = v[g].x - mean, b = v[g].y - mean, c = v[g].z - mean, d = v[g].w - mean;
+      ss += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(ss) * (1.0f / C) + eps);
+    const int bidx = row / rows_per_batch;
+    const float* sh = shift + (size_t)bidx * mod_bs;
+    const float* sc = scale + (size_t)bidx * mod_bs;
+    __nv_bfloat16* orow = out + (size_t)row * C;
 #pragma unroll
-  for (int g = 0; g < kVec; ++g) {
-    const int col = (g * 32 + lane) * 4;
-    const float4 a = __ldg(reinterpret_cast<const float4*>(sc + col));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(sh + col));
-    const float y0 = fmaf((v[g].x - mean) * rstd, 1.0f + a.x, b.x);
-    const float y1 = fmaf((v[g].y - mean) * rstd, 1.0f + a.y, b.y);
-    const float y2 = fmaf((v[g].z - mean) * rstd, 1.0f + a.z, b.z);
-    const float y3 = fmaf((v[g].w - mean) * rstd, 1.0f + a.w, b.w);
-    *reinterpret_cast<uint2*>(orow + col) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+    for (int g = 0; g < kVec; ++g) {
+      const int col = (g * 32 + lane) * 4;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(sc + col));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(sh + col));
+      const float y0 = fmaf((v[g].x - mean) * rstd, 1.0f + a.x, b.x);
+      const float y1 = fmaf((v[g].y - mean) * rstd, 1.0f + a.y, b.y);
+      const float y2 = fmaf((v[g].z - mean) * rstd, 1.0f + a.z, b.z);
+      const float y3 = fmaf((v[g].w - mean) * rstd, 1.0f + a.w, b.w);
+      *reinterpret_cast<uint2*>(orow + col) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+    }
+    if (more) {
+#pragma unroll
+      for (int g = 0; g < kVec; ++g) v[g] = nxt[g];
+    }
   }
 }
 
@@ -151,7 +171,10 @@ extern "C" int pxa_ln_modulate(const PxaLnModArgs* args, void* stream) {
     return fail(PXA_ERR_ALIGN, "pointers must be 16-byte aligned");
   PXA_REQUIRE_SM100();
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int grid = (a.M + 7) / 8;
+  int grid = (a.M + 7) / 8;
+  const int resident = device_info().sms * PXA_LN_CTAS_PER_SM;               // grid-stride: a fixed number of CTAs per SM
+  if (a.max_ctas > 0) { if (grid > a.max_ctas) grid = a.max_ctas; }
+  else if (grid > resident) grid = resident;
   if (a.x_dtype == PXA_DTYPE_F32)
     ln_modulate_kernel<9, float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(a.x),
                                                       reinterpret_cast<__nv_bfloat16*>(a.out), a.shift, a.scale,

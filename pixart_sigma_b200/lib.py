@@ -64,7 +64,7 @@ class LnModArgs(C.Structure):
     _fields_ = [("x", C.c_void_p), ("out", C.c_void_p), ("shift", C.c_void_p), ("scale", C.c_void_p),
                 ("mod_batch_stride", C.c_int64), ("rows_per_batch", C.c_int32),
                 ("M", C.c_int32), ("C", C.c_int32), ("ldx", C.c_int32), ("x_dtype", C.c_int32), ("eps", C.c_float),
-                ("reverse_rows", C.c_int32)]
+                ("reverse_rows", C.c_int32), ("max_ctas", C.c_int32)]
 
 
 class AttnArgs(C.Structure):
@@ -265,14 +265,15 @@ def ln_prepare(x: torch.Tensor, mult: torch.Tensor, a_out: torch.Tensor, stats_o
 
 
 def ln_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, out: torch.Tensor, *,
-                mod_batch_stride: int, rows_per_batch: int, eps: float = 1e-6, reverse_rows: bool = False) -> torch.Tensor:
+                mod_batch_stride: int, rows_per_batch: int, eps: float = 1e-6, reverse_rows: bool = False,
+                max_ctas: int = 0) -> torch.Tensor:
     """out = LN(x) * (1 + scale[b]) + shift[b]; x (M,C) fp32/bf16, shift/scale fp32 views (row b at b*stride)."""
     assert x.dim() == 2 and x.stride(1) == 1 and out.is_contiguous() and out.dtype == torch.bfloat16
     assert shift.dtype == torch.float32 and scale.dtype == torch.float32
     M, Cc = x.shape
     args = LnModArgs(x=_ptr(x), out=_ptr(out), shift=_ptr(shift), scale=_ptr(scale), mod_batch_stride=mod_batch_stride,
                      rows_per_batch=rows_per_batch, M=M, C=Cc, ldx=x.stride(0), x_dtype=_dt(x.dtype), eps=eps,
-                     reverse_rows=int(reverse_rows))
+                     reverse_rows=int(reverse_rows), max_ctas=max_ctas)
     _check(load().pxa_ln_modulate(C.byref(args), _stream()), "pxa_ln_modulate")
     return out
 
@@ -395,7 +396,7 @@ def groupnorm_silu_nhwc(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor
         stats_ws = torch.empty(B * groups * 2, dtype=torch.float32, device=x.device)
     assert stats_ws.dtype == torch.float32 and stats_ws.numel() >= B * groups * 2
     _check(load().pxa_groupnorm_silu_nhwc_bf16(_ptr(x), _ptr(out), _ptr(gamma), _ptr(beta), _ptr(stats_ws), B, H * W, Cc, groups,
-                                               eps, int(silu), _stream()), "pxa_groupnorm_silu_nhwc_bf16", "pxa_adamw_flat", "pxa_mlp_fused_bf16")
+                                               eps, int(silu), _stream()), "pxa_groupnorm_silu_nhwc_bf16")
     return out
 
 

@@ -155,3 +155,12 @@ def test_install_into_reference_repoints_registry_and_nets():
     solver = DPMS(m.forward_with_dpmsolver, condition=cond, uncondition=cond, cfg_scale=4.5,
                   model_kwargs=dict(data_info=None, mask=None))
     assert solver is not None
+
+
+def test_every_binding_checks_its_return_code_with_one_label():
+    """`_check(rc, "name")`: a scripted edit once appended extra labels to one call, which only failed on the GPU box."""
+    import ast
+    import inspect
+    tree = ast.parse(inspect.getsource(lib))
+    calls = [n for n in ast.walk(tree) if isinstance(n, ast.Call) and getattr(n.func, "id", None) == "_check"]
+    assert len(calls) >= 20 and all(len(n.args) == 2 and not n.keywords for n in calls)

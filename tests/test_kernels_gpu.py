@@ -160,9 +160,10 @@ def test_gemm_rejects_bad_arguments():
 
 
 # ------------------------------------------------------------------------------------------------- LN + modulate
+@pytest.mark.parametrize("B,Ntok", [(3, 333), (5, 1001)])     # the second: more rows than resident warps (grid-stride + prefetch)
 @pytest.mark.parametrize("xdtype", [torch.float32, torch.bfloat16])
-def test_ln_modulate(xdtype):
-    B, Ntok, Cc = 3, 333, 1152
+def test_ln_modulate(xdtype, B, Ntok):
+    Cc = 1152
     x = (_randn(B * Ntok, Cc, seed=20, dtype=torch.float32) * 3 + 0.5).to(xdtype)
     mod = _randn(B, 6, Cc, seed=21, dtype=torch.float32)
     out = torch.empty(B * Ntok, Cc, dtype=torch.bfloat16, device=DEV)

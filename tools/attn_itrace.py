@@ -10,7 +10,7 @@ from pixart_sigma_b200 import lib  # noqa: E402
 
 B, H, N = 8, 16, 4096
 Nk = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-VARIANT = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+VARIANT = 5          # item-level stamps are recorded by variant 5 (persistent, no stagger) + debug_trace
 g = torch.Generator().manual_seed(0)
 q = torch.randn(B * N, H * 72, generator=g).to(torch.bfloat16).cuda()
 kv = torch.randn(B * Nk, 2, H * 72, generator=g).to(torch.bfloat16).cuda()
