@@ -39,7 +39,11 @@
 
 // Experiment switch (tools/attn_variants.sh builds and times the alternatives; default = the fastest measured).
 #ifndef PXA_SUM_MMA
-#define PXA_SUM_MMA 1         // row sums of P on the tensor pipe (P x ones, N=16) instead of 32 FADD2 per thread per sub-block
+// Row sums of P on the tensor pipe (P x ones, N = 16) instead of 32 FADD2 per thread per sub-block.  In isolation (clocks not
+// power-capped) the tensor-pipe form is ~5 % faster (profiles/r1_attn_variants2.txt), but inside the c3 step the board sits at
+// its 1 kW cap and the four extra MMAs per sub-block and tile cost more than the FADD2s: in-step attention 685 vs 650 TFLOP/s,
+// step 60.88 vs 62.0 ms (profiles/r2_instep_ab.txt).  The step is what is judged: default 0.
+#define PXA_SUM_MMA 0
 #endif
 #ifndef PXA_PREFETCH_S
 #define PXA_PREFETCH_S 1      // read S of sub-block n+1 from TMEM behind the exp2 work of sub-block n
