@@ -368,7 +368,11 @@ def measure_inference(args, ctx: Ctx, wl_name: str, headline: bool):
             step_resident(i)
         step_e2e(0)
         sampler = ClockSampler(ctx.local) if rank == 0 else None
+        if os.environ.get("PXA_PROFILER_RANGE") == "1":      # ncu --profile-from-start off: capture the timed steps only
+            torch.cuda.profiler.start()
         ms = ctx.timed(step_resident, args.steps)                                   # <- `value`: nothing else in here
+        if os.environ.get("PXA_PROFILER_RANGE") == "1":
+            torch.cuda.profiler.stop()
         ms_e2e = ctx.timed(step_e2e, args.steps)
         clocks = sampler.stop() if sampler else None
         # ---- separate pass: per-kernel CUDA events for the roofline (2 steps; not part of value / e2e)
@@ -417,9 +421,12 @@ def measure_inference(args, ctx: Ctx, wl_name: str, headline: bool):
                           f"({ms_roof / roof_steps:.2f} ms/step with the events)",
                 "launches_timed": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
                 "flops_per_launch_avg": f_gemm * roof_steps / max(gemm_n, 1),
-                "step_share": gemm_ms / ms_roof if ms_roof > 0 else None,
+                # shares of the TIMED step (graph replay), not of the eager events pass: on a slow host that pass is launch-bound
+                # (its wall time grows, the kernels' durations do not)
+                "step_share": gemm_ms / roof_steps / ms_step,
+                "events_pass_host_bound": bool(ms_roof / roof_steps > 1.15 * ms_step),
                 "attention": {"kernel": "pxa::flash_attn_d72_kernel", "achieved": attn_tf, "frac": (attn_tf / sus) if attn_tf else None,
-                              "launches_timed": attn_n, "step_share": attn_ms / ms_roof if ms_roof > 0 else None},
+                              "launches_timed": attn_n, "step_share": attn_ms / roof_steps / ms_step},
                 "whole_step": {"achieved": tot / (ms_step / 1000.0) / 1e12, "frac": tot / (ms_step / 1000.0) / 1e12 / sus}}
         # ---- what was timed is checked: one block at the benchmarked geometry vs the oracle on the host
         parity = None

@@ -28,7 +28,7 @@ timeout -k 10 400 python bench.py --workload vae > gpurun_out/bench_vae_${TAG}.j
 echo "rc=$?" >> $S; cat gpurun_out/bench_vae_${TAG}.json >> $S
 if [ "$2" != "noncu" ]; then
   echo "=== ncu c3 launch list + full" >> $S
-  timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv \
+  PXA_PROFILER_RANGE=1 timeout -k 10 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv \
       --log-file gpurun_out/launches_${TAG}.csv python bench.py --no-cuda-graph --no-extras --no-parity --no-cpu-baseline --steps 1 --warmup 3 > gpurun_out/ncu_launch.log 2>&1
   echo "rc=$?" >> $S
   # one block's kernels (11 launches) from the third block of the first warm-up forward
