@@ -25,6 +25,8 @@ class GraphedForward:
             raise ValueError(f"GraphedForward supports {self.METHODS}, got {method!r}")
         self.model, self.method = model, method
         self._graphs: Dict[Tuple, dict] = {}
+        self._params = list(model.parameters())
+        self._wkey = None
 
     @staticmethod
     def _key(x, y, mask, data_info):
@@ -37,7 +39,14 @@ class GraphedForward:
     @torch.no_grad()
     def __call__(self, x: torch.Tensor, timestep: torch.Tensor, y: torch.Tensor, mask: Optional[torch.Tensor] = None,
                  data_info=None) -> torch.Tensor:
-        dev = next(self.model.parameters()).device
+        dev = self._params[0].device
+        # The kernels read the parameters in place, but the forward also keeps derived copies (the row-stacked kv_linear weights
+        # of model._KvBatch, the fused-LN tables) that a captured graph cannot refresh: an in-place update or a re-assignment of
+        # any parameter (optimizer / EMA step, .to(dtype)) drops the captured graphs.
+        wkey = (sum(p._version for p in self._params), self._params[0].data_ptr(), self._params[-1].data_ptr())
+        if wkey != self._wkey:
+            self._graphs.clear()
+            self._wkey = wkey
         key = self._key(x, y, mask, data_info)
         g = self._graphs.get(key)
         if g is None:

@@ -219,6 +219,31 @@ def _ln_ctx(u: torch.Tensor, v: torch.Tensor, one_plus: torch.Tensor, i: int, st
             "next_one_plus": one_plus[i + 1] if i + 1 < one_plus.shape[0] else None}
 
 
+class _KvBatch:
+    """All `cross_attn.kv_linear` layers of the model as ONE GEMM per forward (PixArt_blocks.py:48: `self.kv_linear(cond)` with the
+    same `cond` in every block).  28 GEMMs with M = B x text tokens (<= 2400 rows: 2 waves of half-empty tiles, 21 us each at c3)
+    become one with N = depth x 2C (0.09 ms).  Owns the row-stacked weight / bias copies, rebuilt when a weight changes."""
+
+    def __init__(self, blocks):
+        self.blocks = list(blocks)
+        self.key = None
+        self.w = self.b = None
+
+    def project(self, cond: torch.Tensor, ws: "_Workspace") -> torch.Tensor:
+        mods = [blk.cross_attn.kv_linear for blk in self.blocks]
+        key = tuple((m.weight._version, m.weight.data_ptr(), m.bias._version, m.bias.data_ptr()) for m in mods)
+        if key != self.key:
+            self.w = torch.cat([m.weight.detach() for m in mods], dim=0).contiguous()          # (depth * 2C, C)
+            self.b = torch.cat([m.bias.detach() for m in mods], dim=0).contiguous()
+            self.key = key
+        out = ws.get("kv_all", (cond.shape[0], self.w.shape[0]), cond.dtype, cond.device)
+        lib.gemm(cond, self.w, self.b, out)
+        return out
+
+
+_KV_BATCH = os.environ.get("PXA_KV_BATCH", "1") == "1"
+
+
 class _LnFusion:
     """Per-forward conditioning of the FUSED LayerNorm-modulate (include/pixart_sm100.h, PXA_EPI_LN_BIAS).
 
@@ -346,13 +371,16 @@ class PixArtMSBlock(nn.Module):
     # -- the fused path ---------------------------------------------------------------------------------------
     def run_kernels(self, x32: torch.Tensor, cond: torch.Tensor, kv_len: Optional[torch.Tensor],
                     kv_off: Optional[torch.Tensor], max_keys: int, mod: torch.Tensor, B: int, N: int,
-                    HW: Tuple[int, int], ws: _Workspace, ln: Optional[dict] = None) -> torch.Tensor:
+                    HW: Tuple[int, int], ws: _Workspace, ln: Optional[dict] = None,
+                    kv_pre: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One block on the kernels, in place on the fp32 residual stream.
 
         x32  (B*N, C) fp32 residual stream (updated in place and returned)
         cond (rows, C) bf16 embedded caption tokens; sample b's keys are rows kv_off[b] .. +kv_len[b]
              (kv_off None -> b*max_keys, kv_len None -> max_keys)
         mod  (B, 6, C) fp32 = scale_shift_table + t0  (shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp)
+        kv_pre  None, or this block's cross-attention keys / values (rows, 2C) bf16 (a strided view is fine) already projected by
+             `_KvBatch` -- the caption tokens are the same for every block, so PixArtMS.forward runs all kv_linear layers as ONE GEMM.
         ln   None: norm + modulate as a stand-alone pass (pxa_ln_modulate) before the QKV / fc1 GEMMs.
              dict (from `_ln_ctx`): the FUSED form -- LayerNorm + t2i_modulate evaluated inside the QKV / fc1 GEMM epilogues
              from the scaled bf16 copy of x and the row statistics that the preceding residual epilogue left behind.
@@ -398,13 +426,16 @@ class PixArtMSBlock(nn.Module):
 
         # (2) x += proj(cross_attn(x, cond))            (no norm, no gate)                       PixArtMS.py:76
         qx = ws.get("q_cross", (M, C), bf, dev)
-        kv = ws.get("kv_cross", (cond.shape[0], 2 * C), bf, dev)
         lib.gemm(xb, ca.q_linear.weight, ca.q_linear.bias, qx)
-        lib.gemm(cond, ca.kv_linear.weight, ca.kv_linear.bias, kv)
+        if kv_pre is None:
+            kv = ws.get("kv_cross", (cond.shape[0], 2 * C), bf, dev)
+            lib.gemm(cond, ca.kv_linear.weight, ca.kv_linear.bias, kv)
+        else:
+            kv = kv_pre
         kv4 = kv.view(-1, 2, H, C // H)
         lib.flash_attn(qx, kv4[:, 0], kv4[:, 1], ao, B=B, H=H, Nq=N, Nk=max_keys, kv_rows=cond.shape[0],
-                       kv_len=kv_len, kv_off=kv_off, q_strides=(C, C // H), k_strides=(2 * C, C // H),
-                       v_strides=(2 * C, C // H), scale=(C // H) ** -0.5)
+                       kv_len=kv_len, kv_off=kv_off, q_strides=(C, C // H), k_strides=(kv.stride(0), C // H),
+                       v_strides=(kv.stride(0), C // H), scale=(C // H) ** -0.5)
         if fused:       # the epilogue that produces x also leaves A = bf16(x (1 + scale_mlp)) and the row statistics of x
             lib.gemm(ao, ca.proj.weight, ca.proj.bias, x32, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x32, rows_per_batch=N,
                      out_aux=xn, aux_scale=one_plus[:, 1], aux_scale_batch_stride=one_plus.stride(0), row_stats_out=stats)
@@ -571,6 +602,7 @@ class PixArtMS(nn.Module):
         # (+13 / +39 us) cost more than the two 48 us passes they remove.  PXA_FUSE_LN=1 turns it on.
         self.fuse_ln_modulate = os.environ.get("PXA_FUSE_LN", "0") == "1"
         self.__dict__["_ln_fusion"] = None
+        self.__dict__["_kv_batch"] = None
         self._ws = _Workspace()
         self.initialize()
 
@@ -656,9 +688,15 @@ class PixArtMS(nn.Module):
                 self.__dict__["_ln_fusion"] = _LnFusion(self.blocks)
             u, v, one_plus = self._ln_fusion.prepare(t0.view(B, 6, C), mod_all, self._ws)
             stats = self._ws.get("ln_stats", (B * N, lib.LN_STAT_PARTS, 2), torch.float32, dev)
+        kv_all = None
+        if _KV_BATCH and len(self.blocks) > 1:
+            if self._kv_batch is None:
+                self.__dict__["_kv_batch"] = _KvBatch(self.blocks)
+            kv_all = self._kv_batch.project(cond, self._ws)
         for i, blk in enumerate(self.blocks):
             blk.run_kernels(x32, cond, kv_len, None, max_keys, mod_all[i], B, N, (self.h, self.w), self._ws,
-                            _ln_ctx(u, v, one_plus, i, stats) if fused else None)
+                            _ln_ctx(u, v, one_plus, i, stats) if fused else None,
+                            None if kv_all is None else kv_all[:, i * 2 * C:(i + 1) * 2 * C])
 
         fl = self.final_layer                                                                  # uses t, not t0 (:208)
         fmod = (fl.scale_shift_table.float()[None] + t[:, None]).contiguous()                  # (B, 2, C): shift, scale

@@ -74,6 +74,8 @@ class DPMSolverPP:
         self.schedule = _DiscreteVPSchedule(diffusion_steps)
         self._graphs: Dict[tuple, tuple] = {}
         self._cfg_cond: Optional[torch.Tensor] = None          # cat([uncondition, condition]), built once
+        owner = getattr(model, "__self__", model)              # the nn.Module behind a bound forward_with_dpmsolver
+        self._params = list(owner.parameters()) if isinstance(owner, torch.nn.Module) else []
 
     # ---- host side: everything that does not depend on the latents
     def plan(self, steps: int, order: int = 2, t_start: Optional[float] = None, t_end: Optional[float] = None,
@@ -155,7 +157,9 @@ class DPMSolverPP:
         # arguments, and `cond` / model_kwargs tensors into the captured forward: all of them are part of the key
         kw_id = tuple(sorted((k, (v.data_ptr(), tuple(v.shape)) if isinstance(v, torch.Tensor) else repr(v))
                              for k, v in (self.model_kwargs or {}).items()))
-        key = (tuple(x.shape), x.device.index, float(self.cfg_scale), cond.data_ptr(), tuple(cond.shape), kw_id,
+        # ... and so are the denoiser's parameters: the forward keeps derived copies (stacked kv_linear weights) a replay cannot refresh
+        wkey = (sum(p._version for p in self._params), self._params[0].data_ptr()) if self._params else None
+        key = (tuple(x.shape), x.device.index, float(self.cfg_scale), cond.data_ptr(), tuple(cond.shape), kw_id, wkey,
                tuple((st["t_input"], st["sigma_s"], st["alpha_s"], st["a"], st["b"], st["c"], st.get("order")) for st in plan))
         if key not in self._graphs:
             x_static = x.to(torch.float32).contiguous().clone()
