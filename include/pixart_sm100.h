@@ -243,9 +243,11 @@ typedef struct PxaAttnArgs {
   int32_t reverse_batch; /* 1: CTAs take the samples from the last to the first (same L2 argument as PxaGemmArgs.reverse_tiles:
                             the qkv rows of the last samples are the ones the QKV GEMM has just written)                   */
   int32_t variant;  /* 0 = auto (= 4).  Work item = 256 query rows of one (sample, head), two 128-row tiles with a double-buffered S:
-                       4 = persistent grid, one CTA per SM walks the items, the next item's loads and first Q K^T overlap the
-                       current item's output store; 2 = one CTA per item (same arithmetic, bit-identical results).
-                       3 = three tiles per CTA, single S buffer each, three softmax warps per sub-partition (attn3_sm100.cu)  */
+                       4 = persistent grid, one CTA per SM walks the items; the next item's loads and first Q K^T overlap the
+                           current item's epilogue; for Nk <= 1024 the output leaves as one TMA tensor store per 128-row tile;
+                       2 = one CTA per item (same arithmetic, bit-identical results);
+                       3 = three tiles per CTA, single S buffer each, three softmax warps per sub-partition (attn3_sm100.cu);
+                       5 / 6 / 7 = experiment forms of 4 (no tile-B stagger / direct output stores always / tile stores always) */
 } PxaAttnArgs;
 int pxa_flash_attn_d72_bf16(const PxaAttnArgs* args, void* stream);
 

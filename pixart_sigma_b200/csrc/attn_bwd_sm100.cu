@@ -53,6 +53,10 @@ namespace pxa {
 #ifndef PXA_BWD_PREFETCH
 #define PXA_BWD_PREFETCH 0
 #endif
+#ifndef PXA_BWD_BULK_OUT
+#define PXA_BWD_BULK_OUT 0    // 1: gradient rows through smem + one TMA bulk copy per ROW -- the forward measured this form slower
+                              // than direct stores (profiles/r2_attn_epilogue.txt); default: 256-bit stores
+#endif
 constexpr int kBEw = PXA_BWD_EW;
 constexpr int kBEwThreads = 128 * kBEw;        // elementwise threads
 constexpr int kBCols = 64 / kBEw;      // score columns per thread per sub-block
@@ -387,6 +391,20 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
 #pragma unroll
         for (int i = 0; i < 36; ++i) ow[i] = 0u;
       }
+#if PXA_BWD_BULK_OUT
+      // The gradient row leaves as ONE asynchronous TMA bulk copy from smem instead of 5 LSU store instructions that each cost 32
+      // transactions per warp (32 lanes = 32 different rows; attn_sm100.cu, profiles/r2_attn_epilogue.txt).  Staging: the stream
+      // ring -- acc_full has completed, so every TMA load has landed and every MMA that read a stage has retired.
+      {
+        uint4* srow = reinterpret_cast<uint4*>(smem + kBOffY + ((warp - 4) * 32 + lane) * 144);
+#pragma unroll
+        for (int c = 0; c < 9; ++c) srow[c] = make_uint4(ow[4 * c], ow[4 * c + 1], ow[4 * c + 2], ow[4 * c + 3]);
+        fence_proxy_async_smem();
+        if (row_ok) bulk_store_1d(dst, srow, 144);
+        tma_store_commit();
+        tma_store_wait_read<0>();                  // the CTA may exit once the copy has read the staging row
+      }
+#else
       if (row_ok) {
         const int lead = static_cast<int>((reinterpret_cast<uintptr_t>(dst) >> 4) & 1) * 4;   // words before the first 32-byte boundary
 #pragma unroll
@@ -401,6 +419,7 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
         if (lead) *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         else *reinterpret_cast<uint4*>(dst + 64) = make_uint4(ow[32], ow[33], ow[34], ow[35]);
       }
+#endif
     }
   }
 

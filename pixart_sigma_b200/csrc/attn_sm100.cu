@@ -59,7 +59,13 @@ constexpr int kD = 72;
 constexpr int kTileQ = 128;
 constexpr int kTileKV = 128;            // keys per TMA stage
 constexpr int kSub = 64;                // keys per MMA / softmax sub-block (half a stage)
-constexpr int kKVStages = 3;
+#ifndef PXA_BULK_OUT
+#define PXA_BULK_OUT 1        // output rows leave through smem + one TMA bulk copy per row (see kOffOut); 0: direct stores
+#endif
+#ifndef PXA_KV_STAGES
+#define PXA_KV_STAGES (PXA_BULK_OUT ? 2 : 3)   // 2 x 128 keys in flight = 5.6 k cycles of prefetch distance; 3 do not fit next to kOffOut
+#endif
+constexpr int kKVStages = PXA_KV_STAGES;
 constexpr int kMainBytes = 128 * 128;   // 128 rows x 64 bf16
 constexpr int kTailBytes = 128 * 32;    // 128 rows x 16 bf16
 constexpr int kTileBytes = kMainBytes + kTailBytes;
@@ -74,7 +80,15 @@ constexpr int kOffVTail = kOffKTail + kKVStages * kTailBytes;      // V tails ar
 constexpr int kVTailBytes = kMainBytes;                            // 128 keys x 128 B: d 64..71 valid, rest zero
 constexpr int kVTileBytes = kMainBytes + kVTailBytes;
 constexpr int kOffOnes = kOffVTail + kKVStages * kVTailBytes;      // 2 KB of bf16 1.0: B operand of the row-sum MMA
-constexpr int kOffBars = kOffOnes + 2048;
+// Output staging (PXA_BULK_OUT): the softmax threads of a tile park their finished rows (72 bf16 = 144 B each) here and ONE
+// elected thread hands the whole 128 x 72 tile to the TMA engine as a single tensor store -- the 5-9 store instructions per row of
+// the direct path go through the LSU, where 32 lanes writing 32 different rows cost 32 transactions per instruction: 20 us of an
+// 816 us self-attention call and 17 of a 79 us cross-attention call (profiles/r2_attn_epilogue.txt; one 144-byte bulk copy per
+// ROW was measured too: slower than the direct stores).  2 tiles x 128 rows x 144 B = 36 KB, paid for with the third K / V stage.
+constexpr int kOutRowBytes = kD * 2;
+constexpr int kOffOut = kOffOnes + 2048;
+constexpr int kOutTileBytes = kTileQ * kOutRowBytes;
+constexpr int kOffBars = kOffOut + (PXA_BULK_OUT ? 2 * kOutTileBytes : 0);
 constexpr int kAttnSmem = kOffBars + 256 + 1024;                    // + alignment slack
 
 // TMEM columns
@@ -96,6 +110,7 @@ struct AttnParams {
   int trace_item;       // debug only: the work item (of CTA 0) whose sub-block stamps PXA_TRACE records
   int stagger;          // persistent grid: tile B starts every item half an exp2 section behind tile A
   int wide_stores;      // out and its row stride are 32-byte aligned: 256-bit output stores
+  int tile_store;       // persistent grid: output tiles leave through smem + one TMA tensor store (drains under the next item)
 };
 
 constexpr int kTraceMax = 512;
@@ -115,7 +130,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_constant__ CUtensorMap tm_q_tail,
                       const __grid_constant__ CUtensorMap tm_k_main, const __grid_constant__ CUtensorMap tm_k_tail,
                       const __grid_constant__ CUtensorMap tm_v_main, const __grid_constant__ CUtensorMap tm_v_tail,
-                      const AttnParams p) {
+                      const __grid_constant__ CUtensorMap tm_out, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
@@ -158,6 +173,7 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
     prefetch_tmap(&tm_q_main); prefetch_tmap(&tm_q_tail);
     prefetch_tmap(&tm_k_main); prefetch_tmap(&tm_k_tail);
     prefetch_tmap(&tm_v_main); prefetch_tmap(&tm_v_tail);
+    prefetch_tmap(&tm_out);
     mbar_init(q_full, 1);
     for (int s = 0; s < kKVStages; ++s) {
       mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
@@ -555,7 +571,32 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
 #pragma unroll
       for (int i = 0; i < 36; ++i) ow[i] = 0u;
     }
-    if (row_ok) {
+#if PXA_BULK_OUT
+    if (p.tile_store) {
+      uint8_t* stile = smem + kOffOut + t * kOutTileBytes;
+      const bool issuer = qd == 0;                 // first warp of the tile: one elected lane talks to the TMA engine
+      if (issuer) {
+        if (elect_one()) tma_store_wait_read<0>(); // the previous item's store has read the staging tile
+      }
+      named_bar_sync(2 + t, 128);
+      uint4* srow = reinterpret_cast<uint4*>(stile + row_in_tile * kOutRowBytes);
+#pragma unroll
+      for (int c = 0; c < 9; ++c) srow[c] = make_uint4(ow[4 * c], ow[4 * c + 1], ow[4 * c + 2], ow[4 * c + 3]);
+      fence_proxy_async_smem();                    // the generic-proxy stores above -> visible to the TMA engine's read
+      named_bar_sync(2 + t, 128);
+      if (issuer && im.q0 + t * kTileQ < p.Nq) {   // rows >= Nq of a partial tile are clipped by the tensor map
+        if (elect_one()) {
+          tma_store_4d(&tm_out, stile, 0, h, im.q0 + t * kTileQ, b);
+          tma_store_commit();
+        }
+      }
+    }
+#endif
+#ifdef PXA_DEBUG_NO_STORE     // experiment only: how much of the epilogue is the output stores (results are wrong)
+    if (row_ok && ow[0] == 0x12345678u) {
+#else
+    if (row_ok && !(PXA_BULK_OUT && p.tile_store)) {
+#endif
       __nv_bfloat16* dst = p.out + (size_t)(b * p.Nq + qrow) * p.ldo + h * kD;
       if (p.wide_stores) {
         const int lead = (h & 1) ? 4 : 0;          // words in front of the first 32-byte boundary
@@ -584,6 +625,11 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       ++it;
     }
     }   // items
+#if PXA_BULK_OUT
+    // The staging tile must outlive the store's READ of it; the write to global memory completes on its own (waiting for it too
+    // cost the one-CTA-per-item launch 4.5 us per CTA: 880 instead of 816 us at 4096 keys).
+    tma_store_wait_read<0>();
+#endif
   }
 
   tc_fence_before();
@@ -627,7 +673,7 @@ extern "C" int pxa_flash_attn_d72_bf16(const PxaAttnArgs* args, void* stream) {
   if (reinterpret_cast<uintptr_t>(a.out) & 15) return fail(PXA_ERR_ALIGN, "out must be 16-byte aligned");
   if (a.H * kD > a.ldo) return fail(PXA_ERR_ARG, "ldo smaller than H*72");
   PXA_REQUIRE_SM100();
-  if (a.variant != 0 && (a.variant < 2 || a.variant > 5)) return fail(PXA_ERR_ARG, "variant must be 0, 2, 3, 4 or 5");
+  if (a.variant != 0 && (a.variant < 2 || a.variant > 7)) return fail(PXA_ERR_ARG, "variant must be 0 or 2..7");
   if (a.variant == 3 && !a.debug_trace) return flash_attn_d72_x3_launch(a, reinterpret_cast<cudaStream_t>(stream));
   CUtensorMap qm, qt, km, kt, vm, vt;
   int rc;
@@ -647,17 +693,29 @@ extern "C" int pxa_flash_attn_d72_bf16(const PxaAttnArgs* args, void* stream) {
   p.wide_stores = ((reinterpret_cast<uintptr_t>(a.out) & 31) == 0 && (a.ldo & 15) == 0) ? 1 : 0;
   p.item_trace = (a.debug_trace && a.variant == 5) ? 1 : 0;
   PXA_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_d72_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-  // variant 4: persistent grid, one CTA per SM walks the items; 2: one CTA per item (round-1 behaviour); 0 = auto: persistent for
-  // short key sets (the 300-token cross-attention: -24 %), one CTA per item for long ones (persistent measured 12 % SLOWER at
-  // 4096 keys, profiles/r2_attn_persistent.txt)
+  // variant 0 / 4: persistent grid, one CTA per SM walks the items; 2: one CTA per item (round-1 behaviour).  In-step A/B under
+  // the power cap (profiles/r2_instep_ab.txt, r2_attn_epilogue.txt): persistent wins for every key count on the boxes of sessions
+  // 19-29 (-0.9 ... -1.5 % of the c3 step; isolated 794 vs 819 us at 4096 keys, 67 vs 107 us for the 300-token cross-attention).
   const long long items = (long long)p.nx * a.H * a.B;
   long long grid = items;
-  const bool persistent = a.variant == 4 || a.variant == 5 || (a.variant == 0 && a.Nk <= 1024);
+  const bool persistent = a.variant != 2;
   if (persistent && grid > device_info().sms) grid = device_info().sms;
   p.stagger = (grid < items && a.variant != 5) ? 1 : 0;      // variant 5 (experiments): persistent without the stagger
+  // Output tiles through smem + one TMA tensor store: pays for short key sets, where the epilogue is a large part of an item
+  // (cross-attention 80 -> 67 us); at 4096 keys the direct 256-bit stores are faster (794 vs 821 us).  With one CTA per item the
+  // CTA could not retire before the TMA engine has read the staging tile (870 vs 816 us): never there.
+  p.tile_store = (PXA_BULK_OUT && grid < items && ((a.Nk <= 1024 && a.variant != 6) || a.variant == 7)) ? 1 : 0;
   p.trace_item = grid < items ? (int)(2 * grid) : 0;          // sub-block trace: CTA 0's third item when persistent
+  CUtensorMap om;
+  {
+    // out as [B][Nq][H][72]: one store per 128-row tile of one head; rows >= Nq (partial last tile) are clipped
+    uint64_t dims[4] = {(uint64_t)kD, (uint64_t)a.H, (uint64_t)a.Nq, (uint64_t)a.B};
+    uint64_t str[3] = {(uint64_t)kD * 2, (uint64_t)a.ldo * 2, (uint64_t)a.Nq * a.ldo * 2};
+    uint32_t box[4] = {(uint32_t)kD, 1, (uint32_t)kTileQ, 1};
+    if ((rc = make_tmap_bf16(&om, a.out, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+  }
   flash_attn_d72_kernel<<<(unsigned)grid, kAttnThreads, kAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(qm, qt, km, kt, vm,
-                                                                                                            vt, p);
+                                                                                                            vt, om, p);
   launch_counter()++;
   PXA_CHECK_CUDA(cudaGetLastError());
   return PXA_OK;

@@ -109,12 +109,22 @@ PXA_DEVICE void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+PXA_DEVICE void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 // smem tile ADDED into global memory by the TMA engine (element type from the tensor map: fp32), bulk-group completion.
 PXA_DEVICE void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
                    reinterpret_cast<uint64_t>(map)),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
+}
+// 1-D bulk copy shared -> global through the TMA engine (asynchronous, off the LSU): 16-byte aligned addresses, bytes % 16 == 0
+PXA_DEVICE void bulk_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
 PXA_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 template <int kN> PXA_DEVICE void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(kN) : "memory"); }
