@@ -6,7 +6,7 @@
 // while the softmax threads still write the current item's output -- the ~6 us of per-CTA prologue + epilogue that the
 // one-CTA-per-item launch exposed 14 times per SM (12 % of the self-attention at 4096 keys, half of the 300-key
 // cross-attention) shrink to the output store.  `variant = 2` launches one CTA per item (the round-1 behaviour).  384 threads:
-//   warp 0      TMA producer: Q once, then K / V stages of 128 keys into two 3-deep smem rings
+//   warp 0      TMA producer: Q per item, then K / V stages of 128 keys into two kKVStages-deep smem rings
 //   warp 1      MMA issuer (one elected thread): S = Q K^T (SS), O += P V (TS: P read from TMEM)
 //   warp 2      TMEM allocator (512 columns: S_A | S_B | O_A | O_B)
 //   warps 4-11  softmax, one thread per query row (tile A: warps 4-7, tile B: warps 8-11; 3 warps per SM sub-partition
