@@ -48,10 +48,12 @@ namespace pxa {
 #ifndef PXA_BWD_TMA_STATS
 #define PXA_BWD_TMA_STATS 1
 #endif
-// Experiment switch (round 2; default 0): split-phase TMEM loads -- S'(n+1) / dP'(n+1) are requested as soon as the registers
-// of sub-block n are free, behind the TMEM store + fence + arrive of n, instead of at the top of the next iteration.
-#ifndef PXA_BWD_PREFETCH
-#define PXA_BWD_PREFETCH 0
+// (Round 2 also measured split-phase TMEM loads -- S'(n+1) / dP'(n+1) requested behind the TMEM store of n: 1.498 vs 1.249 ms,
+// removed.)
+#ifndef PXA_BWD_PERSISTENT
+#define PXA_BWD_PERSISTENT 0  // 1: one CTA per SM walks the work items (same kernel, grid = SM count).  Measured at 4 x 16 x 4096:
+                              // 1.267 vs 1.226 ms, c5 step 122.2 vs 121.7 ms -- unlike the forward kernel, whose short cross-attention
+                              // items were half set-up time, every backward item streams >= 64 sub-blocks: one CTA per item stays.
 #endif
 #ifndef PXA_BWD_BULK_OUT
 #define PXA_BWD_BULK_OUT 0    // 1: gradient rows through smem + one TMA bulk copy per ROW -- the forward measured this form slower
@@ -105,6 +107,7 @@ struct AttnBwdParams {
   const int* kv_len;
   const int* kv_off;
   int B, H, Nq, Nk;
+  int nx;                  // 128-row stationary tiles per (sample, head): work item w -> (x = w % nx, h, b)
   float scale, scale_log2;
 };
 
@@ -124,21 +127,36 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
   uint64_t* s_full = y_empty + kBStages;       // [2]  MMA -> elementwise: S' and dP' of a sub-block are in buffer hh
   uint64_t* p_full = s_full + 2;               // [2]  elementwise -> MMA: P' / dS' written over buffer hh (kBEwThreads arrivals)
   uint64_t* acc_full = p_full + 2;             // [1]  MMA -> epilogue
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* x_empty = acc_full + 1;            // [1]  MMA -> TMA: the item's last score MMA has read the stationary tiles
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_empty + 1);
   float* stat = reinterpret_cast<float*>(smem + kBOffStat);     // [2][128]: -lse[64] | delta[64] of a streamed q sub-block
 
   const int warp = warp_idx_sync();
   const int lane = threadIdx.x & 31;
-  const int b = blockIdx.z, h = blockIdx.y;
-  const int t0 = blockIdx.x * kBT;
 
-  int kv_len = p.kv_len ? p.kv_len[b] : p.Nk;
-  kv_len = min(max(kv_len, 0), p.Nk);
-  const int kv_row0 = p.kv_off ? p.kv_off[b] : b * p.Nk;
-  if (kDKV && t0 >= kv_len) return;            // block-uniform: this key tile holds no keys of the sample
-  const int x_row0 = kDKV ? kv_row0 + t0 : b * p.Nq + t0;
-  const int y_row0 = kDKV ? b * p.Nq : kv_row0;
-  const int n_iter = ((kDKV ? p.Nq : kv_len) + kBSub - 1) / kBSub;          // 64-row sub-blocks of the stream
+  // PERSISTENT grid (like the forward kernel): one CTA per SM walks the work items w = blockIdx.x, + gridDim.x, ...; barrier
+  // phases, the stream ring position and the TMEM allocation carry over, the producer reloads the stationary tiles as soon as the
+  // item's last score MMA has been issued, and the next item's first scores are computed while the gradient rows are stored.
+  const int total_items = p.nx * p.H * p.B;
+  struct Item {
+    int b, h, t0, kv_len, x_row0, y_row0, n_iter;
+    bool skip;
+  };
+  auto decode = [&](int w) {
+    Item im;
+    const int x = w % p.nx, yz = w / p.nx;
+    im.h = yz % p.H;
+    im.b = yz / p.H;
+    im.t0 = x * kBT;
+    int kv_len = p.kv_len ? p.kv_len[im.b] : p.Nk;
+    im.kv_len = min(max(kv_len, 0), p.Nk);
+    const int kv_row0 = p.kv_off ? p.kv_off[im.b] : im.b * p.Nk;
+    im.skip = kDKV && im.t0 >= im.kv_len;          // this key tile holds no keys of the sample: nothing to compute or write
+    im.x_row0 = kDKV ? kv_row0 + im.t0 : im.b * p.Nq + im.t0;
+    im.y_row0 = kDKV ? im.b * p.Nq : kv_row0;
+    im.n_iter = ((kDKV ? p.Nq : im.kv_len) + kBSub - 1) / kBSub;          // 64-row sub-blocks of the stream
+    return im;
+  };
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tm_x1m); prefetch_tmap(&tm_x1t); prefetch_tmap(&tm_x2m); prefetch_tmap(&tm_x2t);
@@ -153,6 +171,7 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
       mbar_init(&p_full[i], kBEwThreads);
     }
     mbar_init(acc_full, 1);
+    mbar_init(x_empty, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -163,38 +182,48 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
 
   if (warp == 0) {
     // ================================================================ TMA producer
-    if (n_iter > 0 && elect_one()) {
-      mbar_arrive_expect_tx(x_full, 2 * kBTile);
-      tma_load_3d(smem + kBOffX1, &tm_x1m, x_full, 0, h, x_row0, kEvictNormal);
-      tma_load_3d(smem + kBOffX1 + kBMain, &tm_x1t, x_full, 64, h, x_row0, kEvictNormal);
-      tma_load_3d(smem + kBOffX2, &tm_x2m, x_full, 0, h, x_row0, kEvictNormal);
-      tma_load_3d(smem + kBOffX2 + kBMain, &tm_x2t, x_full, 64, h, x_row0, kEvictNormal);
-      for (int it = 0; it < n_iter; ++it) {
-        const int stage = it % kBStages;
-        const uint32_t ph = (it / kBStages) & 1;
-        mbar_wait(&y_empty[stage], ph ^ 1);
-        uint8_t* y1 = smem + kBOffY + stage * 2 * kBYTile;
-        uint8_t* y2 = y1 + kBYTile;
-        const int yrow = y_row0 + it * kBSub;
-        if constexpr (kDKV && kTmaStats) {
-          const uint32_t sb = (uint32_t)min(kBSub, p.Nq - it * kBSub) * 4u;            // bytes of lse (and of delta) in this sub-block
-          const size_t so = ((size_t)b * p.H + h) * p.Nq + (size_t)it * kBSub;
-          float* sdst = reinterpret_cast<float*>(smem + kBOffStat) + stage * 128;
-          mbar_arrive_expect_tx(&y_full[stage], 2 * kBYTile + 2 * sb);
-          tma_load_1d(sdst, p.lse + so, sb, &y_full[stage]);
-          tma_load_1d(sdst + 64, p.delta + so, sb, &y_full[stage]);
-        } else {
-          mbar_arrive_expect_tx(&y_full[stage], 2 * kBYTile);
+    if (elect_one()) {
+      uint32_t itc = 0, ybase = 0;                 // items with work so far; stream sub-blocks loaded so far (ring position)
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        const Item im = decode(w);
+        if (im.skip || im.n_iter == 0) continue;
+        const int h = im.h;
+        mbar_wait(x_empty, (itc & 1) ^ 1);         // the previous item's score MMAs are done with the stationary tiles
+        mbar_arrive_expect_tx(x_full, 2 * kBTile);
+        tma_load_3d(smem + kBOffX1, &tm_x1m, x_full, 0, h, im.x_row0, kEvictNormal);
+        tma_load_3d(smem + kBOffX1 + kBMain, &tm_x1t, x_full, 64, h, im.x_row0, kEvictNormal);
+        tma_load_3d(smem + kBOffX2, &tm_x2m, x_full, 0, h, im.x_row0, kEvictNormal);
+        tma_load_3d(smem + kBOffX2 + kBMain, &tm_x2t, x_full, 64, h, im.x_row0, kEvictNormal);
+        for (int n = 0; n < im.n_iter; ++n) {
+          const uint32_t g = ybase + n;
+          const int stage = g % kBStages;
+          const uint32_t ph = (g / kBStages) & 1;
+          mbar_wait(&y_empty[stage], ph ^ 1);
+          uint8_t* y1 = smem + kBOffY + stage * 2 * kBYTile;
+          uint8_t* y2 = y1 + kBYTile;
+          const int yrow = im.y_row0 + n * kBSub;
+          if constexpr (kDKV && kTmaStats) {
+            const uint32_t sb = (uint32_t)min(kBSub, p.Nq - n * kBSub) * 4u;            // bytes of lse (and of delta) in this sub-block
+            const size_t so = ((size_t)im.b * p.H + h) * p.Nq + (size_t)n * kBSub;
+            float* sdst = reinterpret_cast<float*>(smem + kBOffStat) + stage * 128;
+            mbar_arrive_expect_tx(&y_full[stage], 2 * kBYTile + 2 * sb);
+            tma_load_1d(sdst, p.lse + so, sb, &y_full[stage]);
+            tma_load_1d(sdst + 64, p.delta + so, sb, &y_full[stage]);
+          } else {
+            mbar_arrive_expect_tx(&y_full[stage], 2 * kBYTile);
+          }
+          tma_load_3d(y1, &tm_y1m, &y_full[stage], 0, h, yrow, kEvictLast);
+          tma_load_3d(y1 + kBYMain, &tm_y1t, &y_full[stage], 64, h, yrow, kEvictLast);
+          tma_load_3d(y2, &tm_y2m, &y_full[stage], 0, h, yrow, kEvictLast);
+          tma_load_3d(y2 + kBYMain, &tm_y2t, &y_full[stage], 64, h, yrow, kEvictLast);
         }
-        tma_load_3d(y1, &tm_y1m, &y_full[stage], 0, h, yrow, kEvictLast);
-        tma_load_3d(y1 + kBYMain, &tm_y1t, &y_full[stage], 64, h, yrow, kEvictLast);
-        tma_load_3d(y2, &tm_y2m, &y_full[stage], 0, h, yrow, kEvictLast);
-        tma_load_3d(y2 + kBYMain, &tm_y2t, &y_full[stage], 64, h, yrow, kEvictLast);
+        ybase += im.n_iter;
+        ++itc;
       }
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    if (n_iter > 0 && elect_one()) {
+    if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, kBSub, 0, 0);
       constexpr uint32_t idesc_g = make_idesc_bf16(128, 80, 0, 1);     // streamed tile MN-major, N = d 0..79
       const uint32_t sbase = smem_u32(smem);
@@ -219,30 +248,46 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
           umma_ts(acc, a_tmem + kBCols * ((16 * k) / kBCols) + ((16 * k) % kBCols) / 2, yd + (uint64_t)(k * (2048 >> 4)), idesc_g,
                   (first && k == 0) ? 0u : 1u);
       };
-      // S'(n), dP'(n) into score buffer n & 1
-      auto issue_scores = [&](int n) {
-        const int stage = n % kBStages, hh = n & 1;
-        mbar_wait(&y_full[stage], (n / kBStages) & 1);
-        tc_fence_after();
-        const uint32_t y1 = sbase + kBOffY + stage * 2 * kBYTile;
-        issue_score(t_s + kBSub * hh, sbase + kBOffX1, y1);
-        issue_score(t_dp + kBSub * hh, sbase + kBOffX2, y1 + kBYTile);
-        umma_commit(&s_full[hh]);
-      };
-      mbar_wait(x_full, 0);
-      issue_scores(0);
-      if (n_iter > 1) issue_scores(1);
-      for (int n = 0; n < n_iter; ++n) {
-        const int stage = n % kBStages, hh = n & 1;
-        const uint32_t y1 = sbase + kBOffY + stage * 2 * kBYTile;
-        mbar_wait(&p_full[hh], (n >> 1) & 1);
-        tc_fence_after();
-        if (kDKV) issue_grad(tmem_base + kBColAcc1, t_s + kBSub * hh, y1 + kBYTile, n == 0);    // dV += P' dO
-        issue_grad(tmem_base + kBColAcc2, t_dp + kBSub * hh, y1, n == 0);                       // dK += dS' Q  /  dQ += dS' K
-        umma_commit(&y_empty[stage]);
-        if (n + 2 < n_iter) issue_scores(n + 2);       // into the buffer whose P' / dS' the MMAs above have just consumed
+      // running counts across items: stream sub-blocks so far (ring stage / phase), completed uses of score buffer 0 / 1, items
+      uint32_t itc = 0, ybase = 0, hb0 = 0, hb1 = 0;
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        const Item im = decode(w);
+        if (im.skip || im.n_iter == 0) continue;
+        const int n_iter = im.n_iter;
+        // S'(n), dP'(n) into score buffer n & 1
+        auto issue_scores = [&](int n) {
+          const uint32_t g = ybase + n;
+          const int stage = g % kBStages, hh = n & 1;
+          mbar_wait(&y_full[stage], (g / kBStages) & 1);
+          tc_fence_after();
+          const uint32_t y1 = sbase + kBOffY + stage * 2 * kBYTile;
+          issue_score(t_s + kBSub * hh, sbase + kBOffX1, y1);
+          issue_score(t_dp + kBSub * hh, sbase + kBOffX2, y1 + kBYTile);
+          umma_commit(&s_full[hh]);
+          if (n + 1 == n_iter) umma_commit(x_empty);   // the item's last read of the stationary tiles
+        };
+        // The score buffers are free: every P' / dS' of the previous item was consumed by a gradient MMA issued earlier on the
+        // (in-order) tensor pipe.  The accumulators are overwritten by the first gradient MMA below, which waits for a P' that the
+        // elementwise threads publish only after their epilogue has read the previous item's accumulators.
+        mbar_wait(x_full, itc & 1);
+        issue_scores(0);
+        if (n_iter > 1) issue_scores(1);
+        for (int n = 0; n < n_iter; ++n) {
+          const int stage = (ybase + n) % kBStages, hh = n & 1;
+          const uint32_t y1 = sbase + kBOffY + stage * 2 * kBYTile;
+          mbar_wait(&p_full[hh], ((hh ? hb1 : hb0) + (n >> 1)) & 1);
+          tc_fence_after();
+          if (kDKV) issue_grad(tmem_base + kBColAcc1, t_s + kBSub * hh, y1 + kBYTile, n == 0);    // dV += P' dO
+          issue_grad(tmem_base + kBColAcc2, t_dp + kBSub * hh, y1, n == 0);                       // dK += dS' Q  /  dQ += dS' K
+          umma_commit(&y_empty[stage]);
+          if (n + 2 < n_iter) issue_scores(n + 2);       // into the buffer whose P' / dS' the MMAs above have just consumed
+        }
+        umma_commit(acc_full);
+        ybase += n_iter;
+        hb0 += (n_iter + 1) >> 1;
+        hb1 += n_iter >> 1;
+        ++itc;
       }
-      umma_commit(acc_full);
     }
   } else if (warp >= 4) {
     // ================================================================ elementwise stage + epilogue
@@ -252,8 +297,14 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
     const int row = qd * 32 + lane;                // stationary row (TMEM lane)
     const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
     const float sl2 = p.scale_log2;
-    const size_t stat_base = ((size_t)b * p.H + h) * p.Nq;
     const uint64_t sl2x2 = f32x2(sl2, sl2);
+    uint32_t itc = 0, ybase = 0, hb0 = 0, hb1 = 0;   // running counts across items (see the MMA issuer)
+
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+    const Item im = decode(w);
+    if (im.skip) continue;
+    const int b = im.b, h = im.h, t0 = im.t0, kv_len = im.kv_len, x_row0 = im.x_row0, n_iter = im.n_iter;
+    const size_t stat_base = ((size_t)b * p.H + h) * p.Nq;
     uint64_t nlse2 = 0, delta2 = 0;                // dQ pass: (-lse, -lse) and (delta, delta) of this thread's query row
     if (!kDKV) {
       const int qrow = min(t0 + row, p.Nq - 1);
@@ -269,23 +320,15 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
       named_bar_sync(1, kBEwThreads);
     }
 
-#if PXA_BWD_PREFETCH
-    uint32_t vs[kBCols], vd[kBCols];               // scores of the current sub-block (requested one sub-block ahead)
-    if (n_iter > 0) {
-      mbar_wait(&s_full[0], 0);
-      tc_fence_after();
-      ld_scores_nowait(tmem_base + kBColS + lane_sel + kBCols * half, vs, tmem_base + kBColDP + lane_sel + kBCols * half, vd);
-    }
-#endif
     for (int n = 0; n < n_iter; ++n) {
       const int hh = n & 1;
       const uint32_t t_s = tmem_base + kBColS + lane_sel + kBSub * hh + kBCols * half;
       const uint32_t t_dp = tmem_base + kBColDP + lane_sel + kBSub * hh + kBCols * half;
       // kTmaStats: +lse | delta of the stage, landed with the tiles; else -lse | delta handed over through smem buffer n & 1
-      const float* st = stat + (kTmaStats ? (n % kBStages) : (n & 1)) * 128 + kBCols * half;
+      const float* st = stat + (kTmaStats ? ((ybase + n) % kBStages) : (n & 1)) * 128 + kBCols * half;
       [[maybe_unused]] float nxt = 0.f;
       if constexpr (kTmaStats) {
-        if (kDKV) mbar_wait(&y_full[n % kBStages], (n / kBStages) & 1);  // (complete long ago) acquire the TMA-written stats
+        if (kDKV) mbar_wait(&y_full[(ybase + n) % kBStages], ((ybase + n) / kBStages) & 1);  // (complete long ago) acquire the TMA-written stats
       } else {
         if (kDKV && n + 1 < n_iter && tid < 128) {   // next sub-block's statistics: global load in flight during this one
           const size_t o = stat_base + min((n + 1) * kBSub + (tid & 63), p.Nq - 1);    // the last sub-block may be partial
@@ -294,14 +337,10 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
       }
       // the last sub-block of the stream (queries in the dKV pass, keys in the dQ pass) may be partial
       const int rem = (kDKV ? p.Nq : kv_len) - n * kBSub - kBCols * half;
-#if PXA_BWD_PREFETCH
-      ld_scores_wait(vs, vd);
-#else
-      mbar_wait(&s_full[hh], (n >> 1) & 1);
+      mbar_wait(&s_full[hh], ((hh ? hb1 : hb0) + (n >> 1)) & 1);
       tc_fence_after();
       uint32_t vs[kBCols], vd[kBCols];
       ld_scores(t_s, vs, t_dp, vd);
-#endif
       uint32_t pp[kBCols / 2], pd[kBCols / 2];
       // packed fp32 pairs (FFMA2 / FADD2 / FMUL2: one issue slot for two elements), exp2 on the MUFU pipe.  The masking
       // selects exist only in the copy of the loop taken by a partial last sub-block of the dQ pass.
@@ -329,20 +368,18 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
           const uint64_t g = mul2(f32x2(e0, e1), sub2(f32x2(__uint_as_float(vd[i]), __uint_as_float(vd[i + 1])), dl));
           float g0, g1;
           f32x2_split(g, g0, g1);
+          if constexpr (decltype(masked_tag)::value) {
+            // the statistics of columns past the end of the stream are whatever the smem held (the TMA copies stop at the last
+            // valid row): 0 * (dP' - NaN) would poison dS' -- select, do not multiply
+            if (i >= rem) g0 = 0.f;
+            if (i + 1 >= rem) g1 = 0.f;
+          }
           pp[i / 2] = pack_bf16x2(e0, e1);
           pd[i / 2] = pack_bf16x2(g0, g1);
         }
       };
       if (rem < kBCols) compute(std::true_type{});
       else compute(std::false_type{});
-#if PXA_BWD_PREFETCH
-      if (n + 1 < n_iter) {                        // S'(n+1) / dP'(n+1) sit in the other buffer (normally complete long ago)
-        const uint32_t off = kBSub * (hh ^ 1) + kBCols * half;
-        mbar_wait(&s_full[hh ^ 1], ((n + 1) >> 1) & 1);
-        tc_fence_after();
-        ld_scores_nowait(tmem_base + kBColS + lane_sel + off, vs, tmem_base + kBColDP + lane_sel + off, vd);
-      }
-#endif
       // bf16 results over the fp32 columns this thread has just consumed (its own slice: no cross-warp hazard)
       if (kDKV) st_packed(t_s, pp);
       st_packed(t_dp, pd);
@@ -359,7 +396,7 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
 
     // ---- epilogue: column slice 0 writes acc2 (dK / dQ, times the softmax scale), slice 1 writes acc1 (dV, dKV pass only)
     if (n_iter > 0) {
-      mbar_wait(acc_full, 0);
+      mbar_wait(acc_full, itc & 1);
       tc_fence_after();
     }
     if (half == 0 || (kDKV && half == 1)) {
@@ -421,6 +458,13 @@ flash_attn_d72_bwd_kernel(const __grid_constant__ CUtensorMap tm_x1m, const __gr
       }
 #endif
     }
+    if (n_iter > 0) {
+      ybase += n_iter;
+      hb0 += (n_iter + 1) >> 1;
+      hb1 += n_iter >> 1;
+      ++itc;
+    }
+    }   // items
   }
 
   tc_fence_before();
@@ -478,6 +522,7 @@ extern "C" int pxa_flash_attn_d72_bwd_bf16(const PxaAttnBwdArgs* args, void* str
   p.lse = a.lse; p.delta = a.delta;
   p.kv_len = a.kv_len; p.kv_off = a.kv_off;
   p.B = a.B; p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk;
+  p.nx = 0;
   p.scale = a.scale;
   p.scale_log2 = a.scale * 1.4426950408889634f;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -486,7 +531,9 @@ extern "C" int pxa_flash_attn_d72_bwd_bf16(const PxaAttnBwdArgs* args, void* str
     PXA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
     p.d2 = reinterpret_cast<__nv_bfloat16*>(a.dk); p.d2_sn = a.dk_sn; p.d2_sh = a.dk_sh;
     p.d1 = reinterpret_cast<__nv_bfloat16*>(a.dv); p.d1_sn = a.dv_sn; p.d1_sh = a.dv_sh;
-    dim3 grid((a.Nk + kBT - 1) / kBT, a.H, a.B);
+    p.nx = (a.Nk + kBT - 1) / kBT;
+    const long long items = (long long)p.nx * a.H * a.B;
+    const unsigned grid = (unsigned)(PXA_BWD_PERSISTENT && items > device_info().sms ? device_info().sms : items);
     kern<<<grid, kBwdThreads, kBwdSmem, s>>>(km, kt, vm, vt, qms, qts, gms, gts, p);
     launch_counter()++;
     PXA_CHECK_CUDA(cudaGetLastError());
@@ -496,7 +543,9 @@ extern "C" int pxa_flash_attn_d72_bwd_bf16(const PxaAttnBwdArgs* args, void* str
     PXA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
     p.d2 = reinterpret_cast<__nv_bfloat16*>(a.dq); p.d2_sn = a.dq_sn; p.d2_sh = a.dq_sh;
     p.d1 = nullptr; p.d1_sn = p.d1_sh = 0;
-    dim3 grid((a.Nq + kBT - 1) / kBT, a.H, a.B);
+    p.nx = (a.Nq + kBT - 1) / kBT;
+    const long long items = (long long)p.nx * a.H * a.B;
+    const unsigned grid = (unsigned)(PXA_BWD_PERSISTENT && items > device_info().sms ? device_info().sms : items);
     kern<<<grid, kBwdThreads, kBwdSmem, s>>>(qm, qt, gm, gt, kms, kts, vms, vts, p);
     launch_counter()++;
     PXA_CHECK_CUDA(cudaGetLastError());
