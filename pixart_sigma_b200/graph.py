@@ -43,9 +43,12 @@ class GraphedForward:
         # The kernels read the parameters in place, but the forward also keeps derived copies (the row-stacked kv_linear weights
         # of model._KvBatch, the fused-LN tables) that a captured graph cannot refresh: an in-place update or a re-assignment of
         # any parameter (optimizer / EMA step, .to(dtype)) drops the captured graphs.
+        # (Without such copies -- the default configuration -- a replay reads the updated parameters in place and nothing is dropped.)
         wkey = (sum(p._version for p in self._params), self._params[0].data_ptr(), self._params[-1].data_ptr())
         if wkey != self._wkey:
-            self._graphs.clear()
+            derived = getattr(self.model, "_kv_batch", None) is not None or getattr(self.model, "_ln_fusion", None) is not None
+            if self._wkey is not None and derived:
+                self._graphs.clear()
             self._wkey = wkey
         key = self._key(x, y, mask, data_info)
         g = self._graphs.get(key)

@@ -158,7 +158,9 @@ class DPMSolverPP:
         kw_id = tuple(sorted((k, (v.data_ptr(), tuple(v.shape)) if isinstance(v, torch.Tensor) else repr(v))
                              for k, v in (self.model_kwargs or {}).items()))
         # ... and so are the denoiser's parameters: the forward keeps derived copies (stacked kv_linear weights) a replay cannot refresh
-        wkey = (sum(p._version for p in self._params), self._params[0].data_ptr()) if self._params else None
+        owner = getattr(self.model, "__self__", self.model)
+        derived = getattr(owner, "_kv_batch", None) is not None or getattr(owner, "_ln_fusion", None) is not None
+        wkey = (sum(p._version for p in self._params), self._params[0].data_ptr()) if (self._params and derived) else None
         key = (tuple(x.shape), x.device.index, float(self.cfg_scale), cond.data_ptr(), tuple(cond.shape), kw_id, wkey,
                tuple((st["t_input"], st["sigma_s"], st["alpha_s"], st["a"], st["b"], st["c"], st.get("order")) for st in plan))
         if key not in self._graphs:
