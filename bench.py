@@ -489,7 +489,9 @@ def measure_train(args, ctx: Ctx, mode: str, checkpoint: bool, cpu_baseline: boo
     torch.manual_seed(1234)                                   # same initial weights on every rank (DDP replicas)
     with torch.device(dev):
         model = build_model(dict(type="PixArtMS_XL_2", input_size=side, pe_interpolation=pe, model_max_length=L),
-                            use_grad_checkpoint=checkpoint)
+                            use_grad_checkpoint=checkpoint, use_fp32_attention=not args.no_fp32_attention)
+        # configs/pixart_sigma_config/PixArt_sigma_xl2_img1024_internalms.py:14,27: fp32_attention = True, grad_checkpointing = True;
+        # the builder applies the flag together with checkpointing (builder.py:12-13), so --no-checkpoint runs have it off
         for blk in model.blocks:
             torch.nn.init.normal_(blk.cross_attn.proj.weight, std=0.02)
         torch.nn.init.normal_(model.final_layer.linear.weight, std=0.02)
@@ -588,6 +590,7 @@ def measure_train(args, ctx: Ctx, mode: str, checkpoint: bool, cpu_baseline: boo
                            "parallelism": f"ddp{world} (bucketed NCCL all-reduce of {reducer.grad_bytes() / 1e9:.2f} GB "
                                           f"{'bf16' if args.bf16_reduce else 'fp32'} gradients per rank, {len(reducer.buckets)} buckets)",
                            "step_mode": mode, "grad_checkpointing": checkpoint,
+                           "fp32_attention": bool(getattr(model.blocks[0].attn, "fp32_attention", False)),
                            "optimizer_step": "not included (fwd + bwd + all-reduce, as configs[4] states)",
                            "l2": "working set (2.4 GB fp32 weights + activations) larger than L2; no flush needed",
                            "tflop_model_per_step_per_gpu": 3 * fwd / 1e12, "peak_mem_gib": peak_mem, "loss": float(loss0),
@@ -709,6 +712,9 @@ def main():
     ap.add_argument("--train-mode", default="auto", choices=["auto", "eager", "graph", "graph-overlap"],
                     help="c5: how the step is issued; auto = one CUDA graph (all-reduce after the replay)")
     ap.add_argument("--no-checkpoint", action="store_true", help="c5: train without per-block activation checkpointing")
+    ap.add_argument("--no-fp32-attention", action="store_true",
+                    help="c5: leave fp32_attention off (the reference 1024px config sets it; it makes the self-attention forward "
+                         "take P as bf16 hi + lo terms)")
     ap.add_argument("--bf16-reduce", action="store_true", help="c5: gradients travel as bf16 (1.22 GB instead of 2.44 GB)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -289,11 +289,18 @@ class GeluFn(torch.autograd.Function):
         return lib.gelu_tanh(pre, dh=dh.contiguous())
 
 
+def _fp32_p(attn) -> bool:
+    """`fp32_attention` (set on every submodule by `set_grad_checkpoint`, model/utils.py:31-34; read by AttentionKVCompress only,
+    PixArt_blocks.py:145-147): the forward P V takes P as bf16 hi + lo terms (PxaAttnArgs.p_precision = 1).  The backward
+    kernel recomputes P from the same fp32 statistics and keeps its bf16 operands (gradient bars: DESIGN.md section 2)."""
+    return bool(getattr(attn, "fp32_attention", False))
+
+
 class SelfAttnFn(torch.autograd.Function):
     """o (B*N, C) = attention over the q/k/v slices of the qkv GEMM output (B*N, 3C) (PixArt_blocks.py:130-153)."""
 
     @staticmethod
-    def forward(ctx, qkv, B, H, N, scale, keep):
+    def forward(ctx, qkv, B, H, N, scale, keep, fp32_p=False):
         qkv = qkv.contiguous()
         M, C3 = qkv.shape
         C = C3 // 3
@@ -307,7 +314,7 @@ class SelfAttnFn(torch.autograd.Function):
             lse = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device)
             st = (3 * C, D)
             lib.flash_attn(q3[:, 0], q3[:, 1], q3[:, 2], o, B=B, H=H, Nq=N, Nk=N, kv_rows=M, q_strides=st, k_strides=st,
-                           v_strides=st, scale=scale, lse=lse)
+                           v_strides=st, scale=scale, lse=lse, fp32_p=fp32_p)
             if keep is not None and not keep.get("replay"):
                 keep["self"] = (o, lse)
         ctx.save_for_backward(qkv, o, lse)
@@ -328,7 +335,7 @@ class SelfAttnFn(torch.autograd.Function):
         lib.flash_attn_bwd(q3[:, 0], q3[:, 1], q3[:, 2], o, d_o.contiguous(), lse, d3[:, 0], d3[:, 1], d3[:, 2], B=B, H=H,
                            Nq=N, Nk=N, kv_rows=M, q_strides=st, k_strides=st, v_strides=st, dq_strides=st, dk_strides=st,
                            dv_strides=st, scale=scale)
-        return dqkv, None, None, None, None, None
+        return dqkv, None, None, None, None, None, None
 
 
 class QkNormFn(torch.autograd.Function):
@@ -412,7 +419,7 @@ class AttnKVFn(torch.autograd.Function):
     (KV-compressed self-attention, PixArt_blocks.py:137-153)."""
 
     @staticmethod
-    def forward(ctx, qkv, kc, vc, B, H, N, Nk, scale):
+    def forward(ctx, qkv, kc, vc, B, H, N, Nk, scale, fp32_p=False):
         qkv, kc, vc = qkv.contiguous(), kc.contiguous(), vc.contiguous()
         M, C3 = qkv.shape
         C = C3 // 3
@@ -420,7 +427,7 @@ class AttnKVFn(torch.autograd.Function):
         o = torch.empty((M, C), dtype=torch.bfloat16, device=qkv.device)
         lse = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device)
         lib.flash_attn(qkv[:, :C], kc, vc, o, B=B, H=H, Nq=N, Nk=Nk, kv_rows=B * Nk, q_strides=(C3, D), k_strides=(C, D),
-                       v_strides=(C, D), scale=scale, lse=lse)
+                       v_strides=(C, D), scale=scale, lse=lse, fp32_p=fp32_p)
         ctx.save_for_backward(qkv, kc, vc, o, lse)
         ctx.geom = (B, H, N, Nk, scale)
         return o
@@ -437,7 +444,7 @@ class AttnKVFn(torch.autograd.Function):
         lib.flash_attn_bwd(qkv[:, :C], kc, vc, o, d_o.contiguous(), lse, dqkv[:, :C], dkc, dvc, B=B, H=H, Nq=N, Nk=Nk,
                            kv_rows=B * Nk, q_strides=(C3, D), k_strides=(C, D), v_strides=(C, D), dq_strides=(C3, D),
                            dk_strides=(C, D), dv_strides=(C, D), scale=scale)
-        return dqkv, dkc, dvc, None, None, None, None, None
+        return dqkv, dkc, dvc, None, None, None, None, None, None
 
 
 class CrossAttnFn(torch.autograd.Function):
@@ -500,7 +507,7 @@ def _compressed_self_attention(a, qkv: torch.Tensor, B: int, H: int, N: int, HW)
         kc, vc = (qkv[:, i * C:(i + 1) * C].reshape(B, Hh, Ww, C)[:, ::sr, ::sr].reshape(-1, C) for i in (1, 2))
     else:
         raise ValueError(a.sampling)
-    return AttnKVFn.apply(qkv, kc, vc, B, H, N, kc.shape[0] // B, a.scale)
+    return AttnKVFn.apply(qkv, kc, vc, B, H, N, kc.shape[0] // B, a.scale, _fp32_p(a))
 
 
 def block_forward_train(blk, x32: torch.Tensor, cond: torch.Tensor, kv_len: Optional[torch.Tensor],
@@ -521,7 +528,7 @@ def block_forward_train(blk, x32: torch.Tensor, cond: torch.Tensor, kv_len: Opti
     if a.sr_ratio > 1:                                                       # KV token compression, PixArt_blocks.py:137-139
         ao = _compressed_self_attention(a, _qk_norm(a, linear(xn, a.qkv)), B, H, N, HW)
     else:
-        ao = SelfAttnFn.apply(_qk_norm(a, linear(xn, a.qkv)), B, H, N, a.scale, keep)
+        ao = SelfAttnFn.apply(_qk_norm(a, linear(xn, a.qkv)), B, H, N, a.scale, keep, _fp32_p(a))
     x32 = LinearGateResidualFn.apply(ao, a.proj.weight, a.proj.bias, a.proj, x32, mod, 2, N)
     # (2) x += proj(cross_attn(x, cond))                                                          PixArtMS.py:76
     qx = linear(x32.to(torch.bfloat16), ca.q_linear)
@@ -567,7 +574,7 @@ def _block_forward_kernels(blk, x32, cond, mod, kv_len, kv_off, max_keys, B, N, 
     if kept is None:
         t["ao1"], t["lse1"] = torch.empty((M, C), **bf), torch.empty((B, H, N), **f32)
         lib.flash_attn(q3[:, 0], q3[:, 1], q3[:, 2], t["ao1"], B=B, H=H, Nq=N, Nk=N, kv_rows=M, q_strides=st, k_strides=st,
-                       v_strides=st, scale=a.scale, lse=t["lse1"])
+                       v_strides=st, scale=a.scale, lse=t["lse1"], fp32_p=_fp32_p(a))
     else:
         t["ao1"], t["lse1"] = kept[0], kept[1]
     t["x1"], t["y1"] = torch.empty((M, C), **f32), torch.empty((M, C), **bf)

@@ -126,6 +126,15 @@ constexpr int kTraceMax = 512;
     if (p.item_trace && blockIdx.x == 0 && it < 64) p.trace[(slot) * kTraceMax + 8 * it + (k)] = clock64();  \
   } while (0)
 
+// kSplitP = "fp32_attention" grade P V (PxaAttnArgs.p_precision = 1; PixArt_blocks.py:145-147 keeps q / k / v and therefore P in
+// fp32): the softmax threads publish P as TWO bf16 terms, P_hi = bf16(P) over the first 32 columns of the S half (as always) and
+// P_lo = bf16(P - P_hi) over the other 32 columns -- free once the scores are in registers -- and the MMA thread accumulates
+// P_hi V + P_lo V (same V descriptor, A operand 32 TMEM columns further).  P then carries 16 mantissa bits (2^-17 relative
+// instead of 2^-9), V is bf16-valued in the reference too (the qkv GEMM output), the products are exact and the accumulation is
+// fp32: the result is the fp32 attention of the same bf16 q / k / v up to summation order.  Tensor work per 64-key sub-block pair
+// goes 640 -> 960 cycles, still under the 1024-cycle exp2 floor, and no smem or TMEM is added (a kind::tf32 P V would need fp32
+// V tiles -- twice the smem traffic -- for the same tensor-pipe time).
+template <bool kSplitP>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_constant__ CUtensorMap tm_q_tail,
                       const __grid_constant__ CUtensorMap tm_k_main, const __grid_constant__ CUtensorMap tm_k_tail,
@@ -270,6 +279,11 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
           const uint32_t acc = (first && k == 0) ? 0u : 1u;
           umma_ts(om, pt + 8 * k, vd + (uint64_t)((4 * hh + k) * (2048 >> 4)), idesc_pv, acc);
         }
+        if constexpr (kSplitP) {                     // + P_lo V: the low-order bf16 term of P sits 32 columns behind P_hi
+#pragma unroll
+          for (int k = 0; k < kSub / 16; ++k)
+            umma_ts(om, pt + 32 + 8 * k, vd + (uint64_t)((4 * hh + k) * (2048 >> 4)), idesc_pv, 1u);
+        }
 #if PXA_SUM_MMA
         // L_t += P[t][hh] 1 : the row sums of the (bf16-rounded) P that P V multiplies, for free on the tensor pipe.  The
         // B operand is all ones, so any valid descriptor over the 2 KB ones region will do.
@@ -278,6 +292,10 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         const uint32_t lm = tmem_base + kColL + t * 128;
 #pragma unroll
         for (int k = 0; k < kSub / 16; ++k) umma_ts(lm, pt + 8 * k, od, idesc_l, (first && k == 0) ? 0u : 1u);
+        if constexpr (kSplitP) {
+#pragma unroll
+          for (int k = 0; k < kSub / 16; ++k) umma_ts(lm, pt + 32 + 8 * k, od, idesc_l, 1u);
+        }
 #endif
       };
 
@@ -451,8 +469,10 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
       // the polynomial exp2 (FMA pipe) instead of MUFU (16 results/clk/SM), so that both pipes and the issue port end up
       // about equally loaded.
       uint32_t pk[32];
+      [[maybe_unused]] uint32_t pl[16];             // kSplitP: P_lo words of 32 keys at a time
       // one pair of scores -> exp2 -> running packed sum + bf16x2 P word; `pair` (0..31) selects MUFU or polynomial
-      auto exp_pair = [&](float s0, float s1, int pair, [[maybe_unused]] uint64_t& acc, uint32_t& packed) {
+      auto exp_pair = [&](float s0, float s1, int pair, [[maybe_unused]] uint64_t& acc, uint32_t& packed,
+                          [[maybe_unused]] uint32_t& packed_lo) {
         [[maybe_unused]] uint64_t e;
         float e0, e1;
         if (PXA_POLY_OF8 > 0 && ((pair * PXA_POLY_OF8) & 7) < PXA_POLY_OF8) {
@@ -472,12 +492,16 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
         acc = add2(acc, e);
 #endif
         packed = pack_bf16x2(e0, e1);
+        if constexpr (kSplitP) packed_lo = pack_bf16x2(e0 - bf16_lo(packed), e1 - bf16_hi(packed));   // exact differences
       };
 #pragma unroll
       for (int i = 0; i < 16; i += 2) {
-        exp_pair(__uint_as_float(va[2 * i]), __uint_as_float(va[2 * i + 1]), i, sa, pk[i]);
-        exp_pair(__uint_as_float(va[2 * i + 2]), __uint_as_float(va[2 * i + 3]), i + 1, sb, pk[i + 1]);
+        exp_pair(__uint_as_float(va[2 * i]), __uint_as_float(va[2 * i + 1]), i, sa, pk[i], pl[i]);
+        exp_pair(__uint_as_float(va[2 * i + 2]), __uint_as_float(va[2 * i + 3]), i + 1, sb, pk[i + 1], pl[i + 1]);
       }
+      // P_lo of keys 0..31 -> columns 32..47 of this S half (their scores were read into vb long ago; completion is covered by
+      // the tcgen05.wait::st in front of the P barrier)
+      if constexpr (kSplitP) tmem_st_32x32b_x16(ts + 32, pl);
       // Persistent grid: at an item boundary both tiles find their first S complete and would start IN PHASE -- and stay
       // there (1650 instead of 1395 cycles per sub-block, tools/attn_itrace.py): the kernel's good operating point is tile B
       // about half an exp2 section behind tile A, which is what a fresh CTA falls into because S_A(0) is issued first.  So tile B
@@ -496,9 +520,10 @@ flash_attn_d72_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gri
 #endif
 #pragma unroll
       for (int i = 0; i < 16; i += 2) {
-        exp_pair(__uint_as_float(vb[2 * i]), __uint_as_float(vb[2 * i + 1]), 16 + i, sa, pk[16 + i]);
-        exp_pair(__uint_as_float(vb[2 * i + 2]), __uint_as_float(vb[2 * i + 3]), 16 + i + 1, sb, pk[16 + i + 1]);
+        exp_pair(__uint_as_float(vb[2 * i]), __uint_as_float(vb[2 * i + 1]), 16 + i, sa, pk[16 + i], pl[i]);
+        exp_pair(__uint_as_float(vb[2 * i + 2]), __uint_as_float(vb[2 * i + 3]), 16 + i + 1, sb, pk[16 + i + 1], pl[i + 1]);
       }
+      if constexpr (kSplitP) tmem_st_32x32b_x16(ts + 48, pl);
 #if PXA_PREFETCH_S
       if (has_next) tmem_ld_32x32b_x32_nowait(tn + 32, vb);
 #endif
@@ -674,6 +699,8 @@ extern "C" int pxa_flash_attn_d72_bf16(const PxaAttnArgs* args, void* stream) {
   if (a.H * kD > a.ldo) return fail(PXA_ERR_ARG, "ldo smaller than H*72");
   PXA_REQUIRE_SM100();
   if (a.variant != 0 && (a.variant < 2 || a.variant > 7)) return fail(PXA_ERR_ARG, "variant must be 0 or 2..7");
+  if (a.p_precision != 0 && a.p_precision != 1) return fail(PXA_ERR_ARG, "p_precision must be 0 (bf16 P) or 1 (bf16 hi + lo P)");
+  if (a.variant == 3 && a.p_precision) return fail(PXA_ERR_ARG, "variant 3 has no p_precision = 1 form");
   if (a.variant == 3 && !a.debug_trace) return flash_attn_d72_x3_launch(a, reinterpret_cast<cudaStream_t>(stream));
   CUtensorMap qm, qt, km, kt, vm, vt;
   int rc;
@@ -692,7 +719,8 @@ extern "C" int pxa_flash_attn_d72_bf16(const PxaAttnArgs* args, void* stream) {
   p.trace = reinterpret_cast<long long*>(a.debug_trace);
   p.wide_stores = ((reinterpret_cast<uintptr_t>(a.out) & 31) == 0 && (a.ldo & 15) == 0) ? 1 : 0;
   p.item_trace = (a.debug_trace && a.variant == 5) ? 1 : 0;
-  PXA_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_d72_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+  auto kernel = a.p_precision ? flash_attn_d72_kernel<true> : flash_attn_d72_kernel<false>;
+  PXA_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
   // variant 0 / 4: persistent grid, one CTA per SM walks the items; 2: one CTA per item (round-1 behaviour).  In-step A/B under
   // the power cap (profiles/r2_instep_ab.txt, r2_attn_epilogue.txt): persistent wins for every key count on the boxes of sessions
   // 19-29 (-0.9 ... -1.5 % of the c3 step; isolated 794 vs 819 us at 4096 keys, 67 vs 107 us for the 300-token cross-attention).
@@ -714,8 +742,7 @@ extern "C" int pxa_flash_attn_d72_bf16(const PxaAttnArgs* args, void* stream) {
     uint32_t box[4] = {(uint32_t)kD, 1, (uint32_t)kTileQ, 1};
     if ((rc = make_tmap_bf16(&om, a.out, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
   }
-  flash_attn_d72_kernel<<<(unsigned)grid, kAttnThreads, kAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(qm, qt, km, kt, vm,
-                                                                                                            vt, om, p);
+  kernel<<<(unsigned)grid, kAttnThreads, kAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(qm, qt, km, kt, vm, vt, om, p);
   launch_counter()++;
   PXA_CHECK_CUDA(cudaGetLastError());
   return PXA_OK;

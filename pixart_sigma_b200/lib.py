@@ -75,7 +75,7 @@ class AttnArgs(C.Structure):
                 ("kv_rows", C.c_int64),
                 ("B", C.c_int32), ("H", C.c_int32), ("Nq", C.c_int32), ("Nk", C.c_int32),
                 ("ldo", C.c_int32), ("scale", C.c_float), ("debug_trace", C.c_void_p), ("lse", C.c_void_p),
-                ("reverse_batch", C.c_int32), ("variant", C.c_int32)]
+                ("reverse_batch", C.c_int32), ("variant", C.c_int32), ("p_precision", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class KvCompressArgs(C.Structure):
@@ -294,9 +294,9 @@ def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Ten
                Nk: int, kv_rows: int, kv_len: Optional[torch.Tensor] = None, kv_off: Optional[torch.Tensor] = None,
                q_strides=None, k_strides=None, v_strides=None, scale: Optional[float] = None,
                debug_trace: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None,
-               variant: int = 0, reverse_batch: bool = False) -> torch.Tensor:
+               variant: int = 0, reverse_batch: bool = False, fp32_p: bool = False) -> torch.Tensor:
     """Head-dim-72 attention. q/k/v are bf16 *views*; strides are (row, head) in elements, e.g. slices of the
-    (rows, 3, H, 72) qkv GEMM output. out is (B*Nq, H*72) bf16."""
+    (rows, 3, H, 72) qkv GEMM output. out is (B*Nq, H*72) bf16.  fp32_p: `fp32_attention` grade P V (P as bf16 hi + lo)."""
     assert q.dtype == k.dtype == v.dtype == out.dtype == torch.bfloat16
     for tns in (kv_len, kv_off):
         if tns is not None:
@@ -306,7 +306,7 @@ def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Ten
                     v_sn=v_strides[0], v_sh=v_strides[1], kv_rows=kv_rows, B=B, H=H, Nq=Nq, Nk=Nk,
                     ldo=out.stride(0), scale=scale if scale is not None else 72 ** -0.5,
                     debug_trace=_ptr(debug_trace), lse=_ptr(lse), variant=variant or _ATTN_VARIANT,
-                    reverse_batch=int(reverse_batch))
+                    reverse_batch=int(reverse_batch), p_precision=int(bool(fp32_p)), reserved0=0)
     if lse is not None:
         assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == B * H * Nq
     _check(load().pxa_flash_attn_d72_bf16(C.byref(args), _stream()), "pxa_flash_attn_d72_bf16")

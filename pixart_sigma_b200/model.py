@@ -422,7 +422,8 @@ class PixArtMSBlock(nn.Module):
         # L2 chaining (126 MB): each kernel starts on the rows its producer wrote last -- the QKV GEMM runs front to back, the
         # attention back to front (so attn.proj, front to back again, finds the first samples' outputs still cached)
         lib.flash_attn(q3[:, 0], k_src, v_src, ao, B=B, H=H, Nq=N, Nk=n_keys, kv_rows=B * n_keys,
-                       q_strides=(3 * C, C // H), k_strides=k_str, v_strides=k_str, scale=a.scale, reverse_batch=_L2_CHAIN)
+                       q_strides=(3 * C, C // H), k_strides=k_str, v_strides=k_str, scale=a.scale, reverse_batch=_L2_CHAIN,
+                       fp32_p=bool(getattr(a, "fp32_attention", False)))
         lib.gemm(ao, a.proj.weight, a.proj.bias, x32, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x32, gate=mod[:, 2],
                  gate_batch_stride=ms, rows_per_batch=N, out_aux=xb)
 

@@ -480,6 +480,50 @@ def test_flash_attn_persistent_grid_is_bit_identical_to_one_cta_per_item():
     assert all(torch.equal(lses[0], l) for l in lses[1:])
 
 
+@pytest.mark.parametrize("variant", [0, 2])
+def test_flash_attn_fp32_p_mode_matches_fp32_attention(variant):
+    """`fp32_attention` (PixArt_blocks.py:145-147: q / k / v -- and therefore P -- kept in fp32 through P V): p_precision = 1
+    feeds P to the tensor pipe as bf16 hi + lo terms.  Against the fp32 attention of the same bf16 q / k / v the result is then
+    the CORRECTLY ROUNDED bf16 output for nearly every element (the only error left is the final bf16 store), while the default
+    mode (P rounded to bf16, 2^-9) misses the correctly rounded value much more often.  Ragged key sets incl. a partial last
+    sub-block, a single sub-block and an empty set; 4 work items per CTA under the persistent grid at the larger size."""
+    for (B, H, N, Nk, lens) in [(2, 3, 300, 300, [300, 77]), (5, 16, 2048, 1024, [1024, 65, 0, 449, 1000])]:
+        q, k, v = _randn(B, N, H, 72, seed=140), _randn(B, Nk, H, 72, seed=141), _randn(B, Nk, H, 72, seed=142)
+        kl = torch.tensor(lens, dtype=torch.int32, device=DEV)
+        want = torch.zeros(B, N, H, 72, dtype=torch.float64, device=DEV)     # float64: the check below is about single ulps of bf16
+        for b, L in enumerate(lens):
+            if L:
+                sc = torch.einsum("nhd,mhd->hnm", q[b].double(), k[b, :L].double()) * 72 ** -0.5
+                want[b] = torch.einsum("hnm,mhd->nhd", torch.softmax(sc, -1), v[b, :L].double())
+        want = want.reshape(B * N, H * 72).float()
+        outs, lses = {}, {}
+        for fp32_p in (False, True):
+            out = torch.full((B * N, H * 72), float("nan"), dtype=torch.bfloat16, device=DEV)
+            lse = torch.full((B, H, N), float("nan"), dtype=torch.float32, device=DEV)
+            lib.flash_attn(q, k, v, out, B=B, H=H, Nq=N, Nk=Nk, kv_rows=B * Nk, kv_len=kl, q_strides=(H * 72, 72),
+                           k_strides=(H * 72, 72), v_strides=(H * 72, 72), lse=lse, variant=variant, fp32_p=fp32_p)
+            outs[fp32_p], lses[fp32_p] = out, lse
+        torch.cuda.synchronize()
+        assert torch.isfinite(outs[True].float()).all()
+        assert torch.equal(lses[True], lses[False])                 # same fp32 logits and statistics in both modes
+        e_split, e_bf16 = po.rel_err(outs[True].float(), want), po.rel_err(outs[False].float(), want)
+        rounded = want.to(torch.bfloat16)
+        miss_split = (outs[True] != rounded).float().mean().item()
+        miss_bf16 = (outs[False] != rounded).float().mean().item()
+        print(f"fp32_p B={B} N={N} Nk={Nk} variant={variant}: rel_err split {e_split:.3e} / bf16-P {e_bf16:.3e}; "
+              f"not correctly rounded: split {miss_split:.4f} / bf16-P {miss_bf16:.4f}")
+        assert e_split < 2.5e-3 and e_split <= e_bf16 * 1.001       # 2^-9 / sqrt(3) = 1.1e-3 is the bf16 store alone
+        assert miss_split < 0.05 and miss_split < 0.25 * miss_bf16
+
+
+def test_flash_attn_fp32_p_rejected_where_unsupported():
+    q = _randn(1, 128, 1, 72, seed=143)
+    out = torch.empty(128, 72, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(lib.PxaError):
+        lib.flash_attn(q, q, q, out, B=1, H=1, Nq=128, Nk=128, kv_rows=128, q_strides=(72, 72), k_strides=(72, 72),
+                       v_strides=(72, 72), variant=3, fp32_p=True)
+
+
 # ------------------------------------------------------------------------------------------------- fused Mlp (one persistent kernel)
 @pytest.mark.parametrize("M,rpb,max_ctas,group,ring,lag,ks", [
     (256, 256, 0, 4, 3, 1, 0), (2304, 1152, 0, 4, 3, 1, 1), (1000, 500, 0, 2, 2, 1, 0), (4096, 1024, 6, 2, 2, 1, 0),

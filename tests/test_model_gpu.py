@@ -21,7 +21,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 if torch.cuda.is_available():
-    from pixart_sigma_b200 import PixArtMS
+    from pixart_sigma_b200 import PixArtMS, lib
 
 
 def _log(line):
@@ -104,6 +104,46 @@ def test_block_forward_matches_oracle_1e3(B, hw, lens, sr, fused):
         got2 = blk(x.to(torch.bfloat16).cuda(), ycat.cuda()[None], t0.to(torch.bfloat16).cuda(), lens, hw)
     assert got2.dtype == torch.bfloat16 and got2.shape == (B, N, C)
     assert po.rel_err(got2.float().cpu(), want) < 6e-3
+
+
+@pytest.mark.parametrize("sr", [1, 2])
+def test_block_fp32_attention_flag_selects_hi_lo_p(sr):
+    """`fp32_attention = True` (set by `set_grad_checkpoint` on every submodule, model/utils.py:31-34; read by
+    AttentionKVCompress.forward, PixArt_blocks.py:145-147) makes the self-attention take P as bf16 hi + lo terms: the block is
+    at least as close to the fp32 oracle as with bf16 P, the self-attention kernel launch count is unchanged, and the
+    result differs from the default mode (the flag is not ignored)."""
+    B, hw, lens = 2, (32, 32), [300, 77]
+    C, N = 1152, hw[0] * hw[1]
+    cfg = po.OracleConfig(depth=1, kv_sampling="conv" if sr > 1 else None, kv_scale_factor=sr,
+                          kv_compress_layer=[0] if sr > 1 else [])
+    sd = po.synthetic_state_dict(cfg, seed=7)
+    m = _build(cfg, sd)
+    blk = m.blocks[0]
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, N, C, generator=g)
+    t0 = torch.randn(B, 6 * C, generator=g) * 0.3
+    ycat = (torch.randn(sum(lens), C, generator=g)).to(torch.bfloat16)
+    sdr = _bf16_round(sd)
+    want = po.block_forward(sdr, "blocks.0", x, ycat.float()[None], t0, lens, hw, 16, cfg.sr_ratio(0), cfg.kv_sampling)
+    mod = (sdr["blocks.0.scale_shift_table"][None] + t0.view(B, 6, C)).cuda().contiguous()
+    kv_len = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    kv_off = torch.tensor([sum(lens[:i]) for i in range(B)], dtype=torch.int32, device="cuda")
+    got, launches = {}, {}
+    for flag in (False, True):
+        for mod_ in m.modules():
+            mod_.fp32_attention = flag
+        x32 = x.reshape(B * N, C).cuda().contiguous()
+        n0 = lib.launch_count()
+        with torch.no_grad():
+            got[flag] = blk.run_kernels(x32, ycat.cuda(), kv_len, kv_off, max(lens), mod, B, N, hw, blk._ws, None).view(B, N, C).cpu()
+        torch.cuda.synchronize()
+        launches[flag] = lib.launch_count() - n0
+    e0, e1 = po.rel_err(got[False], want), po.rel_err(got[True], want)
+    u0, u1 = po.rel_err(got[False] - x, want - x), po.rel_err(got[True] - x, want - x)
+    _log(f"block fp32_attention sr={sr}: out rel_err bf16-P {e0:.3e} / hi+lo P {e1:.3e}; update rel_err {u0:.3e} / {u1:.3e}")
+    assert launches[True] == launches[False]
+    assert not torch.equal(got[True], got[False])
+    assert e1 < (1e-3 if sr == 1 else 1.5e-3) and e1 <= e0 * 1.02
 
 
 CASES = ["d2_nomask", "d2_nonsquare", "d2_kvconv", "d2_kvave", "d2_kvuniform", "d2_kvuniform_every", "d2_micro",

@@ -33,6 +33,10 @@ for B, Nq, Nk in ((8, 4096, 4096), (2, 16384, 4096)):
     ms = timeit(lambda: lib.flash_attn(q, kv[:, 0], kv[:, 1], o, B=B, H=H, Nq=Nq, Nk=Nk, kv_rows=B * Nk, q_strides=(C, D),
                                        k_strides=(2 * C, D), v_strides=(2 * C, D)))
     print(f"self  B={B} Nq={Nq} Nk={Nk}: {ms * 1e3:8.1f} us ({4.0 * B * H * Nq * Nk * D / ms / 1e9:6.0f} TFLOP/s)", flush=True)
+    # fp32_attention grade P V (P as bf16 hi + lo, PxaAttnArgs.p_precision = 1): 1.5 x the tensor work, same exp2 work
+    ms = timeit(lambda: lib.flash_attn(q, kv[:, 0], kv[:, 1], o, B=B, H=H, Nq=Nq, Nk=Nk, kv_rows=B * Nk, q_strides=(C, D),
+                                       k_strides=(2 * C, D), v_strides=(2 * C, D), fp32_p=True))
+    print(f"self  B={B} Nq={Nq} Nk={Nk} fp32_p: {ms * 1e3:8.1f} us ({4.0 * B * H * Nq * Nk * D / ms / 1e9:6.0f} model TFLOP/s)", flush=True)
 
 B, Nq = 8, 4096
 for lens in ([300] * 8, [300, 77, 120, 256, 33, 300, 180, 64]):
