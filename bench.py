@@ -655,6 +655,25 @@ def measure_vae(args, ctx: Ctx):
     ms = ctx.timed(step, args.steps)
     launches = lib.launch_count() - n0
     clocks = sampler.stop() if sampler else None
+    # e2e: the call scripts/inference.py:136 makes -- `vae.decode(latent / scaling_factor).sample` of the whole autoencoder (conv_in,
+    # mid block incl. its 16384-token attention, the stack above, conv_norm_out, conv_out) with the latent copied from pinned host
+    # memory and the image read back every step
+    from pixart_sigma_b200.vae import AutoencoderKL
+    with torch.device(dev):
+        full = AutoencoderKL().to(torch.bfloat16)
+    h_z = torch.randn(1, 4, 128, 128).pin_memory()
+    h_img = torch.empty(1, 3, 1024, 1024, dtype=torch.bfloat16).pin_memory()
+
+    def step_e2e(i):
+        z = h_z.to(dev, non_blocking=True)
+        img = full.decode(z / full.config.scaling_factor).sample
+        h_img.copy_(img, non_blocking=True)
+        return img
+
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = ctx.timed(step_e2e, args.steps)
+    del full
     timer = KernelTimer(lib, [("conv", "conv3x3_nhwc"), ("gn", "groupnorm_silu_nhwc"), ("gemm", "gemm")])
     timer.on = True
     ms_roof = ctx.timed(step, 2)
@@ -681,6 +700,10 @@ def measure_vae(args, ctx: Ctx):
                 "config": {"workload": "vae: SDXL-VAE decoder ResBlock + upsample convolutions of one 1024x1024 image per GPU "
                                        "(17 ResnetBlock2D + 3 upsample convs, GroupNorm+SiLU kernels, random weights)",
                            "tflop_per_step_per_gpu": flops / 1e12, "l2": "activations up to 268 MB per layer: larger than L2"},
+                "e2e": {"value": world * args.steps / (ms_e2e / 1000.0), "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
+                        "what": "AutoencoderKL.decode of one 128x128 latent -> 1024x1024 image (whole decoder incl. conv_in, mid-block "
+                                "attention, conv_out), latent from pinned host memory, image read back",
+                        "h2d_bytes_per_step": h_z.numel() * 4, "d2h_bytes_per_step": h_img.numel() * 2},
                 "gpu_launches": launches, "clocks": clocks,
                 "roofline": {"bound": "tensor", "kernel": "pxa::gemm_bf16_kernel<kConv> (implicit-GEMM 3x3 convolution, 4-D TMA)",
                              "achieved": conv_tf, "peak": sus, "unit": "TFLOP/s", "frac": conv_tf / sus if conv_tf else None,
