@@ -715,6 +715,88 @@ def measure_vae(args, ctx: Ctx):
     return line
 
 
+# --------------------------------------------------------------------------------------------- our arm: T5 caption encoder
+def measure_t5(args, ctx: Ctx):
+    """one forward of the T5-v1.1-XXL caption encoder (24 layers, d_model 4096, 4.7 B random-init bf16 parameters:
+    there is no checkpoint offline) over the captions of one c3 batch -- 4 captions x 300 tokens per GPU (diffusion/model/t5.py:107-110;
+    the null caption is a stored embedding).  value = captions/s over all ranks; e2e = token ids / mask from pinned host memory and the
+    (4, 300, 4096) embeddings read back."""
+    from pixart_sigma_b200 import lib
+    from pixart_sigma_b200.t5 import T5EncoderModel, T5_V1_1_XXL
+    dev, rank, world = ctx.dev, ctx.rank, ctx.world
+    cfg, caps, L = T5_V1_1_XXL, 4, 300
+    torch.manual_seed(11)
+    with torch.device(dev):
+        torch.set_default_dtype(torch.bfloat16)
+        try:
+            model = T5EncoderModel()
+        finally:
+            torch.set_default_dtype(torch.float32)
+        for n_, p_ in model.named_parameters():
+            if p_.dim() > 1:
+                torch.nn.init.normal_(p_, std=(p_.shape[1] ** -0.5) if "shared" not in n_ else 1.0)
+    g = torch.Generator().manual_seed(3 + rank)
+    h_ids = torch.randint(0, cfg["vocab_size"], (caps, L), generator=g).pin_memory()
+    lens = torch.randint(8, L + 1, (caps,), generator=g)
+    h_mask = (torch.arange(L)[None] < lens[:, None]).long().pin_memory()
+    d_ids, d_mask = h_ids.to(dev), h_mask.to(dev)
+    h_out = torch.empty(caps, L, cfg["d_model"], dtype=torch.bfloat16).pin_memory()
+
+    def step(i):
+        return model(d_ids, d_mask)["last_hidden_state"]
+
+    def step_e2e(i):
+        out = model(h_ids.to(dev, non_blocking=True), h_mask.to(dev, non_blocking=True))["last_hidden_state"]
+        h_out.copy_(out, non_blocking=True)
+        return out
+
+    warm = max(args.warmup, 3)
+    for i in range(warm):
+        step(i)
+    sampler = ClockSampler(ctx.local) if rank == 0 else None
+    n0 = lib.launch_count()
+    ms = ctx.timed(step, args.steps)
+    launches = lib.launch_count() - n0
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = ctx.timed(step_e2e, args.steps)
+    timer = KernelTimer(lib, [("gemm", "gemm"), ("rms", "rmsnorm")])
+    timer.on = True
+    ms_roof = ctx.timed(step, 2)
+    timer.on = False
+    timer.restore()
+    line = None
+    if rank == 0:
+        sus, burst, hbm, src = measured_peaks()
+        D, F_, inner, nl, M = cfg["d_model"], cfg["d_ff"], cfg["num_heads"] * cfg["d_kv"], cfg["num_layers"], caps * L
+        gemm_flops = nl * 2.0 * M * (4 * D * inner + 3 * D * F_)
+        attn_flops = nl * 4.0 * caps * cfg["num_heads"] * L * L * cfg["d_kv"]
+        wbytes = nl * 2.0 * (4 * D * inner + 3 * D * F_)
+        tt = timer.totals_ms()
+        gemm_ms, gemm_n = tt["gemm"]
+        gemm_tf = gemm_flops * 2 / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else None
+        line = {"metric": "t5-xxl captions/sec", "value": caps * world * args.steps / (ms / 1000.0), "unit": "captions/s",
+                "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "t5: T5-v1.1-XXL encoder forward (24 layers, d_model 4096, 64 heads, d_ff 10240), 4 captions x 300 "
+                                       "tokens per GPU, random-init weights",
+                           "tflop_per_step_per_gpu": (gemm_flops + attn_flops) / 1e12, "weight_gb": wbytes / 1e9,
+                           "l2": "9.4 GB of weights streamed per forward: larger than L2"},
+                "e2e": {"value": caps * world * args.steps / (ms_e2e / 1000.0), "unit": "captions/s", "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": h_ids.numel() * 8 + h_mask.numel() * 8, "d2h_bytes_per_step": h_out.numel() * 2},
+                "gpu_launches": launches, "clocks": clocks,
+                "roofline": {"bound": "tensor", "kernel": "pxa::gemm_bf16_kernel (the 7 Linear layers of each T5 block; 99 % of the FLOPs)",
+                             "achieved": gemm_tf, "peak": sus, "unit": "TFLOP/s", "frac": gemm_tf / sus if gemm_tf else None,
+                             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src})", "launches_timed": gemm_n,
+                             "step_share": gemm_ms / ms_roof, "traffic": None,
+                             "weights_gbs": wbytes * 2 / (gemm_ms / 1000.0) / 1e9 if gemm_ms > 0 else None, "hbm_peak_gbs": hbm,
+                             "rmsnorm_step_share": tt["rms"][0] / ms_roof,
+                             "whole_step_tflops": (gemm_flops + attn_flops) / (ms / args.steps / 1000.0) / 1e12},
+                "cpu_baseline": None}
+    del model
+    torch.cuda.empty_cache()
+    return line
+
+
 _JSON_FD = None
 
 
@@ -728,7 +810,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["vae"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["vae", "t5"])
     ap.add_argument("--no-extras", action="store_true",
                     help="headline workload only (default: the c3 line also carries the c5 training step under `train` and "
                          "the c4 2K forward under `c4`, measured at the same N)")
@@ -757,8 +839,9 @@ def main():
     _JSON_FD = os.dup(1)
     os.dup2(2, 1)
     if args.impl == "reference":
-        if args.workload == "vae":
-            _emit({"impl": "reference", "unavailable": "the VAE decoder (diffusers AutoencoderKL) is not part of the reference tree"})
+        if args.workload in ("vae", "t5"):
+            _emit({"impl": "reference", "unavailable": "the VAE (diffusers AutoencoderKL) and the T5 encoder (transformers) are third-party "
+                                                        "dependencies of the reference, not part of its tree"})
             return
         run_reference_arm(args, WORKLOADS[args.workload])
         return
@@ -768,6 +851,8 @@ def main():
     train_mode = "graph" if args.train_mode == "auto" else args.train_mode
     if args.workload == "vae":
         line = measure_vae(args, ctx)
+    elif args.workload == "t5":
+        line = measure_t5(args, ctx)
     elif args.workload == "c5":
         line = measure_train(args, ctx, train_mode, not args.no_checkpoint, ctx.world == 1 and not args.no_cpu_baseline)
     else:

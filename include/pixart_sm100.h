@@ -192,6 +192,12 @@ int pxa_ln_prepare(const PxaLnPrepareArgs* args, void* stream);
 int pxa_layernorm_affine_bf16(void* x, const void* weight, const void* bias, int32_t M, int32_t C, int64_t ld, float eps,
                               void* stream);
 
+/* RMS norm of the T5-v1.1-XXL caption encoder (transformers `T5LayerNorm`, eps 1e-6; reference call site diffusion/model/t5.py:107-110):
+ * out[r, c] = bf16(x[r, c] * rsqrt(mean_c(x[r, :]^2) + eps) * weight[c]) on M rows of the fp32 residual stream (row strides ldx /
+ * ldo in elements, C a multiple of 4).  HBM-bound: 4 C + 2 C bytes per row. */
+int pxa_rmsnorm_bf16(const float* x, const void* weight, void* out, int32_t M, int32_t C, int64_t ldx, int64_t ldo, float eps,
+                     void* stream);
+
 /* GroupNorm (+ SiLU) on an NHWC bf16 image: the prologue of each 3x3 convolution of the SDXL-VAE decoder ResnetBlock2D
  * (diffusers GroupNorm(32, eps 1e-6) -> SiLU; reference call site scripts/inference.py:136).  out[b,p,c] =
  * silu((x[b,p,c] - mean[b,g]) * rstd[b,g] * gamma[c] + beta[c]), g = c / (C / groups), statistics over the HW pixels and the

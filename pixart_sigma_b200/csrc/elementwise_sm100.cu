@@ -409,6 +409,54 @@ extern "C" int pxa_layernorm_affine_bf16(void* x, const void* weight, const void
 
 namespace pxa {
 
+// ------------------------------------------------------------------------------------------------- RMS norm (T5 encoder)
+// T5LayerNorm of the T5-v1.1-XXL caption encoder (transformers `T5LayerNorm`: no mean subtraction, no bias, eps 1e-6; reference
+// call site diffusion/model/t5.py:107-110 `self.model(input_ids, attention_mask)`): out[r, :] = bf16(x[r, :] * rsqrt(mean(x[r, :]^2)
+// + eps) * w).  x is the fp32 residual stream.  Warp per row, two passes over the 16 KB row (the second one hits L1): HBM-bound,
+// algorithmic bytes per row 4 C (read) + 2 C (write).
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                                      __nv_bfloat16* __restrict__ out, int M, int C, long long ldx, long long ldo,
+                                                      float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
+  const int nv = C >> 2;
+  float ss = 0.f;
+  for (int i = lane; i < nv; i += 32) {
+    const float4 v = xr[i];
+    ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
+  __nv_bfloat16* orow = out + (size_t)row * ldo;
+  for (int i = lane; i < nv; i += 32) {
+    const float4 v = xr[i];
+    const uint2 wu = __ldg(reinterpret_cast<const uint2*>(w + 4 * i));
+    *reinterpret_cast<uint2*>(orow + 4 * i) = make_uint2(pack_bf16x2(v.x * rstd * bf16_lo(wu.x), v.y * rstd * bf16_hi(wu.x)),
+                                                          pack_bf16x2(v.z * rstd * bf16_lo(wu.y), v.w * rstd * bf16_hi(wu.y)));
+  }
+}
+
+}  // namespace pxa
+
+extern "C" int pxa_rmsnorm_bf16(const float* x, const void* weight, void* out, int32_t M, int32_t C, int64_t ldx, int64_t ldo,
+                                float eps, void* stream) {
+  using namespace pxa;
+  if (!x || !weight || !out) return fail(PXA_ERR_ARG, "null pointer");
+  if (M <= 0 || C <= 0 || (C & 3)) return fail(PXA_ERR_ARG, "bad M / C (C must be a multiple of 4; got M=%d C=%d)", M, C);
+  if ((ldx & 3) || (ldo & 3) || ((reinterpret_cast<uintptr_t>(x) & 15) | (reinterpret_cast<uintptr_t>(weight) & 7) |
+                                  (reinterpret_cast<uintptr_t>(out) & 7)))
+    return fail(PXA_ERR_ALIGN, "x must be 16-byte, weight / out 8-byte aligned; ldx, ldo multiples of 4");
+  PXA_REQUIRE_SM100();
+  rmsnorm_kernel<<<(M + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<const __nv_bfloat16*>(weight), reinterpret_cast<__nv_bfloat16*>(out), M, C, ldx, ldo, eps);
+  launch_counter()++;
+  PXA_CHECK_CUDA(cudaGetLastError());
+  return PXA_OK;
+}
+
+namespace pxa {
+
 // ------------------------------------------------------------------------------------------------- GroupNorm (+ SiLU), NHWC
 // SDXL-VAE decoder ResnetBlock2D prologue (diffusers GroupNorm(32, eps 1e-6) -> SiLU in front of each 3x3 convolution;
 // reference call site scripts/inference.py:136).  Two passes over an NHWC bf16 image: (1) per (sample, group) sum / sum of

@@ -132,7 +132,8 @@ EXPORTS = ("pxa_transpose_bf16", "pxa_gelu_tanh_bf16", "pxa_gate_residual_fwd", 
            "pxa_ln_modulate_bwd", "pxa_colsum_bf16", "pxa_attn_delta_d72", "pxa_flash_attn_d72_bwd_bf16", "pxa_kv_compress_conv2_ln_bwd",
            "pxa_version", "pxa_last_error", "pxa_launch_count", "pxa_gemm_bf16", "pxa_ln_modulate",
            "pxa_flash_attn_d72_bf16", "pxa_kv_compress_conv2_ln", "pxa_conv3x3_nhwc_bf16", "pxa_dpm_solver_pp_step",
-           "pxa_ln_prepare", "pxa_layernorm_affine_bf16", "pxa_groupnorm_silu_nhwc_bf16", "pxa_adamw_flat", "pxa_mlp_fused_bf16")
+           "pxa_ln_prepare", "pxa_layernorm_affine_bf16", "pxa_groupnorm_silu_nhwc_bf16", "pxa_adamw_flat", "pxa_mlp_fused_bf16",
+           "pxa_rmsnorm_bf16")
 
 _lib = None
 
@@ -164,6 +165,9 @@ def load() -> C.CDLL:
         lib.pxa_layernorm_affine_bf16.restype = C.c_int
         lib.pxa_layernorm_affine_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_float,
                                                   C.c_void_p]
+        lib.pxa_rmsnorm_bf16.restype = C.c_int
+        lib.pxa_rmsnorm_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_float,
+                                         C.c_void_p]
         lib.pxa_groupnorm_silu_nhwc_bf16.restype = C.c_int
         lib.pxa_groupnorm_silu_nhwc_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                                      C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_void_p]
@@ -288,6 +292,16 @@ def layernorm_affine_(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
     _check(load().pxa_layernorm_affine_bf16(_ptr(x), _ptr(weight), _ptr(bias), x.shape[0], x.shape[1], x.stride(0), eps,
                                             _stream()), "pxa_layernorm_affine_bf16")
     return x
+
+
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """T5LayerNorm: out (M, C) bf16 = x * rsqrt(mean(x^2) + eps) * weight on the rows of the fp32 stream x (M, C)."""
+    assert x.is_cuda and x.dtype == torch.float32 and out.dtype == weight.dtype == torch.bfloat16
+    assert x.dim() == 2 and out.shape == x.shape and x.stride(1) == 1 and out.stride(1) == 1
+    assert weight.is_contiguous() and weight.numel() == x.shape[1]
+    _check(load().pxa_rmsnorm_bf16(_ptr(x), _ptr(weight), _ptr(out), x.shape[0], x.shape[1], x.stride(0), out.stride(0), eps,
+                                   _stream()), "pxa_rmsnorm_bf16")
+    return out
 
 
 def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, B: int, H: int, Nq: int,

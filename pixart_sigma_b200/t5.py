@@ -1,0 +1,196 @@
+"""T5-v1.1-XXL caption encoder on the sm_100a kernels.
+
+The reference encodes prompts with transformers' `T5EncoderModel` (diffusion/model/t5.py:12,107-110 `self.model(input_ids=...,
+attention_mask=...)['last_hidden_state']`; scripts/inference.py:80, train_scripts/train.py:166): 24 layers, d_model 4096, 64 heads
+of 64, gated-GELU feed-forward of 10240, 4.7 B parameters, 300 tokens per caption.  This module keeps that call and the
+checkpoint's state-dict keys (`shared.weight`, `encoder.block.i.layer.0.SelfAttention.{q,k,v,o}.weight`,
+`encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight`, `encoder.block.i.layer.{0,1}.layer_norm.weight`,
+`encoder.block.i.layer.1.DenseReluDense.{wi_0,wi_1,wo}.weight`, `encoder.final_layer_norm.weight`) and runs
+
+  * the seven Linear layers of a block -- 99 % of the FLOPs (2 x 4.7 G per token) -- on `pxa_gemm_bf16` (tcgen05): q / k / v, the
+    attention output projection accumulated IN PLACE into the fp32 residual stream (TMA reduce-add epilogue), wi_0 with the
+    GELU(tanh) epilogue (`gelu_new`), wi_1, and wo again in place into the stream;
+  * both T5LayerNorms (RMS norm, no mean, no bias) on `pxa_rmsnorm_bf16`, reading the fp32 stream;
+  * what stays PyTorch: the embedding gather, the 300 x 300 x 64 attention core per head (fp32 logits + relative-position bias +
+    key mask, softmax, P V: 1.1 % of the FLOPs; T5 adds a learned [heads, 300, 300] bias to the logits and uses no 1/sqrt(d)
+    scale, so the head_dim-72 flash kernel of the DiT does not apply) and the gate product gelu(wi_0 x) * (wi_1 x).
+
+Deliberate deviation, towards the fp32 model: the residual stream between layers is fp32 (transformers keeps it in the checkpoint
+dtype; the reference loads T5 in fp16 / bf16).  At 300 tokens per caption one forward is bound by streaming the 9.4 GB of bf16
+weights once (1.45 ms at the measured 6.5 TB/s) against 2.8 TFLOP of GEMMs (2.1 ms at the sustained bf16 peak)."""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import lib
+
+T5_V1_1_XXL = dict(vocab_size=32128, d_model=4096, d_kv=64, d_ff=10240, num_layers=24, num_heads=64,
+                   relative_attention_num_buckets=32, relative_attention_max_distance=128, layer_norm_epsilon=1e-6)
+
+
+class _RMSNorm(nn.Module):          # transformers T5LayerNorm
+    def __init__(self, d: int, eps: float):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(d))
+        self.variance_epsilon = eps
+
+
+class _SelfAttention(nn.Module):    # transformers T5Attention (encoder: bidirectional, no cache)
+    def __init__(self, cfg, has_bias: bool):
+        super().__init__()
+        inner = cfg["num_heads"] * cfg["d_kv"]
+        self.q, self.k, self.v = (nn.Linear(cfg["d_model"], inner, bias=False) for _ in range(3))
+        self.o = nn.Linear(inner, cfg["d_model"], bias=False)
+        if has_bias:
+            self.relative_attention_bias = nn.Embedding(cfg["relative_attention_num_buckets"], cfg["num_heads"])
+
+
+class _LayerSelfAttention(nn.Module):
+    def __init__(self, cfg, has_bias: bool):
+        super().__init__()
+        self.SelfAttention = _SelfAttention(cfg, has_bias)
+        self.layer_norm = _RMSNorm(cfg["d_model"], cfg["layer_norm_epsilon"])
+
+
+class _DenseGated(nn.Module):       # transformers T5DenseGatedActDense, act = gelu_new
+    def __init__(self, cfg):
+        super().__init__()
+        self.wi_0 = nn.Linear(cfg["d_model"], cfg["d_ff"], bias=False)
+        self.wi_1 = nn.Linear(cfg["d_model"], cfg["d_ff"], bias=False)
+        self.wo = nn.Linear(cfg["d_ff"], cfg["d_model"], bias=False)
+
+
+class _LayerFF(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.DenseReluDense = _DenseGated(cfg)
+        self.layer_norm = _RMSNorm(cfg["d_model"], cfg["layer_norm_epsilon"])
+
+
+class _Block(nn.Module):
+    def __init__(self, cfg, has_bias: bool):
+        super().__init__()
+        self.layer = nn.ModuleList([_LayerSelfAttention(cfg, has_bias), _LayerFF(cfg)])
+
+
+class _Stack(nn.Module):
+    def __init__(self, cfg, embed: nn.Embedding):
+        super().__init__()
+        self.embed_tokens = embed
+        self.block = nn.ModuleList([_Block(cfg, i == 0) for i in range(cfg["num_layers"])])
+        self.final_layer_norm = _RMSNorm(cfg["d_model"], cfg["layer_norm_epsilon"])
+
+
+class EncoderOutput(dict):
+    """`model(...)['last_hidden_state']` (diffusion/model/t5.py:110) and `.last_hidden_state` both work."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __getitem__(self, k):
+        return list(self.values())[k] if isinstance(k, int) else super().__getitem__(k)
+
+
+def relative_position_bucket(rel: torch.Tensor, num_buckets: int = 32, max_distance: int = 128) -> torch.Tensor:
+    """Bidirectional T5 bucketing of (key position - query position): half of the buckets per sign; within a sign the first half
+    are exact offsets, the rest logarithmic up to max_distance (Mesh-TensorFlow `_relative_position_bucket`, as in transformers)."""
+    nb = num_buckets // 2
+    out = (rel > 0).to(torch.long) * nb
+    n = rel.abs()
+    max_exact = nb // 2
+    large = max_exact + (torch.log(n.float() / max_exact) / math.log(max_distance / max_exact) * (nb - max_exact)).to(torch.long)
+    large = torch.minimum(large, torch.full_like(large, nb - 1))
+    return out + torch.where(n < max_exact, n, large)
+
+
+def _res_bn(n: int) -> int:
+    return 256 if n % 256 == 0 else (192 if n % 192 == 0 else 128)
+
+
+def _need_kernels(w: torch.Tensor) -> None:
+    if not w.is_cuda or w.dtype != torch.bfloat16:
+        raise RuntimeError("T5EncoderModel runs on the sm_100a kernels only: move it to a B200 and cast it to bfloat16 "
+                           "(model.to(torch.bfloat16); fp16 checkpoints: cast at load)")
+
+
+class T5EncoderModel(nn.Module):
+    def __init__(self, config: Optional[dict] = None):
+        super().__init__()
+        cfg = dict(T5_V1_1_XXL)
+        cfg.update(config or {})
+        self.cfg = cfg
+        self.shared = nn.Embedding(cfg["vocab_size"], cfg["d_model"])
+        self.encoder = _Stack(cfg, self.shared)                 # `encoder.embed_tokens.weight` is tied to `shared.weight`
+        self._ws = {}
+
+    @property
+    def dtype(self):
+        return self.shared.weight.dtype
+
+    @property
+    def device(self):
+        return self.shared.weight.device
+
+    def _buf(self, name, shape, dtype):
+        t = self._ws.get(name)
+        if t is None or t.shape != torch.Size(shape) or t.dtype != dtype or t.device != self.device:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._ws[name] = t
+        return t
+
+    def position_bias(self, L: int) -> torch.Tensor:
+        """(H, L, L) fp32: relative_attention_bias[bucket(j - i), h] -- layer 0 owns the table, every layer uses it."""
+        cfg = self.cfg
+        pos = torch.arange(L, device=self.device)
+        bucket = relative_position_bucket(pos[None, :] - pos[:, None], cfg["relative_attention_num_buckets"],
+                                          cfg["relative_attention_max_distance"])
+        table = self.encoder.block[0].layer[0].SelfAttention.relative_attention_bias.weight
+        return table.float()[bucket].permute(2, 0, 1).contiguous()
+
+    @torch.no_grad()
+    def forward(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None, **kwargs) -> EncoderOutput:
+        _need_kernels(self.encoder.block[0].layer[0].SelfAttention.q.weight)
+        cfg = self.cfg
+        B, L = input_ids.shape
+        D, H, dk, F_ = cfg["d_model"], cfg["num_heads"], cfg["d_kv"], cfg["d_ff"]
+        inner, M, bf = H * dk, B * L, torch.bfloat16
+        input_ids = input_ids.to(self.device)
+        x32 = self._buf("x32", (M, D), torch.float32)
+        x32.copy_(self.shared.weight[input_ids.reshape(-1)])
+        bias = self.position_bias(L)[None]                                            # (1, H, L, L)
+        if attention_mask is not None:                                                # additive key mask, as transformers' extended mask
+            keep = attention_mask.to(self.device).to(torch.float32).view(B, 1, 1, L)
+            bias = bias + (1.0 - keep) * torch.finfo(torch.float32).min
+        xn, q, k, v = (self._buf(n, (M, s), bf) for n, s in (("xn", D), ("q", inner), ("k", inner), ("v", inner)))
+        ao, h0, h1 = self._buf("ao", (M, inner), bf), self._buf("h0", (M, F_), bf), self._buf("h1", (M, F_), bf)
+        for blk in self.encoder.block:
+            at, ff = blk.layer[0], blk.layer[1]
+            sa, dense = at.SelfAttention, ff.DenseReluDense
+            # (1) x += o( softmax(q k^T + bias) v ),  q / k / v = Linear(rmsnorm(x))        (no 1/sqrt(d): T5 folds it into the init)
+            lib.rmsnorm(x32, at.layer_norm.weight, xn, eps=at.layer_norm.variance_epsilon)
+            lib.gemm(xn, sa.q.weight, None, q)
+            lib.gemm(xn, sa.k.weight, None, k)
+            lib.gemm(xn, sa.v.weight, None, v)
+            q4, k4, v4 = (t.view(B, L, H, dk).transpose(1, 2).float() for t in (q, k, v))
+            p = torch.softmax(q4 @ k4.transpose(-1, -2) + bias, dim=-1)
+            ao.view(B, L, H, dk).copy_((p @ v4).transpose(1, 2))
+            # block_n = 256 divides d_model 4096 (the auto choice for the in-place update, 192-column tiles on the CTA pair, is tuned
+            # for the DiT's N = 1152 and would leave a partial last column tile here)
+            lib.gemm(ao, sa.o.weight, None, x32, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x32, block_n=_res_bn(D))
+            # (2) x += wo( gelu_new(wi_0 n) * wi_1 n ),  n = rmsnorm(x)
+            lib.rmsnorm(x32, ff.layer_norm.weight, xn, eps=ff.layer_norm.variance_epsilon)
+            lib.gemm(xn, dense.wi_0.weight, None, h0, epilogue=lib.EPI_BIAS_GELU)
+            lib.gemm(xn, dense.wi_1.weight, None, h1)
+            h0.mul_(h1)
+            lib.gemm(h0, dense.wo.weight, None, x32, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x32, block_n=_res_bn(D))
+        fin = self.encoder.final_layer_norm
+        out = torch.empty(M, D, dtype=bf, device=self.device)
+        lib.rmsnorm(x32, fin.weight, out, eps=fin.variance_epsilon)
+        return EncoderOutput(last_hidden_state=out.view(B, L, D))

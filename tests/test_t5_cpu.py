@@ -1,0 +1,94 @@
+"""CPU tests of the T5 caption encoder (pixart_sigma_b200/t5.py): checkpoint key layout and bucketing against the installed
+`transformers` (the reference's own dependency, diffusion/model/t5.py:10), and the host-side glue -- embedding, relative-position
+bias, key mask, layer order, in-place residual updates, final norm -- against transformers' T5EncoderModel in fp32 with the two
+kernel wrappers replaced by torch stand-ins of their contracts.  The kernels run in tests/test_t5_gpu.py."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import pixart_oracle as po
+from pixart_sigma_b200 import lib, t5
+
+transformers = pytest.importorskip("transformers")
+
+SMALL = dict(vocab_size=384, d_model=256, d_kv=64, d_ff=512, num_layers=3, num_heads=4)
+
+
+def hf_model(cfg, seed=0):
+    torch.manual_seed(seed)
+    hc = transformers.T5Config(feed_forward_proj="gated-gelu", dropout_rate=0.0, **cfg)
+    m = transformers.T5EncoderModel(hc).eval()
+    with torch.no_grad():                                 # T5 inits layer norms to 1 and the bias table small: make them matter
+        for n, p in m.named_parameters():
+            if "layer_norm" in n:
+                p.add_(0.2 * torch.randn_like(p))
+            if "relative_attention_bias" in n:
+                p.mul_(8.0)
+    return m
+
+
+def _standins(monkeypatch):
+    def gemm(a, w, bias, out, *, epilogue=lib.EPI_BIAS, residual=None, block_n=0, **kw):
+        assert not kw and bias is None and block_n in (0, 128, 192, 256)
+        y = F.linear(a.float(), w.float())
+        if epilogue == lib.EPI_BIAS_GELU:
+            y = F.gelu(y, approximate="tanh")
+        elif epilogue == lib.EPI_BIAS_RESIDUAL:
+            assert residual is out and out.dtype == torch.float32
+            y = residual + y
+        else:
+            assert epilogue == lib.EPI_BIAS
+        out.copy_(y)
+        return out
+
+    def rmsnorm(x, weight, out, eps=1e-6):
+        out.copy_(x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * weight.float())
+        return out
+
+    monkeypatch.setattr(lib, "gemm", gemm)
+    monkeypatch.setattr(lib, "rmsnorm", rmsnorm)
+    monkeypatch.setattr(t5, "_need_kernels", lambda w: None)          # the product refuses CPU tensors (last test)
+
+
+def test_state_dict_keys_and_buckets_equal_transformers():
+    hf = hf_model(SMALL)
+    m = t5.T5EncoderModel(SMALL)
+    assert set(m.state_dict()) == set(hf.state_dict())
+    assert all(m.state_dict()[k].shape == v.shape for k, v in hf.state_dict().items())
+    missing, unexpected = m.load_state_dict(hf.state_dict())
+    assert not missing and not unexpected
+    assert m.encoder.embed_tokens.weight is m.shared.weight
+    from transformers.models.t5.modeling_t5 import T5Attention
+    pos = torch.arange(300)
+    rel = pos[None] - pos[:, None]
+    assert torch.equal(t5.relative_position_bucket(rel), T5Attention._relative_position_bucket(rel, True, 32, 128))
+    assert t5.T5_V1_1_XXL["num_layers"] == 24 and t5.T5_V1_1_XXL["d_model"] == 4096 and t5.T5_V1_1_XXL["d_ff"] == 10240
+
+
+def test_forward_glue_equals_transformers_fp32(monkeypatch):
+    _standins(monkeypatch)
+    hf = hf_model(SMALL)
+    m = t5.T5EncoderModel(SMALL)
+    m.load_state_dict(hf.state_dict())
+    m = m.to(torch.bfloat16)
+    hf.load_state_dict({k: v.float() for k, v in m.state_dict().items()})          # the same bf16-valued weights on both sides
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(0, SMALL["vocab_size"], (3, 40), generator=g)
+    mask = (torch.arange(40)[None] < torch.tensor([40, 7, 23])[:, None]).long()
+    got = m(input_ids=ids, attention_mask=mask)["last_hidden_state"]
+    with torch.no_grad():
+        want = hf(input_ids=ids, attention_mask=mask)["last_hidden_state"]
+    assert got.shape == want.shape == (3, 40, 256) and got.dtype == torch.bfloat16
+    assert po.rel_err(got.float(), want) < 1e-2                                    # bf16 activations between the stages
+    valid = mask.bool()
+    assert po.rel_err(got.float()[valid], want[valid]) < 1e-2
+    got2 = m(ids, None).last_hidden_state                                           # no mask, positional call, attribute access
+    with torch.no_grad():
+        want2 = hf(input_ids=ids).last_hidden_state
+    assert po.rel_err(got2.float(), want2) < 1e-2
+
+
+def test_product_refuses_to_run_without_the_kernels():
+    m = t5.T5EncoderModel(SMALL)
+    with pytest.raises(RuntimeError, match="sm_100a kernels only"):
+        m(torch.zeros(1, 8, dtype=torch.long))
