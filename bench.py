@@ -759,7 +759,7 @@ def measure_t5(args, ctx: Ctx):
     launches = lib.launch_count() - n0
     clocks = sampler.stop() if sampler else None
     ms_e2e = ctx.timed(step_e2e, args.steps)
-    timer = KernelTimer(lib, [("gemm", "gemm"), ("rms", "rmsnorm")])
+    timer = KernelTimer(lib, [("gemm", "gemm"), ("rms", "rmsnorm"), ("attn", "t5_attn")])
     timer.on = True
     ms_roof = ctx.timed(step, 2)
     timer.on = False
@@ -774,6 +774,7 @@ def measure_t5(args, ctx: Ctx):
         tt = timer.totals_ms()
         gemm_ms, gemm_n = tt["gemm"]
         gemm_tf = gemm_flops * 2 / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else None
+        attn_ms = tt["attn"][0]
         line = {"metric": "t5-xxl captions/sec", "value": caps * world * args.steps / (ms / 1000.0), "unit": "captions/s",
                 "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -790,6 +791,8 @@ def measure_t5(args, ctx: Ctx):
                              "step_share": gemm_ms / ms_roof, "traffic": None,
                              "weights_gbs": wbytes * 2 / (gemm_ms / 1000.0) / 1e9 if gemm_ms > 0 else None, "hbm_peak_gbs": hbm,
                              "rmsnorm_step_share": tt["rms"][0] / ms_roof,
+                             "attention": {"impl": model.attn_impl, "kernel": "pxa::t5_attn_d64_kernel", "step_share": attn_ms / ms_roof,
+                                           "achieved": attn_flops * 2 / (attn_ms / 1000.0) / 1e12 if attn_ms > 0 else None},
                              "whole_step_tflops": (gemm_flops + attn_flops) / (ms / args.steps / 1000.0) / 1e12},
                 "cpu_baseline": None}
     del model

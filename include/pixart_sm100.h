@@ -198,6 +198,23 @@ int pxa_layernorm_affine_bf16(void* x, const void* weight, const void* bias, int
 int pxa_rmsnorm_bf16(const float* x, const void* weight, void* out, int32_t M, int32_t C, int64_t ldx, int64_t ldo, float eps,
                      void* stream);
 
+/* Self-attention of the T5-v1.1-XXL caption encoder (transformers `T5Attention.forward`; reference call site
+ * diffusion/model/t5.py:107-110): out[b, i, h, :] = softmax_j(q_i . k_j * scale + bias[h, i, j] + key_bias[b, j]) v_j for head_dim 64
+ * and L <= 384 tokens per sample (T5 uses scale = 1 and a learned relative-position bias; key_bias carries the additive padding mask:
+ * 0 for real tokens, a large negative number for padding).  q / k / v: bf16, element (b, i, h, d) at x[(b*L + i)*x_sn + h*x_sh + d]
+ * (strided views of a fused qkv GEMM output are fine); out: bf16 [(b*L + i)*ldo + h*64 + d].  Logits, bias add, softmax and the
+ * accumulation are fp32; P enters P V as bf16. */
+typedef struct PxaT5AttnArgs {
+  const void* q; const void* k; const void* v;
+  void* out;
+  const float* bias;      /* fp32 [H, L, L]                */
+  const float* key_bias;  /* fp32 [B, L] or NULL           */
+  int64_t q_sn, q_sh, k_sn, k_sh, v_sn, v_sh, ldo;
+  int32_t B, H, L;
+  float scale;
+} PxaT5AttnArgs;
+int pxa_t5_attn_d64_bf16(const PxaT5AttnArgs* args, void* stream);
+
 /* GroupNorm (+ SiLU) on an NHWC bf16 image: the prologue of each 3x3 convolution of the SDXL-VAE decoder ResnetBlock2D
  * (diffusers GroupNorm(32, eps 1e-6) -> SiLU; reference call site scripts/inference.py:136).  out[b,p,c] =
  * silu((x[b,p,c] - mean[b,g]) * rstd[b,g] * gamma[c] + beta[c]), g = c / (C / groups), statistics over the HW pixels and the

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpixart_sm100.so")
-SOURCES = ["api.cu", "gemm_sm100.cu", "gemm2_sm100.cu", "mlp_sm100.cu", "elementwise_sm100.cu", "attn_sm100.cu", "attn3_sm100.cu", "attn_bwd_sm100.cu", "backward_sm100.cu"]
+SOURCES = ["api.cu", "gemm_sm100.cu", "gemm2_sm100.cu", "mlp_sm100.cu", "elementwise_sm100.cu", "attn_sm100.cu", "attn3_sm100.cu", "attn_bwd_sm100.cu", "backward_sm100.cu", "t5_attn_sm100.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

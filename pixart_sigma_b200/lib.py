@@ -78,6 +78,13 @@ class AttnArgs(C.Structure):
                 ("reverse_batch", C.c_int32), ("variant", C.c_int32), ("p_precision", C.c_int32), ("reserved0", C.c_int32)]
 
 
+class T5AttnArgs(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p), ("bias", C.c_void_p),
+                ("key_bias", C.c_void_p), ("q_sn", C.c_int64), ("q_sh", C.c_int64), ("k_sn", C.c_int64), ("k_sh", C.c_int64),
+                ("v_sn", C.c_int64), ("v_sh", C.c_int64), ("ldo", C.c_int64), ("B", C.c_int32), ("H", C.c_int32), ("L", C.c_int32),
+                ("scale", C.c_float)]
+
+
 class KvCompressArgs(C.Structure):
     _fields_ = [("k_in", C.c_void_p), ("v_in", C.c_void_p), ("k_out", C.c_void_p), ("v_out", C.c_void_p),
                 ("conv_w", C.c_void_p), ("conv_b", C.c_void_p), ("ln_w", C.c_void_p), ("ln_b", C.c_void_p),
@@ -133,7 +140,7 @@ EXPORTS = ("pxa_transpose_bf16", "pxa_gelu_tanh_bf16", "pxa_gate_residual_fwd", 
            "pxa_version", "pxa_last_error", "pxa_launch_count", "pxa_gemm_bf16", "pxa_ln_modulate",
            "pxa_flash_attn_d72_bf16", "pxa_kv_compress_conv2_ln", "pxa_conv3x3_nhwc_bf16", "pxa_dpm_solver_pp_step",
            "pxa_ln_prepare", "pxa_layernorm_affine_bf16", "pxa_groupnorm_silu_nhwc_bf16", "pxa_adamw_flat", "pxa_mlp_fused_bf16",
-           "pxa_rmsnorm_bf16")
+           "pxa_rmsnorm_bf16", "pxa_t5_attn_d64_bf16")
 
 _lib = None
 
@@ -152,7 +159,7 @@ def load() -> C.CDLL:
                              ("pxa_flash_attn_d72_bf16", AttnArgs), ("pxa_kv_compress_conv2_ln", KvCompressArgs),
                              ("pxa_conv3x3_nhwc_bf16", Conv3x3Args), ("pxa_dpm_solver_pp_step", DpmStepArgs),
                              ("pxa_ln_prepare", LnPrepareArgs), ("pxa_adamw_flat", AdamWArgs),
-                             ("pxa_mlp_fused_bf16", MlpArgs)):
+                             ("pxa_mlp_fused_bf16", MlpArgs), ("pxa_t5_attn_d64_bf16", T5AttnArgs)):
             fn = getattr(lib, name)
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(struct), C.c_void_p]
@@ -301,6 +308,25 @@ def rmsnorm(x: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, eps: float
     assert weight.is_contiguous() and weight.numel() == x.shape[1]
     _check(load().pxa_rmsnorm_bf16(_ptr(x), _ptr(weight), _ptr(out), x.shape[0], x.shape[1], x.stride(0), out.stride(0), eps,
                                    _stream()), "pxa_rmsnorm_bf16")
+    return out
+
+
+T5_ATTN_MAX_KEYS = 384
+
+
+def t5_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, bias: torch.Tensor,
+            key_bias: Optional[torch.Tensor] = None, *, B: int, H: int, L: int, scale: float = 1.0) -> torch.Tensor:
+    """T5 self-attention, head_dim 64, L <= 384: out (B*L, H*64) = softmax(q k^T * scale + bias[h] + key_bias[b]) v.
+    q / k / v: bf16 (B*L, H*64) views with unit column stride (e.g. column slices of a fused qkv GEMM output);
+    bias fp32 (H, L, L); key_bias fp32 (B, L) or None."""
+    for t in (q, k, v, out):
+        assert t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1 and t.shape == (B * L, H * 64)
+    assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.shape == (H, L, L)
+    assert key_bias is None or (key_bias.dtype == torch.float32 and key_bias.is_contiguous() and key_bias.shape == (B, L))
+    args = T5AttnArgs(q=_ptr(q), k=_ptr(k), v=_ptr(v), out=_ptr(out), bias=_ptr(bias), key_bias=_ptr(key_bias),
+                      q_sn=q.stride(0), q_sh=64, k_sn=k.stride(0), k_sh=64, v_sn=v.stride(0), v_sh=64, ldo=out.stride(0),
+                      B=B, H=H, L=L, scale=scale)
+    _check(load().pxa_t5_attn_d64_bf16(C.byref(args), _stream()), "pxa_t5_attn_d64_bf16")
     return out
 
 

@@ -11,9 +11,10 @@ checkpoint's state-dict keys (`shared.weight`, `encoder.block.i.layer.0.SelfAtte
     attention output projection accumulated IN PLACE into the fp32 residual stream (TMA reduce-add epilogue), wi_0 with the
     GELU(tanh) epilogue (`gelu_new`), wi_1, and wo again in place into the stream;
   * both T5LayerNorms (RMS norm, no mean, no bias) on `pxa_rmsnorm_bf16`, reading the fp32 stream;
-  * what stays PyTorch: the embedding gather, the 300 x 300 x 64 attention core per head (fp32 logits + relative-position bias +
-    key mask, softmax, P V: 1.1 % of the FLOPs; T5 adds a learned [heads, 300, 300] bias to the logits and uses no 1/sqrt(d)
-    scale, so the head_dim-72 flash kernel of the DiT does not apply) and the gate product gelu(wi_0 x) * (wi_1 x).
+  * the attention core on `pxa_t5_attn_d64_bf16` (tcgen05; T5 adds a learned [heads, 300, 300] relative-position bias and the key
+    mask to UNSCALED logits at head_dim 64, so the DiT's head_dim-72 flash kernel does not apply; with <= 384 keys the whole logit
+    row sits in TMEM: no key loop, no online softmax), q | k | v coming from ONE GEMM against row-stacked weights;
+  * what stays PyTorch: the embedding gather, the bias table look-up (once per forward) and the gate product gelu(wi_0 x) * (wi_1 x).
 
 Deliberate deviation, towards the fp32 model: the residual stream between layers is fp32 (transformers keeps it in the checkpoint
 dtype; the reference loads T5 in fp16 / bf16).  At 300 tokens per caption one forward is bound by streaming the 9.4 GB of bf16
@@ -21,6 +22,7 @@ weights once (1.45 ms at the measured 6.5 TB/s) against 2.8 TFLOP of GEMMs (2.1 
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -129,6 +131,9 @@ class T5EncoderModel(nn.Module):
         self.shared = nn.Embedding(cfg["vocab_size"], cfg["d_model"])
         self.encoder = _Stack(cfg, self.shared)                 # `encoder.embed_tokens.weight` is tied to `shared.weight`
         self._ws = {}
+        self._qkv_w = {}
+        # "torch": the attention core through PyTorch (fp32 matmuls); env PXA_T5_ATTN for A/B runs of bench.py
+        self.attn_impl = os.environ.get("PXA_T5_ATTN", "kernel")
 
     @property
     def dtype(self):
@@ -144,6 +149,17 @@ class T5EncoderModel(nn.Module):
             t = torch.empty(shape, dtype=dtype, device=self.device)
             self._ws[name] = t
         return t
+
+    def _stacked_qkv(self, li: int, sa) -> torch.Tensor:
+        """[q; k; v] weights of block li row-stacked (3 * inner, d_model) for one GEMM: a derived bf16 copy (2.4 GB for the XXL model,
+        next to 9.4 GB of weights), rebuilt when a parameter's version or storage changes."""
+        ps = (sa.q.weight, sa.k.weight, sa.v.weight)
+        key = tuple((p._version, p.data_ptr()) for p in ps)
+        hit = self._qkv_w.get(li)
+        if hit is None or hit[0] != key:
+            hit = (key, torch.cat([p.detach() for p in ps], 0).contiguous())
+            self._qkv_w[li] = hit
+        return hit[1]
 
     def position_bias(self, L: int) -> torch.Tensor:
         """(H, L, L) fp32: relative_attention_bias[bucket(j - i), h] -- layer 0 owns the table, every layer uses it."""
@@ -164,23 +180,33 @@ class T5EncoderModel(nn.Module):
         input_ids = input_ids.to(self.device)
         x32 = self._buf("x32", (M, D), torch.float32)
         x32.copy_(self.shared.weight[input_ids.reshape(-1)])
-        bias = self.position_bias(L)[None]                                            # (1, H, L, L)
+        pos_bias = self.position_bias(L)                                              # (H, L, L) fp32
+        key_bias = None
         if attention_mask is not None:                                                # additive key mask, as transformers' extended mask
-            keep = attention_mask.to(self.device).to(torch.float32).view(B, 1, 1, L)
-            bias = bias + (1.0 - keep) * torch.finfo(torch.float32).min
-        xn, q, k, v = (self._buf(n, (M, s), bf) for n, s in (("xn", D), ("q", inner), ("k", inner), ("v", inner)))
+            keep = attention_mask.to(self.device).to(torch.float32).view(B, L)
+            key_bias = ((1.0 - keep) * torch.finfo(torch.float32).min).contiguous()
+        native = self.attn_impl == "kernel"
+        if native and L > lib.T5_ATTN_MAX_KEYS:
+            raise RuntimeError(f"pxa_t5_attn_d64_bf16 holds the whole logit row in TMEM: at most {lib.T5_ATTN_MAX_KEYS} tokens per "
+                               f"caption (got {L}; the reference uses 120 / 300).  model.attn_impl = 'torch' runs longer inputs.")
+        if not native:
+            bias = pos_bias[None] if key_bias is None else pos_bias[None] + key_bias.view(B, 1, 1, L)
+        xn, qkv = self._buf("xn", (M, D), bf), self._buf("qkv", (M, 3 * inner), bf)
+        q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]
         ao, h0, h1 = self._buf("ao", (M, inner), bf), self._buf("h0", (M, F_), bf), self._buf("h1", (M, F_), bf)
-        for blk in self.encoder.block:
+        for li, blk in enumerate(self.encoder.block):
             at, ff = blk.layer[0], blk.layer[1]
             sa, dense = at.SelfAttention, ff.DenseReluDense
-            # (1) x += o( softmax(q k^T + bias) v ),  q / k / v = Linear(rmsnorm(x))        (no 1/sqrt(d): T5 folds it into the init)
+            # (1) x += o( softmax(q k^T + bias) v ),  q | k | v = ONE GEMM of rmsnorm(x) against the row-stacked weights
+            #     (no 1/sqrt(d): T5 folds it into the initialisation)
             lib.rmsnorm(x32, at.layer_norm.weight, xn, eps=at.layer_norm.variance_epsilon)
-            lib.gemm(xn, sa.q.weight, None, q)
-            lib.gemm(xn, sa.k.weight, None, k)
-            lib.gemm(xn, sa.v.weight, None, v)
-            q4, k4, v4 = (t.view(B, L, H, dk).transpose(1, 2).float() for t in (q, k, v))
-            p = torch.softmax(q4 @ k4.transpose(-1, -2) + bias, dim=-1)
-            ao.view(B, L, H, dk).copy_((p @ v4).transpose(1, 2))
+            lib.gemm(xn, self._stacked_qkv(li, sa), None, qkv)
+            if native:
+                lib.t5_attn(q, k, v, ao, pos_bias, key_bias, B=B, H=H, L=L, scale=1.0)
+            else:                                                                     # attn_impl = "torch": A/B, and captions > 384 tokens
+                q4, k4, v4 = (t.reshape(B, L, H, dk).transpose(1, 2).float() for t in (q, k, v))
+                p = torch.softmax(q4 @ k4.transpose(-1, -2) + bias, dim=-1)
+                ao.view(B, L, H, dk).copy_((p @ v4).transpose(1, 2))
             # block_n = 256 divides d_model 4096 (the auto choice for the in-place update, 192-column tiles on the CTA pair, is tuned
             # for the DiT's N = 1152 and would leave a partial last column tile here)
             lib.gemm(ao, sa.o.weight, None, x32, epilogue=lib.EPI_BIAS_RESIDUAL, residual=x32, block_n=_res_bn(D))

@@ -103,10 +103,10 @@ def test_library_exports_every_symbol_the_header_declares():
 def test_ctypes_structs_match_header_sizes():
     """Field-by-field size check of the POD argument structs against a compile of the header with gcc."""
     import subprocess, tempfile
-    src = '#include <stdio.h>\n#include "pixart_sm100.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(PxaGemmArgs),' \
+    src = '#include <stdio.h>\n#include "pixart_sm100.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(PxaGemmArgs),' \
           ' sizeof(PxaLnModArgs), sizeof(PxaAttnArgs), sizeof(PxaKvCompressArgs), sizeof(PxaConv3x3Args),' \
           ' sizeof(PxaDpmStepArgs), sizeof(PxaGateResidualArgs), sizeof(PxaLnModBwdArgs), sizeof(PxaAttnBwdArgs),' \
-          ' sizeof(PxaKvCompressBwdArgs), sizeof(PxaLnPrepareArgs), sizeof(PxaAdamWArgs), sizeof(PxaMlpArgs));return 0;}\n'
+          ' sizeof(PxaKvCompressBwdArgs), sizeof(PxaLnPrepareArgs), sizeof(PxaAdamWArgs), sizeof(PxaMlpArgs), sizeof(PxaT5AttnArgs));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
@@ -114,7 +114,8 @@ def test_ctypes_structs_match_header_sizes():
     assert sizes == [ctypes.sizeof(lib.GemmArgs), ctypes.sizeof(lib.LnModArgs), ctypes.sizeof(lib.AttnArgs),
                      ctypes.sizeof(lib.KvCompressArgs), ctypes.sizeof(lib.Conv3x3Args), ctypes.sizeof(lib.DpmStepArgs),
                      ctypes.sizeof(lib.GateResidualArgs), ctypes.sizeof(lib.LnModBwdArgs), ctypes.sizeof(lib.AttnBwdArgs),
-                     ctypes.sizeof(lib.KvCompressBwdArgs), ctypes.sizeof(lib.LnPrepareArgs), ctypes.sizeof(lib.AdamWArgs), ctypes.sizeof(lib.MlpArgs)]
+                     ctypes.sizeof(lib.KvCompressBwdArgs), ctypes.sizeof(lib.LnPrepareArgs), ctypes.sizeof(lib.AdamWArgs), ctypes.sizeof(lib.MlpArgs),
+                     ctypes.sizeof(lib.T5AttnArgs)]
 
 
 def test_integration_md_ctypes_stub_matches_the_header_struct():

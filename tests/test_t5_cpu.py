@@ -45,8 +45,17 @@ def _standins(monkeypatch):
         out.copy_(x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * weight.float())
         return out
 
+    def t5_attn(q, k, v, out, bias, key_bias=None, *, B, H, L, scale=1.0):
+        q4, k4, v4 = (t.reshape(B, L, H, 64).transpose(1, 2).float() for t in (q, k, v))
+        s = q4 @ k4.transpose(-1, -2) * scale + bias[None]
+        if key_bias is not None:
+            s = s + key_bias.view(B, 1, 1, L)
+        out.view(B, L, H, 64).copy_((torch.softmax(s, -1) @ v4).transpose(1, 2))
+        return out
+
     monkeypatch.setattr(lib, "gemm", gemm)
     monkeypatch.setattr(lib, "rmsnorm", rmsnorm)
+    monkeypatch.setattr(lib, "t5_attn", t5_attn)
     monkeypatch.setattr(t5, "_need_kernels", lambda w: None)          # the product refuses CPU tensors (last test)
 
 
@@ -65,10 +74,12 @@ def test_state_dict_keys_and_buckets_equal_transformers():
     assert t5.T5_V1_1_XXL["num_layers"] == 24 and t5.T5_V1_1_XXL["d_model"] == 4096 and t5.T5_V1_1_XXL["d_ff"] == 10240
 
 
-def test_forward_glue_equals_transformers_fp32(monkeypatch):
+@pytest.mark.parametrize("attn_impl", ["kernel", "torch"])
+def test_forward_glue_equals_transformers_fp32(monkeypatch, attn_impl):
     _standins(monkeypatch)
     hf = hf_model(SMALL)
     m = t5.T5EncoderModel(SMALL)
+    m.attn_impl = attn_impl
     m.load_state_dict(hf.state_dict())
     m = m.to(torch.bfloat16)
     hf.load_state_dict({k: v.float() for k, v in m.state_dict().items()})          # the same bf16-valued weights on both sides

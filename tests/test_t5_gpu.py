@@ -28,6 +28,35 @@ def test_rmsnorm_matches_torch(M, C):
     assert torch.equal(big[:, :C], out)
 
 
+@pytest.mark.parametrize("B,H,L,lens", [(1, 1, 128, None), (2, 4, 40, [40, 7]), (3, 8, 300, [300, 77, 129]), (2, 64, 300, [300, 8]),
+                                        (1, 3, 384, [383]), (2, 2, 257, None), (1, 2, 16, [5])])
+def test_t5_attention_kernel_matches_torch(B, H, L, lens):
+    """pxa_t5_attn_d64_bf16 on column slices of a fused (B*L, 3*H*64) qkv buffer against fp32 torch: unscaled logits + per-head bias
+    [H, L, L] + additive key mask, softmax, P V.  1 / 2 / 3 key boxes, partial last boxes / chunks / 16-key steps, one sample
+    running into the next one's rows inside a TMA box."""
+    g = torch.Generator().manual_seed(5)
+    inner = H * 64
+    qkv = (torch.randn(B * L, 3 * inner, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    bias = (torch.randn(H, L, L, generator=g) * 2).cuda()
+    key_bias = None
+    if lens is not None:
+        keep = (torch.arange(L)[None] < torch.tensor(lens)[:, None]).float()
+        key_bias = ((1.0 - keep) * torch.finfo(torch.float32).min).cuda().contiguous()
+    out = torch.full((B * L, inner), float("nan"), dtype=torch.bfloat16, device="cuda")
+    q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]
+    lib.t5_attn(q, k, v, out, bias, key_bias, B=B, H=H, L=L, scale=1.0)
+    q4, k4, v4 = (t.reshape(B, L, H, 64).transpose(1, 2).float() for t in (q, k, v))
+    s = q4 @ k4.transpose(-1, -2) + bias[None]
+    if key_bias is not None:
+        s = s + key_bias.view(B, 1, 1, L)
+    want = (torch.softmax(s, -1) @ v4).transpose(1, 2).reshape(B * L, inner)
+    assert torch.isfinite(out.float()).all()
+    assert po.rel_err(out.float(), want) < 6e-3
+    with pytest.raises(lib.PxaError):
+        big = torch.empty(385, 64, dtype=torch.bfloat16, device="cuda")
+        lib.t5_attn(big, big, big, torch.empty_like(big), torch.zeros(1, 385, 385, device="cuda"), None, B=1, H=1, L=385)
+
+
 def _pair(cfg, seed):
     torch.manual_seed(seed)
     hc = transformers.T5Config(feed_forward_proj="gated-gelu", dropout_rate=0.0, **cfg)
@@ -51,8 +80,10 @@ def _pair(cfg, seed):
     ("xxl-width-1-layer-b5", dict(vocab_size=512, d_model=4096, d_kv=64, d_ff=10240, num_layers=1, num_heads=64), 5, 300,
      [300, 8, 129, 300, 64]),          # M = 1500 rows: the CTA-pair GEMM path
 ])
-def test_t5_encoder_matches_transformers(name, cfg, B, L, lens):
+@pytest.mark.parametrize("attn_impl", ["kernel", "torch"])
+def test_t5_encoder_matches_transformers(name, cfg, B, L, lens, attn_impl):
     m, hf = _pair(cfg, seed=0)
+    m.attn_impl = attn_impl
     g = torch.Generator().manual_seed(3)
     ids = torch.randint(0, cfg["vocab_size"], (B, L), generator=g)
     mask = (torch.arange(L)[None] < torch.tensor(lens)[:, None]).long()
@@ -60,7 +91,8 @@ def test_t5_encoder_matches_transformers(name, cfg, B, L, lens):
     got = m(input_ids=ids.cuda(), attention_mask=mask.cuda())["last_hidden_state"]
     torch.cuda.synchronize()
     launches = lib.launch_count() - n0
-    assert launches == cfg["num_layers"] * 9 + 1                       # 7 GEMMs + 2 RMS norms per block, the final norm
+    # per block: 2 RMS norms, 5 GEMMs (q|k|v as one, o, wi_0, wi_1, wo), the attention kernel; + the final norm
+    assert launches == cfg["num_layers"] * (8 if attn_impl == "kernel" else 7) + 1
     torch.set_num_threads(min(32, max(torch.get_num_threads(), 8)))
     with torch.no_grad():
         want = hf(input_ids=ids, attention_mask=mask)["last_hidden_state"]
@@ -68,5 +100,5 @@ def test_t5_encoder_matches_transformers(name, cfg, B, L, lens):
     err = po.rel_err(got.float().cpu(), want)
     valid = mask.bool()
     err_valid = po.rel_err(got.float().cpu()[valid], want[valid])
-    print(f"T5 {name}: last_hidden_state rel_err {err:.3e} (valid tokens {err_valid:.3e}), {launches} kernel launches")
+    print(f"T5 {name} attn={attn_impl}: last_hidden_state rel_err {err:.3e} (valid tokens {err_valid:.3e}), {launches} kernel launches")
     assert err < 1e-2 and err_valid < 1e-2
