@@ -207,11 +207,13 @@ int pxa_rmsnorm_bf16(const float* x, const void* weight, void* out, int32_t M, i
 typedef struct PxaT5AttnArgs {
   const void* q; const void* k; const void* v;
   void* out;
-  const float* bias;      /* fp32 [H, L, L]                */
-  const float* key_bias;  /* fp32 [B, L] or NULL           */
+  const float* bias;      /* fp32 [H, L, L]; may be NULL when rel_bias is given                                              */
+  const float* key_bias;  /* fp32 [B, L] or NULL                                                                             */
   int64_t q_sn, q_sh, k_sn, k_sh, v_sn, v_sh, ldo;
   int32_t B, H, L;
   float scale;
+  const float* rel_bias;  /* fp32 [H, 2L-1] or NULL: the Toeplitz form bias[h, i, j] = rel_bias[h, j - i + L - 1] that T5's relative
+                             position bias has; staged in shared memory (used instead of `bias` when non-NULL)              */
 } PxaT5AttnArgs;
 int pxa_t5_attn_d64_bf16(const PxaT5AttnArgs* args, void* stream);
 
@@ -302,7 +304,8 @@ int pxa_kv_compress_conv2_ln(const PxaKvCompressArgs* args, void* stream);
  * the NHWC image fetched by a 4-D TMA tensor map whose out-of-bounds fill implements the padding (no im2col buffer).
  * Replaces the conv1 / conv2 of the decoder ResBlocks of diffusers' AutoencoderKL (reference call site
  * scripts/inference.py:136 `vae.decode`; GroupNorm + SiLU stay PyTorch).
- * Requirements: Cin % 64 == 0, Cout % 8 == 0, W a multiple of min(W,128), H a multiple of 128/min(W,128).
+ * Requirements: Cin % 64 == 0, Cout % 8 == 0.  Any H x W: widths that are a power of two <= 128 (with H a multiple of 128 / W) or a
+ * multiple of 128 tile exactly; the others run over a virtual width rounded up to 128 (W / Wp of the MMA work is useful).
  */
 typedef struct PxaConv3x3Args {
   const void* x;        /* bf16 NHWC [B, H, W, Cin] contiguous (torch channels_last)                         */

@@ -37,6 +37,9 @@ struct GemmParams {
   float ln_inv_dim, ln_eps;
   // implicit-GEMM 3x3 convolution mode (kConv): A is an NHWC image read through a 4-D tensor map
   int conv_H, conv_W, conv_tile_w, conv_tile_h, conv_cin_blocks;
+  // widths that do not tile (neither a power of two <= 128 nor a multiple of 128): the M index runs over a VIRTUAL image of width
+  // conv_Wp = W rounded up to 128 -- pixel columns >= W are TMA zero fill on the way in and are not stored on the way out
+  int conv_Wp;
 };
 
 inline void fill_ln_params(GemmParams& p, const PxaGemmArgs& a) {
@@ -160,14 +163,15 @@ struct ResFrag {
 };
 
 template <typename OutT>
-PXA_DEVICE void load_residual_frag(ResFrag& f, const GemmParams& p, int lane, int row0, int col0) {
+PXA_DEVICE void load_residual_frag(ResFrag& f, const GemmParams& p, int lane, int row0, int col0, int m_limit = -1) {
+  const int m_end = m_limit >= 0 ? m_limit : p.M;       // convolution with a virtual width: rows [row0, m_limit) exist
   const int gcol = col0 + (lane & 7) * 4;
   const bool col_ok = gcol < p.N;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int grow = row0 + it * 4 + (lane >> 3);
     f.r[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (grow < p.M && col_ok) {
+    if (grow < m_end && col_ok) {
       const size_t off = (size_t)grow * p.ldo + gcol;
       if constexpr (sizeof(OutT) == 4) {
         f.r[it] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + off);
@@ -181,7 +185,8 @@ PXA_DEVICE void load_residual_frag(ResFrag& f, const GemmParams& p, int lane, in
 
 template <typename OutT>
 PXA_DEVICE void epilogue_chunk_residual(uint32_t (&v)[32], const ResFrag& res, const GemmParams& p, uint8_t* stile,
-                                        int lane, int row0, int col0) {
+                                        int lane, int row0, int col0, int m_limit = -1) {
+  const int m_end = m_limit >= 0 ? m_limit : p.M;
   // smem tile: 32 rows x 128 B; 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) * 16)
   {
     const int sw = lane & 7;
@@ -206,7 +211,7 @@ PXA_DEVICE void epilogue_chunk_residual(uint32_t (&v)[32], const ResFrag& res, c
   for (int it = 0; it < 8; ++it) {
     const int grow = row0 + it * 4 + (lane >> 3);
     g[it] = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (p.gate != nullptr && grow < p.M && col_ok) {
+    if (p.gate != nullptr && grow < m_end && col_ok) {
       const int bidx = grow / p.rows_per_batch;
       g[it] = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)bidx * p.gate_batch_stride + gcol));
     }
@@ -216,7 +221,7 @@ PXA_DEVICE void epilogue_chunk_residual(uint32_t (&v)[32], const ResFrag& res, c
     const int r = it * 4 + (lane >> 3);
     const int grow = row0 + r;
     const float4 a = *reinterpret_cast<const float4*>(stile + r * 128 + ((c ^ (r & 7)) << 4));
-    if (grow < p.M && col_ok) {
+    if (grow < m_end && col_ok) {
       const size_t off = (size_t)grow * p.ldo + gcol;
       float4 o;
       const float4 yb = make_float4(a.x + b0, a.y + b1, a.z + b2, a.w + b3);     // the branch output
@@ -324,8 +329,10 @@ PXA_DEVICE float2 ln_row_coeffs(const GemmParams& p, const LnStatRegs& r) {
 //                          (rstd, -rstd * mu) of this thread's row, u / v of the row's sample from the staged constants.
 template <int EPI>
 PXA_DEVICE void epilogue_chunk_bf16_c(uint32_t (&v)[32], const GemmParams& p, const EpiConst* cb, uint8_t* stile, int lane,
-                                      int row0, int col0, int ccol, float2 ln = make_float2(1.f, 0.f), bool second = false) {
+                                      int row0, int col0, int ccol, float2 ln = make_float2(1.f, 0.f), bool second = false,
+                                      int m_limit = -1) {
   constexpr bool kLn = (EPI == PXA_EPI_LN_BIAS || EPI == PXA_EPI_LN_BIAS_GELU);
+  const int m_end = m_limit >= 0 ? m_limit : p.M;
   uint32_t pk[16];
   [[maybe_unused]] uint32_t pk2[16];
   const float4* bp = reinterpret_cast<const float4*>((kLn && second ? cb->gate0 : cb->bias) + ccol);
@@ -385,7 +392,7 @@ PXA_DEVICE void epilogue_chunk_bf16_c(uint32_t (&v)[32], const GemmParams& p, co
   for (int it = 0; it < 4; ++it) {
     const int grow = row0 + it * 8 + (lane >> 2);
     const int gcol = col0 + c * 8;
-    if (grow < p.M && gcol < p.N) *reinterpret_cast<uint4*>(out + (size_t)grow * p.ldo + gcol) = u[it];
+    if (grow < m_end && gcol < p.N) *reinterpret_cast<uint4*>(out + (size_t)grow * p.ldo + gcol) = u[it];
   }
   __syncwarp();
   if constexpr (EPI == PXA_EPI_BIAS_GELU_AUX) {              // second pass of the same transpose for the pre-activation

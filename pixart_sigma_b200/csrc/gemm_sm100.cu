@@ -84,6 +84,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if constexpr (kTmaRes) {
             if (!(p.out_aux == nullptr && p.residual == p.out && p.row_stats_out == nullptr))
               for (int c = 0; c < BN / 32; ++c) tma_prefetch_l2_2d(&tmap_res, n0 + c * 32, m0);
+          } else if constexpr (kConv) {
+            tma_prefetch_l2_2d(&tmap_res, n0, (m0 / p.conv_Wp) * p.conv_W + m0 % p.conv_Wp);   // real row of the tile's first pixel
           } else {
             tma_prefetch_l2_2d(&tmap_res, n0, m0);
           }
@@ -106,10 +108,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             // tap offset -- zero padding comes for free from TMA out-of-bounds fill on the W / H dimensions
             const int tap = kb / p.conv_cin_blocks;
             const int c0 = (kb - tap * p.conv_cin_blocks) * kBK;
-            const int pix = m0;                                     // first pixel of the tile in (b, y, x) order
-            const int x0 = pix % p.conv_W;
-            const int y0 = (pix / p.conv_W) % p.conv_H;
-            const int b0 = pix / (p.conv_W * p.conv_H);
+            const int pix = m0;                                     // first pixel of the tile in (b, y, x) order of the virtual image
+            const int x0 = pix % p.conv_Wp;
+            const int y0 = (pix / p.conv_Wp) % p.conv_H;
+            const int b0 = pix / (p.conv_Wp * p.conv_H);
             tma_load_4d(sa, &tmap_a, &full_bar[stage], c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, b0, kEvictNormal);
           } else {
             tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBK, m0, kEvictNormal);
@@ -197,15 +199,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
         const uint32_t t_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
+        // this warp's 32 output rows: GEMM rows m0 + 32 q ..; a convolution over a virtual width (conv_Wp > W: one image line per
+        // tile) stores pixel x of line (b, y) at row (b H + y) W + x and drops the columns x >= W
+        int row0 = m0 + q * 32;
+        [[maybe_unused]] int m_lim = -1;
+        if constexpr (kConv) {
+          if (p.conv_Wp != p.conv_W) {
+            const int xs = m0 % p.conv_Wp + q * 32;
+            const int left = p.conv_W - xs;
+            row0 = (m0 / p.conv_Wp) * p.conv_W + xs;
+            m_lim = row0 + (left < 0 ? 0 : (left > 32 ? 32 : left));
+          }
+        }
         auto process = [&](uint32_t (&v)[32], int cc) {
           if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
             ResFrag res;                                            // bf16 residual stream (VAE convolutions): simple path
-            load_residual_frag<OutT>(res, p, lane, m0 + q * 32, n0 + cc * 32);
-            epilogue_chunk_residual<OutT>(v, res, p, stile, lane, m0 + q * 32, n0 + cc * 32);
+            load_residual_frag<OutT>(res, p, lane, row0, n0 + cc * 32, m_lim);
+            epilogue_chunk_residual<OutT>(v, res, p, stile, lane, row0, n0 + cc * 32, m_lim);
           } else if constexpr (kLn) {
-            epilogue_chunk_bf16_c<EPI>(v, p, cb, stile, lane, m0 + q * 32, n0 + cc * 32, cc * 32, ln, second);
+            epilogue_chunk_bf16_c<EPI>(v, p, cb, stile, lane, row0, n0 + cc * 32, cc * 32, ln, second);
           } else {
-            epilogue_chunk_bf16_c<EPI>(v, p, cb, stile, lane, m0 + q * 32, n0 + cc * 32, cc * 32);
+            epilogue_chunk_bf16_c<EPI>(v, p, cb, stile, lane, row0, n0 + cc * 32, cc * 32, make_float2(1.f, 0.f), false, m_lim);
           }
         };
         auto release_acc = [&]() {                                  // all TMEM reads of this accumulator are done
@@ -243,6 +257,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // ------------------------------------------------------------------------------------------------- host
 struct ConvGeom {
   int B, H, W, Cin, tile_w, tile_h;
+  int Wp;          // virtual width of the M index (= W when W tiles; else W rounded up to 128, see GemmParams::conv_Wp)
 };
 
 template <int BN, int EPI, typename OutT, bool kConv = false, bool kMn = false>
@@ -283,6 +298,7 @@ static int launch_gemm(const PxaGemmArgs& a, cudaStream_t stream, const ConvGeom
   CUtensorMap tr = ta, to = ta, tx = ta;   // residual / out / aux maps: only meaningful for EPI_BIAS_RESIDUAL
   if constexpr (EPI == PXA_EPI_BIAS_RESIDUAL) {
     uint64_t dims[2] = {(uint64_t)a.N, (uint64_t)a.M};
+    if constexpr (kConv) dims[1] = (uint64_t)cg->B * cg->H * cg->W;       // the rows that exist (a.M counts the virtual width)
     uint64_t str[1] = {(uint64_t)a.ldo * sizeof(OutT)};
     if constexpr (kTmaRes) {
       uint32_t box[2] = {32, kBM};         // 32 fp32 = 128 B rows: one TMA 128B-swizzle atom per row
@@ -321,6 +337,7 @@ static int launch_gemm(const PxaGemmArgs& a, cudaStream_t stream, const ConvGeom
     p.conv_H = cg->H; p.conv_W = cg->W; p.conv_tile_w = cg->tile_w; p.conv_tile_h = cg->tile_h;
     p.conv_cin_blocks = cg->Cin / kBK;
   }
+  p.conv_Wp = kConv ? cg->Wp : 0;
   auto kern = gemm_bf16_kernel<BN, EPI, OutT, kConv, kMn>;
   PXA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
   int grid = device_info().sms;
@@ -400,17 +417,26 @@ extern "C" int pxa_conv3x3_nhwc_bf16(const PxaConv3x3Args* args, void* stream) {
   if (c.Cout % 8) return fail(PXA_ERR_ARG, "Cout must be a multiple of 8 (got %d)", c.Cout);
   ConvGeom cg;
   cg.B = c.B; cg.H = c.H; cg.W = c.W; cg.Cin = c.Cin;
+  // M tile = 128 consecutive pixels = ONE TMA box: tile_h full lines when W is a power of two <= 128 (and H a multiple of tile_h),
+  // 128 pixels of one line when W is a multiple of 128.  Every other geometry (e.g. the 1024-MS aspect buckets: latent 104 x 152 ->
+  // 832 x 1216) runs over a virtual width Wp = W rounded up to 128, one line segment per tile: columns >= W are zero fill going in
+  // (the right-hand padding of the convolution, exactly) and are dropped going out; the tail tile of a line is partly idle (W / Wp of
+  // the MMA work is useful: 0.81 at W = 104, 0.95 at W = 1216).
   cg.tile_w = c.W < 128 ? c.W : 128;
-  if (128 % cg.tile_w) return fail(PXA_ERR_ARG, "W must be a power of two <= 128 or a multiple of 128 (got %d)", c.W);
-  cg.tile_h = 128 / cg.tile_w;
-  if (c.W % cg.tile_w || c.H % cg.tile_h) return fail(PXA_ERR_ARG, "H x W = %d x %d is not tileable by %d x %d", c.H, c.W, cg.tile_h, cg.tile_w);
+  cg.tile_h = (128 % cg.tile_w) ? 1 : 128 / cg.tile_w;
+  cg.Wp = c.W;
+  if ((128 % cg.tile_w) || c.W % cg.tile_w || c.H % cg.tile_h) {
+    cg.tile_w = 128; cg.tile_h = 1;
+    cg.Wp = (c.W + 127) / 128 * 128;
+  }
   if ((reinterpret_cast<uintptr_t>(c.x) | reinterpret_cast<uintptr_t>(c.w) | reinterpret_cast<uintptr_t>(c.out) |
        reinterpret_cast<uintptr_t>(c.bias) | reinterpret_cast<uintptr_t>(c.residual)) & 15)
     return fail(PXA_ERR_ALIGN, "pointers must be 16-byte aligned");
   PXA_REQUIRE_SM100();
   PxaGemmArgs a = {};
   a.a = c.x; a.w = c.w; a.bias = c.bias; a.out = c.out; a.residual = c.residual;
-  a.M = c.B * c.H * c.W; a.N = c.Cout; a.K = 9 * c.Cin;
+  if ((long long)c.B * c.H * cg.Wp >= (1ll << 31)) return fail(PXA_ERR_ARG, "B x H x W too large");
+  a.M = c.B * c.H * cg.Wp; a.N = c.Cout; a.K = 9 * c.Cin;
   a.lda = c.Cin; a.ldw = 9 * c.Cin; a.ldo = c.Cout;
   a.rows_per_batch = a.M;
   a.epilogue = c.residual ? PXA_EPI_BIAS_RESIDUAL : PXA_EPI_BIAS;

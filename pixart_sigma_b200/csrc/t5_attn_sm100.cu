@@ -10,7 +10,8 @@
 //               S[128 x 128 j..] = Q K_j^T (SS, 4 K-steps of 16 per key box), later O = P V (TS: P read from TMEM, V MN-major in its
 //               natural [key, d] layout), one N = 64 MMA per 16 keys
 //   warp 1      TMEM allocator (512 columns: S at 0..383, O at 384..447)
-//   warps 2-5   softmax, one thread per query row: pass 1 adds the bias rows to S in TMEM and finds the row max, pass 2 forms
+//   warps 2-5   softmax, one thread per query row: pass 1 adds the bias (T5's relative-position bias by offset j - i from a 2 L - 1
+//               entry smem vector, or a dense [H, L, L] table from global memory) to S in TMEM and finds the row max, pass 2 forms
 //               P = exp2((s - max) log2 e), accumulates the row sum and writes P as bf16 over the S columns already consumed
 //               (P chunk c lands in columns 16 c .. 16 c + 15, inside S chunk c / 2 <= c); then O / sum -> bf16 -> global.
 // Every barrier is used once (phase 0): the kernel is a straight line, not a pipeline -- at 300 keys a CTA lives ~10 us and 5 waves of
@@ -30,12 +31,16 @@ constexpr int kT5OffQ = 0;
 constexpr int kT5OffK = kT5OffQ + kT5BoxBytes;
 constexpr int kT5OffV = kT5OffK + kT5MaxKeyBoxes * kT5BoxBytes;
 constexpr int kT5OffBars = kT5OffV + kT5MaxKeyBoxes * kT5BoxBytes;
-constexpr int kT5Smem = kT5OffBars + 128 + 1024;   // + alignment slack
+constexpr int kT5MaxL = kT5Tile * kT5MaxKeyBoxes;  // 384
+constexpr int kT5OffRel = kT5OffBars + 128;        // fp32 [2 * 384]: the head's relative-position bias by offset j - i + L - 1
+constexpr int kT5OffKeyBias = kT5OffRel + 2 * kT5MaxL * 4;   // fp32 [384]: the sample's additive key mask
+constexpr int kT5Smem = kT5OffKeyBias + kT5MaxL * 4 + 1024;  // + alignment slack
 constexpr uint32_t kT5ColO = 384;
 
 struct T5AttnParams {
   __nv_bfloat16* out;
-  const float* bias;        // [H, L, L]
+  const float* bias;        // [H, L, L], or nullptr when rel_bias is given
+  const float* rel_bias;    // [H, 2 L - 1] or nullptr: bias[h, i, j] = rel_bias[h, j - i + L - 1] (T5: the bias is Toeplitz)
   const float* key_bias;    // [B, L] or nullptr
   int B, H, L, ldo;
   float scale_log2;         // scale * log2(e)
@@ -110,9 +115,23 @@ t5_attn_d64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int row = qd * 32 + lane;
     const int qi = q0 + row;                          // query index within the sample
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
-    const float* brow = p.bias + ((size_t)h * L + min(qi, L - 1)) * L;     // rows >= L are computed on clamped bias, never stored
-    const float* krow = p.key_bias ? p.key_bias + (size_t)b * L : nullptr;
+    const int qc = min(qi, L - 1);                    // rows >= L are computed on a clamped bias row, never stored
+    const float* brow = p.bias ? p.bias + ((size_t)h * L + qc) * L : nullptr;
     const float sl2 = p.scale_log2, l2e = p.log2e;
+    // The bias of a query row, one float per key.  Dense form: thread-per-row global loads touch 32 cache lines per instruction
+    // (46 us per CTA at L = 300, session 34).  T5's bias depends on j - i only: 2 L - 1 floats per head staged in smem, where the 32
+    // rows of a warp read 32 consecutive words; the key mask (one float per key, the same for every row) sits next to it.
+    float* rel_s = reinterpret_cast<float*>(smem + kT5OffRel);
+    float* kb_s = reinterpret_cast<float*>(smem + kT5OffKeyBias);
+    {
+      const int t0 = threadIdx.x - 64;                // 0..127
+      if (p.rel_bias != nullptr)
+        for (int t = t0; t < 2 * L - 1; t += 128) rel_s[t] = __ldg(p.rel_bias + (size_t)h * (2 * L - 1) + t);
+      for (int t = t0; t < L; t += 128) kb_s[t] = p.key_bias ? __ldg(p.key_bias + (size_t)b * L + t) : 0.f;
+      named_bar_sync(1, 128);
+    }
+    const float* rrow = rel_s + (L - 1 - qc);         // rrow[j] = rel_bias[h, j - i + L - 1]
+    const bool use_rel = p.rel_bias != nullptr;
 
     mbar_wait(s_full, 0);
     tc_fence_after();
@@ -126,8 +145,7 @@ t5_attn_d64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const int j = 32 * c + i;
         float t = -INFINITY;
         if (j < L) {
-          float add = __ldg(brow + j);
-          if (krow) add += __ldg(krow + j);
+          const float add = (use_rel ? rrow[j] : __ldg(brow + j)) + kb_s[j];
           t = fmaf(__uint_as_float(v[i]), sl2, add * l2e);
         }
         m = fmaxf(m, t);
@@ -197,12 +215,14 @@ extern "C" int pxa_t5_attn_d64_bf16(const PxaT5AttnArgs* args, void* stream) {
   using namespace pxa;
   if (!args) return fail(PXA_ERR_ARG, "null args");
   const PxaT5AttnArgs& a = *args;
-  if (!a.q || !a.k || !a.v || !a.out || !a.bias) return fail(PXA_ERR_ARG, "null q / k / v / out / bias");
+  if (!a.q || !a.k || !a.v || !a.out) return fail(PXA_ERR_ARG, "null q / k / v / out");
+  if (!a.bias && !a.rel_bias) return fail(PXA_ERR_ARG, "one of bias [H, L, L] / rel_bias [H, 2L-1] is required");
   if (a.B <= 0 || a.H <= 0 || a.L <= 0) return fail(PXA_ERR_ARG, "bad B / H / L");
   if (a.L > kT5Tile * kT5MaxKeyBoxes) return fail(PXA_ERR_ARG, "L = %d: at most %d keys (the S row lives in TMEM)", a.L, kT5Tile * kT5MaxKeyBoxes);
   if ((a.q_sn & 7) || (a.q_sh & 7) || (a.k_sn & 7) || (a.k_sh & 7) || (a.v_sn & 7) || (a.v_sh & 7) || (a.ldo & 7))
     return fail(PXA_ERR_ALIGN, "strides must be multiples of 8 elements");
-  if ((reinterpret_cast<uintptr_t>(a.out) & 15) || (reinterpret_cast<uintptr_t>(a.bias) & 3) || (reinterpret_cast<uintptr_t>(a.key_bias) & 3))
+  if ((reinterpret_cast<uintptr_t>(a.out) & 15) || (reinterpret_cast<uintptr_t>(a.bias) & 3) || (reinterpret_cast<uintptr_t>(a.key_bias) & 3) ||
+      (reinterpret_cast<uintptr_t>(a.rel_bias) & 3))
     return fail(PXA_ERR_ALIGN, "out must be 16-byte aligned, bias / key_bias 4-byte aligned");
   if ((long long)a.H * kT5D > a.ldo) return fail(PXA_ERR_ARG, "ldo smaller than H * 64");
   PXA_REQUIRE_SM100();
@@ -214,7 +234,8 @@ extern "C" int pxa_t5_attn_d64_bf16(const PxaT5AttnArgs* args, void* stream) {
   if ((rc = make_t5_map(&vm, a.v, a.H, rows, a.v_sn, a.v_sh))) return rc;
   T5AttnParams p;
   p.out = reinterpret_cast<__nv_bfloat16*>(a.out);
-  p.bias = a.bias;
+  p.bias = a.rel_bias ? nullptr : a.bias;
+  p.rel_bias = a.rel_bias;
   p.key_bias = a.key_bias;
   p.B = a.B; p.H = a.H; p.L = a.L; p.ldo = (int)a.ldo;
   p.log2e = 1.4426950408889634f;

@@ -82,7 +82,7 @@ class T5AttnArgs(C.Structure):
     _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p), ("bias", C.c_void_p),
                 ("key_bias", C.c_void_p), ("q_sn", C.c_int64), ("q_sh", C.c_int64), ("k_sn", C.c_int64), ("k_sh", C.c_int64),
                 ("v_sn", C.c_int64), ("v_sh", C.c_int64), ("ldo", C.c_int64), ("B", C.c_int32), ("H", C.c_int32), ("L", C.c_int32),
-                ("scale", C.c_float)]
+                ("scale", C.c_float), ("rel_bias", C.c_void_p)]
 
 
 class KvCompressArgs(C.Structure):
@@ -314,18 +314,21 @@ def rmsnorm(x: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, eps: float
 T5_ATTN_MAX_KEYS = 384
 
 
-def t5_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, bias: torch.Tensor,
-            key_bias: Optional[torch.Tensor] = None, *, B: int, H: int, L: int, scale: float = 1.0) -> torch.Tensor:
+def t5_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, bias: Optional[torch.Tensor],
+            key_bias: Optional[torch.Tensor] = None, *, B: int, H: int, L: int, scale: float = 1.0,
+            rel_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """T5 self-attention, head_dim 64, L <= 384: out (B*L, H*64) = softmax(q k^T * scale + bias[h] + key_bias[b]) v.
     q / k / v: bf16 (B*L, H*64) views with unit column stride (e.g. column slices of a fused qkv GEMM output);
-    bias fp32 (H, L, L); key_bias fp32 (B, L) or None."""
+    bias fp32 (H, L, L), or rel_bias fp32 (H, 2L-1) with bias[h, i, j] = rel_bias[h, j - i + L - 1]; key_bias fp32 (B, L) or None."""
     for t in (q, k, v, out):
         assert t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1 and t.shape == (B * L, H * 64)
-    assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.shape == (H, L, L)
+    assert (bias is None) != (rel_bias is None), "exactly one of bias / rel_bias"
+    assert bias is None or (bias.dtype == torch.float32 and bias.is_contiguous() and bias.shape == (H, L, L))
+    assert rel_bias is None or (rel_bias.dtype == torch.float32 and rel_bias.is_contiguous() and rel_bias.shape == (H, 2 * L - 1))
     assert key_bias is None or (key_bias.dtype == torch.float32 and key_bias.is_contiguous() and key_bias.shape == (B, L))
     args = T5AttnArgs(q=_ptr(q), k=_ptr(k), v=_ptr(v), out=_ptr(out), bias=_ptr(bias), key_bias=_ptr(key_bias),
                       q_sn=q.stride(0), q_sh=64, k_sn=k.stride(0), k_sh=64, v_sn=v.stride(0), v_sh=64, ldo=out.stride(0),
-                      B=B, H=H, L=L, scale=scale)
+                      B=B, H=H, L=L, scale=scale, rel_bias=_ptr(rel_bias))
     _check(load().pxa_t5_attn_d64_bf16(C.byref(args), _stream()), "pxa_t5_attn_d64_bf16")
     return out
 

@@ -170,6 +170,14 @@ class T5EncoderModel(nn.Module):
         table = self.encoder.block[0].layer[0].SelfAttention.relative_attention_bias.weight
         return table.float()[bucket].permute(2, 0, 1).contiguous()
 
+    def relative_bias(self, L: int) -> torch.Tensor:
+        """(H, 2L-1) fp32: the bias by key-minus-query offset d = j - i, entry d + L - 1 (position_bias(L)[h, i, j] = this[h, j - i + L - 1])."""
+        cfg = self.cfg
+        d = torch.arange(-(L - 1), L, device=self.device)
+        bucket = relative_position_bucket(d, cfg["relative_attention_num_buckets"], cfg["relative_attention_max_distance"])
+        table = self.encoder.block[0].layer[0].SelfAttention.relative_attention_bias.weight
+        return table.float()[bucket].t().contiguous()
+
     @torch.no_grad()
     def forward(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None, **kwargs) -> EncoderOutput:
         _need_kernels(self.encoder.block[0].layer[0].SelfAttention.q.weight)
@@ -180,7 +188,6 @@ class T5EncoderModel(nn.Module):
         input_ids = input_ids.to(self.device)
         x32 = self._buf("x32", (M, D), torch.float32)
         x32.copy_(self.shared.weight[input_ids.reshape(-1)])
-        pos_bias = self.position_bias(L)                                              # (H, L, L) fp32
         key_bias = None
         if attention_mask is not None:                                                # additive key mask, as transformers' extended mask
             keep = attention_mask.to(self.device).to(torch.float32).view(B, L)
@@ -189,7 +196,10 @@ class T5EncoderModel(nn.Module):
         if native and L > lib.T5_ATTN_MAX_KEYS:
             raise RuntimeError(f"pxa_t5_attn_d64_bf16 holds the whole logit row in TMEM: at most {lib.T5_ATTN_MAX_KEYS} tokens per "
                                f"caption (got {L}; the reference uses 120 / 300).  model.attn_impl = 'torch' runs longer inputs.")
-        if not native:
+        if native:
+            rel = self.relative_bias(L)                                               # (H, 2L-1) fp32: the bias is Toeplitz
+        else:
+            pos_bias = self.position_bias(L)                                          # (H, L, L) fp32
             bias = pos_bias[None] if key_bias is None else pos_bias[None] + key_bias.view(B, 1, 1, L)
         xn, qkv = self._buf("xn", (M, D), bf), self._buf("qkv", (M, 3 * inner), bf)
         q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]
@@ -202,7 +212,7 @@ class T5EncoderModel(nn.Module):
             lib.rmsnorm(x32, at.layer_norm.weight, xn, eps=at.layer_norm.variance_epsilon)
             lib.gemm(xn, self._stacked_qkv(li, sa), None, qkv)
             if native:
-                lib.t5_attn(q, k, v, ao, pos_bias, key_bias, B=B, H=H, L=L, scale=1.0)
+                lib.t5_attn(q, k, v, ao, None, key_bias, B=B, H=H, L=L, scale=1.0, rel_bias=rel)
             else:                                                                     # attn_impl = "torch": A/B, and captions > 384 tokens
                 q4, k4, v4 = (t.reshape(B, L, H, dk).transpose(1, 2).float() for t in (q, k, v))
                 p = torch.softmax(q4 @ k4.transpose(-1, -2) + bias, dim=-1)

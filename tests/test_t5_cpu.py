@@ -45,7 +45,11 @@ def _standins(monkeypatch):
         out.copy_(x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * weight.float())
         return out
 
-    def t5_attn(q, k, v, out, bias, key_bias=None, *, B, H, L, scale=1.0):
+    def t5_attn(q, k, v, out, bias, key_bias=None, *, B, H, L, scale=1.0, rel_bias=None):
+        if rel_bias is not None:                      # Toeplitz form: bias[h, i, j] = rel_bias[h, j - i + L - 1]
+            assert bias is None and rel_bias.shape == (H, 2 * L - 1)
+            pos = torch.arange(L)
+            bias = rel_bias[:, pos[None, :] - pos[:, None] + L - 1]
         q4, k4, v4 = (t.reshape(B, L, H, 64).transpose(1, 2).float() for t in (q, k, v))
         s = q4 @ k4.transpose(-1, -2) * scale + bias[None]
         if key_bias is not None:

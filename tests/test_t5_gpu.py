@@ -30,21 +30,28 @@ def test_rmsnorm_matches_torch(M, C):
 
 @pytest.mark.parametrize("B,H,L,lens", [(1, 1, 128, None), (2, 4, 40, [40, 7]), (3, 8, 300, [300, 77, 129]), (2, 64, 300, [300, 8]),
                                         (1, 3, 384, [383]), (2, 2, 257, None), (1, 2, 16, [5])])
-def test_t5_attention_kernel_matches_torch(B, H, L, lens):
+@pytest.mark.parametrize("toeplitz", [False, True])
+def test_t5_attention_kernel_matches_torch(B, H, L, lens, toeplitz):
     """pxa_t5_attn_d64_bf16 on column slices of a fused (B*L, 3*H*64) qkv buffer against fp32 torch: unscaled logits + per-head bias
     [H, L, L] + additive key mask, softmax, P V.  1 / 2 / 3 key boxes, partial last boxes / chunks / 16-key steps, one sample
     running into the next one's rows inside a TMA box."""
     g = torch.Generator().manual_seed(5)
     inner = H * 64
     qkv = (torch.randn(B * L, 3 * inner, generator=g) * 0.5).to(torch.bfloat16).cuda()
-    bias = (torch.randn(H, L, L, generator=g) * 2).cuda()
+    if toeplitz:       # T5's form: the bias depends on j - i only; the kernel takes the (H, 2L-1) vector and stages it in smem
+        rel = (torch.randn(H, 2 * L - 1, generator=g) * 2).cuda()
+        pos = torch.arange(L, device="cuda")
+        bias = rel[:, pos[None, :] - pos[:, None] + L - 1].contiguous()
+    else:
+        rel = None
+        bias = (torch.randn(H, L, L, generator=g) * 2).cuda()
     key_bias = None
     if lens is not None:
         keep = (torch.arange(L)[None] < torch.tensor(lens)[:, None]).float()
         key_bias = ((1.0 - keep) * torch.finfo(torch.float32).min).cuda().contiguous()
     out = torch.full((B * L, inner), float("nan"), dtype=torch.bfloat16, device="cuda")
     q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]
-    lib.t5_attn(q, k, v, out, bias, key_bias, B=B, H=H, L=L, scale=1.0)
+    lib.t5_attn(q, k, v, out, None if toeplitz else bias, key_bias, B=B, H=H, L=L, scale=1.0, rel_bias=rel)
     q4, k4, v4 = (t.reshape(B, L, H, 64).transpose(1, 2).float() for t in (q, k, v))
     s = q4 @ k4.transpose(-1, -2) + bias[None]
     if key_bias is not None:

@@ -20,7 +20,10 @@ def _rand(*shape, seed, scale=1.0):
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 32, 32, 128, 128), (2, 8, 128, 64, 256), (1, 4, 256, 128, 128),
-                                            (1, 16, 16, 512, 512), (1, 64, 64, 256, 128)])
+                                            (1, 16, 16, 512, 512), (1, 64, 64, 256, 128),
+                                            # widths / heights that do not tile: the M index runs over a virtual width rounded up to 128
+                                            (1, 24, 104, 64, 128), (1, 16, 152, 128, 128), (2, 5, 24, 64, 64), (1, 12, 208, 64, 256),
+                                            (1, 5, 32, 64, 128), (2, 3, 300, 64, 72), (1, 7, 129, 128, 192)])
 @pytest.mark.parametrize("with_res", [False, True])
 def test_conv3x3_matches_torch(B, H, W, Cin, Cout, with_res):
     x = _rand(B, H, W, Cin, seed=1).cuda()
@@ -138,6 +141,23 @@ def test_autoencoder_decode_and_encode_match_oracle():
     print(f"SDXL-VAE (random weights) decode rel_err {e_dec:.3e}, encode mean {e_mean:.3e} logvar {e_lv:.3e}; {launches} kernel launches per decode")
     assert e_dec < 2.5e-2 and e_mean < 2.5e-2 and e_lv < 2.5e-2
     assert dist.sample().shape == (1, 4, 16, 16)
+
+
+def test_autoencoder_decode_of_a_multi_aspect_bucket_matches_oracle():
+    """A 1024-MS aspect bucket scaled down (latent 13 x 19 -> 104 x 152 pixels: widths 19, 38, 76, 152 -- none of them tiles):
+    the convolutions take the virtual-width path at every resolution."""
+    from oracle import vae_oracle as vo
+    from pixart_sigma_b200.vae import AutoencoderKL
+    m = _init_vae(AutoencoderKL(), seed=2).to(torch.bfloat16).cuda()
+    sd = {k: v.detach().float().cpu() for k, v in m.state_dict().items() if k.startswith(("decoder.", "post_quant_conv."))}
+    z = _rand(2, 4, 13, 19, seed=31)
+    got = m.decode(z.cuda()).sample.float().cpu()
+    torch.set_num_threads(min(32, torch.get_num_threads() * 4))
+    want = vo.decode(sd, z.float())
+    assert got.shape == want.shape == (2, 3, 104, 152)
+    err = po.rel_err(got, want)
+    print(f"SDXL-VAE decode of a 13 x 19 latent (virtual-width convolutions): rel_err {err:.3e}")
+    assert torch.isfinite(got).all() and err < 2.5e-2
 
 
 def test_autoencoder_decode_1024px_runs_and_is_finite():
