@@ -103,6 +103,18 @@ def test_forward_glue_equals_transformers_fp32(monkeypatch, attn_impl):
     assert po.rel_err(got2.float(), want2) < 1e-2
 
 
+def test_relative_bias_vector_is_the_toeplitz_form_of_the_position_bias():
+    """`pxa_t5_attn_d64_bf16` takes the bias by offset: position_bias(L)[h, i, j] == relative_bias(L)[h, j - i + L - 1]."""
+    m = t5.T5EncoderModel(SMALL)
+    with torch.no_grad():
+        m.encoder.block[0].layer[0].SelfAttention.relative_attention_bias.weight.normal_()
+    for L in (1, 7, 40, 300):
+        pb, rel = m.position_bias(L), m.relative_bias(L)
+        pos = torch.arange(L)
+        assert rel.shape == (SMALL["num_heads"], 2 * L - 1)
+        assert torch.equal(pb, rel[:, pos[None, :] - pos[:, None] + L - 1])
+
+
 def test_product_refuses_to_run_without_the_kernels():
     m = t5.T5EncoderModel(SMALL)
     with pytest.raises(RuntimeError, match="sm_100a kernels only"):

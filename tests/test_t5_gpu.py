@@ -89,6 +89,8 @@ def _pair(cfg, seed):
 ])
 @pytest.mark.parametrize("attn_impl", ["kernel", "torch"])
 def test_t5_encoder_matches_transformers(name, cfg, B, L, lens, attn_impl):
+    if attn_impl == "torch" and name == "xxl-width-2-layers":
+        pytest.skip("the PyTorch attention core is covered by the small and the M = 1500 geometry (saves a 386 M parameter CPU model)")
     m, hf = _pair(cfg, seed=0)
     m.attn_impl = attn_impl
     g = torch.Generator().manual_seed(3)

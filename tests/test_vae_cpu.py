@@ -72,7 +72,7 @@ def test_decode_and_encode_glue_equal_the_oracle(monkeypatch):
     m = _init(vae.AutoencoderKL(SMALL)).to(torch.bfloat16)
     sd = {k: v.float() for k, v in m.state_dict().items()}
     g = torch.Generator().manual_seed(1)
-    z = torch.randn(2, 4, 8, 12, generator=g).to(torch.bfloat16)
+    z = torch.randn(2, 4, 8, 12, generator=g).to(torch.bfloat16)       # non-square, widths 12 .. 96: the multi-aspect buckets
     got = m.decode(z).sample
     want = vo.decode(sd, z.float())
     assert got.shape == want.shape == (2, 3, 64, 96)
