@@ -273,7 +273,7 @@ typedef struct PxaAttnArgs {
                        2 = one CTA per item (same arithmetic, bit-identical results);
                        3 = three tiles per CTA, single S buffer each, three softmax warps per sub-partition (attn3_sm100.cu);
                        5 / 6 / 7 = experiment forms of 4 (no tile-B stagger / direct output stores always / tile stores always) */
-  int32_t p_precision; /* 0 = P rounded to bf16 before P V (2^-9 relative; the default).
+  int32_t p_precision; /* 0 = P rounded to bf16 before P V (up to 2^-8 relative; the default).
                           1 = `fp32_attention` semantics (PixArt_blocks.py:145-147: q / k / v and hence P kept in fp32): P enters
                               the tensor pipe as bf16 hi + lo terms (2^-17 relative), two P V products per 16 keys; logits,
                               softmax and accumulation are fp32 in both modes.  Not available for variant 3.                  */

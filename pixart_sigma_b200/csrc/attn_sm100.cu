@@ -130,7 +130,7 @@ constexpr int kTraceMax = 512;
 // fp32): the softmax threads publish P as TWO bf16 terms, P_hi = bf16(P) over the first 32 columns of the S half (as always) and
 // P_lo = bf16(P - P_hi) over the other 32 columns -- free once the scores are in registers -- and the MMA thread accumulates
 // P_hi V + P_lo V (same V descriptor, A operand 32 TMEM columns further).  P then carries 16 mantissa bits (2^-17 relative
-// instead of 2^-9), V is bf16-valued in the reference too (the qkv GEMM output), the products are exact and the accumulation is
+// instead of 2^-8), V is bf16-valued in the reference too (the qkv GEMM output), the products are exact and the accumulation is
 // fp32: the result is the fp32 attention of the same bf16 q / k / v up to summation order.  Tensor work per 64-key sub-block pair
 // goes 640 -> 960 cycles, still under the 1024-cycle exp2 floor, and no smem or TMEM is added (a kind::tf32 P V would need fp32
 // V tiles -- twice the smem traffic -- for the same tensor-pipe time).

@@ -165,3 +165,18 @@ def test_every_binding_checks_its_return_code_with_one_label():
     tree = ast.parse(inspect.getsource(lib))
     calls = [n for n in ast.walk(tree) if isinstance(n, ast.Call) and getattr(n.func, "id", None) == "_check"]
     assert len(calls) >= 20 and all(len(n.args) == 2 and not n.keywords for n in calls)
+
+
+def test_hi_lo_split_of_p_carries_sixteen_mantissa_bits():
+    """The arithmetic behind `PxaAttnArgs.p_precision = 1`: P_hi = bf16(P), P_lo = bf16(P - P_hi) -- the difference is
+    exact in fp32 -- so P_hi + P_lo reproduces P to 2^-17 relative (one bf16 term: up to 2^-8), for P anywhere in the lazy-rescale range
+    (0, 2^8] incl. values whose low term is subnormal-small."""
+    g = torch.Generator().manual_seed(0)
+    p = torch.exp2(torch.rand(1 << 16, generator=g) * 40 - 32)                 # 2^-32 .. 2^8
+    hi = p.to(torch.bfloat16)
+    diff = p - hi.float()
+    assert torch.equal(diff.double(), p.double() - hi.double())               # exact in fp32
+    lo = diff.to(torch.bfloat16)
+    err1 = ((hi.double() - p.double()).abs() / p.double()).max().item()
+    err2 = ((hi.double() + lo.double() - p.double()).abs() / p.double()).max().item()
+    assert 2.0 ** -9 < err1 <= 2.0 ** -8 and err2 <= 2.0 ** -17

@@ -485,7 +485,7 @@ def test_flash_attn_fp32_p_mode_matches_fp32_attention(variant):
     """`fp32_attention` (PixArt_blocks.py:145-147: q / k / v -- and therefore P -- kept in fp32 through P V): p_precision = 1
     feeds P to the tensor pipe as bf16 hi + lo terms.  Against the fp32 attention of the same bf16 q / k / v the result is then
     the CORRECTLY ROUNDED bf16 output for nearly every element (the only error left is the final bf16 store), while the default
-    mode (P rounded to bf16, 2^-9) misses the correctly rounded value much more often.  Ragged key sets incl. a partial last
+    mode (P rounded to bf16, up to 2^-8) misses the correctly rounded value much more often.  Ragged key sets incl. a partial last
     sub-block, a single sub-block and an empty set; 4 work items per CTA under the persistent grid at the larger size."""
     for (B, H, N, Nk, lens) in [(2, 3, 300, 300, [300, 77]), (5, 16, 2048, 1024, [1024, 65, 0, 449, 1000])]:
         q, k, v = _randn(B, N, H, 72, seed=140), _randn(B, Nk, H, 72, seed=141), _randn(B, Nk, H, 72, seed=142)
