@@ -218,6 +218,50 @@ def cpu_reference_train_sample(side: int, pe: float):
     return 1.0 / (fixed + DEPTH * per_block), t1 + t3
 
 
+def cpu_reference_t5_sample(caps: int, L: int):
+    """`--workload t5`: the reference's own CPU path is transformers' T5EncoderModel (diffusion/model/t5.py:12,107-110).  A full
+    T5-v1.1-XXL forward on the host needs 19 GB of fp32 weights and minutes, so the bounded sample is a 1-block and a 3-block model of
+    XXL width (d_model 4096, 64 heads, d_ff 10240; fp32, CPU_THREADS threads) on the same `caps` x L token ids: per-block time =
+    (t3 - t1) / 2, full forward = fixed + 24 x per-block.  Returns (captions/s, seconds measured)."""
+    import transformers
+    torch.set_num_threads(min(os.cpu_count() or 1, CPU_THREADS))
+
+    def run(layers):
+        cfg = transformers.T5Config(vocab_size=512, d_model=4096, d_kv=64, d_ff=10240, num_layers=layers, num_heads=64,
+                                    feed_forward_proj="gated-gelu", dropout_rate=0.0)
+        m = transformers.T5EncoderModel(cfg).eval()
+        ids = torch.randint(0, 512, (caps, L), generator=torch.Generator().manual_seed(1))
+        with torch.no_grad():
+            m(input_ids=ids[:, :8])                                  # warm-up: thread pool, lazy initialisation
+            t0 = time.perf_counter()
+            m(input_ids=ids, attention_mask=torch.ones_like(ids))
+            return time.perf_counter() - t0
+
+    t1, t3 = run(1), run(3)
+    per_block = max((t3 - t1) / 2.0, 1e-9)
+    fixed = max(t1 - per_block, 0.0)
+    return caps / (fixed + 24 * per_block), t1 + t3
+
+
+def cpu_reference_vae_sample():
+    """`--workload vae`: diffusers is not installed, so the CPU arm is the oracle's restatement of the SDXL-VAE decoder
+    (oracle/vae_oracle.py, fp32, CPU_THREADS threads) on a 32 x 32 latent -> 256 x 256 image: 1 / 16 of the pixels of the benchmarked
+    1024 x 1024 decode (every layer is per-pixel work except the mid-block attention, 6 % of the FLOPs at 1024 px, which grows with the
+    square); images/s = 1 / (16 x t).  Returns (images/s, seconds measured)."""
+    from oracle import vae_oracle as vo             # bench.py may use the oracle ONLY in the CPU arms / parity check
+    from pixart_sigma_b200.vae import AutoencoderKL
+    torch.set_num_threads(min(os.cpu_count() or 1, CPU_THREADS))
+    torch.manual_seed(0)
+    sd = {k: v.float() for k, v in AutoencoderKL().state_dict().items() if k.startswith(("decoder.", "post_quant_conv."))}
+    z = torch.randn(1, 4, 32, 32)
+    with torch.no_grad():
+        vo.decode(sd, z[:, :, :8, :8])                                # warm-up
+        t0 = time.perf_counter()
+        vo.decode(sd, z)
+        dt = time.perf_counter() - t0
+    return 1.0 / (16.0 * dt), dt
+
+
 def run_reference_arm(args, wl):
     """`--impl reference`: the reference's own CPU path (its oracle port: the reference is pure Python and cannot travel),
     same workload string / metric / unit as our arm; every step is one REAL forward of one image (forward batch 2)."""
@@ -711,7 +755,13 @@ def measure_vae(args, ctx: Ctx):
                              "step_share": conv_ms / ms_roof, "traffic": None,
                              "groupnorm_silu": {"bound": "hbm", "achieved_gbs": gn_bytes * 2 / (gn_ms / 1000.0) / 1e9 if gn_ms > 0 else None,
                                                 "peak_gbs": hbm, "step_share": gn_ms / ms_roof},
-                             "whole_step_tflops": flops / (ms / args.steps / 1000.0) / 1e12}}
+                             "whole_step_tflops": flops / (ms / args.steps / 1000.0) / 1e12},
+                "cpu_baseline": None}
+        if world == 1 and not args.no_cpu_baseline:
+            v, dt = cpu_reference_vae_sample()
+            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": min(os.cpu_count() or 1, CPU_THREADS), "kind": "port",
+                                    "sample": f"oracle restatement of the SDXL-VAE decoder (diffusers is not installed), fp32 torch CPU, one 32 x 32 "
+                                              f"latent -> 256 x 256 image in {dt:.1f} s, scaled by 16 to the 1024 x 1024 decode of `e2e`"}
     return line
 
 
@@ -795,6 +845,11 @@ def measure_t5(args, ctx: Ctx):
                                            "achieved": attn_flops * 2 / (attn_ms / 1000.0) / 1e12 if attn_ms > 0 else None},
                              "whole_step_tflops": (gemm_flops + attn_flops) / (ms / args.steps / 1000.0) / 1e12},
                 "cpu_baseline": None}
+        if world == 1 and not args.no_cpu_baseline:
+            v, dt = cpu_reference_t5_sample(caps, L)
+            line["cpu_baseline"] = {"value": v, "unit": "captions/s", "cores": min(os.cpu_count() or 1, CPU_THREADS), "kind": "reference",
+                                    "sample": f"transformers T5EncoderModel (the reference's dependency), fp32 torch CPU, XXL width, {caps} captions x "
+                                              f"{L} tokens through a 1-block and a 3-block model ({dt:.1f} s measured), extrapolated to 24 blocks"}
     del model
     torch.cuda.empty_cache()
     return line
