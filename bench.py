@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- denoise-steps/sec of the PixArt-Sigma-XL/2 denoiser hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4|c5] [--impl ours|reference] [--no-extras]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4|c5|vae|t5] [--impl ours|reference] [--no-extras]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -22,6 +22,12 @@ evaluated on the host.
 The same invocation also puts BASELINE configs[4] (training step: IDDPM loss fwd + bwd + DDP gradient all-reduce, key
 `train`) and configs[3] (2K, KV-compress sr=2, key `c4`) under the same clock at the same N (skip with --no-extras), so that
 the scaling harness sees the NCCL gradient all-reduce too.
+
+`--workload vae` / `--workload t5` time the callers either side of the denoiser: the SDXL-VAE decode of one
+1024 x 1024 image (`value` = the ResBlock / upsample convolution stack, `e2e` = the whole `AutoencoderKL.decode` from a pinned-host
+latent to the image read back) and one T5-v1.1-XXL forward over 4 captions x 300 tokens, each with its kernel roofline and a bounded
+CPU sample of the reference's own path (diffusers is absent: the oracle decoder; transformers' T5EncoderModel).  `c5 --no-fp32-attention`
+leaves the `fp32_attention` flag of the reference's 1024px config off (it selects the hi + lo P form of the attention forward).
 
 One JSON line is printed by rank 0.
 """
