@@ -230,3 +230,20 @@ class T5EncoderModel(nn.Module):
         out = torch.empty(M, D, dtype=bf, device=self.device)
         lib.rmsnorm(x32, fin.weight, out, eps=fin.variance_epsilon)
         return EncoderOutput(last_hidden_state=out.view(B, L, D))
+
+
+def replace_t5_model(embedder, config: Optional[dict] = None):
+    """Swap the transformers model inside the reference's `T5Embedder` (diffusion/model/t5.py:12-88: `self.model`, `self.device`,
+    `self.torch_dtype`) for this one: same weights (`state_dict` keys are identical), cast to bf16, on the embedder's device.
+    `embedder.get_text_embeddings(texts)` (t5.py:90-111) then runs unchanged.  Returns the new model."""
+    old = embedder.model
+    cfg = dict(config or {})
+    hf_cfg = getattr(old, "config", None)
+    if hf_cfg is not None and not cfg:                      # take the geometry from the loaded checkpoint
+        cfg = {k: getattr(hf_cfg, k) for k in T5_V1_1_XXL if hasattr(hf_cfg, k)}
+    new = T5EncoderModel(cfg)
+    missing, unexpected = new.load_state_dict(old.state_dict(), strict=False)
+    if unexpected or [k for k in missing if k != "encoder.embed_tokens.weight"]:
+        raise RuntimeError(f"T5 checkpoint layout mismatch: missing {missing}, unexpected {unexpected}")
+    embedder.model = new.to(torch.bfloat16).to(embedder.device).eval()
+    return embedder.model

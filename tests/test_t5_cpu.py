@@ -115,6 +115,29 @@ def test_relative_bias_vector_is_the_toeplitz_form_of_the_position_bias():
         assert torch.equal(pb, rel[:, pos[None, :] - pos[:, None] + L - 1])
 
 
+def test_replace_t5_model_swaps_the_model_inside_the_reference_embedder(monkeypatch):
+    """diffusion/model/t5.py:12-111: the embedder keeps `.model`, `.device`; after the swap `get_text_embeddings`' call
+    `self.model(input_ids=..., attention_mask=...)['last_hidden_state']` runs on this module with the checkpoint's weights."""
+    _standins(monkeypatch)
+    hf = hf_model(SMALL)
+
+    class Embedder:                                   # the attributes of the reference's T5Embedder that matter here
+        device = torch.device("cpu")
+        torch_dtype = torch.bfloat16
+        model = hf
+
+    emb = Embedder()
+    new = t5.replace_t5_model(emb)
+    assert emb.model is new and isinstance(new, t5.T5EncoderModel) and new.dtype == torch.bfloat16
+    assert new.cfg["d_model"] == SMALL["d_model"] and new.cfg["num_layers"] == SMALL["num_layers"]
+    ids = torch.randint(0, SMALL["vocab_size"], (2, 16), generator=torch.Generator().manual_seed(9))
+    mask = torch.ones_like(ids)
+    got = emb.model(input_ids=ids, attention_mask=mask)["last_hidden_state"]
+    with torch.no_grad():
+        want = hf(input_ids=ids, attention_mask=mask)["last_hidden_state"]
+    assert po.rel_err(got.float(), want) < 2e-2        # bf16-rounded weights here vs the fp32 checkpoint there
+
+
 def test_product_refuses_to_run_without_the_kernels():
     m = t5.T5EncoderModel(SMALL)
     with pytest.raises(RuntimeError, match="sm_100a kernels only"):
