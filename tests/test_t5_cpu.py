@@ -142,3 +142,22 @@ def test_product_refuses_to_run_without_the_kernels():
     m = t5.T5EncoderModel(SMALL)
     with pytest.raises(RuntimeError, match="sm_100a kernels only"):
         m(torch.zeros(1, 8, dtype=torch.long))
+
+
+# ------------------------------------------------------------------------------------------------- committed golden vectors
+@pytest.mark.parametrize("name", ["t5_small_ragged", "t5_wide_300"])
+def test_forward_glue_matches_the_committed_transformers_fixture(monkeypatch, name):
+    """tests/golden/t5_*.pt: outputs of transformers' T5EncoderModel (fp32) on seed-defined weights, written by
+    oracle/gen_golden_t5.py in the build container -- the pin does not depend on the transformers version of the box that runs this."""
+    import os
+    from oracle.gen_golden_t5 import synthetic_t5_state_dict
+    fix = torch.load(os.path.join(os.path.dirname(__file__), "golden", name + ".pt"))
+    _standins(monkeypatch)
+    m = t5.T5EncoderModel(fix["cfg"])
+    m.load_state_dict(synthetic_t5_state_dict(fix["cfg"], fix["seed"]))
+    m = m.to(torch.bfloat16)                                  # the synthetic weights are bf16-valued: nothing is lost
+    if fix["position_bias_h0"] is not None:
+        L = fix["input_ids"].shape[1]
+        assert torch.allclose(m.position_bias(L)[0], fix["position_bias_h0"], atol=1e-6)
+    got = m(input_ids=fix["input_ids"], attention_mask=fix["attention_mask"])["last_hidden_state"]
+    assert po.rel_err(got.float(), fix["last_hidden_state"].float()) < 1e-2
