@@ -7,9 +7,12 @@ Only what the path `PixArtMS.forward -> 28 x PixArtMSBlock.forward` needs:
   sampler.py DPM-Solver++ loop around the path (mirror of the reference's `diffusion.DPMS`), fused step kernel + CUDA graph
   autograd.py / training.py  training path: the block's ops as autograd Functions over forward + backward kernels, IDDPM loss
   parallel.py  batch-sharded inference replicas; bucketed gradient all-reduce for data-parallel training
+  vae.py / t5.py  the callers either side of the path on the same kernels: SDXL-VAE (diffusers' AutoencoderKL layout) and the
+             T5-v1.1-XXL caption encoder (transformers' T5EncoderModel layout)
   build.py   in-tree nvcc build
 """
-from .model import (MODELS, PixArtMS, PixArtMS_XL_2, PixArtMSBlock, build_model, install_into_reference)  # noqa: F401
+from .model import (MODELS, PixArtMS, PixArtMS_XL_2, PixArtMSBlock, build_model, install_into_reference,  # noqa: F401
+                    set_grad_checkpoint)
 from .sampler import DPMS, DPMSolverPP  # noqa: F401
 
 __version__ = "0.1.0"

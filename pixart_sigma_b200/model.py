@@ -50,15 +50,24 @@ class _Registry:
 MODELS = _Registry("models")
 
 
+def set_grad_checkpoint(model, use_fp32_attention=False, gc_step=1):
+    """diffusion/model/utils.py:28-35: mark EVERY submodule -- `grad_checkpointing` makes the blocks recompute their activations in
+    the backward (autograd.py), `fp32_attention` selects the hi + lo P form of the self-attention forward (PixArt_blocks.py:145-147;
+    DESIGN.md 4.2b), `grad_checkpointing_step` is stored for the callers that read it."""
+    assert isinstance(model, nn.Module)
+
+    def mark(m):
+        m.grad_checkpointing, m.fp32_attention, m.grad_checkpointing_step = True, use_fp32_attention, gc_step
+    model.apply(mark)
+
+
 def build_model(cfg, use_grad_checkpoint=False, use_fp32_attention=False, gc_step=1, **kwargs):
     """Same call surface as diffusion/model/builder.py:8-14."""
     if isinstance(cfg, str):
         cfg = dict(type=cfg)
     model = MODELS.build(cfg, default_args=kwargs)
     if use_grad_checkpoint:
-        def mark(m):  # diffusion/model/utils.py:28-35
-            m.grad_checkpointing, m.fp32_attention, m.grad_checkpointing_step = True, use_fp32_attention, gc_step
-        model.apply(mark)
+        set_grad_checkpoint(model, use_fp32_attention=use_fp32_attention, gc_step=gc_step)
     return model
 
 
