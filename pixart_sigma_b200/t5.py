@@ -161,6 +161,12 @@ class T5EncoderModel(nn.Module):
             self._qkv_w[li] = hit
         return hit[1]
 
+    def clear_caches(self) -> None:
+        """Drop the derived copies (row-stacked q | k | v weights) and the activation workspace.  The stacked weights are keyed on the
+        parameters' version counters and storage, which in-place writes through `.data` bypass: call this after such an update."""
+        self._qkv_w.clear()
+        self._ws.clear()
+
     def position_bias(self, L: int) -> torch.Tensor:
         """(H, L, L) fp32: relative_attention_bias[bucket(j - i), h] -- layer 0 owns the table, every layer uses it."""
         cfg = self.cfg
@@ -181,6 +187,9 @@ class T5EncoderModel(nn.Module):
     @torch.no_grad()
     def forward(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None, **kwargs) -> EncoderOutput:
         _need_kernels(self.encoder.block[0].layer[0].SelfAttention.q.weight)
+        unsupported = [k for k, v in kwargs.items() if k != "return_dict" and not (v is None or v is False)]
+        if unsupported:         # transformers' other inputs / outputs (inputs_embeds, output_attentions, ...): the reference passes none
+            raise NotImplementedError(f"T5EncoderModel.forward: unsupported arguments {unsupported}")
         cfg = self.cfg
         B, L = input_ids.shape
         D, H, dk, F_ = cfg["d_model"], cfg["num_heads"], cfg["d_kv"], cfg["d_ff"]

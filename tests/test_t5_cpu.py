@@ -138,6 +138,26 @@ def test_replace_t5_model_swaps_the_model_inside_the_reference_embedder(monkeypa
     assert po.rel_err(got.float(), want) < 2e-2        # bf16-rounded weights here vs the fp32 checkpoint there
 
 
+def test_unsupported_arguments_raise_and_caches_follow_weight_updates(monkeypatch):
+    _standins(monkeypatch)
+    m = t5.T5EncoderModel(SMALL).to(torch.bfloat16)
+    ids = torch.randint(0, SMALL["vocab_size"], (1, 8), generator=torch.Generator().manual_seed(2))
+    with pytest.raises(NotImplementedError):
+        m(ids, None, output_attentions=True)
+    with pytest.raises(NotImplementedError):
+        m(ids, None, inputs_embeds=torch.zeros(1, 8, SMALL["d_model"]))
+    a = m(ids, None, return_dict=True).last_hidden_state.clone()
+    sa = m.encoder.block[0].layer[0].SelfAttention
+    with torch.no_grad():
+        sa.q.weight.mul_(0.5)                         # an in-place update bumps the version: the stacked copy is rebuilt
+    b = m(ids, None).last_hidden_state.clone()
+    assert not torch.equal(a, b)
+    sa.q.weight.data.mul_(2.0)                        # a `.data` write does not: the documented contract is clear_caches()
+    m.clear_caches()
+    c = m(ids, None).last_hidden_state
+    assert torch.equal(a, c)
+
+
 def test_product_refuses_to_run_without_the_kernels():
     m = t5.T5EncoderModel(SMALL)
     with pytest.raises(RuntimeError, match="sm_100a kernels only"):
