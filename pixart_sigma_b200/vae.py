@@ -296,7 +296,10 @@ class DiagonalGaussian:
         self.std = torch.exp(0.5 * self.logvar)
 
     def sample(self, generator=None) -> torch.Tensor:
-        return self.mean + self.std * torch.randn(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype)
+        dev = self.mean.device                              # a CPU generator with CUDA moments: draw where the generator lives (diffusers' randn_tensor)
+        gdev = generator.device if generator is not None else dev
+        noise = torch.randn(self.mean.shape, generator=generator, device=gdev, dtype=self.mean.dtype).to(dev)
+        return self.mean + self.std * noise
 
     def mode(self) -> torch.Tensor:
         return self.mean
