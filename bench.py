@@ -300,6 +300,34 @@ def run_reference_arm(args, wl):
 
 
 # --------------------------------------------------------------------------------------------- our arm: inference
+def run_reference_arm_callers(args):
+    """`--impl reference --workload t5|vae`: the CPU path of the callers.  t5: transformers' T5EncoderModel itself (the reference's
+    dependency, `kind: reference`), bounded to a 1-block + 3-block sample of XXL width per step and extrapolated to 24 blocks; vae:
+    diffusers is not installed, so the oracle's decoder (`kind: port`) on a 256 x 256 image scaled to 1024 x 1024.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    vals, secs = [], []
+    for _ in range(steps):
+        v, dt = cpu_reference_t5_sample(4, 300) if args.workload == "t5" else cpu_reference_vae_sample()
+        vals.append(v)
+        secs.append(dt)
+    v = statistics.median(vals)
+    t5 = args.workload == "t5"
+    unit = "captions/s" if t5 else "images/s"
+    wl = ("t5: T5-v1.1-XXL encoder forward (24 layers, d_model 4096, 64 heads, d_ff 10240), 4 captions x 300 tokens per GPU, random-init weights"
+          if t5 else "vae: SDXL-VAE decode of one 1024x1024 image per GPU (whole AutoencoderKL.decode), random weights")
+    cpu = {"value": v, "unit": unit, "cores": min(os.cpu_count() or 1, CPU_THREADS), "kind": "reference" if t5 else "port",
+           "sample": ("transformers T5EncoderModel, fp32 torch CPU, XXL width, 1-block + 3-block models on 4 x 300 tokens, extrapolated to 24 blocks"
+                      if t5 else "oracle restatement of the SDXL-VAE decoder, fp32 torch CPU, 32 x 32 latent -> 256 x 256 image, scaled by 16")
+                     + f" ({statistics.median(secs):.1f} s measured per step)"}
+    _emit({"impl": "reference", "metric": "t5-xxl captions/sec" if t5 else "vae-decoder images/sec", "value": v, "unit": unit,
+           "n_gpus": args.gpus, "steps": steps, "warmup": 0, "steps_requested": args.steps, "ms_per_step": (4.0 if t5 else 1.0) / v * 1000.0,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": wl}, "cpu_baseline": cpu,
+           "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
 class KernelTimer:
     """CUDA-event timing of every GEMM / attention launch on the launching stream (the separate roofline pass)."""
 
@@ -904,8 +932,7 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         if args.workload in ("vae", "t5"):
-            _emit({"impl": "reference", "unavailable": "the VAE (diffusers AutoencoderKL) and the T5 encoder (transformers) are third-party "
-                                                        "dependencies of the reference, not part of its tree"})
+            run_reference_arm_callers(args)
             return
         run_reference_arm(args, WORKLOADS[args.workload])
         return
