@@ -11,8 +11,8 @@ Only what the path `PixArtMS.forward -> 28 x PixArtMSBlock.forward` needs:
              T5-v1.1-XXL caption encoder (transformers' T5EncoderModel layout)
   build.py   in-tree nvcc build
 """
-from .model import (MODELS, PixArtMS, PixArtMS_XL_2, PixArtMSBlock, build_model, install_into_reference,  # noqa: F401
-                    set_grad_checkpoint)
+from .model import (MODELS, PixArt, PixArt_XL_2, PixArtBlock, PixArtMS, PixArtMS_XL_2, PixArtMSBlock,  # noqa: F401
+                    build_model, install_into_reference, set_grad_checkpoint)
 from .sampler import DPMS, DPMSolverPP  # noqa: F401
 
 __version__ = "0.1.0"

@@ -826,6 +826,55 @@ def PixArtMS_XL_2(**kwargs):
     return PixArtMS(depth=28, hidden_size=1152, patch_size=2, num_heads=16, **kwargs)
 
 
+class PixArtBlock(PixArtMSBlock):
+    """`PixArtBlock` of the single-scale model (nets/PixArt.py:26-57): the same adaLN-single block; `forward(x, y, t, mask)` has no HW
+    argument -- the token grid is the square root of N (PixArt_blocks.py:126-127)."""
+
+    def forward(self, x, y, t, mask=None, **kwargs):
+        return super().forward(x, y, t, mask, None)
+
+
+@MODELS.register_module()
+class PixArt(PixArtMS):
+    """Single-scale PixArt (nets/PixArt.py:62-258; registry names `PixArt`, `PixArt_XL_2`: the 256px Sigma config
+    `PixArt_sigma_xl2_img256_internal.py:12`): the multi-scale model without micro-conditioning, at the fixed resolution `input_size`.
+    Same state-dict keys (the frozen `pos_embed` buffer is recomputed per geometry here too; for the model's own resolution that is the
+    table `initialize_weights` stores, PixArt.py:224-229), same kernels; the three forward signatures are the single-scale ones."""
+
+    def __init__(self, input_size=32, patch_size=2, in_channels=4, hidden_size=1152, depth=28, num_heads=16, mlp_ratio=4.0,
+                 class_dropout_prob=0.1, pred_sigma=True, drop_path: float = 0.0, caption_channels=4096, pe_interpolation=1.0,
+                 config=None, model_max_length=120, qk_norm=False, kv_compress_config=None, **kwargs):
+        super().__init__(input_size=input_size, patch_size=patch_size, in_channels=in_channels, hidden_size=hidden_size, depth=depth,
+                         num_heads=num_heads, mlp_ratio=mlp_ratio, class_dropout_prob=class_dropout_prob, pred_sigma=pred_sigma,
+                         drop_path=drop_path, caption_channels=caption_channels, pe_interpolation=pe_interpolation, config=config,
+                         model_max_length=model_max_length, micro_condition=False, qk_norm=qk_norm,
+                         kv_compress_config=kv_compress_config, **kwargs)
+        self.input_size = input_size
+        for blk in self.blocks:                      # same parameters and kernels, the single-scale call signature
+            blk.__class__ = PixArtBlock
+
+    def forward(self, x, timestep, y, mask=None, data_info=None, **kwargs):
+        """PixArt.py:143-172: x must have the model's own resolution (the reference adds its fixed `pos_embed` table)."""
+        if x.shape[-2] != self.input_size or x.shape[-1] != self.input_size:
+            raise ValueError(f"PixArt is single-scale: expected {self.input_size} x {self.input_size} latents, got "
+                             f"{tuple(x.shape[-2:])} (use PixArtMS for other sizes)")
+        return super().forward(x, timestep, y, mask=mask, data_info=None)
+
+    def forward_with_dpmsolver(self, x, timestep, y, mask=None, **kwargs):
+        """PixArt.py:174-180."""
+        return self.forward(x, timestep, y, mask).chunk(2, dim=1)[0]
+
+    def forward_with_cfg(self, x, timestep, y, cfg_scale, mask=None, **kwargs):
+        """PixArt.py:182-196 (first three channels mixed, as there)."""
+        return super().forward_with_cfg(x, timestep, y, cfg_scale, None, mask=mask)
+
+
+@MODELS.register_module()
+def PixArt_XL_2(**kwargs):
+    """PixArt-XL/2, single scale (PixArt.py:313-315)."""
+    return PixArt(depth=28, hidden_size=1152, patch_size=2, num_heads=16, **kwargs)
+
+
 def install_into_reference() -> bool:
     """Re-point the reference's registry and module names at these classes, so an unmodified
     `scripts/inference.py` / `train_scripts/train.py` builds the B200 model. Returns False when the
@@ -835,13 +884,14 @@ def install_into_reference() -> bool:
         import diffusion.model.nets as nets
     except Exception:
         return False
-    for name, obj in (("PixArtMS", PixArtMS), ("PixArtMS_XL_2", PixArtMS_XL_2)):
+    for name, obj in (("PixArtMS", PixArtMS), ("PixArtMS_XL_2", PixArtMS_XL_2), ("PixArt", PixArt), ("PixArt_XL_2", PixArt_XL_2)):
         reg = builder.MODELS
         table = getattr(reg, "_module_dict", None) or getattr(reg, "module_dict", None) or getattr(reg, "_m", None)
         if table is not None:
             table[name] = obj
         setattr(nets, name, obj)
     nets.PixArtMSBlock = PixArtMSBlock
+    nets.PixArtBlock = PixArtBlock
     try:                                                   # the sampler the inference script imports from `diffusion`
         import diffusion
         from .sampler import DPMS

@@ -180,3 +180,32 @@ def test_hi_lo_split_of_p_carries_sixteen_mantissa_bits():
     err1 = ((hi.double() - p.double()).abs() / p.double()).max().item()
     err2 = ((hi.double() + lo.double() - p.double()).abs() / p.double()).max().item()
     assert 2.0 ** -9 < err1 <= 2.0 ** -8 and err2 <= 2.0 ** -17
+
+
+@pytest.mark.skipif(not refshim.reference_available(), reason="/root/reference not present")
+def test_single_scale_pixart_surface_equals_live_reference():
+    """nets/PixArt.py: `PixArt` / `PixArt_XL_2` / `PixArtBlock` (the 256px Sigma config builds `PixArt_XL_2`,
+    configs/pixart_sigma_config/PixArt_sigma_xl2_img256_internal.py:12): same state-dict keys and shapes as the unmodified reference
+    class, registry names, the single-scale forward signatures."""
+    import inspect
+    from pixart_sigma_b200 import PixArt, PixArt_XL_2, PixArtBlock
+    refshim.install_reference_shims()
+    from diffusion.model.nets.PixArt import PixArt as RefPixArt
+    kv = dict(sampling="conv", scale_factor=2, kv_compress_layer=[1])
+    ref = RefPixArt(input_size=16, depth=2, model_max_length=300, qk_norm=True, kv_compress_config=kv)
+    ours = PixArt(input_size=16, depth=2, model_max_length=300, qk_norm=True, kv_compress_config=kv)
+    rs, os_ = ref.state_dict(), ours.state_dict()
+    assert set(rs) == set(os_) and all(rs[k].shape == os_[k].shape for k in rs)
+    missing, unexpected = ours.load_state_dict(rs, strict=True), None
+    assert set(MODELS.module_dict) >= {"PixArt", "PixArt_XL_2"}
+    assert isinstance(build_model("PixArt", depth=1, input_size=8), PixArt) and callable(PixArt_XL_2)
+    assert all(type(b) is PixArtBlock for b in ours.blocks) and not ours.micro_conditioning and ours.out_channels == 8
+    for name in ("forward", "forward_with_dpmsolver", "forward_with_cfg"):
+        ours_p = list(inspect.signature(getattr(PixArt, name)).parameters)
+        ref_p = list(inspect.signature(getattr(RefPixArt, name)).parameters)
+        assert ours_p == ref_p, (name, ours_p, ref_p)
+    assert list(inspect.signature(PixArtBlock.forward).parameters)[:5] == ["self", "x", "y", "t", "mask"]
+    with pytest.raises(ValueError, match="single-scale"):
+        ours(torch.zeros(1, 4, 32, 32), torch.zeros(1), torch.zeros(1, 1, 300, 4096))
+    with pytest.raises(RuntimeError):                      # right size: reaches the kernel path, which refuses CPU tensors
+        ours(torch.zeros(1, 4, 16, 16), torch.zeros(1), torch.zeros(1, 1, 300, 4096))
