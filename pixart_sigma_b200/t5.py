@@ -8,7 +8,7 @@ checkpoint's state-dict keys (`shared.weight`, `encoder.block.i.layer.0.SelfAtte
 `encoder.block.i.layer.1.DenseReluDense.{wi_0,wi_1,wo}.weight`, `encoder.final_layer_norm.weight`) and runs
 
   * the seven Linear layers of a block -- 99 % of the FLOPs (2 x 4.7 G per token) -- on `pxa_gemm_bf16` (tcgen05): q / k / v, the
-    attention output projection accumulated IN PLACE into the fp32 residual stream (TMA reduce-add epilogue), wi_0 with the
+    attention output projection accumulated IN PLACE into the fp32 residual stream (fp32 residual epilogue), wi_0 with the
     GELU(tanh) epilogue (`gelu_new`), wi_1, and wo again in place into the stream;
   * both T5LayerNorms (RMS norm, no mean, no bias) on `pxa_rmsnorm_bf16`, reading the fp32 stream;
   * the attention core on `pxa_t5_attn_d64_bf16` (tcgen05; T5 adds a learned [heads, 300, 300] relative-position bias and the key
